@@ -1,0 +1,218 @@
+/*
+ * ivf.h — C ABI of libivf.so: the B200 (sm_100a) kernels behind the
+ * temporal-mask search and Grad-CAM hot path of interpreting-video-features.
+ *
+ * The reference is 100 % Python on PyTorch (no native code, no FFI), so there
+ * is no existing binding to replace: each entry point below names the
+ * reference call site (file:line under video_features_pytorch/, "pt/") whose
+ * implicit ATen/cuDNN kernels it stands in for.  The reference-side binding a
+ * maintainer would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless noted.
+ *  - the caller owns all buffers; the library keeps only per-handle caches of
+ *    TMA tensor maps (freed by ivf_destroy).
+ *  - every launch goes to the caller's cudaStream_t (passed as void*), nothing
+ *    synchronises, so a sequence of calls can be captured into a CUDA graph.
+ *  - return 0 on success, an IVF_E* code otherwise; ivf_last_error() gives the
+ *    message (thread local).  There is NO CPU fallback: an unsupported
+ *    shape or a missing GPU is an error.
+ *  - activations are channels-last (N,D,H,W,C) with an explicit per-pixel
+ *    channel stride `ld` and channel offset `coff`, so a branch of an
+ *    Inception block writes straight into its slice of the concat buffer
+ *    (pt/models/I3D_doubled.py:146 torch.cat is never materialised).
+ */
+#ifndef IVF_H_
+#define IVF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ivf_handle ivf_handle;
+
+enum {
+  IVF_OK = 0,
+  IVF_EINVAL = 1,       /* bad argument / inconsistent descriptor            */
+  IVF_EUNSUPPORTED = 2, /* valid request this build has no kernel for        */
+  IVF_ECUDA = 3,        /* CUDA runtime / driver error                       */
+  IVF_ENOGPU = 4        /* no sm_100 device                                  */
+};
+
+enum { IVF_F32 = 0, IVF_BF16 = 1 };
+
+/* epilogue flags shared by conv / pool-backward / head-backward */
+enum {
+  IVF_EP_AFFINE = 1,  /* v = v*scale[c] + shift[c]   (eval BatchNorm fold, pt/models/I3D_doubled.py:111) */
+  IVF_EP_RELU = 2,    /* v = max(v,0)                (pt/models/I3D_doubled.py:113)                      */
+  IVF_EP_ACCUM = 4,   /* v += acc_in[...]  (fp32)    (sum over the consumers of a tensor in backward)    */
+  IVF_EP_MASK = 8,    /* v = mask_y[...]>0 ? v*mask_scale[c] : 0  (ReLU'+BN' of the producing Unit3D)     */
+  IVF_EP_OUT_F32 = 16 /* store fp32 instead of the activation dtype                                       */
+};
+
+/* ---- lifetime ------------------------------------------------------------ */
+int ivf_create(int device, ivf_handle** out);
+int ivf_destroy(ivf_handle* h);
+const char* ivf_last_error(void);
+const char* ivf_version(void);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t ivf_launch_count(const ivf_handle* h);
+
+/* ---- convolution (pt/models/I3D_doubled.py:83-118 Unit3D.forward and its autograd;
+ *      pt/models/convolution_lstm.py:25-32 gate convolutions) ------------------------
+ * One generalised gather-GEMM:  out[n,o,c'] = epilogue( sum_{tap,c} in[n, g(o,tap), c] * W[tap,c,c'] )
+ *   transposed == 0:  g = o*stride - pad + tap          (forward; also the data-gradient of a
+ *                                                        stride-1 conv with flipped weights)
+ *   transposed == 1:  g = (o + pad - tap)/stride, taps with a remainder skipped
+ *                                                       (data-gradient of a strided conv; fp32 kernel only)
+ * Out-of-range gathers read 0 ('same' zero padding, pt/models/I3D_doubled.py:96-106 F.pad).
+ *
+ * dtype IVF_BF16: tcgen05/TMEM implicit GEMM, TMA-im2col fed, fp32 accumulate; requires
+ *   transposed == 0 and stride 1 (strided layers are presented space-to-depth by the host side),
+ *   cin/ld/coff multiples of 8.  Weights: bf16 [cout_pad][taps][cin_pad] (K-major) with
+ *   cin_pad = ivf_conv_bf16_cin_pad(cin), cout_pad = ivf_conv_bf16_cout_pad(cout).
+ * dtype IVF_F32: CUDA-core implicit GEMM (the 1e-4 "fp32 mode"); weights fp32 [taps][cin][cout].
+ */
+typedef struct ivf_conv_desc {
+  int32_t n, id, ih, iw; /* gathered tensor: batch and spatial extent            */
+  int32_t od, oh, ow;    /* produced tensor spatial extent                       */
+  int32_t cin, cout;     /* channels reduced per tap, channels produced          */
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t pd, ph, pw;    /* front padding                                        */
+  int32_t transposed;
+  int32_t in_ld, in_coff;
+  int32_t out_ld, out_coff;
+  int32_t mask_ld, mask_coff;
+  int32_t flags;         /* IVF_EP_*                                             */
+  int32_t dtype;         /* IVF_F32 | IVF_BF16                                   */
+} ivf_conv_desc;
+
+int ivf_conv_bf16_kchunk(int cin);   /* channels per K stage: 16, 32 or 64 */
+int ivf_conv_bf16_cin_pad(int cin);  /* cin rounded up to the K stage      */
+int ivf_conv_bf16_ntile(int cout);   /* UMMA N of one CTA tile             */
+int ivf_conv_bf16_cout_pad(int cout);
+
+int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+               const float* scale, const float* shift, const float* acc_in, const void* mask_y,
+               const float* mask_scale, void* out, void* stream);
+
+/* ---- max-pool with TF-'same' ZERO padding (pt/models/I3D_doubled.py:8-40;
+ *      nn.MaxPool2d of pt/models/convolution_lstm.py:79 with pad 0) ------------------
+ * argmax: uint8 [n*od*oh*ow][c] window-scan index of the first maximum (ATen tie rule),
+ * padded positions take part with value 0 exactly as F.pad + MaxPool3d does.           */
+typedef struct ivf_pool_desc {
+  int32_t n, id, ih, iw, c;
+  int32_t od, oh, ow;
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t pd, ph, pw;
+  int32_t in_ld, in_coff;
+  int32_t out_ld, out_coff;
+  int32_t mask_ld, mask_coff; /* backward epilogue: mask tensor indexed like the pool INPUT */
+  int32_t flags;              /* backward: IVF_EP_ACCUM | IVF_EP_MASK | IVF_EP_OUT_F32       */
+  int32_t dtype;
+} ivf_pool_desc;
+
+int ivf_maxpool3d_fwd(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
+                      uint8_t* argmax, void* stream);
+/* dx (at in_ld/in_coff) = epilogue( sum of dy over the windows whose argmax is this element ) */
+int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* argmax,
+                      const float* acc_in, const void* mask_y, const float* mask_scale, void* dx,
+                      void* stream);
+
+/* ---- I3D head (pt/models/I3D_doubled.py:360-371: avg_pool -> dropout(eval) -> 1x1x1 logits
+ *      with bias -> squeeze -> softmax(dim=1)) ---------------------------------------
+ * feat: [n][p][c] channels-last (p = all pooled positions; the pool must cover the whole map).
+ * out: fp32 [n][ncls] probabilities (softmax != 0) or logits.  With p == 1 this is the
+ * Linear(+Softmax) classifier of the ConvLSTM model (pt/models/CLSTM_4.py:78-83).      */
+int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int n, int p, int c, int ld,
+                     const float* w, const float* b, int ncls, int softmax, float* logits,
+                     float* out, void* stream);
+/* dfeat[n][p][c] = epilogue( (1/p) * W^T * dlogits ), dlogits from dout through softmax'. */
+int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, int ld, const float* w,
+                     int ncls, int softmax, const float* out, const float* dout, int flags,
+                     const void* mask_y, int mask_ld, int mask_coff, const float* mask_scale,
+                     void* dfeat, void* stream);
+
+/* ---- temporal perturbation (pt/mask.py:4-56 perturb_sequence) ----------------------
+ * x: fp32 [b][c][t][h][w] (the loader's layout, pt/data_loader_jpg.py:27-37).
+ * mask: fp32, row `i*mask_bstride` for clip i (mask_bstride 0 = one mask for the batch,
+ *       the reference's semantics).  mode 0 = 'freeze' (first-order recurrence over t),
+ *       1 = 'reverse' (swap-blend inside each run of mask > 0.1, pt/mask.py:60-85).
+ * out_fmt: IVF_PFMT_NCDHW_F32  fp32 [b][c][t][h][w]          (drop-in perturb_sequence result)
+ *          IVF_PFMT_NDHWC_F32  fp32 [b][t][h][w][c]          (fp32 conv path)
+ *          IVF_PFMT_S2D_BF16   bf16 [b][t/2][h/2][w/2][32]   (space-to-depth operand of the
+ *              stride-2 7x7x7 stem, channel = ((dt*2+dh)*2+dw)*c + ch, 24..31 zero)
+ */
+enum { IVF_PFMT_NCDHW_F32 = 0, IVF_PFMT_NDHWC_F32 = 1, IVF_PFMT_S2D_BF16 = 2 };
+int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const float* mask, int mask_bstride,
+                    int b, int c, int t, int hh, int ww, int out_fmt, void* out, void* stream);
+/* dmask[b][t] (fp32, one row per clip) = d<gout, P>/dmask; gout is laid out like `out` above
+ * (fp32 for the two F32 formats; for IVF_PFMT_S2D_BF16 gout is bf16 or fp32 [b][t/2][h/2][w/2][32]
+ * selected by gout_dtype).                                                              */
+int ivf_perturb_bwd(ivf_handle* h, int mode, const float* x, const float* mask, int mask_bstride,
+                    int b, int c, int t, int hh, int ww, int out_fmt, int gout_dtype,
+                    const void* gout, float* dmask, void* stream);
+
+/* ---- mask objective + optimiser (pt/mask.py:88-100 calc_tv_norm;
+ *      pt/FindMasksComparison_I3D_smth.py:191-214: sigmoid, L1, TV(p=q=3), Adam lr) ----
+ * One launch per iteration for nclip independent masks:
+ *   s = sigmoid(m); g = (lam1*sign(s) + lam2*dTV(s) + dclass) * s(1-s); Adam(m, g).
+ * losses[nclip][3] = {lam1*L1, lam2*TV, sum}.  sig_out = sigmoid of the UPDATED m.
+ * Adam's step number is `step` (1-based), or, when step_dev != NULL, the per-clip device
+ * counter step_dev[clip]+1 which the kernel then stores back (CUDA-graph replay safe).
+ * A constant mask makes dTV NaN exactly as the reference's pow chain does (pt/mask.py:163-165). */
+int ivf_mask_loss_adam(ivf_handle* h, float* m, float* exp_avg, float* exp_avg_sq,
+                       const float* dclass, int nclip, int t, int step, int* step_dev, float lam1,
+                       float lam2,
+                       float lr, float beta1, float beta2, float eps, float* losses,
+                       float* sig_out, void* stream);
+int ivf_sigmoid(ivf_handle* h, const float* m, float* out, int count, void* stream);
+/* general-(p,q) TV norm used by the drop-in calc_tv_norm: val[0] and dval/dmask[t] */
+int ivf_tv_norm(ivf_handle* h, const float* mask, int t, float p, float q, float* val,
+                float* dmask, void* stream);
+
+/* ---- Grad-CAM tail (pt/grad_cam_videos.py:85-140) -----------------------------------
+ * act, grad: [n][tp][hp][wp][c] channels-last activations of the target layer and the
+ * gradient of the class score w.r.t. them.  cam: fp32 [n][tp*step][hout][wout]:
+ *   w_k = mean_{t,h,w} grad ; cam = relu(sum_k w_k act_k) ; bilinear (cv2 INTER_LINEAR,
+ *   half-pixel) to hout x wout ; repeated `step` times along t ; min/max normalised per
+ *   feature-time slice (per_frame != 0) or per clip.  One fused kernel.               */
+int ivf_gradcam(ivf_handle* h, int act_dtype, int grad_dtype, const void* act, const void* grad,
+                int n, int tp, int hp, int wp, int c, int ld, int step, int hout, int wout,
+                int per_frame, float* cam, float* cam_lowres, void* stream);
+
+/* ---- ConvLSTM (pt/models/convolution_lstm.py:38-60 cell, :96-132 stack) --------------
+ * pre: fp32 [m][4*hid] gate pre-activations = x-conv(+bias) + h-conv (summed by the conv
+ * epilogue, IVF_EP_ACCUM), gate order i,f,c,o along the channel axis; fused:
+ *   i=s(.) f=s(.) c'=f*c+i*tanh(.) o=s(.) h'=o*tanh(c')      (zero peepholes, :52-54)
+ * c_prev may be NULL (step 0, zero state).  gate_act (fp32 [m][4*hid]) keeps the activated
+ * gates for the backward pass.                                                          */
+int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, const float* c_prev, int m,
+                        int hid, float* c_next, void* h_next, float* gate_act, void* stream);
+/* BPTT step: dh = dL/dh' (fp32 [m][hid]); dc_io holds dL/dc' carried from step t+1 on entry
+ * and dL/dc for step t-1 on exit; dgates ([m][4*hid], activation dtype) = dL/dpre.      */
+int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_act, const float* c_prev,
+                        const float* c_next, const float* dh, float* dc_io, int m, int hid,
+                        void* dgates, void* stream);
+/* eval BatchNorm2d affine + MaxPool2d(2) (pt/models/convolution_lstm.py:120-124);
+ * x [n][hh][ww][c] -> y [n][hh/2][ww/2][c]; backward returns fp32 dx (+ acc_in if given) */
+int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n, int hh, int ww, int c,
+                      const float* scale, const float* shift, void* y, uint8_t* argmax, void* stream);
+int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* argmax, int n, int hh,
+                      int ww, int c, const float* scale, const float* acc_in, float* dx, void* stream);
+
+/* ---- bring-up probes (tests only) ---------------------------------------------------
+ * Loads one 128-pixel x kchunk im2col TMA tile exactly as the conv kernel does and
+ * copies the shared-memory image (de-swizzled, [128][kchunk] bf16) to `tile_out`.      */
+int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0, int tap,
+                     int c0, void* tile_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVF_H_ */

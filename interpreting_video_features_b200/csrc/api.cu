@@ -1,0 +1,67 @@
+// libivf.so — handle lifetime, error reporting and the dtype dispatch of ivf_conv3d.
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void ivf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* ivf_last_error(void) { return g_err; }
+extern "C" const char* ivf_version(void) { return "ivf-b200 0.1 (sm_100a)"; }
+
+extern "C" int ivf_create(int device, ivf_handle** out) {
+  if (!out) IVF_FAIL(IVF_EINVAL, "ivf_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    IVF_FAIL(IVF_ENOGPU, "ivf_create: no CUDA device (%s); libivf has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    IVF_FAIL(IVF_EINVAL, "ivf_create: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  IVF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    IVF_FAIL(IVF_ENOGPU, "ivf_create: device %d is sm_%d%d; libivf is built for sm_100a only",
+             device, prop.major, prop.minor);
+  ivf_handle* h = new ivf_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  *out = h;
+  return IVF_OK;
+}
+
+extern "C" int ivf_destroy(ivf_handle* h) {
+  delete h;
+  return IVF_OK;
+}
+
+extern "C" int64_t ivf_launch_count(const ivf_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+                          const float* scale, const float* shift, const float* acc_in,
+                          const void* mask_y, const float* mask_scale, void* out, void* stream) {
+  IVF_REQUIRE(h && d && in && w && out, "ivf_conv3d: null argument");
+  IVF_REQUIRE(d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->od > 0 && d->oh > 0 &&
+                  d->ow > 0 && d->cin > 0 && d->cout > 0,
+              "ivf_conv3d: non-positive extent");
+  IVF_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0,
+              "ivf_conv3d: bad kernel/stride");
+  IVF_REQUIRE(d->in_ld >= d->in_coff + d->cin && d->out_ld >= d->out_coff + d->cout,
+              "ivf_conv3d: channel slice exceeds ld");
+  if ((d->flags & IVF_EP_AFFINE)) IVF_REQUIRE(scale && shift, "ivf_conv3d: AFFINE needs scale/shift");
+  if ((d->flags & IVF_EP_ACCUM)) IVF_REQUIRE(acc_in, "ivf_conv3d: ACCUM needs acc_in");
+  if ((d->flags & IVF_EP_MASK)) IVF_REQUIRE(mask_y && mask_scale, "ivf_conv3d: MASK needs mask_y/mask_scale");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == IVF_F32)
+    return ivf_conv3d_f32_launch(h, d, (const float*)in, (const float*)w, scale, shift, acc_in,
+                                 (const float*)mask_y, mask_scale, (float*)out, st);
+  if (d->dtype == IVF_BF16)
+    return ivf_conv3d_tc_launch(h, d, in, w, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  IVF_FAIL(IVF_EINVAL, "ivf_conv3d: unknown dtype %d", d->dtype);
+}

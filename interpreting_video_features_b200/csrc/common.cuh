@@ -1,0 +1,96 @@
+// Internal helpers shared by the libivf.so translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ivf.h"
+
+struct ivf_handle {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  int64_t launches = 0;
+  std::mutex mu;
+  // cache of encoded TMA tensor maps keyed by a byte string of everything that shapes them
+  std::map<std::string, CUtensorMap> tmaps;
+  bool tc_attr_set[4] = {false, false, false, false};
+};
+
+void ivf_set_error(const char* fmt, ...);
+
+#define IVF_FAIL(code, ...)       \
+  do {                            \
+    ivf_set_error(__VA_ARGS__);   \
+    return (code);                \
+  } while (0)
+
+#define IVF_REQUIRE(cond, ...)                       \
+  do {                                               \
+    if (!(cond)) IVF_FAIL(IVF_EINVAL, __VA_ARGS__);  \
+  } while (0)
+
+#define IVF_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      IVF_FAIL(IVF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+               __FILE__, __LINE__);                                                      \
+  } while (0)
+
+// every kernel launch is followed by this: counts the launch and surfaces launch errors
+#define IVF_LAUNCHED(h)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      IVF_FAIL(IVF_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),   \
+               __FILE__, __LINE__);                                                      \
+    (h)->launches++;                                                                     \
+  } while (0)
+
+static inline int ivf_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- dtype helpers (device) -------------------------------------------------------
+__device__ __forceinline__ float ivf_to_float(float v) { return v; }
+__device__ __forceinline__ float ivf_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T ivf_from_float(float v);
+template <>
+__device__ __forceinline__ float ivf_from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 ivf_from_float<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float ivf_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float ivf_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float ivf_warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// entry points implemented per translation unit
+int ivf_conv3d_f32_launch(ivf_handle* h, const ivf_conv_desc* d, const float* in, const float* w,
+                          const float* scale, const float* shift, const float* acc_in,
+                          const float* mask_y, const float* mask_scale, float* out,
+                          cudaStream_t st);
+int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+                         const float* scale, const float* shift, const float* acc_in,
+                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st);

@@ -1,0 +1,692 @@
+// bf16 implicit-GEMM 3-D convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands
+// staged by TMA: the activation tile with the im2col tensor-map mode (the hardware walks
+// 128 consecutive output pixels across W/H/D/N, adds the filter-tap offset and zero-fills
+// the 'same' padding), the K-major packed weights with a tiled map.  fp32 accumulation in
+// TMEM; the epilogue (tcgen05.ld) fuses eval-BatchNorm affine + ReLU for the forward pass and
+// sum-over-consumers + ReLU'/BN' masking for the data-gradient pass, and writes straight into
+// the channel slice of the concat buffer.
+//
+// Stands in for aten::conv3d / convolution_backward(data) + native_batch_norm + relu +
+// constant_pad_nd + cat at pt/models/I3D_doubled.py:96-118,146 and for the gate convolutions of
+// pt/models/convolution_lstm.py:25-32.
+//
+// GEMM view: D[M=128 pixels][N=cout tile] += A[128][kchunk] * B[N][kchunk]^T per (tap, channel
+// chunk).  Warp roles: warp 0 = TMA producer (+TMEM alloc), warp 1 = MMA issuer (one lane),
+// warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include "common.cuh"
+
+#include <cstring>
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct TcParams {
+  int M;                 // n*od*oh*ow
+  int od, oh, ow;
+  int cout;              // real produced channels
+  int bn;                // UMMA N of this launch (multiple of 16, <= 256)
+  int kh, kw;            // tap decode
+  int ntaps, cchunks;    // K iterations = ntaps*cchunks
+  int sd, sh, sw;
+  int pd, ph, pw;
+  int out_ld, out_coff;
+  int mask_ld, mask_coff;
+  int flags;
+  int stages;
+  int tmem_cols;
+  uint32_t a_stage_bytes, b_stage_bytes;  // smem pitch of the A / B part of a stage
+  uint32_t tx_bytes;                      // bytes the two TMA boxes of a stage deliver
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const CUtensorMap* map,
+                                                   uint64_t* bar, int c, int w, int h, int d, int n,
+                                                   uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d),
+      "r"(n), "h"(ow), "h"(oh), "h"(od)
+      : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) swizzle type.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;  // LBO (unused for swizzled K-major; CUTLASS writes 1)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// KCH = channels per K stage: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
+template <int KCH>
+struct KTraits {
+  static constexpr uint32_t row_bytes = KCH * 2;
+  static constexpr uint32_t sbo = 8 * row_bytes;  // 8-row core-matrix group pitch
+  static constexpr uint32_t layout = KCH == 64 ? 2u : (KCH == 32 ? 4u : 6u);
+  static constexpr int ksteps = KCH / 16;
+};
+
+template <int KCH>
+__global__ void __launch_bounds__(NUM_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p, const float* __restrict__ scale, const float* __restrict__ shift,
+               const float* __restrict__ acc_in, const __nv_bfloat16* __restrict__ mask_y,
+               const float* __restrict__ mask_scale, void* __restrict__ out) {
+  using KT = KTraits<KCH>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TILE_M;
+  const int ntile = blockIdx.y;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int kiters = p.ntaps * p.cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    // per-channel epilogue vectors of this N tile
+    for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
+      int n = ntile * p.bn + i;
+      bool ok = n < p.cout;
+      s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[n] : 1.f;
+      s_shift[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? shift[n] : 0.f;
+      s_mscale[i] = (ok && (p.flags & IVF_EP_MASK)) ? mask_scale[n] : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ow0 = m0 % p.ow;
+      int t = m0 / p.ow;
+      int oh0 = t % p.oh;
+      t /= p.oh;
+      int od0 = t % p.od;
+      int n0 = t / p.od;
+      const int cw = ow0 * p.sw - p.pw, ch = oh0 * p.sh - p.ph, cd = od0 * p.sd - p.pd;
+      int stage = 0;
+      uint32_t phase = 0;
+      int tap = 0, cc = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+        const uint32_t a_dst = smem_base + stage * stage_bytes;
+        const uint32_t b_dst = a_dst + p.a_stage_bytes;
+        int kw_i = tap % p.kw;
+        int t2 = tap / p.kw;
+        int kh_i = t2 % p.kh;
+        int kd_i = t2 / p.kh;
+        tma_load_im2col_5d(a_dst, &tmA, &full_bar[stage], cc * KCH, cw, ch, cd, n0, (uint16_t)kw_i,
+                           (uint16_t)kh_i, (uint16_t)kd_i);
+        tma_load_2d(b_dst, &tmB, &full_bar[stage], it * KCH, ntile * p.bn);
+        if (++cc == p.cchunks) {
+          cc = 0;
+          ++tap;
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
+                             ((uint32_t)(TILE_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_src = smem_base + stage * stage_bytes;
+        const uint32_t b_src = a_src + p.a_stage_bytes;
+#pragma unroll
+        for (int k = 0; k < KT::ksteps; ++k) {
+          uint64_t adesc = make_smem_desc(a_src + k * 32, KT::sbo, KT::layout);
+          uint64_t bdesc = make_smem_desc(b_src + k * 32, KT::sbo, KT::layout);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr_row = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
+    const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + c0, r);
+      const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
+      if (!row_ok || nb >= p.cout) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full = nb + 16 <= p.cout;
+      if (p.flags & IVF_EP_ACCUM) {
+        if (full) {
+          const float4* a4 = reinterpret_cast<const float4*>(acc_in + out_row + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 a = a4[j];
+            v[4 * j + 0] += a.x;
+            v[4 * j + 1] += a.y;
+            v[4 * j + 2] += a.z;
+            v[4 * j + 3] += a.w;
+          }
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout) v[j] += acc_in[out_row + nb + j];
+        }
+      }
+      if (p.flags & IVF_EP_AFFINE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]);
+      }
+      if (p.flags & IVF_EP_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.flags & IVF_EP_MASK) {
+        if (full) {
+          const uint4* m4 = reinterpret_cast<const uint4*>(mask_y + mask_row + nb);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint4 mm = m4[hh];
+            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              int jj = hh * 8 + j;
+              v[jj] = __bfloat162float(mb[j]) > 0.f ? v[jj] * s_mscale[c0 + jj] : 0.f;
+            }
+          }
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout)
+              v[j] = __bfloat162float(mask_y[mask_row + nb + j]) > 0.f ? v[j] * s_mscale[c0 + j]
+                                                                         : 0.f;
+        }
+      }
+      if (p.flags & IVF_EP_OUT_F32) {
+        float* o = reinterpret_cast<float*>(out) + out_row + nb;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(o)[j] =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout) o[j] = v[j];
+        }
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + out_row + nb;
+        if (full) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- bring-up probe: one im2col TMA tile -> global, de-swizzled -------------------------
+template <int KCH>
+__global__ void __launch_bounds__(128)
+probe_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int cw, int ch, int cd, int n0, int c0,
+                    int kw_i, int kh_i, int kd_i, __nv_bfloat16* __restrict__ tile_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tile = smem_raw + (smem_base - smem_u32(smem_raw));
+  // poison so that rows the TMA does not write are visible in the dump
+  for (int i = threadIdx.x; i < TILE_M * KCH; i += blockDim.x)
+    reinterpret_cast<__nv_bfloat16*>(tile)[i] = __float2bfloat16_rn(-777.f);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, TILE_M * KCH * 2);
+    tma_load_im2col_5d(smem_base, &tmA, &bar, c0, cw, ch, cd, n0, (uint16_t)kw_i, (uint16_t)kh_i,
+                       (uint16_t)kd_i);
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  constexpr int chunks = KCH * 2 / 16;  // 16-byte chunks per row
+  for (int i = threadIdx.x; i < TILE_M * chunks; i += blockDim.x) {
+    int r = i / chunks, j = i % chunks;
+    int sw = KCH == 64 ? (r & 7) : (KCH == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+    const uint4* src = reinterpret_cast<const uint4*>(tile + (size_t)r * KCH * 2 + ((j ^ sw) * 16));
+    reinterpret_cast<uint4*>(tile_out + (size_t)r * KCH)[j] = *src;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn g_encode_im2col = nullptr;
+EncodeTiledFn g_encode_tiled = nullptr;
+
+int load_driver_entry_points() {
+  static std::once_flag once;
+  static int status = IVF_OK;
+  std::call_once(once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      status = IVF_ECUDA;
+      return;
+    }
+    g_encode_im2col = (EncodeIm2colFn)fn;
+    fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      status = IVF_ECUDA;
+      return;
+    }
+    g_encode_tiled = (EncodeTiledFn)fn;
+  });
+  if (status != IVF_OK) ivf_set_error("cudaGetDriverEntryPoint(cuTensorMapEncode*) failed");
+  return status;
+}
+
+CUtensorMapSwizzle swizzle_for(int kch) {
+  return kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : (kch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct MapKeyA {
+  const void* base;
+  int n, id, ih, iw, cin, ld, coff, kd, kh, kw, sd, sh, sw, pd, ph, pw, od, oh, ow, kch;
+};
+struct MapKeyB {
+  const void* base;
+  int ktot, cout_pad, kch, bn;
+};
+
+template <typename K>
+std::string key_bytes(char tag, const K& k) {
+  std::string s(1, tag);
+  s.append(reinterpret_cast<const char*>(&k), sizeof(K));
+  return s;
+}
+
+int get_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int kch, CUtensorMap* out) {
+  MapKeyA key;
+  memset(&key, 0, sizeof(key));
+  key.base = in;
+  key.n = d->n; key.id = d->id; key.ih = d->ih; key.iw = d->iw; key.cin = d->cin;
+  key.ld = d->in_ld; key.coff = d->in_coff;
+  key.kd = d->kd; key.kh = d->kh; key.kw = d->kw; key.sd = d->sd; key.sh = d->sh; key.sw = d->sw;
+  key.pd = d->pd; key.ph = d->ph; key.pw = d->pw; key.od = d->od; key.oh = d->oh; key.ow = d->ow;
+  key.kch = kch;
+  std::string kb = key_bytes('A', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  const char* base = reinterpret_cast<const char*>(in) + (size_t)d->in_coff * 2;
+  IVF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv(bf16): input slice not 16-B aligned");
+  cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->iw, (cuuint64_t)d->ih, (cuuint64_t)d->id,
+                        (cuuint64_t)d->n};
+  cuuint64_t pix = (cuuint64_t)d->in_ld * 2;
+  cuuint64_t strides[4] = {pix, pix * d->iw, pix * d->iw * d->ih, pix * d->iw * d->ih * d->id};
+  // bounding box of the window origin: lower = -front pad; upper = back pad - (k-1)
+  int pbw = (d->ow - 1) * d->sw + d->kw - d->iw - d->pw;
+  int pbh = (d->oh - 1) * d->sh + d->kh - d->ih - d->ph;
+  int pbd = (d->od - 1) * d->sd + d->kd - d->id - d->pd;
+  int lower[3] = {-d->pw, -d->ph, -d->pd};
+  int upper[3] = {pbw - (d->kw - 1), pbh - (d->kh - 1), pbd - (d->kd - 1)};
+  for (int i = 0; i < 3; ++i)
+    IVF_REQUIRE(lower[i] >= -16 && lower[i] <= 15 && upper[i] >= -16 && upper[i] <= 15,
+                "conv(bf16): padding/kernel outside the im2col corner range");
+  cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
+  CUtensorMap m;
+  CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides,
+                               lower, upper, (cuuint32_t)kch, (cuuint32_t)TILE_M, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeIm2col failed (%d): dims c%d w%d h%d d%d n%d ld%d k%d%d%d",
+             (int)r, d->cin, d->iw, d->ih, d->id, d->n, d->in_ld, d->kd, d->kh, d->kw);
+  // CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp) clears bit 21 of the second descriptor word
+  // for tensors smaller than 128 KiB on drivers <= 13.1; same workaround here.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  unsigned long long span = strides[3] * (cuuint64_t)d->n;
+  if (drv <= 13010 && span < 131072ull) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
+int get_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int kch, int bn, CUtensorMap* out) {
+  MapKeyB key;
+  memset(&key, 0, sizeof(key));
+  key.base = w; key.ktot = ktot; key.cout_pad = cout_pad; key.kch = kch; key.bn = bn;
+  std::string kb = key_bytes('B', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  IVF_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv(bf16): weights not 16-B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(weights) failed (%d): ktot %d cout_pad %d", (int)r,
+             ktot, cout_pad);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
+int check_bf16_desc(const ivf_conv_desc* d) {
+  IVF_REQUIRE(!d->transposed,
+              "conv(bf16): transposed gather is fp32-only; present strided layers space-to-depth");
+  IVF_REQUIRE(d->cin % 8 == 0 && d->in_ld % 8 == 0 && d->in_coff % 8 == 0,
+              "conv(bf16): cin/in_ld/in_coff must be multiples of 8 (got %d/%d/%d)", d->cin,
+              d->in_ld, d->in_coff);
+  IVF_REQUIRE(d->out_ld % 8 == 0 && d->out_coff % 8 == 0,
+              "conv(bf16): out_ld/out_coff must be multiples of 8");
+  if (d->flags & IVF_EP_MASK)
+    IVF_REQUIRE(d->mask_ld % 8 == 0 && d->mask_coff % 8 == 0,
+                "conv(bf16): mask_ld/mask_coff must be multiples of 8");
+  IVF_REQUIRE(d->sd <= 8 && d->sh <= 8 && d->sw <= 8, "conv(bf16): stride > 8");
+  return IVF_OK;
+}
+
+template <int KCH>
+int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CUtensorMap& ma,
+              const CUtensorMap& mb, int ntiles, const float* scale, const float* shift,
+              const float* acc_in, const void* mask_y, const float* mask_scale, void* out,
+              cudaStream_t st) {
+  const int max_smem = 200 * 1024 + 2048;
+  const int slot = KCH == 64 ? 0 : (KCH == 32 ? 1 : 2);
+  if (!h->tc_attr_set[slot]) {
+    IVF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  max_smem));
+    h->tc_attr_set[slot] = true;
+  }
+  size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024;
+  dim3 grid(ivf_cdiv(p.M, TILE_M), ntiles);
+  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
+                                                       (const __nv_bfloat16*)mask_y, mask_scale, out);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+}  // namespace
+
+extern "C" int ivf_conv_bf16_kchunk(int cin) {
+  if (cin <= 16) return 16;
+  int p64 = (cin + 63) / 64 * 64, p32 = (cin + 31) / 32 * 32;
+  return p32 < p64 ? 32 : 64;
+}
+extern "C" int ivf_conv_bf16_cin_pad(int cin) {
+  int k = ivf_conv_bf16_kchunk(cin);
+  return (cin + k - 1) / k * k;
+}
+extern "C" int ivf_conv_bf16_ntile(int cout) {
+  int tiles = (cout + 255) / 256;
+  int per = (cout + tiles - 1) / tiles;
+  return (per + 15) / 16 * 16;
+}
+extern "C" int ivf_conv_bf16_cout_pad(int cout) {
+  int tiles = (cout + 255) / 256;
+  return ivf_conv_bf16_ntile(cout) * tiles;
+}
+
+int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+                         const float* scale, const float* shift, const float* acc_in,
+                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
+  int rc = check_bf16_desc(d);
+  if (rc) return rc;
+  rc = load_driver_entry_points();
+  if (rc) return rc;
+  const int kch = ivf_conv_bf16_kchunk(d->cin);
+  const int cin_pad = ivf_conv_bf16_cin_pad(d->cin);
+  const int bn = ivf_conv_bf16_ntile(d->cout);
+  const int cout_pad = ivf_conv_bf16_cout_pad(d->cout);
+  const int ntiles = cout_pad / bn;
+  const int ntaps = d->kd * d->kh * d->kw;
+  long long M = (long long)d->n * d->od * d->oh * d->ow;
+  IVF_REQUIRE(M < (1ll << 31), "conv(bf16): too many output pixels");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M;
+  p.od = d->od; p.oh = d->oh; p.ow = d->ow;
+  p.cout = d->cout;
+  p.bn = bn;
+  p.kh = d->kh; p.kw = d->kw;
+  p.ntaps = ntaps;
+  p.cchunks = cin_pad / kch;
+  p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+  p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
+  p.flags = d->flags;
+  p.a_stage_bytes = TILE_M * kch * 2;
+  uint32_t bbytes = (uint32_t)bn * kch * 2;
+  p.b_stage_bytes = (bbytes + 1023u) & ~1023u;
+  p.tx_bytes = p.a_stage_bytes + bbytes;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  int kiters = ntaps * p.cchunks;
+  int stages = (int)((100u * 1024u) / stage_bytes);
+  if (stages < 4) stages = 4;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  while ((size_t)stages * stage_bytes > 200u * 1024u) --stages;
+  if (stages > kiters) stages = kiters;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < bn) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap ma, mb;
+  rc = get_map_a(h, d, in, kch, &ma);
+  if (rc) return rc;
+  rc = get_map_b(h, w, ntaps * cin_pad, cout_pad, kch, bn, &mb);
+  if (rc) return rc;
+  if (kch == 64)
+    return launch_tc<64>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  if (kch == 32)
+    return launch_tc<32>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  return launch_tc<16>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
+}
+
+extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0,
+                                int tap, int c0, void* tile_out, void* stream) {
+  IVF_REQUIRE(h && d && in && tile_out, "ivf_probe_im2col: null argument");
+  int rc = check_bf16_desc(d);
+  if (rc) return rc;
+  rc = load_driver_entry_points();
+  if (rc) return rc;
+  const int kch = ivf_conv_bf16_kchunk(d->cin);
+  CUtensorMap ma;
+  rc = get_map_a(h, d, in, kch, &ma);
+  if (rc) return rc;
+  int ow0 = m0 % d->ow;
+  int t = m0 / d->ow;
+  int oh0 = t % d->oh;
+  t /= d->oh;
+  int od0 = t % d->od;
+  int n0 = t / d->od;
+  int cw = ow0 * d->sw - d->pw, ch = oh0 * d->sh - d->ph, cd = od0 * d->sd - d->pd;
+  int kw_i = tap % d->kw, t2 = tap / d->kw, kh_i = t2 % d->kh, kd_i = t2 / d->kh;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = (size_t)TILE_M * kch * 2 + 1024;
+  if (kch == 64)
+    probe_im2col_kernel<64><<<1, 128, smem, st>>>(ma, cw, ch, cd, n0, c0, kw_i, kh_i, kd_i,
+                                                  (__nv_bfloat16*)tile_out);
+  else if (kch == 32)
+    probe_im2col_kernel<32><<<1, 128, smem, st>>>(ma, cw, ch, cd, n0, c0, kw_i, kh_i, kd_i,
+                                                  (__nv_bfloat16*)tile_out);
+  else
+    probe_im2col_kernel<16><<<1, 128, smem, st>>>(ma, cw, ch, cd, n0, c0, kw_i, kh_i, kd_i,
+                                                  (__nv_bfloat16*)tile_out);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}

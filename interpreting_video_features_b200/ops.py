@@ -1,0 +1,260 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point of include/ivf.h).
+
+Activations are channels-last views described by `Act`: a torch buffer plus the per-pixel channel
+stride (`ld`) and the channel offset/extent of the slice — the Inception concat of
+pt/models/I3D_doubled.py:146 is never materialised, each branch writes its slice.
+torch is used for allocation and streams only; every computation below is a libivf kernel.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (EP_ACCUM, EP_AFFINE, EP_MASK, EP_OUT_F32, EP_RELU, IVF_BF16, IVF_F32,
+                   PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, ConvDesc, PoolDesc, check, ptr)
+
+
+class Act:
+    """A channel slice [coff, coff+c) of a channels-last buffer of logical shape (n,d,h,w,ld)."""
+
+    __slots__ = ("buf", "n", "d", "h", "w", "ld", "coff", "c")
+
+    def __init__(self, buf, n, d, h, w, ld, coff=0, c=None):
+        self.buf, self.n, self.d, self.h, self.w, self.ld, self.coff = buf, n, d, h, w, ld, coff
+        self.c = ld - coff if c is None else c
+
+    @staticmethod
+    def empty(n, d, h, w, c, dtype, device, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return Act(f((n, d, h, w, c), dtype=dtype, device=device), n, d, h, w, c, 0, c)
+
+    def slice(self, coff, c):
+        assert coff + c <= self.c
+        return Act(self.buf, self.n, self.d, self.h, self.w, self.ld, self.coff + coff, c)
+
+    def like(self, dtype=None, zero=False):
+        return Act.empty(self.n, self.d, self.h, self.w, self.c, dtype or self.buf.dtype,
+                         self.buf.device, zero)
+
+    @property
+    def pixels(self):
+        return self.n * self.d * self.h * self.w
+
+    def tensor(self):
+        """(n,d,h,w,c) torch view of the slice."""
+        return self.buf.view(self.n, self.d, self.h, self.w, self.ld)[..., self.coff:self.coff + self.c]
+
+    def ncdhw(self):
+        """fp32 (n,c,d,h,w) copy — test/interop helper, not on the hot path."""
+        return self.tensor().permute(0, 4, 1, 2, 3).float().contiguous()
+
+
+def same_pad(size, k, s):
+    """TF 'same' padding of pt/models/I3D_doubled.py:77-101: (front, back, out)."""
+    total = max(k - s, 0) if size % s == 0 else max(k - (size % s), 0)
+    front = total // 2
+    return front, total - front, int(math.ceil(size / s))
+
+
+def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None, acc_in=None,
+           mask=None, mask_scale=None, transposed=0, cin=None, cout=None):
+    """out = epilogue(conv(x, w)); see ivf_conv3d. x/out/mask are Act; w is the packed weight."""
+    d = ConvDesc()
+    d.n, d.id, d.ih, d.iw = x.n, x.d, x.h, x.w
+    d.od, d.oh, d.ow = out.d, out.h, out.w
+    d.cin = x.c if cin is None else cin
+    d.cout = out.c if cout is None else cout
+    d.kd, d.kh, d.kw = kernel
+    d.sd, d.sh, d.sw = stride
+    d.pd, d.ph, d.pw = pad_front
+    d.transposed = transposed
+    d.in_ld, d.in_coff = x.ld, x.coff
+    d.out_ld, d.out_coff = out.ld, out.coff
+    if mask is not None:
+        d.mask_ld, d.mask_coff = mask.ld, mask.coff
+        flags |= EP_MASK
+    if acc_in is not None:
+        flags |= EP_ACCUM
+    if scale is not None:
+        flags |= EP_AFFINE
+    d.dtype = _lib.dtype_code(x.buf)
+    if out.buf.dtype == torch.float32 and x.buf.dtype == torch.bfloat16:
+        flags |= EP_OUT_F32
+    d.flags = flags
+    check(_lib.load().ivf_conv3d(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(w), ptr(scale),
+                                 ptr(shift), ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
+                                 ptr(mask.buf if mask is not None else None), ptr(mask_scale),
+                                 ptr(out.buf), _lib.stream_ptr()), "ivf_conv3d")
+    return out
+
+
+def _pool_desc(x, out, kernel, stride, pad_front, mask=None, flags=0):
+    d = PoolDesc()
+    d.n, d.id, d.ih, d.iw, d.c = x.n, x.d, x.h, x.w, x.c
+    d.od, d.oh, d.ow = out.d, out.h, out.w
+    d.kd, d.kh, d.kw = kernel
+    d.sd, d.sh, d.sw = stride
+    d.pd, d.ph, d.pw = pad_front
+    d.in_ld, d.in_coff = x.ld, x.coff
+    d.out_ld, d.out_coff = out.ld, out.coff
+    if mask is not None:
+        d.mask_ld, d.mask_coff = mask.ld, mask.coff
+    d.flags = flags
+    return d
+
+
+def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front):
+    d = _pool_desc(x, out, kernel, stride, pad_front)
+    d.dtype = _lib.dtype_code(x.buf)
+    check(_lib.load().ivf_maxpool3d_fwd(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(out.buf),
+                                        ptr(argmax), _lib.stream_ptr()), "ivf_maxpool3d_fwd")
+    return out
+
+
+def maxpool3d_bwd(dy, argmax, dx, kernel, stride, pad_front, acc_in=None, mask=None, mask_scale=None):
+    """dx (Act shaped like the pool input) from dy (Act shaped like the pool output)."""
+    flags = 0
+    if acc_in is not None:
+        flags |= EP_ACCUM
+    if mask is not None:
+        flags |= EP_MASK
+    if dx.buf.dtype == torch.float32 and dy.buf.dtype == torch.bfloat16:
+        flags |= EP_OUT_F32
+    d = _pool_desc(dx, dy, kernel, stride, pad_front, mask, flags)
+    d.dtype = _lib.dtype_code(dy.buf)
+    check(_lib.load().ivf_maxpool3d_bwd(_lib.handle(dy.buf.device), C.byref(d), ptr(dy.buf), ptr(argmax),
+                                        ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
+                                        ptr(mask.buf if mask is not None else None), ptr(mask_scale),
+                                        ptr(dx.buf), _lib.stream_ptr()), "ivf_maxpool3d_bwd")
+    return dx
+
+
+def head_fwd(feat, w, b, softmax, out, logits=None):
+    """feat: Act (whole map is pooled); w fp32 [ncls, c]; out fp32 [n, ncls]."""
+    assert feat.coff == 0
+    p = feat.d * feat.h * feat.w
+    check(_lib.load().ivf_i3d_head_fwd(_lib.handle(feat.buf.device), _lib.dtype_code(feat.buf),
+                                       ptr(feat.buf), feat.n, p, feat.c, feat.ld, ptr(w), ptr(b),
+                                       w.shape[0], int(bool(softmax)), ptr(logits), ptr(out),
+                                       _lib.stream_ptr()), "ivf_i3d_head_fwd")
+    return out
+
+
+def head_bwd(dfeat, w, softmax, out, dout, mask=None, mask_scale=None):
+    """dfeat: Act to fill (dtype of the activations, or fp32)."""
+    assert dfeat.coff == 0
+    p = dfeat.d * dfeat.h * dfeat.w
+    flags = 0
+    dtype = _lib.dtype_code(mask.buf) if mask is not None else _lib.dtype_code(dfeat.buf)
+    if mask is not None:
+        flags |= EP_MASK
+    if dfeat.buf.dtype == torch.float32 and dtype == IVF_BF16:
+        flags |= EP_OUT_F32
+    check(_lib.load().ivf_i3d_head_bwd(_lib.handle(dfeat.buf.device), dtype, dfeat.n, p, dfeat.c, dfeat.ld,
+                                       ptr(w), w.shape[0], int(bool(softmax)), ptr(out), ptr(dout), flags,
+                                       ptr(mask.buf if mask is not None else None),
+                                       mask.ld if mask is not None else 0,
+                                       mask.coff if mask is not None else 0, ptr(mask_scale),
+                                       ptr(dfeat.buf), _lib.stream_ptr()), "ivf_i3d_head_bwd")
+    return dfeat
+
+
+_MODES = {"freeze": 0, "reverse": 1}
+
+
+def perturb_fwd(x, mask, mode, out_fmt, out):
+    """x fp32 [b,c,t,h,w]; mask fp32 [t] (shared) or [b,t]; out preallocated per out_fmt."""
+    b, c, t, hh, ww = x.shape
+    bstride = 0 if mask.dim() == 1 else t
+    check(_lib.load().ivf_perturb_fwd(_lib.handle(x.device), _MODES[mode], ptr(x), ptr(mask), bstride, b, c,
+                                      t, hh, ww, out_fmt, ptr(out), _lib.stream_ptr()), "ivf_perturb_fwd")
+    return out
+
+
+def perturb_bwd(x, mask, mode, out_fmt, gout, dmask):
+    """dmask fp32 [b,t] (one row per clip, also for a shared mask)."""
+    b, c, t, hh, ww = x.shape
+    bstride = 0 if mask.dim() == 1 else t
+    check(_lib.load().ivf_perturb_bwd(_lib.handle(x.device), _MODES[mode], ptr(x), ptr(mask), bstride, b, c,
+                                      t, hh, ww, out_fmt, _lib.dtype_code(gout), ptr(gout), ptr(dmask),
+                                      _lib.stream_ptr()), "ivf_perturb_bwd")
+    return dmask
+
+
+def mask_loss_adam(m, exp_avg, exp_avg_sq, dclass, step, lam1, lam2, lr=0.2, beta1=0.9, beta2=0.999,
+                   eps=1e-8, losses=None, sig_out=None, step_dev=None):
+    nclip, t = m.shape
+    check(_lib.load().ivf_mask_loss_adam(_lib.handle(m.device), ptr(m), ptr(exp_avg), ptr(exp_avg_sq),
+                                         ptr(dclass), nclip, t, int(step), ptr(step_dev), lam1, lam2, lr,
+                                         beta1, beta2, eps, ptr(losses), ptr(sig_out), _lib.stream_ptr()),
+          "ivf_mask_loss_adam")
+
+
+def sigmoid(m, out):
+    check(_lib.load().ivf_sigmoid(_lib.handle(m.device), ptr(m), ptr(out), m.numel(), _lib.stream_ptr()),
+          "ivf_sigmoid")
+    return out
+
+
+def tv_norm(mask, p, q, val, dmask=None):
+    check(_lib.load().ivf_tv_norm(_lib.handle(mask.device), ptr(mask), mask.numel(), float(p), float(q),
+                                  ptr(val), ptr(dmask), _lib.stream_ptr()), "ivf_tv_norm")
+    return val
+
+
+def gradcam(act, grad, step, hout, wout, per_frame, cam, cam_lowres=None):
+    """act/grad: Act of the target layer (same geometry); cam fp32 [n, tp*step, hout, wout]."""
+    assert act.coff == 0 and grad.coff == 0 and act.ld == grad.ld
+    check(_lib.load().ivf_gradcam(_lib.handle(act.buf.device), _lib.dtype_code(act.buf),
+                                  _lib.dtype_code(grad.buf), ptr(act.buf), ptr(grad.buf), act.n, act.d,
+                                  act.h, act.w, act.c, act.ld, step, hout, wout, int(bool(per_frame)),
+                                  ptr(cam), ptr(cam_lowres), _lib.stream_ptr()), "ivf_gradcam")
+    return cam
+
+
+def clstm_gates_fwd(pre, c_prev, c_next, h_next, gate_act):
+    m, four_hid = pre.shape
+    check(_lib.load().ivf_clstm_gates_fwd(_lib.handle(pre.device), _lib.dtype_code(h_next), ptr(pre),
+                                          ptr(c_prev), m, four_hid // 4, ptr(c_next), ptr(h_next),
+                                          ptr(gate_act), _lib.stream_ptr()), "ivf_clstm_gates_fwd")
+
+
+def clstm_gates_bwd(gate_act, c_prev, c_next, dh, dc_io, dgates):
+    m, four_hid = gate_act.shape
+    check(_lib.load().ivf_clstm_gates_bwd(_lib.handle(dh.device), _lib.dtype_code(dgates), ptr(gate_act),
+                                          ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_io), m, four_hid // 4,
+                                          ptr(dgates), _lib.stream_ptr()), "ivf_clstm_gates_bwd")
+
+
+def bn_pool2d_fwd(x, scale, shift, y, argmax):
+    n, hh, ww, c = x.shape
+    check(_lib.load().ivf_bn_pool2d_fwd(_lib.handle(x.device), _lib.dtype_code(x), ptr(x), n, hh, ww, c,
+                                        ptr(scale), ptr(shift), ptr(y), ptr(argmax), _lib.stream_ptr()),
+          "ivf_bn_pool2d_fwd")
+
+
+def bn_pool2d_bwd(dy, argmax, scale, dx, acc_in=None):
+    n, hh, ww, c = dx.shape
+    check(_lib.load().ivf_bn_pool2d_bwd(_lib.handle(dy.device), _lib.dtype_code(dy), ptr(dy), ptr(argmax), n,
+                                        hh, ww, c, ptr(scale), ptr(acc_in), ptr(dx), _lib.stream_ptr()),
+          "ivf_bn_pool2d_bwd")
+
+
+def probe_im2col(x, kernel, stride, pad_front, out_dhw, m0, tap, c0):
+    """Bring-up probe: returns the [128, kchunk] bf16 tile the conv kernel's TMA would stage."""
+    d = ConvDesc()
+    d.n, d.id, d.ih, d.iw = x.n, x.d, x.h, x.w
+    d.od, d.oh, d.ow = out_dhw
+    d.cin, d.cout = x.c, 16
+    d.kd, d.kh, d.kw = kernel
+    d.sd, d.sh, d.sw = stride
+    d.pd, d.ph, d.pw = pad_front
+    d.in_ld, d.in_coff = x.ld, x.coff
+    d.out_ld, d.out_coff = 16, 0
+    d.dtype = IVF_BF16
+    kch = _lib.load().ivf_conv_bf16_kchunk(x.c)
+    tile = torch.empty((128, kch), dtype=torch.bfloat16, device=x.buf.device)
+    check(_lib.load().ivf_probe_im2col(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), m0, tap, c0,
+                                       ptr(tile), _lib.stream_ptr()), "ivf_probe_im2col")
+    return tile
