@@ -300,14 +300,24 @@ int launch_bwd(ivf_handle* h, int mode, const float* x, const float* mask, int m
     size_t smem = (size_t)t2 * w2 * 32 * esz;
     IVF_REQUIRE(smem <= 200 * 1024, "perturb_bwd(s2d): row tile of %zu bytes exceeds shared memory", smem);
     dim3 grid(hh / 2, b);
+    // opt in to large dynamic shared memory once per instantiation and device (not per launch, so
+    // a captured iteration contains launches only)
+    static bool attr_done[2][16] = {};
+    int dev = h->device & 15;
     if (gout_dtype == IVF_F32) {
-      IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, float>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (!attr_done[0][dev]) {
+        IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, float>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[0][dev] = true;
+      }
       perturb_bwd_s2d_kernel<TT, float><<<grid, 256, smem, st>>>(mode, x, mask, mask_bstride, c, t, hh,
                                                                  ww, (const float*)gout, dmask);
     } else {
-      IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, __nv_bfloat16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (!attr_done[1][dev]) {
+        IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, __nv_bfloat16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[1][dev] = true;
+      }
       perturb_bwd_s2d_kernel<TT, __nv_bfloat16><<<grid, 256, smem, st>>>(
           mode, x, mask, mask_bstride, c, t, hh, ww, (const __nv_bfloat16*)gout, dmask);
     }

@@ -1,0 +1,347 @@
+"""Native I3D runner: the forward and data-gradient passes of pt/models/I3D_doubled.py (and the
+_kth variant) as a fixed sequence of libivf kernel launches over preallocated channels-last
+buffers, so one mask-search iteration (pt/FindMasksComparison_I3D_smth.py:193-214) can be
+captured in a CUDA graph.
+
+What differs from the reference's execution (not from its results):
+  * eval BatchNorm + ReLU live in the conv epilogue; 'same' padding is TMA zero fill; the
+    Inception concat is a channel offset (pt/models/I3D_doubled.py:96-118,146);
+  * only the data gradient is computed (the reference also computes 12.47 M weight gradients per
+    iteration that nobody reads, pt/FindMasksComparison_I3D_smth.py:191,212-214);
+  * every clip of the batch carries its own mask (the reference forwards B clips under ONE mask and
+    reads one of them, :202-205);
+  * bf16 mode presents the stride-2 7x7x7 stem space-to-depth: a stride-1 4x4x4 convolution over
+    8*3 channels (forward) and its flipped transpose (data gradient), so every convolution of the
+    network is the same stride-1 tcgen05 implicit GEMM.
+
+State-dict keys are the reference's; weights are packed once at construction.
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import PFMT_NDHWC_F32, PFMT_S2D_BF16
+from .ops import Act, same_pad
+
+ENDPOINTS = ("Conv3d_1a_7x7", "MaxPool3d_2a_3x3", "Conv3d_2b_1x1", "Conv3d_2c_3x3", "MaxPool3d_3a_3x3",
+             "Mixed_3b", "Mixed_3c", "MaxPool3d_4a_3x3", "Mixed_4b", "Mixed_4c", "Mixed_4d", "Mixed_4e",
+             "Mixed_4f", "MaxPool3d_5a_2x2", "Mixed_5b", "Mixed_5c")
+POOLS = {"MaxPool3d_2a_3x3": ((1, 3, 3), (1, 2, 2)), "MaxPool3d_3a_3x3": ((1, 3, 3), (1, 2, 2)),
+         "MaxPool3d_4a_3x3": ((3, 3, 3), (2, 2, 2)), "MaxPool3d_5a_2x2": ((2, 2, 2), (2, 2, 2))}
+
+
+def strip_module_prefix(sd):
+    """DataParallel checkpoints carry 'module.' (pt/utils.py:94-104)."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------- weight packing
+def s2d_weight(w, win):
+    """(co,ci,k,k,k) stride-2 kernel -> (co, 8*ci, win,win,win) stride-1 kernel over the
+    space-to-depth input; channel = ((a*2+b)*2+c)*ci + ch, source tap = 2*delta + parity."""
+    co, ci, kd, kh, kw = w.shape
+    out = w.new_zeros(co, 8 * ci, win, win, win)
+    for a in range(2):
+        for b in range(2):
+            for c in range(2):
+                blk = ((a * 2 + b) * 2 + c) * ci
+                for dt in range(win):
+                    kt = 2 * dt + a
+                    if kt >= kd:
+                        continue
+                    for dh in range(win):
+                        kh_ = 2 * dh + b
+                        if kh_ >= kh:
+                            continue
+                        for dw in range(win):
+                            kw_ = 2 * dw + c
+                            if kw_ >= kw:
+                                continue
+                            out[:, blk:blk + ci, dt, dh, dw] = w[:, :, kt, kh_, kw_]
+    return out
+
+
+def _pack_bf16(wk):
+    """(n, taps, k) fp32 -> bf16 [n_pad, taps, k_pad] K-major, padded as the kernel tiles it."""
+    lib = _lib.load()
+    n, taps, k = wk.shape
+    k_pad, n_pad = lib.ivf_conv_bf16_cin_pad(k), lib.ivf_conv_bf16_cout_pad(n)
+    out = torch.zeros((n_pad, taps, k_pad), dtype=torch.bfloat16, device=wk.device)
+    out[:n, :, :k] = wk.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def pack_fwd(w, mode):
+    co, ci = w.shape[:2]
+    if mode == "fp32":
+        return w.permute(2, 3, 4, 1, 0).reshape(-1, co).contiguous().float()
+    return _pack_bf16(w.permute(0, 2, 3, 4, 1).reshape(co, -1, ci))
+
+
+def pack_dgrad(w, mode):
+    """fp32: [taps][co][ci] for the transposed gather; bf16: flipped taps, roles swapped."""
+    co, ci = w.shape[:2]
+    if mode == "fp32":
+        return w.permute(2, 3, 4, 0, 1).reshape(-1, ci).contiguous().float()
+    return _pack_bf16(w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, -1, co))
+
+
+class Unit:
+    """Unit3D (pt/models/I3D_doubled.py:43-118): conv weights packed both ways + folded BN."""
+
+    def __init__(self, sd, prefix, stride, mode, device, s2d=False):
+        w = sd[prefix + ".conv3d.weight"].detach().to(device=device, dtype=torch.float32)
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        self.kernel = tuple(w.shape[2:])
+        self.stride = tuple(stride)
+        self.s2d = s2d
+        if prefix + ".bn.weight" in sd:
+            g = sd[prefix + ".bn.weight"].detach().to(device=device, dtype=torch.float32)
+            b = sd[prefix + ".bn.bias"].detach().to(device=device, dtype=torch.float32)
+            mu = sd[prefix + ".bn.running_mean"].detach().to(device=device, dtype=torch.float32)
+            var = sd[prefix + ".bn.running_var"].detach().to(device=device, dtype=torch.float32)
+            self.scale = (g / torch.sqrt(var + 1e-3)).contiguous()  # BatchNorm3d(eps=0.001), :75
+            self.shift = (b - mu * self.scale).contiguous()
+        else:
+            self.scale = torch.ones(self.cout, device=device)
+            self.shift = torch.zeros(self.cout, device=device)
+        if s2d:
+            assert mode == "bf16" and self.stride == (2, 2, 2)
+            win = (self.kernel[0] + 1) // 2
+            w = s2d_weight(w, win)
+            self.kernel_eff, self.stride_eff, self.cin_eff = (win,) * 3, (1, 1, 1), 8 * self.cin
+        else:
+            self.kernel_eff, self.stride_eff, self.cin_eff = self.kernel, self.stride, self.cin
+        self.w_fwd = pack_fwd(w, mode)
+        self.w_dgrad = pack_dgrad(w, mode)
+
+
+class I3DEngine:
+    def __init__(self, state_dict, batch, clip, mode="bf16", softmax=True, avg_pool=(2, 7, 7),
+                 stride_mods=None, device=None, in_channels=3):
+        assert mode in ("bf16", "fp32")
+        self.mode = mode
+        self.dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.device = torch.device(device if device is not None else "cuda")
+        _lib.handle(self.device)  # fails loudly without the extension / a GPU
+        sd = strip_module_prefix(state_dict)
+        self.B, (self.T, self.H, self.W) = batch, clip
+        self.C = in_channels
+        self.softmax = bool(softmax)
+        stride_mods = stride_mods or {}
+        dev = self.device
+        B = batch
+
+        def strides_of(name, default):
+            return stride_mods.get(name, default)
+
+        # ---- stem input format
+        s1 = strides_of("Conv3d_1a_7x7", (2, 2, 2))
+        if mode == "bf16":
+            if s1 != (2, 2, 2) or self.T % 2 or self.H % 2 or self.W % 2 or in_channels > 4:
+                raise _lib.IvfError("bf16 mode needs the stride-(2,2,2) stem on even T/H/W; use mode='fp32'")
+            self.in_fmt = PFMT_S2D_BF16
+            self.xin = Act.empty(B, self.T // 2, self.H // 2, self.W // 2, 32, torch.bfloat16, dev, zero=True)
+            self.g_xin = Act.empty(B, self.T // 2, self.H // 2, self.W // 2, 32, torch.bfloat16, dev, zero=True)
+        else:
+            self.in_fmt = PFMT_NDHWC_F32
+            self.xin = Act.empty(B, self.T, self.H, self.W, in_channels, torch.float32, dev)
+            self.g_xin = Act.empty(B, self.T, self.H, self.W, in_channels, torch.float32, dev)
+
+        self.fwd_ops, self.bwd_ops = [], []
+        self.acts = {}  # endpoint -> Act (forward output)
+        # each stage: dict(out=Act, scale=tensor|None (None: pool-type output), gout=Act)
+        stages = []
+
+        def new_act(n, d, h, w, c, dtype=None, zero=False):
+            return Act.empty(n, d, h, w, c, dtype or self.dtype, dev, zero)
+
+        # ------------------------------------------------------------------ builders
+        def add_unit_fwd(unit, x, out, xin_is_s2d=False):
+            if xin_is_s2d:
+                pf = (1, 1, 1)
+                xa = Act(x.buf, x.n, x.d, x.h, x.w, x.ld, 0, unit.cin_eff)
+            else:
+                pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in zip((x.d, x.h, x.w), unit.kernel, unit.stride))
+                xa = x
+            self.fwd_ops.append(lambda: ops.conv3d(xa, unit.w_fwd, out, unit.kernel_eff, unit.stride_eff, pf,
+                                                   flags=_lib.EP_RELU, scale=unit.scale, shift=unit.shift))
+
+        def add_unit_bwd(unit, dz_out, x_shape_act, g_in, acc_in=None, mask=None, mask_scale=None,
+                         xin_is_s2d=False):
+            """g_in (+)= dgrad(dz_out); g_in is an Act shaped like the unit's input."""
+            if self.mode == "fp32":
+                pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in
+                           zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel, unit.stride))
+                self.bwd_ops.append(lambda: ops.conv3d(dz_out, unit.w_dgrad, g_in, unit.kernel, unit.stride, pf,
+                                                       acc_in=acc_in, mask=mask, mask_scale=mask_scale,
+                                                       transposed=1))
+            else:
+                if xin_is_s2d:
+                    pf = tuple(k - 1 - 1 for k in unit.kernel_eff)
+                    gi = Act(g_in.buf, g_in.n, g_in.d, g_in.h, g_in.w, g_in.ld, 0, unit.cin_eff)
+                else:
+                    assert unit.stride == (1, 1, 1)
+                    pf = tuple(k - 1 - same_pad(sz, k, 1)[0] for sz, k in
+                               zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel))
+                    gi = g_in
+                self.bwd_ops.append(lambda: ops.conv3d(dz_out, unit.w_dgrad, gi, unit.kernel_eff, (1, 1, 1), pf,
+                                                       acc_in=acc_in, mask=mask, mask_scale=mask_scale))
+
+        def out_dims(x, k, s):
+            return tuple(same_pad(sz, kk, ss)[2] for sz, kk, ss in zip((x.d, x.h, x.w), k, s))
+
+        # ------------------------------------------------------------------ build the network
+        self.units = {}
+        x = self.xin
+        prev = None  # previous stage record
+        for name in ENDPOINTS:
+            if name.startswith("Conv3d"):
+                stride = strides_of(name, (2, 2, 2)) if name == "Conv3d_1a_7x7" else (1, 1, 1)
+                first = name == "Conv3d_1a_7x7"
+                unit = Unit(sd, name, stride, mode, dev, s2d=(first and mode == "bf16"))
+                self.units[name] = unit
+                if first and mode == "bf16":
+                    od, oh, ow = x.d, x.h, x.w
+                else:
+                    od, oh, ow = out_dims(x, unit.kernel, unit.stride)
+                out = new_act(B, od, oh, ow, unit.cout)
+                add_unit_fwd(unit, x, out, xin_is_s2d=(first and mode == "bf16"))
+                stages.append(dict(kind="unit", name=name, unit=unit, x=x, out=out, scale=unit.scale,
+                                   gout=out.like(), first=first))
+            elif name.startswith("MaxPool"):
+                k, s0 = POOLS[name]
+                s = strides_of(name, s0)
+                pads = tuple(same_pad(sz, kk, ss)[0] for sz, kk, ss in zip((x.d, x.h, x.w), k, s))
+                od, oh, ow = out_dims(x, k, s)
+                out = new_act(B, od, oh, ow, x.c)
+                am = torch.empty((out.pixels, x.c), dtype=torch.uint8, device=dev)
+                self.fwd_ops.append(lambda x=x, out=out, am=am, k=k, s=s, pads=pads:
+                                    ops.maxpool3d_fwd(x, out, am, k, s, pads))
+                stages.append(dict(kind="pool", name=name, x=x, out=out, scale=None, gout=out.like(), argmax=am,
+                                   k=k, s=s, pads=pads))
+            else:  # Inception module
+                rec = self._build_inception(sd, name, x, new_act, add_unit_fwd)
+                stages.append(rec)
+            x = stages[-1]["out"]
+            self.acts[name] = x
+        self.stages = stages
+
+        # ---- head (pt/models/I3D_doubled.py:313-333,360-371)
+        feat = x
+        if (feat.d, feat.h, feat.w) != tuple(avg_pool):
+            raise _lib.IvfError(
+                "Mixed_5c map %s is not covered by avg_pool %s: the reference's squeeze() would not give "
+                "[B, classes] here (SURVEY fact 10)" % ((feat.d, feat.h, feat.w), tuple(avg_pool)))
+        wl = sd["logits.conv3d.weight"].detach().to(device=dev, dtype=torch.float32)
+        self.num_classes = wl.shape[0]
+        self.w_logits = wl.reshape(self.num_classes, -1).contiguous()
+        self.b_logits = sd["logits.conv3d.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.logits = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
+        self.probs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
+        self.dprobs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
+        self.fwd_ops.append(lambda: ops.head_fwd(feat, self.w_logits, self.b_logits, self.softmax, self.probs,
+                                                 self.logits))
+        # Grad-CAM reads the raw (unmasked) gradient w.r.t. Mixed_5c in fp32
+        self.g_feat_raw = feat.like(torch.float32)
+
+        # ---- backward program
+        last = stages[-1]
+        self.bwd_ops.append(lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
+                                                 self.dprobs, mask=last["out"], mask_scale=last["scale"]))
+        for i in range(len(stages) - 1, -1, -1):
+            st = stages[i]
+            prv = stages[i - 1] if i > 0 else None
+            if prv is None:
+                g_in, mask, mscale = self.g_xin, None, None
+            else:
+                g_in = prv["gout"]
+                mask = prv["out"] if prv["scale"] is not None else None
+                mscale = prv["scale"]
+            if st["kind"] == "unit":
+                add_unit_bwd(st["unit"], st["gout"], st["x"], g_in, mask=mask, mask_scale=mscale,
+                             xin_is_s2d=(st["first"] and mode == "bf16"))
+            elif st["kind"] == "pool":
+                self.bwd_ops.append(lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
+                                    ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
+                                                      mask=mask, mask_scale=mscale))
+            else:
+                self._build_inception_bwd(st, g_in, mask, mscale, add_unit_bwd)
+
+        # ---- mask-search state; x is a static buffer so a captured graph stays valid across batches
+        self.x = torch.zeros((B, in_channels, self.T, self.H, self.W), dtype=torch.float32, device=dev)
+        self.dm = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
+        self.zero_mask = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
+
+    # -------------------------------------------------------------------------------------
+    def _build_inception(self, sd, name, x, new_act, add_unit_fwd):
+        mode, dev = self.mode, self.device
+        u = {b: Unit(sd, "%s.%s" % (name, b), (1, 1, 1), mode, dev) for b in ("b0", "b1a", "b1b", "b2a", "b2b", "b3b")}
+        for b, unit in u.items():
+            self.units["%s.%s" % (name, b)] = unit
+        c0, c1, c2, c3, c4, c5 = (u[b].cout for b in ("b0", "b1a", "b1b", "b2a", "b2b", "b3b"))
+        cout = c0 + c2 + c4 + c5
+        out = new_act(x.n, x.d, x.h, x.w, cout)
+        t1 = new_act(x.n, x.d, x.h, x.w, c1)
+        t2 = new_act(x.n, x.d, x.h, x.w, c3)
+        t3 = new_act(x.n, x.d, x.h, x.w, x.c)
+        am = torch.empty((x.pixels, x.c), dtype=torch.uint8, device=dev)
+        k3 = (3, 3, 3)
+        pads = tuple(same_pad(sz, 3, 1)[0] for sz in (x.d, x.h, x.w))
+        add_unit_fwd(u["b0"], x, out.slice(0, c0))
+        add_unit_fwd(u["b1a"], x, t1)
+        add_unit_fwd(u["b1b"], t1, out.slice(c0, c2))
+        add_unit_fwd(u["b2a"], x, t2)
+        add_unit_fwd(u["b2b"], t2, out.slice(c0 + c2, c4))
+        self.fwd_ops.append(lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads))
+        add_unit_fwd(u["b3b"], t3, out.slice(c0 + c2 + c4, c5))
+        scale = torch.cat([u["b0"].scale, u["b1b"].scale, u["b2b"].scale, u["b3b"].scale]).contiguous()
+        return dict(kind="inception", name=name, units=u, x=x, out=out, scale=scale, gout=out.like(),
+                    t1=t1, t2=t2, t3=t3, argmax=am, pads=pads,
+                    g_t1=t1.like(), g_t2=t2.like(), g_t3=t3.like(), g_x32=x.like(torch.float32))
+
+    def _build_inception_bwd(self, st, g_in, mask, mscale, add_unit_bwd):
+        u, x, dz = st["units"], st["x"], st["gout"]
+        c0, c2, c4, c5 = u["b0"].cout, u["b1b"].cout, u["b2b"].cout, u["b3b"].cout
+        # branch tails: gradients w.r.t. the 1x1 bottleneck outputs (ReLU'/BN' of b1a/b2a fused)
+        add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
+        add_unit_bwd(u["b1b"], dz.slice(c0, c2), st["t1"], st["g_t1"], mask=st["t1"], mask_scale=u["b1a"].scale)
+        add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
+        # the four consumers of x: summed in fp32, the last one applies the producer's ReLU'/BN'
+        acc = st["g_x32"]
+        add_unit_bwd(u["b0"], dz.slice(0, c0), x, acc)
+        add_unit_bwd(u["b1a"], st["g_t1"], x, acc, acc_in=acc)
+        add_unit_bwd(u["b2a"], st["g_t2"], x, acc, acc_in=acc)
+        self.bwd_ops.append(lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], g_in, (3, 3, 3), (1, 1, 1),
+                                                      st["pads"], acc_in=acc, mask=mask, mask_scale=mscale))
+
+    # ------------------------------------------------------------------------------------- running
+    def set_input(self, x):
+        """x: fp32 [B,3,T,H,W] (the loader's layout), host or device; copied into the static buffer."""
+        assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
+        self.x.copy_(x, non_blocking=True)
+
+    def forward(self, mask=None, perturb="freeze"):
+        """Perturb (mask: sigmoid-ed values [T] or [B,T]; None = unperturbed clip) and run the network.
+        Returns the [B, classes] probability (or logit) buffer — a live buffer, not a copy."""
+        self._mask, self._perturb = (self.zero_mask if mask is None else mask), perturb
+        ops.perturb_fwd(self.x, self._mask, perturb, self.in_fmt, self.xin.buf)
+        for op in self.fwd_ops:
+            op()
+        return self.probs
+
+    def backward(self, to_mask=True):
+        """Data-gradient pass from self.dprobs; returns d(sum dprobs*probs)/dmask [B,T] (live buffer)."""
+        for op in self.bwd_ops:
+            op()
+        if to_mask:
+            ops.perturb_bwd(self.x, self._mask, self._perturb, self.in_fmt, self.g_xin.buf, self.dm)
+        return self.dm
+
+    def set_targets(self, targets):
+        """dprobs = one-hot(targets): the class_loss of pt/FindMasksComparison_I3D_smth.py:205."""
+        self.dprobs.zero_()
+        self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
+
+    def head_grad_raw(self):
+        """fp32 gradient of sum(dprobs*probs) w.r.t. Mixed_5c (no ReLU mask): Grad-CAM's `grads_val`."""
+        return ops.head_bwd(self.g_feat_raw, self.w_logits, self.softmax, self.probs, self.dprobs)

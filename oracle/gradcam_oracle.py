@@ -1,0 +1,78 @@
+"""Oracle (test infrastructure): Grad-CAM tail restated from pt/grad_cam_videos.py:64-142 in numpy,
+with cv2.resize(INTER_LINEAR) restated as an explicit half-pixel bilinear so the oracle has no
+OpenCV dependency (pinned against cv2 in oracle/pin_against_reference.py).
+"""
+import numpy as np
+import torch
+
+
+def resize_bilinear(src, dsize):
+    """cv2.resize(src, dsize=(width, height)) for float32, INTER_LINEAR: source coordinate
+    (d + 0.5) * scale - 0.5, floor, replicated border (opencv modules/imgproc/src/resize.cpp)."""
+    w_out, h_out = dsize
+    h_in, w_in = src.shape
+
+    def taps(n_out, n_in):
+        scale = n_in / n_out
+        f = ((np.arange(n_out) + 0.5) * scale - 0.5).astype(np.float32)
+        i0 = np.floor(f).astype(np.int64)
+        frac = (f - i0).astype(np.float32)
+        lo = i0 < 0
+        i0[lo], frac[lo] = 0, 0.0
+        hi = i0 >= n_in - 1
+        i0[hi], frac[hi] = n_in - 1, 0.0
+        i1 = np.minimum(i0 + 1, n_in - 1)
+        return i0, i1, frac
+
+    y0, y1, fy = taps(h_out, h_in)
+    x0, x1, fx = taps(w_out, w_in)
+    src = src.astype(np.float32)
+    rows0 = src[y0][:, x0] * (1 - fx)[None, :] + src[y0][:, x1] * fx[None, :]
+    rows1 = src[y1][:, x0] * (1 - fx)[None, :] + src[y1][:, x1] * fx[None, :]
+    return (rows0 * (1 - fy)[:, None] + rows1 * fy[:, None]).astype(np.float32)
+
+
+def cam_from_features(target, grads_val, clip_size, input_spatial_size, normalize_per_frame=True):
+    """pt/grad_cam_videos.py:96-140.  target [C,T',h,w] activations, grads_val [1,C,T',h,w]."""
+    weights = np.mean(grads_val, axis=(2, 3, 4))[0, :]
+    cam = np.zeros(target.shape[1:], dtype=np.float32)
+    for i, w in enumerate(weights):
+        cam += w * target[i]
+    cam = np.maximum(cam, 0)
+    step = clip_size // target.shape[1]
+    cam_vid = []
+    for i in range(cam.shape[0]):
+        m = resize_bilinear(cam[i], (input_spatial_size[0], input_spatial_size[1]))
+        cam_vid.append(np.repeat(np.expand_dims(m, 0), step, axis=0))
+    cam_vid = np.array(cam_vid)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if normalize_per_frame:
+            for i in range(cam_vid.shape[0]):
+                cam_vid[i] = cam_vid[i] - np.min(cam_vid[i])
+                cam_vid[i] = cam_vid[i] / np.max(cam_vid[i])
+        else:
+            cam_vid = cam_vid - np.min(cam_vid)
+            cam_vid = cam_vid / np.max(cam_vid)
+    if cam_vid.shape[0] > 1:
+        cam_vid = np.concatenate(cam_vid, axis=0)
+    if cam_vid.shape[0] == 1:
+        cam_vid = np.squeeze(cam_vid, 0)
+    return cam_vid, cam
+
+
+def gradcam_i3d(sd, x, index=None, input_spatial_size=(224, 224), normalize_per_frame=True,
+                avg_pool=(2, 7, 7), softmax=True):
+    """pt/grad_cam_videos.py:27-43,64-98 for archType 'I3D', target layer Mixed_5c.
+    x [1,3,T,H,W]; returns (cam [T,H,W] float32, output [1,classes], lowres cam)."""
+    from . import i3d_oracle
+
+    feat, _ = i3d_oracle.features(sd, x)
+    feat = feat.detach().requires_grad_(True)
+    output = i3d_oracle.head(sd, feat, avg_pool, softmax)
+    if index is None:
+        index = int(np.argmax(output.detach().cpu().numpy()))
+    score = output[0, int(index)]  # sum(one_hot * output)
+    (grad,) = torch.autograd.grad(score, feat)
+    cam, lowres = cam_from_features(feat.detach().cpu().numpy()[0], grad.cpu().numpy(), x.shape[2],
+                                    input_spatial_size, normalize_per_frame)
+    return cam, output.detach(), lowres

@@ -1,0 +1,259 @@
+"""GPU (-m gpu): the native I3D engine, the batched mask search, the drop-in call surface and
+Grad-CAM against the oracle and the committed golden vectors.  Tolerances are the north star's:
+1e-4 relative in fp32 mode, 1e-2 in bf16 mode; final-mask frame-wise IoU >= 0.95."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLD, i3d_state_dict, quiet, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(clip=(16, 64, 64), avg_pool=(2, 2, 2))
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from interpreting_video_features_b200 import _lib
+    _lib.handle()
+    return torch.device("cuda")
+
+
+@pytest.fixture(scope="module")
+def small_setup():
+    """Seeded I3D, sharpened on a small geometry the CPU oracle iterates quickly."""
+    from oracle import i3d_oracle, synthetic
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = synthetic.clips(3, t=16, h=64, w=64)
+    sds = i3d_oracle.calibrate_and_sharpen(sd, x, avg_pool=SMALL["avg_pool"])
+    return sds, x
+
+
+@pytest.fixture(scope="module")
+def full_setup():
+    from oracle import i3d_oracle, synthetic
+    sd, _ = quiet(i3d_state_dict, 174)
+    x2 = synthetic.clips(2)
+    return sd, i3d_oracle.calibrate_and_sharpen(sd, x2), x2
+
+
+def make_engine(sd, batch, mode, dev, clip, avg_pool):
+    from interpreting_video_features_b200.engine import I3DEngine
+    return I3DEngine(sd, batch, clip, mode=mode, softmax=True, avg_pool=avg_pool, device=dev)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_forward_activations_and_probs_small(dev, small_setup, mode):
+    from oracle import i3d_oracle
+    sds, x = small_setup
+    eng = make_engine(sds, 3, mode, dev, **SMALL)
+    eng.set_input(x.to(dev))
+    probs = eng.forward(None).cpu()
+    with torch.no_grad():
+        feat, outs = i3d_oracle.features(sds, x)
+        want = i3d_oracle.head(sds, feat, SMALL["avg_pool"], True)
+    for name in ("Conv3d_1a_7x7", "MaxPool3d_2a_3x3", "Conv3d_2c_3x3", "Mixed_3b", "Mixed_3c", "Mixed_4b", "Mixed_4f",
+                 "Mixed_5c"):
+        e = rel_err(eng.acts[name].ncdhw().cpu(), outs[name])
+        assert e < (2e-2 if mode == "bf16" else 1e-4), (name, e)
+    assert rel_err(probs, want) < TOL[mode], rel_err(probs, want)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("perturb", ["freeze", "reverse"])
+def test_class_gradient_wrt_mask_small(dev, small_setup, mode, perturb):
+    """d p[target] / d mask in isolation (the regulariser must not hide conv backward)."""
+    from oracle import i3d_oracle, mask_oracle
+    sds, x = small_setup
+    g = torch.Generator().manual_seed(5)
+    masks = torch.rand((3, 16), generator=g)
+    targets = torch.tensor([0, 3, 17])
+    eng = make_engine(sds, 3, mode, dev, **SMALL)
+    eng.set_input(x.to(dev))
+    eng.set_targets(targets)
+    probs = eng.forward(masks.to(dev), perturb).clone().cpu()
+    dm = eng.backward().clone().cpu()
+    for i in range(3):
+        mi = masks[i].clone().requires_grad_()
+        out = i3d_oracle.forward(sds, mask_oracle.perturb_sequence(x[i:i + 1], mi, perturb), SMALL["avg_pool"])
+        p = out[0, targets[i]]
+        (gm,) = torch.autograd.grad(p, mi)
+        assert abs(float(probs[i, targets[i]]) - float(p)) < TOL[mode] * max(abs(float(p)), 1e-3)
+        assert float(gm.abs().max()) > 1e-6, "degenerate class gradient; sharpening failed"
+        e = rel_err(dm[i], gm)
+        assert e < (3e-2 if mode == "bf16" else 2e-4), (i, e)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_geometry_against_golden(dev, full_setup, mode):
+    """16x224x224 (config C2 geometry): probabilities and class gradient vs the reference's golden."""
+    g = np.load(os.path.join(GOLD, "i3d_smth.npz"))
+    sd, sds, x2 = full_setup
+    eng = make_engine(sd, 2, mode, dev, clip=(16, 224, 224), avg_pool=(2, 7, 7))
+    eng.set_input(x2.to(dev))
+    p_def = eng.forward(None).clone().cpu().numpy()
+    np.testing.assert_allclose(p_def, g["probs_default"], rtol=TOL[mode] * 2, atol=1e-6)
+    eng = None
+    torch.cuda.empty_cache()
+    eng = make_engine(sds, 2, mode, dev, clip=(16, 224, 224), avg_pool=(2, 7, 7))
+    eng.set_input(x2.to(dev))
+    p = eng.forward(None).clone().cpu().numpy()
+    assert rel_err(p, g["probs_sharp"]) < TOL[mode] * 3
+    tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4)
+    sig = torch.sigmoid(tm)
+    eng.set_targets(torch.tensor([0, 3]))
+    eng.forward(sig.to(dev), "freeze")
+    dm = eng.backward().clone().cpu()
+    for bi in (0, 1):
+        ref = torch.from_numpy(g["classgrad_%d" % bi])  # w.r.t. the RAW mask: chain through sigmoid'
+        got = dm[bi] * sig * (1 - sig)
+        assert rel_err(got, ref) < (5e-2 if mode == "bf16" else 1e-3), (bi, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_mask_search_trajectory_50_iterations(dev, small_setup, mode):
+    """50 iterations of the search vs the oracle loop: class-gradient trajectory, masks, final IoU."""
+    from interpreting_video_features_b200.search import MaskSearch
+    from oracle import i3d_oracle, mask_oracle
+    sds, x = small_setup
+    targets = torch.tensor([3, 3, 40])
+    raw0 = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4).repeat(3, 1)
+    raw0[2] = torch.tensor([5.] * 16)
+    raw0[2, :2] = -5.0
+    eng = make_engine(sds, 3, mode, dev, **SMALL)
+    ms = MaskSearch(eng, lam1=0.01, lam2=0.02, n_iter=50, perturb="freeze", use_graph=True)
+    rec = {}
+    res = ms.run(x.to(dev), targets, raw_masks=raw0.to(dev), record=rec)
+    model = i3d_oracle.Model(sds, SMALL["avg_pool"], True)
+    for i in range(3):
+        tm = raw0[i].clone().requires_grad_()
+        r = {}
+        final, cls = mask_oracle.mask_search(x[i:i + 1], model, 0, [int(targets[i])], tm, 0.01, 0.02, 50, record=r)
+        got_final = res["time_mask"][i].cpu()
+        # frame-wise IoU at 0.5
+        a, b = got_final > 0.5, final > 0.5
+        iou = float((a & b).sum()) / max(float((a | b).sum()), 1.0)
+        assert iou >= 0.95, (i, iou)
+        for it in (0, 1, 2, 5, 10, 25, 49):
+            s_ref = torch.sigmoid(r["mask"][it - 1]) if it > 0 else torch.sigmoid(raw0[i])
+            g_raw = rec["dm_class"][it][i].cpu() * s_ref * (1 - s_ref)
+            # reference grad = regulariser + class term; isolate the class term with the oracle's own closed form
+            tmr = (r["mask"][it - 1] if it > 0 else raw0[i]).clone().requires_grad_()
+            sr = torch.sigmoid(tmr)
+            reg = 0.01 * sr.abs().sum() + 0.02 * mask_oracle.calc_tv_norm(sr, 3, 3)
+            (g_reg,) = torch.autograd.grad(reg, tmr)
+            g_cls_ref = r["grad"][it] - g_reg
+            if float(g_cls_ref.abs().max()) > 1e-7:
+                assert rel_err(g_raw, g_cls_ref) < (0.1 if mode == "bf16" else 5e-3), (i, it, rel_err(g_raw, g_cls_ref))
+        tol = 5e-2 if mode == "bf16" else 2e-3
+        assert float((rec["mask"][49][i].cpu() - r["mask"][49]).abs().max()) < tol * 10
+        assert abs(float(res["freeze_score"][i]) - cls) < max(TOL[mode] * 5 * abs(cls), 1e-4)
+
+
+def test_graph_replay_equals_eager(dev, small_setup):
+    from interpreting_video_features_b200.search import MaskSearch
+    sds, x = small_setup
+    targets = torch.tensor([3, 3, 40])
+    out = []
+    for use_graph in (False, True):
+        eng = make_engine(sds, 3, "bf16", dev, **SMALL)
+        res = MaskSearch(eng, n_iter=8, use_graph=use_graph).run(x.to(dev), targets)
+        out.append(res)
+    assert torch.equal(out[0]["init_mask"], out[1]["init_mask"])
+    torch.testing.assert_close(out[0]["time_mask"], out[1]["time_mask"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out[0]["reverse_score"], out[1]["reverse_score"], rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_init_mask_central_matches_oracle(dev, small_setup, mode):
+    from interpreting_video_features_b200.search import MaskSearch
+    from oracle import i3d_oracle, mask_oracle
+    sds, x = small_setup
+    targets = torch.tensor([3, 3, 40])
+    eng = make_engine(sds, 3, mode, dev, **SMALL)
+    eng.set_input(x.to(dev))
+    raw, _ = MaskSearch(eng).init_masks(targets)
+    model = i3d_oracle.Model(sds, SMALL["avg_pool"], True)
+    for i in range(3):
+        want = mask_oracle.init_mask(x[i:i + 1], model, 0, [int(targets[i])]).detach()
+        assert torch.equal(raw[i].cpu(), want), (i, raw[i].cpu(), want)
+
+
+def test_dropin_reference_style_loop(dev, full_setup):
+    """The reference's own loop (pt/FindMasksComparison_I3D_smth.py:191-214) written against the drop-in
+    modules, stock torch.optim.Adam on a leaf mask — three iterations vs the reference's golden."""
+    import torch.nn as nn
+    from interpreting_video_features_b200.pt import mask
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    g = np.load(os.path.join(GOLD, "i3d_smth.npz"))
+    _, sds, x2 = full_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sds)
+    model = nn.DataParallel(model, device_ids=[0]).to(dev).eval()  # the drivers wrap it (smth.py:61)
+    model.module.set_mode("fp32")
+    xd = x2.to(dev)
+    tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, device=dev, requires_grad=True)
+    opt = torch.optim.Adam([tm], lr=0.2)
+    losses = []
+    for _ in range(3):
+        mc = torch.sigmoid(tm)
+        loss = 0.01 * torch.sum(torch.abs(mc)) + 0.02 * mask.calc_tv_norm(mc, p=3, q=3) + \
+            model(mask.perturb_sequence(xd, mc, perturbation_type='freeze'))[0, 3]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    np.testing.assert_allclose(losses, g["iter3_losses"], rtol=1e-3)
+    np.testing.assert_allclose(torch.sigmoid(tm).detach().cpu().numpy(), g["iter3_mask"], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_gradcam_i3d_dropin(dev, full_setup, mode):
+    from interpreting_video_features_b200.pt.grad_cam_videos import GradCamVideo
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    from oracle import gradcam_oracle
+    g = np.load(os.path.join(GOLD, "gradcam_i3d.npz"))
+    _, sds, x2 = full_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sds)
+    model = model.to(dev).eval().set_mode(mode)
+    gc = GradCamVideo(model=model, target_layer_names=['Mixed_5c'], class_dict=None, use_cuda=True,
+                      input_spatial_size=(224, 224), normalizePerFrame=True, archType="I3D")
+    cam, out = gc(x2[1:2].to(dev), None)
+    assert cam.shape == (16, 224, 224) and cam.dtype == np.float32
+    assert rel_err(out.cpu(), g["output_argmax"]) < TOL[mode] * 3
+    want, _, _ = gradcam_oracle.gradcam_i3d(sds, x2[1:2], None, (224, 224), True)
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(cam), np.isnan(want))
+    assert np.abs(cam[ok] - want[ok]).max() < (5e-2 if mode == "bf16" else 1e-3)
+    samp = cam[::8, ::16, ::16]
+    gk = ~np.isnan(g["cam_sample_argmax"])
+    assert np.abs(samp[gk] - g["cam_sample_argmax"][gk]).max() < (5e-2 if mode == "bf16" else 2e-3)
+    # an all-zero slice gives NaN exactly as the reference does (class 3 on clip 0)
+    cam3, _ = gc(x2[:1].to(dev), 3)
+    want3, _, _ = gradcam_oracle.gradcam_i3d(sds, x2[:1], 3, (224, 224), True)
+    if mode == "fp32":
+        assert np.array_equal(np.isnan(cam3), np.isnan(want3))
+
+
+def test_sharded_search_equals_single(dev, small_setup):
+    """Clip-parallel sharding: ranks' shards put back in clip order == one rank."""
+    from interpreting_video_features_b200 import search
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    sds, x = small_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sds)
+    model = model.to(dev).eval()
+    model.avg_pool.kernel_size = [2, 2, 2]
+    clips = torch.cat([x, x.flip(0)])[:5]  # 5 clips: ragged against micro_batch 2
+    targets = torch.tensor([3, 3, 40, 40, 3])
+    full = search.find_masks_batched(model, clips, targets, n_iter=6, micro_batch=2)
+    parts = [search.find_masks_batched(model, clips, targets, n_iter=6, micro_batch=2, rank=r, world=2) for r in (0, 1)]
+    merged = torch.zeros_like(full["time_mask"])
+    for r in (0, 1):
+        merged[search.shard_indices(5, r, 2)] = parts[r]["time_mask"]
+    torch.testing.assert_close(merged, full["time_mask"], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,422 @@
+"""GPU (-m gpu): every libivf kernel through the C ABI against the oracle / plain torch fp32 on the
+same seeded inputs.  fp32 kernels: 1e-4; bf16 tensor-core kernels: 1e-2 relative (the north star's
+tolerances), bit-exact for index work (max-pool argmax)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import GOLD, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from interpreting_video_features_b200 import _lib
+    _lib.handle()  # raises if libivf.so is missing: the CUDA path is the only path
+    return torch.device("cuda")
+
+
+def to_act(x, dtype):
+    from interpreting_video_features_b200.ops import Act
+    n, c, d, h, w = x.shape
+    return Act(x.permute(0, 2, 3, 4, 1).to(dtype).contiguous(), n, d, h, w, c, 0, c)
+
+
+def ref_conv(x, w, stride, pf, out_dhw):
+    """fp32 CPU reference of the generalised conv with explicit front pads and given output size."""
+    pads = []
+    for size, k, s, p, o in zip(x.shape[2:], w.shape[2:], stride, pf, out_dhw):
+        back = (o - 1) * s + k - size - p
+        pads.append((p, back))
+    (tf, tb), (hf, hb), (wf, wb) = pads
+    xp = F.pad(x, (wf, max(wb, 0), hf, max(hb, 0), tf, max(tb, 0)))
+    if wb < 0:
+        xp = xp[..., :wb]
+    if hb < 0:
+        xp = xp[..., :hb, :]
+    if tb < 0:
+        xp = xp[:, :, :tb]
+    return F.conv3d(xp, w, stride=stride)
+
+
+# ----------------------------------------------------------------------------- TMA im2col probe
+@pytest.mark.parametrize("cfg", [
+    dict(n=2, c=64, dhw=(4, 6, 10), k=(3, 3, 3), pf=(1, 1, 1), m0=0, tap=0),
+    dict(n=2, c=64, dhw=(4, 6, 10), k=(3, 3, 3), pf=(1, 1, 1), m0=128, tap=13),
+    dict(n=2, c=64, dhw=(4, 6, 10), k=(3, 3, 3), pf=(1, 1, 1), m0=384, tap=26),
+    dict(n=3, c=32, dhw=(2, 7, 7), k=(3, 3, 3), pf=(1, 1, 1), m0=128, tap=5),
+    dict(n=2, c=16, dhw=(3, 5, 9), k=(1, 1, 1), pf=(0, 0, 0), m0=128, tap=0),
+    dict(n=1, c=32, dhw=(4, 8, 8), k=(4, 4, 4), pf=(1, 1, 1), m0=128, tap=63),
+    dict(n=1, c=24, dhw=(4, 8, 8), k=(4, 4, 4), pf=(2, 2, 2), m0=0, tap=0),
+])
+def test_im2col_tma_tile(dev, cfg):
+    """What the conv kernel's TMA stages for (tile m0, filter tap) == the im2col definition."""
+    from interpreting_video_features_b200 import _lib, ops
+    n, c, (d, h, w) = cfg["n"], cfg["c"], cfg["dhw"]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(-8, 9, (n, c, d, h, w), generator=g).float()
+    xa = to_act(x.to(dev), torch.bfloat16)
+    k, pf = cfg["k"], cfg["pf"]
+    tile = ops.probe_im2col(xa, k, (1, 1, 1), pf, (d, h, w), cfg["m0"], cfg["tap"], 0).float().cpu()
+    kch = _lib.load().ivf_conv_bf16_kchunk(c)
+    kw_i = cfg["tap"] % k[2]
+    kh_i = (cfg["tap"] // k[2]) % k[1]
+    kd_i = cfg["tap"] // (k[2] * k[1])
+    want = torch.zeros(128, kch)
+    M = n * d * h * w
+    for r in range(128):
+        m = cfg["m0"] + r
+        if m >= M:
+            continue
+        ow, t = m % w, m // w
+        oh, t = t % h, t // h
+        od, nn = t % d, t // d
+        zd, zh, zw = od - pf[0] + kd_i, oh - pf[1] + kh_i, ow - pf[2] + kw_i
+        if 0 <= zd < d and 0 <= zh < h and 0 <= zw < w:
+            want[r, :min(c, kch)] = x[nn, :kch, zd, zh, zw]
+    rows_ok = [r for r in range(128) if cfg["m0"] + r < M]
+    bad = [r for r in rows_ok if not torch.equal(tile[r], want[r])]
+    assert not bad, "im2col rows differ: %s\n got %s\n want %s" % (bad[:8], tile[bad[0]][:8], want[bad[0]][:8])
+
+
+# ----------------------------------------------------------------------------- convolution
+CONV_CASES = [
+    # n, cin, cout, dhw, kernel, stride, note
+    (2, 64, 64, (3, 9, 10), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 192, (4, 12, 12), (3, 3, 3), (1, 1, 1)),
+    (2, 16, 48, (2, 7, 7), (3, 3, 3), (1, 1, 1)),
+    (2, 24, 64, (2, 7, 7), (3, 3, 3), (1, 1, 1)),
+    (1, 96, 208, (4, 14, 14), (3, 3, 3), (1, 1, 1)),
+    (1, 112, 288, (2, 7, 7), (3, 3, 3), (1, 1, 1)),
+    (2, 832, 384, (2, 7, 7), (1, 1, 1), (1, 1, 1)),
+    (1, 480, 16, (4, 14, 14), (1, 1, 1), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward_bn_relu(dev, mode, case):
+    from interpreting_video_features_b200 import _lib, engine, ops
+    from interpreting_video_features_b200.ops import Act, same_pad
+    n, cin, cout, dhw, k, s = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn((n, cin) + dhw, generator=g)
+    w = torch.randn((cout, cin) + k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    if mode == "bf16":
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    geo = [same_pad(sz, kk, ss) for sz, kk, ss in zip(dhw, k, s)]
+    pf, out_dhw = tuple(g_[0] for g_ in geo), tuple(g_[2] for g_ in geo)
+    ref = F.relu(ref_conv(x, w, s, pf, out_dhw) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    xa = to_act(x.to(dev), dt)
+    # write into a channel slice of a wider buffer (the Inception concat path)
+    wide = Act.empty(n, *out_dhw, cout + 16, dt, dev, zero=True)
+    out = wide.slice(8, cout)
+    ops.conv3d(xa, engine.pack_fwd(w.to(dev), mode), out, k, s, pf, flags=_lib.EP_RELU, scale=scale.to(dev),
+               shift=shift.to(dev))
+    torch.cuda.synchronize()
+    got = out.ncdhw().cpu()
+    tol = 1e-2 if mode == "bf16" else 1e-4
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
+    # neighbours of the slice untouched
+    assert float(wide.tensor()[..., :8].float().abs().max()) == 0.0
+    assert float(wide.tensor()[..., 8 + cout:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES[:6])
+def test_conv_data_gradient_with_fused_mask_and_accumulate(dev, mode, case):
+    """dX = (acc + conv_dgrad(dZ)) * 1[y_prev>0] * scale_prev — what the backward pass launches."""
+    from interpreting_video_features_b200 import engine, ops
+    from interpreting_video_features_b200.ops import same_pad
+    n, cin, cout, dhw, k, s = case
+    g = torch.Generator().manual_seed(7 + hash(case) % 1000)
+    x = torch.randn((n, cin) + dhw, generator=g, requires_grad=True)
+    w = torch.randn((cout, cin) + k, generator=g) / (cout * k[0] * k[1] * k[2]) ** 0.5
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    if mode == "bf16":
+        w = w.bfloat16().float()
+    geo = [same_pad(sz, kk, ss) for sz, kk, ss in zip(dhw, k, s)]
+    pf, out_dhw = tuple(g_[0] for g_ in geo), tuple(g_[2] for g_ in geo)
+    y = ref_conv(x, w, s, pf, out_dhw)
+    dz = torch.randn(y.shape, generator=g)
+    if mode == "bf16":
+        dz = dz.bfloat16().float()
+    (gx,) = torch.autograd.grad(y, x, dz)
+    y_prev = torch.randn(x.shape, generator=g)
+    acc = torch.randn(x.shape, generator=g) * 0.1
+    sc_prev = torch.rand(cin, generator=g) + 0.5
+    ref = (gx + acc) * (y_prev > 0).float() * sc_prev.view(1, -1, 1, 1, 1)
+    dza = to_act(dz.to(dev), dt)
+    ya = to_act(y_prev.to(dev), dt)
+    acc_a = to_act(acc.to(dev), torch.float32)
+    gxa = to_act(torch.zeros_like(y_prev).to(dev), dt)
+    wd = engine.pack_dgrad(w.to(dev), mode)
+    if mode == "fp32":
+        ops.conv3d(dza, wd, gxa, k, s, pf, acc_in=acc_a, mask=ya, mask_scale=sc_prev.to(dev), transposed=1)
+    else:
+        pfd = tuple(kk - 1 - p for kk, p in zip(k, pf))
+        ops.conv3d(dza, wd, gxa, k, (1, 1, 1), pfd, acc_in=acc_a, mask=ya, mask_scale=sc_prev.to(dev))
+    torch.cuda.synchronize()
+    tol = 1e-2 if mode == "bf16" else 1e-4
+    assert rel_err(gxa.ncdhw().cpu(), ref) < tol
+
+
+def test_conv_fp32_strided_stem_and_its_gradient(dev):
+    """The 7x7x7 stride-2 stem in fp32 mode (true strided gather, transposed data-gradient)."""
+    from interpreting_video_features_b200 import _lib, engine, ops
+    from interpreting_video_features_b200.ops import Act, same_pad
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((1, 3, 8, 20, 18), generator=g, requires_grad=True)
+    w = torch.randn((16, 3, 7, 7, 7), generator=g) * 0.05
+    geo = [same_pad(sz, 7, 2) for sz in x.shape[2:]]
+    pf, od = tuple(q[0] for q in geo), tuple(q[2] for q in geo)
+    y = ref_conv(x, w, (2, 2, 2), pf, od)
+    dz = torch.randn(y.shape, generator=g)
+    (gx,) = torch.autograd.grad(y, x, dz)
+    xa = to_act(x.detach().to(dev), torch.float32)
+    out = Act.empty(1, *od, 16, torch.float32, dev)
+    ops.conv3d(xa, engine.pack_fwd(w.to(dev), "fp32"), out, (7, 7, 7), (2, 2, 2), pf)
+    assert rel_err(out.ncdhw().cpu(), y.detach()) < 1e-4
+    gxa = Act.empty(1, 8, 20, 18, 3, torch.float32, dev)
+    ops.conv3d(to_act(dz.to(dev), torch.float32), engine.pack_dgrad(w.to(dev), "fp32"), gxa, (7, 7, 7), (2, 2, 2),
+               pf, transposed=1)
+    assert rel_err(gxa.ncdhw().cpu(), gx) < 1e-4
+
+
+def test_conv_bf16_space_to_depth_stem(dev):
+    """bf16 stem: stride-2 7x7x7 presented as a stride-1 4x4x4 conv over the space-to-depth clip,
+    forward and data gradient, against the true strided convolution."""
+    from interpreting_video_features_b200 import _lib, engine, ops
+    from interpreting_video_features_b200.ops import Act
+    g = torch.Generator().manual_seed(5)
+    b, t, h, w_ = 2, 8, 24, 20
+    x = (torch.rand((b, 3, t, h, w_), generator=g) * 255).bfloat16().float()
+    w = (torch.randn((64, 3, 7, 7, 7), generator=g) * 0.01).bfloat16().float()
+    xr = x.clone().requires_grad_()
+    y = F.conv3d(F.pad(xr, (2, 3, 2, 3, 2, 3)), w, stride=2)
+    dz = torch.randn(y.shape, generator=g).bfloat16().float()
+    (gx,) = torch.autograd.grad(y, xr, dz)
+    # clip -> s2d operand via the perturb kernel with a zero mask (P == x)
+    xin = Act.empty(b, t // 2, h // 2, w_ // 2, 32, torch.bfloat16, dev, zero=True)
+    ops.perturb_fwd(x.to(dev), torch.zeros(t, device=dev), "freeze", _lib.PFMT_S2D_BF16, xin.buf)
+    sd = {"u.conv3d.weight": w}
+    unit = engine.Unit(sd, "u", (2, 2, 2), "bf16", dev, s2d=True)
+    out = Act.empty(b, t // 2, h // 2, w_ // 2, 64, torch.bfloat16, dev)
+    ops.conv3d(xin.slice(0, 24), unit.w_fwd, out, (4, 4, 4), (1, 1, 1), (1, 1, 1))
+    assert rel_err(out.ncdhw().cpu(), y.detach()) < 1e-2
+    gin = Act.empty(b, t // 2, h // 2, w_ // 2, 32, torch.bfloat16, dev, zero=True)
+    ops.conv3d(to_act(dz.to(dev), torch.bfloat16), unit.w_dgrad, gin.slice(0, 24), (4, 4, 4), (1, 1, 1), (2, 2, 2))
+    gs = gin.tensor()[..., :24].float().cpu().view(b, t // 2, h // 2, w_ // 2, 2, 2, 2, 3)
+    got = gs.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(b, 3, t, h, w_)
+    assert rel_err(got, gx) < 1e-2
+
+
+# ----------------------------------------------------------------------------- max-pool
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [((1, 3, 3), (1, 2, 2), (4, 13, 12), 64), ((3, 3, 3), (2, 2, 2), (5, 9, 10), 40),
+                                  ((2, 2, 2), (2, 2, 2), (4, 7, 6), 24), ((3, 3, 3), (1, 1, 1), (2, 7, 7), 48),
+                                  ((3, 3, 3), (1, 1, 1), (3, 5, 4), 6)])
+def test_maxpool_same_zero_padding(dev, dt, case):
+    from interpreting_video_features_b200 import ops
+    from interpreting_video_features_b200.ops import Act, same_pad
+    from oracle import i3d_oracle
+    k, s, dhw, c = case
+    g = torch.Generator().manual_seed(11)
+    # mix of negatives and zeros so that padded zeros and ties take part (post-ReLU maps are like this)
+    x = torch.randn((2, c) + dhw, generator=g)
+    x = torch.where(torch.rand(x.shape, generator=g) < 0.4, torch.zeros_like(x), x)
+    x = x.to(dt).float().requires_grad_()
+    y = i3d_oracle.maxpool_same(x, k, s)
+    gy = torch.randn(y.shape, generator=g).to(dt).float()
+    (gx,) = torch.autograd.grad(y, x, gy)
+    geo = [same_pad(sz, kk, ss) for sz, kk, ss in zip(dhw, k, s)]
+    pf, od = tuple(q[0] for q in geo), tuple(q[2] for q in geo)
+    xa = to_act(x.detach().to(dev), dt)
+    out = Act.empty(2, *od, c, dt, dev)
+    am = torch.empty((out.pixels, c), dtype=torch.uint8, device=dev)
+    ops.maxpool3d_fwd(xa, out, am, k, s, pf)
+    assert torch.equal(out.ncdhw().cpu(), y.detach()), "max-pool forward must be exact"
+    gxa = xa.like(zero=True)
+    ops.maxpool3d_bwd(to_act(gy.to(dev), dt), am, gxa, k, s, pf)
+    torch.testing.assert_close(gxa.ncdhw().cpu(), gx.to(dt).float(), rtol=2e-2 if dt == torch.bfloat16 else 1e-6,
+                               atol=2e-2 if dt == torch.bfloat16 else 1e-6)
+
+
+# ----------------------------------------------------------------------------- head
+@pytest.mark.parametrize("softmax", [True, False])
+def test_head_forward_backward(dev, softmax):
+    from interpreting_video_features_b200 import ops
+    from interpreting_video_features_b200.ops import Act
+    g = torch.Generator().manual_seed(2)
+    feat = torch.rand((3, 1024, 2, 7, 7), generator=g, requires_grad=True)
+    w = torch.randn((174, 1024), generator=g) * 0.2
+    b = torch.randn(174, generator=g) * 0.1
+    logits = F.linear(feat.mean(dim=(2, 3, 4)), w, b)
+    out = F.softmax(logits, dim=1) if softmax else logits
+    dout = torch.randn(out.shape, generator=g)
+    (gf,) = torch.autograd.grad(out, feat, dout)
+    fa = to_act(feat.detach().to(dev), torch.float32)
+    o = torch.empty((3, 174), device=dev)
+    ops.head_fwd(fa, w.to(dev), b.to(dev), softmax, o)
+    assert rel_err(o.cpu(), out.detach()) < 1e-5
+    dfa = fa.like()
+    ops.head_bwd(dfa, w.to(dev), softmax, o, dout.to(dev))
+    assert rel_err(dfa.ncdhw().cpu(), gf) < 1e-4
+
+
+# ----------------------------------------------------------------------------- perturb
+@pytest.mark.parametrize("mode", ["freeze", "reverse"])
+def test_perturb_known_answers_and_random(dev, mode):
+    from interpreting_video_features_b200 import _lib, ops
+    from oracle import mask_oracle
+    k = np.load(os.path.join(GOLD, "mask_kats.npz"))
+    xs = torch.from_numpy(k["rand_x"])
+    m = torch.from_numpy(k["rand_%s_mask" % mode])
+    out = torch.empty_like(xs, device=dev)
+    ops.perturb_fwd(xs.to(dev), m.to(dev), mode, _lib.PFMT_NCDHW_F32, out)
+    np.testing.assert_allclose(out.cpu().numpy(), k["rand_%s_out" % mode], rtol=1e-6, atol=1e-4)
+    dm = torch.empty((2, 12), device=dev)
+    ops.perturb_bwd(xs.to(dev), m.to(dev), mode, _lib.PFMT_NCDHW_F32, torch.from_numpy(k["rand_%s_gout" % mode]).to(dev), dm)
+    np.testing.assert_allclose(dm.sum(0).cpu().numpy(), k["rand_%s_dmask" % mode], rtol=1e-4, atol=1e-2)
+    # RNG-free known answers of SURVEY §4.3
+    if mode == "freeze":
+        x = torch.arange(16.).reshape(2, 1, 4, 1, 2)
+        o = torch.empty_like(x, device=dev)
+        ops.perturb_fwd(x.to(dev), torch.tensor([.9, .5, 1, .25], device=dev), mode, _lib.PFMT_NCDHW_F32, o)
+        assert o.flatten().tolist() == [0, 1, 1, 2, 1, 2, 4.75, 5.75, 8, 9, 9, 10, 9, 10, 12.75, 13.75]
+    else:
+        xr = torch.tensor([0., 10, 20, 30, 40, 50]).reshape(1, 1, 6, 1, 1)
+        for mr, want in (([0, .5, 1, .2, .05, .8], [0, 20, 20, 20, 40, 50]),
+                         ([.6, .5, 1, .2, .3, .05], [24, 20, 20, 20, 16, 50])):
+            o = torch.empty_like(xr, device=dev)
+            ops.perturb_fwd(xr.to(dev), torch.tensor(mr, device=dev), mode, _lib.PFMT_NCDHW_F32, o)
+            np.testing.assert_allclose(o.flatten().cpu().numpy(), want, rtol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["freeze", "reverse"])
+@pytest.mark.parametrize("fmt", ["ndhwc", "s2d_bf16", "s2d_f32grad"])
+def test_perturb_formats_per_clip_masks(dev, mode, fmt):
+    """Per-clip masks [B,T], the NDHWC fp32 and space-to-depth bf16 layouts, forward and dmask."""
+    from interpreting_video_features_b200 import _lib, ops
+    from oracle import mask_oracle
+    g = torch.Generator().manual_seed(9)
+    b, t, h, w = 3, 16, 12, 20
+    x = torch.rand((b, 3, t, h, w), generator=g) * 255
+    masks = torch.rand((b, t), generator=g)
+    gout = torch.randn((b, 3, t, h, w), generator=g)
+    ref_out, ref_dm = [], []
+    for i in range(b):
+        mi = masks[i].clone().requires_grad_()
+        o = mask_oracle.perturb_sequence(x[i:i + 1], mi, mode)
+        (gm,) = torch.autograd.grad((o * gout[i:i + 1]).sum(), mi)
+        ref_out.append(o.detach())
+        ref_dm.append(gm)
+    ref_out, ref_dm = torch.cat(ref_out), torch.stack(ref_dm)
+    xd, md = x.to(dev), masks.to(dev)
+    dm = torch.empty((b, t), device=dev)
+    if fmt == "ndhwc":
+        out = torch.empty((b, t, h, w, 3), device=dev)
+        ops.perturb_fwd(xd, md, mode, _lib.PFMT_NDHWC_F32, out)
+        torch.testing.assert_close(out.permute(0, 4, 1, 2, 3).cpu(), ref_out, rtol=1e-6, atol=1e-4)
+        ops.perturb_bwd(xd, md, mode, _lib.PFMT_NDHWC_F32, gout.permute(0, 2, 3, 4, 1).contiguous().to(dev), dm)
+        assert rel_err(dm.cpu(), ref_dm) < 1e-4
+    else:
+        out = torch.zeros((b, t // 2, h // 2, w // 2, 32), dtype=torch.bfloat16, device=dev)
+        ops.perturb_fwd(xd, md, mode, _lib.PFMT_S2D_BF16, out)
+        o = out[..., :24].float().cpu().view(b, t // 2, h // 2, w // 2, 2, 2, 2, 3)
+        o = o.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(b, 3, t, h, w)
+        assert rel_err(o, ref_out) < 4e-3  # bf16 rounding of the stored operand
+        assert float(out[..., 24:].float().abs().max()) == 0.0
+        gs = gout.view(b, 3, t // 2, 2, h // 2, 2, w // 2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(
+            b, t // 2, h // 2, w // 2, 24)
+        gs = torch.cat([gs, torch.zeros(b, t // 2, h // 2, w // 2, 8)], dim=-1).contiguous()
+        if fmt == "s2d_bf16":
+            gsd = gs.bfloat16()
+            tol = 1e-2
+        else:
+            gsd, tol = gs, 1e-4
+        ops.perturb_bwd(xd, md, mode, _lib.PFMT_S2D_BF16, gsd.to(dev), dm)
+        assert rel_err(dm.cpu(), ref_dm) < tol
+
+
+# ----------------------------------------------------------------------------- loss + Adam
+def test_mask_loss_adam_matches_torch(dev):
+    from interpreting_video_features_b200 import ops
+    from oracle import mask_oracle
+    g = torch.Generator().manual_seed(4)
+    nclip, t = 5, 16
+    m0 = torch.randn((nclip, t), generator=g) * 3
+    dclass = torch.randn((20, nclip, t), generator=g) * 1e-3
+    lam1, lam2 = 0.01, 0.02
+    ref_m = []
+    for c in range(nclip):
+        p = m0[c].clone().requires_grad_()
+        opt = torch.optim.Adam([p], lr=0.2)
+        for it in range(20):
+            s = torch.sigmoid(p)
+            loss = lam1 * s.abs().sum() + lam2 * mask_oracle.calc_tv_norm(s, 3, 3) + (s * dclass[it, c]).sum()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        ref_m.append(p.detach())
+    ref_m = torch.stack(ref_m)
+    m = m0.clone().to(dev)
+    ea, es = torch.zeros_like(m), torch.zeros_like(m)
+    step = torch.zeros(nclip, dtype=torch.int32, device=dev)
+    sig = torch.empty_like(m)
+    losses = torch.empty((nclip, 3), device=dev)
+    for it in range(20):
+        ops.mask_loss_adam(m, ea, es, dclass[it].to(dev), 0, lam1, lam2, losses=losses, sig_out=sig, step_dev=step)
+    assert step.tolist() == [20] * nclip
+    torch.testing.assert_close(m.cpu(), ref_m, rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(sig.cpu(), torch.sigmoid(ref_m), rtol=1e-3, atol=1e-3)
+
+
+def test_tv_norm_general_pq_and_nan_on_constant_mask(dev):
+    from interpreting_video_features_b200 import ops
+    from oracle import mask_oracle
+    g = torch.Generator().manual_seed(6)
+    for p, q in ((3, 3), (2, 3), (3, 1)):
+        m = torch.rand(16, generator=g, requires_grad=True)
+        v = mask_oracle.calc_tv_norm(m, p, q)
+        (gm,) = torch.autograd.grad(v, m)
+        val = torch.empty(1, device=dev)
+        dm = torch.empty(16, device=dev)
+        ops.tv_norm(m.detach().to(dev), p, q, val, dm)
+        assert abs(float(val) - float(v)) < 1e-4 * max(1.0, abs(float(v)))
+        assert rel_err(dm.cpu(), gm) < 1e-3
+    m = torch.full((16,), 0.3, requires_grad=True)
+    (gm,) = torch.autograd.grad(mask_oracle.calc_tv_norm(m, 3, 3), m)
+    val = torch.empty(1, device=dev)
+    dm = torch.empty(16, device=dev)
+    ops.tv_norm(m.detach().to(dev), 3, 3, val, dm)
+    assert float(val) == 0.0 and bool(torch.isnan(gm).all()) and bool(torch.isnan(dm).all())
+
+
+# ----------------------------------------------------------------------------- Grad-CAM tail
+@pytest.mark.parametrize("per_frame", [True, False])
+@pytest.mark.parametrize("geom", [((2, 7, 7), 16, (224, 224)), ((4, 4, 5), 32, (160, 120))])
+def test_gradcam_fused_kernel(dev, per_frame, geom):
+    from interpreting_video_features_b200 import ops
+    from oracle import gradcam_oracle
+    (tp, hp, wp), clip, size = geom
+    g = torch.Generator().manual_seed(8)
+    c = 1024
+    act = torch.rand((2, c, tp, hp, wp), generator=g)
+    grad = torch.randn((2, c, tp, hp, wp), generator=g) * 1e-3
+    cam = torch.empty((2, clip, size[1], size[0]), device=dev)
+    low = torch.empty((2, tp, hp, wp), device=dev)
+    ops.gradcam(to_act(act.to(dev), torch.float32), to_act(grad.to(dev), torch.float32), clip // tp, size[1], size[0],
+                per_frame, cam, low)
+    for i in range(2):
+        want, want_low = gradcam_oracle.cam_from_features(act[i].numpy(), grad[i:i + 1].numpy(), clip, size, per_frame)
+        np.testing.assert_allclose(low[i].cpu().numpy(), want_low, rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(cam[i].cpu().numpy(), want, rtol=1e-3, atol=2e-5)
