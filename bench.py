@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — mask-search throughput of the hot path (BASELINE.json metric, config C2).
+
+One STEP = one temporal-mask-search iteration for a micro-batch of 8 synthetic 16x224x224 clips
+(BASELINE.json configs[1]: I3D Something-Something-v2, 174 classes, freeze perturbation):
+perturb -> I3D forward -> head -> head' -> I3D data-gradient -> perturb' -> L1/TV loss + Adam, for 8
+independent (clip, mask) pairs = 8 clip-iterations.  Metric: clip-iterations/s, whole job over all
+ranks (weak scaling: every rank owns 8 clips; no collective inside the search).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bf16|fp32]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+
+value   : inputs resident in HBM, K CUDA-graph replays timed with CUDA events (max over ranks)
+e2e     : the public API (search.find_masks_batched) on pinned HOST clips: H2D of the clips, init_mask,
+          300 iterations, reverse score, D2H of the masks — all inside the timed region
+roofline: the tcgen05 convolution kernel: algorithmic conv FLOPs (forward + data gradient, no weight
+          gradient) / summed conv-kernel time measured with CUDA events around every conv launch
+cpu_baseline / --impl reference: the oracle restatement of the reference's PyTorch-CPU path (the
+          reference itself is Python and cannot travel to the GPU box), all host threads.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+CLIPS, T, H, W, NCLS, N_ITER = 8, 16, 224, 224, 174, 300
+METRIC, UNIT = "mask_search_clip_iterations_per_sec", "clip-iterations/s"
+CONFIG = {"workload": "C2: I3D smth (174 classes) temporal-mask search, freeze, batch 8 x 3x16x224x224 "
+                      "synthetic clips, lam 0.01/0.02, Adam lr 0.2; one step = one iteration for the 8 clips",
+          "clips_per_gpu": CLIPS, "clip": [3, T, H, W], "iterations_per_search": N_ITER,
+          "l2": "per-step working set (~1.5 GB of activations for 8 clips) exceeds the 126 MB L2"}
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def state_dict():
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    torch.manual_seed(0)
+    m = quiet(I3D_doubled.Model, NCLS, last_stride=1, stride_mod_layers="", softMax=1).eval()
+    return m
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active")
+                                                          for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step(model_sd, x1, raw, target, opt_state):
+    """One reference mask-search iteration for ONE clip on the CPU (oracle restatement of
+    pt/FindMasksComparison_I3D_smth.py:198-214 with B = 1)."""
+    from oracle import i3d_oracle, mask_oracle
+    tm, opt = opt_state
+    mc = torch.sigmoid(tm)
+    loss = 0.01 * mc.abs().sum() + 0.02 * mask_oracle.calc_tv_norm(mc, 3, 3) + \
+        i3d_oracle.forward(model_sd, mask_oracle.perturb_sequence(x1, mc, "freeze"))[0, target]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return float(loss)
+
+
+def time_cpu_reference(steps, warmup):
+    from oracle import synthetic
+    model = state_dict()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    x1 = synthetic.clips(1)
+    tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, requires_grad=True)
+    st = (tm, torch.optim.Adam([tm], lr=0.2))
+    for _ in range(warmup):
+        cpu_reference_step(sd, x1, None, 3, st)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sd, x1, None, 3, st)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    val, per_step, cores = time_cpu_reference(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CONFIG, sample="one clip-iteration (B=1) per step"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps of one clip-iteration, oracle port of the reference's PyTorch-CPU "
+                                       "path (torch %s, %d threads)" % (args.steps, torch.__version__, cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def conv_time_per_step(eng):
+    """Sum of the convolution kernels' durations in one eager iteration (CUDA events around every conv
+    launch on the launching stream); returns (seconds, launches)."""
+    from interpreting_video_features_b200 import ops
+    events = []
+    orig = ops.conv3d
+
+    def timed(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(*a, **k)
+        e1.record()
+        events.append((e0, e1))
+        return r
+
+    ops.conv3d = timed
+    try:
+        eng.forward(eng._mask, eng._perturb)
+        eng.backward(to_mask=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv3d = orig
+    return sum(a.elapsed_time(b) for a, b in events) * 1e-3, len(events)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from interpreting_video_features_b200 import _lib, search
+    from oracle import i3d_oracle, synthetic  # FLOP count + synthetic clips only (not on the timed path)
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    model = state_dict().to(dev).eval().set_mode(args.mode)
+    sd = model.state_dict()
+    conv_flops = i3d_oracle.conv_flops_per_clip({k: v for k, v in sd.items()}, (T, H, W))  # forward, 2*MAC
+    clips = torch.stack([synthetic.uniform_clip(rank * CLIPS + i) for i in range(CLIPS)])
+    targets = torch.randint(0, NCLS, (CLIPS,), generator=torch.Generator().manual_seed(100 + rank))
+
+    eng = model._engine(clips, batch=CLIPS)
+    ms = search.MaskSearch(eng, 0.01, 0.02, 0.2, N_ITER, "freeze", 0.9, use_graph=True)
+    xd = clips.to(dev)
+    eng.set_input(xd)
+    eng.set_targets(targets)
+    raw = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, device=dev).repeat(CLIPS, 1)
+    ms.m.copy_(raw)
+    from interpreting_video_features_b200 import ops
+    ops.sigmoid(ms.m, ms.sig)
+    ms._capture()
+    launches_per_step = ms.launches_per_iter
+    for _ in range(max(args.warmup - 1, 0)):
+        ms.graph.replay()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ms.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        elapsed = float(t.item())
+    sampler.stop_flag = True
+    value = world * CLIPS * args.steps / elapsed
+
+    # ---- roofline of the convolution kernel (rank 0, eager iteration with per-launch events)
+    conv_s, conv_launches = conv_time_per_step(eng)
+    pk, pk_src = peaks()
+    flops_step = 2.0 * conv_flops * CLIPS  # forward + data gradient, no weight gradient
+    achieved = flops_step / conv_s / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) if args.mode == "bf16" else None
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of a step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if peak else None, "peak_source": pk_src + " (sustained bf16 GEMM)",
+                "traffic": None, "conv_launches_per_step": conv_launches, "conv_ms_per_step": conv_s * 1e3,
+                "algorithmic_gflop_per_clip_iteration": 2.0 * conv_flops / 1e9,
+                "conv_share_of_step": conv_s / (elapsed / args.steps)}
+
+    # ---- end to end through the public API with pinned host clips
+    host = clips.pin_memory()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = search.find_masks_batched(model, host, targets, lam1=0.01, lam2=0.02, n_iter=N_ITER, perturb="freeze",
+                                    micro_batch=CLIPS, device=dev)
+    masks_host = res["time_mask"].cpu()
+    scores_host = res["freeze_score"].cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * CLIPS * N_ITER / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(host.numel() * 4 / N_ITER), "d2h_bytes_per_step": int((masks_host.numel() + scores_host.numel()) * 4 / N_ITER),
+           "h2d_bytes_per_search": int(host.numel() * 4), "seconds_per_search": e2e_s,
+           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + 300 iterations + "
+                   "reverse score + D2H, per rank; step = 1/300 of a search"}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, per, cores = time_cpu_reference(2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2 timed clip-iterations (B=1, 16x224x224) of the oracle port of the reference's "
+                         "PyTorch-CPU path after 1 warm-up, %d threads" % cores}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32",
+            "data": "synthetic", "config": CONFIG, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+            "clocks": sampler.summary()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done;
+  // try_wait suspends in hardware for a bounded time per call; a pipeline bug must not hang the
+  // GPU, so after ~2^24 failed probes (seconds) the CTA traps and the launch reports an error.
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n"
@@ -66,6 +69,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 24)) {
+      printf("libivf: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, parity);
+      __trap();
+    }
   } while (!done);
 }
 

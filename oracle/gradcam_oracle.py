@@ -61,12 +61,12 @@ def cam_from_features(target, grads_val, clip_size, input_spatial_size, normaliz
 
 
 def gradcam_i3d(sd, x, index=None, input_spatial_size=(224, 224), normalize_per_frame=True,
-                avg_pool=(2, 7, 7), softmax=True):
+                avg_pool=(2, 7, 7), softmax=True, quant=False):
     """pt/grad_cam_videos.py:27-43,64-98 for archType 'I3D', target layer Mixed_5c.
     x [1,3,T,H,W]; returns (cam [T,H,W] float32, output [1,classes], lowres cam)."""
     from . import i3d_oracle
 
-    feat, _ = i3d_oracle.features(sd, x)
+    feat, _ = i3d_oracle.features(sd, x, quant=quant)
     feat = feat.detach().requires_grad_(True)
     output = i3d_oracle.head(sd, feat, avg_pool, softmax)
     if index is None:

@@ -24,43 +24,80 @@ def _same_pad(x, kernel, stride):
     return F.pad(x, (wf, wb, hf, hb, tf, tb))
 
 
-def unit3d(sd, prefix, x, stride=(1, 1, 1), relu=True):
+# --- optional bf16 quantisation points ---------------------------------------------------------
+# quant=True restates the SAME network as the mixed-precision computation the bf16 tensor-core path
+# is specified to perform: conv weights and every stored activation rounded to bf16 (fp32
+# accumulation, fp32 BatchNorm affine, fp32 head), and in the backward pass every stored gradient
+# tensor rounded to bf16 (gradient w.r.t. each conv output after ReLU'/BN', w.r.t. pool outputs and
+# w.r.t. the network input); sums over the consumers of a tensor stay fp32.  A random deep ReLU
+# network amplifies ANY perturbation of its features (measured: 0.4 % after the stem, >50 % at
+# Mixed_5c for bf16 rounding alone), so bf16 results are checked against this matched-rounding
+# restatement, and against the plain fp32 oracle only where the north star says so.
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _q(x):
+    """round to bf16 in the forward pass, identity gradient"""
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def quant_input(x):
+    """the bf16 operand the stem convolution reads, with a bf16-stored input gradient"""
+    return _q(_RoundGrad.apply(x))
+
+
+def unit3d(sd, prefix, x, stride=(1, 1, 1), relu=True, quant=False):
     """pt/models/I3D_doubled.py:83-118: pad -> conv3d -> BatchNorm3d(eval, eps 1e-3) -> ReLU."""
     w = sd[prefix + ".conv3d.weight"]
     b = sd.get(prefix + ".conv3d.bias")
+    if quant:
+        w = w.bfloat16().float()
     x = F.conv3d(_same_pad(x, w.shape[2:], stride), w, b, stride=stride)
+    if quant:
+        x = _RoundGrad.apply(x)
     if prefix + ".bn.weight" in sd:
         x = F.batch_norm(x, sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"],
                          sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"], training=False, eps=1e-3)
-    return F.relu(x) if relu else x
+    x = F.relu(x) if relu else x
+    return _q(x) if quant else x
 
 
-def maxpool_same(x, kernel, stride):
-    return F.max_pool3d(_same_pad(x, kernel, stride), kernel, stride)
+def maxpool_same(x, kernel, stride, quant=False):
+    y = F.max_pool3d(_same_pad(x, kernel, stride), kernel, stride)
+    return _RoundGrad.apply(y) if quant else y
 
 
-def inception(sd, name, x):
+def inception(sd, name, x, quant=False):
     """pt/models/I3D_doubled.py:121-146."""
-    b0 = unit3d(sd, name + ".b0", x)
-    b1 = unit3d(sd, name + ".b1b", unit3d(sd, name + ".b1a", x))
-    b2 = unit3d(sd, name + ".b2b", unit3d(sd, name + ".b2a", x))
-    b3 = unit3d(sd, name + ".b3b", maxpool_same(x, (3, 3, 3), (1, 1, 1)))
+    b0 = unit3d(sd, name + ".b0", x, quant=quant)
+    b1 = unit3d(sd, name + ".b1b", unit3d(sd, name + ".b1a", x, quant=quant), quant=quant)
+    b2 = unit3d(sd, name + ".b2b", unit3d(sd, name + ".b2a", x, quant=quant), quant=quant)
+    b3 = unit3d(sd, name + ".b3b", maxpool_same(x, (3, 3, 3), (1, 1, 1), quant), quant=quant)
     return torch.cat([b0, b1, b2, b3], dim=1)
 
 
-def features(sd, x, upto="Mixed_5c", stride_mods=None):
+def features(sd, x, upto="Mixed_5c", stride_mods=None, quant=False):
     stride_mods = stride_mods or {}
     outs = {}
+    if quant:
+        x = quant_input(x)
     for name in ENDPOINTS:
         if name == "Conv3d_1a_7x7":
-            x = unit3d(sd, name, x, stride_mods.get(name, (2, 2, 2)))
+            x = unit3d(sd, name, x, stride_mods.get(name, (2, 2, 2)), quant=quant)
         elif name.startswith("Conv3d"):
-            x = unit3d(sd, name, x)
+            x = unit3d(sd, name, x, quant=quant)
         elif name.startswith("MaxPool"):
             k, s = POOLS[name]
-            x = maxpool_same(x, k, stride_mods.get(name, s))
+            x = maxpool_same(x, k, stride_mods.get(name, s), quant)
         else:
-            x = inception(sd, name, x)
+            x = inception(sd, name, x, quant)
         outs[name] = x
         if name == upto:
             break
@@ -78,19 +115,19 @@ def head(sd, feat, avg_pool=(2, 7, 7), softmax=True):
     return F.softmax(logits, dim=1) if softmax else logits
 
 
-def forward(sd, x, avg_pool=(2, 7, 7), softmax=True, stride_mods=None):
-    feat, _ = features(sd, x, stride_mods=stride_mods)
+def forward(sd, x, avg_pool=(2, 7, 7), softmax=True, stride_mods=None, quant=False):
+    feat, _ = features(sd, x, stride_mods=stride_mods, quant=quant)
     return head(sd, feat, avg_pool, softmax)
 
 
 class Model:
     """Callable wrapper so the mask oracle can call model(x) like the reference does."""
 
-    def __init__(self, sd, avg_pool=(2, 7, 7), softmax=True):
-        self.sd, self.avg_pool, self.softmax = sd, avg_pool, softmax
+    def __init__(self, sd, avg_pool=(2, 7, 7), softmax=True, quant=False):
+        self.sd, self.avg_pool, self.softmax, self.quant = sd, avg_pool, softmax, quant
 
     def __call__(self, x):
-        return forward(self.sd, x, self.avg_pool, self.softmax)
+        return forward(self.sd, x, self.avg_pool, self.softmax, quant=self.quant)
 
 
 def conv_flops_per_clip(sd, clip_shape):

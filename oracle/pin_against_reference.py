@@ -115,11 +115,13 @@ def main():
     sds = i3d_oracle.calibrate_and_sharpen(sd, x2)
     ref.load_state_dict(sds)
     tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4)
-    target = [0, 3]
     with torch.no_grad():
         ps_ref = ref(x2)
     close(i3d_oracle.forward(sds, x2).detach(), ps_ref, 1e-5, "I3D smth forward probs (sharpened)")
     gold["probs_sharp"] = ps_ref.numpy()
+    # targets = the predicted class of each clip: a class with ~1e-30 probability has no gradient
+    target = ps_ref.argmax(dim=1).tolist()
+    gold["targets"] = np.array(target, dtype=np.int64)
     for bi in (0, 1):
         tmr = tm.clone().requires_grad_()
         out = ref(ref_mask.perturb_sequence(x2, torch.sigmoid(tmr), 'freeze'))[bi, target[bi]]
@@ -127,23 +129,24 @@ def main():
         tmo = tm.clone().requires_grad_()
         out_o = i3d_oracle.forward(sds, mask_oracle.perturb_sequence(x2, torch.sigmoid(tmo), 'freeze'))[bi, target[bi]]
         (g_or,) = torch.autograd.grad(out_o, tmo)
-        close(g_or, g_ref, 1e-4, "I3D smth class-gradient d p/d raw-mask, clip %d" % bi)
+        close(g_or, g_ref, 1e-4, "I3D smth class-gradient d p/d raw-mask, clip %d (|g|max %.1e)" % (bi, g_ref.abs().max()))
         gold["classgrad_%d" % bi] = g_ref.numpy()
         gold["classprob_%d" % bi] = np.float32(out.item())
-    # three reference iterations (SURVEY §4.3 last bullet) on the sharpened model
-    rec_ref, rec_or = {}, {}
+    # three reference iterations (SURVEY §4.3 last bullet) on the sharpened model, clip 0
+    rec_or = {}
     tmr = tm.clone().requires_grad_()
     opt = torch.optim.Adam([tmr], lr=0.2)
     losses = []
     for _ in range(3):
         mc = torch.sigmoid(tmr)
-        loss = 0.01 * mc.abs().sum() + 0.02 * ref_mask.calc_tv_norm(mc) + ref(ref_mask.perturb_sequence(x2, mc, 'freeze'))[0, 3]
+        loss = 0.01 * mc.abs().sum() + 0.02 * ref_mask.calc_tv_norm(mc) + \
+            ref(ref_mask.perturb_sequence(x2, mc, 'freeze'))[0, target[0]]
         opt.zero_grad()
         loss.backward()
         opt.step()
         losses.append(loss.item())
     tmo = tm.clone().requires_grad_()
-    fm, _ = mask_oracle.mask_search(x2, i3d_oracle.Model(sds), 0, [3, 3], tmo, 0.01, 0.02, 3, record=rec_or)
+    fm, _ = mask_oracle.mask_search(x2, i3d_oracle.Model(sds), 0, target, tmo, 0.01, 0.02, 3, record=rec_or)
     close(rec_or["loss"], losses, 1e-5, "3 mask-search iterations: losses")
     close(fm, torch.sigmoid(tmr).detach(), 1e-5, "3 mask-search iterations: sigmoid(mask)")
     gold["iter3_losses"] = np.array(losses, dtype=np.float32)
