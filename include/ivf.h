@@ -147,8 +147,17 @@ int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, int ld, cons
  *          IVF_PFMT_NDHWC_F32  fp32 [b][t][h][w][c]          (fp32 conv path)
  *          IVF_PFMT_S2D_BF16   bf16 [b][t/2][h/2][w/2][32]   (space-to-depth operand of the
  *              stride-2 7x7x7 stem, channel = ((dt*2+dh)*2+dw)*c + ch, 24..31 zero)
+ *          IVF_PFMT_TBHWC_F32  fp32 [t][b][h][w][c]          (time-major frames: ConvLSTM, fp32 path)
+ *          IVF_PFMT_S2D2_BF16  bf16 [t][b][h/2][w/2][16]     (time-major, 2-D space-to-depth operand of
+ *              the stride-2 5x5 ConvLSTM x-convolution, channel = (dh*2+dw)*c + ch, 12..15 zero)
  */
-enum { IVF_PFMT_NCDHW_F32 = 0, IVF_PFMT_NDHWC_F32 = 1, IVF_PFMT_S2D_BF16 = 2 };
+enum {
+  IVF_PFMT_NCDHW_F32 = 0,
+  IVF_PFMT_NDHWC_F32 = 1,
+  IVF_PFMT_S2D_BF16 = 2,
+  IVF_PFMT_TBHWC_F32 = 3,
+  IVF_PFMT_S2D2_BF16 = 4
+};
 int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const float* mask, int mask_bstride,
                     int b, int c, int t, int hh, int ww, int out_fmt, void* out, void* stream);
 /* dmask[b][t] (fp32, one row per clip) = d<gout, P>/dmask; gout is laid out like `out` above

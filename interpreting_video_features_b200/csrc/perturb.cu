@@ -88,35 +88,45 @@ __global__ void perturb_fwd_planar_kernel(int mode, const float* __restrict__ x,
       }
       if (FMT == IVF_PFMT_NCDHW_F32)
         out[((size_t)(b * c + ch) * t + u) * hw + p] = v;
-      else
+      else if (FMT == IVF_PFMT_NDHWC_F32)
         out[(((size_t)b * t + u) * hw + p) * c + ch] = v;
+      else  // IVF_PFMT_TBHWC_F32: time-major frames for the ConvLSTM
+        out[(((size_t)u * gridDim.y + b) * hw + p) * c + ch] = v;
     }
   }
 }
 
 // ------------------------------------------------------------------ forward, space-to-depth bf16
-// one thread per macro pixel (h/2, w/2): 2x2 pixels x c channels, two frames per 64-byte record
+// one thread per macro pixel (h/2, w/2): 2x2 pixels x c channels.
+// S2D3 = true : I3D stem operand, two frames per 64-byte record [b][t/2][h/2][w/2][32]
+// S2D3 = false: ConvLSTM x-conv operand, one frame per 32-byte record, time-major [t][b][h/2][w/2][16]
+template <bool S2D3>
 __global__ void perturb_fwd_s2d_kernel(int mode, const float* __restrict__ x,
                                        const float* __restrict__ mask, int mask_bstride, int c,
                                        int t, int hh, int ww, __nv_bfloat16* __restrict__ out) {
   __shared__ MaskInfo mi;
   const int b = blockIdx.y;
+  const int nb = gridDim.y;
   build_mask_info(&mi, mask + (size_t)b * mask_bstride, t, mode);
   const int h2 = hh / 2, w2 = ww / 2, t2 = t / 2;
   const size_t hw = (size_t)hh * ww;
+  constexpr int FR = S2D3 ? 2 : 1;    // frames per record
+  constexpr int REC = S2D3 ? 32 : 16;  // channels per record
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < h2 * w2; idx += gridDim.x * blockDim.x) {
     const int y = idx / w2, xq = idx - y * w2;
     float P[MAX_C][2][2];
-    for (int u2 = 0; u2 < t2; ++u2) {
-      __align__(16) __nv_bfloat16 rec[32];
+    for (int r = 0; r < t / FR; ++r) {
+      __align__(16) __nv_bfloat16 rec[REC];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) rec[i] = __float2bfloat16_rn(0.f);
+      for (int i = 0; i < REC; ++i) rec[i] = __float2bfloat16_rn(0.f);
 #pragma unroll
-      for (int dt = 0; dt < 2; ++dt) {
-        const int u = 2 * u2 + dt;
+      for (int dt = 0; dt < FR; ++dt) {
+        const int u = FR * r + dt;
         const float mu = mi.m[u], cf = mi.coef[u];
         const int q = mi.partner[u];
-        for (int ch = 0; ch < c; ++ch) {
+#pragma unroll
+        for (int ch = 0; ch < MAX_C; ++ch) {
+          if (ch >= c) break;
           const float* xf = x + ((size_t)(b * c + ch) * t) * hw;
 #pragma unroll
           for (int dh = 0; dh < 2; ++dh) {
@@ -146,12 +156,12 @@ __global__ void perturb_fwd_s2d_kernel(int mode, const float* __restrict__ x,
           }
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(out + ((((size_t)b * t2 + u2) * h2 + y) * w2 + xq) * 32);
+      size_t rec_index = S2D3 ? ((((size_t)b * t2 + r) * h2 + y) * w2 + xq)
+                              : ((((size_t)r * nb + b) * h2 + y) * w2 + xq);
+      uint4* dst = reinterpret_cast<uint4*>(out + rec_index * REC);
       const uint4* src = reinterpret_cast<const uint4*>(rec);
-      dst[0] = src[0];
-      dst[1] = src[1];
-      dst[2] = src[2];
-      dst[3] = src[3];
+#pragma unroll
+      for (int i = 0; i < REC / 8; ++i) dst[i] = src[i];
     }
   }
 }
@@ -236,37 +246,45 @@ perturb_bwd_planar_kernel(int mode, const float* __restrict__ x, const float* __
       const float* gs = gout + ((size_t)(b * c + ch) * t) * hw + p;
       auto gl = [&](int u) { return gs[(size_t)u * hw]; };
       item_bwd<TT>(mode, t, mi, xl, gl, acc);
-    } else {
+    } else if (FMT == IVF_PFMT_NDHWC_F32) {
       const float* gs = gout + ((size_t)b * t * hw + p) * c + ch;
       auto gl = [&](int u) { return gs[(size_t)u * hw * c]; };
+      item_bwd<TT>(mode, t, mi, xl, gl, acc);
+    } else {  // time-major frames
+      const float* gs = gout + ((size_t)b * hw + p) * c + ch;
+      const size_t fstride = (size_t)gridDim.y * hw * c;
+      auto gl = [&](int u) { return gs[(size_t)u * fstride]; };
       item_bwd<TT>(mode, t, mi, xl, gl, acc);
     }
   }
   block_reduce_dm<TT>(acc, t, red, dmask + (size_t)b * t);
 }
 
-// space-to-depth gout (bf16 or fp32 records of 32 channels): one block per (macro row, clip);
-// the row's records for all frames are staged in shared memory with 16-byte loads, then each
-// thread walks full-resolution pixels of the two rows (coalesced x reads along W).
-template <int TT, typename GT>
+// space-to-depth gout (bf16 or fp32 records): one block per (macro row, clip); the row's records for
+// all frames are staged in shared memory with 16-byte loads, then each thread walks full-resolution
+// pixels of the two rows (coalesced x reads along W).  S2D3: 32-channel two-frame records (I3D);
+// otherwise 16-channel one-frame time-major records (ConvLSTM).
+template <int TT, typename GT, bool S2D3>
 __global__ void __launch_bounds__(256)
 perturb_bwd_s2d_kernel(int mode, const float* __restrict__ x, const float* __restrict__ mask,
                        int mask_bstride, int c, int t, int hh, int ww, const GT* __restrict__ gout,
                        float* __restrict__ dmask) {
   extern __shared__ __align__(16) uint8_t gsm_raw[];
-  GT* gsm = reinterpret_cast<GT*>(gsm_raw);  // [t2][w2][32]
+  GT* gsm = reinterpret_cast<GT*>(gsm_raw);  // [records][w2][REC]
   __shared__ MaskInfo mi;
   __shared__ float red[8 * TT];
-  const int b = blockIdx.y, y = blockIdx.x;
+  const int b = blockIdx.y, y = blockIdx.x, nb = gridDim.y;
   build_mask_info(&mi, mask + (size_t)b * mask_bstride, t, mode);
-  const int h2 = hh / 2, w2 = ww / 2, t2 = t / 2;
+  constexpr int FR = S2D3 ? 2 : 1;
+  constexpr int REC = S2D3 ? 32 : 16;
+  const int h2 = hh / 2, w2 = ww / 2, nrec = t / FR;
   constexpr int PER16 = 16 / sizeof(GT);
-  const int vec_per_frame = w2 * 32 / PER16;
-  for (int i = threadIdx.x; i < t2 * vec_per_frame; i += blockDim.x) {
-    int u2 = i / vec_per_frame, r = i - u2 * vec_per_frame;
-    const uint4* src =
-        reinterpret_cast<const uint4*>(gout + ((((size_t)b * t2 + u2) * h2 + y) * w2) * 32) + r;
-    reinterpret_cast<uint4*>(gsm + (size_t)u2 * w2 * 32)[r] = *src;
+  const int vec_per_frame = w2 * REC / PER16;
+  for (int i = threadIdx.x; i < nrec * vec_per_frame; i += blockDim.x) {
+    int r = i / vec_per_frame, v = i - r * vec_per_frame;
+    size_t row = S2D3 ? (((size_t)b * nrec + r) * h2 + y) : (((size_t)r * nb + b) * h2 + y);
+    const uint4* src = reinterpret_cast<const uint4*>(gout + row * w2 * REC) + v;
+    reinterpret_cast<uint4*>(gsm + (size_t)r * w2 * REC)[v] = *src;
   }
   __syncthreads();
   float acc[TT];
@@ -279,14 +297,38 @@ perturb_bwd_s2d_kernel(int mode, const float* __restrict__ x, const float* __res
     const int r = it / ww;
     const int dh = r & 1, ch = r >> 1;
     const float* xs = x + ((size_t)(b * c + ch) * t) * hw + (size_t)(2 * y + dh) * ww + wx;
-    const GT* gs = gsm + (size_t)(wx >> 1) * 32 + (dh * 2 + (wx & 1)) * c + ch;
+    const GT* gs = gsm + (size_t)(wx >> 1) * REC + (dh * 2 + (wx & 1)) * c + ch;
     auto xl = [&](int u) { return xs[(size_t)u * hw]; };
     auto gl = [&](int u) {
-      return ivf_to_float(gs[(size_t)(u >> 1) * w2 * 32 + (u & 1) * 4 * c]);
+      return S2D3 ? ivf_to_float(gs[(size_t)(u >> 1) * w2 * REC + (u & 1) * 4 * c])
+                  : ivf_to_float(gs[(size_t)u * w2 * REC]);
     };
     item_bwd<TT>(mode, t, mi, xl, gl, acc);
   }
   block_reduce_dm<TT>(acc, t, red, dmask + (size_t)b * t);
+}
+
+template <int TT, typename GT, bool S2D3>
+int launch_bwd_s2d(ivf_handle* h, int mode, const float* x, const float* mask, int mask_bstride, int b,
+                   int c, int t, int hh, int ww, const void* gout, float* dmask, cudaStream_t st) {
+  constexpr int FR = S2D3 ? 2 : 1;
+  constexpr int REC = S2D3 ? 32 : 16;
+  size_t smem = (size_t)(t / FR) * (ww / 2) * REC * sizeof(GT);
+  IVF_REQUIRE(smem <= 200 * 1024, "perturb_bwd(s2d): row tile of %zu bytes exceeds shared memory", smem);
+  // opt in to large dynamic shared memory once per instantiation and device (not per launch, so a
+  // captured iteration contains launches only)
+  static bool attr_done[16] = {};
+  int dev = h->device & 15;
+  if (!attr_done[dev]) {
+    IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, GT, S2D3>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done[dev] = true;
+  }
+  dim3 grid(hh / 2, b);
+  perturb_bwd_s2d_kernel<TT, GT, S2D3><<<grid, 256, smem, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
+                                                                (const GT*)gout, dmask);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
 }
 
 template <int TT>
@@ -295,42 +337,26 @@ int launch_bwd(ivf_handle* h, int mode, const float* x, const float* mask, int m
                float* dmask, cudaStream_t st) {
   const int hw = hh * ww;
   if (out_fmt == IVF_PFMT_S2D_BF16) {
-    const int t2 = t / 2, w2 = ww / 2;
-    size_t esz = gout_dtype == IVF_F32 ? 4 : 2;
-    size_t smem = (size_t)t2 * w2 * 32 * esz;
-    IVF_REQUIRE(smem <= 200 * 1024, "perturb_bwd(s2d): row tile of %zu bytes exceeds shared memory", smem);
-    dim3 grid(hh / 2, b);
-    // opt in to large dynamic shared memory once per instantiation and device (not per launch, so
-    // a captured iteration contains launches only)
-    static bool attr_done[2][16] = {};
-    int dev = h->device & 15;
-    if (gout_dtype == IVF_F32) {
-      if (!attr_done[0][dev]) {
-        IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, float>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[0][dev] = true;
-      }
-      perturb_bwd_s2d_kernel<TT, float><<<grid, 256, smem, st>>>(mode, x, mask, mask_bstride, c, t, hh,
-                                                                 ww, (const float*)gout, dmask);
-    } else {
-      if (!attr_done[1][dev]) {
-        IVF_CUDA(cudaFuncSetAttribute(perturb_bwd_s2d_kernel<TT, __nv_bfloat16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[1][dev] = true;
-      }
-      perturb_bwd_s2d_kernel<TT, __nv_bfloat16><<<grid, 256, smem, st>>>(
-          mode, x, mask, mask_bstride, c, t, hh, ww, (const __nv_bfloat16*)gout, dmask);
-    }
-  } else {
-    int bx = std::min(ivf_cdiv((long long)c * hw, 256), 8 * h->sm_count / std::max(b, 1) + 1);
-    dim3 grid(bx, b);
-    if (out_fmt == IVF_PFMT_NCDHW_F32)
-      perturb_bwd_planar_kernel<TT, IVF_PFMT_NCDHW_F32><<<grid, 256, 0, st>>>(
-          mode, x, mask, mask_bstride, c, t, hw, (const float*)gout, dmask);
-    else
-      perturb_bwd_planar_kernel<TT, IVF_PFMT_NDHWC_F32><<<grid, 256, 0, st>>>(
-          mode, x, mask, mask_bstride, c, t, hw, (const float*)gout, dmask);
+    if (gout_dtype == IVF_F32)
+      return launch_bwd_s2d<TT, float, true>(h, mode, x, mask, mask_bstride, b, c, t, hh, ww, gout, dmask, st);
+    return launch_bwd_s2d<TT, __nv_bfloat16, true>(h, mode, x, mask, mask_bstride, b, c, t, hh, ww, gout, dmask, st);
   }
+  if (out_fmt == IVF_PFMT_S2D2_BF16) {
+    if (gout_dtype == IVF_F32)
+      return launch_bwd_s2d<TT, float, false>(h, mode, x, mask, mask_bstride, b, c, t, hh, ww, gout, dmask, st);
+    return launch_bwd_s2d<TT, __nv_bfloat16, false>(h, mode, x, mask, mask_bstride, b, c, t, hh, ww, gout, dmask, st);
+  }
+  int bx = std::min(ivf_cdiv((long long)c * hw, 256), 8 * h->sm_count / std::max(b, 1) + 1);
+  dim3 grid(bx, b);
+  if (out_fmt == IVF_PFMT_NCDHW_F32)
+    perturb_bwd_planar_kernel<TT, IVF_PFMT_NCDHW_F32><<<grid, 256, 0, st>>>(
+        mode, x, mask, mask_bstride, c, t, hw, (const float*)gout, dmask);
+  else if (out_fmt == IVF_PFMT_NDHWC_F32)
+    perturb_bwd_planar_kernel<TT, IVF_PFMT_NDHWC_F32><<<grid, 256, 0, st>>>(
+        mode, x, mask, mask_bstride, c, t, hw, (const float*)gout, dmask);
+  else
+    perturb_bwd_planar_kernel<TT, IVF_PFMT_TBHWC_F32><<<grid, 256, 0, st>>>(
+        mode, x, mask, mask_bstride, c, t, hw, (const float*)gout, dmask);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -339,10 +365,13 @@ int check_common(int mode, int b, int c, int t, int hh, int ww, int out_fmt) {
   IVF_REQUIRE(mode == 0 || mode == 1, "perturb: mode must be 0 (freeze) or 1 (reverse)");
   IVF_REQUIRE(b > 0 && c > 0 && t > 0 && hh > 0 && ww > 0, "perturb: non-positive extent");
   IVF_REQUIRE(t <= MAX_T, "perturb: t = %d exceeds %d frames", t, MAX_T);
-  IVF_REQUIRE(out_fmt >= 0 && out_fmt <= 2, "perturb: unknown out_fmt %d", out_fmt);
+  IVF_REQUIRE(out_fmt >= 0 && out_fmt <= 4, "perturb: unknown out_fmt %d", out_fmt);
   if (out_fmt == IVF_PFMT_S2D_BF16)
     IVF_REQUIRE(c <= MAX_C && t % 2 == 0 && hh % 2 == 0 && ww % 2 == 0,
                 "perturb(s2d): needs c <= 4 and even t/h/w (got c%d t%d h%d w%d)", c, t, hh, ww);
+  if (out_fmt == IVF_PFMT_S2D2_BF16)
+    IVF_REQUIRE(c <= MAX_C && hh % 2 == 0 && ww % 2 == 0,
+                "perturb(s2d2): needs c <= 4 and even h/w (got c%d h%d w%d)", c, hh, ww);
   return IVF_OK;
 }
 
@@ -356,18 +385,25 @@ extern "C" int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const fl
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int hw = hh * ww;
-  if (out_fmt == IVF_PFMT_S2D_BF16) {
+  if (out_fmt == IVF_PFMT_S2D_BF16 || out_fmt == IVF_PFMT_S2D2_BF16) {
     int items = (hh / 2) * (ww / 2);
     dim3 grid(ivf_cdiv(items, 128), b);
-    perturb_fwd_s2d_kernel<<<grid, 128, 0, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
-                                                 (__nv_bfloat16*)out);
+    if (out_fmt == IVF_PFMT_S2D_BF16)
+      perturb_fwd_s2d_kernel<true><<<grid, 128, 0, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
+                                                         (__nv_bfloat16*)out);
+    else
+      perturb_fwd_s2d_kernel<false><<<grid, 128, 0, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
+                                                          (__nv_bfloat16*)out);
   } else {
     dim3 grid(ivf_cdiv((long long)c * hw, 256), b);
     if (out_fmt == IVF_PFMT_NCDHW_F32)
       perturb_fwd_planar_kernel<IVF_PFMT_NCDHW_F32><<<grid, 256, 0, st>>>(mode, x, mask, mask_bstride,
                                                                           c, t, hw, (float*)out);
-    else
+    else if (out_fmt == IVF_PFMT_NDHWC_F32)
       perturb_fwd_planar_kernel<IVF_PFMT_NDHWC_F32><<<grid, 256, 0, st>>>(mode, x, mask, mask_bstride,
+                                                                          c, t, hw, (float*)out);
+    else
+      perturb_fwd_planar_kernel<IVF_PFMT_TBHWC_F32><<<grid, 256, 0, st>>>(mode, x, mask, mask_bstride,
                                                                           c, t, hw, (float*)out);
   }
   IVF_LAUNCHED(h);
@@ -380,7 +416,7 @@ extern "C" int ivf_perturb_bwd(ivf_handle* h, int mode, const float* x, const fl
   IVF_REQUIRE(h && x && mask && gout && dmask, "ivf_perturb_bwd: null argument");
   int rc = check_common(mode, b, c, t, hh, ww, out_fmt);
   if (rc) return rc;
-  if (out_fmt != IVF_PFMT_S2D_BF16)
+  if (out_fmt != IVF_PFMT_S2D_BF16 && out_fmt != IVF_PFMT_S2D2_BF16)
     IVF_REQUIRE(gout_dtype == IVF_F32, "perturb_bwd: planar gout must be fp32");
   cudaStream_t st = (cudaStream_t)stream;
   IVF_CUDA(cudaMemsetAsync(dmask, 0, (size_t)b * t * sizeof(float), st));

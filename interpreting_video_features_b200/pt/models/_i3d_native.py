@@ -319,7 +319,10 @@ class I3DBase(nn.Module):
 
     def _engine(self, x, batch=None):
         b, c, t, h, w = x.shape
-        key = (batch or b, c, t, h, w, self.ivf_mode, str(x.device))
+        device = next(self.parameters()).device  # the model's GPU; x may still be on the host
+        if device.type != "cuda":
+            raise _lib.IvfError("the native I3D needs the model on a CUDA device (model.cuda())")
+        key = (batch or b, c, t, h, w, self.ivf_mode, str(device))
         ver = self._version()
         hit = self._engines.get(key)
         if hit is None or hit[0] != ver:
@@ -330,7 +333,7 @@ class I3DBase(nn.Module):
             sd = {k: v for k, v in self.state_dict().items()}
             eng = I3DEngine(sd, batch or b, (t, h, w), mode=self.ivf_mode, softmax=bool(self.softMax),
                             avg_pool=tuple(self.avg_pool.kernel_size), stride_mods=self._stride_mods,
-                            device=x.device, in_channels=c)
+                            device=device, in_channels=c)
             hit = (ver, eng)
             self._engines = {key: hit}  # one geometry at a time: activations are large
         return hit[1]
