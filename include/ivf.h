@@ -209,11 +209,15 @@ int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_act, const f
                         const float* c_next, const float* dh, float* dc_io, int m, int hid,
                         void* dgates, void* stream);
 /* eval BatchNorm2d affine + MaxPool2d(2) (pt/models/convolution_lstm.py:120-124);
- * x [n][hh][ww][c] -> y [n][hh/2][ww/2][c]; backward returns fp32 dx (+ acc_in if given) */
+ * x [n][hh][ww][c] -> y [n][hh/2][ww/2][c]; backward returns fp32 dx (+ acc_in if given).
+ * s2d != 0: y (and dy) use the 2-D space-to-depth layout [n][hh/4][ww/4][4c] that the next layer's
+ * stride-2 x-convolution reads as a stride-1 3x3 convolution (channel = (dy*2+dx)*c + k).  */
 int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n, int hh, int ww, int c,
-                      const float* scale, const float* shift, void* y, uint8_t* argmax, void* stream);
+                      const float* scale, const float* shift, void* y, uint8_t* argmax, int s2d,
+                      void* stream);
 int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* argmax, int n, int hh,
-                      int ww, int c, const float* scale, const float* acc_in, float* dx, void* stream);
+                      int ww, int c, const float* scale, const float* acc_in, float* dx, int s2d,
+                      void* stream);
 
 /* ---- bring-up probes (tests only) ---------------------------------------------------
  * Loads one 128-pixel x kchunk im2col TMA tile exactly as the conv kernel does and

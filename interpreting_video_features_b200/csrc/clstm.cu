@@ -71,7 +71,8 @@ __global__ void gates_bwd_kernel(const float* __restrict__ gate_act, const float
 template <typename T>
 __global__ void bn_pool2d_fwd_kernel(const T* __restrict__ x, int hh, int ww, int c,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                     T* __restrict__ y, uint8_t* __restrict__ argmax, long long total) {
+                                     T* __restrict__ y, uint8_t* __restrict__ argmax, int s2d,
+                                     long long total) {
   const int ho = hh / 2, wo = ww / 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -95,7 +96,11 @@ __global__ void bn_pool2d_fwd_kernel(const T* __restrict__ x, int hh, int ww, in
           bi = a * 2 + e;
         }
       }
-    y[idx] = ivf_from_float<T>(best);
+    // s2d: [n][ho/2][wo/2][4c], channel = ((oy&1)*2 + (ox&1))*c + k — the operand layout of the next
+    // layer's stride-2 x-convolution presented as a stride-1 3x3 convolution
+    long long yo = s2d ? ((((n * (ho / 2) + (oy >> 1)) * (wo / 2) + (ox >> 1)) * 4 + ((oy & 1) * 2 + (ox & 1))) * c + k)
+                       : idx;
+    y[yo] = ivf_from_float<T>(best);
     argmax[idx] = (uint8_t)bi;
   }
 }
@@ -103,7 +108,7 @@ __global__ void bn_pool2d_fwd_kernel(const T* __restrict__ x, int hh, int ww, in
 template <typename T>
 __global__ void bn_pool2d_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, int hh,
                                      int ww, int c, const float* __restrict__ scale,
-                                     const float* __restrict__ acc_in, float* __restrict__ dx,
+                                     const float* __restrict__ acc_in, float* __restrict__ dx, int s2d,
                                      long long total) {
   const int ho = hh / 2, wo = ww / 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -118,7 +123,9 @@ __global__ void bn_pool2d_bwd_kernel(const T* __restrict__ dy, const uint8_t* __
     int oy = iy / 2, ox = ix / 2;
     if (oy < ho && ox < wo) {
       long long o = ((n * ho + oy) * wo + ox) * c + k;
-      if (argmax[o] == (iy & 1) * 2 + (ix & 1)) g = ivf_to_float(dy[o]) * (scale ? scale[k] : 1.f);
+      long long yo = s2d ? ((((n * (ho / 2) + (oy >> 1)) * (wo / 2) + (ox >> 1)) * 4 + ((oy & 1) * 2 + (ox & 1))) * c + k)
+                         : o;
+      if (argmax[o] == (iy & 1) * 2 + (ix & 1)) g = ivf_to_float(dy[yo]) * (scale ? scale[k] : 1.f);
     }
     if (acc_in) g += acc_in[idx];
     dx[idx] = g;
@@ -173,17 +180,18 @@ extern "C" int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_a
 
 extern "C" int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n, int hh, int ww, int c,
                                  const float* scale, const float* shift, void* y, uint8_t* argmax,
-                                 void* stream) {
+                                 int s2d, void* stream) {
   IVF_REQUIRE(h && x && y && argmax, "ivf_bn_pool2d_fwd: null argument");
   IVF_REQUIRE(n > 0 && hh >= 2 && ww >= 2 && c > 0, "ivf_bn_pool2d_fwd: bad extent");
+  if (s2d) IVF_REQUIRE((hh / 2) % 2 == 0 && (ww / 2) % 2 == 0, "ivf_bn_pool2d_fwd: s2d needs an even pooled map");
   long long total = (long long)n * (hh / 2) * (ww / 2) * c;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IVF_F32)
     bn_pool2d_fwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>((const float*)x, hh, ww, c, scale,
-                                                                    shift, (float*)y, argmax, total);
+                                                                    shift, (float*)y, argmax, s2d, total);
   else if (dtype == IVF_BF16)
     bn_pool2d_fwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
-        (const __nv_bfloat16*)x, hh, ww, c, scale, shift, (__nv_bfloat16*)y, argmax, total);
+        (const __nv_bfloat16*)x, hh, ww, c, scale, shift, (__nv_bfloat16*)y, argmax, s2d, total);
   else
     IVF_FAIL(IVF_EINVAL, "ivf_bn_pool2d_fwd: unknown dtype");
   IVF_LAUNCHED(h);
@@ -192,17 +200,17 @@ extern "C" int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n,
 
 extern "C" int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* argmax, int n,
                                  int hh, int ww, int c, const float* scale, const float* acc_in,
-                                 float* dx, void* stream) {
+                                 float* dx, int s2d, void* stream) {
   IVF_REQUIRE(h && dy && argmax && dx, "ivf_bn_pool2d_bwd: null argument");
   IVF_REQUIRE(n > 0 && hh >= 2 && ww >= 2 && c > 0, "ivf_bn_pool2d_bwd: bad extent");
   long long total = (long long)n * hh * ww * c;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IVF_F32)
     bn_pool2d_bwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>((const float*)dy, argmax, hh, ww, c,
-                                                                    scale, acc_in, dx, total);
+                                                                    scale, acc_in, dx, s2d, total);
   else if (dtype == IVF_BF16)
     bn_pool2d_bwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
-        (const __nv_bfloat16*)dy, argmax, hh, ww, c, scale, acc_in, dx, total);
+        (const __nv_bfloat16*)dy, argmax, hh, ww, c, scale, acc_in, dx, s2d, total);
   else
     IVF_FAIL(IVF_EINVAL, "ivf_bn_pool2d_bwd: unknown dtype");
   IVF_LAUNCHED(h);

@@ -12,7 +12,8 @@ import torch
 
 from . import _lib
 from ._lib import (EP_ACCUM, EP_AFFINE, EP_MASK, EP_OUT_F32, EP_RELU, IVF_BF16, IVF_F32,
-                   PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, ConvDesc, PoolDesc, check, ptr)
+                   PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D2_BF16, PFMT_S2D_BF16, PFMT_TBHWC_F32, ConvDesc,
+                   PoolDesc, check, ptr)
 
 
 class Act:
@@ -227,18 +228,18 @@ def clstm_gates_bwd(gate_act, c_prev, c_next, dh, dc_io, dgates):
                                           ptr(dgates), _lib.stream_ptr()), "ivf_clstm_gates_bwd")
 
 
-def bn_pool2d_fwd(x, scale, shift, y, argmax):
+def bn_pool2d_fwd(x, scale, shift, y, argmax, s2d=False):
     n, hh, ww, c = x.shape
     check(_lib.load().ivf_bn_pool2d_fwd(_lib.handle(x.device), _lib.dtype_code(x), ptr(x), n, hh, ww, c,
-                                        ptr(scale), ptr(shift), ptr(y), ptr(argmax), _lib.stream_ptr()),
-          "ivf_bn_pool2d_fwd")
+                                        ptr(scale), ptr(shift), ptr(y), ptr(argmax), int(s2d),
+                                        _lib.stream_ptr()), "ivf_bn_pool2d_fwd")
 
 
-def bn_pool2d_bwd(dy, argmax, scale, dx, acc_in=None):
+def bn_pool2d_bwd(dy, argmax, scale, dx, acc_in=None, s2d=False):
     n, hh, ww, c = dx.shape
     check(_lib.load().ivf_bn_pool2d_bwd(_lib.handle(dy.device), _lib.dtype_code(dy), ptr(dy), ptr(argmax), n,
-                                        hh, ww, c, ptr(scale), ptr(acc_in), ptr(dx), _lib.stream_ptr()),
-          "ivf_bn_pool2d_bwd")
+                                        hh, ww, c, ptr(scale), ptr(acc_in), ptr(dx), int(s2d),
+                                        _lib.stream_ptr()), "ivf_bn_pool2d_bwd")
 
 
 def probe_im2col(x, kernel, stride, pad_front, out_dhw, m0, tap, c0):

