@@ -32,11 +32,22 @@ extern "C" int ivf_create(int device, ivf_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  h->scratch_bytes = 4u << 20;
+  cudaError_t me = cudaMalloc(&h->scratch, h->scratch_bytes);
+  cudaSetDevice(prev);
+  if (me != cudaSuccess) {
+    delete h;
+    IVF_FAIL(IVF_ECUDA, "ivf_create: scratch allocation failed: %s", cudaGetErrorString(me));
+  }
   *out = h;
   return IVF_OK;
 }
 
 extern "C" int ivf_destroy(ivf_handle* h) {
+  if (h && h->scratch) cudaFree(h->scratch);
   delete h;
   return IVF_OK;
 }

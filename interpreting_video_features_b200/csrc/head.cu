@@ -27,35 +27,51 @@ __device__ float block_reduce(float v, float* red, bool is_max) {
   return r;
 }
 
+constexpr int HEAD_CHUNK = 128;  // channels per forward block
+
+// Forward, stage 1: grid (clip, channel chunk).  256 threads = 128 channels x 2 position halves;
+// average-pool the chunk, then its partial logits -> scratch[clip][chunk][class].
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS)
-head_fwd_kernel(const T* __restrict__ feat, int p, int c, int ld, const float* __restrict__ w,
-                const float* __restrict__ b, int ncls, int softmax, float* __restrict__ logits,
-                float* __restrict__ out) {
-  extern __shared__ float sm[];  // avg[c] | logit[ncls]
-  __shared__ float red[32];
-  float* avg = sm;
-  float* lg = sm + c;
-  const int n = blockIdx.x;
+head_fwd_partial_kernel(const T* __restrict__ feat, int p, int c, int ld, const float* __restrict__ w,
+                        int ncls, float* __restrict__ partial) {
+  __shared__ float half_sum[2][HEAD_CHUNK];
+  __shared__ float avg[HEAD_CHUNK];
+  const int n = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+  const int k0 = chunk * HEAD_CHUNK;
+  const int kl = threadIdx.x % HEAD_CHUNK, half = threadIdx.x / HEAD_CHUNK;
   const T* f = feat + (size_t)n * p * ld;
-  const float inv = 1.f / (float)p;
-  for (int k = threadIdx.x; k < c; k += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < p; ++i) s += ivf_to_float(f[(size_t)i * ld + k]);
-    avg[k] = s * inv;
-  }
+  float s = 0.f;
+  if (k0 + kl < c)
+    for (int i = half; i < p; i += 2) s += ivf_to_float(f[(size_t)i * ld + k0 + kl]);
+  half_sum[half][kl] = s;
+  __syncthreads();
+  if (threadIdx.x < HEAD_CHUNK) avg[kl] = (half_sum[0][kl] + half_sum[1][kl]) / (float)p;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int j = warp; j < ncls; j += nw) {
-    const float* wr = w + (size_t)j * c;
-    float s = 0.f;
-    for (int k = lane; k < c; k += 32) s = fmaf(__ldg(wr + k), avg[k], s);
-    s = ivf_warp_sum(s);
-    if (lane == 0) lg[j] = s + (b ? b[j] : 0.f);
+    const float* wr = w + (size_t)j * c + k0;
+    float a = 0.f;
+    for (int k = lane; k < HEAD_CHUNK && k0 + k < c; k += 32) a = fmaf(__ldg(wr + k), avg[k], a);
+    a = ivf_warp_sum(a);
+    if (lane == 0) partial[((size_t)n * nchunks + chunk) * ncls + j] = a;
+  }
+}
+
+// Forward, stage 2: grid (clip): sum the chunk partials in a fixed order (deterministic), bias, softmax.
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_fwd_finish_kernel(const float* __restrict__ partial, int nchunks, const float* __restrict__ b, int ncls,
+                       int softmax, float* __restrict__ logits, float* __restrict__ out) {
+  extern __shared__ float lg[];
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  for (int j = threadIdx.x; j < ncls; j += blockDim.x) {
+    float s = b ? b[j] : 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) s += partial[((size_t)n * nchunks + ch) * ncls + j];
+    lg[j] = s;
+    if (logits) logits[(size_t)n * ncls + j] = s;
   }
   __syncthreads();
-  if (logits)
-    for (int j = threadIdx.x; j < ncls; j += blockDim.x) logits[(size_t)n * ncls + j] = lg[j];
   if (!softmax) {
     for (int j = threadIdx.x; j < ncls; j += blockDim.x) out[(size_t)n * ncls + j] = lg[j];
     return;
@@ -70,6 +86,9 @@ head_fwd_kernel(const T* __restrict__ feat, int p, int c, int ld, const float* _
     out[(size_t)n * ncls + j] = expf(lg[j] - mx) / se;
 }
 
+// Backward: grid (clip, position chunk).  Every block rebuilds dlogits (ncls values) and the channel
+// gradient of its HEAD_CHUNK..c range is recomputed per block (ncls*c MACs, cheap) so that the p*c
+// output elements are written by many blocks instead of one.
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int softmax,
@@ -81,6 +100,9 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
   float* dl = sm;
   float* davg = sm + ncls;
   const int n = blockIdx.x;
+  const int pchunks = gridDim.y;
+  const int per = (p + pchunks - 1) / pchunks;
+  const int i0 = blockIdx.y * per, i1 = min(p, i0 + per);
   const float* o = out + (size_t)n * ncls;
   const float* g = dout + (size_t)n * ncls;
   if (softmax) {
@@ -94,14 +116,19 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
   __syncthreads();
   const float inv = 1.f / (float)p;
   for (int k = threadIdx.x; k < c; k += blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j < ncls; ++j) s = fmaf(__ldg(w + (size_t)j * c + k), dl[j], s);
-    davg[k] = s * inv;
+    float s0 = 0.f, s1 = 0.f;
+    int j = 0;
+    for (; j + 1 < ncls; j += 2) {
+      s0 = fmaf(__ldg(w + (size_t)j * c + k), dl[j], s0);
+      s1 = fmaf(__ldg(w + (size_t)(j + 1) * c + k), dl[j + 1], s1);
+    }
+    if (j < ncls) s0 = fmaf(__ldg(w + (size_t)j * c + k), dl[j], s0);
+    davg[k] = (s0 + s1) * inv;
   }
   __syncthreads();
   const size_t base = (size_t)n * p;
-  for (int e = threadIdx.x; e < p * c; e += blockDim.x) {
-    int i = e / c, k = e - i * c;
+  for (int e = threadIdx.x; e < (i1 - i0) * c; e += blockDim.x) {
+    int i = i0 + e / c, k = e % c;
     float v = davg[k];
     if (flags & IVF_EP_MASK) {
       float y = ivf_to_float(mask_y[(base + i) * mask_ld + mask_coff + k]);
@@ -122,17 +149,22 @@ extern "C" int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int 
                                 float* logits, float* out, void* stream) {
   IVF_REQUIRE(h && feat && w && out, "ivf_i3d_head_fwd: null argument");
   IVF_REQUIRE(n > 0 && p > 0 && c > 0 && ncls > 0 && ld >= c, "ivf_i3d_head_fwd: bad extent");
-  size_t smem = (size_t)(c + ncls) * sizeof(float);
-  IVF_REQUIRE(smem <= 48 * 1024, "ivf_i3d_head_fwd: c + ncls too large (%d + %d)", c, ncls);
+  const int nchunks = (c + HEAD_CHUNK - 1) / HEAD_CHUNK;
+  size_t need = (size_t)n * nchunks * ncls * sizeof(float);
+  IVF_REQUIRE(need <= h->scratch_bytes, "ivf_i3d_head_fwd: n*c*ncls too large for the handle scratch (%zu B)", need);
+  IVF_REQUIRE((size_t)ncls * sizeof(float) <= 48 * 1024, "ivf_i3d_head_fwd: ncls too large");
   cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n, nchunks);
   if (dtype == IVF_F32)
-    head_fwd_kernel<float><<<n, HEAD_THREADS, smem, st>>>((const float*)feat, p, c, ld, w, b, ncls,
-                                                          softmax, logits, out);
+    head_fwd_partial_kernel<float><<<grid, HEAD_THREADS, 0, st>>>((const float*)feat, p, c, ld, w, ncls, h->scratch);
   else if (dtype == IVF_BF16)
-    head_fwd_kernel<__nv_bfloat16><<<n, HEAD_THREADS, smem, st>>>((const __nv_bfloat16*)feat, p, c,
-                                                                  ld, w, b, ncls, softmax, logits, out);
+    head_fwd_partial_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, 0, st>>>((const __nv_bfloat16*)feat, p, c, ld, w,
+                                                                          ncls, h->scratch);
   else
     IVF_FAIL(IVF_EINVAL, "ivf_i3d_head_fwd: unknown dtype %d", dtype);
+  IVF_LAUNCHED(h);
+  head_fwd_finish_kernel<<<n, HEAD_THREADS, ncls * sizeof(float), st>>>(h->scratch, nchunks, b, ncls, softmax, logits,
+                                                                        out);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -147,12 +179,14 @@ extern "C" int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, i
   size_t smem = (size_t)(c + ncls) * sizeof(float);
   IVF_REQUIRE(smem <= 48 * 1024, "ivf_i3d_head_bwd: c + ncls too large (%d + %d)", c, ncls);
   cudaStream_t st = (cudaStream_t)stream;
+  int pchunks = p >= 14 ? (p + 13) / 14 : 1;
+  dim3 grid(n, pchunks);
   if (dtype == IVF_F32)
-    head_bwd_kernel<float><<<n, HEAD_THREADS, smem, st>>>(p, c, ld, w, ncls, softmax, out, dout, flags,
+    head_bwd_kernel<float><<<grid, HEAD_THREADS, smem, st>>>(p, c, ld, w, ncls, softmax, out, dout, flags,
                                                           (const float*)mask_y, mask_ld, mask_coff,
                                                           mask_scale, dfeat);
   else if (dtype == IVF_BF16)
-    head_bwd_kernel<__nv_bfloat16><<<n, HEAD_THREADS, smem, st>>>(
+    head_bwd_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, smem, st>>>(
         p, c, ld, w, ncls, softmax, out, dout, flags, (const __nv_bfloat16*)mask_y, mask_ld,
         mask_coff, mask_scale, dfeat);
   else

@@ -10,11 +10,6 @@
 namespace {
 
 template <typename T, int VEC>
-struct Vec {
-  T v[VEC];
-};
-
-template <typename T, int VEC>
 __device__ __forceinline__ void load_vec(const T* p, float (&f)[VEC]) {
   if constexpr (VEC == 1) {
     f[0] = ivf_to_float(p[0]);
@@ -38,10 +33,32 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
   }
 }
 
-template <typename T, int VEC>
-__global__ void maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T* __restrict__ out,
-                                   uint8_t* __restrict__ argmax, long long total) {
+// Compile-time window geometry (KD..SW > 0) removes every runtime division from the tap loops and lets the
+// compiler unroll them; GEN = true keeps the fully general runtime-geometry path.
+template <int KD, int KH, int KW, int SD, int SH, int SW>
+struct PoolGeo {
+  __device__ static int kd(const ivf_pool_desc&) { return KD; }
+  __device__ static int kh(const ivf_pool_desc&) { return KH; }
+  __device__ static int kw(const ivf_pool_desc&) { return KW; }
+  __device__ static int sd(const ivf_pool_desc&) { return SD; }
+  __device__ static int sh(const ivf_pool_desc&) { return SH; }
+  __device__ static int sw(const ivf_pool_desc&) { return SW; }
+};
+struct PoolGeoDyn {
+  __device__ static int kd(const ivf_pool_desc& d) { return d.kd; }
+  __device__ static int kh(const ivf_pool_desc& d) { return d.kh; }
+  __device__ static int kw(const ivf_pool_desc& d) { return d.kw; }
+  __device__ static int sd(const ivf_pool_desc& d) { return d.sd; }
+  __device__ static int sh(const ivf_pool_desc& d) { return d.sh; }
+  __device__ static int sw(const ivf_pool_desc& d) { return d.sw; }
+};
+
+template <typename T, int VEC, typename G>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T* __restrict__ out,
+                   uint8_t* __restrict__ argmax, long long total) {
   const int cv = d.c / VEC;
+  const int KD = G::kd(d), KH = G::kh(d), KW = G::kw(d), SD = G::sd(d), SH = G::sh(d), SW = G::sw(d);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int c = (int)(idx % cv) * VEC;
@@ -59,17 +76,21 @@ __global__ void maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T*
       best[i] = -INFINITY;
       bidx[i] = 0;
     }
-    int tap = 0;
-    for (int a = 0; a < d.kd; ++a) {
-      int zd = od * d.sd - d.pd + a;
-      for (int b = 0; b < d.kh; ++b) {
-        int zh = oh * d.sh - d.ph + b;
-        for (int e = 0; e < d.kw; ++e, ++tap) {
-          int zw = ow * d.sw - d.pw + e;
+    const T* base = in + d.in_coff + c;
+#pragma unroll
+    for (int a = 0; a < KD; ++a) {
+      int zd = od * SD - d.pd + a;
+#pragma unroll
+      for (int b = 0; b < KH; ++b) {
+        int zh = oh * SH - d.ph + b;
+#pragma unroll
+        for (int e = 0; e < KW; ++e) {
+          int zw = ow * SW - d.pw + e;
+          const int tap = (a * KH + b) * KW + e;
           float v[VEC];
-          if (zd >= 0 && zd < d.id && zh >= 0 && zh < d.ih && zw >= 0 && zw < d.iw) {
+          if ((unsigned)zd < (unsigned)d.id && (unsigned)zh < (unsigned)d.ih && (unsigned)zw < (unsigned)d.iw) {
             size_t pix = (((size_t)n * d.id + zd) * d.ih + zh) * d.iw + zw;
-            load_vec<T, VEC>(in + pix * d.in_ld + d.in_coff + c, v);
+            load_vec<T, VEC>(base + pix * d.in_ld, v);
           } else {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) v[i] = 0.f;  // explicit zero padding
@@ -86,19 +107,29 @@ __global__ void maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T*
     }
     store_vec<T, VEC>(out + (size_t)opix * d.out_ld + d.out_coff + c, best);
     if (argmax) {
+      uint8_t* am = argmax + (size_t)opix * d.c + c;
+      if constexpr (VEC == 8) {
+        uint2 pk;
+        pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+        pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+        *reinterpret_cast<uint2*>(am) = pk;
+      } else if constexpr (VEC == 4) {
+        *reinterpret_cast<uint32_t*>(am) = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) argmax[(size_t)opix * d.c + c + i] = (uint8_t)bidx[i];
+        for (int i = 0; i < VEC; ++i) am[i] = (uint8_t)bidx[i];
+      }
     }
   }
 }
 
-template <typename T, int VEC>
-__global__ void maxpool_bwd_kernel(ivf_pool_desc d, const T* __restrict__ dy,
-                                   const uint8_t* __restrict__ argmax,
-                                   const float* __restrict__ acc_in, const T* __restrict__ mask_y,
-                                   const float* __restrict__ mask_scale, void* __restrict__ dx,
-                                   long long total) {
+template <typename T, int VEC, typename G>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(ivf_pool_desc d, const T* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                   const float* __restrict__ acc_in, const T* __restrict__ mask_y,
+                   const float* __restrict__ mask_scale, void* __restrict__ dx, long long total) {
   const int cv = d.c / VEC;
+  const int KD = G::kd(d), KH = G::kh(d), KW = G::kw(d), SD = G::sd(d), SH = G::sh(d), SW = G::sw(d);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int c = (int)(idx % cv) * VEC;
@@ -112,31 +143,65 @@ __global__ void maxpool_bwd_kernel(ivf_pool_desc d, const T* __restrict__ dy,
     float g[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] = 0.f;
-    int tap = 0;
-    for (int a = 0; a < d.kd; ++a) {
+#pragma unroll
+    for (int a = 0; a < KD; ++a) {
       int nd = idd + d.pd - a;
-      for (int b = 0; b < d.kh; ++b) {
+      if (nd < 0 || (SD > 1 && nd % SD)) continue;
+      int od = SD > 1 ? nd / SD : nd;
+      if (od >= d.od) continue;
+#pragma unroll
+      for (int b = 0; b < KH; ++b) {
         int nh = ih + d.ph - b;
-        for (int e = 0; e < d.kw; ++e, ++tap) {
+        if (nh < 0 || (SH > 1 && nh % SH)) continue;
+        int oh = SH > 1 ? nh / SH : nh;
+        if (oh >= d.oh) continue;
+#pragma unroll
+        for (int e = 0; e < KW; ++e) {
           int nw = iw + d.pw - e;
-          if (nd < 0 || nh < 0 || nw < 0) continue;
-          if (nd % d.sd || nh % d.sh || nw % d.sw) continue;
-          int od = nd / d.sd, oh = nh / d.sh, ow = nw / d.sw;
-          if (od >= d.od || oh >= d.oh || ow >= d.ow) continue;
+          if (nw < 0 || (SW > 1 && nw % SW)) continue;
+          int ow = SW > 1 ? nw / SW : nw;
+          if (ow >= d.ow) continue;
+          const int tap = (a * KH + b) * KW + e;
           size_t opix = (((size_t)n * d.od + od) * d.oh + oh) * d.ow + ow;
+          const uint8_t* am = argmax + opix * d.c + c;
+          uint32_t a0, a1 = 0;
+          if constexpr (VEC == 8) {
+            uint2 pk = *reinterpret_cast<const uint2*>(am);
+            a0 = pk.x;
+            a1 = pk.y;
+          } else if constexpr (VEC == 4) {
+            a0 = *reinterpret_cast<const uint32_t*>(am);
+          } else {
+            a0 = am[0];
+          }
+          // skip the 16-byte gradient load when no channel of this vector selected this tap
+          bool any = false;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) any |= (((i < 4 ? a0 : a1) >> (8 * (i & 3))) & 0xffu) == (unsigned)tap;
+          if (!any) continue;
           float v[VEC];
           load_vec<T, VEC>(dy + opix * d.out_ld + d.out_coff + c, v);
-          const uint8_t* am = argmax + opix * d.c + c;
 #pragma unroll
           for (int i = 0; i < VEC; ++i)
-            if (am[i] == tap) g[i] += v[i];
+            if ((((i < 4 ? a0 : a1) >> (8 * (i & 3))) & 0xffu) == (unsigned)tap) g[i] += v[i];
         }
       }
     }
     size_t o = (size_t)ipix * d.in_ld + d.in_coff + c;
     if (d.flags & IVF_EP_ACCUM) {
+      if constexpr (VEC % 4 == 0) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) g[i] += acc_in[o + i];
+        for (int i = 0; i < VEC / 4; ++i) {
+          float4 a4 = *reinterpret_cast<const float4*>(acc_in + o + 4 * i);
+          g[4 * i] += a4.x;
+          g[4 * i + 1] += a4.y;
+          g[4 * i + 2] += a4.z;
+          g[4 * i + 3] += a4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g[i] += acc_in[o + i];
+      }
     }
     if (d.flags & IVF_EP_MASK) {
       float y[VEC];
@@ -177,20 +242,37 @@ int check_pool(const ivf_pool_desc* d) {
   return IVF_OK;
 }
 
+int pool_blocks(ivf_handle* h, long long total) {
+  long long b = (total + 255) / 256;
+  long long cap = (long long)h->sm_count * 64;
+  return (int)(b < cap ? b : cap);
+}
+
+#define IVF_POOL_GEO_DISPATCH(CALL)                                                              \
+  do {                                                                                           \
+    const int kd = d->kd, kh = d->kh, kw = d->kw, sd = d->sd, sh = d->sh, sw = d->sw;            \
+    if (kd == 3 && kh == 3 && kw == 3 && sd == 1 && sh == 1 && sw == 1) { using G = PoolGeo<3, 3, 3, 1, 1, 1>; CALL; } \
+    else if (kd == 1 && kh == 3 && kw == 3 && sd == 1 && sh == 2 && sw == 2) { using G = PoolGeo<1, 3, 3, 1, 2, 2>; CALL; } \
+    else if (kd == 3 && kh == 3 && kw == 3 && sd == 2 && sh == 2 && sw == 2) { using G = PoolGeo<3, 3, 3, 2, 2, 2>; CALL; } \
+    else if (kd == 2 && kh == 2 && kw == 2 && sd == 2 && sh == 2 && sw == 2) { using G = PoolGeo<2, 2, 2, 2, 2, 2>; CALL; } \
+    else if (kd == 1 && kh == 1 && kw == 1 && sd == 1 && sh == 1 && sw == 1) { using G = PoolGeo<1, 1, 1, 1, 1, 1>; CALL; } \
+    else { using G = PoolGeoDyn; CALL; }                                                         \
+  } while (0)
+
 template <typename T>
 int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint8_t* argmax,
           cudaStream_t st) {
   constexpr int V = full_vec<T>();
   long long opix = (long long)d->n * d->od * d->oh * d->ow;
   const int threads = 256;
-  if (vec_ok(d, V, in, out, nullptr)) {
+  if (vec_ok(d, V, in, out, argmax)) {
     long long total = opix * (d->c / V);
-    int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)h->sm_count * 32);
-    maxpool_fwd_kernel<T, V><<<blocks, threads, 0, st>>>(*d, (const T*)in, (T*)out, argmax, total);
+    IVF_POOL_GEO_DISPATCH((maxpool_fwd_kernel<T, V, G><<<pool_blocks(h, total), threads, 0, st>>>(
+        *d, (const T*)in, (T*)out, argmax, total)));
   } else {
     long long total = opix * d->c;
-    int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)h->sm_count * 32);
-    maxpool_fwd_kernel<T, 1><<<blocks, threads, 0, st>>>(*d, (const T*)in, (T*)out, argmax, total);
+    maxpool_fwd_kernel<T, 1, PoolGeoDyn><<<pool_blocks(h, total), threads, 0, st>>>(*d, (const T*)in, (T*)out,
+                                                                                  argmax, total);
   }
   IVF_LAUNCHED(h);
   return IVF_OK;
@@ -204,17 +286,17 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
   long long ipix = (long long)d->n * d->id * d->ih * d->iw;
   const int threads = 256;
   // the fp32-out path stores scalars, so only the typed loads need 16-byte alignment
-  bool v_ok = vec_ok(d, V, dy, mask_y, (d->flags & IVF_EP_OUT_F32) ? nullptr : dx);
+  bool v_ok = vec_ok(d, V, dy, mask_y, (d->flags & IVF_EP_OUT_F32) ? nullptr : dx) &&
+              (reinterpret_cast<uintptr_t>(argmax) & 15) == 0 &&
+              (acc_in == nullptr || (reinterpret_cast<uintptr_t>(acc_in) & 15) == 0);
   if (v_ok) {
     long long total = ipix * (d->c / V);
-    int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)h->sm_count * 32);
-    maxpool_bwd_kernel<T, V><<<blocks, threads, 0, st>>>(*d, (const T*)dy, argmax, acc_in,
-                                                         (const T*)mask_y, mask_scale, dx, total);
+    IVF_POOL_GEO_DISPATCH((maxpool_bwd_kernel<T, V, G><<<pool_blocks(h, total), threads, 0, st>>>(
+        *d, (const T*)dy, argmax, acc_in, (const T*)mask_y, mask_scale, dx, total)));
   } else {
     long long total = ipix * d->c;
-    int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)h->sm_count * 32);
-    maxpool_bwd_kernel<T, 1><<<blocks, threads, 0, st>>>(*d, (const T*)dy, argmax, acc_in,
-                                                         (const T*)mask_y, mask_scale, dx, total);
+    maxpool_bwd_kernel<T, 1, PoolGeoDyn><<<pool_blocks(h, total), threads, 0, st>>>(
+        *d, (const T*)dy, argmax, acc_in, (const T*)mask_y, mask_scale, dx, total);
   }
   IVF_LAUNCHED(h);
   return IVF_OK;

@@ -1,0 +1,256 @@
+"""Native ConvLSTM classifier runner (pt/models/convolution_lstm.py:63-132 + pt/models/CLSTM_4.py:69-85)
+as a fixed sequence of libivf launches, forward and BPTT data-gradient, CUDA-graph capturable.
+
+Schedule (results identical to the reference's step-major loop, :99-129, because layer l at step t
+depends on layer l-1 at step t only):
+  per layer:  x-convolution of ALL T steps as one implicit GEMM (4 gates side by side, bias in the
+              epilogue)  ->  T sequential steps { h-convolution accumulated into the gate
+              pre-activations by the conv epilogue (skipped at t=0: zero state); fused gate kernel }
+              ->  eval-BatchNorm + MaxPool2d(2) of all steps in one launch.
+  classifier: Linear(+softmax) on the last effective step (use_entire_seq=False).
+Frames are time-major ([t][b]...) so that a step's batch is contiguous.
+
+bf16 mode: the stride-2 5x5 x-convolutions run space-to-depth (stride-1 3x3 over 4*cin channels, the
+perturbation kernel / the pool kernel write that layout directly); hidden sizes below 8 are padded
+to 8 with zero weights (padded channels stay exactly 0: gates 0.5/0.5/0/0.5 on a zero state).
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import PFMT_S2D2_BF16, PFMT_TBHWC_F32
+from .engine import pack_dgrad, pack_fwd, strip_module_prefix
+from .ops import Act
+
+GATES = ("i", "f", "c", "o")
+
+
+def s2d_weight_2d(w, win):
+    """(co,ci,k,k) stride-2 kernel -> (co,4ci,win,win) stride-1 kernel over the 2-D space-to-depth
+    input; channel = (a*2+b)*ci + ch, source tap = 2*delta + parity."""
+    co, ci, kh, kw = w.shape
+    out = w.new_zeros(co, 4 * ci, win, win)
+    for a in range(2):
+        for b in range(2):
+            blk = (a * 2 + b) * ci
+            for dh in range(win):
+                if 2 * dh + a >= kh:
+                    continue
+                for dw in range(win):
+                    if 2 * dw + b >= kw:
+                        continue
+                    out[:, blk:blk + ci, dh, dw] = w[:, :, 2 * dh + a, 2 * dw + b]
+    return out
+
+
+class CLSTMEngine:
+    def __init__(self, state_dict, batch, clip, hidden, layers, num_classes, kernel=5, conv_stride=2, mode="bf16",
+                 softmax=False, batch_norm=True, effective_step=(7, 15, 23, 31), device=None, in_channels=3):
+        assert mode in ("bf16", "fp32")
+        if kernel != 5 or conv_stride != 2:
+            raise _lib.IvfError("native ConvLSTM supports kernel 5 / conv_stride 2 (the reference configs)")
+        self.mode = mode
+        self.dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.device = dev = torch.device(device if device is not None else "cuda")
+        _lib.handle(dev)
+        sd = {k: v.detach().to(device=dev, dtype=torch.float32) for k, v in strip_module_prefix(state_dict).items()
+              if v.is_floating_point()}
+        self.B, (self.T, self.H, self.W) = batch, clip
+        self.C, self.L, self.hid, self.softmax = in_channels, layers, hidden, bool(softmax)
+        self.eff = list(effective_step)
+        bf = mode == "bf16"
+        he = max(8, (hidden + 7) // 8 * 8) if bf else hidden  # padded hidden size
+        self.he = he
+        B, T = batch, clip[0]
+        N = T * B
+        if self.H % 2 or self.W % 2:
+            raise _lib.IvfError("native ConvLSTM needs even frame sizes")
+
+        def pad_gates(w4, cin_eff, cin):
+            """list of 4 per-gate [hid, cin, k, k] -> [4*he, cin_eff, 1, k, k] (zero padded)."""
+            out = torch.zeros((4 * he, cin_eff, 1, 5, 5), device=dev)
+            for gi, w in enumerate(w4):
+                out[gi * he:gi * he + hidden, :cin, 0] = w
+            return out
+
+        if batch_norm:
+            g, b_, mu, var = (sd["clstm.bn." + k] for k in ("weight", "bias", "running_mean", "running_var"))
+            sc = g / torch.sqrt(var + 1e-5)  # BatchNorm2d(eps=1e-05), convolution_lstm.py:85
+            self.bn_scale = torch.zeros(he, device=dev)
+            self.bn_shift = torch.zeros(he, device=dev)
+            self.bn_scale[:hidden] = sc
+            self.bn_shift[:hidden] = b_ - mu * sc
+        else:
+            self.bn_scale = torch.zeros(he, device=dev)
+            self.bn_scale[:hidden] = 1.0
+            self.bn_shift = torch.zeros(he, device=dev)
+
+        # ---- input operand of layer 0
+        if bf:
+            self.in_fmt = PFMT_S2D2_BF16
+            self.xin = Act.empty(N, 1, self.H // 2, self.W // 2, 16, torch.bfloat16, dev, zero=True)
+            self.g_xin = Act.empty(N, 1, self.H // 2, self.W // 2, 16, torch.bfloat16, dev, zero=True)
+        else:
+            self.in_fmt = PFMT_TBHWC_F32
+            self.xin = Act.empty(N, 1, self.H, self.W, in_channels, torch.float32, dev)
+            self.g_xin = Act.empty(N, 1, self.H, self.W, in_channels, torch.float32, dev)
+
+        self.layers = []
+        hin, win, cin = self.H, self.W, in_channels
+        x_act, gx_in = self.xin, self.g_xin
+        for l in range(layers):
+            p = "clstm.cell%d." % l
+            cin_real = cin if l == 0 else hidden
+            cin_eff = cin_real if l == 0 else he
+            wx = pad_gates([sd[p + "Wx%s.weight" % g] for g in GATES], cin_eff, cin_real)
+            bias = torch.zeros(4 * he, device=dev)
+            for gi, g in enumerate(GATES):
+                bias[gi * he:gi * he + hidden] = sd[p + "Wx%s.bias" % g]
+            wh = pad_gates([sd[p + "Wh%s.weight" % g] for g in GATES], he, hidden)
+            ho, wo = hin // 2, win // 2
+            if (hin + 4 - 5) // 2 + 1 != ho or (win + 4 - 5) // 2 + 1 != wo:
+                raise _lib.IvfError("ConvLSTM layer %d: odd input %dx%d (the reference asserts here too)" % (l, hin, win))
+            last = l == layers - 1
+            s2d_out = bf and not last
+            if s2d_out and ((ho // 2) % 2 or (wo // 2) % 2):
+                raise _lib.IvfError("bf16 ConvLSTM needs an even pooled map between layers; use mode='fp32'")
+            rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias.contiguous(), ones=torch.ones(4 * he, device=dev))
+            if bf:
+                w2 = s2d_weight_2d(wx[:, :, 0], 3)  # [4he, 4*cin_eff, 3, 3]
+                if l == 0:  # operand buffer has 16 channels (12 used)
+                    w2 = torch.cat([w2, w2.new_zeros(4 * he, 16 - w2.shape[1], 3, 3)], dim=1)
+                w2 = w2.unsqueeze(2)
+                rec.update(wx_f=pack_fwd(w2, mode), wx_d=pack_dgrad(w2, mode), xk=(1, 3, 3), xs=(1, 1, 1), xpf=(0, 1, 1),
+                           xdpf=(0, 1, 1))
+            else:
+                rec.update(wx_f=pack_fwd(wx, mode), wx_d=pack_dgrad(wx, mode), xk=(1, 5, 5), xs=(1, 2, 2), xpf=(0, 2, 2))
+            rec.update(wh_f=pack_fwd(wh, mode), wh_d=pack_dgrad(wh, mode))
+            rec["x"], rec["g_x"] = x_act, gx_in
+            rec["gx"] = Act.empty(N, 1, ho, wo, 4 * he, torch.float32, dev)            # gate pre-activations
+            rec["h"] = Act.empty(N, 1, ho, wo, he, self.dtype, dev, zero=True)
+            rec["c"] = torch.zeros((N, ho, wo, he), dtype=torch.float32, device=dev)
+            rec["gact"] = torch.zeros((N, ho * wo, 4 * he), dtype=torch.float32, device=dev)
+            rec["argmax"] = torch.zeros((N, ho // 2, wo // 2, he), dtype=torch.uint8, device=dev)
+            if s2d_out:
+                rec["pooled"] = Act.empty(N, 1, ho // 4, wo // 4, 4 * he, self.dtype, dev, zero=True)
+            else:
+                rec["pooled"] = Act.empty(N, 1, ho // 2, wo // 2, he, self.dtype, dev, zero=True)
+            rec["s2d_out"] = s2d_out
+            rec["g_pooled"] = rec["pooled"].like(zero=True)
+            rec["dH"] = torch.zeros((N, ho, wo, he), dtype=torch.float32, device=dev)
+            rec["dc"] = torch.zeros((B, ho, wo, he), dtype=torch.float32, device=dev)
+            rec["dpre"] = Act.empty(N, 1, ho, wo, 4 * he, self.dtype, dev, zero=True)
+            self.layers.append(rec)
+            x_act, gx_in = rec["pooled"], rec["g_pooled"]
+            hin, win = ho // 2, wo // 2
+        self.fh, self.fw = hin, win
+
+        # ---- classifier: Linear over the NCHW-flattened last effective step (CLSTM_4.py:78-80), columns
+        # permuted once to our channels-last flattening
+        wfc = sd["endFC.weight"]
+        ncls = wfc.shape[0]
+        if wfc.shape[1] != hidden * hin * win:
+            raise _lib.IvfError("endFC expects %d features, the stack produces %d (use_entire_seq is not supported)"
+                                % (wfc.shape[1], hidden * hin * win))
+        wp = torch.zeros((ncls, hin * win, he), device=dev)
+        wp[:, :, :hidden] = wfc.view(ncls, hidden, hin * win).permute(0, 2, 1)
+        self.w_fc = wp.reshape(ncls, -1).contiguous()
+        self.b_fc = sd["endFC.bias"].contiguous()
+        self.num_classes = ncls
+        self.logits = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
+        self.probs = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
+        self.dprobs = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
+        self.x = torch.zeros((B, in_channels, T, self.H, self.W), dtype=torch.float32, device=dev)
+        self.dm = torch.zeros((B, T), dtype=torch.float32, device=dev)
+        self.zero_mask = torch.zeros((B, T), dtype=torch.float32, device=dev)
+        self.g_feat_raw = torch.zeros((B, hin * win * he), dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ helpers
+    def _step(self, act, t):
+        """Act view of step t's B frames of a time-major [T*B,...] Act."""
+        B = self.B
+        per = act.d * act.h * act.w * act.ld
+        buf = act.buf.view(-1)[t * B * per:(t + 1) * B * per]
+        return Act(buf, B, act.d, act.h, act.w, act.ld, act.coff, act.c)
+
+    def _feat(self, act, t):
+        a = self._step(act, t)
+        k = a.h * a.w * a.ld
+        return Act(a.buf, self.B, 1, 1, 1, k, 0, k)
+
+    def set_input(self, x):
+        assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
+        self.x.copy_(x, non_blocking=True)
+
+    def set_targets(self, targets):
+        self.dprobs.zero_()
+        self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, mask=None, perturb="reverse"):
+        self._mask, self._perturb = (self.zero_mask if mask is None else mask), perturb
+        ops.perturb_fwd(self.x, self._mask, perturb, self.in_fmt, self.xin.buf)
+        B, T, he = self.B, self.T, self.he
+        for rec in self.layers:
+            ops.conv3d(rec["x"], rec["wx_f"], rec["gx"], rec["xk"], rec["xs"], rec["xpf"], scale=rec["ones"],
+                       shift=rec["bias"])
+            m = B * rec["ho"] * rec["wo"]
+            for t in range(T):
+                gx_t = self._step(rec["gx"], t)
+                if t > 0:
+                    ops.conv3d(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx_t)
+                ops.clstm_gates_fwd(gx_t.buf.view(m, 4 * he), rec["c"][(t - 1) * B:t * B] if t > 0 else None,
+                                    rec["c"][t * B:(t + 1) * B], self._step(rec["h"], t).buf, rec["gact"][t * B:(t + 1) * B].view(m, 4 * he))
+            ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
+                              rec["pooled"].buf, rec["argmax"], s2d=rec["s2d_out"])
+        te = self.eff[-1]
+        ops.head_fwd(self._feat(self.layers[-1]["pooled"], te), self.w_fc, self.b_fc, self.softmax, self.probs, self.logits)
+        return self.probs
+
+    # ------------------------------------------------------------------ backward (BPTT data gradient)
+    def backward(self, to_mask=True):
+        B, T, he = self.B, self.T, self.he
+        te = self.eff[-1]
+        top = self.layers[-1]
+        # only the last effective step feeds the classifier: its rows of g_pooled are rewritten, the rest stay 0
+        ops.head_bwd(self._feat(top["g_pooled"], te), self.w_fc, self.softmax, self.probs, self.dprobs)
+        for rec in reversed(self.layers):
+            ops.bn_pool2d_bwd(rec["g_pooled"].buf, rec["argmax"], self.bn_scale, rec["dH"], s2d=rec["s2d_out"])
+            rec["dc"].zero_()
+            m = B * rec["ho"] * rec["wo"]
+            dH = Act(rec["dH"], T * B, 1, rec["ho"], rec["wo"], he, 0, he)
+            for t in range(T - 1, -1, -1):
+                ops.clstm_gates_bwd(rec["gact"][t * B:(t + 1) * B].view(m, 4 * he),
+                                    rec["c"][(t - 1) * B:t * B] if t > 0 else None, rec["c"][t * B:(t + 1) * B],
+                                    self._step(dH, t).buf, rec["dc"], self._step(rec["dpre"], t).buf)
+                if t > 0:
+                    dprev = self._step(dH, t - 1)
+                    if self.mode == "fp32":
+                        ops.conv3d(self._step(rec["dpre"], t), rec["wh_d"], dprev, (1, 5, 5), (1, 1, 1), (0, 2, 2),
+                                   acc_in=dprev, transposed=1)
+                    else:
+                        ops.conv3d(self._step(rec["dpre"], t), rec["wh_d"], dprev, (1, 5, 5), (1, 1, 1), (0, 2, 2),
+                                   acc_in=dprev)
+            if self.mode == "fp32":
+                ops.conv3d(rec["dpre"], rec["wx_d"], rec["g_x"], (1, 5, 5), (1, 2, 2), (0, 2, 2), transposed=1)
+            else:
+                ops.conv3d(rec["dpre"], rec["wx_d"], rec["g_x"], rec["xk"], (1, 1, 1), rec["xdpf"])
+        if to_mask:
+            ops.perturb_bwd(self.x, self._mask, self._perturb, self.in_fmt, self.g_xin.buf, self.dm)
+        return self.dm
+
+    # ------------------------------------------------------------------ Grad-CAM operands
+    def gradcam_operands(self):
+        """Activations / gradients of the stacked effective-step outputs (pt/pytorch-grad-cam/grad-cam.py:42-49,
+        pt/grad_cam_videos.py:87-91): [B, E, h, w, hid] channels-last; only the last step has a gradient
+        (the classifier reads output[-1] only)."""
+        top = self.layers[-1]
+        B, E = self.B, len(self.eff)
+        hw, he = self.fh * self.fw, self.he
+        pooled = top["pooled"].buf.view(self.T, B, hw * he)
+        act = pooled[self.eff].permute(1, 0, 2).contiguous().view(B, E, self.fh, self.fw, he)
+        grad = torch.zeros((B, E, hw * he), dtype=torch.float32, device=self.device)
+        g = Act(self.g_feat_raw, B, 1, 1, 1, hw * he, 0, hw * he)
+        ops.head_bwd(g, self.w_fc, self.softmax, self.probs, self.dprobs)
+        grad[:, E - 1] = self.g_feat_raw
+        return (Act(act, B, E, self.fh, self.fw, he, 0, he),
+                Act(grad.view(B, E, self.fh, self.fw, he), B, E, self.fh, self.fw, he, 0, he))

@@ -6,13 +6,17 @@ the identity, the ONE BatchNorm2d shared by all layers/steps uses running stats 
 import torch
 import torch.nn.functional as F
 
+from .i3d_oracle import _RoundGrad, _q, quant_input
 
-def _cell(sd, p, x, h, c, k, stride):
+
+def _cell(sd, p, x, h, c, k, stride, quant=False):
     pad = (k - 1) // 2
+    wq = (lambda w: w.bfloat16().float()) if quant else (lambda w: w)
 
     def gate(g):
-        return (F.conv2d(x, sd[p + ".Wx%s.weight" % g], sd[p + ".Wx%s.bias" % g], stride=stride, padding=pad)
-                + F.conv2d(h, sd[p + ".Wh%s.weight" % g], None, stride=1, padding=pad))
+        pre = (F.conv2d(x, wq(sd[p + ".Wx%s.weight" % g]), sd[p + ".Wx%s.bias" % g], stride=stride, padding=pad)
+               + F.conv2d(h, wq(sd[p + ".Wh%s.weight" % g]), None, stride=1, padding=pad))
+        return _RoundGrad.apply(pre) if quant else pre  # the stored gate-pre-activation gradient is bf16
 
     ci = torch.sigmoid(gate("i"))  # + c * Wci with Wci == 0 (convolution_lstm.py:50-54)
     cf = torch.sigmoid(gate("f"))
@@ -22,9 +26,14 @@ def _cell(sd, p, x, h, c, k, stride):
 
 
 def forward(sd, x, num_layers, hidden, kernel=5, conv_stride=2, step=None, effective_step=(7, 15, 23, 31),
-            batch_norm=True, softmax=False, use_entire_seq=False, return_outputs=False):
-    """x [B,C,T,H,W] -> logits/probs [B,classes] (pt/models/CLSTM_4.py:69-85)."""
+            batch_norm=True, softmax=False, use_entire_seq=False, return_outputs=False, quant=False):
+    """x [B,C,T,H,W] -> logits/probs [B,classes] (pt/models/CLSTM_4.py:69-85).
+    quant=True: the same network with the bf16 rounding points of the tensor-core path (bf16 conv
+    weights, bf16-stored clip / hidden states / pooled maps and their stored gradients; fp32 cell
+    state, gate math and accumulation) — see oracle/i3d_oracle.py."""
     B = x.shape[0]
+    if quant:
+        x = quant_input(x)
     step = x.shape[2] if step is None else step
     state = [None] * num_layers
     outputs = []
@@ -37,12 +46,16 @@ def forward(sd, x, num_layers, hidden, kernel=5, conv_stride=2, step=None, effec
                 z = torch.zeros(B, hidden, hh, ww, dtype=x.dtype, device=x.device)
                 state[i] = (z, z)
             h, c = state[i]
-            cur, new_c = _cell(sd, p, cur, h, c, kernel, conv_stride)
+            cur, new_c = _cell(sd, p, cur, h, c, kernel, conv_stride, quant)
+            if quant:
+                cur = _q(cur)  # h is stored in bf16 (next step's h-conv operand and the pool input)
             state[i] = (cur, new_c)
             if batch_norm:
                 cur = F.batch_norm(cur, sd["clstm.bn.running_mean"], sd["clstm.bn.running_var"],
                                    sd["clstm.bn.weight"], sd["clstm.bn.bias"], training=False, eps=1e-5)
             cur = F.max_pool2d(cur, 2)
+            if quant:
+                cur = _q(_RoundGrad.apply(cur))
         if t in effective_step:
             outputs.append(cur)
     if use_entire_seq:

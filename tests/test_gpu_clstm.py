@@ -1,0 +1,166 @@
+"""GPU (-m gpu): the native ConvLSTM classifier (config C3: KTH, 32 frames of 120x160, 2 layers, 5x5
+kernels, conv stride 2, reverse perturbation) against the oracle and the reference's golden vectors:
+forward logits, d logit / d mask, Grad-CAM, the drop-in module surface and the mask search."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLD, quiet, rel_err
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(num_layers=2, kernel=5, conv_stride=2, effective_step=(7, 15, 23, 31))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from interpreting_video_features_b200 import _lib
+    _lib.handle()
+    return torch.device("cuda")
+
+
+def build(hid, softmax=False):
+    """The model of oracle/pin_against_reference.py §6 (same seed, same BN perturbation)."""
+    from interpreting_video_features_b200.pt.models import CLSTM_4
+    torch.manual_seed(0)
+    m = quiet(CLSTM_4.Model, num_classes=6, nb_lstm_units=hid, channels=3, conv_kernel_size=(5, 5), lstm_layers=2,
+              step=32, conv_stride=2, image_size=(160, 120), effective_step=[7, 15, 23, 31],
+              batch_normalization=True, dropout=0.5, add_softmax=softmax).eval()
+    with torch.no_grad():
+        m.clstm.bn.running_mean.uniform_(-0.05, 0.05)
+        m.clstm.bn.running_var.uniform_(0.5, 1.5)
+        m.clstm.bn.weight.uniform_(0.5, 1.5)
+        m.clstm.bn.bias.uniform_(-0.1, 0.1)
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def engine(sd, hid, batch, mode, dev, softmax=False):
+    from interpreting_video_features_b200.engine_clstm import CLSTMEngine
+    return CLSTMEngine(sd, batch, (32, 120, 160), hid, 2, 6, mode=mode, softmax=softmax, device=dev)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("hid", [4, 32])
+def test_forward_and_mask_gradient(dev, hid, mode):
+    from oracle import clstm_oracle, mask_oracle, synthetic
+    g = np.load(os.path.join(GOLD, "clstm_hid%d.npz" % hid))
+    _, sd = build(hid)
+    x1 = synthetic.clips(1, t=32, h=120, w=160) / 255.0
+    x = torch.cat([x1, synthetic.clips(2, t=32, h=120, w=160)[1:] / 255.0])
+    masks = torch.stack([torch.from_numpy(g["mask"]), torch.rand(32, generator=torch.Generator().manual_seed(8))])
+    eng = engine(sd, hid, 2, mode, dev)
+    eng.set_input(x.to(dev))
+    eng.set_targets(torch.tensor([2, 4]))
+    logits = eng.forward(masks.to(dev), "reverse").clone().cpu()
+    dm = eng.backward().clone().cpu()
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    # clip 0 is the reference's golden case (d logit[2] / d mask under the reverse perturbation)
+    assert rel_err(logits[0], g["logits"][0]) < tol, rel_err(logits[0], g["logits"][0])
+    if mode == "fp32":
+        assert rel_err(dm[0], g["dmask"]) < 2e-3, rel_err(dm[0], g["dmask"])
+    for i, tgt in enumerate((2, 4)):
+        mi = masks[i].clone().requires_grad_()
+        out = clstm_oracle.forward(sd, mask_oracle.perturb_sequence(x[i:i + 1], mi, "reverse"), hidden=hid,
+                                   quant=(mode == "bf16"), **KW)
+        (gm,) = torch.autograd.grad(out[0, tgt], mi)
+        assert rel_err(logits[i], out.detach()[0]) < tol
+        assert rel_err(dm[i], gm) < (2e-3 if mode == "fp32" else 3e-2), (i, rel_err(dm[i], gm))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_freeze_perturbation_and_softmax(dev, mode):
+    from oracle import clstm_oracle, mask_oracle, synthetic
+    _, sd = build(4, softmax=True)
+    x = synthetic.clips(2, t=32, h=120, w=160) / 255.0
+    m = torch.rand((2, 32), generator=torch.Generator().manual_seed(2))
+    eng = engine(sd, 4, 2, mode, dev, softmax=True)
+    eng.set_input(x.to(dev))
+    eng.set_targets(torch.tensor([1, 5]))
+    p = eng.forward(m.to(dev), "freeze").clone().cpu()
+    dm = eng.backward().clone().cpu()
+    for i, tgt in enumerate((1, 5)):
+        mi = m[i].clone().requires_grad_()
+        out = clstm_oracle.forward(sd, mask_oracle.perturb_sequence(x[i:i + 1], mi, "freeze"), hidden=4, softmax=True,
+                                   quant=(mode == "bf16"), **KW)
+        (gm,) = torch.autograd.grad(out[0, tgt], mi)
+        assert rel_err(p[i], out.detach()[0]) < (1e-4 if mode == "fp32" else 1e-2)
+        assert rel_err(dm[i], gm) < (2e-3 if mode == "fp32" else 3e-2), (i, rel_err(dm[i], gm))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("hid", [4, 32])
+def test_gradcam_clstm_dropin(dev, hid, mode):
+    from interpreting_video_features_b200.pt.grad_cam_videos import GradCamVideo
+    from oracle import gradcam_oracle, synthetic
+    g = np.load(os.path.join(GOLD, "clstm_hid%d.npz" % hid))
+    model, sd = build(hid)
+    model = model.to(dev).set_mode(mode)
+    xc = synthetic.clips(1, t=32, h=120, w=160) / 255.0
+    gc = GradCamVideo(model=model, target_layer_names=['clstm'], class_dict=None, use_cuda=True,
+                      input_spatial_size=(160, 120), normalizePerFrame=True, archType="CLSTM")
+    cam, out = gc(xc.to(dev), 2)
+    assert cam.shape == (32, 120, 160)
+    assert rel_err(out.cpu(), g["cam_output"]) < (1e-4 if mode == "fp32" else 1e-2)
+    want, _, low = gradcam_oracle.gradcam_clstm(sd, xc, 2, (160, 120), True, hidden=hid, **KW)
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(cam), np.isnan(want))
+    assert np.abs(cam[ok] - want[ok]).max() < (1e-3 if mode == "fp32" else 5e-2)
+    if mode == "fp32":
+        samp = cam[::8, ::12, ::16]
+        gk = ~np.isnan(g["cam_sample"])
+        assert np.abs(samp[gk] - g["cam_sample"][gk]).max() < 1e-3
+
+
+def test_dropin_model_autograd_loop(dev):
+    """model(perturb_sequence(x, sigmoid(m), 'reverse')) + stock Adam, as the KTH driver does
+    (pt/FindMasksComparison_I3D_KTH.py:250-270), against the oracle loop."""
+    from interpreting_video_features_b200.pt import mask
+    from oracle import clstm_oracle, mask_oracle, synthetic
+    model, sd = build(4, softmax=True)
+    model = model.to(dev).set_mode("fp32")
+    x = synthetic.clips(1, t=32, h=120, w=160) / 255.0
+    raw = torch.tensor([-5.] * 8 + [5.] * 16 + [-5.] * 8)
+    tm = raw.clone().to(dev).requires_grad_()
+    opt = torch.optim.Adam([tm], lr=0.2)
+    losses = []
+    for _ in range(3):
+        mc = torch.sigmoid(tm)
+        loss = 0.02 * torch.sum(torch.abs(mc)) + 0.04 * mask.calc_tv_norm(mc, 3, 3) + \
+            model(mask.perturb_sequence(x.to(dev), mc, 'reverse'))[0, 2]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    o = clstm_oracle.Model(sd, hidden=4, softmax=True, **KW)
+    tmo = raw.clone().requires_grad_()
+    rec = {}
+    final, _ = mask_oracle.mask_search(x, o, 0, [2], tmo, 0.02, 0.04, 3, mask_type="reverse", record=rec)
+    np.testing.assert_allclose(losses, rec["loss"], rtol=1e-4)
+    np.testing.assert_allclose(torch.sigmoid(tm).detach().cpu().numpy(), final.numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_clstm_mask_search_reverse(dev):
+    """Config C3: batched mask search on the ConvLSTM with the reverse perturbation, 20 iterations, vs the
+    oracle loop (bf16 path vs fp32 reference path: final-mask IoU)."""
+    from interpreting_video_features_b200.search import MaskSearch
+    from oracle import clstm_oracle, mask_oracle, synthetic
+    _, sd = build(32, softmax=True)
+    x = synthetic.clips(2, t=32, h=120, w=160) / 255.0
+    targets = torch.tensor([2, 4])
+    raw0 = torch.tensor([-5.] * 8 + [5.] * 16 + [-5.] * 8).repeat(2, 1)
+    eng = engine(sd, 32, 2, "bf16", dev, softmax=True)
+    res = MaskSearch(eng, lam1=0.02, lam2=0.04, n_iter=20, perturb="reverse").run(x.to(dev), targets,
+                                                                                raw_masks=raw0.to(dev))
+    o = clstm_oracle.Model(sd, hidden=32, softmax=True, **KW)
+    for i in range(2):
+        tm = raw0[i].clone().requires_grad_()
+        final, cls = mask_oracle.mask_search(x[i:i + 1], o, 0, [int(targets[i])], tm, 0.02, 0.04, 20,
+                                             mask_type="reverse")
+        a, b = res["time_mask"][i].cpu() > 0.5, final > 0.5
+        union = float((a | b).sum())
+        assert union == 0 or float((a & b).sum()) / union >= 0.95
+        assert float((res["time_mask"][i].cpu() - final).abs().max()) < 2e-2
+        assert abs(float(res["freeze_score"][i]) - cls) < 1e-2 * abs(cls) + 1e-5

@@ -2,7 +2,7 @@
 # One gpurun call: the driver's GPU test command, smoke, bench, then the ncu launch list of one iteration.
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name" ; timeout "$TMO" "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/$name.log; tail -n 12 gpurun_out/$name.log | cut -c1-600; }
-TMO=2400 run t_gpu_all python -m pytest tests -x -q -m gpu
+TMO=2400 run t_gpu_all python -m pytest tests -q -m gpu
 TMO=300 run t_smoke python -c "import __graft_entry__ as g; g.smoke()"
 TMO=900 run bench python bench.py --steps 20 --warmup 3
 TMO=300 run prof_plain python tools/profile_step.py
