@@ -154,12 +154,14 @@ def conv_time_per_step(eng):
         return r
 
     ops.conv3d = timed
+    streams, eng.use_streams = eng.use_streams, False  # serialised: one kernel at a time on one stream
     try:
         eng.forward(eng._mask, eng._perturb)
         eng.backward(to_mask=True)
         torch.cuda.synchronize()
     finally:
         ops.conv3d = orig
+        eng.use_streams = streams
     return sum(a.elapsed_time(b) for a, b in events) * 1e-3, len(events)
 
 

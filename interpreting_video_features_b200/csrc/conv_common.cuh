@@ -1,0 +1,235 @@
+// Device helpers shared by the two tcgen05 convolution kernels (conv_tc.cu: TMA-im2col operand;
+// conv_slab.cu: shared-memory resident halo slab operand): mbarrier / TMA / UMMA / TMEM wrappers and the
+// fused epilogue (eval-BatchNorm affine, ReLU, fp32 consumer sum, ReLU'/BN' mask, bf16 or fp32 store).
+#pragma once
+#include "common.cuh"
+
+namespace ivf_tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  // try_wait suspends in hardware for a bounded time per call; a pipeline bug must not hang the
+  // GPU, so after ~2^24 failed probes (seconds) the CTA traps and the launch reports an error.
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) {
+      printf("libivf: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, parity);
+      __trap();
+    }
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// tiled 5-D box (c, w, h, d, n): out-of-range coordinates are zero filled = the 'same' padding
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c,
+                                            int w, int h, int d, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const CUtensorMap* map,
+                                                   uint64_t* bar, int c, int w, int h, int d, int n,
+                                                   uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d),
+      "r"(n), "h"(ow), "h"(oh), "h"(od)
+      : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset,
+// [61,64) swizzle type.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes,
+                                                   uint32_t layout_type, uint32_t base_offset = 0) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;  // LBO (unused for swizzled K-major; CUTLASS writes 1)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7u) << 49;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Epilogue of 16 consecutive produced channels [nb, nb+16) of one output pixel.
+//   r          : the fp32 accumulators as loaded from TMEM
+//   sc/sh/ms   : per-channel scale / shift / mask-scale of these 16 channels (shared memory)
+//   out_row    : element offset of the pixel's channel 0 in `out` (and acc_in); mask_row likewise
+struct EpilogueArgs {
+  int cout, flags;
+  const float* acc_in;
+  const __nv_bfloat16* mask_y;
+  void* out;
+};
+
+__device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const uint32_t (&r)[16], int nb,
+                                                 const float* sc, const float* sh, const float* ms,
+                                                 size_t out_row, size_t mask_row) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  const bool full = nb + 16 <= e.cout;
+  if (e.flags & IVF_EP_ACCUM) {
+    if (full) {
+      const float4* a4 = reinterpret_cast<const float4*>(e.acc_in + out_row + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 a = a4[j];
+        v[4 * j + 0] += a.x;
+        v[4 * j + 1] += a.y;
+        v[4 * j + 2] += a.z;
+        v[4 * j + 3] += a.w;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (nb + j < e.cout) v[j] += e.acc_in[out_row + nb + j];
+    }
+  }
+  if (e.flags & IVF_EP_AFFINE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+  }
+  if (e.flags & IVF_EP_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (e.flags & IVF_EP_MASK) {
+    if (full) {
+      const uint4* m4 = reinterpret_cast<const uint4*>(e.mask_y + mask_row + nb);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint4 mm = m4[hh];
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int jj = hh * 8 + j;
+          v[jj] = __bfloat162float(mb[j]) > 0.f ? v[jj] * ms[jj] : 0.f;
+        }
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (nb + j < e.cout)
+          v[j] = __bfloat162float(e.mask_y[mask_row + nb + j]) > 0.f ? v[j] * ms[j] : 0.f;
+    }
+  }
+  if (e.flags & IVF_EP_OUT_F32) {
+    float* o = reinterpret_cast<float*>(e.out) + out_row + nb;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (nb + j < e.cout) o[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + out_row + nb;
+    if (full) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (nb + j < e.cout) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+}  // namespace ivf_tc
+
+// ---- host side shared by both kernels: driver entry points for tensor-map encoding -------------
+typedef CUresult (*IvfEncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                      cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*IvfEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+extern IvfEncodeIm2colFn ivf_encode_im2col;
+extern IvfEncodeTiledFn ivf_encode_tiled;
+int ivf_load_driver_entry_points();
+
+// slab kernel (conv_slab.cu): returns IVF_EUNSUPPORTED without launching when the layer does not fit it
+int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+                           const float* scale, const float* shift, const float* acc_in,
+                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st);
+bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d);

@@ -61,11 +61,14 @@ conv_igemm_f32_kernel(F32ConvParams p, const float* __restrict__ in, const float
   const int tx = tid % (BN / TN);
   const int ty = tid / (BN / TN);
 
-  float acc[TM][TN];
+  // Blocked summation: products are accumulated in `part` over 64 consecutive k and then folded
+  // into `acc`, so the rounding error grows like 64 + K/64 instead of K (K is up to 3 456 here; the
+  // class gradient of the mask search is a cancellation-heavy 1e-9 quantity).
+  float acc[TM][TN], part[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = part[i][j] = 0.f;
 
   const int a_k = tid % BK;
   const int a_r = tid / BK;
@@ -131,7 +134,16 @@ conv_igemm_f32_kernel(F32ConvParams p, const float* __restrict__ in, const float
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
+    }
+    if (((k0 / BK) & 3) == 3 || k0 + BK >= p.K) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          acc[i][j] += part[i][j];
+          part[i][j] = 0.f;
+        }
     }
     __syncthreads();
   }

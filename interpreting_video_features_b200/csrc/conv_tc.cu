@@ -13,15 +13,20 @@
 // GEMM view: D[M=128 pixels][N=cout tile] += A[128][kchunk] * B[N][kchunk]^T per (tap, channel
 // chunk).  Warp roles: warp 0 = TMA producer (+TMEM alloc), warp 1 = MMA issuer (one lane),
 // warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4).
-#include "common.cuh"
+#include "conv_common.cuh"
 
 #include <cstring>
 
+IvfEncodeIm2colFn ivf_encode_im2col = nullptr;
+IvfEncodeTiledFn ivf_encode_tiled = nullptr;
+
 namespace {
+
+using namespace ivf_tc;
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 
 struct TcParams {
   int M;                 // n*od*oh*ow
@@ -40,104 +45,6 @@ struct TcParams {
   uint32_t a_stage_bytes, b_stage_bytes;  // smem pitch of the A / B part of a stage
   uint32_t tx_bytes;                      // bytes the two TMA boxes of a stage deliver
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  // try_wait suspends in hardware for a bounded time per call; a pipeline bug must not hang the
-  // GPU, so after ~2^24 failed probes (seconds) the CTA traps and the launch reports an error.
-  uint32_t spins = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 24)) {
-      printf("libivf: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
-      __trap();
-    }
-  } while (!done);
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const CUtensorMap* map,
-                                                   uint64_t* bar, int c, int w, int h, int d, int n,
-                                                   uint16_t ow, uint16_t oh, uint16_t od) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d),
-      "r"(n), "h"(ow), "h"(oh), "h"(od)
-      : "memory");
-}
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) swizzle type.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;  // LBO (unused for swizzled K-major; CUTLASS writes 1)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // KCH = channels per K stage: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
 template <int KCH>
@@ -239,9 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) |
-                             ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t idesc = make_idesc_bf16(TILE_M, p.bn);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < kiters; ++it) {
@@ -274,86 +179,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t taddr_row = tmem_acc + ((uint32_t)(q * 32) << 16);
     const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
     const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
+    EpilogueArgs ea;
+    ea.cout = p.cout;
+    ea.flags = p.flags;
+    ea.acc_in = acc_in;
+    ea.mask_y = mask_y;
+    ea.out = out;
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
       uint32_t r[16];
       tmem_ld16(taddr_row + c0, r);
       const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
       if (!row_ok || nb >= p.cout) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      const bool full = nb + 16 <= p.cout;
-      if (p.flags & IVF_EP_ACCUM) {
-        if (full) {
-          const float4* a4 = reinterpret_cast<const float4*>(acc_in + out_row + nb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 a = a4[j];
-            v[4 * j + 0] += a.x;
-            v[4 * j + 1] += a.y;
-            v[4 * j + 2] += a.z;
-            v[4 * j + 3] += a.w;
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout) v[j] += acc_in[out_row + nb + j];
-        }
-      }
-      if (p.flags & IVF_EP_AFFINE) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_scale[c0 + j], s_shift[c0 + j]);
-      }
-      if (p.flags & IVF_EP_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.flags & IVF_EP_MASK) {
-        if (full) {
-          const uint4* m4 = reinterpret_cast<const uint4*>(mask_y + mask_row + nb);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint4 mm = m4[hh];
-            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              int jj = hh * 8 + j;
-              v[jj] = __bfloat162float(mb[j]) > 0.f ? v[jj] * s_mscale[c0 + jj] : 0.f;
-            }
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout)
-              v[j] = __bfloat162float(mask_y[mask_row + nb + j]) > 0.f ? v[j] * s_mscale[c0 + j]
-                                                                         : 0.f;
-        }
-      }
-      if (p.flags & IVF_EP_OUT_F32) {
-        float* o = reinterpret_cast<float*>(out) + out_row + nb;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(o)[j] =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout) o[j] = v[j];
-        }
-      } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + out_row + nb;
-        if (full) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row);
     }
   }
 
@@ -403,20 +240,9 @@ probe_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int cw, int ch, int
 
 // ---- host side ---------------------------------------------------------------------------
 
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
-                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                   CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
-EncodeIm2colFn g_encode_im2col = nullptr;
-EncodeTiledFn g_encode_tiled = nullptr;
-
-int load_driver_entry_points() {
+int ivf_load_driver_entry_points() {
   static std::once_flag once;
   static int status = IVF_OK;
   std::call_once(once, []() {
@@ -427,18 +253,20 @@ int load_driver_entry_points() {
       status = IVF_ECUDA;
       return;
     }
-    g_encode_im2col = (EncodeIm2colFn)fn;
+    ivf_encode_im2col = (IvfEncodeIm2colFn)fn;
     fn = nullptr;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
       status = IVF_ECUDA;
       return;
     }
-    g_encode_tiled = (EncodeTiledFn)fn;
+    ivf_encode_tiled = (IvfEncodeTiledFn)fn;
   });
   if (status != IVF_OK) ivf_set_error("cudaGetDriverEntryPoint(cuTensorMapEncode*) failed");
   return status;
 }
+
+namespace {
 
 CUtensorMapSwizzle swizzle_for(int kch) {
   return kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -496,7 +324,7 @@ int get_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int kch, CU
                 "conv(bf16): padding/kernel outside the im2col corner range");
   cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
   CUtensorMap m;
-  CUresult r = g_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides,
+  CUresult r = ivf_encode_im2col(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides,
                                lower, upper, (cuuint32_t)kch, (cuuint32_t)TILE_M, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -536,7 +364,7 @@ int get_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int kch, int
   cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box,
+  CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch),
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -611,16 +439,29 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
                          const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
   int rc = check_bf16_desc(d);
   if (rc) return rc;
-  rc = load_driver_entry_points();
+  rc = ivf_load_driver_entry_points();
   if (rc) return rc;
   const int kch = ivf_conv_bf16_kchunk(d->cin);
   const int cin_pad = ivf_conv_bf16_cin_pad(d->cin);
-  const int bn = ivf_conv_bf16_ntile(d->cout);
+  int bn = ivf_conv_bf16_ntile(d->cout);
   const int cout_pad = ivf_conv_bf16_cout_pad(d->cout);
-  const int ntiles = cout_pad / bn;
+  int ntiles = cout_pad / bn;
   const int ntaps = d->kd * d->kh * d->kw;
   long long M = (long long)d->n * d->od * d->oh * d->ow;
   IVF_REQUIRE(M < (1ll << 31), "conv(bf16): too many output pixels");
+  // Few 128-pixel tiles (the 14x14 and 7x7 stages): split the output channels over more CTAs so the
+  // grid covers the SMs; the activation tile is re-read per N tile from L2, which is cheap there.
+  // (Rows of the weight box beyond cout_pad are TMA zero fill; the epilogue stores only real channels.)
+  const int mtiles = ivf_cdiv(M, TILE_M);
+  if (mtiles * ntiles < h->sm_count) {
+    int want = ivf_cdiv(h->sm_count, mtiles);
+    int bn2 = (ivf_cdiv(d->cout, want) + 15) / 16 * 16;
+    if (bn2 < 32) bn2 = 32;
+    if (bn2 < bn) {
+      bn = bn2;
+      ntiles = ivf_cdiv(d->cout, bn);
+    }
+  }
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -642,7 +483,9 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   p.tx_bytes = p.a_stage_bytes + bbytes;
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   int kiters = ntaps * p.cchunks;
-  int stages = (int)((100u * 1024u) / stage_bytes);
+  // two CTAs per SM (100 KB each) when the grid has several waves; one deep pipeline otherwise
+  const uint32_t budget = ((long long)mtiles * ntiles > 2ll * h->sm_count ? 100u : 200u) * 1024u;
+  int stages = (int)(budget / stage_bytes);
   if (stages < 4) stages = 4;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   while ((size_t)stages * stage_bytes > 200u * 1024u) --stages;
@@ -670,7 +513,7 @@ extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const voi
   IVF_REQUIRE(h && d && in && tile_out, "ivf_probe_im2col: null argument");
   int rc = check_bf16_desc(d);
   if (rc) return rc;
-  rc = load_driver_entry_points();
+  rc = ivf_load_driver_entry_points();
   if (rc) return rc;
   const int kch = ivf_conv_bf16_kchunk(d->cin);
   CUtensorMap ma;

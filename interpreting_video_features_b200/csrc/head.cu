@@ -42,19 +42,41 @@ head_fwd_partial_kernel(const T* __restrict__ feat, int p, int c, int ld, const 
   const int kl = threadIdx.x % HEAD_CHUNK, half = threadIdx.x / HEAD_CHUNK;
   const T* f = feat + (size_t)n * p * ld;
   float s = 0.f;
-  if (k0 + kl < c)
-    for (int i = half; i < p; i += 2) s += ivf_to_float(f[(size_t)i * ld + k0 + kl]);
+  if (k0 + kl < c) {
+    // fixed summation order (positions half, half+2, ...), four independent partial sums so the
+    // loads are in flight together
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const T* fp = f + k0 + kl;
+    int i = half;
+    for (; i + 6 < p; i += 8) {
+      s0 += ivf_to_float(fp[(size_t)i * ld]);
+      s1 += ivf_to_float(fp[(size_t)(i + 2) * ld]);
+      s2 += ivf_to_float(fp[(size_t)(i + 4) * ld]);
+      s3 += ivf_to_float(fp[(size_t)(i + 6) * ld]);
+    }
+    for (; i < p; i += 2) s0 += ivf_to_float(fp[(size_t)i * ld]);
+    s = (s0 + s1) + (s2 + s3);
+  }
   half_sum[half][kl] = s;
   __syncthreads();
   if (threadIdx.x < HEAD_CHUNK) avg[kl] = (half_sum[0][kl] + half_sum[1][kl]) / (float)p;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < ncls; j += nw) {
+  for (int j = warp; j < ncls; j += 2 * nw) {  // two classes per pass: their loads overlap
+    const int j2 = j + nw;
     const float* wr = w + (size_t)j * c + k0;
-    float a = 0.f;
-    for (int k = lane; k < HEAD_CHUNK && k0 + k < c; k += 32) a = fmaf(__ldg(wr + k), avg[k], a);
+    const float* wr2 = w + (size_t)(j2 < ncls ? j2 : j) * c + k0;
+    float a = 0.f, a2 = 0.f;
+    for (int k = lane; k < HEAD_CHUNK && k0 + k < c; k += 32) {
+      a = fmaf(__ldg(wr + k), avg[k], a);
+      a2 = fmaf(__ldg(wr2 + k), avg[k], a2);
+    }
     a = ivf_warp_sum(a);
-    if (lane == 0) partial[((size_t)n * nchunks + chunk) * ncls + j] = a;
+    a2 = ivf_warp_sum(a2);
+    if (lane == 0) {
+      partial[((size_t)n * nchunks + chunk) * ncls + j] = a;
+      if (j2 < ncls) partial[((size_t)n * nchunks + chunk) * ncls + j2] = a2;
+    }
   }
 }
 
@@ -86,23 +108,23 @@ head_fwd_finish_kernel(const float* __restrict__ partial, int nchunks, const flo
     out[(size_t)n * ncls + j] = expf(lg[j] - mx) / se;
 }
 
-// Backward: grid (clip, position chunk).  Every block rebuilds dlogits (ncls values) and the channel
-// gradient of its HEAD_CHUNK..c range is recomputed per block (ncls*c MACs, cheap) so that the p*c
-// output elements are written by many blocks instead of one.
+// Backward: grid (clip, channel chunk of HEAD_CHUNK).  Every block rebuilds dlogits (ncls values), then
+// the 256 threads = HEAD_CHUNK channels x 2 class halves form davg for the block's channels only (so a
+// block reads just its [ncls][HEAD_CHUNK] slice of W, eight independent loads in flight per thread) and
+// write those channels of all p positions.
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int softmax,
                 const float* __restrict__ out, const float* __restrict__ dout, int flags,
                 const T* __restrict__ mask_y, int mask_ld, int mask_coff,
                 const float* __restrict__ mask_scale, void* __restrict__ dfeat) {
-  extern __shared__ float sm[];  // dlogit[ncls] | davg[c]
+  extern __shared__ float sm[];  // dlogit[ncls]
   __shared__ float red[32];
+  __shared__ float part[2][HEAD_CHUNK];
+  __shared__ float davg[HEAD_CHUNK], mscale[HEAD_CHUNK];
   float* dl = sm;
-  float* davg = sm + ncls;
   const int n = blockIdx.x;
-  const int pchunks = gridDim.y;
-  const int per = (p + pchunks - 1) / pchunks;
-  const int i0 = blockIdx.y * per, i1 = min(p, i0 + per);
+  const int k0 = blockIdx.y * HEAD_CHUNK;
   const float* o = out + (size_t)n * ncls;
   const float* g = dout + (size_t)n * ncls;
   if (softmax) {
@@ -114,27 +136,42 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
     for (int j = threadIdx.x; j < ncls; j += blockDim.x) dl[j] = g[j];
   }
   __syncthreads();
-  const float inv = 1.f / (float)p;
-  for (int k = threadIdx.x; k < c; k += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    int j = 0;
-    for (; j + 1 < ncls; j += 2) {
-      s0 = fmaf(__ldg(w + (size_t)j * c + k), dl[j], s0);
-      s1 = fmaf(__ldg(w + (size_t)(j + 1) * c + k), dl[j + 1], s1);
+  const int kl = threadIdx.x % HEAD_CHUNK, half = threadIdx.x / HEAD_CHUNK;
+  const int k = k0 + kl;
+  {
+    const int jh = (ncls + 1) / 2;
+    const int j0 = half * jh, j1 = min(ncls, j0 + jh);
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    if (k < c) {
+      const float* wk = w + k;
+      int j = j0;
+      for (; j + 8 <= j1; j += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fmaf(__ldg(wk + (size_t)(j + u) * c), dl[j + u], acc[u]);
+      }
+      for (; j < j1; ++j) acc[0] = fmaf(__ldg(wk + (size_t)j * c), dl[j], acc[0]);
     }
-    if (j < ncls) s0 = fmaf(__ldg(w + (size_t)j * c + k), dl[j], s0);
-    davg[k] = (s0 + s1) * inv;
+    part[half][kl] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  }
+  __syncthreads();
+  if (threadIdx.x < HEAD_CHUNK) {
+    davg[kl] = (part[0][kl] + part[1][kl]) / (float)p;
+    mscale[kl] = ((flags & IVF_EP_MASK) && k < c) ? mask_scale[k] : 1.f;
   }
   __syncthreads();
   const size_t base = (size_t)n * p;
-  for (int e = threadIdx.x; e < (i1 - i0) * c; e += blockDim.x) {
-    int i = i0 + e / c, k = e % c;
-    float v = davg[k];
+  const int kc = min(HEAD_CHUNK, c - k0);
+  for (int e = threadIdx.x; e < p * HEAD_CHUNK; e += blockDim.x) {
+    const int i = e / HEAD_CHUNK, kk = e % HEAD_CHUNK;
+    if (kk >= kc) continue;
+    float v = davg[kk];
     if (flags & IVF_EP_MASK) {
-      float y = ivf_to_float(mask_y[(base + i) * mask_ld + mask_coff + k]);
-      v = y > 0.f ? v * mask_scale[k] : 0.f;
+      float y = ivf_to_float(mask_y[(base + i) * mask_ld + mask_coff + k0 + kk]);
+      v = y > 0.f ? v * mscale[kk] : 0.f;
     }
-    size_t idx = (base + i) * ld + k;
+    size_t idx = (base + i) * ld + k0 + kk;
     if (flags & IVF_EP_OUT_F32)
       reinterpret_cast<float*>(dfeat)[idx] = v;
     else
@@ -176,11 +213,10 @@ extern "C" int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, i
   IVF_REQUIRE(h && w && out && dout && dfeat, "ivf_i3d_head_bwd: null argument");
   IVF_REQUIRE(n > 0 && p > 0 && c > 0 && ncls > 0 && ld >= c, "ivf_i3d_head_bwd: bad extent");
   if (flags & IVF_EP_MASK) IVF_REQUIRE(mask_y && mask_scale, "ivf_i3d_head_bwd: MASK needs mask_y/mask_scale");
-  size_t smem = (size_t)(c + ncls) * sizeof(float);
-  IVF_REQUIRE(smem <= 48 * 1024, "ivf_i3d_head_bwd: c + ncls too large (%d + %d)", c, ncls);
+  size_t smem = (size_t)ncls * sizeof(float);
+  IVF_REQUIRE(smem <= 40 * 1024, "ivf_i3d_head_bwd: ncls too large (%d)", ncls);
   cudaStream_t st = (cudaStream_t)stream;
-  int pchunks = p >= 14 ? (p + 13) / 14 : 1;
-  dim3 grid(n, pchunks);
+  dim3 grid(n, (c + HEAD_CHUNK - 1) / HEAD_CHUNK);
   if (dtype == IVF_F32)
     head_bwd_kernel<float><<<grid, HEAD_THREADS, smem, st>>>(p, c, ld, w, ncls, softmax, out, dout, flags,
                                                           (const float*)mask_y, mask_ld, mask_coff,

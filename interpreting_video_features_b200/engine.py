@@ -14,8 +14,15 @@ What differs from the reference's execution (not from its results):
     8*3 channels (forward) and its flipped transpose (data gradient), so every convolution of the
     network is the same stride-1 tcgen05 implicit GEMM.
 
+  * the four branches of an Inception block (pt/models/I3D_doubled.py:121-146) are independent until
+    the concat, so the program forks them onto side streams (joined before the next stage): the
+    14x14 / 7x7 stages launch 49- and 7-CTA grids that cannot fill 148 SMs one at a time.  The fork
+    and join are captured into the CUDA graph as parallel branches.
+
 State-dict keys are the reference's; weights are packed once at construction.
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -147,7 +154,12 @@ class I3DEngine:
             self.xin = Act.empty(B, self.T, self.H, self.W, in_channels, torch.float32, dev)
             self.g_xin = Act.empty(B, self.T, self.H, self.W, in_channels, torch.float32, dev)
 
+        # programs: (lane, fn) launches plus ("fork",)/("join",) markers; lane 0 is the caller's stream,
+        # lanes 1-3 are side streams used between a fork and its join
         self.fwd_ops, self.bwd_ops = [], []
+        self._lane = 0
+        self.use_streams = os.environ.get("IVF_STREAMS", "1") != "0"
+        self._side = None
         self.acts = {}  # endpoint -> Act (forward output)
         # each stage: dict(out=Act, scale=tensor|None (None: pool-type output), gout=Act)
         stages = []
@@ -163,8 +175,9 @@ class I3DEngine:
             else:
                 pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in zip((x.d, x.h, x.w), unit.kernel, unit.stride))
                 xa = x
-            self.fwd_ops.append(lambda: ops.conv3d(xa, unit.w_fwd, out, unit.kernel_eff, unit.stride_eff, pf,
-                                                   flags=_lib.EP_RELU, scale=unit.scale, shift=unit.shift))
+            self.fwd_ops.append((self._lane, lambda: ops.conv3d(xa, unit.w_fwd, out, unit.kernel_eff, unit.stride_eff,
+                                                                pf, flags=_lib.EP_RELU, scale=unit.scale,
+                                                                shift=unit.shift)))
 
         def add_unit_bwd(unit, dz_out, x_shape_act, g_in, acc_in=None, mask=None, mask_scale=None,
                          xin_is_s2d=False):
@@ -172,9 +185,9 @@ class I3DEngine:
             if self.mode == "fp32":
                 pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in
                            zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel, unit.stride))
-                self.bwd_ops.append(lambda: ops.conv3d(dz_out, unit.w_dgrad, g_in, unit.kernel, unit.stride, pf,
-                                                       acc_in=acc_in, mask=mask, mask_scale=mask_scale,
-                                                       transposed=1))
+                self.bwd_ops.append((self._lane, lambda: ops.conv3d(dz_out, unit.w_dgrad, g_in, unit.kernel,
+                                                                    unit.stride, pf, acc_in=acc_in, mask=mask,
+                                                                    mask_scale=mask_scale, transposed=1)))
             else:
                 if xin_is_s2d:
                     pf = tuple(k - 1 - 1 for k in unit.kernel_eff)
@@ -184,8 +197,9 @@ class I3DEngine:
                     pf = tuple(k - 1 - same_pad(sz, k, 1)[0] for sz, k in
                                zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel))
                     gi = g_in
-                self.bwd_ops.append(lambda: ops.conv3d(dz_out, unit.w_dgrad, gi, unit.kernel_eff, (1, 1, 1), pf,
-                                                       acc_in=acc_in, mask=mask, mask_scale=mask_scale))
+                self.bwd_ops.append((self._lane, lambda: ops.conv3d(dz_out, unit.w_dgrad, gi, unit.kernel_eff,
+                                                                    (1, 1, 1), pf, acc_in=acc_in, mask=mask,
+                                                                    mask_scale=mask_scale)))
 
         def out_dims(x, k, s):
             return tuple(same_pad(sz, kk, ss)[2] for sz, kk, ss in zip((x.d, x.h, x.w), k, s))
@@ -215,8 +229,8 @@ class I3DEngine:
                 od, oh, ow = out_dims(x, k, s)
                 out = new_act(B, od, oh, ow, x.c)
                 am = torch.empty((out.pixels, x.c), dtype=torch.uint8, device=dev)
-                self.fwd_ops.append(lambda x=x, out=out, am=am, k=k, s=s, pads=pads:
-                                    ops.maxpool3d_fwd(x, out, am, k, s, pads))
+                self.fwd_ops.append((0, lambda x=x, out=out, am=am, k=k, s=s, pads=pads:
+                                     ops.maxpool3d_fwd(x, out, am, k, s, pads)))
                 stages.append(dict(kind="pool", name=name, x=x, out=out, scale=None, gout=out.like(), argmax=am,
                                    k=k, s=s, pads=pads))
             else:  # Inception module
@@ -239,15 +253,15 @@ class I3DEngine:
         self.logits = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
         self.probs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
         self.dprobs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
-        self.fwd_ops.append(lambda: ops.head_fwd(feat, self.w_logits, self.b_logits, self.softmax, self.probs,
-                                                 self.logits))
+        self.fwd_ops.append((0, lambda: ops.head_fwd(feat, self.w_logits, self.b_logits, self.softmax, self.probs,
+                                                     self.logits)))
         # Grad-CAM reads the raw (unmasked) gradient w.r.t. Mixed_5c in fp32
         self.g_feat_raw = feat.like(torch.float32)
 
         # ---- backward program
         last = stages[-1]
-        self.bwd_ops.append(lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
-                                                 self.dprobs, mask=last["out"], mask_scale=last["scale"]))
+        self.bwd_ops.append((0, lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
+                                                     self.dprobs, mask=last["out"], mask_scale=last["scale"])))
         for i in range(len(stages) - 1, -1, -1):
             st = stages[i]
             prv = stages[i - 1] if i > 0 else None
@@ -261,9 +275,9 @@ class I3DEngine:
                 add_unit_bwd(st["unit"], st["gout"], st["x"], g_in, mask=mask, mask_scale=mscale,
                              xin_is_s2d=(st["first"] and mode == "bf16"))
             elif st["kind"] == "pool":
-                self.bwd_ops.append(lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
-                                    ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
-                                                      mask=mask, mask_scale=mscale))
+                self.bwd_ops.append((0, lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
+                                     ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
+                                                       mask=mask, mask_scale=mscale)))
             else:
                 self._build_inception_bwd(st, g_in, mask, mscale, add_unit_bwd)
 
@@ -287,13 +301,20 @@ class I3DEngine:
         am = torch.empty((x.pixels, x.c), dtype=torch.uint8, device=dev)
         k3 = (3, 3, 3)
         pads = tuple(same_pad(sz, 3, 1)[0] for sz in (x.d, x.h, x.w))
+        self.fwd_ops.append(("fork",))
+        self._lane = 0
         add_unit_fwd(u["b0"], x, out.slice(0, c0))
+        self._lane = 1
         add_unit_fwd(u["b1a"], x, t1)
         add_unit_fwd(u["b1b"], t1, out.slice(c0, c2))
+        self._lane = 2
         add_unit_fwd(u["b2a"], x, t2)
         add_unit_fwd(u["b2b"], t2, out.slice(c0 + c2, c4))
-        self.fwd_ops.append(lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads))
+        self._lane = 3
+        self.fwd_ops.append((3, lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads)))
         add_unit_fwd(u["b3b"], t3, out.slice(c0 + c2 + c4, c5))
+        self._lane = 0
+        self.fwd_ops.append(("join",))
         scale = torch.cat([u["b0"].scale, u["b1b"].scale, u["b2b"].scale, u["b3b"].scale]).contiguous()
         return dict(kind="inception", name=name, units=u, x=x, out=out, scale=scale, gout=out.like(),
                     t1=t1, t2=t2, t3=t3, argmax=am, pads=pads,
@@ -302,17 +323,24 @@ class I3DEngine:
     def _build_inception_bwd(self, st, g_in, mask, mscale, add_unit_bwd):
         u, x, dz = st["units"], st["x"], st["gout"]
         c0, c2, c4, c5 = u["b0"].cout, u["b1b"].cout, u["b2b"].cout, u["b3b"].cout
-        # branch tails: gradients w.r.t. the 1x1 bottleneck outputs (ReLU'/BN' of b1a/b2a fused)
-        add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
-        add_unit_bwd(u["b1b"], dz.slice(c0, c2), st["t1"], st["g_t1"], mask=st["t1"], mask_scale=u["b1a"].scale)
-        add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
-        # the four consumers of x: summed in fp32, the last one applies the producer's ReLU'/BN'
+        # branch tails: gradients w.r.t. the 1x1 bottleneck outputs (ReLU'/BN' of b1a/b2a fused); the three
+        # tails and b0's data gradient are independent -> four lanes
         acc = st["g_x32"]
+        self.bwd_ops.append(("fork",))
+        self._lane = 3
+        add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
+        self._lane = 1
+        add_unit_bwd(u["b1b"], dz.slice(c0, c2), st["t1"], st["g_t1"], mask=st["t1"], mask_scale=u["b1a"].scale)
+        self._lane = 2
+        add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
+        self._lane = 0
         add_unit_bwd(u["b0"], dz.slice(0, c0), x, acc)
+        self.bwd_ops.append(("join",))
+        # the four consumers of x: summed in fp32 (fixed order), the last one applies the producer's ReLU'/BN'
         add_unit_bwd(u["b1a"], st["g_t1"], x, acc, acc_in=acc)
         add_unit_bwd(u["b2a"], st["g_t2"], x, acc, acc_in=acc)
-        self.bwd_ops.append(lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], g_in, (3, 3, 3), (1, 1, 1),
-                                                      st["pads"], acc_in=acc, mask=mask, mask_scale=mscale))
+        self.bwd_ops.append((0, lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], g_in, (3, 3, 3), (1, 1, 1),
+                                                          st["pads"], acc_in=acc, mask=mask, mask_scale=mscale)))
 
     # ------------------------------------------------------------------------------------- running
     def set_input(self, x):
@@ -320,19 +348,43 @@ class I3DEngine:
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
         self.x.copy_(x, non_blocking=True)
 
+    def _run(self, prog):
+        """Issue a program on the current stream; forked lanes go to side streams (also under CUDA-graph
+        capture, where the event waits become graph dependencies)."""
+        if not self.use_streams:
+            for item in prog:
+                if len(item) == 2:
+                    item[1]()
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        for item in prog:
+            if item[0] == "fork":
+                ev = torch.cuda.Event()
+                ev.record(main)
+                for sd in self._side:
+                    sd.wait_event(ev)
+            elif item[0] == "join":
+                for sd in self._side:
+                    main.wait_stream(sd)
+            elif item[0] == 0:
+                item[1]()
+            else:
+                with torch.cuda.stream(self._side[item[0] - 1]):
+                    item[1]()
+
     def forward(self, mask=None, perturb="freeze"):
         """Perturb (mask: sigmoid-ed values [T] or [B,T]; None = unperturbed clip) and run the network.
         Returns the [B, classes] probability (or logit) buffer — a live buffer, not a copy."""
         self._mask, self._perturb = (self.zero_mask if mask is None else mask), perturb
         ops.perturb_fwd(self.x, self._mask, perturb, self.in_fmt, self.xin.buf)
-        for op in self.fwd_ops:
-            op()
+        self._run(self.fwd_ops)
         return self.probs
 
     def backward(self, to_mask=True):
         """Data-gradient pass from self.dprobs; returns d(sum dprobs*probs)/dmask [B,T] (live buffer)."""
-        for op in self.bwd_ops:
-            op()
+        self._run(self.bwd_ops)
         if to_mask:
             ops.perturb_bwd(self.x, self._mask, self._perturb, self.in_fmt, self.g_xin.buf, self.dm)
         return self.dm

@@ -7,6 +7,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("IVF_STREAMS", "0")  # one stream: the launch list is serialised anyway
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import CLIPS, NCLS, state_dict  # noqa: E402
 from interpreting_video_features_b200 import ops, search  # noqa: E402
