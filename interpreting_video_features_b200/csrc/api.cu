@@ -72,7 +72,10 @@ extern "C" int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in,
   if (d->dtype == IVF_F32)
     return ivf_conv3d_f32_launch(h, d, (const float*)in, (const float*)w, scale, shift, acc_in,
                                  (const float*)mask_y, mask_scale, (float*)out, st);
-  if (d->dtype == IVF_BF16)
+  if (d->dtype == IVF_BF16) {
+    if (ivf_conv3d_slab_eligible(h, d))
+      return ivf_conv3d_slab_launch(h, d, in, w, scale, shift, acc_in, mask_y, mask_scale, out, st);
     return ivf_conv3d_tc_launch(h, d, in, w, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  }
   IVF_FAIL(IVF_EINVAL, "ivf_conv3d: unknown dtype %d", d->dtype);
 }

@@ -227,9 +227,3 @@ typedef CUresult (*IvfEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32
 extern IvfEncodeIm2colFn ivf_encode_im2col;
 extern IvfEncodeTiledFn ivf_encode_tiled;
 int ivf_load_driver_entry_points();
-
-// slab kernel (conv_slab.cu): returns IVF_EUNSUPPORTED without launching when the layer does not fit it
-int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
-                           const float* scale, const float* shift, const float* acc_in,
-                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st);
-bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d);

@@ -1,0 +1,487 @@
+// Stride-1 'same' 3-D convolution as a tcgen05 implicit GEMM whose activation operand is a
+// shared-memory resident HALO SLAB instead of a per-tap im2col tile.
+//
+// Why: the im2col kernel (conv_tc.cu) re-fetches the 128-pixel activation tile from L2 once per
+// filter tap (27x for 3x3x3, 64x for the space-to-depth stem) and the weight tile once per 128
+// pixels; on the 56x56 / 28x28 / 112x112 stages that makes it L2->SM bandwidth bound (measured: 8.8
+// TB/s of L2 traffic at 41 % tensor utilisation on Conv3d_2c).  Here one CTA tile is TH output rows
+// of one (clip, depth) slice.  For every depth tap kd and 64-channel chunk ONE tiled TMA box
+// {64 ch, W+kw-1, TH+kh-1} lands the zero-padded input rows in shared memory ('same' padding = TMA
+// out-of-bounds zero fill, pt/models/I3D_doubled.py:96-106).  Pixels of the slab are 128-byte rows
+// (SWIZZLE_128B, 8-row atoms, SBO 1024), so in "padded-width" pixel numbering v = r*(W+kw-1)+c the
+// operand of tap (kh,kw) is the SAME slab read from a start address shifted by (kh*(W+kw-1)+kw) rows:
+// kh*kw MMAs groups reuse one slab, and the kw-1 junk columns per row are computed and never stored.
+// A tile holds MT (1..4) 128-row accumulators so one weight tile feeds MT MMAs.
+//
+// Persistent, warp specialised: warp 0 slab TMA producer, warp 1 MMA issuer, warp 2 weight TMA
+// producer (+ TMEM alloc), warps 3-6 epilogue; TMEM accumulators double buffered so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#include "conv_common.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+using namespace ivf_tc;
+
+constexpr int SLAB_THREADS = 224;
+constexpr int MAX_A_STAGES = 4;
+constexpr int MAX_B_STAGES = 8;
+constexpr uint32_t SLAB_SMEM_BUDGET = 212u * 1024u;
+
+struct SlabParams {
+  int n, dd, hh, ww;  // spatial extent (output == gathered tensor: stride 1, 'same')
+  int kd, kh, kw, pd, ph, pw;
+  int wp;      // padded row length W + kw - 1
+  int th;      // output rows per tile
+  int htiles;  // ceil(H / th)
+  int mt;      // 128-row accumulators per tile = ceil(th*wp / 128)
+  int cin, cchunks, cin_pad;
+  int cout, bn, ntiles, slot;
+  int num_tiles;
+  int out_ld, out_coff, mask_ld, mask_coff, flags;
+  int a_stages, b_stages, tmem_cols;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx, b_tx;
+  int base_off_mode;  // bring-up switch: 1 = put (addr >> 7) & 7 into the descriptor's base-offset field
+};
+
+struct TileCoord {
+  int nt, h0, dz, nn;
+};
+__device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.ntiles;
+  int r = tile / p.ntiles;
+  t.h0 = (r % p.htiles) * p.th;
+  r /= p.htiles;
+  t.dz = r % p.dd;
+  t.nn = r / p.dd;
+  return t;
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS, 1)
+conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const SlabParams p, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const float* __restrict__ acc_in, const __nv_bfloat16* __restrict__ mask_y,
+                 const float* __restrict__ mask_scale, void* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 3) {
+    for (int i = threadIdx.x - 96; i < 256; i += 128) {
+      bool ok = i < p.cout;
+      s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[i] : 1.f;
+      s_shift[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? shift[i] : 0.f;
+      s_mscale[i] = (ok && (p.flags & IVF_EP_MASK)) ? mask_scale[i] : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== slab (A) TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
+          const int zd = t.dz + kd_i - p.pd;
+          if (zd < 0 || zd >= p.dd) continue;  // an all-padding depth tap contributes nothing
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(&a_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&a_full[stage], p.a_tx);
+            tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * 64, -p.pw,
+                        t.h0 - p.ph, zd, t.nn);
+            if (++stage == p.a_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight (B) TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
+          const int zd = t.dz + kd_i - p.pd;
+          if (zd < 0 || zd >= p.dd) continue;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            for (int tap2 = 0; tap2 < p.kh * p.kw; ++tap2) {
+              const int tap = kd_i * p.kh * p.kw + tap2;
+              mbar_wait(&b_empty[stage], phase ^ 1u);
+              mbar_expect_tx(&b_full[stage], p.b_tx);
+              tma_load_2d(b_base + stage * p.b_stage_bytes, &tmB, &b_full[stage],
+                          tap * p.cin_pad + cc * 64, t.nt * p.bn);
+              if (++stage == p.b_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.bn);
+      int as = 0, bs = 0;
+      uint32_t aphase = 0, bphase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const TileCoord t = decode_tile(p, tile);
+        const int acc = it & 1;
+        mbar_wait(&t_empty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.mt * p.slot);
+        bool first = true;
+        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
+          const int zd = t.dz + kd_i - p.pd;
+          if (zd < 0 || zd >= p.dd) continue;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            const int crem = p.cin - cc * 64;
+            const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
+            mbar_wait(&a_full[as], aphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t slab = a_base + as * p.a_stage_bytes;
+            for (int kh_i = 0; kh_i < p.kh; ++kh_i) {
+              for (int kw_i = 0; kw_i < p.kw; ++kw_i) {
+                mbar_wait(&b_full[bs], bphase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t wt = b_base + bs * p.b_stage_bytes;
+                const uint32_t shift_rows = (uint32_t)(kh_i * p.wp + kw_i);
+                for (int m = 0; m < p.mt; ++m) {
+                  const uint32_t a_addr = slab + ((uint32_t)m * 128u + shift_rows) * 128u;
+                  const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+                  for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adesc = make_smem_desc(a_addr + k * 32, 1024, 2, boff);
+                    const uint64_t bdesc = make_smem_desc(wt + k * 32, 1024, 2);
+                    umma_bf16(d_tmem + (uint32_t)(m * p.slot), adesc, bdesc, idesc,
+                              (first && k == 0) ? 0u : 1u);
+                  }
+                }
+                first = false;
+                umma_commit(&b_empty[bs]);  // weight slot free once these MMAs have read it
+                if (++bs == p.b_stages) {
+                  bs = 0;
+                  bphase ^= 1u;
+                }
+              }
+            }
+            umma_commit(&a_empty[as]);  // slab slot free
+            if (++as == p.a_stages) {
+              as = 0;
+              aphase ^= 1u;
+            }
+          }
+        }
+        umma_commit(&t_full[acc]);  // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    EpilogueArgs ea;
+    ea.cout = p.cout;
+    ea.flags = p.flags;
+    ea.acc_in = acc_in;
+    ea.mask_y = mask_y;
+    ea.out = out;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int acc = it & 1;
+      mbar_wait(&t_full[acc], ((uint32_t)it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int m = 0; m < p.mt; ++m) {
+        const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
+        const int r = v / p.wp;
+        const int c = v - r * p.wp;
+        const int hrow = t.h0 + r;
+        const bool ok = r < p.th && hrow < p.hh && c < p.ww;
+        const size_t pix = (((size_t)t.nn * p.dd + t.dz) * p.hh + hrow) * p.ww + c;
+        const size_t out_row = pix * p.out_ld + p.out_coff;
+        const size_t mask_row = pix * p.mask_ld + p.mask_coff;
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)((acc * p.mt + m) * p.slot);
+        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + c0, rr);
+          const int nb = t.nt * p.bn + c0;
+          if (!ok || nb >= p.cout) continue;
+          epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+struct SlabKeyA {
+  const void* base;
+  int n, id, ih, iw, cin, ld, coff, wp, rows;
+};
+struct SlabKeyB {
+  const void* base;
+  int ktot, cout_pad, bn;
+};
+
+template <typename K>
+std::string slab_key(char tag, const K& k) {
+  std::string s(1, tag);
+  s.append(reinterpret_cast<const char*>(&k), sizeof(K));
+  return s;
+}
+
+int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, int rows, CUtensorMap* out) {
+  SlabKeyA key;
+  memset(&key, 0, sizeof(key));
+  key.base = in;
+  key.n = d->n; key.id = d->id; key.ih = d->ih; key.iw = d->iw; key.cin = d->cin;
+  key.ld = d->in_ld; key.coff = d->in_coff; key.wp = wp; key.rows = rows;
+  std::string kb = slab_key('S', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  const char* base = reinterpret_cast<const char*>(in) + (size_t)d->in_coff * 2;
+  IVF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv(slab): input slice not 16-B aligned");
+  cuuint64_t dims[5] = {(cuuint64_t)d->cin, (cuuint64_t)d->iw, (cuuint64_t)d->ih, (cuuint64_t)d->id,
+                        (cuuint64_t)d->n};
+  cuuint64_t pix = (cuuint64_t)d->in_ld * 2;
+  cuuint64_t strides[4] = {pix, pix * d->iw, pix * d->iw * d->ih, pix * d->iw * d->ih * d->id};
+  cuuint32_t box[5] = {64, (cuuint32_t)wp, (cuuint32_t)rows, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(slab) failed (%d): c%d w%d h%d d%d n%d ld%d box %dx%d",
+             (int)r, d->cin, d->iw, d->ih, d->id, d->n, d->in_ld, wp, rows);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
+int slab_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int bn, CUtensorMap* out) {
+  SlabKeyB key;
+  memset(&key, 0, sizeof(key));
+  key.base = w; key.ktot = ktot; key.cout_pad = cout_pad; key.bn = bn;
+  std::string kb = slab_key('T', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  IVF_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv(slab): weights not 16-B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(slab weights) failed (%d): ktot %d cout_pad %d bn %d", (int)r,
+             ktot, cout_pad, bn);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// tile configuration; returns false when the layer does not fit the slab scheme
+bool slab_config(const ivf_conv_desc* d, SlabParams* p) {
+  memset(p, 0, sizeof(*p));
+  const int cout = d->cout;
+  int ntiles = 1, bn, mtmax;
+  if (cout <= 64) {
+    bn = (cout + 15) / 16 * 16;
+    mtmax = 4;
+  } else if (cout <= 128) {
+    bn = (cout + 15) / 16 * 16;
+    mtmax = 2;
+  } else {
+    ntiles = (cout + 127) / 128;
+    bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
+    mtmax = 2;
+  }
+  if (ntiles * bn > 256) return false;
+  const int slot = (bn + 31) / 32 * 32;
+  if (mtmax > 256 / slot) mtmax = 256 / slot;
+  const int forced_mt = env_int("IVF_SLAB_MT", 0);
+  if (forced_mt > 0 && forced_mt < mtmax) mtmax = forced_mt;
+  const int wp = d->iw + d->kw - 1;
+  const uint32_t b_stage = ((uint32_t)bn * 128u + 1023u) & ~1023u;
+  for (int mt = mtmax; mt >= 1; --mt) {
+    int th = (mt * 128) / wp;
+    if (th < 1) continue;
+    if (th > d->ih) th = d->ih;
+    const int htiles = (d->ih + th - 1) / th;
+    th = (d->ih + htiles - 1) / htiles;  // balance the rows over the tiles
+    const int mt_eff = (th * wp + 127) / 128;
+    const int rows = th + d->kh - 1;
+    if (rows > 256) continue;
+    const uint32_t a_stage =
+        (((uint32_t)(mt_eff * 128 + (d->kh - 1) * wp + d->kw) * 128u) + 1023u) & ~1023u;
+    if (2 * a_stage + 3 * b_stage > SLAB_SMEM_BUDGET) continue;
+    int a_stages = 2;
+    if (3 * a_stage + 4 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
+    int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
+    if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
+    p->wp = wp;
+    p->th = th;
+    p->htiles = htiles;
+    p->mt = mt_eff;
+    p->bn = bn;
+    p->ntiles = ntiles;
+    p->slot = slot;
+    p->a_stages = a_stages;
+    p->b_stages = b_stages;
+    p->a_stage_bytes = a_stage;
+    p->b_stage_bytes = b_stage;
+    p->a_tx = (uint32_t)rows * wp * 128u;
+    p->b_tx = (uint32_t)bn * 128u;
+    int cols = 32;
+    while (cols < 2 * mt_eff * slot) cols <<= 1;
+    p->tmem_cols = cols;
+    return cols <= 512;
+  }
+  return false;
+}
+
+}  // namespace
+
+bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d) {
+  (void)h;
+  if (env_int("IVF_SLAB", 1) == 0) return false;
+  if (d->dtype != IVF_BF16 || d->transposed) return false;
+  if (d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
+  if (d->od != d->id || d->oh != d->ih || d->ow != d->iw) return false;
+  if (d->kd * d->kh * d->kw <= 1) return false;  // 1x1x1: nothing to reuse, plain GEMM
+  if (d->kh < 2 && d->kw < 2) return false;
+  if (d->cin % 8 || d->in_ld % 8 || d->in_coff % 8 || d->out_ld % 8 || d->out_coff % 8) return false;
+  if ((d->flags & IVF_EP_MASK) && (d->mask_ld % 8 || d->mask_coff % 8)) return false;
+  // 'same' geometry: front pad within the kernel, the rest is the back pad
+  if (d->pd < 0 || d->pd >= d->kd || d->ph < 0 || d->ph >= d->kh || d->pw < 0 || d->pw >= d->kw) return false;
+  if (d->iw < env_int("IVF_SLAB_MIN_W", 24)) return false;  // narrow maps waste the padded-width tile
+  if (d->iw + d->kw - 1 > 256) return false;
+  SlabParams p;
+  return slab_config(d, &p);
+}
+
+int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+                           const float* scale, const float* shift, const float* acc_in,
+                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
+  int rc = ivf_load_driver_entry_points();
+  if (rc) return rc;
+  SlabParams p;
+  if (!slab_config(d, &p)) IVF_FAIL(IVF_EUNSUPPORTED, "conv(slab): no tile configuration fits");
+  p.n = d->n; p.dd = d->id; p.hh = d->ih; p.ww = d->iw;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
+  p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.cin = d->cin;
+  p.cchunks = (d->cin + 63) / 64;
+  p.cin_pad = ivf_conv_bf16_cin_pad(d->cin);
+  p.cout = d->cout;
+  p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
+  p.flags = d->flags;
+  p.base_off_mode = env_int("IVF_SLAB_BASEOFF", 0);
+  long long tiles = (long long)d->n * d->id * p.htiles * p.ntiles;
+  IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
+  p.num_tiles = (int)tiles;
+
+  CUtensorMap ma, mb;
+  rc = slab_map_a(h, d, in, p.wp, p.th + d->kh - 1, &ma);
+  if (rc) return rc;
+  const int ntaps = d->kd * d->kh * d->kw;
+  rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), p.bn, &mb);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
+  if (!h->tc_attr_set[3]) {
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SLAB_SMEM_BUDGET + 2048)));
+    h->tc_attr_set[3] = true;
+  }
+  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  conv_slab_kernel<<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
+                                                     (const __nv_bfloat16*)mask_y, mask_scale, out);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}

@@ -98,8 +98,22 @@ CONV_CASES = [
 ]
 
 
+# wide stride-1 maps: the bf16 path serves these with the halo-slab kernel (csrc/conv_slab.cu); the cases
+# cover 1/2/3/4 accumulators per tile, a ragged last row tile, a 32-channel tail chunk (96 = 64 + 32), a
+# 16-channel operand, two N tiles (cout 192), the 4x4x4 stem geometry and a 2-D 5x5 (ConvLSTM) kernel
+SLAB_CASES = [
+    (1, 64, 192, (3, 10, 56), (3, 3, 3), (1, 1, 1)),
+    (2, 96, 128, (2, 9, 28), (3, 3, 3), (1, 1, 1)),
+    (1, 64, 32, (2, 30, 30), (3, 3, 3), (1, 1, 1)),
+    (1, 16, 16, (2, 24, 24), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 64, (3, 6, 40), (4, 4, 4), (1, 1, 1)),
+    (3, 32, 128, (1, 30, 40), (1, 5, 5), (1, 1, 1)),
+    (1, 128, 96, (1, 5, 120), (3, 3, 3), (1, 1, 1)),
+]
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("case", CONV_CASES + SLAB_CASES)
 def test_conv_forward_bn_relu(dev, mode, case):
     from interpreting_video_features_b200 import _lib, engine, ops
     from interpreting_video_features_b200.ops import Act, same_pad
@@ -131,7 +145,7 @@ def test_conv_forward_bn_relu(dev, mode, case):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", CONV_CASES[:6])
+@pytest.mark.parametrize("case", CONV_CASES[:6] + SLAB_CASES)
 def test_conv_data_gradient_with_fused_mask_and_accumulate(dev, mode, case):
     """dX = (acc + conv_dgrad(dZ)) * 1[y_prev>0] * scale_prev — what the backward pass launches."""
     from interpreting_video_features_b200 import engine, ops
@@ -191,13 +205,16 @@ def test_conv_fp32_strided_stem_and_its_gradient(dev):
     assert rel_err(gxa.ncdhw().cpu(), gx) < 1e-4
 
 
-def test_conv_bf16_space_to_depth_stem(dev):
+@pytest.mark.parametrize("hw", [(24, 20), (20, 64)])
+def test_conv_bf16_space_to_depth_stem(dev, hw):
     """bf16 stem: stride-2 7x7x7 presented as a stride-1 4x4x4 conv over the space-to-depth clip,
-    forward and data gradient, against the true strided convolution."""
+    forward and data gradient, against the true strided convolution (narrow map: im2col kernel; 64-wide
+    clip -> 32-wide operand: halo-slab kernel, 24-of-32-channel operand)."""
     from interpreting_video_features_b200 import _lib, engine, ops
     from interpreting_video_features_b200.ops import Act
     g = torch.Generator().manual_seed(5)
-    b, t, h, w_ = 2, 8, 24, 20
+    b, t = 2, 8
+    h, w_ = hw
     x = (torch.rand((b, 3, t, h, w_), generator=g) * 255).bfloat16().float()
     w = (torch.randn((64, 3, 7, 7, 7), generator=g) * 0.01).bfloat16().float()
     xr = x.clone().requires_grad_()

@@ -28,6 +28,12 @@ for mode in ("fp32", "bf16"):
         r["dH%d" % l] = rec["dH"].float().cpu()[..., :hid]
         r["dpre%d" % l] = rec["dpre"].buf.float().cpu().view(-1, 4, he)[..., :hid]
         r["h%d" % l] = rec["h"].buf.float().cpu()[..., :hid]
+        gp = rec["g_pooled"].buf.float().cpu()
+        if rec["s2d_out"]:  # [N,1,h/4,w/4,(dy,dx,c)] -> [N,1,h/2,w/2,c]
+            n_, _, a, b, _ = gp.shape
+            gp = gp.view(n_, 1, a, b, 2, 2, he).permute(0, 1, 2, 4, 3, 5, 6).reshape(n_, 1, 2 * a, 2 * b, he)
+        r["gpool%d" % l] = gp[..., :hid]
+        r["argmax%d" % l] = rec["argmax"].cpu()[..., :hid].float()
     if mode == "fp32":
         r["gx"] = eng.g_xin.buf.float().cpu()  # [T*B,1,H,W,3]
     else:
@@ -41,6 +47,13 @@ for k in res["fp32"]:
 print("dm fp32 clip0", res["fp32"]["dm"][0].numpy())
 print("dm bf16 clip0", res["bf16"]["dm"][0].numpy())
 print("golden        ", g["dmask"])
+for l in (1, 0):
+    for k in ("gpool%d" % l, "dH%d" % l, "dpre%d" % l):
+        a, b = res["bf16"][k], res["fp32"][k]
+        a, b = a.reshape(32, 2, -1), b.reshape(32, 2, -1)
+        print(k, "per-step:", [round(rel_err(a[t], b[t]), 3) if float(b[t].norm()) > 0 else None for t in range(32)])
+    am_b, am_f = res["bf16"]["argmax%d" % l], res["fp32"]["argmax%d" % l]
+    print("argmax mismatch fraction layer", l, float((am_b != am_f).float().mean()))
 # per-step error of dH0 (layer 0) to see growth along BPTT
 d0b, d0f = res["bf16"]["dH0"].view(32, 2, -1), res["fp32"]["dH0"].view(32, 2, -1)
 print("dH0 per-step rel err:", [round(rel_err(d0b[t], d0f[t]), 3) for t in range(32)])
