@@ -42,8 +42,7 @@ struct SlabParams {
   int num_tiles;
   int out_ld, out_coff, mask_ld, mask_coff, flags;
   int a_stages, b_stages, tmem_cols;
-  uint32_t a_stage_bytes, b_stage_bytes, a_tx, b_tx;
-  int base_off_mode;  // bring-up switch: 1 = put (addr >> 7) & 7 into the descriptor's base-offset field
+  uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
 };
 
 struct TileCoord {
@@ -116,7 +115,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== slab (A) TMA producer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -126,9 +126,12 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (zd < 0 || zd >= p.dd) continue;  // an all-padding depth tap contributes nothing
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(&a_empty[stage], phase ^ 1u);
-            mbar_expect_tx(&a_full[stage], p.a_tx);
-            tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * 64, -p.pw,
-                        t.h0 - p.ph, zd, t.nn);
+            if (leader) {
+              mbar_expect_tx(&a_full[stage], p.a_tx);
+              tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * 64, -p.pw,
+                          t.h0 - p.ph, zd, t.nn);
+            }
+            __syncwarp();
             if (++stage == p.a_stages) {
               stage = 0;
               phase ^= 1u;
@@ -139,7 +142,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 2) {
     // ===================== weight (B) TMA producer =====================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -148,12 +152,16 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int zd = t.dz + kd_i - p.pd;
           if (zd < 0 || zd >= p.dd) continue;
           for (int cc = 0; cc < p.cchunks; ++cc) {
-            for (int tap2 = 0; tap2 < p.kh * p.kw; ++tap2) {
-              const int tap = kd_i * p.kh * p.kw + tap2;
+            for (int kh_i = 0; kh_i < p.kh; ++kh_i) {
               mbar_wait(&b_empty[stage], phase ^ 1u);
-              mbar_expect_tx(&b_full[stage], p.b_tx);
-              tma_load_2d(b_base + stage * p.b_stage_bytes, &tmB, &b_full[stage],
-                          tap * p.cin_pad + cc * 64, t.nt * p.bn);
+              const int tap0 = (kd_i * p.kh + kh_i) * p.kw;
+              if (leader) {
+                mbar_expect_tx(&b_full[stage], p.b_tx);
+                for (int kw_i = 0; kw_i < p.kw; ++kw_i)
+                  tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                              (tap0 + kw_i) * p.cin_pad + cc * 64, t.nt * p.bn);
+              }
+              __syncwarp();
               if (++stage == p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -164,9 +172,17 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.bn);
+      const uint32_t desc_hi = smem_desc_hi(1024, 2);  // 8-row atoms 1024 B apart, SWIZZLE_128B
+      // everything the loop needs, in registers (not re-read from the parameter bank per MMA)
+      const int kd_n = p.kd, kh_n = p.kh, kw_n = p.kw, pd = p.pd, dd = p.dd, cin = p.cin, cchunks = p.cchunks;
+      const int mt = p.mt, a_stages = p.a_stages, b_stages = p.b_stages;
+      const uint32_t slot = (uint32_t)p.slot;
+      const uint32_t wp8 = (uint32_t)p.wp * 8u;              // one padded row of pixels, in 16-byte units
+      const uint32_t b_tap16 = p.b_tap_bytes >> 4;
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       int it = 0;
@@ -175,49 +191,55 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int acc = it & 1;
         mbar_wait(&t_empty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.mt * p.slot);
-        bool first = true;
-        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
-          const int zd = t.dz + kd_i - p.pd;
-          if (zd < 0 || zd >= p.dd) continue;
-          for (int cc = 0; cc < p.cchunks; ++cc) {
-            const int crem = p.cin - cc * 64;
+        const uint32_t d_tmem = tmem_acc + (uint32_t)acc * (uint32_t)mt * slot;
+        uint32_t accum = 0;  // 0 for the first MMA group of the tile (overwrite), 1 afterwards
+        for (int kd_i = 0; kd_i < kd_n; ++kd_i) {
+          const int zd = t.dz + kd_i - pd;
+          if (zd < 0 || zd >= dd) continue;
+          for (int cc = 0; cc < cchunks; ++cc) {
+            const int crem = cin - cc * 64;
             const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
             mbar_wait(&a_full[as], aphase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t slab = a_base + as * p.a_stage_bytes;
-            for (int kh_i = 0; kh_i < p.kh; ++kh_i) {
-              for (int kw_i = 0; kw_i < p.kw; ++kw_i) {
-                mbar_wait(&b_full[bs], bphase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t wt = b_base + bs * p.b_stage_bytes;
-                const uint32_t shift_rows = (uint32_t)(kh_i * p.wp + kw_i);
-                for (int m = 0; m < p.mt; ++m) {
-                  const uint32_t a_addr = slab + ((uint32_t)m * 128u + shift_rows) * 128u;
-                  const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adesc = make_smem_desc(a_addr + k * 32, 1024, 2, boff);
-                    const uint64_t bdesc = make_smem_desc(wt + k * 32, 1024, 2);
-                    umma_bf16(d_tmem + (uint32_t)(m * p.slot), adesc, bdesc, idesc,
-                              (first && k == 0) ? 0u : 1u);
+            const uint32_t slab_lo = smem_desc_lo(a_base + as * p.a_stage_bytes);
+            uint32_t row_lo = slab_lo;  // + kh * padded row
+            for (int kh_i = 0; kh_i < kh_n; ++kh_i, row_lo += wp8) {
+              mbar_wait(&b_full[bs], bphase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
+              uint32_t a_tap = row_lo;  // + kw pixels (8 x 16 B each)
+              for (int kw_i = 0; kw_i < kw_n; ++kw_i, a_tap += 8u, b_lo += b_tap16) {
+                uint32_t a_lo = a_tap, d = d_tmem;
+                if (leader) {
+                  if (ksteps == 4) {
+                    for (int m = 0; m < mt; ++m, a_lo += 1024u, d += slot) {
+                      umma_bf16_lo(d, a_lo, b_lo, desc_hi, idesc, accum);
+                      umma_bf16_lo(d, a_lo + 2u, b_lo + 2u, desc_hi, idesc, 1u);
+                      umma_bf16_lo(d, a_lo + 4u, b_lo + 4u, desc_hi, idesc, 1u);
+                      umma_bf16_lo(d, a_lo + 6u, b_lo + 6u, desc_hi, idesc, 1u);
+                    }
+                  } else {
+                    for (int m = 0; m < mt; ++m, a_lo += 1024u, d += slot)
+                      for (int k = 0; k < ksteps; ++k)
+                        umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
                   }
                 }
-                first = false;
-                umma_commit(&b_empty[bs]);  // weight slot free once these MMAs have read it
-                if (++bs == p.b_stages) {
-                  bs = 0;
-                  bphase ^= 1u;
-                }
+                accum = 1u;
+              }
+              __syncwarp();
+              if (leader) umma_commit(&b_empty[bs]);  // weight slot free once these MMAs have read it
+              if (++bs == b_stages) {
+                bs = 0;
+                bphase ^= 1u;
               }
             }
-            umma_commit(&a_empty[as]);  // slab slot free
-            if (++as == p.a_stages) {
+            if (leader) umma_commit(&a_empty[as]);  // slab slot free
+            if (++as == a_stages) {
               as = 0;
               aphase ^= 1u;
             }
           }
         }
-        umma_commit(&t_full[acc]);  // accumulators of this tile complete
+        if (leader) umma_commit(&t_full[acc]);  // accumulators of this tile complete
       }
     }
   } else {
@@ -386,7 +408,8 @@ bool slab_config(const ivf_conv_desc* d, SlabParams* p) {
   const int forced_mt = env_int("IVF_SLAB_MT", 0);
   if (forced_mt > 0 && forced_mt < mtmax) mtmax = forced_mt;
   const int wp = d->iw + d->kw - 1;
-  const uint32_t b_stage = ((uint32_t)bn * 128u + 1023u) & ~1023u;
+  const uint32_t b_tap = ((uint32_t)bn * 128u + 1023u) & ~1023u;
+  const uint32_t b_stage = b_tap * (uint32_t)d->kw;  // one stage = the kw taps of a (kd, chunk, kh) row
   for (int mt = mtmax; mt >= 1; --mt) {
     int th = (mt * 128) / wp;
     if (th < 1) continue;
@@ -398,9 +421,9 @@ bool slab_config(const ivf_conv_desc* d, SlabParams* p) {
     if (rows > 256) continue;
     const uint32_t a_stage =
         (((uint32_t)(mt_eff * 128 + (d->kh - 1) * wp + d->kw) * 128u) + 1023u) & ~1023u;
-    if (2 * a_stage + 3 * b_stage > SLAB_SMEM_BUDGET) continue;
+    if (2 * a_stage + 2 * b_stage > SLAB_SMEM_BUDGET) continue;
     int a_stages = 2;
-    if (3 * a_stage + 4 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
+    if (3 * a_stage + 3 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
     int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
     if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
     p->wp = wp;
@@ -414,8 +437,9 @@ bool slab_config(const ivf_conv_desc* d, SlabParams* p) {
     p->b_stages = b_stages;
     p->a_stage_bytes = a_stage;
     p->b_stage_bytes = b_stage;
+    p->b_tap_bytes = b_tap;
     p->a_tx = (uint32_t)rows * wp * 128u;
-    p->b_tx = (uint32_t)bn * 128u;
+    p->b_tx = (uint32_t)bn * 128u * (uint32_t)d->kw;
     int cols = 32;
     while (cols < 2 * mt_eff * slot) cols <<= 1;
     p->tmem_cols = cols;
@@ -461,7 +485,6 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
   p.flags = d->flags;
-  p.base_off_mode = env_int("IVF_SLAB_BASEOFF", 0);
   long long tiles = (long long)d->n * d->id * p.htiles * p.ntiles;
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;

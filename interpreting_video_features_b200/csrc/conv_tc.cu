@@ -109,8 +109,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_acc = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       int ow0 = m0 % p.ow;
       int t = m0 / p.ow;
       int oh0 = t % p.oh;
@@ -120,22 +121,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int cw = ow0 * p.sw - p.pw, ch = oh0 * p.sh - p.ph, cd = od0 * p.sd - p.pd;
       int stage = 0;
       uint32_t phase = 0;
-      int tap = 0, cc = 0;
+      int cc = 0, kw_i = 0, kh_i = 0, kd_i = 0;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
         const uint32_t b_dst = a_dst + p.a_stage_bytes;
-        int kw_i = tap % p.kw;
-        int t2 = tap / p.kw;
-        int kh_i = t2 % p.kh;
-        int kd_i = t2 / p.kh;
-        tma_load_im2col_5d(a_dst, &tmA, &full_bar[stage], cc * KCH, cw, ch, cd, n0, (uint16_t)kw_i,
-                           (uint16_t)kh_i, (uint16_t)kd_i);
-        tma_load_2d(b_dst, &tmB, &full_bar[stage], it * KCH, ntile * p.bn);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          tma_load_im2col_5d(a_dst, &tmA, &full_bar[stage], cc * KCH, cw, ch, cd, n0, (uint16_t)kw_i,
+                             (uint16_t)kh_i, (uint16_t)kd_i);
+          tma_load_2d(b_dst, &tmB, &full_bar[stage], it * KCH, ntile * p.bn);
+        }
+        __syncwarp();
         if (++cc == p.cchunks) {
           cc = 0;
-          ++tap;
+          if (++kw_i == p.kw) {
+            kw_i = 0;
+            if (++kh_i == p.kh) {
+              kh_i = 0;
+              ++kd_i;
+            }
+          }
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -144,29 +150,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(TILE_M, p.bn);
+      const uint32_t desc_hi = smem_desc_hi(KT::sbo, KT::layout);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_src = smem_base + stage * stage_bytes;
-        const uint32_t b_src = a_src + p.a_stage_bytes;
+        const uint32_t a_lo = smem_desc_lo(smem_base + stage * stage_bytes);
+        const uint32_t b_lo = smem_desc_lo(smem_base + stage * stage_bytes + p.a_stage_bytes);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < KT::ksteps; ++k) {
-          uint64_t adesc = make_smem_desc(a_src + k * 32, KT::sbo, KT::layout);
-          uint64_t bdesc = make_smem_desc(b_src + k * 32, KT::sbo, KT::layout);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < KT::ksteps; ++k)
+            umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tmem_full_bar);  // accumulator complete
+      if (leader) umma_commit(&tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================

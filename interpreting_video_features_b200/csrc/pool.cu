@@ -4,10 +4,7 @@
 // max_pool3d_with_indices keeps the FIRST maximum in (d,h,w) window-scan order; backward sends
 // the gradient to that element only (a padded winner drops it).  Also used as nn.MaxPool2d
 // (pt/models/convolution_lstm.py:79) with kd=1, pad 0.
-// Bandwidth-bound: one thread per (pixel, 16-byte channel vector), coalesced along C.  The vector
-// path tiles threads as 8 channel vectors (one 128-byte line) x a 4x8 pixel patch of one depth slice,
-// so the overlapping windows of neighbouring pixels are served by L1 instead of L2 (a flat
-// pixel-major mapping re-read every input line 27 times from L2 for the 3x3x3 stride-1 pools).
+// Bandwidth-bound: one thread per (pixel, 16-byte channel vector), coalesced along C.
 #include "common.cuh"
 
 namespace {
@@ -56,66 +53,22 @@ struct PoolGeoDyn {
   __device__ static int sw(const ivf_pool_desc& d) { return d.sw; }
 };
 
-
-// Tiled thread -> (pixel, channel vector) map of the vector kernels: threadIdx = (ph:2 | pw:3 | cv:3),
-// blockIdx.x enumerates (channel group, w tile, h tile, depth, clip) with the channel group fastest.
-constexpr int POOL_TW = 8, POOL_TH = 4, POOL_TC = 8;
-struct PoolTile {
-  int c, w, h, dd, n;
-  bool ok;
-};
-template <int VEC>
-__device__ __forceinline__ PoolTile pool_tile(int cvecs, int ww, int hh, int dd) {
-  const int ncg = (cvecs + POOL_TC - 1) / POOL_TC;
-  const int nwt = (ww + POOL_TW - 1) / POOL_TW, nht = (hh + POOL_TH - 1) / POOL_TH;
-  int b = blockIdx.x;
-  const int cg = b % ncg;
-  b /= ncg;
-  const int wt = b % nwt;
-  b /= nwt;
-  const int ht = b % nht;
-  b /= nht;
-  PoolTile t;
-  t.dd = b % dd;
-  t.n = b / dd;
-  const int cv = cg * POOL_TC + (threadIdx.x & 7);
-  t.c = cv * VEC;
-  t.w = wt * POOL_TW + ((threadIdx.x >> 3) & 7);
-  t.h = ht * POOL_TH + (threadIdx.x >> 6);
-  t.ok = cv < cvecs && t.w < ww && t.h < hh;
-  return t;
-}
-static long long pool_tile_blocks(int cvecs, int ww, int hh, int dd, int n) {
-  return (long long)((cvecs + POOL_TC - 1) / POOL_TC) * ((ww + POOL_TW - 1) / POOL_TW) *
-         ((hh + POOL_TH - 1) / POOL_TH) * dd * n;
-}
-
-template <typename T, int VEC, typename G, bool TILED>
+template <typename T, int VEC, typename G>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T* __restrict__ out,
                    uint8_t* __restrict__ argmax, long long total) {
   const int cv = d.c / VEC;
   const int KD = G::kd(d), KH = G::kh(d), KW = G::kw(d), SD = G::sd(d), SH = G::sh(d), SW = G::sw(d);
-  for (long long idx = TILED ? 0 : blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c, ow, oh, od, n;
-    long long opix;
-    if constexpr (TILED) {  // one block per tile (grid covers every tile once): leave after one pass
-      const PoolTile pt = pool_tile<VEC>(cv, d.ow, d.oh, d.od);
-      if (!pt.ok) return;
-      c = pt.c; ow = pt.w; oh = pt.h; od = pt.dd; n = pt.n;
-      opix = (((long long)n * d.od + od) * d.oh + oh) * d.ow + ow;
-      idx = total;  // single pass
-    } else {
-      c = (int)(idx % cv) * VEC;
-      opix = idx / cv;
-      ow = (int)(opix % d.ow);
-      long long t = opix / d.ow;
-      oh = (int)(t % d.oh);
-      t /= d.oh;
-      od = (int)(t % d.od);
-      n = (int)(t / d.od);
-    }
+    int c = (int)(idx % cv) * VEC;
+    long long opix = idx / cv;
+    int ow = (int)(opix % d.ow);
+    long long t = opix / d.ow;
+    int oh = (int)(t % d.oh);
+    t /= d.oh;
+    int od = (int)(t % d.od);
+    int n = (int)(t / d.od);
     float best[VEC];
     int bidx[VEC];
 #pragma unroll
@@ -170,33 +123,23 @@ maxpool_fwd_kernel(ivf_pool_desc d, const T* __restrict__ in, T* __restrict__ ou
   }
 }
 
-template <typename T, int VEC, typename G, bool TILED>
+template <typename T, int VEC, typename G>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(ivf_pool_desc d, const T* __restrict__ dy, const uint8_t* __restrict__ argmax,
                    const float* __restrict__ acc_in, const T* __restrict__ mask_y,
                    const float* __restrict__ mask_scale, void* __restrict__ dx, long long total) {
   const int cv = d.c / VEC;
   const int KD = G::kd(d), KH = G::kh(d), KW = G::kw(d), SD = G::sd(d), SH = G::sh(d), SW = G::sw(d);
-  for (long long idx = TILED ? 0 : blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c, iw, ih, idd, n;
-    long long ipix;
-    if constexpr (TILED) {
-      const PoolTile pt = pool_tile<VEC>(cv, d.iw, d.ih, d.id);
-      if (!pt.ok) return;
-      c = pt.c; iw = pt.w; ih = pt.h; idd = pt.dd; n = pt.n;
-      ipix = (((long long)n * d.id + idd) * d.ih + ih) * d.iw + iw;
-      idx = total;  // single pass
-    } else {
-      c = (int)(idx % cv) * VEC;
-      ipix = idx / cv;
-      iw = (int)(ipix % d.iw);
-      long long t = ipix / d.iw;
-      ih = (int)(t % d.ih);
-      t /= d.ih;
-      idd = (int)(t % d.id);
-      n = (int)(t / d.id);
-    }
+    int c = (int)(idx % cv) * VEC;
+    long long ipix = idx / cv;
+    int iw = (int)(ipix % d.iw);
+    long long t = ipix / d.iw;
+    int ih = (int)(t % d.ih);
+    t /= d.ih;
+    int idd = (int)(t % d.id);
+    int n = (int)(t / d.id);
     float g[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] = 0.f;
@@ -324,13 +267,11 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
   const int threads = 256;
   if (vec_ok(d, V, in, out, argmax)) {
     long long total = opix * (d->c / V);
-    long long blocks = pool_tile_blocks(d->c / V, d->ow, d->oh, d->od, d->n);
-    IVF_REQUIRE(blocks < (1ll << 31), "maxpool: too many tiles");
-    IVF_POOL_GEO_DISPATCH((maxpool_fwd_kernel<T, V, G, true><<<(unsigned)blocks, threads, 0, st>>>(
+    IVF_POOL_GEO_DISPATCH((maxpool_fwd_kernel<T, V, G><<<pool_blocks(h, total), threads, 0, st>>>(
         *d, (const T*)in, (T*)out, argmax, total)));
   } else {
     long long total = opix * d->c;
-    maxpool_fwd_kernel<T, 1, PoolGeoDyn, false><<<pool_blocks(h, total), threads, 0, st>>>(*d, (const T*)in, (T*)out,
+    maxpool_fwd_kernel<T, 1, PoolGeoDyn><<<pool_blocks(h, total), threads, 0, st>>>(*d, (const T*)in, (T*)out,
                                                                                   argmax, total);
   }
   IVF_LAUNCHED(h);
@@ -350,13 +291,11 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
               (acc_in == nullptr || (reinterpret_cast<uintptr_t>(acc_in) & 15) == 0);
   if (v_ok) {
     long long total = ipix * (d->c / V);
-    long long blocks = pool_tile_blocks(d->c / V, d->iw, d->ih, d->id, d->n);
-    IVF_REQUIRE(blocks < (1ll << 31), "maxpool: too many tiles");
-    IVF_POOL_GEO_DISPATCH((maxpool_bwd_kernel<T, V, G, true><<<(unsigned)blocks, threads, 0, st>>>(
+    IVF_POOL_GEO_DISPATCH((maxpool_bwd_kernel<T, V, G><<<pool_blocks(h, total), threads, 0, st>>>(
         *d, (const T*)dy, argmax, acc_in, (const T*)mask_y, mask_scale, dx, total)));
   } else {
     long long total = ipix * d->c;
-    maxpool_bwd_kernel<T, 1, PoolGeoDyn, false><<<pool_blocks(h, total), threads, 0, st>>>(
+    maxpool_bwd_kernel<T, 1, PoolGeoDyn><<<pool_blocks(h, total), threads, 0, st>>>(
         *d, (const T*)dy, argmax, acc_in, (const T*)mask_y, mask_scale, dx, total);
   }
   IVF_LAUNCHED(h);
