@@ -49,6 +49,7 @@ SIGNATURES = {
     "ivf_conv_bf16_cin_pad": (_I, [_I]),
     "ivf_conv_bf16_ntile": (_I, [_I]),
     "ivf_conv_bf16_cout_pad": (_I, [_I]),
+    "ivf_conv_slab_plan": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_int)]),
     "ivf_conv3d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ivf_maxpool3d_fwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),

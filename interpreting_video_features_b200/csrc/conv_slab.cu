@@ -18,6 +18,7 @@
 // tile i overlaps the MMAs of tile i+1.
 #include "conv_common.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -42,6 +43,8 @@ struct SlabParams {
   int num_tiles;
   int out_ld, out_coff, mask_ld, mask_coff, flags;
   int a_stages, b_stages, tmem_cols;
+  int acc_stages;  // 2: epilogue of tile i overlaps the MMAs of tile i+1; 1: all TMEM columns for one tile
+  int kch;
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
 };
 
@@ -59,6 +62,9 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) 
   return t;
 }
 
+// KCH = channels per slab row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B, for
+// operands of <= 32 channels: the space-to-depth stem's 24-of-32 and the 16/32-channel bottlenecks)
+template <int KCH>
 __global__ void __launch_bounds__(SLAB_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const SlabParams p, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -71,6 +77,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[256], s_shift[256], s_mscale[256];
 
+  constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
+  constexpr uint32_t ROW16 = ROWB / 16;          // the same in descriptor (16-byte) units
+  constexpr uint32_t LAYOUT = KCH == 64 ? 2u : 4u;
+  constexpr int KSTEPS = KCH / 16;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -128,7 +138,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&a_empty[stage], phase ^ 1u);
             if (leader) {
               mbar_expect_tx(&a_full[stage], p.a_tx);
-              tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * 64, -p.pw,
+              tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
                           t.h0 - p.ph, zd, t.nn);
             }
             __syncwarp();
@@ -159,7 +169,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_expect_tx(&b_full[stage], p.b_tx);
                 for (int kw_i = 0; kw_i < p.kw; ++kw_i)
                   tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
-                              (tap0 + kw_i) * p.cin_pad + cc * 64, t.nt * p.bn);
+                              (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
               }
               __syncwarp();
               if (++stage == p.b_stages) {
@@ -176,20 +186,21 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.bn);
-      const uint32_t desc_hi = smem_desc_hi(1024, 2);  // 8-row atoms 1024 B apart, SWIZZLE_128B
+      const uint32_t desc_hi = smem_desc_hi(8 * ROWB, LAYOUT);  // 8-row swizzle atoms back to back
       // everything the loop needs, in registers (not re-read from the parameter bank per MMA)
       const int kd_n = p.kd, kh_n = p.kh, kw_n = p.kw, pd = p.pd, dd = p.dd, cin = p.cin, cchunks = p.cchunks;
       const int mt = p.mt, a_stages = p.a_stages, b_stages = p.b_stages;
       const uint32_t slot = (uint32_t)p.slot;
-      const uint32_t wp8 = (uint32_t)p.wp * 8u;              // one padded row of pixels, in 16-byte units
+      const uint32_t wp8 = (uint32_t)p.wp * ROW16;           // one padded row of pixels, in 16-byte units
       const uint32_t b_tap16 = p.b_tap_bytes >> 4;
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const TileCoord t = decode_tile(p, tile);
-        const int acc = it & 1;
-        mbar_wait(&t_empty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t tphase = p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
+        mbar_wait(&t_empty[acc], tphase ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_acc + (uint32_t)acc * (uint32_t)mt * slot;
         uint32_t accum = 0;  // 0 for the first MMA group of the tile (overwrite), 1 afterwards
@@ -197,8 +208,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int zd = t.dz + kd_i - pd;
           if (zd < 0 || zd >= dd) continue;
           for (int cc = 0; cc < cchunks; ++cc) {
-            const int crem = cin - cc * 64;
-            const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
+            const int crem = cin - cc * KCH;
+            const int ksteps = crem >= KCH ? KSTEPS : (crem + 15) / 16;
             mbar_wait(&a_full[as], aphase);
             const uint32_t slab_lo = smem_desc_lo(a_base + as * p.a_stage_bytes);
             uint32_t row_lo = slab_lo;  // + kh * padded row
@@ -207,18 +218,17 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
               uint32_t a_tap = row_lo;  // + kw pixels (8 x 16 B each)
-              for (int kw_i = 0; kw_i < kw_n; ++kw_i, a_tap += 8u, b_lo += b_tap16) {
+              for (int kw_i = 0; kw_i < kw_n; ++kw_i, a_tap += ROW16, b_lo += b_tap16) {
                 uint32_t a_lo = a_tap, d = d_tmem;
                 if (leader) {
-                  if (ksteps == 4) {
-                    for (int m = 0; m < mt; ++m, a_lo += 1024u, d += slot) {
-                      umma_bf16_lo(d, a_lo, b_lo, desc_hi, idesc, accum);
-                      umma_bf16_lo(d, a_lo + 2u, b_lo + 2u, desc_hi, idesc, 1u);
-                      umma_bf16_lo(d, a_lo + 4u, b_lo + 4u, desc_hi, idesc, 1u);
-                      umma_bf16_lo(d, a_lo + 6u, b_lo + 6u, desc_hi, idesc, 1u);
+                  if (ksteps == KSTEPS) {
+                    for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot) {
+#pragma unroll
+                      for (int k = 0; k < KSTEPS; ++k)
+                        umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
                     }
                   } else {
-                    for (int m = 0; m < mt; ++m, a_lo += 1024u, d += slot)
+                    for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot)
                       for (int k = 0; k < ksteps; ++k)
                         umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
                   }
@@ -254,8 +264,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
-      const int acc = it & 1;
-      mbar_wait(&t_full[acc], ((uint32_t)it >> 1) & 1u);
+      const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+      mbar_wait(&t_full[acc], p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int m = 0; m < p.mt; ++m) {
         const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
@@ -296,11 +306,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 struct SlabKeyA {
   const void* base;
-  int n, id, ih, iw, cin, ld, coff, wp, rows;
+  int n, id, ih, iw, cin, ld, coff, wp, rows, kch;
 };
 struct SlabKeyB {
   const void* base;
-  int ktot, cout_pad, bn;
+  int ktot, cout_pad, bn, kch;
 };
 
 template <typename K>
@@ -310,12 +320,13 @@ std::string slab_key(char tag, const K& k) {
   return s;
 }
 
-int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, int rows, CUtensorMap* out) {
+int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, int rows, int kch,
+               CUtensorMap* out) {
   SlabKeyA key;
   memset(&key, 0, sizeof(key));
   key.base = in;
   key.n = d->n; key.id = d->id; key.ih = d->ih; key.iw = d->iw; key.cin = d->cin;
-  key.ld = d->in_ld; key.coff = d->in_coff; key.wp = wp; key.rows = rows;
+  key.ld = d->in_ld; key.coff = d->in_coff; key.wp = wp; key.rows = rows; key.kch = kch;
   std::string kb = slab_key('S', key);
   {
     std::lock_guard<std::mutex> g(h->mu);
@@ -331,15 +342,16 @@ int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, in
                         (cuuint64_t)d->n};
   cuuint64_t pix = (cuuint64_t)d->in_ld * 2;
   cuuint64_t strides[4] = {pix, pix * d->iw, pix * d->iw * d->ih, pix * d->iw * d->ih * d->id};
-  cuuint32_t box[5] = {64, (cuuint32_t)wp, (cuuint32_t)rows, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)kch, (cuuint32_t)wp, (cuuint32_t)rows, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(slab) failed (%d): c%d w%d h%d d%d n%d ld%d box %dx%d",
-             (int)r, d->cin, d->iw, d->ih, d->id, d->n, d->in_ld, wp, rows);
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(slab) failed (%d): c%d w%d h%d d%d n%d ld%d box %dx%dx%d",
+             (int)r, d->cin, d->iw, d->ih, d->id, d->n, d->in_ld, kch, wp, rows);
   {
     std::lock_guard<std::mutex> g(h->mu);
     h->tmaps[kb] = m;
@@ -348,10 +360,10 @@ int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, in
   return IVF_OK;
 }
 
-int slab_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int bn, CUtensorMap* out) {
+int slab_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int bn, int kch, CUtensorMap* out) {
   SlabKeyB key;
   memset(&key, 0, sizeof(key));
-  key.base = w; key.ktot = ktot; key.cout_pad = cout_pad; key.bn = bn;
+  key.base = w; key.ktot = ktot; key.cout_pad = cout_pad; key.bn = bn; key.kch = kch;
   std::string kb = slab_key('T', key);
   {
     std::lock_guard<std::mutex> g(h->mu);
@@ -364,11 +376,12 @@ int slab_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int bn, CUt
   IVF_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv(slab): weights not 16-B aligned");
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
   cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(slab weights) failed (%d): ktot %d cout_pad %d bn %d", (int)r,
@@ -386,72 +399,121 @@ int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-// tile configuration; returns false when the layer does not fit the slab scheme
-bool slab_config(const ivf_conv_desc* d, SlabParams* p) {
-  memset(p, 0, sizeof(*p));
-  const int cout = d->cout;
-  int ntiles = 1, bn, mtmax;
-  if (cout <= 64) {
-    bn = (cout + 15) / 16 * 16;
-    mtmax = 4;
-  } else if (cout <= 128) {
-    bn = (cout + 15) / 16 * 16;
-    mtmax = 2;
-  } else {
-    ntiles = (cout + 127) / 128;
-    bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
-    mtmax = 2;
-  }
-  if (ntiles * bn > 256) return false;
-  const int slot = (bn + 31) / 32 * 32;
-  if (mtmax > 256 / slot) mtmax = 256 / slot;
-  const int forced_mt = env_int("IVF_SLAB_MT", 0);
-  if (forced_mt > 0 && forced_mt < mtmax) mtmax = forced_mt;
+// Tile configuration by a small cost model.  Candidates: N tiles (bn), accumulators per tile (mt),
+// single or double buffered TMEM.  Per tile: tensor time = #MMA x max(bn/2, 32) cycles (an MMA reads its
+// 128 x 32 B activation rows from shared memory, a 32-cycle floor below N = 64); L2->SM bytes = slabs +
+// weights at ~40 B/cycle/SM with the whole chip pulling (the measured LTS cap / 148); the epilogue is
+// exposed only when TMEM is single buffered.  Weights are re-streamed per tile, so a larger mt (more rows
+// per weight byte) usually wins on the 64..192-channel 3x3x3 layers even at the price of single buffering.
+// Returns false when no candidate fits shared memory / TMEM.
+bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
+  memset(best, 0, sizeof(*best));
+  const int cout = d->cout, cin = d->cin;
+  const int kch = cin <= 32 ? 32 : 64;
+  const int rowb = kch * 2;
   const int wp = d->iw + d->kw - 1;
-  const uint32_t b_tap = ((uint32_t)bn * 128u + 1023u) & ~1023u;
-  const uint32_t b_stage = b_tap * (uint32_t)d->kw;  // one stage = the kw taps of a (kd, chunk, kh) row
-  for (int mt = mtmax; mt >= 1; --mt) {
-    int th = (mt * 128) / wp;
-    if (th < 1) continue;
-    if (th > d->ih) th = d->ih;
-    const int htiles = (d->ih + th - 1) / th;
-    th = (d->ih + htiles - 1) / htiles;  // balance the rows over the tiles
-    const int mt_eff = (th * wp + 127) / 128;
-    const int rows = th + d->kh - 1;
-    if (rows > 256) continue;
-    const uint32_t a_stage =
-        (((uint32_t)(mt_eff * 128 + (d->kh - 1) * wp + d->kw) * 128u) + 1023u) & ~1023u;
-    if (2 * a_stage + 2 * b_stage > SLAB_SMEM_BUDGET) continue;
-    int a_stages = 2;
-    if (3 * a_stage + 3 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
-    int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
-    if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
-    p->wp = wp;
-    p->th = th;
-    p->htiles = htiles;
-    p->mt = mt_eff;
-    p->bn = bn;
-    p->ntiles = ntiles;
-    p->slot = slot;
-    p->a_stages = a_stages;
-    p->b_stages = b_stages;
-    p->a_stage_bytes = a_stage;
-    p->b_stage_bytes = b_stage;
-    p->b_tap_bytes = b_tap;
-    p->a_tx = (uint32_t)rows * wp * 128u;
-    p->b_tx = (uint32_t)bn * 128u * (uint32_t)d->kw;
-    int cols = 32;
-    while (cols < 2 * mt_eff * slot) cols <<= 1;
-    p->tmem_cols = cols;
-    return cols <= 512;
+  const int cchunks = (cin + kch - 1) / kch;
+  const int taps = d->kd * d->kh * d->kw;
+  int ksteps_total = 0;  // MMAs of K=16 per tap over all channel chunks
+  for (int cc = 0; cc < cchunks; ++cc) {
+    int crem = cin - cc * kch;
+    ksteps_total += crem >= kch ? kch / 16 : (crem + 15) / 16;
   }
-  return false;
+  const int forced_mt = env_int("IVF_SLAB_MT", 0), forced_nt = env_int("IVF_SLAB_NT", 0);
+  const int forced_acc = env_int("IVF_SLAB_ACC", 0);
+  double best_cost = 1e30;
+  bool found = false;
+  for (int ntiles = 1; ntiles <= 4; ++ntiles) {
+    if (forced_nt && ntiles != forced_nt) continue;
+    const int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
+    if (bn > 256 || ntiles * bn > 256 + 15) continue;
+    if (ntiles > 1 && bn < 32) continue;
+    const int slot = (bn + 31) / 32 * 32;
+    const uint32_t b_tap = ((uint32_t)bn * rowb + 1023u) & ~1023u;
+    const uint32_t b_stage = b_tap * (uint32_t)d->kw;
+    for (int acc_stages = 2; acc_stages >= 1; --acc_stages) {
+      if (forced_acc && acc_stages != forced_acc) continue;
+      for (int mt = 4; mt >= 1; --mt) {
+        if (forced_mt && mt != forced_mt) continue;
+        int th = (mt * 128) / wp;
+        if (th < 1) continue;
+        if (th > d->ih) th = d->ih;
+        const int htiles = (d->ih + th - 1) / th;
+        th = (d->ih + htiles - 1) / htiles;  // balance the rows over the tiles
+        const int mt_eff = (th * wp + 127) / 128;
+        if (acc_stages * mt_eff * slot > 512) continue;
+        const int rows = th + d->kh - 1;
+        if (rows > 256) continue;
+        const uint32_t a_stage =
+            (((uint32_t)(mt_eff * 128 + (d->kh - 1) * wp + d->kw) * rowb) + 1023u) & ~1023u;
+        if (2 * a_stage + 2 * b_stage > SLAB_SMEM_BUDGET) continue;
+        int a_stages = 2;
+        if (3 * a_stage + 3 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
+        int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
+        if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
+        // ---- cost
+        const double tiles = (double)d->n * d->id * htiles * ntiles;
+        const double waves = ceil(tiles / sm_count);
+        const double mma_clk = (double)taps * ksteps_total * mt_eff * (bn / 2 > 32 ? bn / 2 : 32);
+        const int cin_real_bytes = (cin < kch ? cin : kch) * 2;
+        const double l2_bytes = (double)d->kd * cchunks * rows * wp * cin_real_bytes +
+                                (double)taps * cchunks * bn * rowb;
+        const double epi_clk = (double)mt_eff * (bn / 16) * 220.0;
+        double tile_clk = mma_clk > l2_bytes / 40.0 ? mma_clk : l2_bytes / 40.0;
+        if (acc_stages == 1) tile_clk += epi_clk;
+        else if (epi_clk > tile_clk) tile_clk = epi_clk;
+        const double cost = waves * tile_clk + 4000.0;
+        if (cost < best_cost) {
+          best_cost = cost;
+          found = true;
+          SlabParams* p = best;
+          p->kch = kch;
+          p->wp = wp;
+          p->th = th;
+          p->htiles = htiles;
+          p->mt = mt_eff;
+          p->bn = bn;
+          p->ntiles = ntiles;
+          p->slot = slot;
+          p->acc_stages = acc_stages;
+          p->a_stages = a_stages;
+          p->b_stages = b_stages;
+          p->a_stage_bytes = a_stage;
+          p->b_stage_bytes = b_stage;
+          p->b_tap_bytes = b_tap;
+          p->a_tx = (uint32_t)rows * wp * rowb;
+          p->b_tx = (uint32_t)bn * rowb * (uint32_t)d->kw;
+          int cols = 32;
+          while (cols < acc_stages * mt_eff * slot) cols <<= 1;
+          p->tmem_cols = cols;
+        }
+      }
+    }
+  }
+  return found;
+}
+
+template <int KCH>
+int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, const CUtensorMap& mb,
+                  const float* scale, const float* shift, const float* acc_in, const void* mask_y,
+                  const float* mask_scale, void* out, cudaStream_t st) {
+  const int slot = KCH == 64 ? 3 : 2;
+  if (!h->slab_attr_set[slot - 2]) {
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SLAB_SMEM_BUDGET + 2048)));
+    h->slab_attr_set[slot - 2] = true;
+  }
+  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
+  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  conv_slab_kernel<KCH><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
+                                                          (const __nv_bfloat16*)mask_y, mask_scale, out);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
 }
 
 }  // namespace
 
 bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d) {
-  (void)h;
   if (env_int("IVF_SLAB", 1) == 0) return false;
   if (d->dtype != IVF_BF16 || d->transposed) return false;
   if (d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
@@ -464,8 +526,9 @@ bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d) {
   if (d->pd < 0 || d->pd >= d->kd || d->ph < 0 || d->ph >= d->kh || d->pw < 0 || d->pw >= d->kw) return false;
   if (d->iw < env_int("IVF_SLAB_MIN_W", 24)) return false;  // narrow maps waste the padded-width tile
   if (d->iw + d->kw - 1 > 256) return false;
+  if (d->cout > 256) return false;
   SlabParams p;
-  return slab_config(d, &p);
+  return slab_config(d, h->sm_count, &p);
 }
 
 int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
@@ -474,12 +537,12 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
   int rc = ivf_load_driver_entry_points();
   if (rc) return rc;
   SlabParams p;
-  if (!slab_config(d, &p)) IVF_FAIL(IVF_EUNSUPPORTED, "conv(slab): no tile configuration fits");
+  if (!slab_config(d, h->sm_count, &p)) IVF_FAIL(IVF_EUNSUPPORTED, "conv(slab): no tile configuration fits");
   p.n = d->n; p.dd = d->id; p.hh = d->ih; p.ww = d->iw;
   p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   p.cin = d->cin;
-  p.cchunks = (d->cin + 63) / 64;
+  p.cchunks = (d->cin + p.kch - 1) / p.kch;
   p.cin_pad = ivf_conv_bf16_cin_pad(d->cin);
   p.cout = d->cout;
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;
@@ -488,23 +551,34 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
   long long tiles = (long long)d->n * d->id * p.htiles * p.ntiles;
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;
+  if (env_int("IVF_SLAB_VERBOSE", 0))
+    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) tiles %d\n",
+            d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.mt, p.th,
+            p.acc_stages, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.num_tiles);
 
   CUtensorMap ma, mb;
-  rc = slab_map_a(h, d, in, p.wp, p.th + d->kh - 1, &ma);
+  rc = slab_map_a(h, d, in, p.wp, p.th + d->kh - 1, p.kch, &ma);
   if (rc) return rc;
   const int ntaps = d->kd * d->kh * d->kw;
-  rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), p.bn, &mb);
+  rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), p.bn, p.kch, &mb);
   if (rc) return rc;
+  if (p.kch == 64)
+    return slab_launch_t<64>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  return slab_launch_t<32>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+}
 
-  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
-  if (!h->tc_attr_set[3]) {
-    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SLAB_SMEM_BUDGET + 2048)));
-    h->tc_attr_set[3] = true;
-  }
-  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  conv_slab_kernel<<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
-                                                     (const __nv_bfloat16*)mask_y, mask_scale, out);
-  IVF_LAUNCHED(h);
-  return IVF_OK;
+// diagnostic (no GPU needed): the tile plan the slab kernel would use for a layer, or 0 when the layer
+// goes to the im2col kernel.  plan = {kch, bn, ntiles, mt, th, acc_stages, a_stages, b_stages, tiles, smem}
+extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* plan) {
+  if (!d || !plan) return 0;
+  ivf_handle fake;
+  fake.sm_count = sm_count;
+  if (!ivf_conv3d_slab_eligible(&fake, d)) return 0;
+  SlabParams p;
+  if (!slab_config(d, sm_count, &p)) return 0;
+  plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
+  plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
+  plan[8] = d->n * d->id * p.htiles * p.ntiles;
+  plan[9] = (int)(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes);
+  return 1;
 }

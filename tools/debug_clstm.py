@@ -59,3 +59,20 @@ d0b, d0f = res["bf16"]["dH0"].view(32, 2, -1), res["fp32"]["dH0"].view(32, 2, -1
 print("dH0 per-step rel err:", [round(rel_err(d0b[t], d0f[t]), 3) for t in range(32)])
 gb, gf = res["bf16"]["gx"].view(32, 2, -1), res["fp32"]["gx"].view(32, 2, -1)
 print("gx per-step rel err:", [round(rel_err(gb[t], gf[t]), 3) for t in range(32)])
+
+# structured clips: is the bf16 mask gradient usable where the clip has real temporal content?
+xs = synthetic.clips(2, kind="moving_square", t=32, h=120, w=160) / 255.0
+ms = torch.stack([torch.from_numpy(g["mask"]), torch.rand(32, generator=torch.Generator().manual_seed(8))])
+out = {}
+for mode in ("fp32", "bf16"):
+    eng = engine(sd, hid, 2, mode, dev)
+    eng.set_input(xs.to(dev)); eng.set_targets(torch.tensor([2, 4]))
+    eng.forward(ms.to(dev), "reverse")
+    out[mode] = eng.backward().clone().cpu()
+for i in range(2):
+    a, b = out["bf16"][i], out["fp32"][i]
+    print("moving-square clip %d: dm rel_err %.4f cos %.4f |dm| %.3e" % (
+        i, rel_err(a, b), float(torch.nn.functional.cosine_similarity(a, b, dim=0)), float(b.norm())))
+for i in range(2):
+    a, b = res["bf16"]["dm"][i], res["fp32"]["dm"][i]
+    print("noise clip %d: dm rel_err %.4f cos %.4f" % (i, rel_err(a, b), float(torch.nn.functional.cosine_similarity(a, b, dim=0))))
