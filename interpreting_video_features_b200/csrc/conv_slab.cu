@@ -13,6 +13,14 @@
 // kh*kw MMAs groups reuse one slab, and the kw-1 junk columns per row are computed and never stored.
 // A tile holds MT (1..4) 128-row accumulators so one weight tile feeds MT MMAs.
 //
+// kw-merge (kwm > 1): an MMA's cost is bounded by fetching its 128 x 16 activation sub-tile from shared
+// memory (32 cycles) unless N >= 128, and the layers with few output channels (stem 64, data gradients
+// 24..96) would run at N/64 of the tensor rate.  For those the kwm filter taps of a row are stacked along
+// N: P_g[u] = sum_k A[u + kh*wp][k] * W[kh, kw=g][k], one MMA of N = kwm*bn for all g, accumulated over
+// (kd, kh, channel chunk) in TMEM, and the epilogue forms out[v] = sum_g P_g[v + g]: a row shift of g
+// between column blocks, done with warp shuffles plus a small shared-memory exchange of the first kwm-1
+// rows of the next 32-row quarter.
+//
 // Persistent, warp specialised: warp 0 slab TMA producer, warp 1 MMA issuer, warp 2 weight TMA
 // producer (+ TMEM alloc), warps 3-6 epilogue; TMEM accumulators double buffered so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
@@ -39,7 +47,8 @@ struct SlabParams {
   int htiles;  // ceil(H / th)
   int mt;      // 128-row accumulators per tile = ceil(th*wp / 128)
   int cin, cchunks, cin_pad;
-  int cout, bn, ntiles, slot;
+  int cout, bn, ntiles, slot;  // slot = TMEM columns of one 128-row accumulator (>= kwm*bn)
+  int kwm;                     // kw taps merged into the MMA's N (1 = none)
   int num_tiles;
   int out_ld, out_coff, mask_ld, mask_coff, flags;
   int a_stages, b_stages, tmem_cols;
@@ -76,6 +85,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+  __shared__ float xch[2][4][3][3][16];  // kw-merge: [parity][quarter slot][g-1][row][column] boundary rows
 
   constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
   constexpr uint32_t ROW16 = ROWB / 16;          // the same in descriptor (16-byte) units
@@ -185,11 +195,12 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     {
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128, p.bn);
+      const uint32_t idesc = make_idesc_bf16(128, p.bn * p.kwm);
       const uint32_t desc_hi = smem_desc_hi(8 * ROWB, LAYOUT);  // 8-row swizzle atoms back to back
       // everything the loop needs, in registers (not re-read from the parameter bank per MMA)
       const int kd_n = p.kd, kh_n = p.kh, kw_n = p.kw, pd = p.pd, dd = p.dd, cin = p.cin, cchunks = p.cchunks;
       const int mt = p.mt, a_stages = p.a_stages, b_stages = p.b_stages;
+      const uint32_t kwm = (uint32_t)p.kwm;
       const uint32_t slot = (uint32_t)p.slot;
       const uint32_t wp8 = (uint32_t)p.wp * ROW16;           // one padded row of pixels, in 16-byte units
       const uint32_t b_tap16 = p.b_tap_bytes >> 4;
@@ -217,8 +228,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(&b_full[bs], bphase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
-              uint32_t a_tap = row_lo;  // + kw pixels (8 x 16 B each)
-              for (int kw_i = 0; kw_i < kw_n; ++kw_i, a_tap += ROW16, b_lo += b_tap16) {
+              uint32_t a_tap = row_lo;  // + kw pixels; a merged group of kwm taps is one MMA of N = kwm*bn
+              for (int kw_i = 0; kw_i < kw_n; kw_i += kwm, a_tap += kwm * ROW16, b_lo += kwm * b_tap16) {
                 uint32_t a_lo = a_tap, d = d_tmem;
                 if (leader) {
                   if (ksteps == KSTEPS) {
@@ -262,6 +273,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.mask_y = mask_y;
     ea.out = out;
     int it = 0;
+    uint32_t xpar = 0;  // exchange-buffer parity (kw-merge)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
       const int acc = p.acc_stages == 2 ? (it & 1) : 0;
@@ -278,12 +290,66 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const size_t mask_row = pix * p.mask_ld + p.mask_coff;
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
                                (uint32_t)((acc * p.mt + m) * p.slot);
-        for (int c0 = 0; c0 < p.bn; c0 += 16) {
-          uint32_t rr[16];
-          tmem_ld16(taddr + c0, rr);
-          const int nb = t.nt * p.bn + c0;
-          if (!ok || nb >= p.cout) continue;
-          epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+        if (p.kwm == 1) {
+          for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            uint32_t rr[16];
+            tmem_ld16(taddr + c0, rr);
+            const int nb = t.nt * p.bn + c0;
+            if (!ok || nb >= p.cout) continue;
+            epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+          }
+        } else {
+          // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down
+          const int kwm = p.kwm;
+          const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
+          for (int c0 = 0; c0 < p.bn; c0 += 16, ++xpar) {
+            uint32_t tg[4][16];
+            uint32_t nx[3][16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g < kwm) tmem_ld16_nowait(taddr + g * p.bn + c0, tg[g]);
+            if (next_blk) {
+#pragma unroll
+              for (int g = 1; g < 4; ++g)
+                if (g < kwm) tmem_ld16_nowait(taddr + p.slot + g * p.bn + c0, nx[g - 1]);
+            }
+            tmem_ld_wait();
+            float(*xb)[3][3][16] = xch[xpar & 1];
+            if (lane < kwm - 1) {
+#pragma unroll
+              for (int g = 1; g < 4; ++g) {
+                if (g >= kwm) break;
+                if (q > 0) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) xb[q - 1][g - 1][lane][j] = __uint_as_float(tg[g][j]);
+                } else if (next_blk) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) xb[3][g - 1][lane][j] = __uint_as_float(nx[g - 1][j]);
+                }
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+            float accv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[0][j]);
+#pragma unroll
+            for (int g = 1; g < 4; ++g) {
+              if (g >= kwm) break;
+              const int src = lane + g - 32;  // >= 0: the row lives in the next quarter
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[g][j]), g);
+                if (src >= 0) sv = xb[q][g - 1][src][j];
+                accv[j] += sv;
+              }
+            }
+            const int nb = t.nt * p.bn + c0;
+            if (!ok || nb >= p.cout) continue;
+            uint32_t rr[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
+            epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -400,12 +466,15 @@ int env_int(const char* name, int dflt) {
 }
 
 // Tile configuration by a small cost model.  Candidates: N tiles (bn), accumulators per tile (mt),
-// single or double buffered TMEM.  Per tile: tensor time = #MMA x max(bn/2, 32) cycles (an MMA reads its
-// 128 x 32 B activation rows from shared memory, a 32-cycle floor below N = 64); L2->SM bytes = slabs +
-// weights at ~40 B/cycle/SM with the whole chip pulling (the measured LTS cap / 148); the epilogue is
-// exposed only when TMEM is single buffered.  Weights are re-streamed per tile, so a larger mt (more rows
-// per weight byte) usually wins on the 64..192-channel 3x3x3 layers even at the price of single buffering.
-// Returns false when no candidate fits shared memory / TMEM.
+// single or double buffered TMEM.  What bounds this kernel (ncu --set full, profiles/r01_ncu_full_conv_slab.md)
+// is the shared-memory port, not L2 or DRAM: an M128 x N x K16 MMA re-reads its 4 KB activation sub-tile and
+// N x 32 B of weights from shared memory (128 B/clk), 32 + N/4 cycles against N/2 cycles of math, and the
+// TMA writes of slabs and weights go through the same port.  Per tile:
+//   math  = #MMA x bn/2
+//   smem  = #MMA x (32 + bn/4) + (slab bytes + weight bytes) / 128
+//   l2    = (slab bytes read + weight bytes) / 40      (LTS cap / 148 SMs with the whole chip pulling)
+// so a large bn always wins (N >= 128 hides the operand fetch) and mt amortises the weight writes; the
+// epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
   const int cout = d->cout, cin = d->cin;
@@ -420,7 +489,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     ksteps_total += crem >= kch ? kch / 16 : (crem + 15) / 16;
   }
   const int forced_mt = env_int("IVF_SLAB_MT", 0), forced_nt = env_int("IVF_SLAB_NT", 0);
-  const int forced_acc = env_int("IVF_SLAB_ACC", 0);
+  const int forced_acc = env_int("IVF_SLAB_ACC", 0), forced_kwm = env_int("IVF_SLAB_KWM", 0);
   double best_cost = 1e30;
   bool found = false;
   for (int ntiles = 1; ntiles <= 4; ++ntiles) {
@@ -428,9 +497,12 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     const int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
     if (bn > 256 || ntiles * bn > 256 + 15) continue;
     if (ntiles > 1 && bn < 32) continue;
-    const int slot = (bn + 31) / 32 * 32;
-    const uint32_t b_tap = ((uint32_t)bn * rowb + 1023u) & ~1023u;
+    const uint32_t b_tap = ((uint32_t)bn * rowb + 1023u) & ~1023u;  // == bn*rowb (bn % 16 == 0): taps are dense
     const uint32_t b_stage = b_tap * (uint32_t)d->kw;
+    for (int kwm = 1; kwm <= 4 && kwm <= d->kw; ++kwm) {
+    if (d->kw % kwm || kwm * bn > 256) continue;
+    if (forced_kwm && kwm != forced_kwm && !(forced_kwm > 1 && (d->kw % forced_kwm || forced_kwm * bn > 256))) continue;
+    const int slot = (kwm * bn + 31) / 32 * 32;
     for (int acc_stages = 2; acc_stages >= 1; --acc_stages) {
       if (forced_acc && acc_stages != forced_acc) continue;
       for (int mt = 4; mt >= 1; --mt) {
@@ -454,12 +526,18 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         // ---- cost
         const double tiles = (double)d->n * d->id * htiles * ntiles;
         const double waves = ceil(tiles / sm_count);
-        const double mma_clk = (double)taps * ksteps_total * mt_eff * (bn / 2 > 32 ? bn / 2 : 32);
+        const double n_mma = (double)taps / kwm * ksteps_total * mt_eff;
+        const int n_eff = kwm * bn;
         const int cin_real_bytes = (cin < kch ? cin : kch) * 2;
-        const double l2_bytes = (double)d->kd * cchunks * rows * wp * cin_real_bytes +
-                                (double)taps * cchunks * bn * rowb;
-        const double epi_clk = (double)mt_eff * (bn / 16) * 220.0;
-        double tile_clk = mma_clk > l2_bytes / 40.0 ? mma_clk : l2_bytes / 40.0;
+        const double slab_smem = (double)d->kd * cchunks * rows * wp * rowb;
+        const double slab_l2 = (double)d->kd * cchunks * rows * wp * cin_real_bytes;
+        const double w_bytes = (double)taps * cchunks * bn * rowb;
+        const double math_clk = n_mma * n_eff / 2.0;
+        const double smem_clk = n_mma * (32.0 + n_eff / 4.0) + (slab_smem + w_bytes) / 128.0;
+        const double l2_clk = (slab_l2 + w_bytes) / 40.0;
+        const double epi_clk = (double)mt_eff * (bn / 16) * (220.0 + 200.0 * (kwm - 1));
+        double tile_clk = math_clk > smem_clk ? math_clk : smem_clk;
+        if (l2_clk > tile_clk) tile_clk = l2_clk;
         if (acc_stages == 1) tile_clk += epi_clk;
         else if (epi_clk > tile_clk) tile_clk = epi_clk;
         const double cost = waves * tile_clk + 4000.0;
@@ -475,6 +553,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->bn = bn;
           p->ntiles = ntiles;
           p->slot = slot;
+          p->kwm = kwm;
           p->acc_stages = acc_stages;
           p->a_stages = a_stages;
           p->b_stages = b_stages;
@@ -488,6 +567,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->tmem_cols = cols;
         }
       }
+    }
     }
   }
   return found;
@@ -552,8 +632,8 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;
   if (env_int("IVF_SLAB_VERBOSE", 0))
-    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) tiles %d\n",
-            d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.mt, p.th,
+    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) tiles %d\n",
+            d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.kwm, p.mt, p.th,
             p.acc_stages, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.num_tiles);
 
   CUtensorMap ma, mb;
@@ -568,7 +648,7 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
 }
 
 // diagnostic (no GPU needed): the tile plan the slab kernel would use for a layer, or 0 when the layer
-// goes to the im2col kernel.  plan = {kch, bn, ntiles, mt, th, acc_stages, a_stages, b_stages, tiles, smem}
+// goes to the im2col kernel.  plan = {kch, bn, ntiles, mt, th, acc_stages, a_stages, b_stages, tiles, smem, kwm}
 extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* plan) {
   if (!d || !plan) return 0;
   ivf_handle fake;
@@ -580,5 +660,6 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
   plan[8] = d->n * d->id * p.htiles * p.ntiles;
   plan[9] = (int)(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes);
+  plan[10] = p.kwm;
   return 1;
 }
