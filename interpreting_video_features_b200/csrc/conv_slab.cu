@@ -465,16 +465,16 @@ int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-// Tile configuration by a small cost model.  Candidates: N tiles (bn), accumulators per tile (mt),
-// single or double buffered TMEM.  What bounds this kernel (ncu --set full, profiles/r01_ncu_full_conv_slab.md)
-// is the shared-memory port, not L2 or DRAM: an M128 x N x K16 MMA re-reads its 4 KB activation sub-tile and
-// N x 32 B of weights from shared memory (128 B/clk), 32 + N/4 cycles against N/2 cycles of math, and the
-// TMA writes of slabs and weights go through the same port.  Per tile:
-//   math  = #MMA x bn/2
-//   smem  = #MMA x (32 + bn/4) + (slab bytes + weight bytes) / 128
+// Tile configuration by a small cost model.  Candidates: N tiles (bn), kw taps merged into N (kwm),
+// accumulators per tile (mt), single or double buffered TMEM.  What bounds this kernel is the tensor core's
+// operand fetch from shared memory, not L2 or DRAM (ncu --set full: profiles/r01_ncu_full_conv_slab.md):
+// measured over all the configurations of round 1 an M128 x N x K16 MMA (cta_group::1, both operands in
+// shared memory) takes ~ 64 + N/2 cycles = (4 KB activations + 32N B weights) at 64 B/clk, against N/2 cycles
+// of math: N = 32 -> 80 clk, 64 -> 96, 96 -> 112, 128 -> 128.  So efficiency is N/(128+N): as large an N as
+// TMEM allows (kwm*bn <= 256), and the rest of the model only arbitrates ties:
+//   mma   = #MMA x (64 + N/2) + half of the TMA shared-memory writes ((slab + weight bytes) / 128)
 //   l2    = (slab bytes read + weight bytes) / 40      (LTS cap / 148 SMs with the whole chip pulling)
-// so a large bn always wins (N >= 128 hides the operand fetch) and mt amortises the weight writes; the
-// epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
+// the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
   const int cout = d->cout, cin = d->cin;
@@ -532,12 +532,10 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         const double slab_smem = (double)d->kd * cchunks * rows * wp * rowb;
         const double slab_l2 = (double)d->kd * cchunks * rows * wp * cin_real_bytes;
         const double w_bytes = (double)taps * cchunks * bn * rowb;
-        const double math_clk = n_mma * n_eff / 2.0;
-        const double smem_clk = n_mma * (32.0 + n_eff / 4.0) + (slab_smem + w_bytes) / 128.0;
+        const double mma_clk = n_mma * (64.0 + n_eff / 2.0) + 0.5 * (slab_smem + w_bytes) / 128.0;
         const double l2_clk = (slab_l2 + w_bytes) / 40.0;
         const double epi_clk = (double)mt_eff * (bn / 16) * (220.0 + 200.0 * (kwm - 1));
-        double tile_clk = math_clk > smem_clk ? math_clk : smem_clk;
-        if (l2_clk > tile_clk) tile_clk = l2_clk;
+        double tile_clk = mma_clk > l2_clk ? mma_clk : l2_clk;
         if (acc_stages == 1) tile_clk += epi_clk;
         else if (epi_clk > tile_clk) tile_clk = epi_clk;
         const double cost = waves * tile_clk + 4000.0;
