@@ -473,7 +473,8 @@ int env_int(const char* name, int dflt) {
 // of math: N = 32 -> 80 clk, 64 -> 96, 96 -> 112, 128 -> 128.  So efficiency is N/(128+N): as large an N as
 // TMEM allows (kwm*bn <= 256), and the rest of the model only arbitrates ties:
 //   mma   = #MMA x (64 + N/2) + half of the TMA shared-memory writes ((slab + weight bytes) / 128)
-//   l2    = (slab bytes read + weight bytes) / 40      (LTS cap / 148 SMs with the whole chip pulling)
+//   l2    = (slab bytes read + weight bytes) / 30      (B/clk/SM with all 148 SMs pulling; fitted on the stem,
+//           where one-row tiles re-stream the 256 KB of weights per 112 pixels)
 // the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
@@ -533,7 +534,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         const double slab_l2 = (double)d->kd * cchunks * rows * wp * cin_real_bytes;
         const double w_bytes = (double)taps * cchunks * bn * rowb;
         const double mma_clk = n_mma * (64.0 + n_eff / 2.0) + 0.5 * (slab_smem + w_bytes) / 128.0;
-        const double l2_clk = (slab_l2 + w_bytes) / 40.0;
+        const double l2_clk = (slab_l2 + w_bytes) / 30.0;
         const double epi_clk = (double)mt_eff * (bn / 16) * (220.0 + 200.0 * (kwm - 1));
         double tile_clk = mma_clk > l2_clk ? mma_clk : l2_clk;
         if (acc_stages == 1) tile_clk += epi_clk;

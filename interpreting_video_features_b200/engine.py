@@ -295,52 +295,61 @@ class I3DEngine:
         c0, c1, c2, c3, c4, c5 = (u[b].cout for b in ("b0", "b1a", "b1b", "b2a", "b2b", "b3b"))
         cout = c0 + c2 + c4 + c5
         out = new_act(x.n, x.d, x.h, x.w, cout)
-        t1 = new_act(x.n, x.d, x.h, x.w, c1)
-        t2 = new_act(x.n, x.d, x.h, x.w, c3)
+        # the two 1x1x1 bottlenecks read the same x: ONE GEMM with their output channels side by side
+        # (t12 = [t1 | t2]); backward likewise one data-gradient GEMM over the concatenated K
+        pre = "%s.b1a|b2a" % name
+        fsd = {pre + ".conv3d.weight": torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in ("b1a", "b2a")])}
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            fsd["%s.bn.%s" % (pre, k)] = torch.cat([sd["%s.%s.bn.%s" % (name, b, k)] for b in ("b1a", "b2a")])
+        fused = Unit(fsd, pre, (1, 1, 1), mode, dev)
+        t12 = new_act(x.n, x.d, x.h, x.w, c1 + c3)
+        t1, t2 = t12.slice(0, c1), t12.slice(c1, c3)
         t3 = new_act(x.n, x.d, x.h, x.w, x.c)
         am = torch.empty((x.pixels, x.c), dtype=torch.uint8, device=dev)
         k3 = (3, 3, 3)
         pads = tuple(same_pad(sz, 3, 1)[0] for sz in (x.d, x.h, x.w))
         self.fwd_ops.append(("fork",))
-        self._lane = 0
-        add_unit_fwd(u["b0"], x, out.slice(0, c0))
-        self._lane = 1
-        add_unit_fwd(u["b1a"], x, t1)
-        add_unit_fwd(u["b1b"], t1, out.slice(c0, c2))
-        self._lane = 2
-        add_unit_fwd(u["b2a"], x, t2)
-        add_unit_fwd(u["b2b"], t2, out.slice(c0 + c2, c4))
         self._lane = 3
         self.fwd_ops.append((3, lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads)))
         add_unit_fwd(u["b3b"], t3, out.slice(c0 + c2 + c4, c5))
         self._lane = 0
+        add_unit_fwd(fused, x, t12)
+        self.fwd_ops.append(("fork", (1, 2)))  # the 3x3x3 branches start once their bottlenecks exist
+        self._lane = 1
+        add_unit_fwd(u["b1b"], t1, out.slice(c0, c2))
+        self._lane = 2
+        add_unit_fwd(u["b2b"], t2, out.slice(c0 + c2, c4))
+        self._lane = 0
+        add_unit_fwd(u["b0"], x, out.slice(0, c0))
         self.fwd_ops.append(("join",))
         scale = torch.cat([u["b0"].scale, u["b1b"].scale, u["b2b"].scale, u["b3b"].scale]).contiguous()
-        return dict(kind="inception", name=name, units=u, x=x, out=out, scale=scale, gout=out.like(),
-                    t1=t1, t2=t2, t3=t3, argmax=am, pads=pads,
-                    g_t1=t1.like(), g_t2=t2.like(), g_t3=t3.like(), g_x32=x.like(torch.float32))
+        g_t12 = t12.like()
+        return dict(kind="inception", name=name, units=u, fused=fused, x=x, out=out, scale=scale, gout=out.like(),
+                    t1=t1, t2=t2, t3=t3, t12=t12, argmax=am, pads=pads, g_t12=g_t12,
+                    g_t1=g_t12.slice(0, c1), g_t2=g_t12.slice(c1, c3), g_t3=t3.like(),
+                    g_x32=x.like(torch.float32))
 
     def _build_inception_bwd(self, st, g_in, mask, mscale, add_unit_bwd):
         u, x, dz = st["units"], st["x"], st["gout"]
         c0, c2, c4, c5 = u["b0"].cout, u["b1b"].cout, u["b2b"].cout, u["b3b"].cout
-        # branch tails: gradients w.r.t. the 1x1 bottleneck outputs (ReLU'/BN' of b1a/b2a fused); the three
-        # tails and b0's data gradient are independent -> four lanes
+        # Four lanes: the two 3x3x3 branch tails (ReLU'/BN' of b1a/b2a fused, written side by side into
+        # g_t12), and the pool branch: b3b' -> b0' (starts the fp32 sum over x's consumers) -> pool' added in
+        # place.  After the join ONE data-gradient GEMM over the concatenated K of the two bottlenecks adds
+        # the sum and applies the producer's ReLU'/BN'.  (Summation order per element is fixed: b0, pool, GEMM.)
         acc = st["g_x32"]
         self.bwd_ops.append(("fork",))
-        self._lane = 3
-        add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
         self._lane = 1
         add_unit_bwd(u["b1b"], dz.slice(c0, c2), st["t1"], st["g_t1"], mask=st["t1"], mask_scale=u["b1a"].scale)
         self._lane = 2
         add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
-        self._lane = 0
+        self._lane = 3
+        add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
         add_unit_bwd(u["b0"], dz.slice(0, c0), x, acc)
+        self.bwd_ops.append((3, lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], acc, (3, 3, 3), (1, 1, 1),
+                                                          st["pads"], acc_in=acc)))
+        self._lane = 0
         self.bwd_ops.append(("join",))
-        # the four consumers of x: summed in fp32 (fixed order), the last one applies the producer's ReLU'/BN'
-        add_unit_bwd(u["b1a"], st["g_t1"], x, acc, acc_in=acc)
-        add_unit_bwd(u["b2a"], st["g_t2"], x, acc, acc_in=acc)
-        self.bwd_ops.append((0, lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], g_in, (3, 3, 3), (1, 1, 1),
-                                                          st["pads"], acc_in=acc, mask=mask, mask_scale=mscale)))
+        add_unit_bwd(st["fused"], st["g_t12"], x, g_in, acc_in=acc, mask=mask, mask_scale=mscale)
 
     # ------------------------------------------------------------------------------------- running
     def set_input(self, x):
@@ -353,18 +362,19 @@ class I3DEngine:
         capture, where the event waits become graph dependencies)."""
         if not self.use_streams:
             for item in prog:
-                if len(item) == 2:
+                if isinstance(item[0], int):
                     item[1]()
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         for item in prog:
-            if item[0] == "fork":
+            if item[0] == "fork":  # ("fork",) all side lanes, ("fork", (lanes...)) only those
                 ev = torch.cuda.Event()
                 ev.record(main)
-                for sd in self._side:
-                    sd.wait_event(ev)
+                for i, sd in enumerate(self._side):
+                    if len(item) == 1 or (i + 1) in item[1]:
+                        sd.wait_event(ev)
             elif item[0] == "join":
                 for sd in self._side:
                     main.wait_stream(sd)

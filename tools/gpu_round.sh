@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name" ; timeout "$TMO" "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "exit $rc" | tee -a gpurun_out/$name.log; tail -n 12 gpurun_out/$name.log | cut -c1-700; return $rc; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt; nproc >> gpurun_out/gpu.txt
 TMO=600 run t_conv python -m pytest tests/test_gpu_kernels.py -k conv -q -m gpu -x || exit 1
-TMO=2400 run t_gpu_all python -m pytest tests -q -m gpu --deselect tests/test_gpu_clstm.py::test_forward_and_mask_gradient
+TMO=2400 run t_gpu_all python -m pytest tests -q -m gpu
 TMO=900 run bench python bench.py --steps 20 --warmup 3
 [ -n "$EXTRA" ] && TMO=600 run extra bash -c "$EXTRA"
 TMO=300 run prof_plain python tools/profile_step.py
