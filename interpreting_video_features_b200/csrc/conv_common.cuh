@@ -184,23 +184,43 @@ struct EpilogueArgs {
   void* out;
 };
 
+// Global operands of one full 16-channel chunk's epilogue (fp32 consumer sum, bf16 ReLU mask), fetched one
+// chunk AHEAD of their use so that their latency (~1 us) overlaps the TMEM loads and math of the previous
+// chunk instead of serialising every chunk (the data-gradient epilogues were bounded by exactly that).
+struct EpiPre {
+  float4 ac[4];
+  uint4 mk[2];
+};
+__device__ __forceinline__ void epilogue_prefetch(const EpilogueArgs& e, int nb, size_t out_row, size_t mask_row,
+                                                  bool active, EpiPre& pre) {
+  if (!active || nb + 16 > e.cout) return;  // partial chunks take the scalar path at use
+  if (e.flags & IVF_EP_ACCUM) {
+    const float4* a4 = reinterpret_cast<const float4*>(e.acc_in + out_row + nb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre.ac[j] = a4[j];
+  }
+  if (e.flags & IVF_EP_MASK) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(e.mask_y + mask_row + nb);
+    pre.mk[0] = m4[0];
+    pre.mk[1] = m4[1];
+  }
+}
+
 __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const uint32_t (&r)[16], int nb,
                                                  const float* sc, const float* sh, const float* ms,
-                                                 size_t out_row, size_t mask_row) {
+                                                 size_t out_row, size_t mask_row, const EpiPre& pre) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
   const bool full = nb + 16 <= e.cout;
   if (e.flags & IVF_EP_ACCUM) {
     if (full) {
-      const float4* a4 = reinterpret_cast<const float4*>(e.acc_in + out_row + nb);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float4 a = a4[j];
-        v[4 * j + 0] += a.x;
-        v[4 * j + 1] += a.y;
-        v[4 * j + 2] += a.z;
-        v[4 * j + 3] += a.w;
+        v[4 * j + 0] += pre.ac[j].x;
+        v[4 * j + 1] += pre.ac[j].y;
+        v[4 * j + 2] += pre.ac[j].z;
+        v[4 * j + 3] += pre.ac[j].w;
       }
     } else {
       for (int j = 0; j < 16; ++j)
@@ -217,11 +237,9 @@ __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const ui
   }
   if (e.flags & IVF_EP_MASK) {
     if (full) {
-      const uint4* m4 = reinterpret_cast<const uint4*>(e.mask_y + mask_row + nb);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        uint4 mm = m4[hh];
-        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mm);
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&pre.mk[hh]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           int jj = hh * 8 + j;

@@ -290,19 +290,24 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const size_t mask_row = pix * p.mask_ld + p.mask_coff;
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
                                (uint32_t)((acc * p.mt + m) * p.slot);
+        EpiPre cur, nxt;
+        epilogue_prefetch(ea, t.nt * p.bn, out_row, mask_row, ok, cur);
         if (p.kwm == 1) {
           for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            const int nb = t.nt * p.bn + c0;
+            if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, ok, nxt);
             uint32_t rr[16];
             tmem_ld16(taddr + c0, rr);
-            const int nb = t.nt * p.bn + c0;
-            if (!ok || nb >= p.cout) continue;
-            epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+            if (ok && nb < p.cout)
+              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row, cur);
+            cur = nxt;
           }
         } else {
           // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down
           const int kwm = p.kwm;
           const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
           for (int c0 = 0; c0 < p.bn; c0 += 16, ++xpar) {
+            if (c0 + 16 < p.bn) epilogue_prefetch(ea, t.nt * p.bn + c0 + 16, out_row, mask_row, ok, nxt);
             uint32_t tg[4][16];
             uint32_t nx[3][16];
 #pragma unroll
@@ -344,11 +349,13 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const int nb = t.nt * p.bn + c0;
-            if (!ok || nb >= p.cout) continue;
-            uint32_t rr[16];
+            if (ok && nb < p.cout) {
+              uint32_t rr[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
-            epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row);
+              for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
+              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row, cur);
+            }
+            cur = nxt;
           }
         }
       }
@@ -473,8 +480,8 @@ int env_int(const char* name, int dflt) {
 // of math: N = 32 -> 80 clk, 64 -> 96, 96 -> 112, 128 -> 128.  So efficiency is N/(128+N): as large an N as
 // TMEM allows (kwm*bn <= 256), and the rest of the model only arbitrates ties:
 //   mma   = #MMA x (64 + N/2) + half of the TMA shared-memory writes ((slab + weight bytes) / 128)
-//   l2    = (slab bytes read + weight bytes) / 30      (B/clk/SM with all 148 SMs pulling; fitted on the stem,
-//           where one-row tiles re-stream the 256 KB of weights per 112 pixels)
+//   l2    = (slab bytes read + weight bytes) / 40      (B/clk/SM with all 148 SMs pulling = the LTS cap; a slab
+//           pixel costs at least 128 B: the 48-byte rows of the 24-channel stem operand move at that rate)
 // the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
@@ -531,11 +538,13 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         const int n_eff = kwm * bn;
         const int cin_real_bytes = (cin < kch ? cin : kch) * 2;
         const double slab_smem = (double)d->kd * cchunks * rows * wp * rowb;
-        const double slab_l2 = (double)d->kd * cchunks * rows * wp * cin_real_bytes;
+        const double slab_l2 = (double)d->kd * cchunks * rows * wp * (cin_real_bytes < 128 ? 128 : cin_real_bytes);
         const double w_bytes = (double)taps * cchunks * bn * rowb;
         const double mma_clk = n_mma * (64.0 + n_eff / 2.0) + 0.5 * (slab_smem + w_bytes) / 128.0;
-        const double l2_clk = (slab_l2 + w_bytes) / 30.0;
-        const double epi_clk = (double)mt_eff * (bn / 16) * (220.0 + 200.0 * (kwm - 1));
+        const double l2_clk = (slab_l2 + w_bytes) / 40.0;
+        const double epi_clk = (double)mt_eff * (bn / 16) *
+                               (220.0 + 200.0 * (kwm - 1) + ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 150.0 : 0.0)) +
+                               ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 1200.0 * mt_eff : 0.0);
         double tile_clk = mma_clk > l2_clk ? mma_clk : l2_clk;
         if (acc_stages == 1) tile_clk += epi_clk;
         else if (epi_clk > tile_clk) tile_clk = epi_clk;

@@ -183,8 +183,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr_row = tmem_acc + ((uint32_t)(q * 32) << 16);
     const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
     const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
@@ -194,12 +192,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.acc_in = acc_in;
     ea.mask_y = mask_y;
     ea.out = out;
+    // the first chunk's global operands are fetched while the MMAs still run
+    EpiPre cur, nxt;
+    epilogue_prefetch(ea, ntile * p.bn, out_row, mask_row, row_ok, cur);
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
+      if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, row_ok, nxt);
       uint32_t r[16];
       tmem_ld16(taddr_row + c0, r);
-      const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
-      if (!row_ok || nb >= p.cout) continue;
-      epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row);
+      if (row_ok && nb < p.cout)
+        epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+      cur = nxt;
     }
   }
 
