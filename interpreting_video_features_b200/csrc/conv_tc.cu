@@ -35,6 +35,7 @@ struct TcParams {
   int bn;                // UMMA N of this launch (multiple of 16, <= 256)
   int kh, kw;            // tap decode
   int ntaps, cchunks;    // K iterations = ntaps*cchunks
+  int cin, cin_pad;      // real channels (last chunk issues only its valid K steps); weight K pitch per tap
   int sd, sh, sw;
   int pd, ph, pw;
   int out_ld, out_coff;
@@ -121,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int cw = ow0 * p.sw - p.pw, ch = oh0 * p.sh - p.ph, cd = od0 * p.sd - p.pd;
       int stage = 0;
       uint32_t phase = 0;
-      int cc = 0, kw_i = 0, kh_i = 0, kd_i = 0;
+      int cc = 0, kw_i = 0, kh_i = 0, kd_i = 0, tap = 0;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
@@ -130,11 +131,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full_bar[stage], p.tx_bytes);
           tma_load_im2col_5d(a_dst, &tmA, &full_bar[stage], cc * KCH, cw, ch, cd, n0, (uint16_t)kw_i,
                              (uint16_t)kh_i, (uint16_t)kd_i);
-          tma_load_2d(b_dst, &tmB, &full_bar[stage], it * KCH, ntile * p.bn);
+          tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_pad + cc * KCH, ntile * p.bn);
         }
         __syncwarp();
         if (++cc == p.cchunks) {
           cc = 0;
+          ++tap;
           if (++kw_i == p.kw) {
             kw_i = 0;
             if (++kh_i == p.kh) {
@@ -155,7 +157,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(TILE_M, p.bn);
       const uint32_t desc_hi = smem_desc_hi(KT::sbo, KT::layout);
-      int stage = 0;
+      const int tail_ksteps = (p.cin - (p.cchunks - 1) * KCH + 15) / 16;
+      int stage = 0, cc = 0;
       uint32_t phase = 0;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full_bar[stage], phase);
@@ -163,12 +166,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_lo = smem_desc_lo(smem_base + stage * stage_bytes);
         const uint32_t b_lo = smem_desc_lo(smem_base + stage * stage_bytes + p.a_stage_bytes);
         if (leader) {
+          if (cc + 1 < p.cchunks || tail_ksteps == KT::ksteps) {
 #pragma unroll
-          for (int k = 0; k < KT::ksteps; ++k)
-            umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KT::ksteps; ++k)
+              umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          } else {  // last channel chunk of a tap: only the K steps that hold real channels
+            for (int k = 0; k < tail_ksteps; ++k)
+              umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
         __syncwarp();
+        if (++cc == p.cchunks) cc = 0;
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -429,14 +438,16 @@ int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CU
 
 }  // namespace
 
-extern "C" int ivf_conv_bf16_kchunk(int cin) {
-  if (cin <= 16) return 16;
-  int p64 = (cin + 63) / 64 * 64, p32 = (cin + 31) / 32 * 32;
-  return p32 < p64 ? 32 : 64;
-}
+// Channels per K stage: one 128-byte swizzled row (64 channels) unless the operand is narrower.  A wider
+// operand whose channel count is not a multiple of 64 (96, 112, 144, 160 ...) still moves 64-channel boxes
+// (TMA zero-fills past the last channel) and the last chunk issues only its real K steps: 128-byte TMA rows
+// and half as many pipeline stages as the former 32-channel chunking of those layers.
+extern "C" int ivf_conv_bf16_kchunk(int cin) { return cin <= 16 ? 16 : (cin <= 32 ? 32 : 64); }
+// K pitch of one filter tap in the packed weights
 extern "C" int ivf_conv_bf16_cin_pad(int cin) {
-  int k = ivf_conv_bf16_kchunk(cin);
-  return (cin + k - 1) / k * k;
+  if (cin <= 16) return 16;
+  if (cin <= 32) return 32;
+  return (cin + 15) / 16 * 16;
 }
 extern "C" int ivf_conv_bf16_ntile(int cout) {
   int tiles = (cout + 255) / 256;
@@ -485,7 +496,9 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   p.bn = bn;
   p.kh = d->kh; p.kw = d->kw;
   p.ntaps = ntaps;
-  p.cchunks = cin_pad / kch;
+  p.cchunks = (d->cin + kch - 1) / kch;
+  p.cin = d->cin;
+  p.cin_pad = cin_pad;
   p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;

@@ -195,8 +195,11 @@ maxpool_bwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
   if (d.flags & IVF_EP_MASK) {
     const uint4 raw = *reinterpret_cast<const uint4*>(mask_y + (long long)ipix * d.mask_ld + d.mask_coff + c);
     const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(&raw);
+    const float4 s0 = *reinterpret_cast<const float4*>(mask_scale + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(mask_scale + c + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = __bfloat162float(y[i]) > 0.f ? g[i] * mask_scale[c + i] : 0.f;
+    for (int i = 0; i < 8; ++i) g[i] = __bfloat162float(y[i]) > 0.f ? g[i] * sc[i] : 0.f;
   }
   if (d.flags & IVF_EP_OUT_F32) {
     float* p = reinterpret_cast<float*>(dx) + o;
@@ -467,7 +470,8 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
   if (v_ok) {
     long long total = ipix * (d->c / V);
     if constexpr (sizeof(T) == 2) {
-      const bool f32_ok = !(d->flags & IVF_EP_OUT_F32) || (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
+      const bool f32_ok = (!(d->flags & IVF_EP_OUT_F32) || (reinterpret_cast<uintptr_t>(dx) & 15) == 0) &&
+                          (reinterpret_cast<uintptr_t>(mask_scale) & 15) == 0;
       if (fits31(d) && f32_ok && d->in_ld % 4 == 0) {
         const int rows = d->n * d->id * d->ih;
         IVF_POOL_GEO_DISPATCH((maxpool_bwd_bf16x8_kernel<G><<<row_grid(rows, d->iw * (d->c / V)), threads, 0, st>>>(
