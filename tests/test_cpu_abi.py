@@ -29,10 +29,11 @@ def test_version_and_tiling_helpers():
     from interpreting_video_features_b200 import _lib
     lib = _lib.load()
     assert b"sm_100a" in lib.ivf_version()
-    # K stage selection: smallest padding, ties to the wider stage
+    # K stage: one 128-byte row (64 channels) unless the operand is narrower; tap pitch padded to 16
     assert [lib.ivf_conv_bf16_kchunk(c) for c in (8, 16, 24, 32, 48, 64, 96, 112, 144, 160, 192, 832)] == \
-        [16, 16, 32, 32, 64, 64, 32, 64, 32, 32, 64, 64]
+        [16, 16, 32, 32, 64, 64, 64, 64, 64, 64, 64, 64]
     assert lib.ivf_conv_bf16_cin_pad(24) == 32 and lib.ivf_conv_bf16_cin_pad(96) == 96
+    assert lib.ivf_conv_bf16_cin_pad(8) == 16 and lib.ivf_conv_bf16_cin_pad(112) == 112
     assert lib.ivf_conv_bf16_ntile(174) == 176 and lib.ivf_conv_bf16_ntile(384) == 192
     assert lib.ivf_conv_bf16_cout_pad(384) == 384 and lib.ivf_conv_bf16_cout_pad(288) == 288
     assert lib.ivf_conv_bf16_cout_pad(24) == 32
@@ -62,3 +63,39 @@ def test_product_package_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(root, f)
+
+
+def test_slab_plan_diagnostic_needs_no_gpu():
+    """ivf_conv_slab_plan: the wide stride-1 layers of C2 get the halo-slab kernel, the 14x14 stage and
+    every 1x1x1 convolution the im2col kernel; the plan fits shared memory and TMEM."""
+    import ctypes as C
+    from interpreting_video_features_b200 import _lib
+    lib = _lib.load()
+
+    def plan(dhw, cin, cout, k, pf, flags=0):
+        d = _lib.ConvDesc()
+        d.n = 8
+        d.id, d.ih, d.iw = dhw
+        d.od, d.oh, d.ow = dhw
+        d.cin, d.cout = cin, cout
+        d.kd, d.kh, d.kw = k
+        d.sd = d.sh = d.sw = 1
+        d.pd, d.ph, d.pw = pf
+        d.in_ld, d.out_ld = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+        d.dtype, d.flags = _lib.IVF_BF16, flags
+        out = (C.c_int * 11)()
+        return lib.ivf_conv_slab_plan(C.byref(d), 148, out), list(out)
+
+    for args in [((8, 112, 112), 24, 64, (4, 4, 4), (1, 1, 1)), ((8, 112, 112), 64, 24, (4, 4, 4), (2, 2, 2), 8),
+                 ((8, 56, 56), 64, 192, (3, 3, 3), (1, 1, 1)), ((8, 28, 28), 96, 128, (3, 3, 3), (1, 1, 1)),
+                 ((8, 28, 28), 32, 16, (3, 3, 3), (1, 1, 1), 12)]:
+        ok, (kch, bn, ntiles, mt, th, acc, a_st, b_st, tiles, smem, kwm) = plan(*args)
+        assert ok == 1, args
+        assert kch in (32, 64) and bn % 16 == 0 and bn * ntiles >= args[2]
+        assert 1 <= mt <= 4 and acc in (1, 2) and a_st >= 2 and b_st >= 2 and tiles > 0
+        assert kwm >= 1 and args[3][2] % kwm == 0 and kwm * bn <= 256
+        assert acc * mt * ((kwm * bn + 31) // 32 * 32) <= 512          # TMEM columns
+        assert smem <= 212 * 1024                                       # dynamic shared memory budget
+        assert th * (args[0][2] + args[3][2] - 1) <= mt * 128           # the tile's padded-width pixels fit
+    assert plan((4, 14, 14), 96, 208, (3, 3, 3), (1, 1, 1))[0] == 0      # narrow map -> im2col
+    assert plan((8, 56, 56), 64, 64, (1, 1, 1), (0, 0, 0))[0] == 0       # 1x1x1 -> im2col
