@@ -96,9 +96,9 @@ int ivf_conv_bf16_cin_pad(int cin);  /* cin rounded up to the K stage      */
 int ivf_conv_bf16_ntile(int cout);   /* UMMA N of one CTA tile             */
 int ivf_conv_bf16_cout_pad(int cout);
 
-/* Diagnostic, needs no GPU: which bf16 kernel a layer gets.  Returns 1 and fills plan[11] =
+/* Diagnostic, needs no GPU: which bf16 kernel a layer gets.  Returns 1 and fills plan[12] =
  * {channels per slab row, N tile, N tiles, accumulators per tile, rows per tile, TMEM stages, slab stages,
- *  weight stages, tiles, dynamic smem bytes, kw taps merged into N} when the halo-slab kernel serves it, 0 for the im2col kernel. */
+ *  weight stages, tiles, dynamic smem bytes, kw taps merged into N, CTAs per work item (2 = cta_group::2 pairs)} when the halo-slab kernel serves it, 0 for the im2col kernel. */
 int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* plan);
 
 int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,

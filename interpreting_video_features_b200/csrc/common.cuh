@@ -23,7 +23,7 @@ struct ivf_handle {
   // cache of encoded TMA tensor maps keyed by a byte string of everything that shapes them
   std::map<std::string, CUtensorMap> tmaps;
   bool tc_attr_set[4] = {false, false, false, false};
-  bool slab_attr_set[2] = {false, false};
+  bool slab_attr_set[4] = {false, false, false, false};
   // small per-handle scratch (partial logits of the head kernels); allocated once in ivf_create so
   // that no call allocates (CUDA-graph capture safe), freed in ivf_destroy
   float* scratch = nullptr;

@@ -21,6 +21,13 @@
 // between column blocks, done with warp shuffles plus a small shared-memory exchange of the first kwm-1
 // rows of the next 32-row quarter.
 //
+// NCTA = 2 (cta_group::2): a CTA pair on one TPC works on two row-adjacent tiles in lockstep.  Each SM loads
+// its own slab and HALF of the weight rows; the leader CTA issues M = 256 MMAs that read both SMs' shared
+// memory and write each SM's TMEM.  Per SM an MMA then fetches 4 KB + 16N bytes instead of 4 KB + 32N (the
+// operand fetch is what bounds this kernel), and the weights cross L2->SM once per pair.  TMA completions of
+// both CTAs are counted on the leader's "full" barriers; MMA commits are multicast to both CTAs' "empty" and
+// "accumulator full" barriers; both CTAs' epilogues arrive on the leader's "accumulator empty" barrier.
+//
 // Persistent, warp specialised: warp 0 slab TMA producer, warp 1 MMA issuer, warp 2 weight TMA
 // producer (+ TMEM alloc), warps 3-6 epilogue; TMEM accumulators double buffered so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
@@ -54,18 +61,22 @@ struct SlabParams {
   int a_stages, b_stages, tmem_cols;
   int acc_stages;  // 2: epilogue of tile i overlaps the MMAs of tile i+1; 1: all TMEM columns for one tile
   int kch;
+  int ncta;  // 1, or 2 = CTA pairs (cta_group::2)
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
 };
 
 struct TileCoord {
   int nt, h0, dz, nn;
 };
-__device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
+// hpairs = row tiles per slice in units of one work item: htiles (single CTA) or ceil(htiles/2) (CTA pair:
+// rank r takes row tile 2*j + r; a tile past the last row is all padding and stores nothing)
+__device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile, int ncta, int rank) {
   TileCoord t;
   t.nt = tile % p.ntiles;
   int r = tile / p.ntiles;
-  t.h0 = (r % p.htiles) * p.th;
-  r /= p.htiles;
+  const int hp = ncta == 2 ? (p.htiles + 1) / 2 : p.htiles;
+  t.h0 = ((r % hp) * ncta + rank) * p.th;
+  r /= hp;
   t.dz = r % p.dd;
   t.nn = r / p.dd;
   return t;
@@ -73,7 +84,7 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) 
 
 // KCH = channels per slab row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B, for
 // operands of <= 32 channels: the space-to-depth stem's 24-of-32 and the 16/32-channel bottlenecks)
-template <int KCH>
+template <int KCH, int NCTA>
 __global__ void __launch_bounds__(SLAB_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const SlabParams p, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -93,6 +104,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int KSTEPS = KCH / 16;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;  // 0 = leader of the pair
+  const int item0 = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
@@ -108,17 +122,25 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&t_empty[s], 4 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(&tmem_base_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(&tmem_base_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (warp >= 3) {
     for (int i = threadIdx.x - 96; i < 256; i += 128) {
@@ -130,6 +152,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = tmem_base_slot;
 
@@ -139,17 +162,23 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = item0; tile < p.num_tiles; tile += item_step) {
+        const TileCoord t = decode_tile(p, tile, NCTA, rank);
         for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
           const int zd = t.dz + kd_i - p.pd;
           if (zd < 0 || zd >= p.dd) continue;  // an all-padding depth tap contributes nothing
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(&a_empty[stage], phase ^ 1u);
             if (leader) {
-              mbar_expect_tx(&a_full[stage], p.a_tx);
-              tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
-                          t.h0 - p.ph, zd, t.nn);
+              if constexpr (NCTA == 2) {
+                if (rank == 0) mbar_expect_tx(&a_full[stage], 2u * p.a_tx);  // both CTAs' slabs
+                tma_load_5d_pair(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
+                                 t.h0 - p.ph, zd, t.nn);
+              } else {
+                mbar_expect_tx(&a_full[stage], p.a_tx);
+                tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
+                            t.h0 - p.ph, zd, t.nn);
+              }
             }
             __syncwarp();
             if (++stage == p.a_stages) {
@@ -166,8 +195,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = item0; tile < p.num_tiles; tile += item_step) {
+        const TileCoord t = decode_tile(p, tile, NCTA, rank);
         for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
           const int zd = t.dz + kd_i - p.pd;
           if (zd < 0 || zd >= p.dd) continue;
@@ -176,10 +205,30 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(&b_empty[stage], phase ^ 1u);
               const int tap0 = (kd_i * p.kh + kh_i) * p.kw;
               if (leader) {
-                mbar_expect_tx(&b_full[stage], p.b_tx);
-                for (int kw_i = 0; kw_i < p.kw; ++kw_i)
-                  tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
-                              (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
+                if constexpr (NCTA == 2) {
+                  // The N rows of an MMA (kwm stacked taps of bn rows) are split in halves over the pair:
+                  // kwm == 1: this CTA holds rows [rank*bn/2, +bn/2) of every tap; kwm == 2 / 4: it holds
+                  // the taps rank*kwm/2 .. of every merged group.  b_tap_bytes is this CTA's share of a tap.
+                  if (rank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_tx);
+                  const uint32_t dst0 = b_base + stage * p.b_stage_bytes;
+                  if (p.kwm == 1) {
+                    for (int kw_i = 0; kw_i < p.kw; ++kw_i)
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                                       (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn + rank * (p.bn / 2));
+                  } else {
+                    const int half = p.kwm / 2;
+                    int slot_i = 0;
+                    for (int g0 = 0; g0 < p.kw; g0 += p.kwm)
+                      for (int j = 0; j < half; ++j, ++slot_i)
+                        tma_load_2d_pair(dst0 + slot_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                                         (tap0 + g0 + rank * half + j) * p.cin_pad + cc * KCH, t.nt * p.bn);
+                  }
+                } else {
+                  mbar_expect_tx(&b_full[stage], p.b_tx);
+                  for (int kw_i = 0; kw_i < p.kw; ++kw_i)
+                    tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                                (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
+                }
               }
               __syncwarp();
               if (++stage == p.b_stages) {
@@ -193,9 +242,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    {
+    if (rank == 0) {  // of a pair only the leader CTA issues
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128, p.bn * p.kwm);
+      const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.bn * p.kwm);
       const uint32_t desc_hi = smem_desc_hi(8 * ROWB, LAYOUT);  // 8-row swizzle atoms back to back
       // everything the loop needs, in registers (not re-read from the parameter bank per MMA)
       const int kd_n = p.kd, kh_n = p.kh, kw_n = p.kw, pd = p.pd, dd = p.dd, cin = p.cin, cchunks = p.cchunks;
@@ -203,12 +252,13 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t kwm = (uint32_t)p.kwm;
       const uint32_t slot = (uint32_t)p.slot;
       const uint32_t wp8 = (uint32_t)p.wp * ROW16;           // one padded row of pixels, in 16-byte units
-      const uint32_t b_tap16 = p.b_tap_bytes >> 4;
+      // 16-byte units between the weight operands of consecutive merged groups (per CTA: its half of N)
+      const uint32_t b_grp16 = (NCTA == 2 && p.kwm > 1 ? (uint32_t)(p.kwm / 2) : (uint32_t)p.kwm) * (p.b_tap_bytes >> 4);
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
+        const TileCoord t = decode_tile(p, tile, NCTA, rank);
         const int acc = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t tphase = p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
         mbar_wait(&t_empty[acc], tphase ^ 1u);
@@ -229,38 +279,52 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
               uint32_t a_tap = row_lo;  // + kw pixels; a merged group of kwm taps is one MMA of N = kwm*bn
-              for (int kw_i = 0; kw_i < kw_n; kw_i += kwm, a_tap += kwm * ROW16, b_lo += kwm * b_tap16) {
+              for (int kw_i = 0; kw_i < kw_n; kw_i += kwm, a_tap += kwm * ROW16, b_lo += b_grp16) {
                 uint32_t a_lo = a_tap, d = d_tmem;
                 if (leader) {
                   if (ksteps == KSTEPS) {
                     for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot) {
 #pragma unroll
-                      for (int k = 0; k < KSTEPS; ++k)
-                        umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                      for (int k = 0; k < KSTEPS; ++k) {
+                        if constexpr (NCTA == 2)
+                          umma_bf16_lo_pair(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                        else
+                          umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                      }
                     }
                   } else {
                     for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot)
-                      for (int k = 0; k < ksteps; ++k)
-                        umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                      for (int k = 0; k < ksteps; ++k) {
+                        if constexpr (NCTA == 2)
+                          umma_bf16_lo_pair(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                        else
+                          umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
+                      }
                   }
                 }
                 accum = 1u;
               }
               __syncwarp();
-              if (leader) umma_commit(&b_empty[bs]);  // weight slot free once these MMAs have read it
+              if (leader) {  // weight slot free once these MMAs have read it
+                if constexpr (NCTA == 2) umma_commit_pair(&b_empty[bs]); else umma_commit(&b_empty[bs]);
+              }
               if (++bs == b_stages) {
                 bs = 0;
                 bphase ^= 1u;
               }
             }
-            if (leader) umma_commit(&a_empty[as]);  // slab slot free
+            if (leader) {  // slab slot free
+              if constexpr (NCTA == 2) umma_commit_pair(&a_empty[as]); else umma_commit(&a_empty[as]);
+            }
             if (++as == a_stages) {
               as = 0;
               aphase ^= 1u;
             }
           }
         }
-        if (leader) umma_commit(&t_full[acc]);  // accumulators of this tile complete
+        if (leader) {  // accumulators of this tile complete
+          if constexpr (NCTA == 2) umma_commit_pair(&t_full[acc]); else umma_commit(&t_full[acc]);
+        }
       }
     }
   } else {
@@ -274,8 +338,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.out = out;
     int it = 0;
     uint32_t xpar = 0;  // exchange-buffer parity (kw-merge)
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
+      const TileCoord t = decode_tile(p, tile, NCTA, rank);
       const int acc = p.acc_stages == 2 ? (it & 1) : 0;
       mbar_wait(&t_full[acc], p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -361,17 +425,25 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_leader(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
+      }
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();  // the peer may still be reading this SM's operands / signalling
   if (warp == 2) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    if constexpr (NCTA == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -434,6 +506,7 @@ int slab_map_a(ivf_handle* h, const ivf_conv_desc* d, const void* in, int wp, in
 }
 
 int slab_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int bn, int kch, CUtensorMap* out) {
+  // bn here = rows of one TMA box (the N tile, or half of it per CTA of a pair)
   SlabKeyB key;
   memset(&key, 0, sizeof(key));
   key.base = w; key.ktot = ktot; key.cout_pad = cout_pad; key.bn = bn; key.kch = kch;
@@ -498,6 +571,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   }
   const int forced_mt = env_int("IVF_SLAB_MT", 0), forced_nt = env_int("IVF_SLAB_NT", 0);
   const int forced_acc = env_int("IVF_SLAB_ACC", 0), forced_kwm = env_int("IVF_SLAB_KWM", 0);
+  const bool allow_pair = env_int("IVF_SLAB_2CTA", 0) != 0 && sm_count % 2 == 0;
   double best_cost = 1e30;
   bool found = false;
   for (int ntiles = 1; ntiles <= 4; ++ntiles) {
@@ -505,12 +579,18 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     const int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
     if (bn > 256 || ntiles * bn > 256 + 15) continue;
     if (ntiles > 1 && bn < 32) continue;
-    const uint32_t b_tap = ((uint32_t)bn * rowb + 1023u) & ~1023u;  // == bn*rowb (bn % 16 == 0): taps are dense
-    const uint32_t b_stage = b_tap * (uint32_t)d->kw;
+    for (int ncta = 1; ncta <= 2; ++ncta) {
+    if (ncta == 2 && !allow_pair) continue;
     for (int kwm = 1; kwm <= 4 && kwm <= d->kw; ++kwm) {
     if (d->kw % kwm || kwm * bn > 256) continue;
+    if (ncta == 2 && kwm == 3) continue;  // the pair splits the stacked N rows in halves: whole taps or half a tap
     if (forced_kwm && kwm != forced_kwm && !(forced_kwm > 1 && (d->kw % forced_kwm || forced_kwm * bn > 256))) continue;
     const int slot = (kwm * bn + 31) / 32 * 32;
+    // one CTA's share of a tap's weight rows: all bn, or (pair) bn/2 when kwm == 1; with kwm 2/4 a pair CTA holds
+    // kwm/2 whole taps per merged group.  Taps are dense (bn % 16 == 0 keeps them on swizzle-atom boundaries).
+    const uint32_t b_tap = (uint32_t)((ncta == 2 && kwm == 1) ? bn / 2 : bn) * rowb;
+    const uint32_t b_stage = (uint32_t)bn * rowb * (uint32_t)d->kw / ncta;
+    if (b_tap % (8u * rowb)) continue;
     for (int acc_stages = 2; acc_stages >= 1; --acc_stages) {
       if (forced_acc && acc_stages != forced_acc) continue;
       for (int mt = 4; mt >= 1; --mt) {
@@ -532,15 +612,18 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
         if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
         // ---- cost
-        const double tiles = (double)d->n * d->id * htiles * ntiles;
-        const double waves = ceil(tiles / sm_count);
+        const double tiles = (double)d->n * d->id * ((htiles + ncta - 1) / ncta) * ntiles;  // work items
+        const double waves = ceil(tiles / (sm_count / ncta));
         const double n_mma = (double)taps / kwm * ksteps_total * mt_eff;
         const int n_eff = kwm * bn;
         const int cin_real_bytes = (cin < kch ? cin : kch) * 2;
         const double slab_smem = (double)d->kd * cchunks * rows * wp * rowb;
         const double slab_l2 = (double)d->kd * cchunks * rows * wp * (cin_real_bytes < 128 ? 128 : cin_real_bytes);
-        const double w_bytes = (double)taps * cchunks * bn * rowb;
-        const double mma_clk = n_mma * (64.0 + n_eff / 2.0) + 0.5 * (slab_smem + w_bytes) / 128.0;
+        const double w_bytes = (double)taps * cchunks * bn * rowb / ncta;  // per SM
+        // per SM: 4 KB of activations + its share of the weight rows at ~64 B/clk, never below the math
+        double per_mma = 64.0 + n_eff / (2.0 * ncta);
+        if (per_mma < n_eff / 2.0) per_mma = n_eff / 2.0;
+        const double mma_clk = n_mma * per_mma + 0.5 * (slab_smem + w_bytes) / 128.0;
         const double l2_clk = (slab_l2 + w_bytes) / 40.0;
         const double epi_clk = (double)mt_eff * (bn / 16) *
                                (220.0 + 200.0 * (kwm - 1) + ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 150.0 : 0.0)) +
@@ -562,6 +645,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->ntiles = ntiles;
           p->slot = slot;
           p->kwm = kwm;
+          p->ncta = ncta;
           p->acc_stages = acc_stages;
           p->a_stages = a_stages;
           p->b_stages = b_stages;
@@ -569,7 +653,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->b_stage_bytes = b_stage;
           p->b_tap_bytes = b_tap;
           p->a_tx = (uint32_t)rows * wp * rowb;
-          p->b_tx = (uint32_t)bn * rowb * (uint32_t)d->kw;
+          p->b_tx = b_stage;
           int cols = 32;
           while (cols < acc_stages * mt_eff * slot) cols <<= 1;
           p->tmem_cols = cols;
@@ -577,24 +661,43 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
       }
     }
     }
+    }
   }
   return found;
 }
 
-template <int KCH>
+template <int KCH, int NCTA>
 int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, const CUtensorMap& mb,
                   const float* scale, const float* shift, const float* acc_in, const void* mask_y,
                   const float* mask_scale, void* out, cudaStream_t st) {
-  const int slot = KCH == 64 ? 3 : 2;
-  if (!h->slab_attr_set[slot - 2]) {
-    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const int slot = (KCH == 64 ? 0 : 1) + 2 * (NCTA - 1);
+  if (!h->slab_attr_set[slot]) {
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(SLAB_SMEM_BUDGET + 2048)));
-    h->slab_attr_set[slot - 2] = true;
+    h->slab_attr_set[slot] = true;
   }
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
-  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  conv_slab_kernel<KCH><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
-                                                          (const __nv_bfloat16*)mask_y, mask_scale, out);
+  const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
+  if (NCTA == 1) {
+    conv_slab_kernel<KCH, 1><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
+                                                               (const __nv_bfloat16*)mask_y, mask_scale, out);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(SLAB_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IVF_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<KCH, 2>, ma, mb, p, scale, shift, acc_in,
+                                (const __nv_bfloat16*)mask_y, mask_scale, out));
+  }
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -636,27 +739,33 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
   p.flags = d->flags;
-  long long tiles = (long long)d->n * d->id * p.htiles * p.ntiles;
+  long long tiles = (long long)d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;  // work items
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;
   if (env_int("IVF_SLAB_VERBOSE", 0))
-    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) tiles %d\n",
+    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) items %d ncta %d\n",
             d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.kwm, p.mt, p.th,
-            p.acc_stages, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.num_tiles);
+            p.acc_stages, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.num_tiles, p.ncta);
 
   CUtensorMap ma, mb;
   rc = slab_map_a(h, d, in, p.wp, p.th + d->kh - 1, p.kch, &ma);
   if (rc) return rc;
   const int ntaps = d->kd * d->kh * d->kw;
-  rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), p.bn, p.kch, &mb);
+  const int box_rows = (p.ncta == 2 && p.kwm == 1) ? p.bn / 2 : p.bn;
+  rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), box_rows, p.kch, &mb);
   if (rc) return rc;
+  if (p.ncta == 2) {
+    if (p.kch == 64)
+      return slab_launch_t<64, 2>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+    return slab_launch_t<32, 2>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  }
   if (p.kch == 64)
-    return slab_launch_t<64>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
-  return slab_launch_t<32>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+    return slab_launch_t<64, 1>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  return slab_launch_t<32, 1>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
 }
 
 // diagnostic (no GPU needed): the tile plan the slab kernel would use for a layer, or 0 when the layer
-// goes to the im2col kernel.  plan = {kch, bn, ntiles, mt, th, acc_stages, a_stages, b_stages, tiles, smem, kwm}
+// goes to the im2col kernel.  plan = {kch, bn, ntiles, mt, th, acc_stages, a_stages, b_stages, tiles, smem, kwm, ncta}
 extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* plan) {
   if (!d || !plan) return 0;
   ivf_handle fake;
@@ -666,8 +775,9 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   if (!slab_config(d, sm_count, &p)) return 0;
   plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
   plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
-  plan[8] = d->n * d->id * p.htiles * p.ntiles;
+  plan[8] = d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
   plan[9] = (int)(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes);
   plan[10] = p.kwm;
+  plan[11] = p.ncta;
   return 1;
 }

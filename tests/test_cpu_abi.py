@@ -83,13 +83,13 @@ def test_slab_plan_diagnostic_needs_no_gpu():
         d.pd, d.ph, d.pw = pf
         d.in_ld, d.out_ld = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
         d.dtype, d.flags = _lib.IVF_BF16, flags
-        out = (C.c_int * 11)()
+        out = (C.c_int * 12)()
         return lib.ivf_conv_slab_plan(C.byref(d), 148, out), list(out)
 
     for args in [((8, 112, 112), 24, 64, (4, 4, 4), (1, 1, 1)), ((8, 112, 112), 64, 24, (4, 4, 4), (2, 2, 2), 8),
                  ((8, 56, 56), 64, 192, (3, 3, 3), (1, 1, 1)), ((8, 28, 28), 96, 128, (3, 3, 3), (1, 1, 1)),
                  ((8, 28, 28), 32, 16, (3, 3, 3), (1, 1, 1), 12)]:
-        ok, (kch, bn, ntiles, mt, th, acc, a_st, b_st, tiles, smem, kwm) = plan(*args)
+        ok, (kch, bn, ntiles, mt, th, acc, a_st, b_st, tiles, smem, kwm, ncta) = plan(*args)
         assert ok == 1, args
         assert kch in (32, 64) and bn % 16 == 0 and bn * ntiles >= args[2]
         assert 1 <= mt <= 4 and acc in (1, 2) and a_st >= 2 and b_st >= 2 and tiles > 0
