@@ -96,7 +96,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[256], s_shift[256], s_mscale[256];
-  __shared__ float xch[2][4][3][3][16];  // kw-merge: [parity][quarter slot][g-1][row][column] boundary rows
+  __shared__ float xch[4][576];  // kw-merge boundary rows: [quarter slot][((g-1)*(kwm-1) + row)*bn + column]
 
   constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
   constexpr uint32_t ROW16 = ROWB / 16;          // the same in descriptor (16-byte) units
@@ -337,7 +337,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.mask_y = mask_y;
     ea.out = out;
     int it = 0;
-    uint32_t xpar = 0;  // exchange-buffer parity (kw-merge)
     for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
       const TileCoord t = decode_tile(p, tile, NCTA, rank);
       const int acc = p.acc_stages == 2 ? (it & 1) : 0;
@@ -367,37 +366,42 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             cur = nxt;
           }
         } else {
-          // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down
-          const int kwm = p.kwm;
+          // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  Rows v+g of the
+          // next 32-row quarter (or of the next accumulator, served by quarter 0) come through shared memory:
+          // published once per accumulator for all columns (two block barriers per accumulator instead of one
+          // per 16-column chunk), the rest by warp shuffles.
+          const int kwm = p.kwm, bn = p.bn;
           const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
-          for (int c0 = 0; c0 < p.bn; c0 += 16, ++xpar) {
-            if (c0 + 16 < p.bn) epilogue_prefetch(ea, t.nt * p.bn + c0 + 16, out_row, mask_row, ok, nxt);
-            uint32_t tg[4][16];
-            uint32_t nx[3][16];
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g < kwm) tmem_ld16_nowait(taddr + g * p.bn + c0, tg[g]);
-            if (next_blk) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // readers of the previous accumulator are done
+          if (q > 0 || next_blk) {
+            float* xw = xch[q > 0 ? q - 1 : 3];
+            const uint32_t src_addr = q > 0 ? taddr : taddr + (uint32_t)p.slot;
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+              uint32_t bt[3][16];
 #pragma unroll
               for (int g = 1; g < 4; ++g)
-                if (g < kwm) tmem_ld16_nowait(taddr + p.slot + g * p.bn + c0, nx[g - 1]);
-            }
-            tmem_ld_wait();
-            float(*xb)[3][3][16] = xch[xpar & 1];
-            if (lane < kwm - 1) {
+                if (g < kwm) tmem_ld16_nowait(src_addr + g * bn + c0, bt[g - 1]);
+              tmem_ld_wait();
+              if (lane < kwm - 1) {
 #pragma unroll
-              for (int g = 1; g < 4; ++g) {
-                if (g >= kwm) break;
-                if (q > 0) {
+                for (int g = 1; g < 4; ++g) {
+                  if (g >= kwm) break;
+                  float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) xb[q - 1][g - 1][lane][j] = __uint_as_float(tg[g][j]);
-                } else if (next_blk) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) xb[3][g - 1][lane][j] = __uint_as_float(nx[g - 1][j]);
+                  for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[g - 1][j]);
                 }
               }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // boundary rows visible
+          const float* xr = xch[q];
+          for (int c0 = 0; c0 < bn; c0 += 16) {
+            if (c0 + 16 < bn) epilogue_prefetch(ea, t.nt * bn + c0 + 16, out_row, mask_row, ok, nxt);
+            uint32_t tg[4][16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g < kwm) tmem_ld16_nowait(taddr + g * bn + c0, tg[g]);
+            tmem_ld_wait();
             float accv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[0][j]);
@@ -405,14 +409,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int g = 1; g < 4; ++g) {
               if (g >= kwm) break;
               const int src = lane + g - 32;  // >= 0: the row lives in the next quarter
+              const float* xs = xr + ((g - 1) * (kwm - 1) + (src >= 0 ? src : 0)) * bn + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[g][j]), g);
-                if (src >= 0) sv = xb[q][g - 1][src][j];
+                if (src >= 0) sv = xs[j];
                 accv[j] += sv;
               }
             }
-            const int nb = t.nt * p.bn + c0;
+            const int nb = t.nt * bn + c0;
             if (ok && nb < p.cout) {
               uint32_t rr[16];
 #pragma unroll
@@ -571,7 +576,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   }
   const int forced_mt = env_int("IVF_SLAB_MT", 0), forced_nt = env_int("IVF_SLAB_NT", 0);
   const int forced_acc = env_int("IVF_SLAB_ACC", 0), forced_kwm = env_int("IVF_SLAB_KWM", 0);
-  const bool allow_pair = env_int("IVF_SLAB_2CTA", 0) != 0 && sm_count % 2 == 0;
+  const bool allow_pair = env_int("IVF_SLAB_2CTA", 1) != 0 && sm_count % 2 == 0;
   double best_cost = 1e30;
   bool found = false;
   for (int ntiles = 1; ntiles <= 4; ++ntiles) {
