@@ -37,8 +37,6 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
 // compiler unroll them; GEN = true keeps the fully general runtime-geometry path.
 template <int KD, int KH, int KW, int SD, int SH, int SW>
 struct PoolGeo {
-  static constexpr bool is_static = true;
-  static constexpr int KHW = KH * KW;  // taps per depth slice
   __device__ static int kd(const ivf_pool_desc&) { return KD; }
   __device__ static int kh(const ivf_pool_desc&) { return KH; }
   __device__ static int kw(const ivf_pool_desc&) { return KW; }
@@ -47,8 +45,6 @@ struct PoolGeo {
   __device__ static int sw(const ivf_pool_desc&) { return SW; }
 };
 struct PoolGeoDyn {
-  static constexpr bool is_static = false;
-  static constexpr int KHW = 1;
   __device__ static int kd(const ivf_pool_desc& d) { return d.kd; }
   __device__ static int kh(const ivf_pool_desc& d) { return d.kh; }
   __device__ static int kw(const ivf_pool_desc& d) { return d.kw; }
@@ -152,79 +148,35 @@ maxpool_bwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
   float g[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = 0.f;
-  if constexpr (G::is_static) {
-    // Compile-time window: per depth tap first every window's argmax word is requested (independent
-    // loads), then the gradient rows of the windows that selected this element, then the sums - three waves
-    // of loads in flight instead of a dependent load pair per window.
-    constexpr int KHW = G::KHW;
 #pragma unroll
-    for (int a = 0; a < KD; ++a) {
-      const int nd = idd + d.pd - a;
-      if (nd < 0 || (SD > 1 && nd % SD)) continue;
-      const int od = SD > 1 ? nd / SD : nd;
-      if (od >= d.od) continue;
-      uint2 pk[KHW];
-      int opx[KHW];
+  for (int a = 0; a < KD; ++a) {
+    const int nd = idd + d.pd - a;
+    if (nd < 0 || (SD > 1 && nd % SD)) continue;
+    const int od = SD > 1 ? nd / SD : nd;
+    if (od >= d.od) continue;
 #pragma unroll
-      for (int k = 0; k < KHW; ++k) {
-        const int b = k / KW, e = k - b * KW;
-        const int nh = ih + d.ph - b, nw = iw + d.pw - e;
-        const int oh = SH > 1 ? nh / SH : nh, ow = SW > 1 ? nw / SW : nw;
-        const bool ok = nh >= 0 && !(SH > 1 && nh % SH) && oh < d.oh && nw >= 0 && !(SW > 1 && nw % SW) && ow < d.ow;
-        opx[k] = ((n * d.od + od) * d.oh + oh) * d.ow + ow;
-        pk[k] = make_uint2(0xffffffffu, 0xffffffffu);  // tap index 255 never occurs
-        if (ok) pk[k] = *reinterpret_cast<const uint2*>(argmax + (long long)opx[k] * d.c + c);
-      }
-      uint4 gy[KHW];
-      uint32_t e0[KHW], e1[KHW];
+    for (int b = 0; b < KH; ++b) {
+      const int nh = ih + d.ph - b;
+      if (nh < 0 || (SH > 1 && nh % SH)) continue;
+      const int oh = SH > 1 ? nh / SH : nh;
+      if (oh >= d.oh) continue;
+      const int orow = ((n * d.od + od) * d.oh + oh) * d.ow;
 #pragma unroll
-      for (int k = 0; k < KHW; ++k) {
-        const uint32_t tap4 = (uint32_t)(a * KHW + k) * 0x01010101u;
-        e0[k] = __vcmpeq4(pk[k].x, tap4);
-        e1[k] = __vcmpeq4(pk[k].y, tap4);
-        gy[k] = make_uint4(0u, 0u, 0u, 0u);
-        if ((e0[k] | e1[k]) != 0u)
-          gy[k] = *reinterpret_cast<const uint4*>(dy + (long long)opx[k] * d.out_ld + d.out_coff + c);
-      }
-#pragma unroll
-      for (int k = 0; k < KHW; ++k) {
-        const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&gy[k]);
+      for (int e = 0; e < KW; ++e) {
+        const int nw = iw + d.pw - e;
+        if (nw < 0 || (SW > 1 && nw % SW)) continue;
+        const int ow = SW > 1 ? nw / SW : nw;
+        if (ow >= d.ow) continue;
+        const int opix = orow + ow;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + (long long)opix * d.c + c);
+        const uint32_t tap4 = (uint32_t)((a * KH + b) * KW + e) * 0x01010101u;
+        const uint32_t e0 = __vcmpeq4(pk.x, tap4), e1 = __vcmpeq4(pk.y, tap4);
+        if ((e0 | e1) == 0u) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(dy + (long long)opix * d.out_ld + d.out_coff + c);
+        const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (((i < 4 ? e0[k] : e1[k]) >> (8 * (i & 3))) & 1u) g[i] += __bfloat162float(v[i]);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int a = 0; a < KD; ++a) {
-      const int nd = idd + d.pd - a;
-      if (nd < 0 || (SD > 1 && nd % SD)) continue;
-      const int od = SD > 1 ? nd / SD : nd;
-      if (od >= d.od) continue;
-  #pragma unroll
-      for (int b = 0; b < KH; ++b) {
-        const int nh = ih + d.ph - b;
-        if (nh < 0 || (SH > 1 && nh % SH)) continue;
-        const int oh = SH > 1 ? nh / SH : nh;
-        if (oh >= d.oh) continue;
-        const int orow = ((n * d.od + od) * d.oh + oh) * d.ow;
-  #pragma unroll
-        for (int e = 0; e < KW; ++e) {
-          const int nw = iw + d.pw - e;
-          if (nw < 0 || (SW > 1 && nw % SW)) continue;
-          const int ow = SW > 1 ? nw / SW : nw;
-          if (ow >= d.ow) continue;
-          const int opix = orow + ow;
-          const uint2 pk = *reinterpret_cast<const uint2*>(argmax + (long long)opix * d.c + c);
-          const uint32_t tap4 = (uint32_t)((a * KH + b) * KW + e) * 0x01010101u;
-          const uint32_t e0 = __vcmpeq4(pk.x, tap4), e1 = __vcmpeq4(pk.y, tap4);
-          if ((e0 | e1) == 0u) continue;
-          const uint4 raw = *reinterpret_cast<const uint4*>(dy + (long long)opix * d.out_ld + d.out_coff + c);
-          const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
-  #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (((i < 4 ? e0 : e1) >> (8 * (i & 3))) & 1u) g[i] += __bfloat162float(v[i]);
-        }
+          if (((i < 4 ? e0 : e1) >> (8 * (i & 3))) & 1u) g[i] += __bfloat162float(v[i]);
       }
     }
   }
