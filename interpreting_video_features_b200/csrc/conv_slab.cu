@@ -41,7 +41,8 @@ namespace {
 
 using namespace ivf_tc;
 
-constexpr int SLAB_THREADS = 224;
+constexpr int SLAB_THREADS = 352;  // 3 role warps + 8 epilogue warps (two per TMEM lane quarter, half the columns each)
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr uint32_t SLAB_SMEM_BUDGET = 212u * 1024u;
@@ -122,7 +123,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 4 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(&t_empty[s], 8 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,7 +144,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   if (warp >= 3) {
-    for (int i = threadIdx.x - 96; i < 256; i += 128) {
+    for (int i = threadIdx.x - 96; i < 256; i += EPI_THREADS) {
       bool ok = i < p.cout;
       s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[i] : 1.f;
       s_shift[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? shift[i] : 0.f;
@@ -329,7 +330,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int chalf = (warp - 3) >> 2;  // which half of the tile's 16-column chunks this warp handles
     EpilogueArgs ea;
     ea.cout = p.cout;
     ea.flags = p.flags;
@@ -353,12 +355,15 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const size_t mask_row = pix * p.mask_ld + p.mask_coff;
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
                                (uint32_t)((acc * p.mt + m) * p.slot);
+        // this warp's chunks: [c_lo, c_hi)
+        const int nchunks = p.bn >> 4, c_lo = ((nchunks + 1) / 2) * 16 * chalf;
+        const int c_hi = chalf == 0 ? ((nchunks + 1) / 2) * 16 : p.bn;
         EpiPre cur, nxt;
-        epilogue_prefetch(ea, t.nt * p.bn, out_row, mask_row, ok, cur);
+        epilogue_prefetch(ea, t.nt * p.bn + c_lo, out_row, mask_row, ok && c_lo < c_hi, cur);
         if (p.kwm == 1) {
-          for (int c0 = 0; c0 < p.bn; c0 += 16) {
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             const int nb = t.nt * p.bn + c0;
-            if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, ok, nxt);
+            if (c0 + 16 < c_hi) epilogue_prefetch(ea, nb + 16, out_row, mask_row, ok, nxt);
             uint32_t rr[16];
             tmem_ld16(taddr + c0, rr);
             if (ok && nb < p.cout)
@@ -372,47 +377,38 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // per 16-column chunk), the rest by warp shuffles.
           const int kwm = p.kwm, bn = p.bn;
           const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // readers of the previous accumulator are done
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // readers of the previous accumulator are done
           if (q > 0 || next_blk) {
             float* xw = xch[q > 0 ? q - 1 : 3];
             const uint32_t src_addr = q > 0 ? taddr : taddr + (uint32_t)p.slot;
-            for (int c0 = 0; c0 < bn; c0 += 16) {
-              uint32_t bt[3][16];
-#pragma unroll
-              for (int g = 1; g < 4; ++g)
-                if (g < kwm) tmem_ld16_nowait(src_addr + g * bn + c0, bt[g - 1]);
-              tmem_ld_wait();
-              if (lane < kwm - 1) {
-#pragma unroll
-                for (int g = 1; g < 4; ++g) {
-                  if (g >= kwm) break;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              for (int g = 1; g < kwm; ++g) {
+                uint32_t bt[16];
+                tmem_ld16(src_addr + g * bn + c0, bt);
+                if (lane < kwm - 1) {
                   float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[g - 1][j]);
+                  for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[j]);
                 }
               }
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // boundary rows visible
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // boundary rows visible
           const float* xr = xch[q];
-          for (int c0 = 0; c0 < bn; c0 += 16) {
-            if (c0 + 16 < bn) epilogue_prefetch(ea, t.nt * bn + c0 + 16, out_row, mask_row, ok, nxt);
-            uint32_t tg[4][16];
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g < kwm) tmem_ld16_nowait(taddr + g * bn + c0, tg[g]);
-            tmem_ld_wait();
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            if (c0 + 16 < c_hi) epilogue_prefetch(ea, t.nt * bn + c0 + 16, out_row, mask_row, ok, nxt);
+            uint32_t tg[16];
+            tmem_ld16(taddr + c0, tg);
             float accv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[0][j]);
-#pragma unroll
-            for (int g = 1; g < 4; ++g) {
-              if (g >= kwm) break;
+            for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[j]);
+            for (int g = 1; g < kwm; ++g) {
+              tmem_ld16(taddr + g * bn + c0, tg);
               const int src = lane + g - 32;  // >= 0: the row lives in the next quarter
               const float* xs = xr + ((g - 1) * (kwm - 1) + (src >= 0 ? src : 0)) * bn + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[g][j]), g);
+                float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[j]), g);
                 if (src >= 0) sv = xs[j];
                 accv[j] += sv;
               }
