@@ -45,7 +45,8 @@ constexpr int SLAB_THREADS = 352;  // 3 role warps + 8 epilogue warps (two per T
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
-constexpr uint32_t SLAB_SMEM_BUDGET = 212u * 1024u;
+constexpr uint32_t SLAB_SMEM_BUDGET = 208u * 1024u;
+constexpr int SLAB_MAX_COUT = 1024;  // per-channel epilogue vectors live in shared memory
 
 struct SlabParams {
   int n, dd, hh, ww;  // spatial extent (output == gathered tensor: stride 1, 'same')
@@ -96,7 +97,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+  // per-channel epilogue vectors: s_scale = BN scale (AFFINE) or the producer's BN' mask scale (MASK; the two
+  // are never combined on this path, the host checks), s_shift = BN shift
+  __shared__ float s_scale[SLAB_MAX_COUT], s_shift[SLAB_MAX_COUT];
   __shared__ float xch[4][576];  // kw-merge boundary rows: [quarter slot][((g-1)*(kwm-1) + row)*bn + column]
 
   constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
@@ -144,11 +147,13 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   if (warp >= 3) {
-    for (int i = threadIdx.x - 96; i < 256; i += EPI_THREADS) {
+    for (int i = threadIdx.x - 96; i < SLAB_MAX_COUT; i += EPI_THREADS) {
       bool ok = i < p.cout;
-      s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[i] : 1.f;
+      float sc = 1.f;
+      if (ok && (p.flags & IVF_EP_AFFINE)) sc = scale[i];
+      if (ok && (p.flags & IVF_EP_MASK)) sc = mask_scale[i];
+      s_scale[i] = sc;
       s_shift[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? shift[i] : 0.f;
-      s_mscale[i] = (ok && (p.flags & IVF_EP_MASK)) ? mask_scale[i] : 0.f;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -367,7 +372,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t rr[16];
             tmem_ld16(taddr + c0, rr);
             if (ok && nb < p.cout)
-              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row, cur);
+              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
             cur = nxt;
           }
         } else {
@@ -418,7 +423,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t rr[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
-              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_mscale + nb, out_row, mask_row, cur);
+              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
             }
             cur = nxt;
           }
@@ -575,10 +580,10 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   const bool allow_pair = env_int("IVF_SLAB_2CTA", 1) != 0 && sm_count % 2 == 0;
   double best_cost = 1e30;
   bool found = false;
-  for (int ntiles = 1; ntiles <= 4; ++ntiles) {
+  for (int ntiles = 1; ntiles <= 16; ++ntiles) {
     if (forced_nt && ntiles != forced_nt) continue;
     const int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
-    if (bn > 256 || ntiles * bn > 256 + 15) continue;
+    if (bn > 256 || ntiles * bn > SLAB_MAX_COUT + 15) continue;
     if (ntiles > 1 && bn < 32) continue;
     for (int ncta = 1; ncta <= 2; ++ncta) {
     if (ncta == 2 && !allow_pair) continue;
@@ -674,7 +679,7 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
   const int slot = (KCH == 64 ? 0 : 1) + 2 * (NCTA - 1);
   if (!h->slab_attr_set[slot]) {
     IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SLAB_SMEM_BUDGET + 2048)));
+                                  (int)(SLAB_SMEM_BUDGET + 1024)));
     h->slab_attr_set[slot] = true;
   }
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
@@ -705,27 +710,48 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
 
 }  // namespace
 
-bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d) {
+namespace {
+// A 1x1x1 convolution has no halo: its (clip, depth, row) axes are one long row axis, so a tile is any run
+// of th rows (full 128-row accumulators on the 14x14 and 7x7 maps too) and the kernel is a persistent GEMM
+// with the epilogue overlapped - the im2col kernel's one-tile CTAs spent most of such a launch in prologue
+// and epilogue.
+ivf_conv_desc slab_view(const ivf_conv_desc* d) {
+  ivf_conv_desc v = *d;
+  if (d->kd * d->kh * d->kw == 1) {
+    v.ih = v.oh = d->n * d->id * d->ih;
+    v.id = v.od = 1;
+    v.n = 1;
+  }
+  return v;
+}
+}  // namespace
+
+bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d0) {
+  const ivf_conv_desc dv = slab_view(d0);
+  const ivf_conv_desc* d = &dv;
   if (env_int("IVF_SLAB", 1) == 0) return false;
   if (d->dtype != IVF_BF16 || d->transposed) return false;
   if (d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
   if (d->od != d->id || d->oh != d->ih || d->ow != d->iw) return false;
-  if (d->kd * d->kh * d->kw <= 1) return false;  // 1x1x1: nothing to reuse, plain GEMM
-  if (d->kh < 2 && d->kw < 2) return false;
+  if (d->kd * d->kh * d->kw == 1 && env_int("IVF_SLAB_1X1", 1) == 0) return false;
+  if ((long long)d0->n * d0->id * d0->ih >= (1ll << 30)) return false;
   if (d->cin % 8 || d->in_ld % 8 || d->in_coff % 8 || d->out_ld % 8 || d->out_coff % 8) return false;
   if ((d->flags & IVF_EP_MASK) && (d->mask_ld % 8 || d->mask_coff % 8)) return false;
   // 'same' geometry: front pad within the kernel, the rest is the back pad
   if (d->pd < 0 || d->pd >= d->kd || d->ph < 0 || d->ph >= d->kh || d->pw < 0 || d->pw >= d->kw) return false;
-  if (d->iw < env_int("IVF_SLAB_MIN_W", 24)) return false;  // narrow maps waste the padded-width tile
+  if (d->iw < env_int("IVF_SLAB_MIN_W", 7)) return false;  // very narrow maps waste the padded-width tile
   if (d->iw + d->kw - 1 > 256) return false;
-  if (d->cout > 256) return false;
+  if (d->cout > SLAB_MAX_COUT) return false;
+  if ((d->flags & IVF_EP_AFFINE) && (d->flags & IVF_EP_MASK)) return false;  // one shared scale vector
   SlabParams p;
   return slab_config(d, h->sm_count, &p);
 }
 
-int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
+int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* in, const void* w,
                            const float* scale, const float* shift, const float* acc_in,
                            const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
+  const ivf_conv_desc dv = slab_view(d0);
+  const ivf_conv_desc* d = &dv;
   int rc = ivf_load_driver_entry_points();
   if (rc) return rc;
   SlabParams p;
@@ -772,6 +798,8 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   ivf_handle fake;
   fake.sm_count = sm_count;
   if (!ivf_conv3d_slab_eligible(&fake, d)) return 0;
+  const ivf_conv_desc dv = slab_view(d);
+  d = &dv;
   SlabParams p;
   if (!slab_config(d, sm_count, &p)) return 0;
   plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
