@@ -713,8 +713,10 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
 namespace {
 // A 1x1x1 convolution has no halo: its (clip, depth, row) axes are one long row axis, so a tile is any run
 // of th rows (full 128-row accumulators on the 14x14 and 7x7 maps too) and the kernel is a persistent GEMM
-// with the epilogue overlapped - the im2col kernel's one-tile CTAs spent most of such a launch in prologue
-// and epilogue.
+// with the epilogue overlapped.  Measured (round 1): per launch it ties with the im2col kernel's one-tile
+// CTAs (1.09 vs 1.11 ms per step over the 64 1x1x1 launches) but a persistent 148-CTA kernel with ~200 KB of
+// shared memory cannot share the SMs with the launches of the other Inception branches, and the step got
+// slower (3.18 vs 3.08 ms) - so this route is opt-in (IVF_SLAB_1X1=1).
 ivf_conv_desc slab_view(const ivf_conv_desc* d) {
   ivf_conv_desc v = *d;
   if (d->kd * d->kh * d->kw == 1) {
@@ -733,7 +735,7 @@ bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d0) {
   if (d->dtype != IVF_BF16 || d->transposed) return false;
   if (d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
   if (d->od != d->id || d->oh != d->ih || d->ow != d->iw) return false;
-  if (d->kd * d->kh * d->kw == 1 && env_int("IVF_SLAB_1X1", 1) == 0) return false;
+  if (d->kd * d->kh * d->kw == 1 && env_int("IVF_SLAB_1X1", 0) == 0) return false;
   if ((long long)d0->n * d0->id * d0->ih >= (1ll << 30)) return false;
   if (d->cin % 8 || d->in_ld % 8 || d->in_coff % 8 || d->out_ld % 8 || d->out_coff % 8) return false;
   if ((d->flags & IVF_EP_MASK) && (d->mask_ld % 8 || d->mask_coff % 8)) return false;

@@ -98,6 +98,6 @@ def test_slab_plan_diagnostic_needs_no_gpu():
         assert smem <= 208 * 1024                                       # dynamic shared memory budget
         assert th * (args[0][2] + args[3][2] - 1) <= mt * 128           # the tile's padded-width pixels fit
     assert plan((4, 14, 14), 96, 208, (3, 3, 3), (1, 1, 1))[0] == 1      # 14x14 stage
-    assert plan((8, 56, 56), 64, 64, (1, 1, 1), (0, 0, 0))[0] == 1       # 1x1x1: persistent GEMM over flat rows
-    assert plan((2, 7, 7), 240, 832, (1, 1, 1), (0, 0, 0), 12)[0] == 1   # wide data gradient: 4+ N tiles
+    assert plan((8, 56, 56), 64, 64, (1, 1, 1), (0, 0, 0))[0] == 0       # 1x1x1 -> im2col kernel (slab route opt-in)
+    assert plan((2, 7, 7), 256, 832, (3, 3, 3), (1, 1, 1), 12)[0] == 1   # wide data gradient: 4+ N tiles
     assert plan((2, 4, 4), 64, 64, (3, 3, 3), (1, 1, 1))[0] == 0         # map narrower than 7 -> im2col kernel
