@@ -148,25 +148,25 @@ maxpool_bwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
   float g[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = 0.f;
+  // The kernel is issue bound (ncu: 72-78 % issue-slot utilisation, DRAM at 20 %), so only the windows that
+  // can contain this element are visited: along a dimension of stride S these are the taps congruent to
+  // (x + pad) mod S - ceil(K/S) of them instead of K (4 of 9 for the 1x3x3 stride-2 pools, 8 of 27 for 3x3x3
+  // stride 2, 1 of 8 for 2x2x2 stride 2), with no divisibility test left inside the loop.
+  const int pd0 = (idd + d.pd) % SD, ph0 = (ih + d.ph) % SH, pw0 = (iw + d.pw) % SW;
+  const int qd = (idd + d.pd) / SD, qh = (ih + d.ph) / SH, qw = (iw + d.pw) / SW;  // window of tap == remainder
 #pragma unroll
-  for (int a = 0; a < KD; ++a) {
-    const int nd = idd + d.pd - a;
-    if (nd < 0 || (SD > 1 && nd % SD)) continue;
-    const int od = SD > 1 ? nd / SD : nd;
-    if (od >= d.od) continue;
+  for (int ja = 0; ja * SD < KD; ++ja) {
+    const int a = pd0 + ja * SD, od = qd - ja;
+    if (a >= KD || od < 0 || od >= d.od) continue;
 #pragma unroll
-    for (int b = 0; b < KH; ++b) {
-      const int nh = ih + d.ph - b;
-      if (nh < 0 || (SH > 1 && nh % SH)) continue;
-      const int oh = SH > 1 ? nh / SH : nh;
-      if (oh >= d.oh) continue;
+    for (int jb = 0; jb * SH < KH; ++jb) {
+      const int b = ph0 + jb * SH, oh = qh - jb;
+      if (b >= KH || oh < 0 || oh >= d.oh) continue;
       const int orow = ((n * d.od + od) * d.oh + oh) * d.ow;
 #pragma unroll
-      for (int e = 0; e < KW; ++e) {
-        const int nw = iw + d.pw - e;
-        if (nw < 0 || (SW > 1 && nw % SW)) continue;
-        const int ow = SW > 1 ? nw / SW : nw;
-        if (ow >= d.ow) continue;
+      for (int je = 0; je * SW < KW; ++je) {
+        const int e = pw0 + je * SW, ow = qw - je;
+        if (e >= KW || ow < 0 || ow >= d.ow) continue;
         const int opix = orow + ow;
         const uint2 pk = *reinterpret_cast<const uint2*>(argmax + (long long)opix * d.c + c);
         const uint32_t tap4 = (uint32_t)((a * KH + b) * KW + e) * 0x01010101u;
