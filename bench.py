@@ -264,10 +264,16 @@ def run_ours(args, rank, world, local_rank):
     flops_step = 2.0 * conv_flops * CLIPS  # forward + data gradient, no weight gradient
     achieved = flops_step / conv_s / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) if args.mode == "bf16" else None
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all launches of a step)",
+    traffic, traffic_src = None, None
+    tp = os.path.join(REPO, "profiles", "r01_step_metrics.json")
+    if os.path.exists(tp) and args.mode == "bf16":  # DRAM bytes of the conv launches of one step (ncu, committed)
+        traffic = json.load(open(tp))["families"]["conv"]["dram_bytes"]
+        traffic_src = "profiles/r01_step_metrics.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the " \
+                      "conv launches of one step (8 clips), one ncu capture"
+    roofline = {"bound": "tensor", "kernel": "conv_slab_kernel + conv_tc_kernel (tcgen05 implicit GEMMs, all conv launches of a step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if peak else None, "peak_source": pk_src + " (sustained bf16 GEMM)",
-                "traffic": None, "conv_launches_per_step": conv_launches, "conv_ms_per_step": conv_s * 1e3,
+                "traffic": traffic, "traffic_source": traffic_src, "conv_launches_per_step": conv_launches, "conv_ms_per_step": conv_s * 1e3,
                 "algorithmic_gflop_per_clip_iteration": 2.0 * conv_flops / 1e9,
                 "conv_share_of_step": conv_s / (elapsed / args.steps)}
 
