@@ -333,8 +333,8 @@ class I3DEngine:
         u, x, dz = st["units"], st["x"], st["gout"]
         c0, c2, c4, c5 = u["b0"].cout, u["b1b"].cout, u["b2b"].cout, u["b3b"].cout
         # Four lanes: the two 3x3x3 branch tails (ReLU'/BN' of b1a/b2a fused, written side by side into
-        # g_t12), and the pool branch: b3b' -> b0' (starts the fp32 sum over x's consumers) -> pool' added in
-        # place.  After the join ONE data-gradient GEMM over the concatenated K of the two bottlenecks adds
+        # g_t12), b0' (starts the fp32 sum over x's consumers) and the pool branch b3b' -> pool' (added in
+        # place once b0' is done).  After the join ONE data-gradient GEMM over the concatenated K of the two bottlenecks adds
         # the sum and applies the producer's ReLU'/BN'.  (Summation order per element is fixed: b0, pool, GEMM.)
         acc = st["g_x32"]
         self.bwd_ops.append(("fork",))
@@ -344,10 +344,11 @@ class I3DEngine:
         add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
         self._lane = 3
         add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
+        self._lane = 0
         add_unit_bwd(u["b0"], dz.slice(0, c0), x, acc)
+        self.bwd_ops.append(("sync", 0, 3))  # pool' adds into the sum b0' started
         self.bwd_ops.append((3, lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], acc, (3, 3, 3), (1, 1, 1),
                                                           st["pads"], acc_in=acc)))
-        self._lane = 0
         self.bwd_ops.append(("join",))
         add_unit_bwd(st["fused"], st["g_t12"], x, g_in, acc_in=acc, mask=mask, mask_scale=mscale)
 
@@ -375,6 +376,11 @@ class I3DEngine:
                 for i, sd in enumerate(self._side):
                     if len(item) == 1 or (i + 1) in item[1]:
                         sd.wait_event(ev)
+            elif item[0] == "sync":  # ("sync", src lane, dst lane): dst waits for src's work so far
+                lanes = [main] + self._side
+                ev = torch.cuda.Event()
+                ev.record(lanes[item[1]])
+                lanes[item[2]].wait_event(ev)
             elif item[0] == "join":
                 for sd in self._side:
                     main.wait_stream(sd)
