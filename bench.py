@@ -171,6 +171,10 @@ def conv_time_per_step(eng):
     ops.conv3d = timed
     streams, eng.use_streams = eng.use_streams, False  # serialised: one kernel at a time on one stream
     try:
+        # hold the stream for ~60 ms so that every launch and event of the iteration is already queued when
+        # the GPU starts: the event pairs then bracket kernel time, not the host's launch latency
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.06 * 1.9e9))
         eng.forward(eng._mask, eng._perturb)
         eng.backward(to_mask=True)
         torch.cuda.synchronize()
