@@ -317,12 +317,14 @@ class I3DBase(nn.Module):
     def _version(self):
         return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
 
-    def _engine(self, x, batch=None):
+    def _engine(self, x, batch=None, tag=0):
+        """The native runner for this geometry (cached).  `tag` distinguishes several engines of the same
+        geometry that are alive together (clip groups of the batched mask search)."""
         b, c, t, h, w = x.shape
         device = next(self.parameters()).device  # the model's GPU; x may still be on the host
         if device.type != "cuda":
             raise _lib.IvfError("the native I3D needs the model on a CUDA device (model.cuda())")
-        key = (batch or b, c, t, h, w, self.ivf_mode, str(device))
+        key = (batch or b, c, t, h, w, self.ivf_mode, str(device), tag)
         ver = self._version()
         hit = self._engines.get(key)
         if hit is None or hit[0] != ver:
@@ -335,7 +337,9 @@ class I3DBase(nn.Module):
                             avg_pool=tuple(self.avg_pool.kernel_size), stride_mods=self._stride_mods,
                             device=device, in_channels=c)
             hit = (ver, eng)
-            self._engines = {key: hit}  # one geometry at a time: activations are large
+            # one geometry at a time (activations are large): drop engines of other geometries / older weights
+            self._engines = {k: v for k, v in self._engines.items() if k[:-1] == key[:-1] and v[0] == ver}
+            self._engines[key] = hit
         return hit[1]
 
     def set_mode(self, mode):

@@ -21,14 +21,26 @@ from . import _lib, ops
 
 
 class MaskSearch:
-    """Mask search over micro-batches of `engine.B` clips on one GPU."""
+    """Mask search over micro-batches of clips on one GPU.
+
+    `engine` is one runner for the whole micro-batch, or a list of runners over consecutive clip groups
+    (their batch sizes add up to the micro-batch).  Groups are independent (each clip owns its mask), so
+    their iterations are issued on separate streams and captured as parallel branches of ONE CUDA graph: the
+    small-grid kernels of one group (7x7 / 14x14 stages, head, loss) fill SMs the other group leaves idle."""
 
     def __init__(self, engine, lam1=0.01, lam2=0.02, lr=0.2, n_iter=300, perturb="freeze", threshold=0.9,
                  use_graph=True):
-        self.eng = engine
+        self.engs = list(engine) if isinstance(engine, (list, tuple)) else [engine]
+        self.eng = self.engs[0]
         self.lam1, self.lam2, self.lr, self.n_iter = float(lam1), float(lam2), float(lr), int(n_iter)
         self.perturb, self.threshold, self.use_graph = perturb, float(threshold), use_graph
-        B, T, dev = engine.B, engine.T, engine.device
+        self.B = sum(e.B for e in self.engs)
+        self.T, self.device = self.eng.T, self.eng.device
+        self.slices, off = [], 0
+        for e in self.engs:
+            self.slices.append(slice(off, off + e.B))
+            off += e.B
+        B, T, dev = self.B, self.T, self.device
         self.m = torch.zeros((B, T), dtype=torch.float32, device=dev)        # raw mask (Adam parameter)
         self.sig = torch.zeros((B, T), dtype=torch.float32, device=dev)      # sigmoid(m)
         self.exp_avg = torch.zeros_like(self.m)
@@ -37,24 +49,63 @@ class MaskSearch:
         self.losses = torch.zeros((B, 3), dtype=torch.float32, device=dev)
         self.graph = None
         self.launches_per_iter = None
+        self._gstreams = None
+
+    # ---- the clip groups behind one interface
+    def set_input(self, x):
+        for e, sl in zip(self.engs, self.slices):
+            e.set_input(x[sl])
+
+    def set_targets(self, tg):
+        for e, sl in zip(self.engs, self.slices):
+            e.set_targets(tg[sl])
+
+    def forward(self, mask, perturb):
+        """mask: None, [T] (shared) or [B,T]; returns a COPY of the [B, classes] outputs."""
+        outs = []
+        for e, sl in zip(self.engs, self.slices):
+            mg = mask if (mask is None or mask.dim() == 1) else mask[sl]
+            outs.append(e.forward(mg, perturb))
+        return torch.cat(outs) if len(outs) > 1 else outs[0].clone()
+
+    def probs(self):
+        return torch.cat([e.probs for e in self.engs]) if len(self.engs) > 1 else self.eng.probs
+
+    def dm(self):
+        return torch.cat([e.dm for e in self.engs]) if len(self.engs) > 1 else self.eng.dm
+
+    def _group_iteration(self, e, sl):
+        e.forward(self.sig[sl], self.perturb)
+        dm = e.backward(to_mask=True)
+        ops.mask_loss_adam(self.m[sl], self.exp_avg[sl], self.exp_avg_sq[sl], dm, 0, self.lam1, self.lam2, self.lr,
+                           losses=self.losses[sl], sig_out=self.sig[sl], step_dev=self.step[sl])
 
     # one iteration on the static buffers (what the graph captures)
     def _iteration(self):
-        eng = self.eng
-        eng.forward(self.sig, self.perturb)
-        dm = eng.backward(to_mask=True)
-        ops.mask_loss_adam(self.m, self.exp_avg, self.exp_avg_sq, dm, 0, self.lam1, self.lam2, self.lr,
-                           losses=self.losses, sig_out=self.sig, step_dev=self.step)
+        if len(self.engs) == 1:
+            self._group_iteration(self.eng, self.slices[0])
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._gstreams is None:
+            self._gstreams = [torch.cuda.Stream(device=self.device) for _ in self.engs]
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for e, sl, gs in zip(self.engs, self.slices, self._gstreams):
+            gs.wait_event(ev)
+            with torch.cuda.stream(gs):
+                self._group_iteration(e, sl)
+        for gs in self._gstreams:
+            main.wait_stream(gs)
 
     def _capture(self):
-        s = torch.cuda.Stream(device=self.eng.device)
+        s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):  # warm-up outside capture (first-use attribute calls, tensor maps)
-            n0 = _lib.launch_count(self.eng.device)
+            n0 = _lib.launch_count(self.device)
             self._iteration()
-            self.launches_per_iter = _lib.launch_count(self.eng.device) - n0
+            self.launches_per_iter = _lib.launch_count(self.device) - n0
         torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize(self.eng.device)
+        torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._iteration()
@@ -62,11 +113,10 @@ class MaskSearch:
 
     def init_masks(self, targets, mode="central", generator=None):
         """Batched pt/mask.py:103-169; returns raw masks [B,T] on the device and the unperturbed probs."""
-        eng = self.eng
-        B, T, dev = eng.B, eng.T, eng.device
+        B, T, dev = self.B, self.T, self.device
         idx = torch.arange(B, device=dev)
         tg = targets.to(dev).long()
-        probs_orig = eng.forward(None, "freeze").clone()
+        probs_orig = self.forward(None, "freeze")
         if mode == "random":
             m = (torch.rand((B, T), generator=generator) > 0.7).float()
             m = (m - 0.5) * 5
@@ -82,7 +132,7 @@ class MaskSearch:
             cand.append(c)
         scores = [probs_orig[idx, tg]]
         for c in cand:
-            scores.append(eng.forward(c.to(dev), self.perturb if c is not cand[0] else "freeze")[idx, tg].clone())
+            scores.append(self.forward(c.to(dev), self.perturb if c is not cand[0] else "freeze")[idx, tg])
         sc = torch.stack(scores).cpu().numpy()  # [2 + ncand, B]; the one host read-back of init
         orig, frozen, cen = sc[0], sc[1], sc[2:]
         raw = np.empty((B, T), dtype=np.float32)
@@ -99,17 +149,16 @@ class MaskSearch:
 
     def run(self, x, targets, init="central", raw_masks=None, n_iter=None, record=None):
         """x fp32 [B,3,T,H,W] on the device; targets [B].  Returns a dict of device tensors."""
-        eng = self.eng
         n_iter = self.n_iter if n_iter is None else n_iter
-        dev = eng.device
-        idx = torch.arange(eng.B, device=dev)
+        dev = self.device
+        idx = torch.arange(self.B, device=dev)
         tg = targets.to(dev).long()
-        eng.set_input(x)
-        eng.set_targets(tg)
+        self.set_input(x)
+        self.set_targets(tg)
         if raw_masks is None:
             raw_masks, probs_orig = self.init_masks(tg, init)
         else:
-            probs_orig = eng.forward(None, "freeze").clone()
+            probs_orig = self.forward(None, "freeze")
         self.m.copy_(raw_masks)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
@@ -126,13 +175,13 @@ class MaskSearch:
             else:
                 self._iteration()
             if record is not None:
-                record.setdefault("class", []).append(eng.probs[idx, tg].clone())
-                record.setdefault("dm_class", []).append(eng.dm.clone())
+                record.setdefault("class", []).append(self.probs()[idx, tg].clone())
+                record.setdefault("dm_class", []).append(self.dm().clone())
                 record.setdefault("loss_reg", []).append(self.losses[:, 2].clone())
                 record.setdefault("mask", []).append(self.m.clone())
-        freeze_score = eng.probs[idx, tg].clone() if n_iter > 0 else probs_orig[idx, tg]
+        freeze_score = self.probs()[idx, tg].clone() if n_iter > 0 else probs_orig[idx, tg]
         final = self.sig.clone()
-        reverse_score = eng.forward(final, "reverse")[idx, tg].clone()
+        reverse_score = self.forward(final, "reverse")[idx, tg]
         return dict(time_mask=final, raw_mask=self.m.clone(), freeze_score=freeze_score,
                     reverse_score=reverse_score, probs_orig=probs_orig, init_mask=raw_masks)
 
@@ -163,9 +212,28 @@ def gather_rows(local_rows, local_idx, n_total, world, group=None):
     return out
 
 
+def default_groups(micro_batch):
+    """Clip groups per micro-batch: IVF_GROUPS, else 2 when the micro-batch splits evenly into groups of >= 2."""
+    import os
+    g = int(os.environ.get("IVF_GROUPS", "0"))
+    if g <= 0:
+        g = 2 if (micro_batch % 2 == 0 and micro_batch >= 4) else 1
+    while micro_batch % g:
+        g -= 1
+    return max(g, 1)
+
+
+def make_engines(model, x, micro_batch, groups):
+    """`groups` runners of micro_batch/groups clips each (one runner when groups == 1)."""
+    if groups <= 1:
+        return [model._engine(x, batch=micro_batch)]
+    per = micro_batch // groups
+    return [model._engine(x, batch=per, tag=g) for g in range(groups)]
+
+
 def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, perturb="freeze",
                        init="central", threshold=0.9, micro_batch=8, lr=0.2, use_graph=True, rank=0, world=1,
-                       device=None):
+                       device=None, groups=None):
     """Mask search over `clips` [N,3,T,H,W] (host or device) for this rank's shard; returns a dict of
     [N, ...] tensors (gathered over ranks when torch.distributed is initialised and world > 1).
     `model` is a drop-in models.I3D_doubled[_kth].Model in eval mode."""
@@ -182,8 +250,8 @@ def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, 
         x = clips[sel].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
         tg = targets[sel]
         if searcher is None:
-            eng = model._engine(x, batch=micro_batch)
-            searcher = MaskSearch(eng, lam1, lam2, lr, n_iter, perturb, threshold, use_graph)
+            engs = make_engines(model, x, micro_batch, default_groups(micro_batch) if groups is None else groups)
+            searcher = MaskSearch(engs, lam1, lam2, lr, n_iter, perturb, threshold, use_graph)
         res = searcher.run(x, tg, init=init)
         row = torch.cat([res["time_mask"], res["freeze_score"][:, None], res["reverse_score"][:, None],
                          res["probs_orig"]], dim=1)[:n_valid]

@@ -496,3 +496,20 @@ def test_sharded_search_equals_single(dev, small_setup):
     for r in (0, 1):
         merged[search.shard_indices(5, r, 2)] = parts[r]["time_mask"]
     torch.testing.assert_close(merged, full["time_mask"], rtol=1e-5, atol=1e-6)
+
+
+def test_clip_groups_equal_single_group(dev, small_setup):
+    """Two clip groups on parallel graph branches == one group (clips are independent)."""
+    from interpreting_video_features_b200 import search
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    _, sds, x, _ = small_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sds)
+    model = model.to(dev).eval()
+    model.avg_pool.kernel_size = [2, 2, 2]
+    clips = torch.cat([x, x.flip(0)])[:4]
+    targets = torch.tensor([3, 40, 3, 40])
+    one = search.find_masks_batched(model, clips, targets, n_iter=6, micro_batch=4, groups=1)
+    two = search.find_masks_batched(model, clips, targets, n_iter=6, micro_batch=4, groups=2)
+    torch.testing.assert_close(two["time_mask"], one["time_mask"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(two["reverse_score"], one["reverse_score"], rtol=1e-4, atol=1e-7)

@@ -18,10 +18,10 @@ clips_n = int(os.environ.get("IVF_PROFILE_CLIPS", CLIPS))
 dev = torch.device("cuda:0")
 model = state_dict().to(dev).eval().set_mode("bf16")
 clips = torch.stack([synthetic.uniform_clip(i) for i in range(clips_n)])
-eng = model._engine(clips, batch=clips_n)
-ms = search.MaskSearch(eng, use_graph=False)
-eng.set_input(clips.to(dev))
-eng.set_targets(torch.arange(clips_n) % NCLS)
+groups = int(os.environ.get("IVF_PROFILE_GROUPS", "1"))  # serialised launch list: one group by default
+ms = search.MaskSearch(search.make_engines(model, clips, clips_n, groups), use_graph=False)
+ms.set_input(clips.to(dev))
+ms.set_targets((torch.arange(clips_n) % NCLS).to(dev))
 ms.m.copy_(torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, device=dev).repeat(clips_n, 1))
 ops.sigmoid(ms.m, ms.sig)
 for _ in range(2):
