@@ -38,7 +38,6 @@ METRIC, UNIT = "mask_search_clip_iterations_per_sec", "clip-iterations/s"
 CONFIG = {"workload": "C2: I3D smth (174 classes) temporal-mask search, freeze, batch 8 x 3x16x224x224 "
                       "synthetic clips, lam 0.01/0.02, Adam lr 0.2; one step = one iteration for the 8 clips",
           "clips_per_gpu": CLIPS, "clip": [3, T, H, W], "iterations_per_search": N_ITER,
-          "clip_groups": "the 8 clips of a step run as independent groups on parallel graph branches (IVF_GROUPS, default 2)",
           "l2": "per-step working set (~1.5 GB of activations for 8 clips) exceeds the 126 MB L2"}
 
 
