@@ -89,6 +89,11 @@ typedef struct ivf_conv_desc {
   int32_t mask_ld, mask_coff;
   int32_t flags;         /* IVF_EP_*                                             */
   int32_t dtype;         /* IVF_F32 | IVF_BF16                                   */
+  /* Tile-plan request for the halo-slab kernel, 0 = let the cost model decide: kw taps merged into N,
+   * accumulators per tile, TMEM stages (1|2), CTAs per work item (1|2), N tiles.  A request the layer cannot
+   * satisfy falls back to the model.  The host side measures a few plans per layer shape once and passes
+   * the fastest (interpreting_video_features_b200/tune.py). */
+  int32_t plan_kwm, plan_mt, plan_acc, plan_ncta, plan_ntiles;
 } ivf_conv_desc;
 
 int ivf_conv_bf16_kchunk(int cin);   /* channels per K stage: 16, 32 or 64 */

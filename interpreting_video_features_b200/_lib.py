@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n", "id", "ih", "iw", "od", "oh", "ow", "cin", "cout", "kd", "kh", "kw", "sd", "sh", "sw",
         "pd", "ph", "pw", "transposed", "in_ld", "in_coff", "out_ld", "out_coff", "mask_ld",
-        "mask_coff", "flags", "dtype")]
+        "mask_coff", "flags", "dtype", "plan_kwm", "plan_mt", "plan_acc", "plan_ncta", "plan_ntiles")]
 
 
 class PoolDesc(C.Structure):

@@ -562,7 +562,17 @@ int env_int(const char* name, int dflt) {
 //   l2    = (slab bytes read + weight bytes) / 40      (B/clk/SM with all 148 SMs pulling = the LTS cap; a slab
 //           pixel costs at least 128 B: the 48-byte rows of the 24-channel stem operand move at that rate)
 // the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
+bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best);
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
+  if (slab_config_impl(d, sm_count, best)) return true;
+  if (d->plan_kwm | d->plan_mt | d->plan_acc | d->plan_ncta | d->plan_ntiles) {  // unsatisfiable request
+    ivf_conv_desc auto_d = *d;
+    auto_d.plan_kwm = auto_d.plan_mt = auto_d.plan_acc = auto_d.plan_ncta = auto_d.plan_ntiles = 0;
+    return slab_config_impl(&auto_d, sm_count, best);
+  }
+  return false;
+}
+bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
   const int cout = d->cout, cin = d->cin;
   const int kch = cin <= 32 ? 32 : 64;
@@ -575,8 +585,12 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     int crem = cin - cc * kch;
     ksteps_total += crem >= kch ? kch / 16 : (crem + 15) / 16;
   }
-  const int forced_mt = env_int("IVF_SLAB_MT", 0), forced_nt = env_int("IVF_SLAB_NT", 0);
-  const int forced_acc = env_int("IVF_SLAB_ACC", 0), forced_kwm = env_int("IVF_SLAB_KWM", 0);
+  // requests: the descriptor's plan fields (host-side tuner), else the environment (diagnostics), else none
+  const int forced_mt = d->plan_mt ? d->plan_mt : env_int("IVF_SLAB_MT", 0);
+  const int forced_nt = d->plan_ntiles ? d->plan_ntiles : env_int("IVF_SLAB_NT", 0);
+  const int forced_acc = d->plan_acc ? d->plan_acc : env_int("IVF_SLAB_ACC", 0);
+  const int forced_kwm = d->plan_kwm ? d->plan_kwm : env_int("IVF_SLAB_KWM", 0);
+  const int forced_ncta = d->plan_ncta;
   const bool allow_pair = env_int("IVF_SLAB_2CTA", 1) != 0 && sm_count % 2 == 0;
   double best_cost = 1e30;
   bool found = false;
@@ -587,6 +601,7 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     if (ntiles > 1 && bn < 32) continue;
     for (int ncta = 1; ncta <= 2; ++ncta) {
     if (ncta == 2 && !allow_pair) continue;
+    if (forced_ncta && ncta != forced_ncta) continue;
     for (int kwm = 1; kwm <= 4 && kwm <= d->kw; ++kwm) {
     if (d->kw % kwm || kwm * bn > 256) continue;
     if (ncta == 2 && kwm == 3) continue;  // the pair splits the stacked N rows in halves: whole taps or half a tap

@@ -25,7 +25,7 @@ import os
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, tune
 from ._lib import PFMT_NDHWC_F32, PFMT_S2D_BF16
 from .ops import Act, same_pad
 
@@ -90,6 +90,28 @@ def pack_dgrad(w, mode):
     if mode == "fp32":
         return w.permute(2, 3, 4, 0, 1).reshape(-1, ci).contiguous().float()
     return _pack_bf16(w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, -1, co))
+
+
+class ConvOp:
+    """One convolution launch of a program, kept as data so that its tile plan can be measured (tune.py)."""
+
+    def __init__(self, x, w, out, kernel, stride, pf, **kw):
+        self.x, self.w, self.out, self.kernel, self.stride, self.pf, self.kw = x, w, out, kernel, stride, pf, kw
+        self.plan = None
+
+    def desc(self, plan=None):
+        kw = self.kw
+        return ops.conv_desc(self.x, self.out, self.kernel, self.stride, self.pf, kw.get("flags", 0), kw.get("scale"),
+                             kw.get("acc_in"), kw.get("mask"), kw.get("transposed", 0), plan=plan)
+
+    def launch(self, plan):
+        ops.conv3d(self.x, self.w, self.out, self.kernel, self.stride, self.pf, plan=plan, **self.kw)
+
+    def __call__(self):
+        self.launch(self.plan)
+
+    def tune(self, device):
+        self.plan = tune.best_plan(self.desc, self.launch, device)
 
 
 class Unit:
@@ -175,9 +197,8 @@ class I3DEngine:
             else:
                 pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in zip((x.d, x.h, x.w), unit.kernel, unit.stride))
                 xa = x
-            self.fwd_ops.append((self._lane, lambda: ops.conv3d(xa, unit.w_fwd, out, unit.kernel_eff, unit.stride_eff,
-                                                                pf, flags=_lib.EP_RELU, scale=unit.scale,
-                                                                shift=unit.shift)))
+            self.fwd_ops.append((self._lane, ConvOp(xa, unit.w_fwd, out, unit.kernel_eff, unit.stride_eff, pf,
+                                                    flags=_lib.EP_RELU, scale=unit.scale, shift=unit.shift)))
 
         def add_unit_bwd(unit, dz_out, x_shape_act, g_in, acc_in=None, mask=None, mask_scale=None,
                          xin_is_s2d=False):
@@ -185,9 +206,9 @@ class I3DEngine:
             if self.mode == "fp32":
                 pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in
                            zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel, unit.stride))
-                self.bwd_ops.append((self._lane, lambda: ops.conv3d(dz_out, unit.w_dgrad, g_in, unit.kernel,
-                                                                    unit.stride, pf, acc_in=acc_in, mask=mask,
-                                                                    mask_scale=mask_scale, transposed=1)))
+                self.bwd_ops.append((self._lane, ConvOp(dz_out, unit.w_dgrad, g_in, unit.kernel, unit.stride, pf,
+                                                        acc_in=acc_in, mask=mask, mask_scale=mask_scale,
+                                                        transposed=1)))
             else:
                 if xin_is_s2d:
                     pf = tuple(k - 1 - 1 for k in unit.kernel_eff)
@@ -197,9 +218,8 @@ class I3DEngine:
                     pf = tuple(k - 1 - same_pad(sz, k, 1)[0] for sz, k in
                                zip((x_shape_act.d, x_shape_act.h, x_shape_act.w), unit.kernel))
                     gi = g_in
-                self.bwd_ops.append((self._lane, lambda: ops.conv3d(dz_out, unit.w_dgrad, gi, unit.kernel_eff,
-                                                                    (1, 1, 1), pf, acc_in=acc_in, mask=mask,
-                                                                    mask_scale=mask_scale)))
+                self.bwd_ops.append((self._lane, ConvOp(dz_out, unit.w_dgrad, gi, unit.kernel_eff, (1, 1, 1), pf,
+                                                        acc_in=acc_in, mask=mask, mask_scale=mask_scale)))
 
         def out_dims(x, k, s):
             return tuple(same_pad(sz, kk, ss)[2] for sz, kk, ss in zip((x.d, x.h, x.w), k, s))
@@ -285,6 +305,12 @@ class I3DEngine:
         self.x = torch.zeros((B, in_channels, self.T, self.H, self.W), dtype=torch.float32, device=dev)
         self.dm = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
         self.zero_mask = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
+        if mode == "bf16" and tune.enabled():  # measured tile plans for the slab convolutions (cached per shape)
+            with torch.cuda.device(dev):
+                for item in self.fwd_ops + self.bwd_ops:
+                    if isinstance(item[0], int) and isinstance(item[1], ConvOp):
+                        item[1].tune(dev)
+                torch.cuda.synchronize(dev)
 
     # -------------------------------------------------------------------------------------
     def _build_inception(self, sd, name, x, new_act, add_unit_fwd):

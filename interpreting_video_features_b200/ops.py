@@ -58,9 +58,10 @@ def same_pad(size, k, s):
     return front, total - front, int(math.ceil(size / s))
 
 
-def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None, acc_in=None,
-           mask=None, mask_scale=None, transposed=0, cin=None, cout=None):
-    """out = epilogue(conv(x, w)); see ivf_conv3d. x/out/mask are Act; w is the packed weight."""
+def conv_desc(x, out, kernel, stride, pad_front, flags=0, scale=None, acc_in=None, mask=None, transposed=0,
+              cin=None, cout=None, plan=None):
+    """The ivf_conv_desc of a launch (also used without launching: tile-plan queries of the tuner).
+    plan = (kwm, mt, acc, ncta, ntiles) requests a slab-kernel tile plan, None/0 = cost model."""
     d = ConvDesc()
     d.n, d.id, d.ih, d.iw = x.n, x.d, x.h, x.w
     d.od, d.oh, d.ow = out.d, out.h, out.w
@@ -83,6 +84,15 @@ def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None
     if out.buf.dtype == torch.float32 and x.buf.dtype == torch.bfloat16:
         flags |= EP_OUT_F32
     d.flags = flags
+    if plan is not None:
+        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = plan
+    return d
+
+
+def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None, acc_in=None,
+           mask=None, mask_scale=None, transposed=0, cin=None, cout=None, plan=None):
+    """out = epilogue(conv(x, w)); see ivf_conv3d. x/out/mask are Act; w is the packed weight."""
+    d = conv_desc(x, out, kernel, stride, pad_front, flags, scale, acc_in, mask, transposed, cin, cout, plan)
     check(_lib.load().ivf_conv3d(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(w), ptr(scale),
                                  ptr(shift), ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
                                  ptr(mask.buf if mask is not None else None), ptr(mask_scale),

@@ -1,0 +1,86 @@
+"""Measured tile-plan selection for the halo-slab convolution kernel (csrc/conv_slab.cu).
+
+The kernel's cost model ranks (kw-merge, accumulators per tile, TMEM buffering, CTA pairs, N tiles) well
+within ~10 % for most layers but misses by 15-30 % where the TMA slab rows or the epilogue dominate (the
+stem, the 64-channel data gradients, the 7x7 stage - tools/tune_slab.py).  So each distinct layer shape is
+measured once per process on the device it runs on: every plan the kernel accepts is timed with CUDA events
+and the fastest is passed with the launch (ivf_conv_desc.plan_*).  Results are cached per shape, so every
+engine of a process uses the same plan for the same layer (and therefore the same summation order).
+IVF_TUNE=0 disables the measurement (cost model only).
+"""
+import ctypes as C
+import itertools
+import os
+
+import torch
+
+from . import _lib
+
+_CACHE = {}
+_FIELDS = ("n", "id", "ih", "iw", "od", "oh", "ow", "cin", "cout", "kd", "kh", "kw", "pd", "ph", "pw",
+           "in_ld", "in_coff", "out_ld", "out_coff", "mask_ld", "mask_coff", "flags", "dtype")
+
+
+def enabled():
+    return os.environ.get("IVF_TUNE", "1") != "0"
+
+
+def _key(d, device):
+    return (str(device),) + tuple(getattr(d, f) for f in _FIELDS)
+
+
+def _plan_of(d, sm_count):
+    out = (C.c_int * 12)()
+    if not _lib.load().ivf_conv_slab_plan(C.byref(d), sm_count, out):
+        return None
+    return tuple(out)
+
+
+def candidates(make_desc, sm_count):
+    """Distinct plans the kernel accepts for this layer: list of request tuples (kwm, mt, acc, ncta, ntiles)."""
+    seen, reqs = set(), []
+    kw = make_desc(None).kw
+    for ncta, kwm, mt, acc, nt in itertools.product((1, 2), (1, 2, 3, 4), (1, 2, 3, 4), (1, 2), (0, 1, 2, 3, 4, 6, 8)):
+        if kw % kwm:
+            continue
+        req = (kwm, mt, acc, ncta, nt)
+        p = _plan_of(make_desc(req), sm_count)
+        if p is None:
+            continue
+        got = (p[10], p[3], p[5], p[11], p[2], p[1])  # kwm mt acc ncta ntiles bn
+        if (p[10], p[3], p[5], p[11]) != (kwm, mt, acc, ncta) or got in seen:
+            continue
+        seen.add(got)
+        reqs.append((kwm, mt, acc, ncta, p[2]))
+    return reqs
+
+
+def best_plan(make_desc, launch, device, reps=3):
+    """make_desc(plan) -> ConvDesc; launch(plan) issues the convolution.  Returns the fastest request tuple,
+    or None when the layer is not served by the slab kernel (or tuning is off)."""
+    if not enabled():
+        return None
+    d0 = make_desc(None)
+    if d0.dtype != _lib.IVF_BF16:
+        return None
+    key = _key(d0, device)
+    if key in _CACHE:
+        return _CACHE[key]
+    sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+    if _plan_of(d0, sm_count) is None:
+        _CACHE[key] = None
+        return None
+    best, best_t = None, None
+    for req in [None] + candidates(make_desc, sm_count):
+        launch(req)  # first use: tensor maps, function attributes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            launch(req)
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        if best_t is None or t < best_t * 0.97:  # keep the model's plan (tried first) unless clearly beaten
+            best, best_t = req, t
+    _CACHE[key] = best
+    return best
