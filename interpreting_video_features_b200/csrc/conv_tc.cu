@@ -12,8 +12,7 @@
 //
 // GEMM view: D[M=128 pixels][N=cout tile] += A[128][kchunk] * B[N][kchunk]^T per (tap, channel
 // chunk).  Warp roles: warp 0 = TMA producer (+TMEM alloc), warp 1 = MMA issuer (one lane),
-// warps 2-9 = epilogue (TMEM lane quarter = warp_idx % 4; the two warps of a quarter split the 16-column
-// chunks - with K as small as 64..832 the epilogue is most of a 1x1x1 launch).
+// warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include "conv_common.cuh"
 
 #include <cstring>
@@ -26,7 +25,7 @@ namespace {
 using namespace ivf_tc;
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int NUM_THREADS = 192;
 constexpr int MAX_STAGES = 12;
 
 struct TcParams {
@@ -58,7 +57,7 @@ struct KTraits {
 };
 
 template <int KCH>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p, const float* __restrict__ scale, const float* __restrict__ shift,
                const float* __restrict__ acc_in, const __nv_bfloat16* __restrict__ mask_y,
@@ -97,7 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp >= 2) {
     // per-channel epilogue vectors of this N tile
-    for (int i = threadIdx.x - 64; i < p.bn; i += 256) {
+    for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
       int n = ntile * p.bn + i;
       bool ok = n < p.cout;
       s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[n] : 1.f;
@@ -204,15 +203,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.out = out;
     // the first chunk's global operands are fetched while the MMAs still run
     EpiPre cur, nxt;
-    const int chalf = (warp - 2) >> 2;  // which half of the chunks this warp stores
-    const int nchunks = p.bn >> 4, c_lo = ((nchunks + 1) / 2) * 16 * chalf;
-    const int c_hi = chalf == 0 ? ((nchunks + 1) / 2) * 16 : p.bn;
-    epilogue_prefetch(ea, ntile * p.bn + c_lo, out_row, mask_row, row_ok && c_lo < c_hi, cur);
+    epilogue_prefetch(ea, ntile * p.bn, out_row, mask_row, row_ok, cur);
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
       const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
-      if (c0 + 16 < c_hi) epilogue_prefetch(ea, nb + 16, out_row, mask_row, row_ok, nxt);
+      if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, row_ok, nxt);
       uint32_t r[16];
       tmem_ld16(taddr_row + c0, r);
       if (row_ok && nb < p.cout)
