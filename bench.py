@@ -237,6 +237,51 @@ def gradcam_throughput(dev, rank, world, mode, clips_n=8, reps=5):
                         "native geometry, SURVEY fact 10), %d clips per call, not CUDA-graphed" % clips_n}
 
 
+def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10):
+    """Config C3: ConvLSTM (KTH geometry, 2 layers, 5x5, conv stride 2, 32 hidden units as in the paper)
+    temporal-mask search with the reverse perturbation on 32x120x160 clips: clip-iterations/s, iteration
+    replayed from a CUDA graph, clips resident in HBM."""
+    import torch.distributed as dist
+    from interpreting_video_features_b200 import ops, search
+    from interpreting_video_features_b200.pt.models import CLSTM_4
+    from oracle import synthetic
+    torch.manual_seed(0)
+    m = quiet(CLSTM_4.Model, num_classes=6, nb_lstm_units=32, channels=3, conv_kernel_size=(5, 5), lstm_layers=2,
+              step=32, conv_stride=2, image_size=(160, 120), effective_step=[7, 15, 23, 31],
+              batch_normalization=True, dropout=0.5, add_softmax=True).to(dev).eval().set_mode(mode)
+    x = torch.stack([synthetic.uniform_clip(2000 + rank * clips_n + i, t=32, h=120, w=160)
+                     for i in range(clips_n)]).to(dev) / 255.0
+    eng = m._engine(x, batch=clips_n)
+    ms = search.MaskSearch(eng, 0.02, 0.04, 0.2, 100, "reverse", 0.9, use_graph=True)
+    ms.set_input(x)
+    ms.set_targets((torch.arange(clips_n) % 6).to(dev))
+    ms.m.copy_(torch.tensor([-5.] * 8 + [5.] * 16 + [-5.] * 8, device=dev).repeat(clips_n, 1))
+    ops.sigmoid(ms.m, ms.sig)
+    ms._capture()
+    for _ in range(3):
+        ms.graph.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ms.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([sec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t[0])
+    return {"metric": "clstm_mask_search_clip_iterations_per_sec", "unit": "clip-iterations/s",
+            "value": world * clips_n * steps / sec, "ms_per_step": sec / steps * 1e3, "clips_per_gpu": clips_n,
+            "launches_per_step": int(ms.launches_per_iter),
+            "algorithmic_gflop_per_clip_iteration": 76.7,
+            "workload": "C3: ConvLSTM (6 classes, hidden 32, 2 layers) temporal-mask search, reverse perturbation, "
+                        "%d synthetic 32x120x160 clips per step" % clips_n}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from interpreting_video_features_b200 import _lib, search
@@ -331,6 +376,7 @@ def run_ours(args, rank, world, local_rank):
                    "reverse score + D2H, per rank; step = 1/300 of a search"}
 
     gradcam = gradcam_throughput(dev, rank, world, args.mode) if not args.no_gradcam else None
+    clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
 
     if rank != 0:
         return
@@ -344,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32",
             "data": "synthetic", "config": CONFIG, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gradcam": gradcam,
+            "gradcam": gradcam, "clstm": clstm,
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "clocks": sampler.summary()}
     print(json.dumps(line), flush=True)
@@ -359,6 +405,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")
+    ap.add_argument("--no-clstm", action="store_true", help="skip the ConvLSTM (config C3) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
