@@ -32,3 +32,20 @@ ms._iteration()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("profiled one iteration for %d clips" % clips_n)
+
+# ---- program structure (lanes, forks, joins, launches per op) for critical-path analysis of the launch list
+import json  # noqa: E402
+from interpreting_video_features_b200 import _lib  # noqa: E402
+eng = ms.engs[0]
+prog = []
+for name, ops_list in (("fwd", eng.fwd_ops), ("bwd", eng.bwd_ops)):
+    for item in ops_list:
+        if isinstance(item[0], int):
+            n0 = _lib.launch_count(dev)
+            item[1]()
+            prog.append([name, "op", item[0], _lib.launch_count(dev) - n0])
+        else:
+            prog.append([name] + [list(v) if isinstance(v, tuple) else v for v in item])
+torch.cuda.synchronize()
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(prog, open("gpurun_out/program.json", "w"))
