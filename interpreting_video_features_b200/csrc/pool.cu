@@ -154,8 +154,6 @@ maxpool_bwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
   // stride 2, 1 of 8 for 2x2x2 stride 2), with no divisibility test left inside the loop.
   const int pd0 = (idd + d.pd) % SD, ph0 = (ih + d.ph) % SH, pw0 = (iw + d.pw) % SW;
   const int qd = (idd + d.pd) / SD, qh = (ih + d.ph) / SH, qw = (iw + d.pw) / SW;  // window of tap == remainder
-  const uint8_t* am_c = argmax + c;                       // this thread's channel group in any window
-  const __nv_bfloat16* dy_c = dy + d.out_coff + c;
 #pragma unroll
   for (int ja = 0; ja * SD < KD; ++ja) {
     const int a = pd0 + ja * SD, od = qd - ja;
@@ -164,26 +162,21 @@ maxpool_bwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
     for (int jb = 0; jb * SH < KH; ++jb) {
       const int b = ph0 + jb * SH, oh = qh - jb;
       if (b >= KH || oh < 0 || oh >= d.oh) continue;
-      // window (od, oh, qw): pointers walk one window to the left per tap (no index rebuild per window)
-      const long long o0 = (long long)((n * d.od + od) * d.oh + oh) * d.ow + qw;
-      const uint8_t* am_p = am_c + o0 * d.c;
-      const __nv_bfloat16* dy_p = dy_c + o0 * d.out_ld;
+      const int orow = ((n * d.od + od) * d.oh + oh) * d.ow;
 #pragma unroll
-      for (int je = 0; je * SW < KW; ++je, am_p -= d.c, dy_p -= d.out_ld) {
+      for (int je = 0; je * SW < KW; ++je) {
         const int e = pw0 + je * SW, ow = qw - je;
         if (e >= KW || ow < 0 || ow >= d.ow) continue;
-        const uint2 pk = *reinterpret_cast<const uint2*>(am_p);
-        // any byte of the two words equal to this tap?  x = pk ^ tap has a zero byte there; the classic
-        // (x - 0x01..) & ~x & 0x80.. test is exact for "any" and costs three operations per word
+        const int opix = orow + ow;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + (long long)opix * d.c + c);
         const uint32_t tap4 = (uint32_t)((a * KH + b) * KW + e) * 0x01010101u;
-        const uint32_t x0 = pk.x ^ tap4, x1 = pk.y ^ tap4;
-        const uint32_t z = ((x0 - 0x01010101u) & ~x0 & 0x80808080u) | ((x1 - 0x01010101u) & ~x1 & 0x80808080u);
-        if (z == 0u) continue;
-        const uint4 raw = *reinterpret_cast<const uint4*>(dy_p);
+        const uint32_t e0 = __vcmpeq4(pk.x, tap4), e1 = __vcmpeq4(pk.y, tap4);
+        if ((e0 | e1) == 0u) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(dy + (long long)opix * d.out_ld + d.out_coff + c);
         const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if ((((i < 4 ? x0 : x1) >> (8 * (i & 3))) & 0xffu) == 0u) g[i] += __bfloat162float(v[i]);
+          if (((i < 4 ? e0 : e1) >> (8 * (i & 3))) & 1u) g[i] += __bfloat162float(v[i]);
       }
     }
   }
