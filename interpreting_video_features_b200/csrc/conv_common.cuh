@@ -76,36 +76,12 @@ __device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const CUtensorM
 }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset,
-// [61,64) swizzle type.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes,
-                                                   uint32_t layout_type, uint32_t base_offset = 0) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;  // LBO (unused for swizzled K-major; CUTLASS writes 1)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7u) << 49;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Same MMA with the descriptors given as (low word, shared high word): the issuing thread then needs
-// one 32-bit add per operand per MMA instead of rebuilding two 64-bit descriptors (the single issuing
-// thread's dependent uniform-datapath chain, not the tensor pipe, bounded the first slab kernel at
-// ~200 cycles per MMA).  lo = (smem_addr >> 4) | (1 << 16);  hi = SBO>>4 | version<<14 | layout<<29.
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset (0: the swizzle is
+// applied on absolute shared-memory address bits, so a start address off the 8-row atom needs none),
+// [61,64) swizzle type.  The issuing thread keeps the constant high word and adds to the low word: one 32-bit
+// add per operand per MMA (rebuilding 64-bit descriptors in a divergent single-thread region bounded the
+// first slab kernel at ~200 cycles per MMA).  lo = (smem_addr >> 4) | (1 << 16) [LBO = 1, unused for swizzled
+// K-major];  hi = SBO>>4 | version<<14 | layout<<29.
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);

@@ -183,6 +183,43 @@ def test_conv_data_gradient_with_fused_mask_and_accumulate(dev, mode, case):
     assert rel_err(gxa.ncdhw().cpu(), ref) < tol
 
 
+@pytest.mark.parametrize("case", [(1, 64, 64, (3, 10, 56), (3, 3, 3)), (2, 32, 32, (2, 9, 28), (3, 3, 3)),
+                                  (1, 32, 64, (3, 6, 40), (4, 4, 4)), (1, 96, 16, (2, 14, 14), (3, 3, 3))])
+def test_conv_slab_every_tile_plan(dev, case):
+    """Every tile plan the halo-slab kernel accepts for a layer (kw-merge 1..4, 1..4 accumulators per tile, single
+    and double buffered TMEM, single CTAs and cta_group::2 pairs, 1..N tiles) gives the same convolution: each
+    within 1e-2 of the fp32 reference (bf16 operands) and within 2e-3 of the cost model's own plan."""
+    from interpreting_video_features_b200 import _lib, engine, ops, tune
+    from interpreting_video_features_b200.ops import Act, same_pad
+    n, cin, cout, dhw, k = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((n, cin) + dhw, generator=g).bfloat16().float()
+    w = (torch.randn((cout, cin) + k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5).bfloat16().float()
+    geo = [same_pad(sz, kk, 1) for sz, kk in zip(dhw, k)]
+    pf = tuple(q[0] for q in geo)
+    ref = ref_conv(x, w, (1, 1, 1), pf, dhw)
+    xa = to_act(x.to(dev), torch.bfloat16)
+    wp = engine.pack_fwd(w.to(dev), "bf16")
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = Act.empty(n, *dhw, cout, torch.bfloat16, dev)
+
+    def make_desc(plan):
+        return ops.conv_desc(xa, out, k, (1, 1, 1), pf, plan=plan)
+
+    plans = tune.candidates(make_desc, sm)
+    assert len(plans) >= 6, plans
+    assert {p[3] for p in plans} == {1, 2} and len({p[0] for p in plans}) >= 2 and len({p[2] for p in plans}) == 2
+    ops.conv3d(xa, wp, out, k, (1, 1, 1), pf)
+    base = out.ncdhw().cpu()
+    assert rel_err(base, ref) < 1e-2
+    for plan in plans:
+        out.buf.zero_()
+        ops.conv3d(xa, wp, out, k, (1, 1, 1), pf, plan=plan)
+        got = out.ncdhw().cpu()
+        assert rel_err(got, ref) < 1e-2, (plan, rel_err(got, ref))
+        assert rel_err(got, base) < 2e-3, (plan, rel_err(got, base))
+
+
 def test_conv_fp32_strided_stem_and_its_gradient(dev):
     """The 7x7x7 stride-2 stem in fp32 mode (true strided gather, transposed data-gradient)."""
     from interpreting_video_features_b200 import _lib, engine, ops
