@@ -27,55 +27,82 @@ __device__ float block_reduce(float v, float* red, bool is_max) {
   return r;
 }
 
-constexpr int HEAD_CHUNK = 128;  // channels per forward block
+constexpr int HEAD_CHUNK = 64;  // channels per block: 32 lanes x 2 adjacent channels
+constexpr int HEAD_WARPS = HEAD_THREADS / 32;
+constexpr int HEAD_MAX_PP = 16;  // positions per warp kept in flight at once
 
-// Forward, stage 1: grid (clip, channel chunk).  256 threads = 128 channels x 2 position halves;
-// average-pool the chunk, then its partial logits -> scratch[clip][chunk][class].
-template <typename T>
+// two adjacent channels k, k+1 of one position (vector load when the row is even-aligned)
+template <typename T, bool VEC2>
+__device__ __forceinline__ float2 head_load2(const T* p, bool has2) {
+  if (VEC2) {
+    if (sizeof(T) == 2) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+      return make_float2(__low2float(v), __high2float(v));
+    }
+    return *reinterpret_cast<const float2*>(p);
+  }
+  return make_float2(ivf_to_float(p[0]), has2 ? ivf_to_float(p[1]) : 0.f);
+}
+
+// Forward, stage 1: grid (clip, channel chunk).  The head is a few MFLOP on a few MB: pure latency, so
+// the kernels are shaped to have every load of a phase in flight at once.  Lane = channel pair,
+// warp = position group (pool) then class group (logits); partial logits -> scratch[clip][chunk][class].
+template <typename T, bool VEC2>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_fwd_partial_kernel(const T* __restrict__ feat, int p, int c, int ld, const float* __restrict__ w,
                         int ncls, float* __restrict__ partial) {
-  __shared__ float half_sum[2][HEAD_CHUNK];
-  __shared__ float avg[HEAD_CHUNK];
+  __shared__ float2 wsum[HEAD_WARPS][32];
+  __shared__ float2 avg[32];
   const int n = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
-  const int k0 = chunk * HEAD_CHUNK;
-  const int kl = threadIdx.x % HEAD_CHUNK, half = threadIdx.x / HEAD_CHUNK;
-  const T* f = feat + (size_t)n * p * ld;
-  float s = 0.f;
-  if (k0 + kl < c) {
-    // fixed summation order (positions half, half+2, ...), four independent partial sums so the
-    // loads are in flight together
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const T* fp = f + k0 + kl;
-    int i = half;
-    for (; i + 6 < p; i += 8) {
-      s0 += ivf_to_float(fp[(size_t)i * ld]);
-      s1 += ivf_to_float(fp[(size_t)(i + 2) * ld]);
-      s2 += ivf_to_float(fp[(size_t)(i + 4) * ld]);
-      s3 += ivf_to_float(fp[(size_t)(i + 6) * ld]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = chunk * HEAD_CHUNK + 2 * lane;
+  const bool has1 = k < c, has2 = k + 1 < c;
+  const T* f = feat + (size_t)n * p * ld + k;
+  // fixed summation order: warp g sums positions g, g+8, ... ; warps are combined in order below
+  float2 s = make_float2(0.f, 0.f);
+  if (has1) {
+    for (int i0 = warp; i0 < p; i0 += HEAD_WARPS * HEAD_MAX_PP) {
+      float2 v[HEAD_MAX_PP];
+#pragma unroll
+      for (int u = 0; u < HEAD_MAX_PP; ++u) {
+        const int i = i0 + u * HEAD_WARPS;
+        v[u] = i < p ? head_load2<T, VEC2>(f + (size_t)i * ld, has2) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < HEAD_MAX_PP; ++u) {
+        s.x += v[u].x;
+        s.y += v[u].y;
+      }
     }
-    for (; i < p; i += 2) s0 += ivf_to_float(fp[(size_t)i * ld]);
-    s = (s0 + s1) + (s2 + s3);
   }
-  half_sum[half][kl] = s;
+  wsum[warp][lane] = s;
   __syncthreads();
-  if (threadIdx.x < HEAD_CHUNK) avg[kl] = (half_sum[0][kl] + half_sum[1][kl]) / (float)p;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < ncls; j += 2 * nw) {  // two classes per pass: their loads overlap
-    const int j2 = j + nw;
-    const float* wr = w + (size_t)j * c + k0;
-    const float* wr2 = w + (size_t)(j2 < ncls ? j2 : j) * c + k0;
-    float a = 0.f, a2 = 0.f;
-    for (int k = lane; k < HEAD_CHUNK && k0 + k < c; k += 32) {
-      a = fmaf(__ldg(wr + k), avg[k], a);
-      a2 = fmaf(__ldg(wr2 + k), avg[k], a2);
+  if (warp == 0) {
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < HEAD_WARPS; ++g) {
+      a.x += wsum[g][lane].x;
+      a.y += wsum[g][lane].y;
     }
-    a = ivf_warp_sum(a);
-    a2 = ivf_warp_sum(a2);
-    if (lane == 0) {
-      partial[((size_t)n * nchunks + chunk) * ncls + j] = a;
-      if (j2 < ncls) partial[((size_t)n * nchunks + chunk) * ncls + j2] = a2;
+    avg[lane] = make_float2(a.x / (float)p, a.y / (float)p);
+  }
+  __syncthreads();
+  const float2 av = avg[lane];
+  float* pout = partial + ((size_t)n * nchunks + chunk) * ncls;
+  for (int j0 = warp; j0 < ncls; j0 += HEAD_WARPS * 8) {  // eight classes per pass, loads overlapped
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * HEAD_WARPS;
+      float2 wv = make_float2(0.f, 0.f);
+      if (j < ncls && has1) wv = head_load2<float, VEC2>(w + (size_t)j * c + k, has2);
+      a[u] = fmaf(wv.x, av.x, wv.y * av.y);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float r = ivf_warp_sum(a[u]);
+      const int j = j0 + u * HEAD_WARPS;
+      if (lane == 0 && j < ncls) pout[j] = r;
     }
   }
 }
@@ -108,11 +135,13 @@ head_fwd_finish_kernel(const float* __restrict__ partial, int nchunks, const flo
     out[(size_t)n * ncls + j] = expf(lg[j] - mx) / se;
 }
 
-// Backward: grid (clip, channel chunk of HEAD_CHUNK).  Every block rebuilds dlogits (ncls values), then
-// the 256 threads = HEAD_CHUNK channels x 2 class halves form davg for the block's channels only (so a
-// block reads just its [ncls][HEAD_CHUNK] slice of W, eight independent loads in flight per thread) and
-// write those channels of all p positions.
-template <typename T>
+// Backward: grid (clip, channel chunk of HEAD_CHUNK).  Every block rebuilds dlogits (ncls values); then
+// lane = channel pair, warp = class group: each thread has all its W loads in flight at once (the block
+// reads just its [ncls][HEAD_CHUNK] slice of W); davg is combined over the warps in a fixed order and
+// the block writes its channels of all p positions, warp = position group.
+constexpr int HEAD_MAX_CLS = 24;  // classes per thread per pass
+
+template <typename T, bool VEC2>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int softmax,
                 const float* __restrict__ out, const float* __restrict__ dout, int flags,
@@ -120,11 +149,13 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
                 const float* __restrict__ mask_scale, void* __restrict__ dfeat) {
   extern __shared__ float sm[];  // dlogit[ncls]
   __shared__ float red[32];
-  __shared__ float part[2][HEAD_CHUNK];
-  __shared__ float davg[HEAD_CHUNK], mscale[HEAD_CHUNK];
+  __shared__ float2 part[HEAD_WARPS][32];
+  __shared__ float2 davg_s[32];
   float* dl = sm;
   const int n = blockIdx.x;
-  const int k0 = blockIdx.y * HEAD_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.y * HEAD_CHUNK + 2 * lane;
+  const bool has1 = k < c, has2 = k + 1 < c;
   const float* o = out + (size_t)n * ncls;
   const float* g = dout + (size_t)n * ncls;
   if (softmax) {
@@ -136,46 +167,83 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
     for (int j = threadIdx.x; j < ncls; j += blockDim.x) dl[j] = g[j];
   }
   __syncthreads();
-  const int kl = threadIdx.x % HEAD_CHUNK, half = threadIdx.x / HEAD_CHUNK;
-  const int k = k0 + kl;
   {
-    const int jh = (ncls + 1) / 2;
-    const int j0 = half * jh, j1 = min(ncls, j0 + jh);
-    float acc[8];
+    float2 a = make_float2(0.f, 0.f);
+    if (has1) {
+      for (int j0 = warp; j0 < ncls; j0 += HEAD_WARPS * HEAD_MAX_CLS) {
+        float2 wv[HEAD_MAX_CLS];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-    if (k < c) {
-      const float* wk = w + k;
-      int j = j0;
-      for (; j + 8 <= j1; j += 8) {
+        for (int u = 0; u < HEAD_MAX_CLS; ++u) {
+          const int j = j0 + u * HEAD_WARPS;
+          wv[u] = j < ncls ? head_load2<float, VEC2>(w + (size_t)j * c + k, has2) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = fmaf(__ldg(wk + (size_t)(j + u) * c), dl[j + u], acc[u]);
+        for (int u = 0; u < HEAD_MAX_CLS; ++u) {
+          const int j = j0 + u * HEAD_WARPS;
+          const float d = j < ncls ? dl[j] : 0.f;
+          a.x = fmaf(wv[u].x, d, a.x);
+          a.y = fmaf(wv[u].y, d, a.y);
+        }
       }
-      for (; j < j1; ++j) acc[0] = fmaf(__ldg(wk + (size_t)j * c), dl[j], acc[0]);
     }
-    part[half][kl] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    part[warp][lane] = a;
   }
   __syncthreads();
-  if (threadIdx.x < HEAD_CHUNK) {
-    davg[kl] = (part[0][kl] + part[1][kl]) / (float)p;
-    mscale[kl] = ((flags & IVF_EP_MASK) && k < c) ? mask_scale[k] : 1.f;
+  if (warp == 0) {
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int gq = 0; gq < HEAD_WARPS; ++gq) {
+      a.x += part[gq][lane].x;
+      a.y += part[gq][lane].y;
+    }
+    davg_s[lane] = make_float2(a.x / (float)p, a.y / (float)p);
   }
   __syncthreads();
+  if (!has1) return;
+  const float2 dv = davg_s[lane];
+  float2 ms = make_float2(1.f, 1.f);
+  if (flags & IVF_EP_MASK) ms = make_float2(mask_scale[k], has2 ? mask_scale[k + 1] : 1.f);
   const size_t base = (size_t)n * p;
-  const int kc = min(HEAD_CHUNK, c - k0);
-  for (int e = threadIdx.x; e < p * HEAD_CHUNK; e += blockDim.x) {
-    const int i = e / HEAD_CHUNK, kk = e % HEAD_CHUNK;
-    if (kk >= kc) continue;
-    float v = davg[kk];
+  for (int i0 = warp; i0 < p; i0 += HEAD_WARPS * HEAD_MAX_PP) {
+    float2 yv[HEAD_MAX_PP];
     if (flags & IVF_EP_MASK) {
-      float y = ivf_to_float(mask_y[(base + i) * mask_ld + mask_coff + k0 + kk]);
-      v = y > 0.f ? v * mscale[kk] : 0.f;
+#pragma unroll
+      for (int u = 0; u < HEAD_MAX_PP; ++u) {
+        const int i = i0 + u * HEAD_WARPS;
+        yv[u] = i < p ? head_load2<T, VEC2>(mask_y + (base + i) * mask_ld + mask_coff + k, has2)
+                      : make_float2(0.f, 0.f);
+      }
     }
-    size_t idx = (base + i) * ld + k0 + kk;
-    if (flags & IVF_EP_OUT_F32)
-      reinterpret_cast<float*>(dfeat)[idx] = v;
-    else
-      reinterpret_cast<T*>(dfeat)[idx] = ivf_from_float<T>(v);
+#pragma unroll
+    for (int u = 0; u < HEAD_MAX_PP; ++u) {
+      const int i = i0 + u * HEAD_WARPS;
+      if (i >= p) continue;
+      float2 v = dv;
+      if (flags & IVF_EP_MASK) {
+        v.x = yv[u].x > 0.f ? v.x * ms.x : 0.f;
+        v.y = yv[u].y > 0.f ? v.y * ms.y : 0.f;
+      }
+      const size_t idx = (base + i) * ld + k;
+      if (flags & IVF_EP_OUT_F32) {
+        float* d = reinterpret_cast<float*>(dfeat) + idx;
+        if (VEC2) {
+          *reinterpret_cast<float2*>(d) = v;
+        } else {
+          d[0] = v.x;
+          if (has2) d[1] = v.y;
+        }
+      } else {
+        T* d = reinterpret_cast<T*>(dfeat) + idx;
+        if (VEC2 && sizeof(T) == 2) {
+          *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(v.x, v.y);
+        } else if (VEC2) {
+          *reinterpret_cast<float2*>(d) = v;
+        } else {
+          d[0] = ivf_from_float<T>(v.x);
+          if (has2) d[1] = ivf_from_float<T>(v.y);
+        }
+      }
+    }
   }
 }
 
@@ -192,13 +260,17 @@ extern "C" int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int 
   IVF_REQUIRE((size_t)ncls * sizeof(float) <= 48 * 1024, "ivf_i3d_head_fwd: ncls too large");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(n, nchunks);
-  if (dtype == IVF_F32)
-    head_fwd_partial_kernel<float><<<grid, HEAD_THREADS, 0, st>>>((const float*)feat, p, c, ld, w, ncls, h->scratch);
-  else if (dtype == IVF_BF16)
-    head_fwd_partial_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, 0, st>>>((const __nv_bfloat16*)feat, p, c, ld, w,
-                                                                          ncls, h->scratch);
-  else
-    IVF_FAIL(IVF_EINVAL, "ivf_i3d_head_fwd: unknown dtype %d", dtype);
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_i3d_head_fwd: unknown dtype %d", dtype);
+  const size_t pair_bytes = dtype == IVF_F32 ? 8 : 4;
+  const bool vec2 = c % 2 == 0 && ld % 2 == 0 && (uintptr_t)feat % pair_bytes == 0 && (uintptr_t)w % 8 == 0;
+#define IVF_HEAD_FWD(T, V) \
+  head_fwd_partial_kernel<T, V><<<grid, HEAD_THREADS, 0, st>>>((const T*)feat, p, c, ld, w, ncls, h->scratch)
+  if (dtype == IVF_F32) {
+    if (vec2) IVF_HEAD_FWD(float, true); else IVF_HEAD_FWD(float, false);
+  } else {
+    if (vec2) IVF_HEAD_FWD(__nv_bfloat16, true); else IVF_HEAD_FWD(__nv_bfloat16, false);
+  }
+#undef IVF_HEAD_FWD
   IVF_LAUNCHED(h);
   head_fwd_finish_kernel<<<n, HEAD_THREADS, ncls * sizeof(float), st>>>(h->scratch, nchunks, b, ncls, softmax, logits,
                                                                         out);
@@ -217,16 +289,21 @@ extern "C" int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, i
   IVF_REQUIRE(smem <= 40 * 1024, "ivf_i3d_head_bwd: ncls too large (%d)", ncls);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(n, (c + HEAD_CHUNK - 1) / HEAD_CHUNK);
-  if (dtype == IVF_F32)
-    head_bwd_kernel<float><<<grid, HEAD_THREADS, smem, st>>>(p, c, ld, w, ncls, softmax, out, dout, flags,
-                                                          (const float*)mask_y, mask_ld, mask_coff,
-                                                          mask_scale, dfeat);
-  else if (dtype == IVF_BF16)
-    head_bwd_kernel<__nv_bfloat16><<<grid, HEAD_THREADS, smem, st>>>(
-        p, c, ld, w, ncls, softmax, out, dout, flags, (const __nv_bfloat16*)mask_y, mask_ld,
-        mask_coff, mask_scale, dfeat);
-  else
-    IVF_FAIL(IVF_EINVAL, "ivf_i3d_head_bwd: unknown dtype %d", dtype);
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_i3d_head_bwd: unknown dtype %d", dtype);
+  const size_t pair_bytes = dtype == IVF_F32 ? 8 : 4;
+  const size_t out_pair = (flags & IVF_EP_OUT_F32) ? 8 : pair_bytes;
+  bool vec2 = c % 2 == 0 && ld % 2 == 0 && (uintptr_t)dfeat % out_pair == 0 && (uintptr_t)w % 8 == 0;
+  if (flags & IVF_EP_MASK)
+    vec2 = vec2 && mask_ld % 2 == 0 && mask_coff % 2 == 0 && (uintptr_t)mask_y % pair_bytes == 0;
+#define IVF_HEAD_BWD(T, V)                                                                           \
+  head_bwd_kernel<T, V><<<grid, HEAD_THREADS, smem, st>>>(p, c, ld, w, ncls, softmax, out, dout, flags, \
+                                                          (const T*)mask_y, mask_ld, mask_coff, mask_scale, dfeat)
+  if (dtype == IVF_F32) {
+    if (vec2) IVF_HEAD_BWD(float, true); else IVF_HEAD_BWD(float, false);
+  } else {
+    if (vec2) IVF_HEAD_BWD(__nv_bfloat16, true); else IVF_HEAD_BWD(__nv_bfloat16, false);
+  }
+#undef IVF_HEAD_BWD
   IVF_LAUNCHED(h);
   return IVF_OK;
 }

@@ -97,72 +97,103 @@ __global__ void perturb_fwd_planar_kernel(int mode, const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------ forward, space-to-depth bf16
-// one thread per macro pixel (h/2, w/2): 2x2 pixels x c channels.
 // S2D3 = true : I3D stem operand, two frames per 64-byte record [b][t/2][h/2][w/2][32]
 // S2D3 = false: ConvLSTM x-conv operand, one frame per 32-byte record, time-major [t][b][h/2][w/2][16]
-template <bool S2D3>
-__global__ void perturb_fwd_s2d_kernel(int mode, const float* __restrict__ x,
-                                       const float* __restrict__ mask, int mask_bstride, int c,
-                                       int t, int hh, int ww, __nv_bfloat16* __restrict__ out) {
+// Block = 128 macro pixels (h/2, w/2) x C channels, one thread per (macro pixel, channel) so the x
+// reads of a warp are 256 contiguous bytes and the occupancy is not capped by a fat per-thread state.
+// The record of a macro pixel interleaves channels, so the threads assemble records in shared memory
+// (odd word pitch: conflict-free 2-byte scatter) and the block writes them out as one contiguous run
+// of 128 records per frame (pair).  Shared memory is double-buffered: one barrier per record.
+constexpr int S2D_PX = 128;
+
+template <bool S2D3, int C>
+__global__ void __launch_bounds__(S2D_PX * C)
+perturb_fwd_s2d_kernel(int mode, const float* __restrict__ x, const float* __restrict__ mask,
+                       int mask_bstride, int t, int hh, int ww, __nv_bfloat16* __restrict__ out) {
+  constexpr int FR = S2D3 ? 2 : 1;        // frames per record
+  constexpr int REC = S2D3 ? 32 : 16;     // bf16 channels per record
+  constexpr int WORDS = REC / 2, PITCH = WORDS + 1;
   __shared__ MaskInfo mi;
-  const int b = blockIdx.y;
-  const int nb = gridDim.y;
+  __shared__ uint32_t recs[2][S2D_PX * PITCH];
+  const int b = blockIdx.y, nb = gridDim.y;
   build_mask_info(&mi, mask + (size_t)b * mask_bstride, t, mode);
-  const int h2 = hh / 2, w2 = ww / 2, t2 = t / 2;
+  const int h2 = hh / 2, w2 = ww / 2, nrec = t / FR, npx = h2 * w2;
   const size_t hw = (size_t)hh * ww;
-  constexpr int FR = S2D3 ? 2 : 1;    // frames per record
-  constexpr int REC = S2D3 ? 32 : 16;  // channels per record
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < h2 * w2; idx += gridDim.x * blockDim.x) {
-    const int y = idx / w2, xq = idx - y * w2;
-    float P[MAX_C][2][2];
-    for (int r = 0; r < t / FR; ++r) {
-      __align__(16) __nv_bfloat16 rec[REC];
+  const int px = threadIdx.x % S2D_PX, ch = threadIdx.x / S2D_PX;
+  const int idx0 = blockIdx.x * S2D_PX;
+  const int idx = idx0 + px;
+  const bool live = idx < npx;
+  const int y = live ? idx / w2 : 0, xq = live ? idx - y * w2 : 0;
+  // channels 4*FR*C.. of a record are padding: zero them once in both buffers
+  for (int i = threadIdx.x; i < 2 * S2D_PX * PITCH; i += blockDim.x) (&recs[0][0])[i] = 0u;
+  __syncthreads();
+  const float* xs = x + ((size_t)(b * C + ch) * t) * hw + (size_t)(2 * y) * ww + 2 * xq;
+  float2 cur[FR][2], nxt[FR][2];
+  float P[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  if (live) {
 #pragma unroll
-      for (int i = 0; i < REC; ++i) rec[i] = __float2bfloat16_rn(0.f);
+    for (int dt = 0; dt < FR; ++dt)
+#pragma unroll
+      for (int dh = 0; dh < 2; ++dh)
+        nxt[dt][dh] = *reinterpret_cast<const float2*>(xs + (size_t)dt * hw + (size_t)dh * ww);
+  }
+  const int block_px = min(S2D_PX, npx - idx0);
+  for (int r = 0; r < nrec; ++r) {
+    __nv_bfloat16* mine = reinterpret_cast<__nv_bfloat16*>(&recs[r & 1][px * PITCH]);
+    if (live) {
+#pragma unroll
+      for (int dt = 0; dt < FR; ++dt)
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) cur[dt][dh] = nxt[dt][dh];
+      if (r + 1 < nrec) {
+#pragma unroll
+        for (int dt = 0; dt < FR; ++dt)
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh)
+            nxt[dt][dh] = *reinterpret_cast<const float2*>(xs + (size_t)(FR * (r + 1) + dt) * hw +
+                                                           (size_t)dh * ww);
+      }
 #pragma unroll
       for (int dt = 0; dt < FR; ++dt) {
         const int u = FR * r + dt;
         const float mu = mi.m[u], cf = mi.coef[u];
         const int q = mi.partner[u];
 #pragma unroll
-        for (int ch = 0; ch < MAX_C; ++ch) {
-          if (ch >= c) break;
-          const float* xf = x + ((size_t)(b * c + ch) * t) * hw;
-#pragma unroll
-          for (int dh = 0; dh < 2; ++dh) {
-            const size_t off = (size_t)(2 * y + dh) * ww + 2 * xq;
-            float2 xv = *reinterpret_cast<const float2*>(xf + (size_t)u * hw + off);
-            float v0, v1;
-            if (mode == 0) {
-              if (u == 0) {
-                v0 = xv.x;
-                v1 = xv.y;
-              } else {
-                v0 = (1.f - mu) * xv.x + mu * P[ch][dh][0];
-                v1 = (1.f - mu) * xv.y + mu * P[ch][dh][1];
-              }
-              P[ch][dh][0] = v0;
-              P[ch][dh][1] = v1;
-            } else if (q == u) {
+        for (int dh = 0; dh < 2; ++dh) {
+          const float2 xv = cur[dt][dh];
+          float v0, v1;
+          if (mode == 0) {
+            if (u == 0) {
               v0 = xv.x;
               v1 = xv.y;
             } else {
-              float2 xp = *reinterpret_cast<const float2*>(xf + (size_t)q * hw + off);
-              v0 = (1.f - cf) * xv.x + cf * xp.x;
-              v1 = (1.f - cf) * xv.y + cf * xp.y;
+              v0 = (1.f - mu) * xv.x + mu * P[dh][0];
+              v1 = (1.f - mu) * xv.y + mu * P[dh][1];
             }
-            rec[((dt * 2 + dh) * 2 + 0) * c + ch] = __float2bfloat16_rn(v0);
-            rec[((dt * 2 + dh) * 2 + 1) * c + ch] = __float2bfloat16_rn(v1);
+            P[dh][0] = v0;
+            P[dh][1] = v1;
+          } else if (q == u) {
+            v0 = xv.x;
+            v1 = xv.y;
+          } else {
+            const float2 xp = *reinterpret_cast<const float2*>(xs + (size_t)q * hw + (size_t)dh * ww);
+            v0 = (1.f - cf) * xv.x + cf * xp.x;
+            v1 = (1.f - cf) * xv.y + cf * xp.y;
           }
+          mine[((dt * 2 + dh) * 2 + 0) * C + ch] = __float2bfloat16_rn(v0);
+          mine[((dt * 2 + dh) * 2 + 1) * C + ch] = __float2bfloat16_rn(v1);
         }
       }
-      size_t rec_index = S2D3 ? ((((size_t)b * t2 + r) * h2 + y) * w2 + xq)
-                              : ((((size_t)r * nb + b) * h2 + y) * w2 + xq);
-      uint4* dst = reinterpret_cast<uint4*>(out + rec_index * REC);
-      const uint4* src = reinterpret_cast<const uint4*>(rec);
-#pragma unroll
-      for (int i = 0; i < REC / 8; ++i) dst[i] = src[i];
     }
+    __syncthreads();
+    // records of this block for record row r are contiguous in the output
+    const size_t rec0 = S2D3 ? (((size_t)b * nrec + r) * npx + idx0) : (((size_t)r * nb + b) * npx + idx0);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + rec0 * REC);
+    const uint32_t* src = recs[r & 1];
+    for (int i = threadIdx.x; i < block_px * WORDS; i += blockDim.x)
+      dst[i] = src[(i / WORDS) * PITCH + (i % WORDS)];
+    // no second barrier: the next record goes to the other buffer, and the barrier of iteration r+1
+    // orders these reads before the writes of iteration r+2
   }
 }
 
@@ -260,50 +291,126 @@ perturb_bwd_planar_kernel(int mode, const float* __restrict__ x, const float* __
   block_reduce_dm<TT>(acc, t, red, dmask + (size_t)b * t);
 }
 
-// space-to-depth gout (bf16 or fp32 records): one block per (macro row, clip); the row's records for
-// all frames are staged in shared memory with 16-byte loads, then each thread walks full-resolution
-// pixels of the two rows (coalesced x reads along W).  S2D3: 32-channel two-frame records (I3D);
-// otherwise 16-channel one-frame time-major records (ConvLSTM).
+// Two horizontally adjacent pixels of one channel at once (float2 x loads, two g values of one record).
+template <int TT, typename XL, typename GL>
+__device__ __forceinline__ void item_bwd2(int mode, int t, const MaskInfo& mi, XL xl, GL gl,
+                                          float (&acc)[TT]) {
+  if (mode == 0) {
+    float2 D[TT];
+    float2 P = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+      if (u < t) {
+        float2 xv = xl(u);
+        if (u == 0) {
+          D[u] = make_float2(0.f, 0.f);
+          P = xv;
+        } else {
+          const float mu = mi.m[u];
+          D[u] = make_float2(P.x - xv.x, P.y - xv.y);
+          P.x = (1.f - mu) * xv.x + mu * P.x;
+          P.y = (1.f - mu) * xv.y + mu * P.y;
+        }
+      }
+    }
+    float2 G = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = TT - 1; u >= 1; --u) {
+      if (u < t) {
+        const float mn = (u + 1 < t) ? mi.m[u + 1] : 0.f;
+        const float2 g = gl(u);
+        G.x = fmaf(mn, G.x, g.x);
+        G.y = fmaf(mn, G.y, g.y);
+        acc[u] = fmaf(G.x, D[u].x, fmaf(G.y, D[u].y, acc[u]));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+      if (u < t && mi.front[u]) {
+        const int q = mi.partner[u];
+        const float2 gu = gl(u), gq = gl(q), xu = xl(u), xq = xl(q);
+        acc[u] = fmaf(gu.x - gq.x, xq.x - xu.x, fmaf(gu.y - gq.y, xq.y - xu.y, acc[u]));
+      }
+    }
+  }
+}
+
+// space-to-depth gout (bf16 or fp32 records): one block per (macro row, clip).  The real channels of
+// the row's records for all frames are staged in shared memory (16-byte global loads, records re-pitched
+// to an odd number of words so that threads reading the same element of neighbouring records hit
+// different banks), then each thread owns (row parity, macro column) and walks the channels: float2 x
+// reads, 256 contiguous bytes per warp.  S2D3: 32-channel two-frame records (I3D); otherwise
+// 16-channel one-frame time-major records (ConvLSTM).
 template <int TT, typename GT, bool S2D3>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (TT <= 16 && sizeof(GT) == 2) ? 3 : 1)
 perturb_bwd_s2d_kernel(int mode, const float* __restrict__ x, const float* __restrict__ mask,
                        int mask_bstride, int c, int t, int hh, int ww, const GT* __restrict__ gout,
                        float* __restrict__ dmask) {
-  extern __shared__ __align__(16) uint8_t gsm_raw[];
-  GT* gsm = reinterpret_cast<GT*>(gsm_raw);  // [records][w2][REC]
+  extern __shared__ __align__(16) uint32_t gsm_words[];  // [records][w2][pitch]
   __shared__ MaskInfo mi;
   __shared__ float red[8 * TT];
   const int b = blockIdx.y, y = blockIdx.x, nb = gridDim.y;
   build_mask_info(&mi, mask + (size_t)b * mask_bstride, t, mode);
   constexpr int FR = S2D3 ? 2 : 1;
   constexpr int REC = S2D3 ? 32 : 16;
-  const int h2 = hh / 2, w2 = ww / 2, nrec = t / FR;
   constexpr int PER16 = 16 / sizeof(GT);
-  const int vec_per_frame = w2 * REC / PER16;
-  for (int i = threadIdx.x; i < nrec * vec_per_frame; i += blockDim.x) {
-    int r = i / vec_per_frame, v = i - r * vec_per_frame;
-    size_t row = S2D3 ? (((size_t)b * nrec + r) * h2 + y) : (((size_t)r * nb + b) * h2 + y);
-    const uint4* src = reinterpret_cast<const uint4*>(gout + row * w2 * REC) + v;
-    reinterpret_cast<uint4*>(gsm + (size_t)r * w2 * REC)[v] = *src;
+  constexpr int PERW = 4 / sizeof(GT);
+  const int h2 = hh / 2, w2 = ww / 2, nrec = t / FR;
+  const int real_words = FR * 4 * c / PERW;  // even
+  const int pitch = real_words + 1;
+  const int nvec = (real_words + 3) / 4;
+  const int per_row = w2 * nvec;
+  // the loads of a batch are all issued before the first shared-memory store waits on one of them
+  constexpr int STAGE_BATCH = 6;
+  const int stage_total = nrec * per_row;
+  for (int i0 = threadIdx.x; i0 < stage_total; i0 += STAGE_BATCH * blockDim.x) {
+    uint4 val[STAGE_BATCH];
+    int dsto[STAGE_BATCH], left[STAGE_BATCH];
+#pragma unroll
+    for (int k = 0; k < STAGE_BATCH; ++k) {
+      const int i = i0 + k * blockDim.x;
+      left[k] = 0;
+      if (i < stage_total) {
+        const int r = i / per_row, rem = i - r * per_row;
+        const int px = rem / nvec, v = rem - px * nvec;
+        const size_t row = S2D3 ? (((size_t)b * nrec + r) * h2 + y) : (((size_t)r * nb + b) * h2 + y);
+        val[k] = *reinterpret_cast<const uint4*>(gout + (row * w2 + px) * REC + v * PER16);
+        dsto[k] = (r * w2 + px) * pitch + v * 4;
+        left[k] = real_words - v * 4;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < STAGE_BATCH; ++k) {
+      if (left[k] > 0) {
+        uint32_t* dst = gsm_words + dsto[k];
+        dst[0] = val[k].x;
+        if (left[k] > 1) dst[1] = val[k].y;
+        if (left[k] > 2) dst[2] = val[k].z;
+        if (left[k] > 3) dst[3] = val[k].w;
+      }
+    }
   }
   __syncthreads();
+  const GT* gsm = reinterpret_cast<const GT*>(gsm_words);
+  const int gpitch = pitch * PERW;  // record pitch in GT elements
   float acc[TT];
 #pragma unroll
   for (int u = 0; u < TT; ++u) acc[u] = 0.f;
   const size_t hw = (size_t)hh * ww;
-  const int items = c * 2 * ww;
+  const int items = c * 2 * w2;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int wx = it % ww;
-    const int r = it / ww;
+    const int xq = it % w2;
+    const int r = it / w2;
     const int dh = r & 1, ch = r >> 1;
-    const float* xs = x + ((size_t)(b * c + ch) * t) * hw + (size_t)(2 * y + dh) * ww + wx;
-    const GT* gs = gsm + (size_t)(wx >> 1) * REC + (dh * 2 + (wx & 1)) * c + ch;
-    auto xl = [&](int u) { return xs[(size_t)u * hw]; };
+    const float* xs = x + ((size_t)(b * c + ch) * t) * hw + (size_t)(2 * y + dh) * ww + 2 * xq;
+    const GT* gs = gsm + (size_t)xq * gpitch + (dh * 2) * c + ch;
+    auto xl = [&](int u) { return *reinterpret_cast<const float2*>(xs + (size_t)u * hw); };
     auto gl = [&](int u) {
-      return S2D3 ? ivf_to_float(gs[(size_t)(u >> 1) * w2 * REC + (u & 1) * 4 * c])
-                  : ivf_to_float(gs[(size_t)u * w2 * REC]);
+      const GT* g = S2D3 ? gs + (size_t)(u >> 1) * w2 * gpitch + (u & 1) * 4 * c : gs + (size_t)u * w2 * gpitch;
+      return make_float2(ivf_to_float(g[0]), ivf_to_float(g[c]));
     };
-    item_bwd<TT>(mode, t, mi, xl, gl, acc);
+    item_bwd2<TT>(mode, t, mi, xl, gl, acc);
   }
   block_reduce_dm<TT>(acc, t, red, dmask + (size_t)b * t);
 }
@@ -312,8 +419,8 @@ template <int TT, typename GT, bool S2D3>
 int launch_bwd_s2d(ivf_handle* h, int mode, const float* x, const float* mask, int mask_bstride, int b,
                    int c, int t, int hh, int ww, const void* gout, float* dmask, cudaStream_t st) {
   constexpr int FR = S2D3 ? 2 : 1;
-  constexpr int REC = S2D3 ? 32 : 16;
-  size_t smem = (size_t)(t / FR) * (ww / 2) * REC * sizeof(GT);
+  const int real_words = FR * 4 * c / (4 / (int)sizeof(GT));
+  size_t smem = (size_t)(t / FR) * (ww / 2) * (real_words + 1) * 4;
   IVF_REQUIRE(smem <= 200 * 1024, "perturb_bwd(s2d): row tile of %zu bytes exceeds shared memory", smem);
   // opt in to large dynamic shared memory once per instantiation and device (not per launch, so a
   // captured iteration contains launches only)
@@ -325,8 +432,11 @@ int launch_bwd_s2d(ivf_handle* h, int mode, const float* x, const float* mask, i
     attr_done[dev] = true;
   }
   dim3 grid(hh / 2, b);
-  perturb_bwd_s2d_kernel<TT, GT, S2D3><<<grid, 256, smem, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
-                                                                (const GT*)gout, dmask);
+  // one thread per (row parity, macro column) when the row fits a block: the channel loop then has no
+  // ragged last pass
+  const int threads = std::min(256, std::max(64, (ww + 31) / 32 * 32));
+  perturb_bwd_s2d_kernel<TT, GT, S2D3><<<grid, threads, smem, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
+                                                                    (const GT*)gout, dmask);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -387,13 +497,18 @@ extern "C" int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const fl
   const int hw = hh * ww;
   if (out_fmt == IVF_PFMT_S2D_BF16 || out_fmt == IVF_PFMT_S2D2_BF16) {
     int items = (hh / 2) * (ww / 2);
-    dim3 grid(ivf_cdiv(items, 128), b);
-    if (out_fmt == IVF_PFMT_S2D_BF16)
-      perturb_fwd_s2d_kernel<true><<<grid, 128, 0, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
-                                                         (__nv_bfloat16*)out);
-    else
-      perturb_fwd_s2d_kernel<false><<<grid, 128, 0, st>>>(mode, x, mask, mask_bstride, c, t, hh, ww,
-                                                          (__nv_bfloat16*)out);
+    dim3 grid(ivf_cdiv(items, S2D_PX), b);
+    const bool s3 = out_fmt == IVF_PFMT_S2D_BF16;
+#define IVF_PFWD(S, CC)                                                                              \
+  perturb_fwd_s2d_kernel<S, CC><<<grid, S2D_PX * CC, 0, st>>>(mode, x, mask, mask_bstride, t, hh, ww, \
+                                                              (__nv_bfloat16*)out)
+    switch (c) {
+      case 1: if (s3) IVF_PFWD(true, 1); else IVF_PFWD(false, 1); break;
+      case 2: if (s3) IVF_PFWD(true, 2); else IVF_PFWD(false, 2); break;
+      case 3: if (s3) IVF_PFWD(true, 3); else IVF_PFWD(false, 3); break;
+      default: if (s3) IVF_PFWD(true, 4); else IVF_PFWD(false, 4); break;
+    }
+#undef IVF_PFWD
   } else {
     dim3 grid(ivf_cdiv((long long)c * hw, 256), b);
     if (out_fmt == IVF_PFMT_NCDHW_F32)

@@ -304,6 +304,55 @@ def test_maxpool_same_zero_padding(dev, dt, case):
                                atol=2e-2 if dt == torch.bfloat16 else 1e-6)
 
 
+@pytest.mark.parametrize("flags", ["plain", "accum_mask_f32", "mask_bf16"])
+@pytest.mark.parametrize("case", [((3, 3, 3), (1, 1, 1), (8, 28, 28), 32),    # branch pool, several row tiles
+                                  ((3, 3, 3), (1, 1, 1), (4, 14, 14), 24),    # 8-channel blocks (c % 16 != 0)
+                                  ((1, 3, 3), (1, 2, 2), (3, 38, 34), 64),    # stem pool: one depth per tile
+                                  ((3, 3, 3), (2, 2, 2), (8, 28, 28), 16),    # Mixed_3c -> 4b pool
+                                  ((3, 3, 3), (2, 2, 2), (5, 9, 11), 16),     # odd sizes, stride 2
+                                  ((2, 2, 2), (2, 2, 2), (4, 14, 14), 32)])   # Mixed_4f -> 5b pool
+def test_maxpool_backward_epilogues_bf16(dev, case, flags):
+    """The shared-memory scatter backward (and its gather fallback) with the fused epilogues the engine uses:
+    consumer-sum accumulation into an fp32 gradient and the ReLU'/BN' mask of the producing unit."""
+    from interpreting_video_features_b200 import ops
+    from interpreting_video_features_b200.ops import Act, same_pad
+    from oracle import i3d_oracle
+    k, s, dhw, c = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, c) + dhw, generator=g)
+    x = torch.where(torch.rand(x.shape, generator=g) < 0.4, torch.zeros_like(x), x)
+    x = x.bfloat16().float().requires_grad_()
+    y = i3d_oracle.maxpool_same(x, k, s)
+    gy = torch.randn(y.shape, generator=g).bfloat16().float()
+    (gx,) = torch.autograd.grad(y, x, gy)
+    geo = [same_pad(sz, kk, ss) for sz, kk, ss in zip(dhw, k, s)]
+    pf, od = tuple(q[0] for q in geo), tuple(q[2] for q in geo)
+    xa = to_act(x.detach().to(dev), torch.bfloat16)
+    out = Act.empty(2, *od, c, torch.bfloat16, dev)
+    am = torch.empty((out.pixels, c), dtype=torch.uint8, device=dev)
+    ops.maxpool3d_fwd(xa, out, am, k, s, pf)
+    dy = to_act(gy.to(dev), torch.bfloat16)
+    scale = torch.rand(c, generator=g) + 0.5
+    sc5 = scale.view(1, c, 1, 1, 1)
+    if flags == "plain":
+        dx = xa.like(zero=True)
+        ops.maxpool3d_bwd(dy, am, dx, k, s, pf)
+        want = gx.bfloat16().float()
+        tol = 1e-2
+    elif flags == "accum_mask_f32":
+        acc = torch.randn(x.shape, generator=g)
+        dx = to_act(acc.to(dev), torch.float32)          # in place: acc_in == dx, as the engine does
+        ops.maxpool3d_bwd(dy, am, dx, k, s, pf, acc_in=dx, mask=xa, mask_scale=scale.to(dev))
+        want = torch.where(x.detach() > 0, (gx + acc) * sc5, torch.zeros_like(gx))
+        tol = 1e-6
+    else:
+        dx = xa.like(zero=True)
+        ops.maxpool3d_bwd(dy, am, dx, k, s, pf, mask=xa, mask_scale=scale.to(dev))
+        want = torch.where(x.detach() > 0, gx * sc5, torch.zeros_like(gx)).bfloat16().float()
+        tol = 1e-2
+    torch.testing.assert_close(dx.ncdhw().float().cpu(), want, rtol=tol, atol=tol)
+
+
 # ----------------------------------------------------------------------------- head
 @pytest.mark.parametrize("softmax", [True, False])
 def test_head_forward_backward(dev, softmax):
@@ -324,6 +373,36 @@ def test_head_forward_backward(dev, softmax):
     dfa = fa.like()
     ops.head_bwd(dfa, w.to(dev), softmax, o, dout.to(dev))
     assert rel_err(dfa.ncdhw().cpu(), gf) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(1024, (2, 7, 7), 174, torch.bfloat16), (832, (1, 3, 5), 6, torch.bfloat16),
+                                  (99, (1, 2, 3), 11, torch.float32), (70, (1, 1, 1), 101, torch.bfloat16),
+                                  (1568, (1, 1, 1), 6, torch.float32)])
+def test_head_shapes_dtypes_and_mask(dev, case):
+    """Channel counts that are not a multiple of the 64-channel block (and odd ones: scalar loads), bf16
+    features, p == 1 (the ConvLSTM Linear) and the fused ReLU'/BN' mask with an fp32 gradient output."""
+    from interpreting_video_features_b200 import ops
+    c, dhw, ncls, dt = case
+    g = torch.Generator().manual_seed(7)
+    feat = (torch.rand((3, c) + dhw, generator=g) - 0.3).to(dt).float().requires_grad_()
+    w = torch.randn((ncls, c), generator=g) * 0.2
+    b = torch.randn(ncls, generator=g) * 0.1
+    out = F.softmax(F.linear(feat.mean(dim=(2, 3, 4)), w, b), dim=1)
+    dout = torch.randn(out.shape, generator=g)
+    (gf,) = torch.autograd.grad(out, feat, dout)
+    fa = to_act(feat.detach().to(dev), dt)
+    o = torch.empty((3, ncls), device=dev)
+    ops.head_fwd(fa, w.to(dev), b.to(dev), True, o)
+    assert rel_err(o.cpu(), out.detach()) < 1e-5
+    scale = torch.rand(c, generator=g) + 0.5
+    dfa = fa.like(dtype=torch.float32)
+    ops.head_bwd(dfa, w.to(dev), True, o, dout.to(dev), mask=fa, mask_scale=scale.to(dev))
+    want = torch.where(feat.detach() > 0, gf * scale.view(1, c, 1, 1, 1), torch.zeros_like(gf))
+    assert rel_err(dfa.ncdhw().cpu(), want) < 1e-4
+    if dt == torch.bfloat16:
+        dfb = fa.like()
+        ops.head_bwd(dfb, w.to(dev), True, o, dout.to(dev))
+        assert rel_err(dfb.ncdhw().float().cpu(), gf) < 1e-2
 
 
 # ----------------------------------------------------------------------------- perturb
