@@ -126,6 +126,116 @@ maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in,
   }
 }
 
+// Forward of the 3x3x3 stride-1 branch pools: a thread owns one (row, column, 8 channels) and walks the depth.
+// The 27-tap window of consecutive depths shares two of its three planes, so the thread reduces each input
+// plane ONCE to its 3x3 maximum (value + first-maximum tap, 9 taps) and combines three plane results per
+// output (2 more compares): 11 compare blocks per output instead of 27, and 9 loads instead of 27.  Scan
+// order is (depth, row, column), so "first maximum wins" composes: within a plane the first tap wins, across
+// planes a later plane must be strictly greater (or NaN) to take over - the same rule the flat scan applies.
+struct PlaneMax {
+  __nv_bfloat162 v[4];
+  uint32_t idx[4];  // 2 x 16-bit tap index within the plane
+};
+
+__device__ __forceinline__ void pool_take(__nv_bfloat162 (&best)[4], uint32_t (&bidx)[4], const __nv_bfloat162* v,
+                                          const uint32_t* vidx) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t m = __hgt2_mask(v[i], best[i]) | __hneu2_mask(v[i], v[i]);
+    best[i] = __hmax2_nan(best[i], v[i]);
+    bidx[i] = (bidx[i] & ~m) | (vidx[i] & m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_s1col_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                         uint8_t* __restrict__ argmax, int rows, int dseg) {
+  const int row = blockIdx.z * gridDim.y + blockIdx.y;  // (clip, depth segment, output row)
+  if (row >= rows) return;
+  const int cv = d.c >> 3;
+  const int el = blockIdx.x * 256 + threadIdx.x;
+  if (el >= d.ow * cv) return;
+  const int ow = el / cv, c = (el - ow * cv) << 3;
+  const int oh = row % d.oh;
+  const int t = row / d.oh;
+  const int nseg = (d.od + dseg - 1) / dseg;
+  const int seg = t % nseg, n = t / nseg;
+  const int od0 = seg * dseg, od1 = min(d.od, od0 + dseg);
+  const int zh0 = oh - d.ph, zw0 = ow - d.pw;
+  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+  const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+  // tap validity in the plane (block-uniform rows, per-thread columns)
+  bool hok[3], wok[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    hok[k] = (unsigned)(zh0 + k) < (unsigned)d.ih;
+    wok[k] = (unsigned)(zw0 + k) < (unsigned)d.iw;
+  }
+  const int plane_stride = d.ih * d.iw * d.in_ld;
+  const __nv_bfloat16* p00 = in + (long long)(((n * d.id) * d.ih + zh0) * d.iw + zw0) * d.in_ld + d.in_coff + c;
+  auto plane_max = [&](int zd, PlaneMax& pm) {
+    if ((unsigned)zd >= (unsigned)d.id) {  // a plane of padding: all zeros, first tap wins
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pm.v[i] = zero2;
+        pm.idx[i] = 0u;
+      }
+      return;
+    }
+    const __nv_bfloat16* pz = p00 + (long long)zd * plane_stride;
+    uint4 raw[9];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        raw[b * 3 + e] = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
+        if (hok[b] && wok[e]) raw[b * 3 + e] = *reinterpret_cast<const uint4*>(pz + (b * d.iw + e) * d.in_ld);
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pm.v[i] = ninf;
+      pm.idx[i] = 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const uint32_t tap2[4] = {k * 0x00010001u, k * 0x00010001u, k * 0x00010001u, k * 0x00010001u};
+      pool_take(pm.v, pm.idx, reinterpret_cast<const __nv_bfloat162*>(&raw[k]), tap2);
+    }
+  };
+  PlaneMax pa, pb, pc;
+  plane_max(od0 - d.pd, pa);
+  plane_max(od0 - d.pd + 1, pb);
+  for (int od = od0; od < od1; ++od) {
+    plane_max(od - d.pd + 2, pc);
+    __nv_bfloat162 best[4];
+    uint32_t bidx[4], ib[4], ic[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      best[i] = pa.v[i];
+      bidx[i] = pa.idx[i];
+      ib[i] = pb.idx[i] + 9u * 0x00010001u;
+      ic[i] = pc.idx[i] + 18u * 0x00010001u;
+    }
+    pool_take(best, bidx, pb.v, ib);
+    pool_take(best, bidx, pc.v, ic);
+    const int opix = ((n * d.od + od) * d.oh + oh) * d.ow + ow;
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&best[0]);
+    o.y = *reinterpret_cast<uint32_t*>(&best[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&best[2]);
+    o.w = *reinterpret_cast<uint32_t*>(&best[3]);
+    *reinterpret_cast<uint4*>(out + (long long)opix * d.out_ld + d.out_coff + c) = o;
+    if (argmax) {
+      uint2 pk;  // 2 x 16-bit indices per word -> bytes
+      pk.x = (bidx[0] & 0xffu) | ((bidx[0] >> 8) & 0xff00u) | ((bidx[1] & 0xffu) << 16) | ((bidx[1] & 0xff0000u) << 8);
+      pk.y = (bidx[2] & 0xffu) | ((bidx[2] >> 8) & 0xff00u) | ((bidx[3] & 0xffu) << 16) | ((bidx[3] & 0xff0000u) << 8);
+      *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
+    }
+    pa = pb;
+    pb = pc;
+  }
+}
+
 // Backward of the same shape: one block row per INPUT row; a thread owns 8 channels of one input pixel and
 // visits the windows that cover it.  Depth/row window indices are block-uniform; one SIMD byte compare per
 // four channels decides whether the 16-byte gradient load is needed at all.
@@ -724,6 +834,24 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
     long long total = opix * (d->c / V);
     if constexpr (sizeof(T) == 2) {
       if (fits31(d)) {  // row-block packed kernel
+        static const bool col_on = [] {
+          const char* e = getenv("IVF_POOL_S1COL");
+          return !e || atoi(e) != 0;
+        }();
+        if (col_on && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 &&
+            d->od == d->id && d->oh == d->ih && d->ow == d->iw && d->od >= 2) {
+          // depth segments: enough threads to fill the machine, at least 4 outputs per thread when split
+          long long threads_total = (long long)d->n * d->oh * d->ow * (d->c / V);
+          int segs = 1;
+          while (threads_total * segs < (long long)h->sm_count * 2048 && d->od / (segs * 2) >= 4) segs *= 2;
+          const int dseg = (d->od + segs - 1) / segs;
+          const int nseg = (d->od + dseg - 1) / dseg;
+          const int rows = d->n * nseg * d->oh;
+          maxpool_fwd_s1col_kernel<<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
+              *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows, dseg);
+          IVF_LAUNCHED(h);
+          return IVF_OK;
+        }
         const int rows = d->n * d->od * d->oh;
         IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G><<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
             *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows)));

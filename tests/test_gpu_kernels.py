@@ -331,6 +331,7 @@ def test_maxpool_backward_epilogues_bf16(dev, case, flags):
     out = Act.empty(2, *od, c, torch.bfloat16, dev)
     am = torch.empty((out.pixels, c), dtype=torch.uint8, device=dev)
     ops.maxpool3d_fwd(xa, out, am, k, s, pf)
+    assert torch.equal(out.ncdhw().cpu(), y.detach()), "max-pool forward must be exact"
     dy = to_act(gy.to(dev), torch.bfloat16)
     scale = torch.rand(c, generator=g) + 0.5
     sc5 = scale.view(1, c, 1, 1, 1)

@@ -7,8 +7,10 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 lau = []
+H = rows[hdr]
+MI = H.index("Metric Name") if "Metric Name" in H else None
 for r in rows[hdr + 1:]:
-    if len(r) >= 15:
+    if len(r) >= 15 and (MI is None or r[MI] == "gpu__time_duration.sum"):  # multi-metric lists: time rows only
         name = r[4]
         lau.append((name.split("::")[1].split("(")[0] if "::" in name else name[:30], float(r[-1]) / 1e3))
 prog = json.load(open(sys.argv[2]))

@@ -9,9 +9,10 @@ def main():
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     H = rows[hdr]
     tot, agg, per = 0.0, {}, []
+    mi = H.index("Metric Name") if "Metric Name" in H else None
     for r in rows[hdr + 1:]:
-        if len(r) < len(H):
-            continue
+        if len(r) < len(H) or (mi is not None and r[mi] != "gpu__time_duration.sum"):
+            continue  # multi-metric lists: time rows only
         name = r[4]
         short = name.split("::")[1].split("(")[0] if "::" in name else name[:40]
         t = float(r[-1].replace(",", ""))
