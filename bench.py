@@ -176,7 +176,18 @@ def conv_time_one_engine(eng):
         events.append((e0, e1))
         return r
 
+    orig_split = ops.conv1x1_split
+
+    def timed_split(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_split(*a, **k)
+        e1.record()
+        events.append((e0, e1))
+        return r
+
     ops.conv3d = timed
+    ops.conv1x1_split = timed_split
     streams, eng.use_streams = eng.use_streams, False  # serialised: one kernel at a time on one stream
     try:
         # hold the stream for ~60 ms so that every launch and event of the iteration is already queued when
@@ -188,6 +199,7 @@ def conv_time_one_engine(eng):
         torch.cuda.synchronize()
     finally:
         ops.conv3d = orig
+        ops.conv1x1_split = orig_split
         eng.use_streams = streams
     return sum(a.elapsed_time(b) for a, b in events) * 1e-3, len(events)
 

@@ -110,6 +110,23 @@ int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void
                const float* scale, const float* shift, const float* acc_in, const void* mask_y,
                const float* mask_scale, void* out, void* stream);
 
+/* 1x1x1 stride-1 bf16 convolution with two destinations and/or two sources: the Inception bottleneck trio
+ * b0 | b1a | b2a reads the same x (pt/models/I3D_doubled.py:136-146: three Unit3D calls on one input, b0's
+ * result concatenated with the branch outputs), so ONE GEMM produces all three - channels [0, split_cout)
+ * land in the concat buffer (out), the rest in the bottleneck buffer (out2) - and ONE data-gradient GEMM
+ * reduces over [dz of b0 (in) | dz of the bottlenecks (in2)].  d->cin / d->cout are the totals; in_ld/in_coff
+ * and out_ld/out_coff describe the first source / destination.  Weights: K-major [cout_pad][K] with
+ * K = round_up(split_cin, 64) + (cin - split_cin), rounded up to 16; the K pad holds zeros.  split_cout must
+ * be a multiple of 16.  Either split may be 0 (unused). */
+typedef struct ivf_conv_split {
+  int32_t split_cout, out2_ld, out2_coff;
+  int32_t split_cin, in2_ld, in2_coff;
+} ivf_conv_split;
+int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf_conv_split* sp, const void* in,
+                     const void* in2, const void* w, const float* scale, const float* shift,
+                     const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
+                     void* stream);
+
 /* ---- max-pool with TF-'same' ZERO padding (pt/models/I3D_doubled.py:8-40;
  *      nn.MaxPool2d of pt/models/convolution_lstm.py:79 with pad 0) ------------------
  * argmax: uint8 [n*od*oh*ow][c] window-scan index of the first maximum (ATen tie rule),

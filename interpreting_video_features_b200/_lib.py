@@ -28,6 +28,10 @@ class ConvDesc(C.Structure):
         "mask_coff", "flags", "dtype", "plan_kwm", "plan_mt", "plan_acc", "plan_ncta", "plan_ntiles")]
 
 
+class ConvSplit(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("split_cout", "out2_ld", "out2_coff", "split_cin", "in2_ld", "in2_coff")]
+
+
 class PoolDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n", "id", "ih", "iw", "c", "od", "oh", "ow", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph",
@@ -51,6 +55,8 @@ SIGNATURES = {
     "ivf_conv_bf16_cout_pad": (_I, [_I]),
     "ivf_conv_slab_plan": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_int)]),
     "ivf_conv3d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ivf_conv3d_split": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvSplit), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                _P]),
     "ivf_maxpool3d_fwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ivf_i3d_head_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),

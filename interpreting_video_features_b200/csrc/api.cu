@@ -79,3 +79,41 @@ extern "C" int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in,
   }
   IVF_FAIL(IVF_EINVAL, "ivf_conv3d: unknown dtype %d", d->dtype);
 }
+
+extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf_conv_split* sp, const void* in,
+                                const void* in2, const void* w, const float* scale, const float* shift,
+                                const float* acc_in, const void* mask_y, const float* mask_scale, void* out,
+                                void* out2, void* stream) {
+  IVF_REQUIRE(h && d && sp && in && w && out, "ivf_conv3d_split: null argument");
+  IVF_REQUIRE(d->dtype == IVF_BF16, "ivf_conv3d_split: bf16 only");
+  IVF_REQUIRE(d->kd == 1 && d->kh == 1 && d->kw == 1 && d->sd == 1 && d->sh == 1 && d->sw == 1 && !d->transposed &&
+                  d->pd == 0 && d->ph == 0 && d->pw == 0 && d->od == d->id && d->oh == d->ih && d->ow == d->iw,
+              "ivf_conv3d_split: 1x1x1 stride-1 convolutions only");
+  IVF_REQUIRE(d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->cin > 0 && d->cout > 0,
+              "ivf_conv3d_split: non-positive extent");
+  IVF_REQUIRE(sp->split_cout >= 0 && sp->split_cout < d->cout && sp->split_cout % 16 == 0,
+              "ivf_conv3d_split: split_cout %d must be a multiple of 16 below cout %d", sp->split_cout, d->cout);
+  IVF_REQUIRE(sp->split_cin >= 0 && sp->split_cin < d->cin && sp->split_cin % 8 == 0 &&
+                  (d->cin - sp->split_cin) % 8 == 0,
+              "ivf_conv3d_split: split_cin %d must be a multiple of 8 below cin %d", sp->split_cin, d->cin);
+  const int cout1 = sp->split_cout > 0 ? sp->split_cout : d->cout;
+  const int cin1 = sp->split_cin > 0 ? sp->split_cin : d->cin;
+  IVF_REQUIRE(d->in_ld >= d->in_coff + cin1 && d->out_ld >= d->out_coff + cout1,
+              "ivf_conv3d_split: channel slice exceeds ld");
+  if (sp->split_cout > 0)
+    IVF_REQUIRE(out2 && sp->out2_ld % 8 == 0 && sp->out2_coff % 8 == 0 &&
+                    sp->out2_ld >= sp->out2_coff + d->cout - sp->split_cout,
+                "ivf_conv3d_split: bad second destination");
+  if (sp->split_cin > 0)
+    IVF_REQUIRE(in2 && sp->in2_ld % 8 == 0 && sp->in2_coff % 8 == 0 &&
+                    sp->in2_ld >= sp->in2_coff + d->cin - sp->split_cin,
+                "ivf_conv3d_split: bad second source");
+  if ((d->flags & IVF_EP_AFFINE)) IVF_REQUIRE(scale && shift, "ivf_conv3d_split: AFFINE needs scale/shift");
+  if ((d->flags & IVF_EP_ACCUM)) IVF_REQUIRE(acc_in, "ivf_conv3d_split: ACCUM needs acc_in");
+  if ((d->flags & IVF_EP_MASK)) IVF_REQUIRE(mask_y && mask_scale, "ivf_conv3d_split: MASK needs mask_y/mask_scale");
+  if (sp->split_cout > 0)
+    IVF_REQUIRE(!(d->flags & (IVF_EP_ACCUM | IVF_EP_MASK)),
+                "ivf_conv3d_split: two destinations support the forward epilogue (affine, ReLU) only");
+  return ivf_conv3d_tc_launch(h, d, in, w, scale, shift, acc_in, mask_y, mask_scale, out, (cudaStream_t)stream, sp,
+                              in2, out2);
+}

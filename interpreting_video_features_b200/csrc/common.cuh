@@ -98,7 +98,8 @@ int ivf_conv3d_f32_launch(ivf_handle* h, const ivf_conv_desc* d, const float* in
                           cudaStream_t st);
 int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                          const float* scale, const float* shift, const float* acc_in,
-                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st);
+                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st,
+                         const ivf_conv_split* sp = nullptr, const void* in2 = nullptr, void* out2 = nullptr);
 // halo-slab tcgen05 kernel (conv_slab.cu) for the wide stride-1 'same' layers; the launcher of the im2col
 // kernel above serves everything else the bf16 path supports
 bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d);

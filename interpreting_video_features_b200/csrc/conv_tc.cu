@@ -45,6 +45,10 @@ struct TcParams {
   int tmem_cols;
   uint32_t a_stage_bytes, b_stage_bytes;  // smem pitch of the A / B part of a stage
   uint32_t tx_bytes;                      // bytes the two TMA boxes of a stage deliver
+  // split GEMMs (ivf_conv3d_split): produced channels >= split_cout go to a second tensor; channel chunks
+  // >= ksplit are gathered from a second tensor (its chunk index restarts at 0)
+  int split_cout, out2_ld, out2_coff;
+  int ksplit;
 };
 
 // KCH = channels per K stage: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
@@ -59,9 +63,10 @@ struct KTraits {
 template <int KCH>
 __global__ void __launch_bounds__(NUM_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p, const float* __restrict__ scale, const float* __restrict__ shift,
-               const float* __restrict__ acc_in, const __nv_bfloat16* __restrict__ mask_y,
-               const float* __restrict__ mask_scale, void* __restrict__ out) {
+               const __grid_constant__ CUtensorMap tmA2, const TcParams p, const float* __restrict__ scale,
+               const float* __restrict__ shift, const float* __restrict__ acc_in,
+               const __nv_bfloat16* __restrict__ mask_y, const float* __restrict__ mask_scale,
+               void* __restrict__ out, void* __restrict__ out2) {
   using KT = KTraits<KCH>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -129,8 +134,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t b_dst = a_dst + p.a_stage_bytes;
         if (leader) {
           mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-          tma_load_im2col_5d(a_dst, &tmA, &full_bar[stage], cc * KCH, cw, ch, cd, n0, (uint16_t)kw_i,
-                             (uint16_t)kh_i, (uint16_t)kd_i);
+          const bool second = p.ksplit > 0 && cc >= p.ksplit;
+          tma_load_im2col_5d(a_dst, second ? &tmA2 : &tmA, &full_bar[stage], (second ? cc - p.ksplit : cc) * KCH,
+                             cw, ch, cd, n0, (uint16_t)kw_i, (uint16_t)kh_i, (uint16_t)kd_i);
           tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_pad + cc * KCH, ntile * p.bn);
         }
         __syncwarp();
@@ -201,6 +207,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.acc_in = acc_in;
     ea.mask_y = mask_y;
     ea.out = out;
+    // second destination: its pointer is shifted so that the produced-channel index addresses it directly
+    EpilogueArgs ea2 = ea;
+    const size_t out_row2 = (size_t)m * p.out2_ld + p.out2_coff;
+    if (p.split_cout > 0)
+      ea2.out = (p.flags & IVF_EP_OUT_F32) ? (void*)(reinterpret_cast<float*>(out2) - p.split_cout)
+                                           : (void*)(reinterpret_cast<__nv_bfloat16*>(out2) - p.split_cout);
     // the first chunk's global operands are fetched while the MMAs still run
     EpiPre cur, nxt;
     epilogue_prefetch(ea, ntile * p.bn, out_row, mask_row, row_ok, cur);
@@ -211,8 +223,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, row_ok, nxt);
       uint32_t r[16];
       tmem_ld16(taddr_row + c0, r);
-      if (row_ok && nb < p.cout)
-        epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+      if (row_ok && nb < p.cout) {
+        if (p.split_cout > 0 && nb >= p.split_cout)
+          epilogue_chunk16(ea2, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row2, mask_row, cur);
+        else
+          epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+      }
       cur = nxt;
     }
   }
@@ -418,8 +434,8 @@ int check_bf16_desc(const ivf_conv_desc* d) {
 
 template <int KCH>
 int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CUtensorMap& ma,
-              const CUtensorMap& mb, int ntiles, const float* scale, const float* shift,
-              const float* acc_in, const void* mask_y, const float* mask_scale, void* out,
+              const CUtensorMap& mb, const CUtensorMap& ma2, int ntiles, const float* scale, const float* shift,
+              const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
               cudaStream_t st) {
   const int max_smem = 200 * 1024 + 2048;
   const int slot = KCH == 64 ? 0 : (KCH == 32 ? 1 : 2);
@@ -430,8 +446,8 @@ int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CU
   }
   size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024;
   dim3 grid(ivf_cdiv(p.M, TILE_M), ntiles);
-  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
-                                                       (const __nv_bfloat16*)mask_y, mask_scale, out);
+  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, ma2, p, scale, shift, acc_in,
+                                                       (const __nv_bfloat16*)mask_y, mask_scale, out, out2);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -461,13 +477,19 @@ extern "C" int ivf_conv_bf16_cout_pad(int cout) {
 
 int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                          const float* scale, const float* shift, const float* acc_in,
-                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
+                         const void* mask_y, const float* mask_scale, void* out, cudaStream_t st,
+                         const ivf_conv_split* sp, const void* in2, void* out2) {
   int rc = check_bf16_desc(d);
   if (rc) return rc;
   rc = ivf_load_driver_entry_points();
   if (rc) return rc;
-  const int kch = ivf_conv_bf16_kchunk(d->cin);
-  const int cin_pad = ivf_conv_bf16_cin_pad(d->cin);
+  const int split_cin = sp ? sp->split_cin : 0, split_cout = sp ? sp->split_cout : 0;
+  const int kch = ivf_conv_bf16_kchunk(split_cin > 0 ? 64 : d->cin);
+  // two sources: the first one's channels are padded up to whole K stages (TMA zero-fills past its extent,
+  // the packed weights hold zeros there), the second follows
+  const int ksplit = split_cin > 0 ? (split_cin + kch - 1) / kch : 0;
+  const int cin_k = split_cin > 0 ? ksplit * kch + (d->cin - split_cin) : d->cin;  // K extent per tap
+  const int cin_pad = split_cin > 0 ? (cin_k + 15) / 16 * 16 : ivf_conv_bf16_cin_pad(d->cin);
   int bn = ivf_conv_bf16_ntile(d->cout);
   const int cout_pad = ivf_conv_bf16_cout_pad(d->cout);
   int ntiles = cout_pad / bn;
@@ -496,9 +518,13 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   p.bn = bn;
   p.kh = d->kh; p.kw = d->kw;
   p.ntaps = ntaps;
-  p.cchunks = (d->cin + kch - 1) / kch;
-  p.cin = d->cin;
+  p.cchunks = (cin_k + kch - 1) / kch;
+  p.cin = cin_k;
   p.cin_pad = cin_pad;
+  p.ksplit = ksplit;
+  p.split_cout = split_cout;
+  p.out2_ld = sp ? sp->out2_ld : 0;
+  p.out2_coff = sp ? sp->out2_coff : 0;
   p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;
@@ -523,16 +549,29 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   while (cols < bn) cols <<= 1;
   p.tmem_cols = cols;
 
-  CUtensorMap ma, mb;
-  rc = get_map_a(h, d, in, kch, &ma);
-  if (rc) return rc;
+  CUtensorMap ma, mb, ma2;
+  if (split_cin > 0) {
+    ivf_conv_desc d1 = *d, d2 = *d;
+    d1.cin = split_cin;
+    d2.cin = d->cin - split_cin;
+    d2.in_ld = sp->in2_ld;
+    d2.in_coff = sp->in2_coff;
+    rc = get_map_a(h, &d1, in, kch, &ma);
+    if (rc) return rc;
+    rc = get_map_a(h, &d2, in2, kch, &ma2);
+    if (rc) return rc;
+  } else {
+    rc = get_map_a(h, d, in, kch, &ma);
+    if (rc) return rc;
+    ma2 = ma;
+  }
   rc = get_map_b(h, w, ntaps * cin_pad, cout_pad, kch, bn, &mb);
   if (rc) return rc;
   if (kch == 64)
-    return launch_tc<64>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
+    return launch_tc<64>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
   if (kch == 32)
-    return launch_tc<32>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
-  return launch_tc<16>(h, d, p, ma, mb, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, st);
+    return launch_tc<32>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+  return launch_tc<16>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
 }
 
 extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0,

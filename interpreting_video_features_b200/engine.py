@@ -92,6 +92,28 @@ def pack_dgrad(w, mode):
     return _pack_bf16(w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, -1, co))
 
 
+def pack_dgrad_two_sources(w_first, w_second):
+    """Data-gradient weights of 1x1x1 units that share their input, reduced in ONE GEMM over
+    [dz of the first unit | dz of the second]: K-major [ci][K], the first unit's K padded to whole 64-channel
+    stages (ivf_conv3d_split), zeros in the padding."""
+    ci, c_first = w_first.shape[1], w_first.shape[0]
+    k1 = (c_first + 63) // 64 * 64
+    wk = w_first.new_zeros(ci, 1, k1 + w_second.shape[0])
+    wk[:, 0, :c_first] = w_first.reshape(c_first, ci).t()
+    wk[:, 0, k1:] = w_second.reshape(w_second.shape[0], ci).t()
+    return _pack_bf16(wk)
+
+
+class SplitConvOp:
+    """A 1x1x1 convolution with two destinations or two sources (ops.conv1x1_split) as a program item."""
+
+    def __init__(self, x, w, out, **kw):
+        self.x, self.w, self.out, self.kw = x, w, out, kw
+
+    def __call__(self):
+        ops.conv1x1_split(self.x, self.w, self.out, **self.kw)
+
+
 class ConvOp:
     """One convolution launch of a program, kept as data so that its tile plan can be measured (tune.py)."""
 
@@ -321,13 +343,21 @@ class I3DEngine:
         c0, c1, c2, c3, c4, c5 = (u[b].cout for b in ("b0", "b1a", "b1b", "b2a", "b2b", "b3b"))
         cout = c0 + c2 + c4 + c5
         out = new_act(x.n, x.d, x.h, x.w, cout)
-        # the two 1x1x1 bottlenecks read the same x: ONE GEMM with their output channels side by side
-        # (t12 = [t1 | t2]); backward likewise one data-gradient GEMM over the concatenated K
-        pre = "%s.b1a|b2a" % name
-        fsd = {pre + ".conv3d.weight": torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in ("b1a", "b2a")])}
+        # the 1x1x1 units that read x: b1a and b2a always share ONE GEMM (t12 = [t1 | t2]); on the tensor-core
+        # path b0 joins them (its channels go straight into the concat buffer: ivf_conv3d_split), and backward
+        # is likewise one data-gradient GEMM over the concatenated K
+        fuse_b0 = mode == "bf16" and os.environ.get("IVF_FUSE_B0", "1") != "0"
+        group = ("b0", "b1a", "b2a") if fuse_b0 else ("b1a", "b2a")
+        pre = "%s.%s" % (name, "|".join(group))
+        fsd = {pre + ".conv3d.weight": torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in group])}
         for k in ("weight", "bias", "running_mean", "running_var"):
-            fsd["%s.bn.%s" % (pre, k)] = torch.cat([sd["%s.%s.bn.%s" % (name, b, k)] for b in ("b1a", "b2a")])
+            fsd["%s.bn.%s" % (pre, k)] = torch.cat([sd["%s.%s.bn.%s" % (name, b, k)] for b in group])
         fused = Unit(fsd, pre, (1, 1, 1), mode, dev)
+        if fuse_b0:
+            w12 = torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in ("b1a", "b2a")])
+            fused.w_dgrad = pack_dgrad_two_sources(
+                sd["%s.b0.conv3d.weight" % name].detach().to(device=dev, dtype=torch.float32),
+                w12.detach().to(device=dev, dtype=torch.float32))
         t12 = new_act(x.n, x.d, x.h, x.w, c1 + c3)
         t1, t2 = t12.slice(0, c1), t12.slice(c1, c3)
         t3 = new_act(x.n, x.d, x.h, x.w, x.c)
@@ -339,18 +369,24 @@ class I3DEngine:
         self.fwd_ops.append((3, lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads)))
         add_unit_fwd(u["b3b"], t3, out.slice(c0 + c2 + c4, c5))
         self._lane = 0
-        add_unit_fwd(fused, x, t12)
+        if fuse_b0:
+            self.fwd_ops.append((0, SplitConvOp(x, fused.w_fwd, out.slice(0, c0), out2=t12, flags=_lib.EP_RELU,
+                                                scale=fused.scale, shift=fused.shift)))
+        else:
+            add_unit_fwd(fused, x, t12)
         self.fwd_ops.append(("fork", (1, 2)))  # the 3x3x3 branches start once their bottlenecks exist
         self._lane = 1
         add_unit_fwd(u["b1b"], t1, out.slice(c0, c2))
         self._lane = 2
         add_unit_fwd(u["b2b"], t2, out.slice(c0 + c2, c4))
         self._lane = 0
-        add_unit_fwd(u["b0"], x, out.slice(0, c0))
+        if not fuse_b0:
+            add_unit_fwd(u["b0"], x, out.slice(0, c0))
         self.fwd_ops.append(("join",))
         scale = torch.cat([u["b0"].scale, u["b1b"].scale, u["b2b"].scale, u["b3b"].scale]).contiguous()
         g_t12 = t12.like()
-        return dict(kind="inception", name=name, units=u, fused=fused, x=x, out=out, scale=scale, gout=out.like(),
+        return dict(kind="inception", name=name, units=u, fused=fused, fuse_b0=fuse_b0, x=x, out=out, scale=scale,
+                    gout=out.like(),
                     t1=t1, t2=t2, t3=t3, t12=t12, argmax=am, pads=pads, g_t12=g_t12,
                     g_t1=g_t12.slice(0, c1), g_t2=g_t12.slice(c1, c3), g_t3=t3.like(),
                     g_x32=x.like(torch.float32))
@@ -363,6 +399,7 @@ class I3DEngine:
         # place once b0' is done).  After the join ONE data-gradient GEMM over the concatenated K of the two bottlenecks adds
         # the sum and applies the producer's ReLU'/BN'.  (Summation order per element is fixed: b0, pool, GEMM.)
         acc = st["g_x32"]
+        fuse_b0 = st["fuse_b0"]
         self.bwd_ops.append(("fork",))
         self._lane = 1
         add_unit_bwd(u["b1b"], dz.slice(c0, c2), st["t1"], st["g_t1"], mask=st["t1"], mask_scale=u["b1a"].scale)
@@ -370,6 +407,15 @@ class I3DEngine:
         add_unit_bwd(u["b2b"], dz.slice(c0 + c2, c4), st["t2"], st["g_t2"], mask=st["t2"], mask_scale=u["b2a"].scale)
         self._lane = 3
         add_unit_bwd(u["b3b"], dz.slice(c0 + c2 + c4, c5), st["t3"], st["g_t3"])
+        if fuse_b0:
+            # pool' starts the fp32 sum; b0' is part of the data-gradient GEMM after the join (K = [dz of b0 | g_t12])
+            self.bwd_ops.append((3, lambda: ops.maxpool3d_bwd(st["g_t3"], st["argmax"], acc, (3, 3, 3), (1, 1, 1),
+                                                              st["pads"])))
+            self.bwd_ops.append(("join",))
+            self._lane = 0
+            self.bwd_ops.append((0, SplitConvOp(dz.slice(0, c0), st["fused"].w_dgrad, g_in, x2=st["g_t12"],
+                                                acc_in=acc, mask=mask, mask_scale=mscale)))
+            return
         self._lane = 0
         add_unit_bwd(u["b0"], dz.slice(0, c0), x, acc)
         self.bwd_ops.append(("sync", 0, 3))  # pool' adds into the sum b0' started

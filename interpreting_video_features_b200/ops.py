@@ -100,6 +100,27 @@ def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None
     return out
 
 
+def conv1x1_split(x, w, out, x2=None, out2=None, flags=0, scale=None, shift=None, acc_in=None, mask=None,
+                  mask_scale=None):
+    """1x1x1 bf16 convolution with two sources (channels of x then of x2) and/or two destinations (produced
+    channels fill out, then out2); see ivf_conv3d_split.  Totals are taken from the Acts."""
+    cin = x.c + (x2.c if x2 is not None else 0)
+    cout = out.c + (out2.c if out2 is not None else 0)
+    d = conv_desc(x, out, (1, 1, 1), (1, 1, 1), (0, 0, 0), flags, scale, acc_in, mask, 0, cin, cout)
+    sp = _lib.ConvSplit()
+    if out2 is not None:
+        sp.split_cout, sp.out2_ld, sp.out2_coff = out.c, out2.ld, out2.coff
+    if x2 is not None:
+        sp.split_cin, sp.in2_ld, sp.in2_coff = x.c, x2.ld, x2.coff
+    check(_lib.load().ivf_conv3d_split(_lib.handle(x.buf.device), C.byref(d), C.byref(sp), ptr(x.buf),
+                                       ptr(x2.buf if x2 is not None else None), ptr(w), ptr(scale), ptr(shift),
+                                       ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
+                                       ptr(mask.buf if mask is not None else None), ptr(mask_scale), ptr(out.buf),
+                                       ptr(out2.buf if out2 is not None else None), _lib.stream_ptr()),
+          "ivf_conv3d_split")
+    return out
+
+
 def _pool_desc(x, out, kernel, stride, pad_front, mask=None, flags=0):
     d = PoolDesc()
     d.n, d.id, d.ih, d.iw, d.c = x.n, x.d, x.h, x.w, x.c

@@ -273,6 +273,53 @@ def test_conv_bf16_space_to_depth_stem(dev, hw):
     assert rel_err(got, gx) < 1e-2
 
 
+@pytest.mark.parametrize("case", [(192, (64, 96 + 16), (2, 6, 7)), (480, (192, 96 + 16), (3, 5, 5)),
+                                  (528, (112, 144 + 32), (1, 14, 14)), (832, (384, 192 + 48), (2, 7, 7)),
+                                  (528, (160, 112 + 24), (2, 9, 9))])
+def test_conv1x1_two_destinations_and_two_sources(dev, case):
+    """ivf_conv3d_split, as the Inception modules use it: forward b0|b1a|b2a in one GEMM with b0's channels going
+    to a slice of the concat buffer and the bottlenecks to their own buffer; backward one data-gradient GEMM
+    over [dz of b0 (a slice of the concat gradient) | dz of the bottlenecks] with the consumer sum and the
+    ReLU'/BN' mask.  160 and 112 are not multiples of the 64-channel K stage (zero-filled tail)."""
+    from interpreting_video_features_b200 import engine, ops
+    from interpreting_video_features_b200.ops import Act
+    cin, (c0, c12), dhw = case
+    n = 2
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn((n, cin) + dhw, generator=g)).bfloat16().float()
+    w0 = torch.randn((c0, cin, 1, 1, 1), generator=g) * 0.05
+    w12 = torch.randn((c12, cin, 1, 1, 1), generator=g) * 0.05
+    wall = torch.cat([w0, w12])
+    scale = torch.rand(c0 + c12, generator=g) + 0.5
+    shift = torch.randn(c0 + c12, generator=g) * 0.1
+    wb = wall.bfloat16().float()
+    y = F.relu(F.conv3d(x, wb) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    xa = to_act(x.to(dev), torch.bfloat16)
+    ctot = c0 + 40  # concat buffer: b0's channels first, others behind
+    concat = Act.empty(n, *dhw, ctot, torch.bfloat16, dev, zero=True)
+    t12 = Act.empty(n, *dhw, c12, torch.bfloat16, dev)
+    ops.conv1x1_split(xa, engine.pack_fwd(wall.to(dev), "bf16"), concat.slice(0, c0), out2=t12,
+                      flags=ops.EP_RELU, scale=scale.to(dev), shift=shift.to(dev))
+    assert rel_err(concat.ncdhw().cpu()[:, :c0], y[:, :c0]) < 1e-2
+    assert rel_err(t12.ncdhw().cpu(), y[:, c0:]) < 1e-2
+    assert float(concat.ncdhw()[:, c0:].abs().max()) == 0.0, "channels behind b0's slice must stay untouched"
+    # backward: g_x = mask(acc + W0^T dz0 + W12^T dz12)
+    dz0 = torch.randn((n, c0) + dhw, generator=g).bfloat16().float()
+    dz12 = torch.randn((n, c12) + dhw, generator=g).bfloat16().float()
+    acc = torch.randn((n, cin) + dhw, generator=g)
+    mscale = torch.rand(cin, generator=g) + 0.5
+    want = (F.conv_transpose3d(dz0, w0.bfloat16().float()) + F.conv_transpose3d(dz12, w12.bfloat16().float()) + acc)
+    want = torch.where(x > 0, want * mscale.view(1, -1, 1, 1, 1), torch.zeros_like(want))
+    gconcat = Act.empty(n, *dhw, ctot, torch.bfloat16, dev, zero=True)
+    gconcat.tensor()[..., :c0] = dz0.permute(0, 2, 3, 4, 1).to(dev).bfloat16()
+    gconcat.tensor()[..., c0:] = 7.0  # the other branches' gradients: must not leak into the reduction
+    wd = engine.pack_dgrad_two_sources(w0.to(dev), w12.to(dev))
+    gx = xa.like()
+    ops.conv1x1_split(gconcat.slice(0, c0), wd, gx, x2=to_act(dz12.to(dev), torch.bfloat16),
+                      acc_in=to_act(acc.to(dev), torch.float32), mask=xa, mask_scale=mscale.to(dev))
+    assert rel_err(gx.ncdhw().cpu(), want) < 1e-2
+
+
 # ----------------------------------------------------------------------------- max-pool
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("case", [((1, 3, 3), (1, 2, 2), (4, 13, 12), 64), ((3, 3, 3), (2, 2, 2), (5, 9, 10), 40),
