@@ -127,6 +127,10 @@ int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf_conv_split
                      const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
                      void* stream);
 
+/* Diagnostic: copy the head of the handle's scratch buffer to the host after a device synchronise (kernel
+ * phase traces written when IVF_TC_TRACE=1). */
+int ivf_debug_read_scratch(ivf_handle* h, void* dst, size_t bytes);
+
 /* ---- max-pool with TF-'same' ZERO padding (pt/models/I3D_doubled.py:8-40;
  *      nn.MaxPool2d of pt/models/convolution_lstm.py:79 with pad 0) ------------------
  * argmax: uint8 [n*od*oh*ow][c] window-scan index of the first maximum (ATen tie rule),

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ivf_conv3d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ivf_conv3d_split": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvSplit), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _P]),
+    "ivf_debug_read_scratch": (_I, [_P, _P, C.c_size_t]),
     "ivf_maxpool3d_fwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ivf_i3d_head_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),

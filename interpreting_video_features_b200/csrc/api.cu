@@ -117,3 +117,12 @@ extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf
   return ivf_conv3d_tc_launch(h, d, in, w, scale, shift, acc_in, mask_y, mask_scale, out, (cudaStream_t)stream, sp,
                               in2, out2);
 }
+
+// Diagnostic: copy the first `bytes` of the handle's scratch buffer to the host (kernel traces written under
+// IVF_TC_TRACE=1).  Synchronises the device.
+extern "C" int ivf_debug_read_scratch(ivf_handle* h, void* dst, size_t bytes) {
+  IVF_REQUIRE(h && dst && bytes <= h->scratch_bytes, "ivf_debug_read_scratch: bad argument");
+  IVF_CUDA(cudaDeviceSynchronize());
+  IVF_CUDA(cudaMemcpy(dst, h->scratch, bytes, cudaMemcpyDeviceToHost));
+  return IVF_OK;
+}

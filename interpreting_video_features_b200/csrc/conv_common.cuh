@@ -216,7 +216,27 @@ struct EpilogueArgs {
   const float* acc_in;
   const __nv_bfloat16* mask_y;
   void* out;
+  // != 0: shared-memory address of this lane's 32-byte row in a staging box; the 16 bf16 results of a chunk
+  // go there and the warp sends the box with one TMA store (rows and channels past the tensor are clipped by
+  // the tensor map, so no validity tests apply)
+  uint32_t stage_smem = 0;
 };
+
+// TMA store of a staged box: [tensor map, {channel, row}] <- shared memory; bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // Global operands of one full 16-channel chunk's epilogue (fp32 consumer sum, bf16 ReLU mask), fetched one
 // chunk AHEAD of their use so that their latency (~1 us) overlaps the TMEM loads and math of the previous
@@ -298,7 +318,20 @@ __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const ui
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + out_row + nb;
-    if (full) {
+    if (e.stage_smem) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.stage_smem), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                   "r"(pk[3])
+                   : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.stage_smem + 16u), "r"(pk[4]), "r"(pk[5]),
+                   "r"(pk[6]), "r"(pk[7])
+                   : "memory");
+    } else if (full) {
       uint32_t pk[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {

@@ -25,7 +25,13 @@ namespace {
 using namespace ivf_tc;
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, then EPI_WARPS epilogue warps: four TMEM lane quarters (warp % 4)
+// x EPI_GROUPS column groups that take the 16-channel chunks round-robin.  The epilogue is a latency chain per
+// warp (TMEM load -> a few dependent ALU ops -> store); with one warp per scheduler it ran at ~0.2 IPC and was
+// the whole kernel for the 1x1x1 layers, so it gets four warps per scheduler.
+constexpr int EPI_GROUPS = 3;
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_STAGES = 12;
 
 struct TcParams {
@@ -49,7 +55,21 @@ struct TcParams {
   // >= ksplit are gathered from a second tensor (its chunk index restarts at 0)
   int split_cout, out2_ld, out2_coff;
   int ksplit;
+  int mtiles, grid_x;        // 128-pixel tiles; a CTA walks blockIdx.x, blockIdx.x + gridDim.x, ...
+  int acc_stages, acc_cols;  // TMEM accumulators (1|2) and the column pitch between them
+  int tma_store;             // bf16 results staged in shared memory and written by TMA stores
+  long long* trace;          // IVF_TC_TRACE=1: globaltimer stamps of CTA (0, 0) (diagnostic), else null
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(slot)                                                                   \
+  do {                                                                                   \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) p.trace[slot] = gtime(); \
+  } while (0)
 
 // KCH = channels per K stage: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B
 template <int KCH>
@@ -60,10 +80,15 @@ struct KTraits {
   static constexpr int ksteps = KCH / 16;
 };
 
+// Persistent over M tiles: CTA (x, ntile) walks the 128-pixel tiles x, x + gridDim.x, ... of its N tile.  The
+// accumulator is double-buffered in TMEM whenever two buffers fit (p.acc_stages), so the epilogue of one tile -
+// for the 1x1x1 layers, a handful of K steps per tile, the epilogue IS most of the work - runs while the
+// producer and the MMA issuer are already on the next tile; the shared-memory ring keeps running across tiles.
 template <int KCH>
 __global__ void __launch_bounds__(NUM_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const TcParams p, const float* __restrict__ scale,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ CUtensorMap tmO2, const TcParams p, const float* __restrict__ scale,
                const float* __restrict__ shift, const float* __restrict__ acc_in,
                const __nv_bfloat16* __restrict__ mask_y, const float* __restrict__ mask_scale,
                void* __restrict__ out, void* __restrict__ out2) {
@@ -71,13 +96,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+  // bf16 results leave through TMA stores: per epilogue warp two boxes of 32 rows x 16 channels
+  __shared__ __align__(128) uint8_t stage_buf[EPI_WARPS][2][32 * 32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TILE_M;
   const int ntile = blockIdx.y;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
@@ -88,7 +115,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -101,7 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp >= 2) {
     // per-channel epilogue vectors of this N tile
-    for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
+    for (int i = threadIdx.x - 64; i < p.bn; i += 32 * EPI_WARPS) {
       int n = ntile * p.bn + i;
       bool ok = n < p.cout;
       s_scale[i] = (ok && (p.flags & IVF_EP_AFFINE)) ? scale[n] : 1.f;
@@ -113,11 +143,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = tmem_base_slot;
+  if (warp == 1) TC_TRACE(2);  // set-up done
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-    {
-      const bool leader = elect_one();
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int tcount = 0;
+    TC_TRACE(0);
+    for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x, ++tcount) {
+      if (tcount < 4) TC_TRACE(8 + tcount * 8 + 0);  // producer starts tile
+      const int m0 = mt * TILE_M;
       int ow0 = m0 % p.ow;
       int t = m0 / p.ow;
       int oh0 = t % p.oh;
@@ -125,8 +162,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int od0 = t % p.od;
       int n0 = t / p.od;
       const int cw = ow0 * p.sw - p.pw, ch = oh0 * p.sh - p.ph, cd = od0 * p.sd - p.pd;
-      int stage = 0;
-      uint32_t phase = 0;
       int cc = 0, kw_i = 0, kh_i = 0, kd_i = 0, tap = 0;
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -159,15 +194,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    {
-      const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(TILE_M, p.bn);
-      const uint32_t desc_hi = smem_desc_hi(KT::sbo, KT::layout);
-      const int tail_ksteps = (p.cin - (p.cchunks - 1) * KCH + 15) / 16;
-      int stage = 0, cc = 0;
-      uint32_t phase = 0;
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(TILE_M, p.bn);
+    const uint32_t desc_hi = smem_desc_hi(KT::sbo, KT::layout);
+    const int tail_ksteps = (p.cin - (p.cchunks - 1) * KCH + 15) / 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // the epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.acc_cols);
+      int cc = 0;
+      if (tcount < 4) TC_TRACE(8 + tcount * 8 + 1);  // MMA warp has the accumulator
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full_bar[stage], phase);
+        if (tcount < 4 && it == 0) TC_TRACE(8 + tcount * 8 + 2);  // first operands landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_lo = smem_desc_lo(smem_base + stage * stage_bytes);
         const uint32_t b_lo = smem_desc_lo(smem_base + stage * stage_bytes + p.a_stage_bytes);
@@ -175,10 +219,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (cc + 1 < p.cchunks || tail_ksteps == KT::ksteps) {
 #pragma unroll
             for (int k = 0; k < KT::ksteps; ++k)
-              umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
           } else {  // last channel chunk of a tap: only the K steps that hold real channels
             for (int k = 0; k < tail_ksteps; ++k)
-              umma_bf16_lo(tmem_acc, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
@@ -189,18 +233,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1u;
         }
       }
-      if (leader) umma_commit(&tmem_full_bar);  // accumulator complete
+      if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       __syncwarp();
+      if (tcount < 4) TC_TRACE(8 + tcount * 8 + 3);  // all MMAs issued
+      ++tcount;
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int cgrp = (warp - 2) >> 2;  // column group: chunks cgrp, cgrp + EPI_GROUPS, ...
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    const uint32_t taddr_row = tmem_acc + ((uint32_t)(q * 32) << 16);
-    const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
-    const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
     EpilogueArgs ea;
     ea.cout = p.cout;
     ea.flags = p.flags;
@@ -209,32 +255,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ea.out = out;
     // second destination: its pointer is shifted so that the produced-channel index addresses it directly
     EpilogueArgs ea2 = ea;
-    const size_t out_row2 = (size_t)m * p.out2_ld + p.out2_coff;
     if (p.split_cout > 0)
       ea2.out = (p.flags & IVF_EP_OUT_F32) ? (void*)(reinterpret_cast<float*>(out2) - p.split_cout)
                                            : (void*)(reinterpret_cast<__nv_bfloat16*>(out2) - p.split_cout);
-    // the first chunk's global operands are fetched while the MMAs still run
-    EpiPre cur, nxt;
-    epilogue_prefetch(ea, ntile * p.bn, out_row, mask_row, row_ok, cur);
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < p.bn; c0 += 16) {
-      const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
-      if (c0 + 16 < p.bn) epilogue_prefetch(ea, nb + 16, out_row, mask_row, row_ok, nxt);
-      uint32_t r[16];
-      tmem_ld16(taddr_row + c0, r);
-      if (row_ok && nb < p.cout) {
-        if (p.split_cout > 0 && nb >= p.split_cout)
-          epilogue_chunk16(ea2, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row2, mask_row, cur);
-        else
-          epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    int sbuf = 0;
+    for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+      const int m = mt * TILE_M + row;
+      const bool row_ok = m < p.M;
+      const uint32_t taddr_row = tmem_acc + (uint32_t)(acc * p.acc_cols) + ((uint32_t)(q * 32) << 16);
+      const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
+      const size_t out_row2 = (size_t)m * p.out2_ld + p.out2_coff;
+      const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
+      // the first chunk's global operands are fetched while the MMAs still run
+      EpiPre cur;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 4);  // accumulator complete
+      for (int c0 = 16 * cgrp; c0 < p.bn; c0 += 16 * EPI_GROUPS) {
+        const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
+        // global operands of the chunk are requested before the TMEM load; the other warps of the scheduler
+        // cover the latency
+        epilogue_prefetch(ea, nb, out_row, mask_row, row_ok, cur);
+        uint32_t r[16];
+        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 0);
+        tmem_ld16(taddr_row + c0, r);
+        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 1);
+        if (p.tma_store) {
+          if (nb < p.cout) {  // warp-uniform
+            const uint32_t box = smem_u32(&stage_buf[warp - 2][sbuf][0]);
+            if (lane == 0) tma_store_wait_read<1>();  // the store that last read this box has finished reading
+            __syncwarp();
+            const bool second = p.split_cout > 0 && nb >= p.split_cout;
+            if (row_ok) {
+              ea.stage_smem = ea2.stage_smem = box + (uint32_t)lane * 32u;
+              epilogue_chunk16(second ? ea2 : ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(second ? &tmO2 : &tmO, box, second ? nb - p.split_cout : nb, mt * TILE_M + q * 32);
+              tma_store_commit();
+            }
+            sbuf ^= 1;
+          }
+        } else if (row_ok && nb < p.cout) {
+          if (p.split_cout > 0 && nb >= p.split_cout)
+            epilogue_chunk16(ea2, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row2, mask_row, cur);
+          else
+            epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+        }
+        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 2);
       }
-      cur = nxt;
+      // this warp's TMEM reads are complete (tmem_ld16 waits): hand the accumulator back
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 5);  // epilogue of the tile done
+      ++tcount;
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();  // the boxes are read until the stores complete
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 0) TC_TRACE(1);
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
@@ -417,6 +508,46 @@ int get_map_b(ivf_handle* h, const void* w, int ktot, int cout_pad, int kch, int
   return IVF_OK;
 }
 
+// Output tensor map for the TMA-store epilogue: [rows = pixels][channels of the destination slice], boxes of
+// 32 rows x 16 channels (one epilogue warp's chunk); writes past either extent are clipped.
+int get_map_out(ivf_handle* h, const void* base, int coff, int ld, int channels, long long rows, CUtensorMap* out) {
+  struct {
+    const void* base;
+    int coff, ld, channels;
+    long long rows;
+  } key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.coff = coff; key.ld = ld; key.channels = channels; key.rows = rows;
+  std::string kb = key_bytes('O', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  const char* p0 = reinterpret_cast<const char*>(base) + (size_t)coff * 2;
+  IVF_REQUIRE((reinterpret_cast<uintptr_t>(p0) & 15) == 0 && ld % 8 == 0, "conv(bf16): output slice not 16-B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = ivf_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p0, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(output) failed (%d): channels %d ld %d rows %lld", (int)r, channels,
+             ld, rows);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
 int check_bf16_desc(const ivf_conv_desc* d) {
   IVF_REQUIRE(!d->transposed,
               "conv(bf16): transposed gather is fp32-only; present strided layers space-to-depth");
@@ -434,10 +565,11 @@ int check_bf16_desc(const ivf_conv_desc* d) {
 
 template <int KCH>
 int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CUtensorMap& ma,
-              const CUtensorMap& mb, const CUtensorMap& ma2, int ntiles, const float* scale, const float* shift,
+              const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mo, const CUtensorMap& mo2,
+              int ntiles, const float* scale, const float* shift,
               const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
               cudaStream_t st) {
-  const int max_smem = 200 * 1024 + 2048;
+  const int max_smem = 196 * 1024;  // 227 KB minus the static part (barriers, epilogue vectors, TMA-store boxes)
   const int slot = KCH == 64 ? 0 : (KCH == 32 ? 1 : 2);
   if (!h->tc_attr_set[slot]) {
     IVF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -445,8 +577,8 @@ int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CU
     h->tc_attr_set[slot] = true;
   }
   size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024;
-  dim3 grid(ivf_cdiv(p.M, TILE_M), ntiles);
-  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, ma2, p, scale, shift, acc_in,
+  dim3 grid(p.grid_x, ntiles);
+  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, ma2, mo, mo2, p, scale, shift, acc_in,
                                                        (const __nv_bfloat16*)mask_y, mask_scale, out, out2);
   IVF_LAUNCHED(h);
   return IVF_OK;
@@ -501,7 +633,7 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   // (Rows of the weight box beyond cout_pad are TMA zero fill; the epilogue stores only real channels.)
   const int mtiles = ivf_cdiv(M, TILE_M);
   if (mtiles * ntiles < h->sm_count) {
-    int want = ivf_cdiv(h->sm_count, mtiles);
+    int want = std::max(1, h->sm_count / mtiles);  // one CTA per SM: stay within one wave
     int bn2 = (ivf_cdiv(d->cout, want) + 15) / 16 * 16;
     if (bn2 < 32) bn2 = 32;
     if (bn2 < bn) {
@@ -536,18 +668,42 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   p.tx_bytes = p.a_stage_bytes + bbytes;
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   int kiters = ntaps * p.cchunks;
-  // two CTAs per SM (100 KB each) when the grid has several waves; one deep pipeline otherwise
-  const uint32_t budget = ((long long)mtiles * ntiles > 2ll * h->sm_count ? 100u : 200u) * 1024u;
-  int stages = (int)(budget / stage_bytes);
-  if (stages < 4) stages = 4;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  while ((size_t)stages * stage_bytes > 200u * 1024u) --stages;
-  if (stages > kiters) stages = kiters;
-  if (stages < 1) stages = 1;
-  p.stages = stages;
+  // TMEM and residency: an accumulator takes the next power of two >= bn columns.  Up to 128 columns two
+  // CTAs share an SM with two accumulators each (4 x 128 = all 512 columns); wider tiles get one CTA per SM
+  // with two accumulators and the whole shared memory as pipeline.  A CTA walks ceil(mtiles / capacity) tiles.
   int cols = 32;
   while (cols < bn) cols <<= 1;
-  p.tmem_cols = cols;
+  static const int acc_env = [] { const char* e = getenv("IVF_TC_ACC"); return e ? atoi(e) : 2; }();
+  static const int cta_env = [] { const char* e = getenv("IVF_TC_CTAS"); return e ? atoi(e) : 0; }();
+  int ctas_per_sm = 1;  // 18 warps and the whole shared memory per CTA
+  if (cta_env > 0) ctas_per_sm = cta_env;
+  int acc_stages = acc_env >= 2 ? 2 : 1;
+  while (acc_stages > 1 && acc_stages * cols * ctas_per_sm > 512) --acc_stages;
+  while (ctas_per_sm > 1 && acc_stages * cols * ctas_per_sm > 512) --ctas_per_sm;
+  int capacity = ctas_per_sm * h->sm_count / ntiles;
+  if (capacity < 1) capacity = 1;
+  int grid_x = mtiles;
+  if (mtiles > capacity) {
+    const int per_cta = ivf_cdiv(mtiles, capacity);
+    grid_x = ivf_cdiv(mtiles, per_cta);
+  } else {
+    acc_stages = 1;  // one tile per CTA: nothing to overlap
+  }
+  p.mtiles = mtiles;
+  p.acc_stages = acc_stages;
+  p.acc_cols = cols;
+  p.tmem_cols = acc_stages * cols;
+  const uint32_t budget = (ctas_per_sm >= 2 && (long long)grid_x * ntiles > h->sm_count ? 100u : 190u) * 1024u;
+  int stages = (int)(budget / stage_bytes);
+  if (stages < 2) stages = 2;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  while ((size_t)stages * stage_bytes > 190u * 1024u) --stages;
+  if (stages > kiters * ivf_cdiv(mtiles, grid_x)) stages = kiters * ivf_cdiv(mtiles, grid_x);
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  p.grid_x = grid_x;
+  static const bool trace_env = [] { const char* e = getenv("IVF_TC_TRACE"); return e && atoi(e) != 0; }();
+  p.trace = trace_env ? reinterpret_cast<long long*>(h->scratch) : nullptr;
 
   CUtensorMap ma, mb, ma2;
   if (split_cin > 0) {
@@ -567,11 +723,25 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   }
   rc = get_map_b(h, w, ntaps * cin_pad, cout_pad, kch, bn, &mb);
   if (rc) return rc;
+  // bf16 results go out through TMA stores (a thread holds one output ROW, and row-scattered 16-byte stores
+  // measured ~0.2 us per warp instruction - the epilogue, not the MMAs, bounded the 1x1x1 layers)
+  static const bool tma_store_env = [] { const char* e = getenv("IVF_TC_TMA_STORE"); return !e || atoi(e) != 0; }();
+  CUtensorMap mo = ma, mo2 = ma;
+  p.tma_store = (tma_store_env && !(d->flags & IVF_EP_OUT_F32)) ? 1 : 0;
+  if (p.tma_store) {
+    rc = get_map_out(h, out, d->out_coff, d->out_ld, split_cout > 0 ? split_cout : d->cout, M, &mo);
+    if (rc) return rc;
+    mo2 = mo;
+    if (split_cout > 0) {
+      rc = get_map_out(h, out2, sp->out2_coff, sp->out2_ld, d->cout - split_cout, M, &mo2);
+      if (rc) return rc;
+    }
+  }
   if (kch == 64)
-    return launch_tc<64>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+    return launch_tc<64>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
   if (kch == 32)
-    return launch_tc<32>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
-  return launch_tc<16>(h, d, p, ma, mb, ma2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+    return launch_tc<32>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+  return launch_tc<16>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
 }
 
 extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0,
