@@ -41,8 +41,15 @@ namespace {
 
 using namespace ivf_tc;
 
-constexpr int SLAB_THREADS = 352;  // 3 role warps + 8 epilogue warps (two per TMEM lane quarter, half the columns each)
-constexpr int EPI_THREADS = 256;
+// 3 role warps + SLAB_EPI_GROUPS epilogue warps per TMEM lane quarter, each group a contiguous share of the tile's
+// 16-column chunks.  The epilogue is a dependent chain per warp (TMEM load, shuffles of the kw-merge, a few ALU
+// ops, stores); it needs several warps per scheduler to run at speed (measured on the 1x1x1 kernel: one warp
+// per scheduler ran at ~0.2 IPC), and the kw-merged plans are bounded by it.
+#ifndef SLAB_EPI_GROUPS
+#define SLAB_EPI_GROUPS 3
+#endif
+constexpr int EPI_THREADS = 128 * SLAB_EPI_GROUPS;
+constexpr int SLAB_THREADS = 96 + EPI_THREADS;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr uint32_t SLAB_SMEM_BUDGET = 208u * 1024u;
@@ -126,7 +133,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 8 * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(&t_empty[s], 4 * SLAB_EPI_GROUPS * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -336,7 +343,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int chalf = (warp - 3) >> 2;  // which half of the tile's 16-column chunks this warp handles
+    const int cgrp = (warp - 3) >> 2;  // which share of the tile's 16-column chunks this warp handles
     EpilogueArgs ea;
     ea.cout = p.cout;
     ea.flags = p.flags;
@@ -361,19 +368,18 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
                                (uint32_t)((acc * p.mt + m) * p.slot);
         // this warp's chunks: [c_lo, c_hi)
-        const int nchunks = p.bn >> 4, c_lo = ((nchunks + 1) / 2) * 16 * chalf;
-        const int c_hi = chalf == 0 ? ((nchunks + 1) / 2) * 16 : p.bn;
-        EpiPre cur, nxt;
-        epilogue_prefetch(ea, t.nt * p.bn + c_lo, out_row, mask_row, ok && c_lo < c_hi, cur);
+        const int nchunks = p.bn >> 4;
+        const int c_lo = 16 * (nchunks * cgrp / SLAB_EPI_GROUPS), c_hi = 16 * (nchunks * (cgrp + 1) / SLAB_EPI_GROUPS);
+        EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
+                     // the scheduler cover the latency
         if (p.kwm == 1) {
           for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             const int nb = t.nt * p.bn + c0;
-            if (c0 + 16 < c_hi) epilogue_prefetch(ea, nb + 16, out_row, mask_row, ok, nxt);
+            epilogue_prefetch(ea, nb, out_row, mask_row, ok, cur);
             uint32_t rr[16];
             tmem_ld16(taddr + c0, rr);
             if (ok && nb < p.cout)
               epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
-            cur = nxt;
           }
         } else {
           // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  Rows v+g of the
@@ -382,7 +388,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // per 16-column chunk), the rest by warp shuffles.
           const int kwm = p.kwm, bn = p.bn;
           const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // readers of the previous accumulator are done
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous accumulator are done
           if (q > 0 || next_blk) {
             float* xw = xch[q > 0 ? q - 1 : 3];
             const uint32_t src_addr = q > 0 ? taddr : taddr + (uint32_t)p.slot;
@@ -398,10 +404,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // boundary rows visible
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows visible
           const float* xr = xch[q];
           for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            if (c0 + 16 < c_hi) epilogue_prefetch(ea, t.nt * bn + c0 + 16, out_row, mask_row, ok, nxt);
+            epilogue_prefetch(ea, t.nt * bn + c0, out_row, mask_row, ok, cur);
             uint32_t tg[16];
             tmem_ld16(taddr + c0, tg);
             float accv[16];
@@ -425,7 +431,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
               epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
             }
-            cur = nxt;
           }
         }
       }
