@@ -367,6 +367,10 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API with pinned host clips
     host = clips.pin_memory()
+    # one short untimed call first: CUDA loads kernels lazily, and the init-mask / reverse-score kernels have not
+    # run yet in this process (measured: ~130 ms of one-time loading inside the first call)
+    search.find_masks_batched(model, host, targets, lam1=0.01, lam2=0.02, n_iter=2, perturb="freeze",
+                              micro_batch=CLIPS, device=dev)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -384,8 +388,9 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": world * CLIPS * N_ITER / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(host.numel() * 4 / N_ITER), "d2h_bytes_per_step": int((masks_host.numel() + scores_host.numel()) * 4 / N_ITER),
            "h2d_bytes_per_search": int(host.numel() * 4), "seconds_per_search": e2e_s,
-           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + 300 iterations + "
-                   "reverse score + D2H, per rank; step = 1/300 of a search"}
+           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + graph capture + 300 "
+                   "iterations + reverse score + D2H, per rank; step = 1/300 of a search; one 2-iteration call runs "
+                   "untimed first (lazy kernel loading)"}
 
     gradcam = gradcam_throughput(dev, rank, world, args.mode) if not args.no_gradcam else None
     clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
