@@ -10,7 +10,7 @@ TMO=900 run bench python bench.py --steps 50 --warmup 5 ${BENCH_ARGS}
 TMO=300 run prof_plain python tools/profile_step.py
 grep -q "exit 0" gpurun_out/prof_plain.log || exit 1
 if [ "${NCU:-list}" = "list" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --profile-from-start off --csv \
       --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launches.log 2>&1
 else
   timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k "regex:$KREGEX" ${NCU_COUNT:+-c $NCU_COUNT} \
