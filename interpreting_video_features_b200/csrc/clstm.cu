@@ -132,6 +132,182 @@ __global__ void bn_pool2d_bwd_kernel(const T* __restrict__ dy, const uint8_t* __
   }
 }
 
+// ---- bf16 path, 4 channels per thread, 32-bit indices --------------------------------------------------
+// The scalar kernels above serve the fp32 mode and odd channel counts.  Per recurrence step the gate kernels
+// move ~42 bytes per hidden element and were at a quarter of the HBM rate with scalar accesses and 64-bit
+// divisions; here every access is a 16-byte vector (8 for bf16x4) and the row/column split is a shift or a
+// 32-bit division.  The activations stay the accurate expf/tanhf: with tanh.approx (relative error ~2^-11) the
+// forward still agreed to 1e-3, but the perturbed hidden state flips 2x2 max-pool argmax decisions and the mask
+// gradient moved by 8-12 % (measured; DESIGN section 5 on that sensitivity) - the kernels are bandwidth bound anyway.
+__device__ __forceinline__ float sigm_fast(float v) { return sigm(v); }
+__device__ __forceinline__ float tanh_fast(float v) { return tanhf(v); }
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+gates_fwd_bf16x4_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, int m, int hid,
+                        float* __restrict__ c_next, __nv_bfloat16* __restrict__ h_next, float* __restrict__ gate_act) {
+  const int hv = hid >> 2;
+  const int total = m * hv;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / hv, k = (idx - r * hv) << 2;
+    const float* p = pre + (size_t)r * 4 * hid + k;
+    const float4 pi = *reinterpret_cast<const float4*>(p), pf = *reinterpret_cast<const float4*>(p + hid);
+    const float4 pg = *reinterpret_cast<const float4*>(p + 2 * hid), po = *reinterpret_cast<const float4*>(p + 3 * hid);
+    const size_t e = (size_t)r * hid + k;
+    const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gi, gf, gg, go, cn, hn;
+#define IVF_GATE(x)                         \
+  gi.x = sigm_fast(pi.x);                   \
+  gf.x = sigm_fast(pf.x);                   \
+  gg.x = tanh_fast(pg.x);                   \
+  go.x = sigm_fast(po.x);                   \
+  cn.x = fmaf(gf.x, cp.x, gi.x * gg.x);     \
+  hn.x = go.x * tanh_fast(cn.x);
+    IVF_GATE(x) IVF_GATE(y) IVF_GATE(z) IVF_GATE(w)
+#undef IVF_GATE
+    *reinterpret_cast<float4*>(c_next + e) = cn;
+    *reinterpret_cast<uint2*>(h_next + e) = pack_bf16x4(hn.x, hn.y, hn.z, hn.w);
+    if (gate_act) {
+      float* a = gate_act + (size_t)r * 4 * hid + k;
+      *reinterpret_cast<float4*>(a) = gi;
+      *reinterpret_cast<float4*>(a + hid) = gf;
+      *reinterpret_cast<float4*>(a + 2 * hid) = gg;
+      *reinterpret_cast<float4*>(a + 3 * hid) = go;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gates_bwd_bf16x4_kernel(const float* __restrict__ gate_act, const float* __restrict__ c_prev,
+                        const float* __restrict__ c_next, const float* __restrict__ dh, float* __restrict__ dc_io,
+                        int m, int hid, __nv_bfloat16* __restrict__ dgates) {
+  const int hv = hid >> 2;
+  const int total = m * hv;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / hv, k = (idx - r * hv) << 2;
+    const float* a = gate_act + (size_t)r * 4 * hid + k;
+    const float4 gi = *reinterpret_cast<const float4*>(a), gf = *reinterpret_cast<const float4*>(a + hid);
+    const float4 gg = *reinterpret_cast<const float4*>(a + 2 * hid), go = *reinterpret_cast<const float4*>(a + 3 * hid);
+    const size_t e = (size_t)r * hid + k;
+    const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 cn = *reinterpret_cast<const float4*>(c_next + e);
+    const float4 dhv = *reinterpret_cast<const float4*>(dh + e);
+    const float4 dci = *reinterpret_cast<const float4*>(dc_io + e);
+    float4 dco, d_i, d_f, d_g, d_o;
+#define IVF_GATE(x)                                                   \
+  {                                                                   \
+    const float tc = tanh_fast(cn.x);                                 \
+    const float dcn = fmaf(dhv.x * go.x, 1.f - tc * tc, dci.x);       \
+    dco.x = dcn * gf.x;                                               \
+    d_i.x = dcn * gg.x * gi.x * (1.f - gi.x);                         \
+    d_f.x = dcn * cp.x * gf.x * (1.f - gf.x);                         \
+    d_g.x = dcn * gi.x * (1.f - gg.x * gg.x);                         \
+    d_o.x = dhv.x * tc * go.x * (1.f - go.x);                         \
+  }
+    IVF_GATE(x) IVF_GATE(y) IVF_GATE(z) IVF_GATE(w)
+#undef IVF_GATE
+    *reinterpret_cast<float4*>(dc_io + e) = dco;
+    __nv_bfloat16* d = dgates + (size_t)r * 4 * hid + k;
+    *reinterpret_cast<uint2*>(d) = pack_bf16x4(d_i.x, d_i.y, d_i.z, d_i.w);
+    *reinterpret_cast<uint2*>(d + hid) = pack_bf16x4(d_f.x, d_f.y, d_f.z, d_f.w);
+    *reinterpret_cast<uint2*>(d + 2 * hid) = pack_bf16x4(d_g.x, d_g.y, d_g.z, d_g.w);
+    *reinterpret_cast<uint2*>(d + 3 * hid) = pack_bf16x4(d_o.x, d_o.y, d_o.z, d_o.w);
+  }
+}
+
+// one thread per (pooled pixel, 4 channels): the 2x2 window is four 8-byte loads
+__global__ void __launch_bounds__(256)
+bn_pool2d_fwd_bf16x4_kernel(const __nv_bfloat16* __restrict__ x, int hh, int ww, int c, const float* __restrict__ scale,
+                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                            uint8_t* __restrict__ argmax, int s2d, int total) {
+  const int ho = hh / 2, wo = ww / 2, cv = c >> 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = (idx % cv) << 2;
+    int t = idx / cv;
+    const int ox = t % wo;
+    t /= wo;
+    const int oy = t % ho, n = t / ho;
+    const float4 s = scale ? *reinterpret_cast<const float4*>(scale + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b = shift ? *reinterpret_cast<const float4*>(shift + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0, 0, 0, 0};
+    const float sc[4] = {s.x, s.y, s.z, s.w}, sh[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(x + ((size_t)(n * hh + 2 * oy + a) * ww + 2 * ox + e) * c + k);
+        const float v4[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                             __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float v = fmaf(v4[i], sc[i], sh[i]);
+          if (v > best[i] || v != v) {
+            best[i] = v;
+            bi[i] = a * 2 + e;
+          }
+        }
+      }
+    const size_t o = ((size_t)(n * ho + oy) * wo + ox) * c + k;
+    const size_t yo = s2d ? ((((size_t)(n * (ho / 2) + (oy >> 1)) * (wo / 2) + (ox >> 1)) * 4 + ((oy & 1) * 2 + (ox & 1))) * c + k)
+                          : o;
+    *reinterpret_cast<uint2*>(y + yo) = pack_bf16x4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<uint32_t*>(argmax + o) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) |
+                                               ((uint32_t)bi[3] << 24);
+  }
+}
+
+// one thread per (input pixel, 4 channels)
+__global__ void __launch_bounds__(256)
+bn_pool2d_bwd_bf16x4_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax, int hh, int ww,
+                            int c, const float* __restrict__ scale, const float* __restrict__ acc_in,
+                            float* __restrict__ dx, int s2d, int total) {
+  const int ho = hh / 2, wo = ww / 2, cv = c >> 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = (idx % cv) << 2;
+    int t = idx / cv;
+    const int ix = t % ww;
+    t /= ww;
+    const int iy = t % hh, n = t / hh;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oy = iy >> 1, ox = ix >> 1;
+    if (oy < ho && ox < wo) {
+      const size_t o = ((size_t)(n * ho + oy) * wo + ox) * c + k;
+      const size_t yo = s2d ? ((((size_t)(n * (ho / 2) + (oy >> 1)) * (wo / 2) + (ox >> 1)) * 4 + ((oy & 1) * 2 + (ox & 1))) * c + k)
+                            : o;
+      const uint32_t am = *reinterpret_cast<const uint32_t*>(argmax + o);
+      const uint32_t me = (uint32_t)((iy & 1) * 2 + (ix & 1)) * 0x01010101u;
+      const uint32_t eq = __vcmpeq4(am, me);
+      if (eq) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(dy + yo);
+        const float4 s = scale ? *reinterpret_cast<const float4*>(scale + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (eq & 0x000000ffu) g.x = __uint_as_float(raw.x << 16) * s.x;
+        if (eq & 0x0000ff00u) g.y = __uint_as_float(raw.x & 0xffff0000u) * s.y;
+        if (eq & 0x00ff0000u) g.z = __uint_as_float(raw.y << 16) * s.z;
+        if (eq & 0xff000000u) g.w = __uint_as_float(raw.y & 0xffff0000u) * s.w;
+      }
+    }
+    const size_t e = (size_t)idx << 2;
+    if (acc_in) {
+      const float4 a = *reinterpret_cast<const float4*>(acc_in + e);
+      g.x += a.x;
+      g.y += a.y;
+      g.z += a.z;
+      g.w += a.w;
+    }
+    *reinterpret_cast<float4*>(dx + e) = g;
+  }
+}
+
+bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool aligned8(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
 int grid_for(ivf_handle* h, long long total) {
   long long b = (total + 255) / 256;
   long long cap = (long long)h->sm_count * 32;
@@ -150,6 +326,10 @@ extern "C" int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, c
   if (dtype == IVF_F32)
     gates_fwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
                                                                 (float*)h_next, gate_act);
+  else if (dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(pre) && aligned16(c_prev) &&
+           aligned16(c_next) && aligned8(h_next) && aligned16(gate_act))
+    gates_fwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
+                                                                    (__nv_bfloat16*)h_next, gate_act);
   else if (dtype == IVF_BF16)
     gates_fwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         pre, c_prev, m, hid, c_next, (__nv_bfloat16*)h_next, gate_act);
@@ -169,6 +349,10 @@ extern "C" int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_a
   if (dtype == IVF_F32)
     gates_bwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m,
                                                                 hid, (float*)dgates);
+  else if (dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(gate_act) && aligned16(c_prev) &&
+           aligned16(c_next) && aligned16(dh) && aligned16(dc_io) && aligned8(dgates))
+    gates_bwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m, hid,
+                                                                    (__nv_bfloat16*)dgates);
   else if (dtype == IVF_BF16)
     gates_bwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         gate_act, c_prev, c_next, dh, dc_io, m, hid, (__nv_bfloat16*)dgates);
@@ -189,6 +373,10 @@ extern "C" int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n,
   if (dtype == IVF_F32)
     bn_pool2d_fwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>((const float*)x, hh, ww, c, scale,
                                                                     shift, (float*)y, argmax, s2d, total);
+  else if (dtype == IVF_BF16 && c % 4 == 0 && (long long)n * hh * ww * c < (1ll << 31) && aligned8(x) && aligned8(y) &&
+           aligned16(scale) && aligned16(shift) && (reinterpret_cast<uintptr_t>(argmax) & 3) == 0)
+    bn_pool2d_fwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, hh, ww, c, scale, shift, (__nv_bfloat16*)y, argmax, s2d, (int)(total / 4));
   else if (dtype == IVF_BF16)
     bn_pool2d_fwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         (const __nv_bfloat16*)x, hh, ww, c, scale, shift, (__nv_bfloat16*)y, argmax, s2d, total);
@@ -208,6 +396,10 @@ extern "C" int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const
   if (dtype == IVF_F32)
     bn_pool2d_bwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>((const float*)dy, argmax, hh, ww, c,
                                                                     scale, acc_in, dx, s2d, total);
+  else if (dtype == IVF_BF16 && c % 4 == 0 && total < (1ll << 31) && aligned8(dy) && aligned16(scale) &&
+           aligned16(acc_in) && aligned16(dx) && (reinterpret_cast<uintptr_t>(argmax) & 3) == 0)
+    bn_pool2d_bwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(
+        (const __nv_bfloat16*)dy, argmax, hh, ww, c, scale, acc_in, dx, s2d, (int)(total / 4));
   else if (dtype == IVF_BF16)
     bn_pool2d_bwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         (const __nv_bfloat16*)dy, argmax, hh, ww, c, scale, acc_in, dx, s2d, total);
