@@ -132,8 +132,8 @@ class ConvOp:
     def __call__(self):
         self.launch(self.plan)
 
-    def tune(self, device):
-        self.plan = tune.best_plan(self.desc, self.launch, device)
+    def tune(self, device, min_ms=None):
+        self.plan = tune.best_plan(self.desc, self.launch, device, min_ms=min_ms)
 
 
 class Unit:

@@ -16,7 +16,7 @@ to 8 with zero weights (padded channels stay exactly 0: gates 0.5/0.5/0/0.5 on a
 """
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, tune
 from ._lib import PFMT_S2D2_BF16, PFMT_TBHWC_F32
 from .engine import pack_dgrad, pack_fwd, strip_module_prefix
 from .ops import Act
@@ -164,6 +164,24 @@ class CLSTMEngine:
         self.zero_mask = torch.zeros((B, T), dtype=torch.float32, device=dev)
         self.g_feat_raw = torch.zeros((B, hin * win * he), dtype=torch.float32, device=dev)
 
+        # measured tile plans for the recurrent convolutions: each is a 15-35 us launch repeated T-1 times per
+        # layer and direction with its operands resident in L2 (what the isolated measurement sees)
+        if mode == "bf16" and tune.enabled() and T > 1:
+            from .engine import ConvOp
+            with torch.cuda.device(dev):
+                for rec in self.layers:
+                    dH = Act(rec["dH"], T * B, 1, rec["ho"], rec["wo"], he, 0, he)
+                    gx1, dprev = self._step(rec["gx"], 1), self._step(dH, 0)
+                    fwd = ConvOp(self._step(rec["h"], 0), rec["wh_f"], gx1, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx1)
+                    bwd = ConvOp(self._step(rec["dpre"], 1), rec["wh_d"], dprev, (1, 5, 5), (1, 1, 1), (0, 2, 2),
+                                 acc_in=dprev)
+                    fwd.tune(dev, min_ms=0.012)
+                    bwd.tune(dev, min_ms=0.012)
+                    rec["plan_hf"], rec["plan_hd"] = fwd.plan, bwd.plan
+                    rec["gx"].buf.zero_()
+                    rec["dH"].zero_()
+                torch.cuda.synchronize(dev)
+
     # ------------------------------------------------------------------ helpers
     def _step(self, act, t):
         """Act view of step t's B frames of a time-major [T*B,...] Act."""
@@ -197,7 +215,8 @@ class CLSTMEngine:
             for t in range(T):
                 gx_t = self._step(rec["gx"], t)
                 if t > 0:
-                    ops.conv3d(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx_t)
+                    ops.conv3d(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx_t,
+                               plan=rec.get("plan_hf"))
                 ops.clstm_gates_fwd(gx_t.buf.view(m, 4 * he), rec["c"][(t - 1) * B:t * B] if t > 0 else None,
                                     rec["c"][t * B:(t + 1) * B], self._step(rec["h"], t).buf, rec["gact"][t * B:(t + 1) * B].view(m, 4 * he))
             ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
@@ -229,7 +248,7 @@ class CLSTMEngine:
                                    acc_in=dprev, transposed=1)
                     else:
                         ops.conv3d(self._step(rec["dpre"], t), rec["wh_d"], dprev, (1, 5, 5), (1, 1, 1), (0, 2, 2),
-                                   acc_in=dprev)
+                                   acc_in=dprev, plan=rec.get("plan_hd"))
             if self.mode == "fp32":
                 ops.conv3d(rec["dpre"], rec["wx_d"], rec["g_x"], (1, 5, 5), (1, 2, 2), (0, 2, 2), transposed=1)
             else:
