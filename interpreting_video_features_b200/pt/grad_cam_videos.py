@@ -6,6 +6,8 @@ score through the whole network (weight gradients included) and finishes on the 
 channel weights -> weighted sum -> ReLU -> bilinear upsample -> temporal repeat -> normalisation.
 """
 import numpy as np
+import os
+
 import torch
 
 try:
@@ -60,7 +62,7 @@ class GradCamVideo:
             raise _lib.IvfError("native Grad-CAM targets 'Mixed_5c' (the layer the reference drivers use, "
                                 "pt/FindMasksComparison_I3D_smth.py:258); got %r" % name)
         eng.set_input(x)
-        probs = eng.forward(None)
+        probs = eng.forward_graphed() if os.environ.get("IVF_GRADCAM_GRAPH", "1") != "0" else eng.forward(None)
         out = probs.clone()
         if indices is None:
             tg = torch.argmax(out, dim=1)  # pt/grad_cam_videos.py:70-71
