@@ -388,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": world * CLIPS * N_ITER / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(host.numel() * 4 / N_ITER), "d2h_bytes_per_step": int((masks_host.numel() + scores_host.numel()) * 4 / N_ITER),
            "h2d_bytes_per_search": int(host.numel() * 4), "seconds_per_search": e2e_s,
-           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + graph capture + 300 "
+           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + 300 "
                    "iterations + reverse score + D2H, per rank; step = 1/300 of a search; one 2-iteration call runs "
                    "untimed first (lazy kernel loading)"}
 
