@@ -390,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
            "h2d_bytes_per_search": int(host.numel() * 4), "seconds_per_search": e2e_s,
            "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + 300 "
                    "iterations + reverse score + D2H, per rank; step = 1/300 of a search; one 2-iteration call runs "
-                   "untimed first (lazy kernel loading)"}
+                   "untimed first (lazy kernel loading; it also captures the iteration graph the timed call replays)"}
 
     gradcam = gradcam_throughput(dev, rank, world, args.mode) if not args.no_gradcam else None
     clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
