@@ -513,3 +513,35 @@ def test_clip_groups_equal_single_group(dev, small_setup):
     two = search.find_masks_batched(model, clips, targets, n_iter=6, micro_batch=4, groups=2)
     torch.testing.assert_close(two["time_mask"], one["time_mask"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(two["reverse_score"], one["reverse_score"], rtol=1e-4, atol=1e-7)
+
+
+def test_searcher_reuse_and_graphed_forward(dev, small_setup):
+    """find_masks_batched keeps its searcher (Adam/mask buffers + captured iteration) with the engines: a second
+    call on other clips/targets must give what a fresh searcher gives; and the graph-replayed forward Grad-CAM
+    uses must equal the eager forward."""
+    from interpreting_video_features_b200 import search
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    _, sds, x, _ = small_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sds)
+    model = model.to(dev).eval()
+    model.avg_pool.kernel_size = [2, 2, 2]
+    a, ta = x[:2], torch.tensor([3, 40])
+    b, tb = x.flip(0)[:2] * 0.5, torch.tensor([40, 7])
+    search.find_masks_batched(model, a, ta, n_iter=5, micro_batch=2)            # captures
+    second = search.find_masks_batched(model, b, tb, n_iter=5, micro_batch=2)   # replays the cached graph
+    eng = model._engine(b.to(dev), batch=2)
+    assert len(eng.__dict__["_searchers"]) == 1
+    eng.__dict__["_searchers"].clear()
+    fresh = search.find_masks_batched(model, b, tb, n_iter=5, micro_batch=2)
+    torch.testing.assert_close(second["time_mask"], fresh["time_mask"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(second["freeze_score"], fresh["freeze_score"], rtol=1e-4, atol=1e-7)
+    assert torch.equal(second["probs_orig"], fresh["probs_orig"])
+    # three iterations more than the first call's count, same graph
+    longer = search.find_masks_batched(model, b, tb, n_iter=8, micro_batch=2)
+    assert float((longer["time_mask"] - fresh["time_mask"]).abs().max()) > 0
+    eng.set_input(b.to(dev))
+    eager = eng.forward(None).clone()
+    for _ in range(2):
+        graphed = eng.forward_graphed().clone()
+        assert torch.equal(graphed, eager)
