@@ -49,7 +49,13 @@ using namespace ivf_tc;
 #define SLAB_EPI_GROUPS 3
 #endif
 constexpr int EPI_THREADS = 128 * SLAB_EPI_GROUPS;
-constexpr int SLAB_THREADS = 96 + EPI_THREADS;
+// Role warps: 0 slab (A) producer, 1 and 3 MMA issuers, 2 weight (B) producer + TMEM allocation.  ONE issuing
+// thread sustains one tcgen05.mma per ~70 cycles whatever N (tools/mma_bench.cu on the B200: 75 cycles per
+// M128 x N<=128 x K16 from one warp, 40-64 from two, i.e. the math rate N/2 from N = 128 up); the layers with few
+// output channels (stem N = 64, data gradients N = 32..96) were bound by exactly that, so tiles with two or
+// more accumulators are issued by two warps, even / odd accumulators each.
+constexpr int SLAB_ROLE_WARPS = 4;
+constexpr int SLAB_THREADS = 32 * SLAB_ROLE_WARPS + EPI_THREADS;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr uint32_t SLAB_SMEM_BUDGET = 208u * 1024u;
@@ -123,16 +129,17 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   if (threadIdx.x == 0) {
+    const uint32_t nissue = p.mt >= 2 ? 2u : 1u;  // MMA-issuing warps: each commits once per slot / tile
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], nissue);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], nissue);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&t_full[s], 1);
+      mbar_init(&t_full[s], nissue);
       mbar_init(&t_empty[s], 4 * SLAB_EPI_GROUPS * NCTA);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,8 +160,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  if (warp >= 3) {
-    for (int i = threadIdx.x - 96; i < SLAB_MAX_COUT; i += EPI_THREADS) {
+  if (warp >= SLAB_ROLE_WARPS) {
+    for (int i = threadIdx.x - 32 * SLAB_ROLE_WARPS; i < SLAB_MAX_COUT; i += EPI_THREADS) {
       bool ok = i < p.cout;
       float sc = 1.f;
       if (ok && (p.flags & IVF_EP_AFFINE)) sc = scale[i];
@@ -253,9 +260,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    if (rank == 0) {  // of a pair only the leader CTA issues
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (warp-uniform loop, one elected lane issues) =====================
+    // warp 1 takes the even accumulators of a tile, warp 3 the odd ones (it idles on single-accumulator tiles)
+    const int mw = warp == 1 ? 0 : 1, mstep = p.mt >= 2 ? 2 : 1;
+    if (rank == 0 && (mw == 0 || p.mt >= 2)) {  // of a pair only the leader CTA issues
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.bn * p.kwm);
       const uint32_t desc_hi = smem_desc_hi(8 * ROWB, LAYOUT);  // 8-row swizzle atoms back to back
@@ -293,10 +302,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
               uint32_t a_tap = row_lo;  // + kw pixels; a merged group of kwm taps is one MMA of N = kwm*bn
               for (int kw_i = 0; kw_i < kw_n; kw_i += kwm, a_tap += kwm * ROW16, b_lo += b_grp16) {
-                uint32_t a_lo = a_tap, d = d_tmem;
+                uint32_t a_lo = a_tap + (uint32_t)mw * 128u * ROW16, d = d_tmem + (uint32_t)mw * slot;
+                const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)mstep * slot;
                 if (leader) {
                   if (ksteps == KSTEPS) {
-                    for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot) {
+                    for (int m = mw; m < mt; m += mstep, a_lo += a_inc, d += d_inc) {
 #pragma unroll
                       for (int k = 0; k < KSTEPS; ++k) {
                         if constexpr (NCTA == 2)
@@ -306,7 +316,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                       }
                     }
                   } else {
-                    for (int m = 0; m < mt; ++m, a_lo += 128u * ROW16, d += slot)
+                    for (int m = mw; m < mt; m += mstep, a_lo += a_inc, d += d_inc)
                       for (int k = 0; k < ksteps; ++k) {
                         if constexpr (NCTA == 2)
                           umma_bf16_lo_pair(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
@@ -343,7 +353,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int cgrp = (warp - 3) >> 2;  // which share of the tile's 16-column chunks this warp handles
+    const int cgrp = (warp - SLAB_ROLE_WARPS) >> 2;  // which share of the tile's 16-column chunks this warp handles
     EpilogueArgs ea;
     ea.cout = p.cout;
     ea.flags = p.flags;
