@@ -77,6 +77,8 @@ struct SlabParams {
   int acc_stages;  // 2: epilogue of tile i overlaps the MMAs of tile i+1; 1: all TMEM columns for one tile
   int kch;
   int ncta;  // 1, or 2 = CTA pairs (cta_group::2)
+  int diag;  // IVF_SLAB_DIAG (timing experiments, results are garbage): bit 0 / 1 = after the ring has filled
+             // once, the slab / weight producer signals "full" without loading
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
 };
 
@@ -180,6 +182,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== slab (A) TMA producer =====================
     {
       const bool leader = elect_one();
+      int a_loads = 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = item0; tile < p.num_tiles; tile += item_step) {
@@ -189,7 +192,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (zd < 0 || zd >= p.dd) continue;  // an all-padding depth tap contributes nothing
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(&a_empty[stage], phase ^ 1u);
-            if (leader) {
+            if ((p.diag & 1) && a_loads >= p.a_stages) {
+              if (leader && rank == 0) mbar_arrive(&a_full[stage]);
+            } else if (leader) {
               if constexpr (NCTA == 2) {
                 if (rank == 0) mbar_expect_tx(&a_full[stage], 2u * p.a_tx);  // both CTAs' slabs
                 tma_load_5d_pair(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
@@ -201,6 +206,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             __syncwarp();
+            ++a_loads;
             if (++stage == p.a_stages) {
               stage = 0;
               phase ^= 1u;
@@ -213,6 +219,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== weight (B) TMA producer =====================
     {
       const bool leader = elect_one();
+      int b_loads = 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = item0; tile < p.num_tiles; tile += item_step) {
@@ -224,7 +231,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kh_i = 0; kh_i < p.kh; ++kh_i) {
               mbar_wait(&b_empty[stage], phase ^ 1u);
               const int tap0 = (kd_i * p.kh + kh_i) * p.kw;
-              if (leader) {
+              if ((p.diag & 2) && b_loads >= p.b_stages) {
+                if (leader && rank == 0) mbar_arrive(&b_full[stage]);
+              } else if (leader) {
                 if constexpr (NCTA == 2) {
                   // The N rows of an MMA (kwm stacked taps of bn rows) are split in halves over the pair:
                   // kwm == 1: this CTA holds rows [rank*bn/2, +bn/2) of every tap; kwm == 2 / 4: it holds
@@ -251,6 +260,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
               __syncwarp();
+              ++b_loads;
               if (++stage == p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -276,6 +286,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t wp8 = (uint32_t)p.wp * ROW16;           // one padded row of pixels, in 16-byte units
       // 16-byte units between the weight operands of consecutive merged groups (per CTA: its half of N)
       const uint32_t b_grp16 = (NCTA == 2 && p.kwm > 1 ? (uint32_t)(p.kwm / 2) : (uint32_t)p.kwm) * (p.b_tap_bytes >> 4);
+      const int nm = (mt - mw + mstep - 1) / mstep;  // accumulators of a tile this warp issues (1..4)
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       int it = 0;
@@ -306,15 +317,14 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)mstep * slot;
                 if (leader) {
                   if (ksteps == KSTEPS) {
-                    for (int m = mw; m < mt; m += mstep, a_lo += a_inc, d += d_inc) {
-#pragma unroll
-                      for (int k = 0; k < KSTEPS; ++k) {
-                        if constexpr (NCTA == 2)
-                          umma_bf16_lo_pair(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
-                        else
-                          umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
-                      }
-                    }
+                    // this warp's accumulators of the tile, unrolled: independent address arithmetic instead of a
+                    // loop-carried chain of uniform-register adds between the MMAs
+                    umma_bf16_ksteps<KSTEPS, NCTA>(d, a_lo, b_lo, desc_hi, idesc, accum);
+                    if (nm > 1) umma_bf16_ksteps<KSTEPS, NCTA>(d + d_inc, a_lo + a_inc, b_lo, desc_hi, idesc, accum);
+                    if (nm > 2)
+                      umma_bf16_ksteps<KSTEPS, NCTA>(d + 2u * d_inc, a_lo + 2u * a_inc, b_lo, desc_hi, idesc, accum);
+                    if (nm > 3)
+                      umma_bf16_ksteps<KSTEPS, NCTA>(d + 3u * d_inc, a_lo + 3u * a_inc, b_lo, desc_hi, idesc, accum);
                   } else {
                     for (int m = mw; m < mt; m += mstep, a_lo += a_inc, d += d_inc)
                       for (int k = 0; k < ksteps; ++k) {
@@ -590,7 +600,9 @@ bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
 bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   memset(best, 0, sizeof(*best));
   const int cout = d->cout, cin = d->cin;
-  const int kch = cin <= 32 ? 32 : 64;
+  // 64-byte rows (SWIZZLE_64B) cost more per MMA than 128-byte rows (tools/mma_bench.cu); IVF_SLAB_KCH64=1 gives the
+  // narrow layers 128-byte rows too (the upper half is TMA zero fill and is never multiplied)
+  const int kch = (cin <= 32 && !env_int("IVF_SLAB_KCH64", 0)) ? 32 : 64;
   const int rowb = kch * 2;
   const int wp = d->iw + d->kw - 1;
   const int cchunks = (cin + kch - 1) / kch;
@@ -801,6 +813,7 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* i
   long long tiles = (long long)d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;  // work items
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;
+  p.diag = env_int("IVF_SLAB_DIAG", 0);
   if (env_int("IVF_SLAB_VERBOSE", 0))
     fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) items %d ncta %d\n",
             d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.kwm, p.mt, p.th,

@@ -15,11 +15,11 @@ using namespace ivf_tc;
 void ivf_set_error(const char*, ...) {}
 
 template <int NCTA>
-__global__ void __launch_bounds__(160) mma_bench_kernel(int n, int rowb, int layout, int iters, int nbuf, int ksteps,
+__global__ void __launch_bounds__(256) mma_bench_kernel(int n, int rowb, int layout, int iters, int nbuf, int ksteps,
                                                         int nacc, int nissue, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t done_bar;
-  __shared__ long long t_issue[4], t_done[4];
+  __shared__ long long t_issue[8], t_done[8];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
@@ -115,7 +115,7 @@ double run(int n, int kch, int iters, int nbuf, int sms, int nacc, int nissue) {
   cudaMalloc(&out, sizeof(long long) * 2 * sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sms);
-  cfg.blockDim = dim3(160);
+  cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -148,11 +148,12 @@ int main() {
   printf("%s, %d SMs: cycles per tcgen05.mma K16 (slowest SM, best of 3), math = 128*N*16 / (4096 MAC/clk/SM) = N/2\n", prop.name, sms);
   const int iters = 4000;
   for (int kch : {64, 32}) {
-    for (int nissue : {1, 2}) {
+    for (int nissue : {1, 2, 3, 4, 6}) {
       printf("rows of %3d B (SWIZZLE_%dB), %d issuing warp(s), accumulators in rotation\n", kch * 2, kch * 2, nissue);
       printf("   N :   1-CTA M=128  |  pair M=256   (math per SM)   cycles per MMA, all issuers together\n");
       for (int n : {32, 64, 96, 128, 256}) {
         const int nacc = std::max(1, std::min(2, 512 / (n * nissue)));
+        if (n * nissue > 512) continue;
         double c1 = run<1>(n, kch, iters, 4, sms, nacc, nissue);
         double c2 = run<2>(n, kch, iters, 4, sms - sms % 2, nacc, nissue);
         printf(" %3d :   %7.1f      |   %7.1f      (%5.1f)   [%d acc per issuer]\n", n, c1, c2, 128.0 * n * 16 / 4096.0, nacc);
