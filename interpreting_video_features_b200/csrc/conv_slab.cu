@@ -287,6 +287,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // 16-byte units between the weight operands of consecutive merged groups (per CTA: its half of N)
       const uint32_t b_grp16 = (NCTA == 2 && p.kwm > 1 ? (uint32_t)(p.kwm / 2) : (uint32_t)p.kwm) * (p.b_tap_bytes >> 4);
       const int nm = (mt - mw + mstep - 1) / mstep;  // accumulators of a tile this warp issues (1..4)
+      const int ngroups = kw_n / (int)kwm;            // merged tap groups per filter row (<= 5: checked on the host)
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
       int it = 0;
@@ -311,32 +312,39 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(&b_full[bs], bphase);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               uint32_t b_lo = smem_desc_lo(b_base + bs * p.b_stage_bytes);
-              uint32_t a_tap = row_lo;  // + kw pixels; a merged group of kwm taps is one MMA of N = kwm*bn
-              for (int kw_i = 0; kw_i < kw_n; kw_i += kwm, a_tap += kwm * ROW16, b_lo += b_grp16) {
-                uint32_t a_lo = a_tap + (uint32_t)mw * 128u * ROW16, d = d_tmem + (uint32_t)mw * slot;
-                const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)mstep * slot;
-                if (leader) {
-                  if (ksteps == KSTEPS) {
-                    // this warp's accumulators of the tile, unrolled: independent address arithmetic instead of a
-                    // loop-carried chain of uniform-register adds between the MMAs
-                    umma_bf16_ksteps<KSTEPS, NCTA>(d, a_lo, b_lo, desc_hi, idesc, accum);
-                    if (nm > 1) umma_bf16_ksteps<KSTEPS, NCTA>(d + d_inc, a_lo + a_inc, b_lo, desc_hi, idesc, accum);
-                    if (nm > 2)
-                      umma_bf16_ksteps<KSTEPS, NCTA>(d + 2u * d_inc, a_lo + 2u * a_inc, b_lo, desc_hi, idesc, accum);
-                    if (nm > 3)
-                      umma_bf16_ksteps<KSTEPS, NCTA>(d + 3u * d_inc, a_lo + 3u * a_inc, b_lo, desc_hi, idesc, accum);
-                  } else {
-                    for (int m = mw; m < mt; m += mstep, a_lo += a_inc, d += d_inc)
-                      for (int k = 0; k < ksteps; ++k) {
-                        if constexpr (NCTA == 2)
-                          umma_bf16_lo_pair(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
-                        else
-                          umma_bf16_lo(d, a_lo + 2u * k, b_lo + 2u * k, desc_hi, idesc, k == 0 ? accum : 1u);
-                      }
+              // kw taps in merged groups of kwm (one MMA of N = kwm*bn each): group g reads the slab g*kwm pixels
+              // further and the next group of weight rows.  Unrolled over the (at most 5) groups so that every
+              // operand address is base + constant * g: no loop-carried adds between the MMAs.
+              const uint32_t a_row = row_lo + (uint32_t)mw * 128u * ROW16, d0 = d_tmem + (uint32_t)mw * slot;
+              const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)mstep * slot;
+              const uint32_t a_grp = kwm * ROW16;
+              if (leader) {
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                  if (g < ngroups) {
+                    const uint32_t a_lo = a_row + (uint32_t)g * a_grp, bg = b_lo + (uint32_t)g * b_grp16;
+                    const uint32_t acc_g = g == 0 ? accum : 1u;
+                    if (ksteps == KSTEPS) {
+                      umma_bf16_ksteps<KSTEPS, NCTA>(d0, a_lo, bg, desc_hi, idesc, acc_g);
+                      if (nm > 1) umma_bf16_ksteps<KSTEPS, NCTA>(d0 + d_inc, a_lo + a_inc, bg, desc_hi, idesc, acc_g);
+                      if (nm > 2)
+                        umma_bf16_ksteps<KSTEPS, NCTA>(d0 + 2u * d_inc, a_lo + 2u * a_inc, bg, desc_hi, idesc, acc_g);
+                      if (nm > 3)
+                        umma_bf16_ksteps<KSTEPS, NCTA>(d0 + 3u * d_inc, a_lo + 3u * a_inc, bg, desc_hi, idesc, acc_g);
+                    } else {
+                      uint32_t am = a_lo, d = d0;
+                      for (int m = mw; m < mt; m += mstep, am += a_inc, d += d_inc)
+                        for (int k = 0; k < ksteps; ++k) {
+                          if constexpr (NCTA == 2)
+                            umma_bf16_lo_pair(d, am + 2u * k, bg + 2u * k, desc_hi, idesc, k == 0 ? acc_g : 1u);
+                          else
+                            umma_bf16_lo(d, am + 2u * k, bg + 2u * k, desc_hi, idesc, k == 0 ? acc_g : 1u);
+                        }
+                    }
                   }
                 }
-                accum = 1u;
               }
+              accum = 1u;
               __syncwarp();
               if (leader) {  // weight slot free once these MMAs have read it
                 if constexpr (NCTA == 2) umma_commit_pair(&b_empty[bs]); else umma_commit(&b_empty[bs]);
@@ -785,6 +793,7 @@ bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d0) {
   if (d->pd < 0 || d->pd >= d->kd || d->ph < 0 || d->ph >= d->kh || d->pw < 0 || d->pw >= d->kw) return false;
   if (d->iw < env_int("IVF_SLAB_MIN_W", 7)) return false;  // very narrow maps waste the padded-width tile
   if (d->iw + d->kw - 1 > 256) return false;
+  if (d->kw > 5) return false;  // the issue loop is unrolled over at most five tap groups per filter row
   if (d->cout > SLAB_MAX_COUT) return false;
   if ((d->flags & IVF_EP_AFFINE) && (d->flags & IVF_EP_MASK)) return false;  // one shared scale vector
   SlabParams p;
