@@ -157,36 +157,32 @@ __device__ __forceinline__ void umma_bf16_lo_pair(uint32_t tmem_d, uint32_t a_lo
 template <int KS, int NCTA>
 __device__ __forceinline__ void umma_bf16_ksteps(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                                  uint32_t idesc, uint32_t accumulate) {
-  static_assert(KS == 2 || KS == 4, "K steps per stage: 2 (64-byte rows) or 4 (128-byte rows)");
+  static_assert(KS >= 1 && KS <= 4, "K steps per stage: up to 4 (128-byte rows)");
 #define IVF_MMA1(CG, PRED) "mov.b64 da, {al, %3};\n" "mov.b64 db, {bl, %3};\n" \
                            "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %4, " PRED ";\n"
-#define IVF_MMA_STEP "add.u32 al, al, 2;\n" "add.u32 bl, bl, 2;\n"
+#define IVF_MMA_NEXT(CG) "add.u32 al, al, 2;\n" "add.u32 bl, bl, 2;\n" IVF_MMA1(CG, "pt")
 #define IVF_MMA_HEAD "{\n" ".reg .pred p, pt;\n" ".reg .b64 da, db;\n" ".reg .b32 al, bl;\n" \
                      "setp.ne.b32 p, %5, 0;\n" "setp.eq.b32 pt, %4, %4;\n" "mov.b32 al, %1;\n" "mov.b32 bl, %2;\n"
+#define IVF_MMA_ARGS ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory"
   if constexpr (NCTA == 2) {
-    if constexpr (KS == 2)
-      asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") IVF_MMA_STEP IVF_MMA1("2", "pt") "}\n" ::"r"(tmem_d), "r"(a_lo),
-                   "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-                   : "memory");
-    else
-      asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") IVF_MMA_STEP IVF_MMA1("2", "pt") IVF_MMA_STEP IVF_MMA1("2", "pt")
-                       IVF_MMA_STEP IVF_MMA1("2", "pt") "}\n" ::"r"(tmem_d),
-                   "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-                   : "memory");
+    if constexpr (KS == 1) asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 2) asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") IVF_MMA_NEXT("2") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 3)
+      asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") IVF_MMA_NEXT("2") IVF_MMA_NEXT("2") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 4)
+      asm volatile(IVF_MMA_HEAD IVF_MMA1("2", "p") IVF_MMA_NEXT("2") IVF_MMA_NEXT("2") IVF_MMA_NEXT("2") "}\n" IVF_MMA_ARGS);
   } else {
-    if constexpr (KS == 2)
-      asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") IVF_MMA_STEP IVF_MMA1("1", "pt") "}\n" ::"r"(tmem_d), "r"(a_lo),
-                   "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-                   : "memory");
-    else
-      asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") IVF_MMA_STEP IVF_MMA1("1", "pt") IVF_MMA_STEP IVF_MMA1("1", "pt")
-                       IVF_MMA_STEP IVF_MMA1("1", "pt") "}\n" ::"r"(tmem_d),
-                   "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-                   : "memory");
+    if constexpr (KS == 1) asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 2) asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") IVF_MMA_NEXT("1") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 3)
+      asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") IVF_MMA_NEXT("1") IVF_MMA_NEXT("1") "}\n" IVF_MMA_ARGS);
+    if constexpr (KS == 4)
+      asm volatile(IVF_MMA_HEAD IVF_MMA1("1", "p") IVF_MMA_NEXT("1") IVF_MMA_NEXT("1") IVF_MMA_NEXT("1") "}\n" IVF_MMA_ARGS);
   }
 #undef IVF_MMA1
-#undef IVF_MMA_STEP
+#undef IVF_MMA_NEXT
 #undef IVF_MMA_HEAD
+#undef IVF_MMA_ARGS
 }
 
 // commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs

@@ -324,23 +324,24 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   if (g < ngroups) {
                     const uint32_t a_lo = a_row + (uint32_t)g * a_grp, bg = b_lo + (uint32_t)g * b_grp16;
                     const uint32_t acc_g = g == 0 ? accum : 1u;
+                    // the K steps that hold real channels (the last chunk of a tap may have fewer)
+#define IVF_ISSUE_BLOCKS(KS)                                                                                       \
+  do {                                                                                                             \
+    umma_bf16_ksteps<KS, NCTA>(d0, a_lo, bg, desc_hi, idesc, acc_g);                                               \
+    if (nm > 1) umma_bf16_ksteps<KS, NCTA>(d0 + d_inc, a_lo + a_inc, bg, desc_hi, idesc, acc_g);                   \
+    if (nm > 2) umma_bf16_ksteps<KS, NCTA>(d0 + 2u * d_inc, a_lo + 2u * a_inc, bg, desc_hi, idesc, acc_g);         \
+    if (nm > 3) umma_bf16_ksteps<KS, NCTA>(d0 + 3u * d_inc, a_lo + 3u * a_inc, bg, desc_hi, idesc, acc_g);         \
+  } while (0)
                     if (ksteps == KSTEPS) {
-                      umma_bf16_ksteps<KSTEPS, NCTA>(d0, a_lo, bg, desc_hi, idesc, acc_g);
-                      if (nm > 1) umma_bf16_ksteps<KSTEPS, NCTA>(d0 + d_inc, a_lo + a_inc, bg, desc_hi, idesc, acc_g);
-                      if (nm > 2)
-                        umma_bf16_ksteps<KSTEPS, NCTA>(d0 + 2u * d_inc, a_lo + 2u * a_inc, bg, desc_hi, idesc, acc_g);
-                      if (nm > 3)
-                        umma_bf16_ksteps<KSTEPS, NCTA>(d0 + 3u * d_inc, a_lo + 3u * a_inc, bg, desc_hi, idesc, acc_g);
+                      IVF_ISSUE_BLOCKS(KSTEPS);
+                    } else if (ksteps == 1) {
+                      IVF_ISSUE_BLOCKS(1);
+                    } else if (ksteps == 2) {
+                      IVF_ISSUE_BLOCKS(2);
                     } else {
-                      uint32_t am = a_lo, d = d0;
-                      for (int m = mw; m < mt; m += mstep, am += a_inc, d += d_inc)
-                        for (int k = 0; k < ksteps; ++k) {
-                          if constexpr (NCTA == 2)
-                            umma_bf16_lo_pair(d, am + 2u * k, bg + 2u * k, desc_hi, idesc, k == 0 ? acc_g : 1u);
-                          else
-                            umma_bf16_lo(d, am + 2u * k, bg + 2u * k, desc_hi, idesc, k == 0 ? acc_g : 1u);
-                        }
+                      IVF_ISSUE_BLOCKS(3);
                     }
+#undef IVF_ISSUE_BLOCKS
                   }
                 }
               }
