@@ -58,7 +58,7 @@ constexpr int SLAB_ROLE_WARPS = 4;
 constexpr int SLAB_THREADS = 32 * SLAB_ROLE_WARPS + EPI_THREADS;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
-constexpr uint32_t SLAB_SMEM_BUDGET = 208u * 1024u;
+constexpr uint32_t SLAB_SMEM_BUDGET = 216u * 1024u;  // + 1 KB alignment slack + ~9.5 KB static = 227 KB
 constexpr int SLAB_MAX_COUT = 1024;  // per-channel epilogue vectors live in shared memory
 
 struct SlabParams {
@@ -77,6 +77,8 @@ struct SlabParams {
   int acc_stages;  // 2: epilogue of tile i overlaps the MMAs of tile i+1; 1: all TMEM columns for one tile
   int kch;
   int ncta;  // 1, or 2 = CTA pairs (cta_group::2)
+  uint32_t xch_off;  // kw-merge: byte offset (from the aligned dynamic shared memory base) of the boundary-row
+  int xch_seg;       // exchange [2 tile parities][4*mt segments][xch_seg floats], xch_seg = (kwm-1)^2 * bn
   int diag;  // IVF_SLAB_DIAG (timing experiments, results are garbage): bit 0 / 1 = after the ring has filled
              // once, the slab / weight producer signals "full" without loading
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
@@ -115,7 +117,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // per-channel epilogue vectors: s_scale = BN scale (AFFINE) or the producer's BN' mask scale (MASK; the two
   // are never combined on this path, the host checks), s_shift = BN shift
   __shared__ float s_scale[SLAB_MAX_COUT], s_shift[SLAB_MAX_COUT];
-  __shared__ float xch[4][576];  // kw-merge boundary rows: [quarter slot][((g-1)*(kwm-1) + row)*bn + column]
 
   constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
   constexpr uint32_t ROW16 = ROWB / 16;          // the same in descriptor (16-byte) units
@@ -385,6 +386,39 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = p.acc_stages == 2 ? (it & 1) : 0;
       mbar_wait(&t_full[acc], p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // this warp's chunks: [c_lo, c_hi)
+      const int nchunks = p.bn >> 4;
+      const int c_lo = 16 * (nchunks * cgrp / SLAB_EPI_GROUPS), c_hi = 16 * (nchunks * (cgrp + 1) / SLAB_EPI_GROUPS);
+      float* xbase = nullptr;
+      if (p.kwm > 1) {
+        // kw-merge, out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  The rows v+g
+        // that fall into the NEXT 32-row segment (next TMEM lane quarter, or quarter 0 of the next accumulator)
+        // come through shared memory.  Every warp first publishes the first kwm-1 rows of each of its segments
+        // for its columns, ONE barrier per tile makes them visible, then the tile is finished without further
+        // synchronisation (the exchange is double buffered by tile parity; the barrier of the next tile orders
+        // this tile's reads before the buffer is written again two tiles later).
+        const int kwm = p.kwm, bn = p.bn, seg = p.xch_seg;
+        xbase = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.xch_off) +
+                (size_t)(it & 1) * 4 * p.mt * seg;
+        for (int m = 0; m < p.mt; ++m) {
+          const int sidx = m * 4 + q;
+          if (sidx == 0) continue;  // nobody looks below the first segment
+          const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.mt + m) * p.slot);
+          float* xw = xbase + (size_t)sidx * seg;
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            for (int g = 1; g < kwm; ++g) {
+              uint32_t bt[16];
+              tmem_ld16(taddr + g * bn + c0, bt);
+              if (lane < kwm - 1) {
+                float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[j]);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows of the tile visible
+      }
       for (int m = 0; m < p.mt; ++m) {
         const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
         const int r = v / p.wp;
@@ -396,9 +430,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const size_t mask_row = pix * p.mask_ld + p.mask_coff;
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
                                (uint32_t)((acc * p.mt + m) * p.slot);
-        // this warp's chunks: [c_lo, c_hi)
-        const int nchunks = p.bn >> 4;
-        const int c_lo = 16 * (nchunks * cgrp / SLAB_EPI_GROUPS), c_hi = 16 * (nchunks * (cgrp + 1) / SLAB_EPI_GROUPS);
         EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
                      // the scheduler cover the latency
         if (p.kwm == 1) {
@@ -411,30 +442,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
           }
         } else {
-          // out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  Rows v+g of the
-          // next 32-row quarter (or of the next accumulator, served by quarter 0) come through shared memory:
-          // published once per accumulator for all columns (two block barriers per accumulator instead of one
-          // per 16-column chunk), the rest by warp shuffles.
           const int kwm = p.kwm, bn = p.bn;
-          const bool next_blk = (q == 0) && (m + 1 < p.mt);  // quarter 0 also serves quarter 3's boundary
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous accumulator are done
-          if (q > 0 || next_blk) {
-            float* xw = xch[q > 0 ? q - 1 : 3];
-            const uint32_t src_addr = q > 0 ? taddr : taddr + (uint32_t)p.slot;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-              for (int g = 1; g < kwm; ++g) {
-                uint32_t bt[16];
-                tmem_ld16(src_addr + g * bn + c0, bt);
-                if (lane < kwm - 1) {
-                  float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[j]);
-                }
-              }
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows visible
-          const float* xr = xch[q];
+          // the segment after this one (rows past the last segment of the tile are padding nobody stores)
+          const int snext = min(m * 4 + q + 1, 4 * p.mt - 1);
+          const float* xr = xbase + (size_t)snext * p.xch_seg;
           for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             epilogue_prefetch(ea, t.nt * bn + c0, out_row, mask_row, ok, cur);
             uint32_t tg[16];
@@ -444,7 +455,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[j]);
             for (int g = 1; g < kwm; ++g) {
               tmem_ld16(taddr + g * bn + c0, tg);
-              const int src = lane + g - 32;  // >= 0: the row lives in the next quarter
+              const int src = lane + g - 32;  // >= 0: the row lives in the next segment
               const float* xs = xr + ((g - 1) * (kwm - 1) + (src >= 0 ? src : 0)) * bn + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -663,10 +674,14 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         if (rows > 256) continue;
         const uint32_t a_stage =
             (((uint32_t)(mt_eff * 128 + (d->kh - 1) * wp + d->kw) * rowb) + 1023u) & ~1023u;
-        if (2 * a_stage + 2 * b_stage > SLAB_SMEM_BUDGET) continue;
+        // kw-merge: boundary-row exchange of the epilogue, [2 tile parities][4*mt segments][(kwm-1)^2 * bn] floats
+        const int xch_seg = kwm > 1 ? (kwm - 1) * (kwm - 1) * bn : 0;
+        const uint32_t xch_bytes = (uint32_t)(2 * 4 * mt_eff * xch_seg) * 4u;
+        const uint32_t budget = SLAB_SMEM_BUDGET - ((xch_bytes + 1023u) & ~1023u);
+        if (2 * a_stage + 2 * b_stage > budget) continue;
         int a_stages = 2;
-        if (3 * a_stage + 3 * b_stage <= SLAB_SMEM_BUDGET) a_stages = 3;
-        int b_stages = (int)((SLAB_SMEM_BUDGET - (uint32_t)a_stages * a_stage) / b_stage);
+        if (3 * a_stage + 3 * b_stage <= budget) a_stages = 3;
+        int b_stages = (int)((budget - (uint32_t)a_stages * a_stage) / b_stage);
         if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
         // ---- cost
         const double tiles = (double)d->n * d->id * ((htiles + ncta - 1) / ncta) * ntiles;  // work items
@@ -706,6 +721,8 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->acc_stages = acc_stages;
           p->a_stages = a_stages;
           p->b_stages = b_stages;
+          p->xch_seg = xch_seg;
+          p->xch_off = (uint32_t)a_stages * a_stage + (((uint32_t)b_stages * b_stage + 1023u) & ~1023u);
           p->a_stage_bytes = a_stage;
           p->b_stage_bytes = b_stage;
           p->b_tap_bytes = b_tap;
@@ -733,7 +750,7 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
                                   (int)(SLAB_SMEM_BUDGET + 1024)));
     h->slab_attr_set[slot] = true;
   }
-  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024;
+  const size_t smem = (size_t)p.xch_off + (size_t)2 * 4 * p.mt * p.xch_seg * 4 + 1024;
   const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
   if (NCTA == 1) {
@@ -860,7 +877,7 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
   plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
   plan[8] = d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
-  plan[9] = (int)(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes);
+  plan[9] = (int)(p.xch_off + 2u * 4u * (uint32_t)p.mt * (uint32_t)p.xch_seg * 4u);
   plan[10] = p.kwm;
   plan[11] = p.ncta;
   return 1;
