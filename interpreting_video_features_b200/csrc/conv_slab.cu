@@ -18,8 +18,8 @@
 // 24..96) would run at N/64 of the tensor rate.  For those the kwm filter taps of a row are stacked along
 // N: P_g[u] = sum_k A[u + kh*wp][k] * W[kh, kw=g][k], one MMA of N = kwm*bn for all g, accumulated over
 // (kd, kh, channel chunk) in TMEM, and the epilogue forms out[v] = sum_g P_g[v + g]: a row shift of g
-// between column blocks, done with warp shuffles plus a small shared-memory exchange of the first kwm-1
-// rows of the next 32-row quarter.
+// between column blocks, done with warp shuffles plus a shared-memory exchange of the first kwm-1 rows of
+// the next 32-row segment (published by every warp for its columns, one block barrier per tile).
 //
 // NCTA = 2 (cta_group::2): a CTA pair on one TPC works on two row-adjacent tiles in lockstep.  Each SM loads
 // its own slab and HALF of the weight rows; the leader CTA issues M = 256 MMAs that read both SMs' shared
