@@ -132,6 +132,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   if (threadIdx.x == 0) {
+    tma_prefetch_map(&tmA);  // descriptor fetch overlaps the set-up
+    tma_prefetch_map(&tmB);
     const uint32_t nissue = p.mt >= 2 ? 2u : 1u;  // MMA-issuing warps: each commits once per slot / tile
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(&a_full[s], 1);

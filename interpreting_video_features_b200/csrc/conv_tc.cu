@@ -111,6 +111,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kiters = p.ntaps * p.cchunks;
 
   if (threadIdx.x == 0) {
+    tma_prefetch_map(&tmA);  // descriptor fetch overlaps the set-up (first operands used to land ~2 us in)
+    tma_prefetch_map(&tmB);
+    if (p.ksplit > 0) tma_prefetch_map(&tmA2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -128,6 +131,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 64 && p.tma_store) {
+    tma_prefetch_map(&tmO);
+    if (p.split_cout > 0) tma_prefetch_map(&tmO2);
   }
   if (warp >= 2) {
     // per-channel epilogue vectors of this N tile
