@@ -101,3 +101,35 @@ def test_slab_plan_diagnostic_needs_no_gpu():
     assert plan((8, 56, 56), 64, 64, (1, 1, 1), (0, 0, 0))[0] == 0       # 1x1x1 -> im2col kernel (slab route opt-in)
     assert plan((2, 7, 7), 256, 832, (3, 3, 3), (1, 1, 1), 12)[0] == 1   # wide data gradient: 4+ N tiles
     assert plan((2, 4, 4), 64, 64, (3, 3, 3), (1, 1, 1))[0] == 0         # map narrower than 7 -> im2col kernel
+
+
+def test_shipped_tile_plans_are_accepted_by_the_kernel():
+    """plans_sm100.json (measured on a B200, tools/write_plans.py): every shape key parses into the descriptor
+    fields tune.py hashes, and every stored request is a plan ivf_conv_slab_plan still accepts for that shape -
+    a table that drifted from the kernel's constraints would silently fall back to the cost model."""
+    import ctypes as C
+    import json
+    import os
+    from interpreting_video_features_b200 import _lib, tune
+    path = os.path.join(os.path.dirname(tune.__file__), "plans_sm100.json")
+    table = json.load(open(path))
+    assert table["fields"] == list(tune._FIELDS)
+    lib = _lib.load()
+    n_req = 0
+    for key, req in table["plans"].items():
+        vals = [int(v) for v in key.split(",")]
+        assert len(vals) == len(tune._FIELDS)
+        d = _lib.ConvDesc()
+        for f, v in zip(tune._FIELDS, vals):
+            setattr(d, f, v)
+        d.sd = d.sh = d.sw = 1
+        assert tune.shape_key(d) == key
+        if req is None:
+            continue
+        n_req += 1
+        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = req
+        out = (C.c_int * 12)()
+        assert lib.ivf_conv_slab_plan(C.byref(d), 148, out) == 1, key
+        got = (out[10], out[3], out[5], out[11], out[2])  # kwm, mt, acc, ncta, ntiles
+        assert got == tuple(req), (key, req, got)
+    assert n_req >= 1
