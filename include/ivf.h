@@ -155,6 +155,17 @@ int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const void* dy, con
                       const float* acc_in, const void* mask_y, const float* mask_scale, void* dx,
                       void* stream);
 
+/* The same pair with a ReLU' bit mask: the forward also writes relu_bits[input pixel][c/8] (bit i of a byte =
+ * element 8*(c/8)+i > 0; bf16, c % 8 == 0), and the backward's MASK epilogue reads that byte instead of the
+ * 16 bytes of mask_y where its kernel supports it (the stride-2 pools; mask_y stays the fallback).  For the
+ * stage pools of I3D, whose input is a Unit3D / Inception output (pt/models/I3D_doubled.py:244-290), this
+ * removes ~230 MB of reads per 8-clip iteration.  relu_bits == NULL is the plain call. */
+int ivf_maxpool3d_fwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint8_t* argmax,
+                           uint8_t* relu_bits, void* stream);
+int ivf_maxpool3d_bwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* argmax,
+                           const float* acc_in, const void* mask_y, const uint8_t* relu_bits,
+                           const float* mask_scale, void* dx, void* stream);
+
 /* ---- I3D head (pt/models/I3D_doubled.py:360-371: avg_pool -> dropout(eval) -> 1x1x1 logits
  *      with bias -> squeeze -> softmax(dim=1)) ---------------------------------------
  * feat: [n][p][c] channels-last (p = all pooled positions; the pool must cover the whole map).

@@ -60,6 +60,8 @@ SIGNATURES = {
     "ivf_debug_read_scratch": (_I, [_P, _P, C.c_size_t]),
     "ivf_maxpool3d_fwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "ivf_maxpool3d_fwd_bits": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P]),
+    "ivf_maxpool3d_bwd_bits": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ivf_i3d_head_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
     "ivf_i3d_head_bwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "ivf_perturb_fwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -53,6 +53,15 @@ struct PoolGeoDyn {
   __device__ static int sw(const ivf_pool_desc& d) { return d.sw; }
 };
 
+// 8 bf16 -> one byte, bit i = (element i > 0).  A positive bf16 is a positive 16-bit integer (a positive NaN
+// counts as positive here, unlike the float compare; a ReLU output is never NaN unless its input was).
+__device__ __forceinline__ uint8_t relu_byte(const uint4& raw) {
+  const uint32_t m0 = __vcmpgts2(raw.x, 0u), m1 = __vcmpgts2(raw.y, 0u), m2 = __vcmpgts2(raw.z, 0u),
+                 m3 = __vcmpgts2(raw.w, 0u);
+  return (uint8_t)((m0 & 1u) | ((m0 >> 15) & 2u) | ((m1 & 1u) << 2) | ((m1 >> 13) & 8u) | ((m2 & 1u) << 4) |
+                   ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u));
+}
+
 // bf16 x 8 channels, packed arithmetic, one block row per output row.  The generic kernels below spend
 // ~5 instructions per channel per tap (convert, compare, two selects) plus 64-bit index arithmetic per
 // tap and are INSTRUCTION bound, not memory bound (ncu: 134 us for the 48 MB Mixed_3c pool; an
@@ -66,7 +75,7 @@ struct PoolGeoDyn {
 template <typename G>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                          uint8_t* __restrict__ argmax, int rows) {
+                          uint8_t* __restrict__ argmax, uint8_t* __restrict__ relu_bits, int rows) {
   const int row = blockIdx.z * gridDim.y + blockIdx.y;
   if (row >= rows) return;
   const int cv = d.c >> 3;
@@ -99,8 +108,16 @@ maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in,
       for (int e = 0; e < KW; ++e) {
         const uint32_t tap2 = (uint32_t)((a * KH + b) * KW + e) * 0x00010001u;
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
-        if (hok && (unsigned)(zw0 + e) < (unsigned)d.iw)
+        if (hok && (unsigned)(zw0 + e) < (unsigned)d.iw) {
           raw = *reinterpret_cast<const uint4*>(p0 + delta_row + e * d.in_ld);
+          // ReLU' bit mask of the INPUT for the backward pass (one bit per element instead of re-reading the
+          // producer's bf16 output there): every input element belongs to exactly one window origin - the taps
+          // below the stride - so that output's thread, which holds the element anyway, writes its byte
+          if (relu_bits && a < SD && b < SH && e < SW) {
+            const int ipix = pix0 + (a * d.ih + b) * d.iw + e;
+            relu_bits[(long long)ipix * cv + (c >> 3)] = relu_byte(raw);
+          }
+        }
         const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -330,8 +347,8 @@ template <typename G>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_s2patch_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy,
                            const uint8_t* __restrict__ argmax, const float* __restrict__ acc_in,
-                           const __nv_bfloat16* __restrict__ mask_y, const float* __restrict__ mask_scale,
-                           void* __restrict__ dx, int rows, int qhn, int qwn) {
+                           const __nv_bfloat16* __restrict__ mask_y, const uint8_t* __restrict__ relu_bits,
+                           const float* __restrict__ mask_scale, void* __restrict__ dx, int rows, int qhn, int qwn) {
   const int row = blockIdx.z * gridDim.y + blockIdx.y;
   if (row >= rows) return;
   const int cv = d.c >> 3;
@@ -408,7 +425,11 @@ maxpool_bwd_s2patch_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy
           gg[4 * i + 3] += a4.w;
         }
       }
-      if (d.flags & IVF_EP_MASK) {
+      if ((d.flags & IVF_EP_MASK) && relu_bits) {  // the forward pass left one bit per element
+        const uint32_t by = relu_bits[(long long)ipix * cv + (c >> 3)];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gg[i] = ((by >> i) & 1u) ? gg[i] * sc[i] : 0.f;
+      } else if (d.flags & IVF_EP_MASK) {
         const uint4 rawy = *reinterpret_cast<const uint4*>(mask_y + (long long)ipix * d.mask_ld + d.mask_coff + c);
         const uint32_t yw[4] = {rawy.x, rawy.y, rawy.z, rawy.w};
 #pragma unroll
@@ -826,7 +847,7 @@ int pool_blocks(ivf_handle* h, long long total) {
 
 template <typename T>
 int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint8_t* argmax,
-          cudaStream_t st) {
+          uint8_t* relu_bits, cudaStream_t st) {
   constexpr int V = full_vec<T>();
   long long opix = (long long)d->n * d->od * d->oh * d->ow;
   const int threads = 256;
@@ -838,7 +859,7 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
           const char* e = getenv("IVF_POOL_S1COL");
           return !e || atoi(e) != 0;
         }();
-        if (col_on && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 &&
+        if (col_on && !relu_bits && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 &&
             d->od == d->id && d->oh == d->ih && d->ow == d->iw && d->od >= 2) {
           // depth segments: enough threads to fill the machine, at least 4 outputs per thread when split
           long long threads_total = (long long)d->n * d->oh * d->ow * (d->c / V);
@@ -854,14 +875,16 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
         }
         const int rows = d->n * d->od * d->oh;
         IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G><<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
-            *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows)));
+            *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, relu_bits, rows)));
         IVF_LAUNCHED(h);
         return IVF_OK;
       }
     }
+    IVF_REQUIRE(!relu_bits, "maxpool(fwd): the ReLU bit mask needs the packed bf16 kernel (bf16, 31-bit offsets)");
     IVF_POOL_GEO_DISPATCH((maxpool_fwd_kernel<T, V, G><<<pool_blocks(h, total), threads, 0, st>>>(
         *d, (const T*)in, (T*)out, argmax, total)));
   } else {
+    IVF_REQUIRE(!relu_bits, "maxpool(fwd): the ReLU bit mask needs 8-channel aligned bf16 tensors");
     long long total = opix * d->c;
     maxpool_fwd_kernel<T, 1, PoolGeoDyn><<<pool_blocks(h, total), threads, 0, st>>>(*d, (const T*)in, (T*)out,
                                                                                   argmax, total);
@@ -936,7 +959,7 @@ int launch_bwd_scatter(ivf_handle* h, const ivf_pool_desc* d, const ScatterPlan&
 
 template <typename T>
 int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* argmax,
-          const float* acc_in, const void* mask_y, const float* mask_scale, void* dx,
+          const float* acc_in, const void* mask_y, const uint8_t* relu_bits, const float* mask_scale, void* dx,
           cudaStream_t st) {
   constexpr int V = full_vec<T>();
   long long ipix = (long long)d->n * d->id * d->ih * d->iw;
@@ -972,7 +995,7 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
           const dim3 pgrid = row_grid(prow, qwn * (d->c / V));
 #define IVF_S2PATCH(GEO)                                                                                   \
   maxpool_bwd_s2patch_kernel<GEO><<<pgrid, threads, 0, st>>>(*d, (const __nv_bfloat16*)dy, argmax, acc_in, \
-                                                             (const __nv_bfloat16*)mask_y, mask_scale, dx, prow, qhn, qwn)
+                                                             (const __nv_bfloat16*)mask_y, relu_bits, mask_scale, dx, prow, qhn, qwn)
           if (d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1) IVF_S2PATCH(GeoStem);
           else if (d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 2) IVF_S2PATCH(Geo3s2);
           else if (d->kd == 2 && d->kh == 2 && d->kw == 2 && d->sd == 2) IVF_S2PATCH(Geo2s2);
@@ -1003,19 +1026,31 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
 
 }  // namespace
 
-extern "C" int ivf_maxpool3d_fwd(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
-                                 uint8_t* argmax, void* stream) {
+extern "C" int ivf_maxpool3d_fwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
+                                      uint8_t* argmax, uint8_t* relu_bits, void* stream) {
   IVF_REQUIRE(h && d && in && out, "ivf_maxpool3d_fwd: null argument");
   int rc = check_pool(d);
   if (rc) return rc;
+  if (relu_bits) {
+    // every input element must lie in the patch of some window origin, or its bits would never be written
+    IVF_REQUIRE(d->dtype == IVF_BF16 && d->c % 8 == 0, "ivf_maxpool3d_fwd_bits: bf16, channels a multiple of 8");
+    IVF_REQUIRE((d->id - 1 + d->pd) / d->sd < d->od && (d->ih - 1 + d->ph) / d->sh < d->oh &&
+                    (d->iw - 1 + d->pw) / d->sw < d->ow && d->kd >= d->sd && d->kh >= d->sh && d->kw >= d->sw,
+                "ivf_maxpool3d_fwd_bits: windows do not cover the input");
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  return d->dtype == IVF_F32 ? fwd_t<float>(h, d, in, out, argmax, st)
-                             : fwd_t<__nv_bfloat16>(h, d, in, out, argmax, st);
+  return d->dtype == IVF_F32 ? fwd_t<float>(h, d, in, out, argmax, relu_bits, st)
+                             : fwd_t<__nv_bfloat16>(h, d, in, out, argmax, relu_bits, st);
 }
 
-extern "C" int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const void* dy,
-                                 const uint8_t* argmax, const float* acc_in, const void* mask_y,
-                                 const float* mask_scale, void* dx, void* stream) {
+extern "C" int ivf_maxpool3d_fwd(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
+                                 uint8_t* argmax, void* stream) {
+  return ivf_maxpool3d_fwd_bits(h, d, in, out, argmax, nullptr, stream);
+}
+
+extern "C" int ivf_maxpool3d_bwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* dy,
+                                      const uint8_t* argmax, const float* acc_in, const void* mask_y,
+                                      const uint8_t* relu_bits, const float* mask_scale, void* dx, void* stream) {
   IVF_REQUIRE(h && d && dy && argmax && dx, "ivf_maxpool3d_bwd: null argument");
   int rc = check_pool(d);
   if (rc) return rc;
@@ -1023,6 +1058,12 @@ extern "C" int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const vo
   if (d->flags & IVF_EP_MASK) IVF_REQUIRE(mask_y && mask_scale, "ivf_maxpool3d_bwd: MASK needs mask_y/mask_scale");
   cudaStream_t st = (cudaStream_t)stream;
   return d->dtype == IVF_F32
-             ? bwd_t<float>(h, d, dy, argmax, acc_in, mask_y, mask_scale, dx, st)
-             : bwd_t<__nv_bfloat16>(h, d, dy, argmax, acc_in, mask_y, mask_scale, dx, st);
+             ? bwd_t<float>(h, d, dy, argmax, acc_in, mask_y, relu_bits, mask_scale, dx, st)
+             : bwd_t<__nv_bfloat16>(h, d, dy, argmax, acc_in, mask_y, relu_bits, mask_scale, dx, st);
+}
+
+extern "C" int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const void* dy,
+                                 const uint8_t* argmax, const float* acc_in, const void* mask_y,
+                                 const float* mask_scale, void* dx, void* stream) {
+  return ivf_maxpool3d_bwd_bits(h, d, dy, argmax, acc_in, mask_y, nullptr, mask_scale, dx, stream);
 }

@@ -271,10 +271,16 @@ class I3DEngine:
                 od, oh, ow = out_dims(x, k, s)
                 out = new_act(B, od, oh, ow, x.c)
                 am = torch.empty((out.pixels, x.c), dtype=torch.uint8, device=dev)
-                self.fwd_ops.append((0, lambda x=x, out=out, am=am, k=k, s=s, pads=pads:
-                                     ops.maxpool3d_fwd(x, out, am, k, s, pads)))
+                # ReLU' bit mask of the pool's input, written by the forward kernel: the backward then reads one
+                # byte per 8 channels instead of the producer's bf16 output (bf16 stride-2 pools only)
+                bits = None
+                if (mode == "bf16" and x.c % 8 == 0 and min(s[1:]) >= 2 and stages and stages[-1]["scale"] is not None
+                        and os.environ.get("IVF_POOL_BITS", "0") != "0"):
+                    bits = torch.empty((x.pixels, x.c // 8), dtype=torch.uint8, device=dev)
+                self.fwd_ops.append((0, lambda x=x, out=out, am=am, k=k, s=s, pads=pads, bits=bits:
+                                     ops.maxpool3d_fwd(x, out, am, k, s, pads, relu_bits=bits)))
                 stages.append(dict(kind="pool", name=name, x=x, out=out, scale=None, gout=out.like(), argmax=am,
-                                   k=k, s=s, pads=pads))
+                                   k=k, s=s, pads=pads, bits=bits))
             else:  # Inception module
                 rec = self._build_inception(sd, name, x, new_act, add_unit_fwd)
                 stages.append(rec)
@@ -319,7 +325,8 @@ class I3DEngine:
             elif st["kind"] == "pool":
                 self.bwd_ops.append((0, lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
                                      ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
-                                                       mask=mask, mask_scale=mscale)))
+                                                       mask=mask, mask_scale=mscale,
+                                                       relu_bits=st["bits"] if mask is not None else None)))
             else:
                 self._build_inception_bwd(st, g_in, mask, mscale, add_unit_bwd)
 

@@ -136,15 +136,17 @@ def _pool_desc(x, out, kernel, stride, pad_front, mask=None, flags=0):
     return d
 
 
-def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front):
+def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front, relu_bits=None):
+    """relu_bits: optional uint8 [x.pixels, c/8] that receives one bit per input element (element > 0) for the
+    backward pass (ivf_maxpool3d_fwd_bits)."""
     d = _pool_desc(x, out, kernel, stride, pad_front)
     d.dtype = _lib.dtype_code(x.buf)
-    check(_lib.load().ivf_maxpool3d_fwd(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(out.buf),
-                                        ptr(argmax), _lib.stream_ptr()), "ivf_maxpool3d_fwd")
+    check(_lib.load().ivf_maxpool3d_fwd_bits(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(out.buf),
+                                             ptr(argmax), ptr(relu_bits), _lib.stream_ptr()), "ivf_maxpool3d_fwd")
     return out
 
 
-def maxpool3d_bwd(dy, argmax, dx, kernel, stride, pad_front, acc_in=None, mask=None, mask_scale=None):
+def maxpool3d_bwd(dy, argmax, dx, kernel, stride, pad_front, acc_in=None, mask=None, mask_scale=None, relu_bits=None):
     """dx (Act shaped like the pool input) from dy (Act shaped like the pool output)."""
     flags = 0
     if acc_in is not None:
@@ -155,10 +157,10 @@ def maxpool3d_bwd(dy, argmax, dx, kernel, stride, pad_front, acc_in=None, mask=N
         flags |= EP_OUT_F32
     d = _pool_desc(dx, dy, kernel, stride, pad_front, mask, flags)
     d.dtype = _lib.dtype_code(dy.buf)
-    check(_lib.load().ivf_maxpool3d_bwd(_lib.handle(dy.buf.device), C.byref(d), ptr(dy.buf), ptr(argmax),
-                                        ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
-                                        ptr(mask.buf if mask is not None else None), ptr(mask_scale),
-                                        ptr(dx.buf), _lib.stream_ptr()), "ivf_maxpool3d_bwd")
+    check(_lib.load().ivf_maxpool3d_bwd_bits(_lib.handle(dy.buf.device), C.byref(d), ptr(dy.buf), ptr(argmax),
+                                             ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
+                                             ptr(mask.buf if mask is not None else None), ptr(relu_bits),
+                                             ptr(mask_scale), ptr(dx.buf), _lib.stream_ptr()), "ivf_maxpool3d_bwd")
     return dx
 
 

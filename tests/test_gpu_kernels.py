@@ -399,6 +399,24 @@ def test_maxpool_backward_epilogues_bf16(dev, case, flags):
         want = torch.where(x.detach() > 0, gx * sc5, torch.zeros_like(gx)).bfloat16().float()
         tol = 1e-2
     torch.testing.assert_close(dx.ncdhw().float().cpu(), want, rtol=tol, atol=tol)
+    if flags != "plain" and s[1] == 2:
+        # the same through the ReLU' bit mask the forward kernel writes (ivf_maxpool3d_fwd_bits / _bwd_bits)
+        bits = torch.zeros((xa.pixels, c // 8), dtype=torch.uint8, device=dev)
+        out2 = Act.empty(2, *od, c, torch.bfloat16, dev)
+        am2 = torch.empty_like(am)
+        ops.maxpool3d_fwd(xa, out2, am2, k, s, pf, relu_bits=bits)
+        assert torch.equal(am2, am) and torch.equal(out2.buf, out.buf)
+        xcl = x.detach().permute(0, 2, 3, 4, 1).reshape(-1, c // 8, 8)
+        want_bits = ((xcl > 0).to(torch.int32) << torch.arange(8)).sum(-1).to(torch.uint8)
+        assert torch.equal(bits.cpu(), want_bits), "ReLU bit mask of the pool input"
+        poison = Act(torch.full_like(xa.buf, float("nan")), xa.n, xa.d, xa.h, xa.w, xa.ld, xa.coff, xa.c)
+        if flags == "accum_mask_f32":
+            dx2 = to_act(acc.to(dev), torch.float32)
+            ops.maxpool3d_bwd(dy, am, dx2, k, s, pf, acc_in=dx2, mask=poison, mask_scale=scale.to(dev), relu_bits=bits)
+        else:
+            dx2 = xa.like(zero=True)
+            ops.maxpool3d_bwd(dy, am, dx2, k, s, pf, mask=poison, mask_scale=scale.to(dev), relu_bits=bits)
+        assert torch.equal(dx2.buf, dx.buf), "bit-mask backward == bf16-mask backward (mask tensor not read)"
 
 
 # ----------------------------------------------------------------------------- head
