@@ -39,7 +39,8 @@ enum {
   IVF_EINVAL = 1,       /* bad argument / inconsistent descriptor            */
   IVF_EUNSUPPORTED = 2, /* valid request this build has no kernel for        */
   IVF_ECUDA = 3,        /* CUDA runtime / driver error                       */
-  IVF_ENOGPU = 4        /* no sm_100 device                                  */
+  IVF_ENOGPU = 4,       /* no sm_100 device                                  */
+  IVF_EWORKSPACE = 5    /* caller-owned workspace missing or too small       */
 };
 
 enum { IVF_F32 = 0, IVF_BF16 = 1 };
@@ -171,9 +172,14 @@ int ivf_maxpool3d_bwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* dy
  * feat: [n][p][c] channels-last (p = all pooled positions; the pool must cover the whole map).
  * out: fp32 [n][ncls] probabilities (softmax != 0) or logits.  With p == 1 this is the
  * Linear(+Softmax) classifier of the ConvLSTM model (pt/models/CLSTM_4.py:78-83).      */
+/* workspace: caller-owned fp32 buffer of ivf_i3d_head_workspace_bytes(n, c, ncls) bytes that holds the
+ * per-chunk partial logits between the two launches of the forward.  It belongs to the CALLER (one per
+ * engine), not to the handle: two engines driven from one thread on different streams (clip groups on
+ * parallel CUDA-graph branches) must not share it. */
+size_t ivf_i3d_head_workspace_bytes(int n, int c, int ncls);
 int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int n, int p, int c, int ld,
                      const float* w, const float* b, int ncls, int softmax, float* logits,
-                     float* out, void* stream);
+                     float* out, float* workspace, size_t workspace_bytes, void* stream);
 /* dfeat[n][p][c] = epilogue( (1/p) * W^T * dlogits ), dlogits from dout through softmax'. */
 int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, int ld, const float* w,
                      int ncls, int softmax, const float* out, const float* dout, int flags,

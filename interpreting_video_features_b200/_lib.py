@@ -62,7 +62,8 @@ SIGNATURES = {
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ivf_maxpool3d_fwd_bits": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd_bits": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "ivf_i3d_head_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "ivf_i3d_head_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "ivf_i3d_head_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "ivf_i3d_head_bwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "ivf_perturb_fwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ivf_perturb_bwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
@@ -138,8 +139,22 @@ def launch_count(device=None):
     return int(load().ivf_launch_count(handle(device)))
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The caller's stream ON THE DEVICE THE BUFFERS LIVE ON (not the thread's current device): an engine built
+    for cuda:1 can be driven while cuda:0 is current."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(fn):
+    """Method decorator: run with self.device current (streams, graph capture and allocations made inside follow
+    the current device; the C ABI guards itself by handle, this covers the torch side)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 def ptr(t):

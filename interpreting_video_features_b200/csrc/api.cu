@@ -57,6 +57,7 @@ extern "C" int64_t ivf_launch_count(const ivf_handle* h) { return h ? h->launche
 extern "C" int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                           const float* scale, const float* shift, const float* acc_in,
                           const void* mask_y, const float* mask_scale, void* out, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && in && w && out, "ivf_conv3d: null argument");
   IVF_REQUIRE(d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->od > 0 && d->oh > 0 &&
                   d->ow > 0 && d->cin > 0 && d->cout > 0,
@@ -84,6 +85,7 @@ extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf
                                 const void* in2, const void* w, const float* scale, const float* shift,
                                 const float* acc_in, const void* mask_y, const float* mask_scale, void* out,
                                 void* out2, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && sp && in && w && out, "ivf_conv3d_split: null argument");
   IVF_REQUIRE(d->dtype == IVF_BF16, "ivf_conv3d_split: bf16 only");
   IVF_REQUIRE(d->kd == 1 && d->kh == 1 && d->kw == 1 && d->sd == 1 && d->sh == 1 && d->sw == 1 && !d->transposed &&
@@ -121,6 +123,7 @@ extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf
 // Diagnostic: copy the first `bytes` of the handle's scratch buffer to the host (kernel traces written under
 // IVF_TC_TRACE=1).  Synchronises the device.
 extern "C" int ivf_debug_read_scratch(ivf_handle* h, void* dst, size_t bytes) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && dst && bytes <= h->scratch_bytes, "ivf_debug_read_scratch: bad argument");
   IVF_CUDA(cudaDeviceSynchronize());
   IVF_CUDA(cudaMemcpy(dst, h->scratch, bytes, cudaMemcpyDeviceToHost));

@@ -319,6 +319,7 @@ int grid_for(ivf_handle* h, long long total) {
 extern "C" int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, const float* c_prev,
                                    int m, int hid, float* c_next, void* h_next, float* gate_act,
                                    void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && pre && c_next && h_next, "ivf_clstm_gates_fwd: null argument");
   IVF_REQUIRE(m > 0 && hid > 0, "ivf_clstm_gates_fwd: bad extent");
   long long total = (long long)m * hid;
@@ -342,6 +343,7 @@ extern "C" int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, c
 extern "C" int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_act,
                                    const float* c_prev, const float* c_next, const float* dh,
                                    float* dc_io, int m, int hid, void* dgates, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && gate_act && c_next && dh && dc_io && dgates, "ivf_clstm_gates_bwd: null argument");
   IVF_REQUIRE(m > 0 && hid > 0, "ivf_clstm_gates_bwd: bad extent");
   long long total = (long long)m * hid;
@@ -365,6 +367,7 @@ extern "C" int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_a
 extern "C" int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n, int hh, int ww, int c,
                                  const float* scale, const float* shift, void* y, uint8_t* argmax,
                                  int s2d, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && x && y && argmax, "ivf_bn_pool2d_fwd: null argument");
   IVF_REQUIRE(n > 0 && hh >= 2 && ww >= 2 && c > 0, "ivf_bn_pool2d_fwd: bad extent");
   if (s2d) IVF_REQUIRE((hh / 2) % 2 == 0 && (ww / 2) % 2 == 0, "ivf_bn_pool2d_fwd: s2d needs an even pooled map");
@@ -389,6 +392,7 @@ extern "C" int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n,
 extern "C" int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* argmax, int n,
                                  int hh, int ww, int c, const float* scale, const float* acc_in,
                                  float* dx, int s2d, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && dy && argmax && dx, "ivf_bn_pool2d_bwd: null argument");
   IVF_REQUIRE(n > 0 && hh >= 2 && ww >= 2 && c > 0, "ivf_bn_pool2d_bwd: bad extent");
   long long total = (long long)n * hh * ww * c;

@@ -32,6 +32,22 @@ struct ivf_handle {
 
 void ivf_set_error(const char* fmt, ...);
 
+// Every entry point that takes a handle issues its work on the handle's device, whatever device is current
+// in the calling thread (an engine built for cuda:1 may be driven while cuda:0 is current): switch for the
+// duration of the call, restore on return.  cudaGetDevice is a thread-local read; no switch, no cost.
+struct ivf_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit ivf_device_guard(const ivf_handle* h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device)
+      switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~ivf_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define IVF_ON_DEVICE(h) ivf_device_guard ivf_guard__(h)
+
 #define IVF_FAIL(code, ...)       \
   do {                            \
     ivf_set_error(__VA_ARGS__);   \

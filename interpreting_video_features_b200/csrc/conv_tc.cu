@@ -753,6 +753,7 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
 
 extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0,
                                 int tap, int c0, void* tile_out, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && in && tile_out, "ivf_probe_im2col: null argument");
   int rc = check_bf16_desc(d);
   if (rc) return rc;

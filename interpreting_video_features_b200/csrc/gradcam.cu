@@ -127,6 +127,7 @@ extern "C" int ivf_gradcam(ivf_handle* h, int act_dtype, int grad_dtype, const v
                            const void* grad, int n, int tp, int hp, int wp, int c, int ld, int step,
                            int hout, int wout, int per_frame, float* cam, float* cam_lowres,
                            void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && act && grad && cam, "ivf_gradcam: null argument");
   IVF_REQUIRE(n > 0 && tp > 0 && hp > 0 && wp > 0 && c > 0 && ld >= c && step > 0 && hout > 0 && wout > 0,
               "ivf_gradcam: bad extent");

@@ -249,14 +249,22 @@ head_bwd_kernel(int p, int c, int ld, const float* __restrict__ w, int ncls, int
 
 }  // namespace
 
+extern "C" size_t ivf_i3d_head_workspace_bytes(int n, int c, int ncls) {
+  if (n <= 0 || c <= 0 || ncls <= 0) return 0;
+  return (size_t)n * ((c + HEAD_CHUNK - 1) / HEAD_CHUNK) * ncls * sizeof(float);
+}
+
 extern "C" int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int n, int p, int c,
                                 int ld, const float* w, const float* b, int ncls, int softmax,
-                                float* logits, float* out, void* stream) {
-  IVF_REQUIRE(h && feat && w && out, "ivf_i3d_head_fwd: null argument");
+                                float* logits, float* out, float* workspace, size_t workspace_bytes,
+                                void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && feat && w && out && workspace, "ivf_i3d_head_fwd: null argument");
   IVF_REQUIRE(n > 0 && p > 0 && c > 0 && ncls > 0 && ld >= c, "ivf_i3d_head_fwd: bad extent");
   const int nchunks = (c + HEAD_CHUNK - 1) / HEAD_CHUNK;
   size_t need = (size_t)n * nchunks * ncls * sizeof(float);
-  IVF_REQUIRE(need <= h->scratch_bytes, "ivf_i3d_head_fwd: n*c*ncls too large for the handle scratch (%zu B)", need);
+  if (need > workspace_bytes)
+    IVF_FAIL(IVF_EWORKSPACE, "ivf_i3d_head_fwd: workspace of %zu bytes, %zu needed", workspace_bytes, need);
   IVF_REQUIRE((size_t)ncls * sizeof(float) <= 48 * 1024, "ivf_i3d_head_fwd: ncls too large");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(n, nchunks);
@@ -264,7 +272,7 @@ extern "C" int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int 
   const size_t pair_bytes = dtype == IVF_F32 ? 8 : 4;
   const bool vec2 = c % 2 == 0 && ld % 2 == 0 && (uintptr_t)feat % pair_bytes == 0 && (uintptr_t)w % 8 == 0;
 #define IVF_HEAD_FWD(T, V) \
-  head_fwd_partial_kernel<T, V><<<grid, HEAD_THREADS, 0, st>>>((const T*)feat, p, c, ld, w, ncls, h->scratch)
+  head_fwd_partial_kernel<T, V><<<grid, HEAD_THREADS, 0, st>>>((const T*)feat, p, c, ld, w, ncls, workspace)
   if (dtype == IVF_F32) {
     if (vec2) IVF_HEAD_FWD(float, true); else IVF_HEAD_FWD(float, false);
   } else {
@@ -272,7 +280,7 @@ extern "C" int ivf_i3d_head_fwd(ivf_handle* h, int dtype, const void* feat, int 
   }
 #undef IVF_HEAD_FWD
   IVF_LAUNCHED(h);
-  head_fwd_finish_kernel<<<n, HEAD_THREADS, ncls * sizeof(float), st>>>(h->scratch, nchunks, b, ncls, softmax, logits,
+  head_fwd_finish_kernel<<<n, HEAD_THREADS, ncls * sizeof(float), st>>>(workspace, nchunks, b, ncls, softmax, logits,
                                                                         out);
   IVF_LAUNCHED(h);
   return IVF_OK;
@@ -282,6 +290,7 @@ extern "C" int ivf_i3d_head_bwd(ivf_handle* h, int dtype, int n, int p, int c, i
                                 const float* w, int ncls, int softmax, const float* out,
                                 const float* dout, int flags, const void* mask_y, int mask_ld,
                                 int mask_coff, const float* mask_scale, void* dfeat, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && w && out && dout && dfeat, "ivf_i3d_head_bwd: null argument");
   IVF_REQUIRE(n > 0 && p > 0 && c > 0 && ncls > 0 && ld >= c, "ivf_i3d_head_bwd: bad extent");
   if (flags & IVF_EP_MASK) IVF_REQUIRE(mask_y && mask_scale, "ivf_i3d_head_bwd: MASK needs mask_y/mask_scale");

@@ -143,6 +143,7 @@ extern "C" int ivf_mask_loss_adam(ivf_handle* h, float* m, float* exp_avg, float
                                   float lam1,
                                   float lam2, float lr, float beta1, float beta2, float eps,
                                   float* losses, float* sig_out, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && m && exp_avg && exp_avg_sq, "ivf_mask_loss_adam: null argument");
   IVF_REQUIRE(nclip > 0 && t > 0 && t <= MAX_T && (step >= 1 || step_dev),
               "ivf_mask_loss_adam: bad nclip/t/step");
@@ -155,6 +156,7 @@ extern "C" int ivf_mask_loss_adam(ivf_handle* h, float* m, float* exp_avg, float
 }
 
 extern "C" int ivf_sigmoid(ivf_handle* h, const float* m, float* out, int count, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && m && out && count > 0, "ivf_sigmoid: bad argument");
   sigmoid_kernel<<<ivf_cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(m, out, count);
   IVF_LAUNCHED(h);
@@ -163,6 +165,7 @@ extern "C" int ivf_sigmoid(ivf_handle* h, const float* m, float* out, int count,
 
 extern "C" int ivf_tv_norm(ivf_handle* h, const float* mask, int t, float p, float q, float* val,
                            float* dmask, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && mask && val, "ivf_tv_norm: null argument");
   IVF_REQUIRE(t > 0 && t <= MAX_T, "ivf_tv_norm: bad t");
   tv_norm_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(mask, t, p, q, val, dmask);

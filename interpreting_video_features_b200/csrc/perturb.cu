@@ -490,6 +490,7 @@ int check_common(int mode, int b, int c, int t, int hh, int ww, int out_fmt) {
 extern "C" int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const float* mask,
                                int mask_bstride, int b, int c, int t, int hh, int ww, int out_fmt,
                                void* out, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && x && mask && out, "ivf_perturb_fwd: null argument");
   int rc = check_common(mode, b, c, t, hh, ww, out_fmt);
   if (rc) return rc;
@@ -528,6 +529,7 @@ extern "C" int ivf_perturb_fwd(ivf_handle* h, int mode, const float* x, const fl
 extern "C" int ivf_perturb_bwd(ivf_handle* h, int mode, const float* x, const float* mask,
                                int mask_bstride, int b, int c, int t, int hh, int ww, int out_fmt,
                                int gout_dtype, const void* gout, float* dmask, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && x && mask && gout && dmask, "ivf_perturb_bwd: null argument");
   int rc = check_common(mode, b, c, t, hh, ww, out_fmt);
   if (rc) return rc;

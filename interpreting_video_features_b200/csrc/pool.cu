@@ -1028,6 +1028,7 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
 
 extern "C" int ivf_maxpool3d_fwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
                                       uint8_t* argmax, uint8_t* relu_bits, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && in && out, "ivf_maxpool3d_fwd: null argument");
   int rc = check_pool(d);
   if (rc) return rc;
@@ -1045,12 +1046,14 @@ extern "C" int ivf_maxpool3d_fwd_bits(ivf_handle* h, const ivf_pool_desc* d, con
 
 extern "C" int ivf_maxpool3d_fwd(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
                                  uint8_t* argmax, void* stream) {
+  IVF_ON_DEVICE(h);
   return ivf_maxpool3d_fwd_bits(h, d, in, out, argmax, nullptr, stream);
 }
 
 extern "C" int ivf_maxpool3d_bwd_bits(ivf_handle* h, const ivf_pool_desc* d, const void* dy,
                                       const uint8_t* argmax, const float* acc_in, const void* mask_y,
                                       const uint8_t* relu_bits, const float* mask_scale, void* dx, void* stream) {
+  IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && dy && argmax && dx, "ivf_maxpool3d_bwd: null argument");
   int rc = check_pool(d);
   if (rc) return rc;
@@ -1065,5 +1068,6 @@ extern "C" int ivf_maxpool3d_bwd_bits(ivf_handle* h, const ivf_pool_desc* d, con
 extern "C" int ivf_maxpool3d_bwd(ivf_handle* h, const ivf_pool_desc* d, const void* dy,
                                  const uint8_t* argmax, const float* acc_in, const void* mask_y,
                                  const float* mask_scale, void* dx, void* stream) {
+  IVF_ON_DEVICE(h);
   return ivf_maxpool3d_bwd_bits(h, d, dy, argmax, acc_in, mask_y, nullptr, mask_scale, dx, stream);
 }

@@ -178,6 +178,7 @@ class I3DEngine:
         self.B, (self.T, self.H, self.W) = batch, clip
         self.C = in_channels
         self.softmax = bool(softmax)
+        self.generation = 0  # bumped by everything that overwrites activations or dprobs
         stride_mods = stride_mods or {}
         dev = self.device
         B = batch
@@ -301,8 +302,9 @@ class I3DEngine:
         self.logits = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
         self.probs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
         self.dprobs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
+        self.head_ws = ops.head_workspace(B, feat.c, self.num_classes, dev)  # this engine's partial logits
         self.fwd_ops.append((0, lambda: ops.head_fwd(feat, self.w_logits, self.b_logits, self.softmax, self.probs,
-                                                     self.logits)))
+                                                     self.logits, workspace=self.head_ws)))
         # Grad-CAM reads the raw (unmasked) gradient w.r.t. Mixed_5c in fp32
         self.g_feat_raw = feat.like(torch.float32)
 
@@ -469,14 +471,17 @@ class I3DEngine:
                 with torch.cuda.stream(self._side[item[0] - 1]):
                     item[1]()
 
+    @_lib.on_device
     def forward(self, mask=None, perturb="freeze"):
         """Perturb (mask: sigmoid-ed values [T] or [B,T]; None = unperturbed clip) and run the network.
         Returns the [B, classes] probability (or logit) buffer — a live buffer, not a copy."""
         self._mask, self._perturb = (self.zero_mask if mask is None else mask), perturb
+        self.generation += 1  # the activations of any earlier forward are gone (autograd nodes check this)
         ops.perturb_fwd(self.x, self._mask, perturb, self.in_fmt, self.xin.buf)
         self._run(self.fwd_ops)
         return self.probs
 
+    @_lib.on_device
     def forward_graphed(self):
         """forward(None) - the unperturbed clip in the static input buffer - replayed from a CUDA graph captured
         on first use.  The eager forward is ~60 launches at ~35 us of host time each: launch bound for Grad-CAM,
@@ -488,9 +493,11 @@ class I3DEngine:
             with torch.cuda.graph(g):
                 self.forward(None)
             self._fwd_graph = g
+        self.generation += 1
         self._fwd_graph.replay()
         return self.probs
 
+    @_lib.on_device
     def backward(self, to_mask=True):
         """Data-gradient pass from self.dprobs; returns d(sum dprobs*probs)/dmask [B,T] (live buffer)."""
         self._run(self.bwd_ops)
@@ -498,11 +505,14 @@ class I3DEngine:
             ops.perturb_bwd(self.x, self._mask, self._perturb, self.in_fmt, self.g_xin.buf, self.dm)
         return self.dm
 
+    @_lib.on_device
     def set_targets(self, targets):
         """dprobs = one-hot(targets): the class_loss of pt/FindMasksComparison_I3D_smth.py:205."""
+        self.generation += 1
         self.dprobs.zero_()
         self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
 
+    @_lib.on_device
     def head_grad_raw(self):
         """fp32 gradient of sum(dprobs*probs) w.r.t. Mixed_5c (no ReLU mask): Grad-CAM's `grads_val`."""
         return ops.head_bwd(self.g_feat_raw, self.w_logits, self.softmax, self.probs, self.dprobs)

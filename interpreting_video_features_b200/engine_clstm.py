@@ -56,7 +56,14 @@ class CLSTMEngine:
               if v.is_floating_point()}
         self.B, (self.T, self.H, self.W) = batch, clip
         self.C, self.L, self.hid, self.softmax = in_channels, layers, hidden, bool(softmax)
-        self.eff = list(effective_step)
+        # the reference collects outputs only for steps that occur (convolution_lstm.py:126 `if step in
+        # self.effective_step` inside `for step in range(self.step)`), so output[-1] is the last effective step
+        # below T
+        self.eff = [int(e) for e in effective_step if 0 <= int(e) < clip[0]]
+        if not self.eff:
+            raise _lib.IvfError("ConvLSTM: no effective_step below step=%d (%s): the reference's output list "
+                                "would be empty" % (clip[0], list(effective_step)))
+        self.generation = 0
         bf = mode == "bf16"
         he = max(8, (hidden + 7) // 8 * 8) if bf else hidden  # padded hidden size
         self.he = he
@@ -163,6 +170,7 @@ class CLSTMEngine:
         self.dm = torch.zeros((B, T), dtype=torch.float32, device=dev)
         self.zero_mask = torch.zeros((B, T), dtype=torch.float32, device=dev)
         self.g_feat_raw = torch.zeros((B, hin * win * he), dtype=torch.float32, device=dev)
+        self.head_ws = ops.head_workspace(B, hin * win * he, ncls, dev)
 
         # measured tile plans for the recurrent convolutions: each is a 15-35 us launch repeated T-1 times per
         # layer and direction with its operands resident in L2 (what the isolated measurement sees)
@@ -199,13 +207,17 @@ class CLSTMEngine:
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
         self.x.copy_(x, non_blocking=True)
 
+    @_lib.on_device
     def set_targets(self, targets):
+        self.generation += 1
         self.dprobs.zero_()
         self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
 
     # ------------------------------------------------------------------ forward
+    @_lib.on_device
     def forward(self, mask=None, perturb="reverse"):
         self._mask, self._perturb = (self.zero_mask if mask is None else mask), perturb
+        self.generation += 1
         ops.perturb_fwd(self.x, self._mask, perturb, self.in_fmt, self.xin.buf)
         B, T, he = self.B, self.T, self.he
         for rec in self.layers:
@@ -222,10 +234,12 @@ class CLSTMEngine:
             ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
                               rec["pooled"].buf, rec["argmax"], s2d=rec["s2d_out"])
         te = self.eff[-1]
-        ops.head_fwd(self._feat(self.layers[-1]["pooled"], te), self.w_fc, self.b_fc, self.softmax, self.probs, self.logits)
+        ops.head_fwd(self._feat(self.layers[-1]["pooled"], te), self.w_fc, self.b_fc, self.softmax, self.probs,
+                     self.logits, workspace=self.head_ws)
         return self.probs
 
     # ------------------------------------------------------------------ backward (BPTT data gradient)
+    @_lib.on_device
     def backward(self, to_mask=True):
         B, T, he = self.B, self.T, self.he
         te = self.eff[-1]
@@ -258,6 +272,7 @@ class CLSTMEngine:
         return self.dm
 
     # ------------------------------------------------------------------ Grad-CAM operands
+    @_lib.on_device
     def gradcam_operands(self):
         """Activations / gradients of the stacked effective-step outputs (pt/pytorch-grad-cam/grad-cam.py:42-49,
         pt/grad_cam_videos.py:87-91): [B, E, h, w, hid] channels-last; only the last step has a gradient

@@ -96,7 +96,7 @@ def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None
     check(_lib.load().ivf_conv3d(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(w), ptr(scale),
                                  ptr(shift), ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
                                  ptr(mask.buf if mask is not None else None), ptr(mask_scale),
-                                 ptr(out.buf), _lib.stream_ptr()), "ivf_conv3d")
+                                 ptr(out.buf), _lib.stream_ptr(x.buf.device)), "ivf_conv3d")
     return out
 
 
@@ -116,7 +116,7 @@ def conv1x1_split(x, w, out, x2=None, out2=None, flags=0, scale=None, shift=None
                                        ptr(x2.buf if x2 is not None else None), ptr(w), ptr(scale), ptr(shift),
                                        ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
                                        ptr(mask.buf if mask is not None else None), ptr(mask_scale), ptr(out.buf),
-                                       ptr(out2.buf if out2 is not None else None), _lib.stream_ptr()),
+                                       ptr(out2.buf if out2 is not None else None), _lib.stream_ptr(x.buf.device)),
           "ivf_conv3d_split")
     return out
 
@@ -142,7 +142,7 @@ def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front, relu_bits=None):
     d = _pool_desc(x, out, kernel, stride, pad_front)
     d.dtype = _lib.dtype_code(x.buf)
     check(_lib.load().ivf_maxpool3d_fwd_bits(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(out.buf),
-                                             ptr(argmax), ptr(relu_bits), _lib.stream_ptr()), "ivf_maxpool3d_fwd")
+                                             ptr(argmax), ptr(relu_bits), _lib.stream_ptr(x.buf.device)), "ivf_maxpool3d_fwd")
     return out
 
 
@@ -160,18 +160,28 @@ def maxpool3d_bwd(dy, argmax, dx, kernel, stride, pad_front, acc_in=None, mask=N
     check(_lib.load().ivf_maxpool3d_bwd_bits(_lib.handle(dy.buf.device), C.byref(d), ptr(dy.buf), ptr(argmax),
                                              ptr(acc_in.buf if isinstance(acc_in, Act) else acc_in),
                                              ptr(mask.buf if mask is not None else None), ptr(relu_bits),
-                                             ptr(mask_scale), ptr(dx.buf), _lib.stream_ptr()), "ivf_maxpool3d_bwd")
+                                             ptr(mask_scale), ptr(dx.buf), _lib.stream_ptr(dy.buf.device)), "ivf_maxpool3d_bwd")
     return dx
 
 
-def head_fwd(feat, w, b, softmax, out, logits=None):
+def head_workspace(n, c, ncls, device):
+    """The caller-owned partial-logit buffer of ivf_i3d_head_fwd: one per engine (engines on parallel streams
+    must not share it)."""
+    nbytes = int(_lib.load().ivf_i3d_head_workspace_bytes(n, c, ncls))
+    return torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+
+
+def head_fwd(feat, w, b, softmax, out, logits=None, workspace=None):
     """feat: Act (whole map is pooled); w fp32 [ncls, c]; out fp32 [n, ncls]."""
     assert feat.coff == 0
     p = feat.d * feat.h * feat.w
+    if workspace is None:  # one-off calls (tests, the per-op surface); engines pass their own buffer
+        workspace = head_workspace(feat.n, feat.c, w.shape[0], feat.buf.device)
     check(_lib.load().ivf_i3d_head_fwd(_lib.handle(feat.buf.device), _lib.dtype_code(feat.buf),
                                        ptr(feat.buf), feat.n, p, feat.c, feat.ld, ptr(w), ptr(b),
-                                       w.shape[0], int(bool(softmax)), ptr(logits), ptr(out),
-                                       _lib.stream_ptr()), "ivf_i3d_head_fwd")
+                                       w.shape[0], int(bool(softmax)), ptr(logits), ptr(out), ptr(workspace),
+                                       workspace.numel() * 4, _lib.stream_ptr(feat.buf.device)),
+          "ivf_i3d_head_fwd")
     return out
 
 
@@ -190,7 +200,7 @@ def head_bwd(dfeat, w, softmax, out, dout, mask=None, mask_scale=None):
                                        ptr(mask.buf if mask is not None else None),
                                        mask.ld if mask is not None else 0,
                                        mask.coff if mask is not None else 0, ptr(mask_scale),
-                                       ptr(dfeat.buf), _lib.stream_ptr()), "ivf_i3d_head_bwd")
+                                       ptr(dfeat.buf), _lib.stream_ptr(dfeat.buf.device)), "ivf_i3d_head_bwd")
     return dfeat
 
 
@@ -202,7 +212,7 @@ def perturb_fwd(x, mask, mode, out_fmt, out):
     b, c, t, hh, ww = x.shape
     bstride = 0 if mask.dim() == 1 else t
     check(_lib.load().ivf_perturb_fwd(_lib.handle(x.device), _MODES[mode], ptr(x), ptr(mask), bstride, b, c,
-                                      t, hh, ww, out_fmt, ptr(out), _lib.stream_ptr()), "ivf_perturb_fwd")
+                                      t, hh, ww, out_fmt, ptr(out), _lib.stream_ptr(x.device)), "ivf_perturb_fwd")
     return out
 
 
@@ -212,7 +222,7 @@ def perturb_bwd(x, mask, mode, out_fmt, gout, dmask):
     bstride = 0 if mask.dim() == 1 else t
     check(_lib.load().ivf_perturb_bwd(_lib.handle(x.device), _MODES[mode], ptr(x), ptr(mask), bstride, b, c,
                                       t, hh, ww, out_fmt, _lib.dtype_code(gout), ptr(gout), ptr(dmask),
-                                      _lib.stream_ptr()), "ivf_perturb_bwd")
+                                      _lib.stream_ptr(x.device)), "ivf_perturb_bwd")
     return dmask
 
 
@@ -221,19 +231,19 @@ def mask_loss_adam(m, exp_avg, exp_avg_sq, dclass, step, lam1, lam2, lr=0.2, bet
     nclip, t = m.shape
     check(_lib.load().ivf_mask_loss_adam(_lib.handle(m.device), ptr(m), ptr(exp_avg), ptr(exp_avg_sq),
                                          ptr(dclass), nclip, t, int(step), ptr(step_dev), lam1, lam2, lr,
-                                         beta1, beta2, eps, ptr(losses), ptr(sig_out), _lib.stream_ptr()),
+                                         beta1, beta2, eps, ptr(losses), ptr(sig_out), _lib.stream_ptr(m.device)),
           "ivf_mask_loss_adam")
 
 
 def sigmoid(m, out):
-    check(_lib.load().ivf_sigmoid(_lib.handle(m.device), ptr(m), ptr(out), m.numel(), _lib.stream_ptr()),
+    check(_lib.load().ivf_sigmoid(_lib.handle(m.device), ptr(m), ptr(out), m.numel(), _lib.stream_ptr(m.device)),
           "ivf_sigmoid")
     return out
 
 
 def tv_norm(mask, p, q, val, dmask=None):
     check(_lib.load().ivf_tv_norm(_lib.handle(mask.device), ptr(mask), mask.numel(), float(p), float(q),
-                                  ptr(val), ptr(dmask), _lib.stream_ptr()), "ivf_tv_norm")
+                                  ptr(val), ptr(dmask), _lib.stream_ptr(mask.device)), "ivf_tv_norm")
     return val
 
 
@@ -243,7 +253,7 @@ def gradcam(act, grad, step, hout, wout, per_frame, cam, cam_lowres=None):
     check(_lib.load().ivf_gradcam(_lib.handle(act.buf.device), _lib.dtype_code(act.buf),
                                   _lib.dtype_code(grad.buf), ptr(act.buf), ptr(grad.buf), act.n, act.d,
                                   act.h, act.w, act.c, act.ld, step, hout, wout, int(bool(per_frame)),
-                                  ptr(cam), ptr(cam_lowres), _lib.stream_ptr()), "ivf_gradcam")
+                                  ptr(cam), ptr(cam_lowres), _lib.stream_ptr(act.buf.device)), "ivf_gradcam")
     return cam
 
 
@@ -251,28 +261,28 @@ def clstm_gates_fwd(pre, c_prev, c_next, h_next, gate_act):
     m, four_hid = pre.shape
     check(_lib.load().ivf_clstm_gates_fwd(_lib.handle(pre.device), _lib.dtype_code(h_next), ptr(pre),
                                           ptr(c_prev), m, four_hid // 4, ptr(c_next), ptr(h_next),
-                                          ptr(gate_act), _lib.stream_ptr()), "ivf_clstm_gates_fwd")
+                                          ptr(gate_act), _lib.stream_ptr(pre.device)), "ivf_clstm_gates_fwd")
 
 
 def clstm_gates_bwd(gate_act, c_prev, c_next, dh, dc_io, dgates):
     m, four_hid = gate_act.shape
     check(_lib.load().ivf_clstm_gates_bwd(_lib.handle(dh.device), _lib.dtype_code(dgates), ptr(gate_act),
                                           ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_io), m, four_hid // 4,
-                                          ptr(dgates), _lib.stream_ptr()), "ivf_clstm_gates_bwd")
+                                          ptr(dgates), _lib.stream_ptr(dh.device)), "ivf_clstm_gates_bwd")
 
 
 def bn_pool2d_fwd(x, scale, shift, y, argmax, s2d=False):
     n, hh, ww, c = x.shape
     check(_lib.load().ivf_bn_pool2d_fwd(_lib.handle(x.device), _lib.dtype_code(x), ptr(x), n, hh, ww, c,
                                         ptr(scale), ptr(shift), ptr(y), ptr(argmax), int(s2d),
-                                        _lib.stream_ptr()), "ivf_bn_pool2d_fwd")
+                                        _lib.stream_ptr(x.device)), "ivf_bn_pool2d_fwd")
 
 
 def bn_pool2d_bwd(dy, argmax, scale, dx, acc_in=None, s2d=False):
     n, hh, ww, c = dx.shape
     check(_lib.load().ivf_bn_pool2d_bwd(_lib.handle(dy.device), _lib.dtype_code(dy), ptr(dy), ptr(argmax), n,
                                         hh, ww, c, ptr(scale), ptr(acc_in), ptr(dx), int(s2d),
-                                        _lib.stream_ptr()), "ivf_bn_pool2d_bwd")
+                                        _lib.stream_ptr(dy.device)), "ivf_bn_pool2d_bwd")
 
 
 def probe_im2col(x, kernel, stride, pad_front, out_dhw, m0, tap, c0):
@@ -290,5 +300,5 @@ def probe_im2col(x, kernel, stride, pad_front, out_dhw, m0, tap, c0):
     kch = _lib.load().ivf_conv_bf16_kchunk(x.c)
     tile = torch.empty((128, kch), dtype=torch.bfloat16, device=x.buf.device)
     check(_lib.load().ivf_probe_im2col(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), m0, tap, c0,
-                                       ptr(tile), _lib.stream_ptr()), "ivf_probe_im2col")
+                                       ptr(tile), _lib.stream_ptr(x.buf.device)), "ivf_probe_im2col")
     return tile

@@ -15,7 +15,6 @@ class _ClstmFn(torch.autograd.Function):
         eng = model._engine(x)
         eng.set_input(x.detach().contiguous())
         out = eng.forward(None, "freeze").clone()  # zero mask: the operand is the clip itself
-        eng.generation = getattr(eng, "generation", 0) + 1
         ctx.eng, ctx.gen, ctx.shape = eng, eng.generation, x.shape
         return out
 
@@ -25,6 +24,7 @@ class _ClstmFn(torch.autograd.Function):
         if eng.generation != ctx.gen:
             raise _lib.IvfError("backward through a forward whose activations were overwritten by a later forward")
         eng.dprobs.copy_(gout)
+        eng.generation += 1
         eng.backward(to_mask=False)
         b, c, t, h, w = ctx.shape
         g = eng.g_xin.buf

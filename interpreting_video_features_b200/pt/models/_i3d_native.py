@@ -221,7 +221,8 @@ class _ModelFn(torch.autograd.Function):
         eng = model._engine(x)
         eng.set_input(x.detach().contiguous())
         out = eng.forward(None).clone()
-        eng.generation = getattr(eng, "generation", 0) + 1
+        # the engine bumps `generation` on everything that overwrites its activations or dprobs (forward, graph
+        # replay, set_targets): a backward issued after, e.g., a Grad-CAM call on the same engine is refused
         ctx.eng, ctx.gen, ctx.shape = eng, eng.generation, x.shape
         return out
 
@@ -232,6 +233,7 @@ class _ModelFn(torch.autograd.Function):
             raise _lib.IvfError("backward through a forward whose activations were overwritten by a later "
                                 "forward of the same model/geometry (the native model keeps one activation set)")
         eng.dprobs.copy_(gout)
+        eng.generation += 1  # dprobs overwritten: a second backward through the same node needs a new forward
         eng.backward(to_mask=False)
         b, c, t, h, w = ctx.shape
         g = eng.g_xin.buf
@@ -245,6 +247,8 @@ class _ModelFn(torch.autograd.Function):
 
 class I3DBase(nn.Module):
     """Inception-v1 I3D with the reference's constructor surface (pt/models/I3D_doubled.py:186-335)."""
+
+    MAX_ENGINE_GEOMETRIES = 3
 
     VALID_ENDPOINTS = ("Conv3d_1a_7x7", "MaxPool3d_2a_3x3", "Conv3d_2b_1x1", "Conv3d_2c_3x3",
                        "MaxPool3d_3a_3x3", "Mixed_3b", "Mixed_3c", "MaxPool3d_4a_3x3", "Mixed_4b", "Mixed_4c",
@@ -330,16 +334,31 @@ class I3DBase(nn.Module):
         if hit is None or hit[0] != ver:
             if self.training:
                 raise _lib.IvfError("the native I3D runs eval-mode BatchNorm only; call model.eval()")
-            if self.lastRelu in ("relu", "leaky"):
-                raise _lib.IvfError("lastRelu is not supported by the native head")
+            # pt/models/I3D_doubled.py:321-326: `if leaky: leaky_relu` is followed by `if relu: relu else: None`,
+            # so "leaky" ends up with NO activation upstream (and so here); only "relu" activates the logits,
+            # and the native head has no ReLU epilogue after the logits.
+            if self.lastRelu == "relu":
+                raise _lib.IvfError("lastRelu='relu' (ReLU on the logits) has no native head epilogue")
             sd = {k: v for k, v in self.state_dict().items()}
             eng = I3DEngine(sd, batch or b, (t, h, w), mode=self.ivf_mode, softmax=bool(self.softMax),
                             avg_pool=tuple(self.avg_pool.kernel_size), stride_mods=self._stride_mods,
                             device=device, in_channels=c)
             hit = (ver, eng)
-            # one geometry at a time (activations are large): drop engines of other geometries / older weights
-            self._engines = {k: v for k, v in self._engines.items() if k[:-1] == key[:-1] and v[0] == ver}
-            self._engines[key] = hit
+            # a small LRU over geometries: the reference driver alternates model(input_var) at B = batch_size
+            # with Grad-CAM at B = 1 for every clip (pt/FindMasksComparison_I3D_smth.py:176,266); rebuilding an
+            # engine per switch (weight packing, buffers, graphs) would cost far more than the kernels.  Engines
+            # of older weights go first; clip groups of one geometry (same key up to `tag`) count as one entry.
+            self._engines = {k: v for k, v in self._engines.items() if v[0] == ver}
+            geos = []
+            for k in self._engines:
+                if k[:-1] not in geos:
+                    geos.append(k[:-1])
+            while len(geos) >= self.MAX_ENGINE_GEOMETRIES and geos[0] != key[:-1]:
+                drop = geos.pop(0)
+                self._engines = {k: v for k, v in self._engines.items() if k[:-1] != drop}
+        else:
+            self._engines.pop(key)  # re-insert: most recently used last
+        self._engines[key] = hit
         return hit[1]
 
     def set_mode(self, mode):

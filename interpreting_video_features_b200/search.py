@@ -60,6 +60,7 @@ class MaskSearch:
         for e, sl in zip(self.engs, self.slices):
             e.set_targets(tg[sl])
 
+    @_lib.on_device
     def forward(self, mask, perturb):
         """mask: None, [T] (shared) or [B,T]; returns a COPY of the [B, classes] outputs."""
         outs = []
@@ -97,20 +98,22 @@ class MaskSearch:
         for gs in self._gstreams:
             main.wait_stream(gs)
 
+    @_lib.on_device
     def _capture(self):
         s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream())
+        s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):  # warm-up outside capture (first-use attribute calls, tensor maps)
             n0 = _lib.launch_count(self.device)
             self._iteration()
             self.launches_per_iter = _lib.launch_count(self.device) - n0
-        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._iteration()
         self.graph = g
 
+    @_lib.on_device
     def init_masks(self, targets, mode="central", generator=None):
         """Batched pt/mask.py:103-169; returns raw masks [B,T] on the device and the unperturbed probs."""
         B, T, dev = self.B, self.T, self.device
@@ -147,6 +150,7 @@ class MaskSearch:
             raw[b] = np.where(row == 0, -5.0, 5.0)
         return torch.from_numpy(raw).to(dev), probs_orig
 
+    @_lib.on_device
     def run(self, x, targets, init="central", raw_masks=None, n_iter=None, record=None):
         """x fp32 [B,3,T,H,W] on the device; targets [B].  Returns a dict of device tensors."""
         n_iter = self.n_iter if n_iter is None else n_iter
