@@ -11,8 +11,12 @@ ranks (weak scaling: every rank owns 8 clips; no collective inside the search, S
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
 
 value   : inputs resident in HBM, K CUDA-graph replays timed with CUDA events (max over ranks)
-e2e     : the public API (search.find_masks_batched) on pinned HOST clips: H2D of the clips, init_mask,
-          300 iterations, reverse score, D2H of the masks — all inside the timed region
+e2e     : the job BASELINE.json configs[3] describes (C4), scaled to the ranks present: 128 clips per GPU as
+          uint8 frames in pinned HOST memory, sharded clip-parallel, through the public API
+          (search.find_masks_batched): H2D of every micro-batch, init_mask (T/2+1 batched forwards), 300
+          iterations, reverse score, Grad-CAM of every clip, the NCCL all_gather of masks + scores + low-res CAMs
+          (N > 1) and the D2H of the gathered result — all inside the timed region; clip-iterations/s =
+          clips x 300 / wall time (max over ranks)
 roofline: the tcgen05 convolution kernel: algorithmic conv FLOPs (forward + data gradient, no weight
           gradient) / summed conv-kernel time measured with CUDA events around every conv launch
 cpu_baseline / --impl reference: the oracle restatement of the reference's PyTorch-CPU path (the
@@ -125,7 +129,7 @@ def time_cpu_reference(steps, warmup):
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    x1 = synthetic.clips(1)
+    x1 = synthetic.uniform_clip_u8(0)[None].float()  # decoded uint8 frames -> .float(), pt/data_loader_jpg.py:27-30
     tm = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4, requires_grad=True)
     st = (tm, torch.optim.Adam([tm], lr=0.2))
     for _ in range(warmup):
@@ -217,9 +221,9 @@ def gradcam_throughput(dev, rank, world, mode, clips_n=8, reps=5):
     m = m.to(dev).eval().set_mode(mode)
     gc = GradCamVideo(model=m, target_layer_names=['Mixed_5c'], class_dict=None, use_cuda=True,
                       input_spatial_size=(160, 120), normalizePerFrame=True, archType="I3D")
-    host = torch.stack([synthetic.uniform_clip(1000 + rank * clips_n + i, t=32, h=120, w=160)
-                        for i in range(clips_n)]).pin_memory()
-    xd = host.to(dev)
+    host = torch.stack([synthetic.uniform_clip_u8(1000 + rank * clips_n + i, t=32, h=120, w=160)
+                        for i in range(clips_n)]).pin_memory()  # decoded uint8 frames, as the loaders produce them
+    xd = host.to(dev).float()
     idx = [i % 6 for i in range(clips_n)]
     for _ in range(2):
         gc._i3d(xd, idx)
@@ -235,7 +239,7 @@ def gradcam_throughput(dev, rank, world, mode, clips_n=8, reps=5):
     dev_s = e0.elapsed_time(e1) * 1e-3 / reps
     t0 = time.perf_counter()
     for _ in range(reps):
-        cams, _ = gc.batched(host.to(dev, non_blocking=True), idx)
+        cams, _ = gc.batched(host, idx)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / reps
     if world > 1:
@@ -244,7 +248,7 @@ def gradcam_throughput(dev, rank, world, mode, clips_n=8, reps=5):
         dev_s, e2e_s = float(t[0]), float(t[1])
     return {"metric": "gradcam_clips_per_sec", "unit": "clips/s", "value": world * clips_n / dev_s,
             "e2e": world * clips_n / e2e_s, "clips_per_gpu": clips_n,
-            "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(cams.size * 4),
+            "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(cams.size * 4),
             "workload": "C1: I3D KTH (6 classes) Grad-CAM at Mixed_5c, 32x120x160 synthetic clips (the model's "
                         "native geometry, SURVEY fact 10), %d clips per call, not CUDA-graphed" % clips_n}
 
@@ -351,7 +355,10 @@ def run_ours(args, rank, world, local_rank):
     pk, pk_src = peaks()
     flops_step = 2.0 * conv_flops * CLIPS  # forward + data gradient, no weight gradient
     achieved = flops_step / conv_s / 1e12
-    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) if args.mode == "bf16" else None
+    # the step runs at the burst clock (1 965 MHz, no power cap on this workload: see "clocks"), so the burst cuBLAS
+    # figure is the denominator; the sustained figure is reported beside it
+    peak = pk["bf16_tflops"] if args.mode == "bf16" else None
+    peak_sus = pk.get("bf16_tflops_sustained") if args.mode == "bf16" else None
     traffic, traffic_src = None, None
     tp = os.path.join(REPO, "profiles", "r01_step_metrics.json")
     if os.path.exists(tp) and args.mode == "bf16":  # DRAM bytes of the conv launches of one step (ncu, committed)
@@ -360,37 +367,67 @@ def run_ours(args, rank, world, local_rank):
                       "conv launches of one step (8 clips), one ncu capture"
     roofline = {"bound": "tensor", "kernel": "conv_slab_kernel + conv_tc_kernel (tcgen05 implicit GEMMs, all conv launches of a step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if peak else None, "peak_source": pk_src + " (sustained bf16 GEMM)",
+                "frac": (achieved / peak) if peak else None, "peak_source": pk_src + " (burst bf16 GEMM, MEASURED_PEAKS.json bf16_tflops)",
+                "frac_burst": (achieved / peak) if peak else None, "peak_sustained": peak_sus,
+                "frac_sustained": (achieved / peak_sus) if peak_sus else None,
                 "traffic": traffic, "traffic_source": traffic_src, "conv_launches_per_step": conv_launches, "conv_ms_per_step": conv_s * 1e3,
                 "algorithmic_gflop_per_clip_iteration": 2.0 * conv_flops / 1e9,
                 "conv_share_of_step": conv_s / (elapsed / args.steps)}
 
-    # ---- end to end through the public API with pinned host clips
-    host = clips.pin_memory()
-    # one short untimed call first: CUDA loads kernels lazily, and the init-mask / reverse-score kernels have not
-    # run yet in this process (measured: ~130 ms of one-time loading inside the first call)
-    search.find_masks_batched(model, host, targets, lam1=0.01, lam2=0.02, n_iter=2, perturb="freeze",
-                              micro_batch=CLIPS, device=dev)
+    # ---- end to end: the sharded C4 job through the public API, uint8 host clips, gather + D2H inside
+    per_gpu = args.clips_per_gpu
+    n_total = per_gpu * world
+    mine = search.shard_indices(n_total, rank, world)
+    host = torch.empty((len(mine), 3, T, H, W), dtype=torch.uint8, pin_memory=True)
+    for i, gidx in enumerate(mine):
+        host[i] = synthetic.uniform_clip_u8(gidx)
+    tg_all = torch.randint(0, NCLS, (n_total,), generator=torch.Generator().manual_seed(7))
+    tg_mine = tg_all[mine]
+    # one short untimed call first: CUDA loads kernels lazily, and the init-mask / reverse-score / Grad-CAM kernels
+    # have not run yet in this process; it also captures the graphs the timed call replays
+    search.find_masks_batched(model, host[:CLIPS], tg_mine[:CLIPS], n_iter=2, micro_batch=CLIPS, device=dev, gradcam=True,
+                              rank=rank, world=world, n_total=CLIPS * world)
+    check = None
+    if world > 1:  # the gathered result == each shard computed alone, bit for bit (small case: 8 clips per rank)
+        small = search.find_masks_batched(model, host[:CLIPS], tg_mine[:CLIPS], n_iter=5, micro_batch=CLIPS, device=dev,
+                                          gradcam=True, rank=rank, world=world, n_total=CLIPS * world)
+        alone = search.find_masks_batched(model, host[:CLIPS], tg_mine[:CLIPS], n_iter=5, micro_batch=CLIPS,
+                                          device=dev, gradcam=True)
+        sel = search.shard_indices(CLIPS * world, rank, world)
+        ok = all(torch.equal(small[k][sel], alone[k]) for k in ("time_mask", "freeze_score", "reverse_score",
+                                                                 "cam_lowres"))
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        check = bool(t.item() == 1.0)
+        assert check, "gathered shard rows differ from the single-rank result"
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    stats = {}
     t0 = time.perf_counter()
-    res = search.find_masks_batched(model, host, targets, lam1=0.01, lam2=0.02, n_iter=N_ITER, perturb="freeze",
-                                    micro_batch=CLIPS, device=dev)
-    masks_host = res["time_mask"].cpu()
-    scores_host = res["freeze_score"].cpu()
+    res = search.find_masks_batched(model, host, tg_mine, lam1=0.01, lam2=0.02, n_iter=N_ITER, perturb="freeze",
+                                    micro_batch=CLIPS, device=dev, gradcam=True, rank=rank, world=world,
+                                    n_total=n_total, stats=stats)
+    out_host = {k: res[k].cpu() for k in ("time_mask", "freeze_score", "reverse_score", "cam_lowres")}
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
+        t = torch.tensor([e2e_s, stats["gather_seconds"]], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * CLIPS * N_ITER / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(host.numel() * 4 / N_ITER), "d2h_bytes_per_step": int((masks_host.numel() + scores_host.numel()) * 4 / N_ITER),
-           "h2d_bytes_per_search": int(host.numel() * 4), "seconds_per_search": e2e_s,
-           "note": "find_masks_batched on pinned host clips: H2D + init_mask (T/2+1 forwards) + 300 "
-                   "iterations + reverse score + D2H, per rank; step = 1/300 of a search; one 2-iteration call runs "
-                   "untimed first (lazy kernel loading; it also captures the iteration graph the timed call replays)"}
+        e2e_s, stats["gather_seconds"] = float(t[0]), float(t[1])
+    assert out_host["time_mask"].shape == (n_total, T) and bool(torch.isfinite(out_host["time_mask"]).all())
+    d2h = sum(v.numel() * 4 for v in out_host.values())
+    steps_per_rank = len(mine) // CLIPS * N_ITER  # micro-batch iterations per rank
+    e2e = {"value": n_total * N_ITER / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(host.numel() / steps_per_rank), "d2h_bytes_per_step": int(d2h / steps_per_rank),
+           "h2d_bytes_per_job_per_rank": int(host.numel()), "d2h_bytes_per_job": int(d2h), "seconds_per_job": e2e_s,
+           "clips_total": n_total, "clips_per_gpu": per_gpu, "gather_seconds": stats["gather_seconds"],
+           "gathered_bytes": stats.get("gathered_bytes"), "gather_equals_single_rank": check,
+           "note": "C4-shaped job: %d uint8 clips per GPU in pinned host memory, find_masks_batched(gradcam=True): per "
+                   "micro-batch of 8 H2D + init_mask (T/2+1 forwards) + 300 iterations + reverse score + Grad-CAM; then "
+                   "NCCL all_gather of masks+scores+low-res CAMs (N>1) and D2H of the gathered result; a step = one "
+                   "iteration of one 8-clip micro-batch; one 2-iteration call runs untimed first (lazy kernel "
+                   "loading, graph capture)" % per_gpu}
 
     gradcam = gradcam_throughput(dev, rank, world, args.mode) if not args.no_gradcam else None
     clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
@@ -420,6 +457,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--clips-per-gpu", type=int, default=128, help="clips per GPU of the end-to-end (C4) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")
     ap.add_argument("--no-clstm", action="store_true", help="skip the ConvLSTM (config C3) leg")

@@ -128,6 +128,53 @@ int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf_conv_split
                      const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
                      void* stream);
 
+/* ---- model load: weight packing and BatchNorm folding -------------------------------
+ * ivf_pack_weights writes ONE source weight tensor (fp32 OIDHW on the device: the nn.Conv3d / nn.Conv2d
+ * parameter of pt/models/I3D_doubled.py:66-72, pt/models/convolution_lstm.py:25-32, kd = 1 for 2-D) into the
+ * operand matrix a convolution kernel reads, as the block starting at row n_off / reduction index k_off of a
+ * packed matrix of n_pad rows and k_pad reduction entries per tap.  Several sources may fill one matrix (the
+ * fused b0|b1a|b2a GEMM, the four ConvLSTM gates): the first call sets zero_first.
+ *   dgrad == 0: rows = output channels, K = operand channels (the forward operand);
+ *   dgrad == 1: rows = operand channels, K = output channels, taps flipped (data gradient as a stride-1
+ *               convolution with flipped weights: the bf16 kernels);
+ *   dgrad == 2: rows = operand channels, K = output channels, taps as stored (the fp32 kernel's transposed
+ *               gather, ivf_conv_desc.transposed = 1).
+ *   s2d_{d,h,w} == 2: the axis has stride 2 and is presented space-to-depth: operand channel =
+ *     ((a*s2d_h + b)*s2d_w + c)*ci_stride + ch, operand tap = ceil(k/2) per axis, source tap = 2*tap + parity
+ *     (taps beyond the kernel are zero).  ci_stride >= ci pads each parity block (0 = ci).
+ *   layout IVF_PACK_KMAJOR:   dst[n_pad][taps][k_pad]  (bf16 tcgen05 kernels; n_pad = ivf_conv_bf16_cout_pad,
+ *                             k_pad = ivf_conv_bf16_cin_pad of the totals)
+ *          IVF_PACK_TAPMAJOR: dst[taps][k_pad][n_pad]  (fp32 kernel)
+ *   dtype: element type of dst (IVF_BF16 | IVF_F32).                                                     */
+enum { IVF_PACK_KMAJOR = 0, IVF_PACK_TAPMAJOR = 1 };
+typedef struct ivf_pack_desc {
+  int32_t co, ci, kd, kh, kw;
+  int32_t ci_stride;
+  int32_t s2d_d, s2d_h, s2d_w;
+  int32_t dgrad;
+  int32_t layout;
+  int32_t dtype;
+  int32_t n_pad, k_pad, n_off, k_off;
+  int32_t zero_first;
+} ivf_pack_desc;
+int ivf_pack_weights(ivf_handle* h, const ivf_pack_desc* d, const float* src, void* dst, void* stream);
+/* scale = gamma/sqrt(var+eps), shift = beta - mean*scale (+ scale*conv_bias): eval BatchNorm folded into the
+ * conv epilogue (pt/models/I3D_doubled.py:75,111 eps 1e-3; pt/models/convolution_lstm.py:85 eps 1e-5).
+ * gamma == NULL: scale 1, shift 0 (+ conv_bias) for units without BatchNorm (the logits layer).          */
+int ivf_bn_fold(ivf_handle* h, const float* gamma, const float* beta, const float* mean, const float* var,
+                float eps, const float* conv_bias, int c, float* scale, float* shift, void* stream);
+/* dst[0 .. bytes) = the 32-bit pattern (buffer initialisation on the caller's stream; bytes % 4 == 0). */
+int ivf_fill_u32(ivf_handle* h, void* dst, size_t bytes, uint32_t pattern, void* stream);
+/* dst[i] = (float)src[i]: uint8 frames as the loaders decode them (pt/data_loader_jpg.py:27-37,
+ * pt/data_loader_kth.py:20-43 produce 0..255 values) converted on the device, so a clip crosses PCIe as one
+ * byte per value instead of four. */
+int ivf_u8_to_f32(ivf_handle* h, const uint8_t* src, float* dst, size_t count, void* stream);
+/* out[n][ncls] = one_hot(targets[n]) — the class selector of pt/FindMasksComparison_I3D_smth.py:205 and
+ * pt/grad_cam_videos.py:73-79 as the upstream gradient of the head. */
+int ivf_one_hot(ivf_handle* h, const int* targets, int n, int ncls, float* out, void* stream);
+/* out[n] = index of the first maximum of row n (np.argmax of pt/grad_cam_videos.py:70-71), on the device. */
+int ivf_argmax_rows(ivf_handle* h, const float* x, int n, int ncls, int* out, void* stream);
+
 /* Diagnostic: copy the head of the handle's scratch buffer to the host after a device synchronise (kernel
  * phase traces written when IVF_TC_TRACE=1). */
 int ivf_debug_read_scratch(ivf_handle* h, void* dst, size_t bytes);
@@ -229,6 +276,16 @@ int ivf_mask_loss_adam(ivf_handle* h, float* m, float* exp_avg, float* exp_avg_s
                        float lr, float beta1, float beta2, float eps, float* losses,
                        float* sig_out, void* stream);
 int ivf_sigmoid(ivf_handle* h, const float* m, float* out, int count, void* stream);
+/* out[i] = probs[i][targets[i]] — the class score the drivers read after every forward
+ * (pt/mask.py:128-129,140-143; pt/FindMasksComparison_I3D_smth.py:205), kept on the device. */
+int ivf_select_scores(ivf_handle* h, const float* probs, const int* targets, int n, int ncls, float* out,
+                      void* stream);
+/* 'central' mask initialisation of pt/mask.py:121-154 for n clips from the class scores of every candidate:
+ * scores is fp32 [1 + t/2][n] - row 0 the unperturbed clip, row 1 the fully frozen clip, row 1+i the centred
+ * window with i frames switched off at both ends (i = 1 .. t/2-1).  raw[n][t] receives -5 / +5; chosen[n]
+ * (optional) the selected i.  No host read-back: the search that follows is queued behind it. */
+int ivf_init_mask_select(ivf_handle* h, const float* scores, int n, int t, float threshold, float* raw,
+                         int* chosen, void* stream);
 /* general-(p,q) TV norm used by the drop-in calc_tv_norm: val[0] and dval/dmask[t] */
 int ivf_tv_norm(ivf_handle* h, const float* mask, int t, float p, float q, float* val,
                 float* dmask, void* stream);
@@ -238,7 +295,9 @@ int ivf_tv_norm(ivf_handle* h, const float* mask, int t, float p, float q, float
  * gradient of the class score w.r.t. them.  cam: fp32 [n][tp*step][hout][wout]:
  *   w_k = mean_{t,h,w} grad ; cam = relu(sum_k w_k act_k) ; bilinear (cv2 INTER_LINEAR,
  *   half-pixel) to hout x wout ; repeated `step` times along t ; min/max normalised per
- *   feature-time slice (per_frame != 0) or per clip.  One fused kernel.               */
+ *   feature-time slice (per_frame != 0) or per clip.  One fused kernel.
+ * cam_lowres (optional): fp32 [n][tp][hp][wp], the map before upsampling and normalisation (what a multi-GPU
+ * job gathers); cam may be NULL when only that is wanted.                      */
 int ivf_gradcam(ivf_handle* h, int act_dtype, int grad_dtype, const void* act, const void* grad,
                 int n, int tp, int hp, int wp, int c, int ld, int step, int hout, int wout,
                 int per_frame, float* cam, float* cam_lowres, void* stream);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libivf.so")
 IVF_F32, IVF_BF16 = 0, 1
 EP_AFFINE, EP_RELU, EP_ACCUM, EP_MASK, EP_OUT_F32 = 1, 2, 4, 8, 16
 PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, PFMT_TBHWC_F32, PFMT_S2D2_BF16 = 0, 1, 2, 3, 4
+PACK_KMAJOR, PACK_TAPMAJOR = 0, 1
 
 
 class IvfError(RuntimeError):
@@ -30,6 +31,12 @@ class ConvDesc(C.Structure):
 
 class ConvSplit(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("split_cout", "out2_ld", "out2_coff", "split_cin", "in2_ld", "in2_coff")]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "co", "ci", "kd", "kh", "kw", "ci_stride", "s2d_d", "s2d_h", "s2d_w", "dgrad", "layout", "dtype", "n_pad",
+        "k_pad", "n_off", "k_off", "zero_first")]
 
 
 class PoolDesc(C.Structure):
@@ -58,6 +65,12 @@ SIGNATURES = {
     "ivf_conv3d_split": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvSplit), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _P]),
     "ivf_debug_read_scratch": (_I, [_P, _P, C.c_size_t]),
+    "ivf_pack_weights": (_I, [_P, C.POINTER(PackDesc), _P, _P, _P]),
+    "ivf_bn_fold": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _P]),
+    "ivf_fill_u32": (_I, [_P, _P, C.c_size_t, C.c_uint32, _P]),
+    "ivf_u8_to_f32": (_I, [_P, _P, _P, C.c_size_t, _P]),
+    "ivf_one_hot": (_I, [_P, _P, _I, _I, _P, _P]),
+    "ivf_argmax_rows": (_I, [_P, _P, _I, _I, _P, _P]),
     "ivf_maxpool3d_fwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P]),
     "ivf_maxpool3d_bwd": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P, _P, _P]),
     "ivf_maxpool3d_fwd_bits": (_I, [_P, C.POINTER(PoolDesc), _P, _P, _P, _P, _P]),
@@ -69,6 +82,8 @@ SIGNATURES = {
     "ivf_perturb_bwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ivf_mask_loss_adam": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "ivf_sigmoid": (_I, [_P, _P, _P, _I, _P]),
+    "ivf_select_scores": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "ivf_init_mask_select": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
     "ivf_tv_norm": (_I, [_P, _P, _I, _F, _F, _P, _P, _P]),
     "ivf_gradcam": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ivf_clstm_gates_fwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),

@@ -84,6 +84,7 @@ gradcam_kernel(const T* __restrict__ act, const TG* __restrict__ grad, int tp, i
     }
   }
   __syncthreads();
+  if (!cam) return;  // low-resolution map only
   // 3. min / max of the upsampled maps (all of this block's slices)
   const double sy = (double)hp / (double)hout, sx = (double)wp / (double)wout;
   const int npix = hout * wout;
@@ -128,7 +129,7 @@ extern "C" int ivf_gradcam(ivf_handle* h, int act_dtype, int grad_dtype, const v
                            int hout, int wout, int per_frame, float* cam, float* cam_lowres,
                            void* stream) {
   IVF_ON_DEVICE(h);
-  IVF_REQUIRE(h && act && grad && cam, "ivf_gradcam: null argument");
+  IVF_REQUIRE(h && act && grad && (cam || cam_lowres), "ivf_gradcam: null argument");
   IVF_REQUIRE(n > 0 && tp > 0 && hp > 0 && wp > 0 && c > 0 && ld >= c && step > 0 && hout > 0 && wout > 0,
               "ivf_gradcam: bad extent");
   int slices = per_frame ? 1 : tp;

@@ -136,7 +136,58 @@ __global__ void tv_norm_kernel(const float* __restrict__ mask, int t, float p, f
   }
 }
 
+// scores[row][clip] = probs[clip][targets[clip]]: the class score the drivers read after every forward
+// (pt/mask.py:128-129,140-143 `model(...)[batch_index, target[batch_index]]`), kept on the device
+__global__ void select_scores_kernel(const float* __restrict__ probs, const int* __restrict__ targets, int n, int ncls,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = probs[(size_t)i * ncls + targets[i]];
+}
+
+// pt/mask.py:121-154 'central' initialisation for n clips at once, from the scores of all candidates:
+// scores[0] = unperturbed clip, scores[1] = fully frozen clip, scores[1 + i] (i = 1 .. T/2-1) = centred window
+// with i frames off at both ends.  The reference shrinks the window while (orig - central)/(orig - frozen) >=
+// threshold and keeps the first candidate that fails (or the last tried); 0 -> -5, 1 -> +5.  A NaN ratio
+// (orig == frozen) never compares below the threshold, as in the reference.
+__global__ void init_mask_select_kernel(const float* __restrict__ scores, int n, int t, float threshold,
+                                        float* __restrict__ raw, int* __restrict__ chosen_out) {
+  const int b = blockIdx.x;
+  __shared__ int chosen;
+  if (threadIdx.x == 0) {
+    const float orig = scores[b], frozen = scores[n + b];
+    int c = 0;  // 0 = no candidate tried: the mask stays all ones (T < 4)
+    for (int i = 1; i < t / 2; ++i) {
+      c = i;
+      const float ratio = (orig - scores[(size_t)(1 + i) * n + b]) / (orig - frozen);
+      if (ratio < threshold) break;
+    }
+    chosen = c;
+    if (chosen_out) chosen_out[b] = c;
+  }
+  __syncthreads();
+  const int c = chosen;
+  for (int u = threadIdx.x; u < t; u += blockDim.x) raw[(size_t)b * t + u] = (u < c || u >= t - c) ? -5.f : 5.f;
+}
+
 }  // namespace
+
+extern "C" int ivf_select_scores(ivf_handle* h, const float* probs, const int* targets, int n, int ncls, float* out,
+                                 void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && probs && targets && out && n > 0 && ncls > 0, "ivf_select_scores: bad argument");
+  select_scores_kernel<<<ivf_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(probs, targets, n, ncls, out);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+extern "C" int ivf_init_mask_select(ivf_handle* h, const float* scores, int n, int t, float threshold, float* raw,
+                                    int* chosen, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && scores && raw && n > 0 && t > 0 && t <= MAX_T, "ivf_init_mask_select: bad argument");
+  init_mask_select_kernel<<<n, 32, 0, (cudaStream_t)stream>>>(scores, n, t, threshold, raw, chosen);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
 
 extern "C" int ivf_mask_loss_adam(ivf_handle* h, float* m, float* exp_avg, float* exp_avg_sq,
                                   const float* dclass, int nclip, int t, int step, int* step_dev,

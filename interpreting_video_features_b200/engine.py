@@ -42,66 +42,95 @@ def strip_module_prefix(sd):
 
 
 # ---------------------------------------------------------------------------- weight packing
-def s2d_weight(w, win):
-    """(co,ci,k,k,k) stride-2 kernel -> (co, 8*ci, win,win,win) stride-1 kernel over the
-    space-to-depth input; channel = ((a*2+b)*2+c)*ci + ch, source tap = 2*delta + parity."""
-    co, ci, kd, kh, kw = w.shape
-    out = w.new_zeros(co, 8 * ci, win, win, win)
-    for a in range(2):
-        for b in range(2):
-            for c in range(2):
-                blk = ((a * 2 + b) * 2 + c) * ci
-                for dt in range(win):
-                    kt = 2 * dt + a
-                    if kt >= kd:
-                        continue
-                    for dh in range(win):
-                        kh_ = 2 * dh + b
-                        if kh_ >= kh:
-                            continue
-                        for dw in range(win):
-                            kw_ = 2 * dw + c
-                            if kw_ >= kw:
-                                continue
-                            out[:, blk:blk + ci, dt, dh, dw] = w[:, :, kt, kh_, kw_]
-    return out
+def _dev32(t, device):
+    """A parameter as a contiguous fp32 device tensor (one H2D/D2D copy, no compute)."""
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
-def _pack_bf16(wk):
-    """(n, taps, k) fp32 -> bf16 [n_pad, taps, k_pad] K-major, padded as the kernel tiles it."""
+def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, co_total=None, ceff_total=None):
+    """Operand matrix of a convolution kernel from one or more fp32 OIDHW (OIHW: kd = 1) device weights that
+    share their input channels and kernel (ivf_pack_weights; nothing is computed by torch).
+
+    forward operand: rows = output channels (sources stacked at co_offs), K = operand channels;
+    data-gradient operand (dgrad): rows = operand channels, K = output channels (sources side by side at co_offs).
+    s2d: per-axis space-to-depth factor of a stride-2 layer; ci_stride pads each parity block of operand
+    channels; ceff_total pads the operand channels as a whole (the 12 -> 16 channel ConvLSTM input record).
+    bf16: K-major [n_pad][taps][k_pad]; fp32: tap-major [taps][k][n] (flat [taps*k, n] like the old packers)."""
     lib = _lib.load()
-    n, taps, k = wk.shape
-    k_pad, n_pad = lib.ivf_conv_bf16_cin_pad(k), lib.ivf_conv_bf16_cout_pad(n)
-    out = torch.zeros((n_pad, taps, k_pad), dtype=torch.bfloat16, device=wk.device)
-    out[:n, :, :k] = wk.to(torch.bfloat16)
-    return out.contiguous()
+    ws = [w if w.dim() == 5 else w.unsqueeze(2) for w in sources]
+    dev = ws[0].device
+    ci = ws[0].shape[1]
+    kd, kh, kw = ws[0].shape[2:]
+    for w in ws:
+        assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (ci, kd, kh, kw)
+    taps = ((kd + s2d[0] - 1) // s2d[0]) * ((kh + s2d[1] - 1) // s2d[1]) * ((kw + s2d[2] - 1) // s2d[2])
+    ceff = s2d[0] * s2d[1] * s2d[2] * max(ci_stride, ci)
+    ceff_total = ceff if ceff_total is None else ceff_total
+    assert ceff_total >= ceff
+    if co_offs is None:
+        co_offs, acc = [], 0
+        for w in ws:
+            co_offs.append(acc)
+            acc += w.shape[0]
+        co_total = acc if co_total is None else co_total
+    assert co_total >= max(o + w.shape[0] for o, w in zip(co_offs, ws))
+    n_total, k_total = (ceff_total, co_total) if dgrad else (co_total, ceff_total)
+    bf = mode == "bf16"
+    if bf:
+        n_pad, k_pad = lib.ivf_conv_bf16_cout_pad(n_total), lib.ivf_conv_bf16_cin_pad(k_total)
+        dst = torch.empty((n_pad, taps, k_pad), dtype=torch.bfloat16, device=dev)
+    else:
+        n_pad, k_pad = n_total, k_total
+        dst = torch.empty((taps * k_pad, n_pad), dtype=torch.float32, device=dev)
+    h = _lib.handle(dev)
+    for i, (w, off) in enumerate(zip(ws, co_offs)):
+        d = _lib.PackDesc()
+        d.co, d.ci, d.kd, d.kh, d.kw = w.shape[0], ci, kd, kh, kw
+        d.ci_stride = ci_stride
+        d.s2d_d, d.s2d_h, d.s2d_w = s2d
+        d.dgrad = (1 if bf else 2) if dgrad else 0
+        d.layout = _lib.PACK_KMAJOR if bf else _lib.PACK_TAPMAJOR
+        d.dtype = _lib.IVF_BF16 if bf else _lib.IVF_F32
+        d.n_pad, d.k_pad = n_pad, k_pad
+        d.n_off, d.k_off = (0, off) if dgrad else (off, 0)
+        d.zero_first = int(i == 0)
+        _lib.check(lib.ivf_pack_weights(h, d, _lib.ptr(w), _lib.ptr(dst), _lib.stream_ptr(dev)), "ivf_pack_weights")
+    return dst
 
 
 def pack_fwd(w, mode):
-    co, ci = w.shape[:2]
-    if mode == "fp32":
-        return w.permute(2, 3, 4, 1, 0).reshape(-1, co).contiguous().float()
-    return _pack_bf16(w.permute(0, 2, 3, 4, 1).reshape(co, -1, ci))
+    return pack([w], mode)
 
 
 def pack_dgrad(w, mode):
     """fp32: [taps][co][ci] for the transposed gather; bf16: flipped taps, roles swapped."""
-    co, ci = w.shape[:2]
-    if mode == "fp32":
-        return w.permute(2, 3, 4, 0, 1).reshape(-1, ci).contiguous().float()
-    return _pack_bf16(w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, -1, co))
+    return pack([w], mode, dgrad=True)
 
 
 def pack_dgrad_two_sources(w_first, w_second):
     """Data-gradient weights of 1x1x1 units that share their input, reduced in ONE GEMM over
     [dz of the first unit | dz of the second]: K-major [ci][K], the first unit's K padded to whole 64-channel
     stages (ivf_conv3d_split), zeros in the padding."""
-    ci, c_first = w_first.shape[1], w_first.shape[0]
-    k1 = (c_first + 63) // 64 * 64
-    wk = w_first.new_zeros(ci, 1, k1 + w_second.shape[0])
-    wk[:, 0, :c_first] = w_first.reshape(c_first, ci).t()
-    wk[:, 0, k1:] = w_second.reshape(w_second.shape[0], ci).t()
-    return _pack_bf16(wk)
+    k1 = (w_first.shape[0] + 63) // 64 * 64
+    return pack([w_first, w_second], "bf16", dgrad=True, co_offs=[0, k1], co_total=k1 + w_second.shape[0])
+
+
+def bn_fold(sd, prefix, device, eps, scale, shift, with_conv_bias=False):
+    """eval BatchNorm of `prefix` folded into scale/shift (views of the caller's buffers); units without a
+    BatchNorm get scale 1 / shift 0; with_conv_bias adds scale * conv bias to the shift."""
+    lib = _lib.load()
+    c = scale.numel()
+    bias = sd.get(prefix + ".conv3d.bias") if with_conv_bias else None
+    bias = _dev32(bias, device) if bias is not None else None
+    if prefix + ".bn.weight" in sd:
+        g, b, mu, var = (_dev32(sd["%s.bn.%s" % (prefix, k)], device)
+                         for k in ("weight", "bias", "running_mean", "running_var"))
+    else:
+        g = b = mu = var = None
+    _lib.check(lib.ivf_bn_fold(_lib.handle(device), _lib.ptr(g), _lib.ptr(b), _lib.ptr(mu), _lib.ptr(var), eps,
+                               _lib.ptr(bias), c, _lib.ptr(scale), _lib.ptr(shift), _lib.stream_ptr(device)),
+               "ivf_bn_fold")
+    return [g, b, mu, var, bias]  # kept alive by the caller until the stream has consumed them
 
 
 class SplitConvOp:
@@ -137,33 +166,40 @@ class ConvOp:
 
 
 class Unit:
-    """Unit3D (pt/models/I3D_doubled.py:43-118): conv weights packed both ways + folded BN."""
+    """Unit3D (pt/models/I3D_doubled.py:43-118): conv weights packed both ways + folded BN.  `prefix` may be a
+    list: 1x1x1 units that read the same input, fused along the output channels into one GEMM."""
 
     def __init__(self, sd, prefix, stride, mode, device, s2d=False):
-        w = sd[prefix + ".conv3d.weight"].detach().to(device=device, dtype=torch.float32)
-        self.cout, self.cin = w.shape[0], w.shape[1]
-        self.kernel = tuple(w.shape[2:])
+        prefixes = [prefix] if isinstance(prefix, str) else list(prefix)
+        ws = [_dev32(sd[p + ".conv3d.weight"], device) for p in prefixes]
+        self.cout, self.cin = sum(w.shape[0] for w in ws), ws[0].shape[1]
+        self.kernel = tuple(ws[0].shape[2:])
         self.stride = tuple(stride)
         self.s2d = s2d
-        if prefix + ".bn.weight" in sd:
-            g = sd[prefix + ".bn.weight"].detach().to(device=device, dtype=torch.float32)
-            b = sd[prefix + ".bn.bias"].detach().to(device=device, dtype=torch.float32)
-            mu = sd[prefix + ".bn.running_mean"].detach().to(device=device, dtype=torch.float32)
-            var = sd[prefix + ".bn.running_var"].detach().to(device=device, dtype=torch.float32)
-            self.scale = (g / torch.sqrt(var + 1e-3)).contiguous()  # BatchNorm3d(eps=0.001), :75
-            self.shift = (b - mu * self.scale).contiguous()
+        self.scale = torch.empty(self.cout, dtype=torch.float32, device=device)
+        self.shift = torch.empty(self.cout, dtype=torch.float32, device=device)
+        keep, off = [], 0
+        for p, w in zip(prefixes, ws):  # BatchNorm3d(eps=0.001), pt/models/I3D_doubled.py:75
+            c = w.shape[0]
+            keep.append(bn_fold(sd, p, device, 1e-3, self.scale[off:off + c], self.shift[off:off + c]))
+            off += c
+        if len(prefixes) == 1 and prefixes[0] + ".conv3d.bias" in sd:  # the logits unit (no BN, bias)
+            self.shift_with_bias = torch.empty_like(self.shift)
+            keep.append(bn_fold(sd, prefixes[0], device, 1e-3, torch.empty_like(self.scale), self.shift_with_bias,
+                                with_conv_bias=True))
         else:
-            self.scale = torch.ones(self.cout, device=device)
-            self.shift = torch.zeros(self.cout, device=device)
+            self.shift_with_bias = self.shift
         if s2d:
             assert mode == "bf16" and self.stride == (2, 2, 2)
             win = (self.kernel[0] + 1) // 2
-            w = s2d_weight(w, win)
             self.kernel_eff, self.stride_eff, self.cin_eff = (win,) * 3, (1, 1, 1), 8 * self.cin
+            f = (2, 2, 2)
         else:
             self.kernel_eff, self.stride_eff, self.cin_eff = self.kernel, self.stride, self.cin
-        self.w_fwd = pack_fwd(w, mode)
-        self.w_dgrad = pack_dgrad(w, mode)
+            f = (1, 1, 1)
+        self.w_fwd = pack(ws, mode, s2d=f)
+        self.w_dgrad = pack(ws, mode, dgrad=True, s2d=f)
+        self._src = (ws, keep)  # the fp32 sources stay referenced: the pack kernels read them asynchronously
 
 
 class I3DEngine:
@@ -299,9 +335,9 @@ class I3DEngine:
         self.num_classes = wl.shape[0]
         self.w_logits = wl.reshape(self.num_classes, -1).contiguous()
         self.b_logits = sd["logits.conv3d.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
-        self.logits = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
-        self.probs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
-        self.dprobs = torch.zeros((B, self.num_classes), dtype=torch.float32, device=dev)
+        self.logits = ops.zeros((B, self.num_classes), torch.float32, dev)
+        self.probs = ops.zeros((B, self.num_classes), torch.float32, dev)
+        self.dprobs = ops.zeros((B, self.num_classes), torch.float32, dev)
         self.head_ws = ops.head_workspace(B, feat.c, self.num_classes, dev)  # this engine's partial logits
         self.fwd_ops.append((0, lambda: ops.head_fwd(feat, self.w_logits, self.b_logits, self.softmax, self.probs,
                                                      self.logits, workspace=self.head_ws)))
@@ -333,9 +369,9 @@ class I3DEngine:
                 self._build_inception_bwd(st, g_in, mask, mscale, add_unit_bwd)
 
         # ---- mask-search state; x is a static buffer so a captured graph stays valid across batches
-        self.x = torch.zeros((B, in_channels, self.T, self.H, self.W), dtype=torch.float32, device=dev)
-        self.dm = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
-        self.zero_mask = torch.zeros((B, self.T), dtype=torch.float32, device=dev)
+        self.x = ops.zeros((B, in_channels, self.T, self.H, self.W), torch.float32, dev)
+        self.dm = ops.zeros((B, self.T), torch.float32, dev)
+        self.zero_mask = ops.zeros((B, self.T), torch.float32, dev)
         if mode == "bf16" and tune.enabled():  # measured tile plans for the slab convolutions (cached per shape)
             with torch.cuda.device(dev):
                 for item in self.fwd_ops + self.bwd_ops:
@@ -357,16 +393,14 @@ class I3DEngine:
         # is likewise one data-gradient GEMM over the concatenated K
         fuse_b0 = mode == "bf16" and os.environ.get("IVF_FUSE_B0", "1") != "0"
         group = ("b0", "b1a", "b2a") if fuse_b0 else ("b1a", "b2a")
-        pre = "%s.%s" % (name, "|".join(group))
-        fsd = {pre + ".conv3d.weight": torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in group])}
-        for k in ("weight", "bias", "running_mean", "running_var"):
-            fsd["%s.bn.%s" % (pre, k)] = torch.cat([sd["%s.%s.bn.%s" % (name, b, k)] for b in group])
-        fused = Unit(fsd, pre, (1, 1, 1), mode, dev)
+        fused = Unit(sd, ["%s.%s" % (name, b) for b in group], (1, 1, 1), mode, dev)
         if fuse_b0:
-            w12 = torch.cat([sd["%s.%s.conv3d.weight" % (name, b)] for b in ("b1a", "b2a")])
-            fused.w_dgrad = pack_dgrad_two_sources(
-                sd["%s.b0.conv3d.weight" % name].detach().to(device=dev, dtype=torch.float32),
-                w12.detach().to(device=dev, dtype=torch.float32))
+            w0 = _dev32(sd["%s.b0.conv3d.weight" % name], dev)
+            k1 = (w0.shape[0] + 63) // 64 * 64
+            w1, w2 = (_dev32(sd["%s.%s.conv3d.weight" % (name, b)], dev) for b in ("b1a", "b2a"))
+            fused.w_dgrad = pack([w0, w1, w2], "bf16", dgrad=True, co_offs=[0, k1, k1 + w1.shape[0]],
+                                 co_total=k1 + w1.shape[0] + w2.shape[0])
+            fused._src2 = (w0, w1, w2)
         t12 = new_act(x.n, x.d, x.h, x.w, c1 + c3)
         t1, t2 = t12.slice(0, c1), t12.slice(c1, c3)
         t3 = new_act(x.n, x.d, x.h, x.w, x.c)
@@ -392,7 +426,11 @@ class I3DEngine:
         if not fuse_b0:
             add_unit_fwd(u["b0"], x, out.slice(0, c0))
         self.fwd_ops.append(("join",))
-        scale = torch.cat([u["b0"].scale, u["b1b"].scale, u["b2b"].scale, u["b3b"].scale]).contiguous()
+        scale = torch.empty(cout, dtype=torch.float32, device=dev)  # BN scales of the concat (ReLU'/BN' masks)
+        off = 0
+        for b in ("b0", "b1b", "b2b", "b3b"):
+            scale[off:off + u[b].cout].copy_(u[b].scale)  # contiguous same-dtype slices: cudaMemcpyAsync
+            off += u[b].cout
         g_t12 = t12.like()
         return dict(kind="inception", name=name, units=u, fused=fused, fuse_b0=fuse_b0, x=x, out=out, scale=scale,
                     gout=out.like(),
@@ -435,9 +473,16 @@ class I3DEngine:
 
     # ------------------------------------------------------------------------------------- running
     def set_input(self, x):
-        """x: fp32 [B,3,T,H,W] (the loader's layout), host or device; copied into the static buffer."""
+        """x: [B,3,T,H,W] in the loader's layout, host or device, fp32 (0..255) or uint8 (frames as decoded: they
+        cross PCIe as bytes and are converted on the device); copied into the static buffer."""
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
-        self.x.copy_(x, non_blocking=True)
+        if x.dtype == torch.uint8:
+            if getattr(self, "x_u8", None) is None:
+                self.x_u8 = torch.empty(self.x.shape, dtype=torch.uint8, device=self.device)
+            self.x_u8.copy_(x, non_blocking=True)
+            ops.u8_to_f32(self.x_u8, self.x)
+        else:
+            self.x.copy_(x, non_blocking=True)
 
     def _run(self, prog):
         """Issue a program on the current stream; forked lanes go to side streams (also under CUDA-graph
@@ -509,8 +554,39 @@ class I3DEngine:
     def set_targets(self, targets):
         """dprobs = one-hot(targets): the class_loss of pt/FindMasksComparison_I3D_smth.py:205."""
         self.generation += 1
-        self.dprobs.zero_()
-        self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
+        self._targets = ops.as_int32_targets(targets, self.device)
+        ops.one_hot(self._targets, self.dprobs)
+
+    @_lib.on_device
+    def gradcam(self, indices=None, out_hw=None, per_frame=True, cam=None, lowres=None, graphed=True,
+                layer="Mixed_5c"):
+        """Grad-CAM of the clips in the static input buffer (pt/grad_cam_videos.py:64-142): one forward, the head's
+        backward only, one fused kernel.  indices None = each clip's arg-max class (:70-71, taken on the device).
+        out_hw=(H, W) writes the upsampled, normalised map into `cam` [B, T, H, W] (allocated when None);
+        `lowres` [B, T', h, w] receives the map before upsampling (what a multi-GPU job gathers).  Returns
+        (cam or None, lowres or None, probs copy)."""
+        if layer != "Mixed_5c":
+            raise _lib.IvfError("the fused Grad-CAM path targets 'Mixed_5c'; other layers go through "
+                                "GradCamVideo's generic route")
+        probs = self.forward_graphed() if graphed else self.forward(None)
+        out = probs.clone()
+        if indices is None:
+            if getattr(self, "_argmax_buf", None) is None:
+                self._argmax_buf = torch.empty(self.B, dtype=torch.int32, device=self.device)
+            ops.argmax_rows(probs, self._argmax_buf)
+            self.generation += 1
+            self._targets = self._argmax_buf
+            ops.one_hot(self._targets, self.dprobs)
+        else:
+            self.set_targets(indices)
+        grad = self.head_grad_raw()
+        act = self.acts[layer]
+        step = self.T // act.d  # pt/grad_cam_videos.py:112-113
+        if out_hw is not None and cam is None:
+            cam = torch.empty((self.B, act.d * step, out_hw[0], out_hw[1]), dtype=torch.float32, device=self.device)
+        h_out, w_out = out_hw if out_hw is not None else (act.h, act.w)
+        ops.gradcam(act, grad, step, h_out, w_out, per_frame, cam, cam_lowres=lowres)
+        return cam, lowres, out
 
     @_lib.on_device
     def head_grad_raw(self):

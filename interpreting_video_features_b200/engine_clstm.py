@@ -18,28 +18,10 @@ import torch
 
 from . import _lib, ops, tune
 from ._lib import PFMT_S2D2_BF16, PFMT_TBHWC_F32
-from .engine import pack_dgrad, pack_fwd, strip_module_prefix
+from .engine import _dev32, pack, strip_module_prefix
 from .ops import Act
 
 GATES = ("i", "f", "c", "o")
-
-
-def s2d_weight_2d(w, win):
-    """(co,ci,k,k) stride-2 kernel -> (co,4ci,win,win) stride-1 kernel over the 2-D space-to-depth
-    input; channel = (a*2+b)*ci + ch, source tap = 2*delta + parity."""
-    co, ci, kh, kw = w.shape
-    out = w.new_zeros(co, 4 * ci, win, win)
-    for a in range(2):
-        for b in range(2):
-            blk = (a * 2 + b) * ci
-            for dh in range(win):
-                if 2 * dh + a >= kh:
-                    continue
-                for dw in range(win):
-                    if 2 * dw + b >= kw:
-                        continue
-                    out[:, blk:blk + ci, dh, dw] = w[:, :, 2 * dh + a, 2 * dw + b]
-    return out
 
 
 class CLSTMEngine:
@@ -72,24 +54,18 @@ class CLSTMEngine:
         if self.H % 2 or self.W % 2:
             raise _lib.IvfError("native ConvLSTM needs even frame sizes")
 
-        def pad_gates(w4, cin_eff, cin):
-            """list of 4 per-gate [hid, cin, k, k] -> [4*he, cin_eff, 1, k, k] (zero padded)."""
-            out = torch.zeros((4 * he, cin_eff, 1, 5, 5), device=dev)
-            for gi, w in enumerate(w4):
-                out[gi * he:gi * he + hidden, :cin, 0] = w
-            return out
-
-        if batch_norm:
-            g, b_, mu, var = (sd["clstm.bn." + k] for k in ("weight", "bias", "running_mean", "running_var"))
-            sc = g / torch.sqrt(var + 1e-5)  # BatchNorm2d(eps=1e-05), convolution_lstm.py:85
-            self.bn_scale = torch.zeros(he, device=dev)
-            self.bn_shift = torch.zeros(he, device=dev)
-            self.bn_scale[:hidden] = sc
-            self.bn_shift[:hidden] = b_ - mu * sc
+        self.bn_scale = ops.zeros((he,), torch.float32, dev)  # padded channels: scale 0, shift 0
+        self.bn_shift = ops.zeros((he,), torch.float32, dev)
+        lib = _lib.load()
+        if batch_norm:  # BatchNorm2d(eps=1e-05), convolution_lstm.py:85
+            _lib.check(lib.ivf_bn_fold(_lib.handle(dev), *(_lib.ptr(sd["clstm.bn." + k]) for k in
+                                                            ("weight", "bias", "running_mean", "running_var")),
+                                       1e-5, None, hidden, _lib.ptr(self.bn_scale), _lib.ptr(self.bn_shift),
+                                       _lib.stream_ptr(dev)), "ivf_bn_fold")
         else:
-            self.bn_scale = torch.zeros(he, device=dev)
-            self.bn_scale[:hidden] = 1.0
-            self.bn_shift = torch.zeros(he, device=dev)
+            _lib.check(lib.ivf_bn_fold(_lib.handle(dev), None, None, None, None, 0.0, None, hidden,
+                                       _lib.ptr(self.bn_scale), _lib.ptr(self.bn_shift), _lib.stream_ptr(dev)),
+                       "ivf_bn_fold")
 
         # ---- input operand of layer 0
         if bf:
@@ -108,11 +84,13 @@ class CLSTMEngine:
             p = "clstm.cell%d." % l
             cin_real = cin if l == 0 else hidden
             cin_eff = cin_real if l == 0 else he
-            wx = pad_gates([sd[p + "Wx%s.weight" % g] for g in GATES], cin_eff, cin_real)
-            bias = torch.zeros(4 * he, device=dev)
+            # the four gates side by side (i, f, c, o), each padded from `hidden` to `he` channels
+            wxs = [sd[p + "Wx%s.weight" % g].contiguous() for g in GATES]
+            whs = [sd[p + "Wh%s.weight" % g].contiguous() for g in GATES]
+            gate_offs = [gi * he for gi in range(4)]
+            bias = ops.zeros((4 * he,), torch.float32, dev)
             for gi, g in enumerate(GATES):
-                bias[gi * he:gi * he + hidden] = sd[p + "Wx%s.bias" % g]
-            wh = pad_gates([sd[p + "Wh%s.weight" % g] for g in GATES], he, hidden)
+                bias[gi * he:gi * he + hidden].copy_(sd[p + "Wx%s.bias" % g])
             ho, wo = hin // 2, win // 2
             if (hin + 4 - 5) // 2 + 1 != ho or (win + 4 - 5) // 2 + 1 != wo:
                 raise _lib.IvfError("ConvLSTM layer %d: odd input %dx%d (the reference asserts here too)" % (l, hin, win))
@@ -120,31 +98,35 @@ class CLSTMEngine:
             s2d_out = bf and not last
             if s2d_out and ((ho // 2) % 2 or (wo // 2) % 2):
                 raise _lib.IvfError("bf16 ConvLSTM needs an even pooled map between layers; use mode='fp32'")
-            rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias.contiguous(), ones=torch.ones(4 * he, device=dev))
-            if bf:
-                w2 = s2d_weight_2d(wx[:, :, 0], 3)  # [4he, 4*cin_eff, 3, 3]
-                if l == 0:  # operand buffer has 16 channels (12 used)
-                    w2 = torch.cat([w2, w2.new_zeros(4 * he, 16 - w2.shape[1], 3, 3)], dim=1)
-                w2 = w2.unsqueeze(2)
-                rec.update(wx_f=pack_fwd(w2, mode), wx_d=pack_dgrad(w2, mode), xk=(1, 3, 3), xs=(1, 1, 1), xpf=(0, 1, 1),
-                           xdpf=(0, 1, 1))
+            ones = torch.empty(4 * he, dtype=torch.float32, device=dev)
+            _lib.check(lib.ivf_fill_u32(_lib.handle(dev), _lib.ptr(ones), 16 * he, 0x3F800000, _lib.stream_ptr(dev)),
+                       "ivf_fill_u32")  # 1.0f
+            rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias, ones=ones)
+            gk = dict(co_offs=gate_offs, co_total=4 * he)
+            if bf:  # stride-2 5x5 as a stride-1 3x3 over the 2-D space-to-depth record (12 -> 16 channels at l = 0)
+                xk = dict(s2d=(1, 2, 2), ci_stride=cin_eff, ceff_total=16 if l == 0 else None, **gk)
+                rec.update(wx_f=pack(wxs, mode, **xk), wx_d=pack(wxs, mode, dgrad=True, **xk), xk=(1, 3, 3),
+                           xs=(1, 1, 1), xpf=(0, 1, 1), xdpf=(0, 1, 1))
             else:
-                rec.update(wx_f=pack_fwd(wx, mode), wx_d=pack_dgrad(wx, mode), xk=(1, 5, 5), xs=(1, 2, 2), xpf=(0, 2, 2))
-            rec.update(wh_f=pack_fwd(wh, mode), wh_d=pack_dgrad(wh, mode))
+                rec.update(wx_f=pack(wxs, mode, ci_stride=cin_eff, **gk),
+                           wx_d=pack(wxs, mode, dgrad=True, ci_stride=cin_eff, **gk), xk=(1, 5, 5), xs=(1, 2, 2),
+                           xpf=(0, 2, 2))
+            rec.update(wh_f=pack(whs, mode, ci_stride=he, **gk), wh_d=pack(whs, mode, dgrad=True, ci_stride=he, **gk))
+            rec["_src"] = (wxs, whs)
             rec["x"], rec["g_x"] = x_act, gx_in
             rec["gx"] = Act.empty(N, 1, ho, wo, 4 * he, torch.float32, dev)            # gate pre-activations
             rec["h"] = Act.empty(N, 1, ho, wo, he, self.dtype, dev, zero=True)
-            rec["c"] = torch.zeros((N, ho, wo, he), dtype=torch.float32, device=dev)
-            rec["gact"] = torch.zeros((N, ho * wo, 4 * he), dtype=torch.float32, device=dev)
-            rec["argmax"] = torch.zeros((N, ho // 2, wo // 2, he), dtype=torch.uint8, device=dev)
+            rec["c"] = ops.zeros((N, ho, wo, he), torch.float32, dev)
+            rec["gact"] = ops.zeros((N, ho * wo, 4 * he), torch.float32, dev)
+            rec["argmax"] = ops.zeros((N, ho // 2, wo // 2, he), torch.uint8, dev)
             if s2d_out:
                 rec["pooled"] = Act.empty(N, 1, ho // 4, wo // 4, 4 * he, self.dtype, dev, zero=True)
             else:
                 rec["pooled"] = Act.empty(N, 1, ho // 2, wo // 2, he, self.dtype, dev, zero=True)
             rec["s2d_out"] = s2d_out
             rec["g_pooled"] = rec["pooled"].like(zero=True)
-            rec["dH"] = torch.zeros((N, ho, wo, he), dtype=torch.float32, device=dev)
-            rec["dc"] = torch.zeros((B, ho, wo, he), dtype=torch.float32, device=dev)
+            rec["dH"] = ops.zeros((N, ho, wo, he), torch.float32, dev)
+            rec["dc"] = ops.zeros((B, ho, wo, he), torch.float32, dev)
             rec["dpre"] = Act.empty(N, 1, ho, wo, 4 * he, self.dtype, dev, zero=True)
             self.layers.append(rec)
             x_act, gx_in = rec["pooled"], rec["g_pooled"]
@@ -153,23 +135,23 @@ class CLSTMEngine:
 
         # ---- classifier: Linear over the NCHW-flattened last effective step (CLSTM_4.py:78-80), columns
         # permuted once to our channels-last flattening
-        wfc = sd["endFC.weight"]
+        wfc = strip_module_prefix(state_dict)["endFC.weight"].detach().float().cpu()  # permuted on the host
         ncls = wfc.shape[0]
         if wfc.shape[1] != hidden * hin * win:
             raise _lib.IvfError("endFC expects %d features, the stack produces %d (use_entire_seq is not supported)"
                                 % (wfc.shape[1], hidden * hin * win))
-        wp = torch.zeros((ncls, hin * win, he), device=dev)
+        wp = torch.zeros((ncls, hin * win, he))
         wp[:, :, :hidden] = wfc.view(ncls, hidden, hin * win).permute(0, 2, 1)
-        self.w_fc = wp.reshape(ncls, -1).contiguous()
+        self.w_fc = wp.reshape(ncls, -1).contiguous().to(dev)
         self.b_fc = sd["endFC.bias"].contiguous()
         self.num_classes = ncls
-        self.logits = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
-        self.probs = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
-        self.dprobs = torch.zeros((B, ncls), dtype=torch.float32, device=dev)
-        self.x = torch.zeros((B, in_channels, T, self.H, self.W), dtype=torch.float32, device=dev)
-        self.dm = torch.zeros((B, T), dtype=torch.float32, device=dev)
-        self.zero_mask = torch.zeros((B, T), dtype=torch.float32, device=dev)
-        self.g_feat_raw = torch.zeros((B, hin * win * he), dtype=torch.float32, device=dev)
+        self.logits = ops.zeros((B, ncls), torch.float32, dev)
+        self.probs = ops.zeros((B, ncls), torch.float32, dev)
+        self.dprobs = ops.zeros((B, ncls), torch.float32, dev)
+        self.x = ops.zeros((B, in_channels, T, self.H, self.W), torch.float32, dev)
+        self.dm = ops.zeros((B, T), torch.float32, dev)
+        self.zero_mask = ops.zeros((B, T), torch.float32, dev)
+        self.g_feat_raw = ops.zeros((B, hin * win * he), torch.float32, dev)
         self.head_ws = ops.head_workspace(B, hin * win * he, ncls, dev)
 
         # measured tile plans for the recurrent convolutions: each is a 15-35 us launch repeated T-1 times per
@@ -186,8 +168,8 @@ class CLSTMEngine:
                     fwd.tune(dev, min_ms=0.012)
                     bwd.tune(dev, min_ms=0.012)
                     rec["plan_hf"], rec["plan_hd"] = fwd.plan, bwd.plan
-                    rec["gx"].buf.zero_()
-                    rec["dH"].zero_()
+                    ops.fill_zero(rec["gx"].buf)
+                    ops.fill_zero(rec["dH"])
                 torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ helpers
@@ -204,14 +186,22 @@ class CLSTMEngine:
         return Act(a.buf, self.B, 1, 1, 1, k, 0, k)
 
     def set_input(self, x):
+        """x: [B,3,T,H,W] in the loader's layout, host or device, fp32 (0..255) or uint8 (frames as decoded: they
+        cross PCIe as bytes and are converted on the device); copied into the static buffer."""
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (x.shape,)
-        self.x.copy_(x, non_blocking=True)
+        if x.dtype == torch.uint8:
+            if getattr(self, "x_u8", None) is None:
+                self.x_u8 = torch.empty(self.x.shape, dtype=torch.uint8, device=self.device)
+            self.x_u8.copy_(x, non_blocking=True)
+            ops.u8_to_f32(self.x_u8, self.x)
+        else:
+            self.x.copy_(x, non_blocking=True)
 
     @_lib.on_device
     def set_targets(self, targets):
         self.generation += 1
-        self.dprobs.zero_()
-        self.dprobs[torch.arange(self.B, device=self.device), targets.to(self.device).long()] = 1.0
+        self._targets = ops.as_int32_targets(targets, self.device)
+        ops.one_hot(self._targets, self.dprobs)
 
     # ------------------------------------------------------------------ forward
     @_lib.on_device
@@ -248,7 +238,7 @@ class CLSTMEngine:
         ops.head_bwd(self._feat(top["g_pooled"], te), self.w_fc, self.softmax, self.probs, self.dprobs)
         for rec in reversed(self.layers):
             ops.bn_pool2d_bwd(rec["g_pooled"].buf, rec["argmax"], self.bn_scale, rec["dH"], s2d=rec["s2d_out"])
-            rec["dc"].zero_()
+            ops.fill_zero(rec["dc"])
             m = B * rec["ho"] * rec["wo"]
             dH = Act(rec["dH"], T * B, 1, rec["ho"], rec["wo"], he, 0, he)
             for t in range(T - 1, -1, -1):
@@ -282,7 +272,7 @@ class CLSTMEngine:
         hw, he = self.fh * self.fw, self.he
         pooled = top["pooled"].buf.view(self.T, B, hw * he)
         act = pooled[self.eff].permute(1, 0, 2).contiguous().view(B, E, self.fh, self.fw, he)
-        grad = torch.zeros((B, E, hw * he), dtype=torch.float32, device=self.device)
+        grad = ops.zeros((B, E, hw * he), torch.float32, self.device)
         g = Act(self.g_feat_raw, B, 1, 1, 1, hw * he, 0, hw * he)
         ops.head_bwd(g, self.w_fc, self.softmax, self.probs, self.dprobs)
         grad[:, E - 1] = self.g_feat_raw

@@ -16,6 +16,57 @@ from ._lib import (EP_ACCUM, EP_AFFINE, EP_MASK, EP_OUT_F32, EP_RELU, IVF_BF16, 
                    PoolDesc, check, ptr)
 
 
+def fill_zero(t):
+    """Zero a contiguous device tensor with a libivf launch on the current stream of its device."""
+    assert t.is_contiguous() and (t.numel() * t.element_size()) % 4 == 0, "fill_zero: 4-byte granularity"
+    if t.numel():
+        check(_lib.load().ivf_fill_u32(_lib.handle(t.device), ptr(t), t.numel() * t.element_size(), 0,
+                                       _lib.stream_ptr(t.device)), "ivf_fill_u32")
+    return t
+
+
+def zeros(shape, dtype, device):
+    """torch.zeros without a torch kernel: allocation by the caching allocator, fill by libivf."""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if (t.numel() * t.element_size()) % 4:
+        return t.zero_()  # odd byte counts (tiny uint8 buffers): not worth a kernel variant
+    return fill_zero(t)
+
+
+def u8_to_f32(src, dst):
+    """dst (fp32, device) = float(src) for a uint8 device tensor of the same element count."""
+    assert src.dtype == torch.uint8 and dst.dtype == torch.float32 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    check(_lib.load().ivf_u8_to_f32(_lib.handle(dst.device), ptr(src), ptr(dst), src.numel(),
+                                    _lib.stream_ptr(dst.device)), "ivf_u8_to_f32")
+    return dst
+
+
+def one_hot(targets, out):
+    """out[n, ncls] (fp32) = one_hot(targets[n]); targets int32 on the device."""
+    n, ncls = out.shape
+    assert targets.dtype == torch.int32 and targets.numel() == n
+    check(_lib.load().ivf_one_hot(_lib.handle(out.device), ptr(targets), n, ncls, ptr(out),
+                                  _lib.stream_ptr(out.device)), "ivf_one_hot")
+    return out
+
+
+def argmax_rows(x, out):
+    """out[n] (int32) = first arg-maximum of each row of x[n, ncls] (fp32), on the device."""
+    n, ncls = x.shape
+    check(_lib.load().ivf_argmax_rows(_lib.handle(x.device), ptr(x), n, ncls, ptr(out), _lib.stream_ptr(x.device)),
+          "ivf_argmax_rows")
+    return out
+
+
+def as_int32_targets(targets, device):
+    """Class indices as an int32 device tensor (converted on the host when they arrive from the host)."""
+    t = torch.as_tensor(targets)
+    if not t.is_cuda:
+        return t.to(torch.int32).to(device, non_blocking=True)
+    return t.to(device=device, dtype=torch.int32)
+
+
 class Act:
     """A channel slice [coff, coff+c) of a channels-last buffer of logical shape (n,d,h,w,ld)."""
 
@@ -27,8 +78,8 @@ class Act:
 
     @staticmethod
     def empty(n, d, h, w, c, dtype, device, zero=False):
-        f = torch.zeros if zero else torch.empty
-        return Act(f((n, d, h, w, c), dtype=dtype, device=device), n, d, h, w, c, 0, c)
+        buf = zeros((n, d, h, w, c), dtype, device) if zero else torch.empty((n, d, h, w, c), dtype=dtype, device=device)
+        return Act(buf, n, d, h, w, c, 0, c)
 
     def slice(self, coff, c):
         assert coff + c <= self.c
@@ -241,6 +292,23 @@ def sigmoid(m, out):
     return out
 
 
+def select_scores(probs, targets, out):
+    """out[n] = probs[n, targets[n]] (targets int32 on the device)."""
+    n, ncls = probs.shape
+    check(_lib.load().ivf_select_scores(_lib.handle(probs.device), ptr(probs), ptr(targets), n, ncls, ptr(out),
+                                        _lib.stream_ptr(probs.device)), "ivf_select_scores")
+    return out
+
+
+def init_mask_select(scores, t, threshold, raw, chosen=None):
+    """scores fp32 [1 + t/2, n] (rows: original, fully frozen, centred windows) -> raw masks [n, t] on the device."""
+    rows, n = scores.shape
+    assert rows == 1 + max(t // 2, 1) and tuple(raw.shape) == (n, t)
+    check(_lib.load().ivf_init_mask_select(_lib.handle(scores.device), ptr(scores), n, t, float(threshold), ptr(raw),
+                                           ptr(chosen), _lib.stream_ptr(scores.device)), "ivf_init_mask_select")
+    return raw
+
+
 def tv_norm(mask, p, q, val, dmask=None):
     check(_lib.load().ivf_tv_norm(_lib.handle(mask.device), ptr(mask), mask.numel(), float(p), float(q),
                                   ptr(val), ptr(dmask), _lib.stream_ptr(mask.device)), "ivf_tv_norm")
@@ -248,7 +316,8 @@ def tv_norm(mask, p, q, val, dmask=None):
 
 
 def gradcam(act, grad, step, hout, wout, per_frame, cam, cam_lowres=None):
-    """act/grad: Act of the target layer (same geometry); cam fp32 [n, tp*step, hout, wout]."""
+    """act/grad: Act of the target layer (same geometry); cam fp32 [n, tp*step, hout, wout] (None: only the
+    low-resolution map cam_lowres [n, tp, hp, wp] is written)."""
     assert act.coff == 0 and grad.coff == 0 and act.ld == grad.ld
     check(_lib.load().ivf_gradcam(_lib.handle(act.buf.device), _lib.dtype_code(act.buf),
                                   _lib.dtype_code(grad.buf), ptr(act.buf), ptr(grad.buf), act.n, act.d,

@@ -46,14 +46,20 @@ class GradCamVideo:
 
     def batched(self, input, indices=None):
         """Any batch size: cams [B,T',H,W] (numpy) and outputs [B,classes] (device tensor)."""
-        x = input.cuda().float().contiguous()
+        x = input if input.dtype == torch.uint8 else input.float()  # uint8 frames are converted on the device
+        x = x.cuda(non_blocking=True).contiguous()
         if self.archType == "I3D":
             cam, out = self._i3d(x, indices)
         elif self.archType == "CLSTM":
             cam, out = self._clstm(x, indices)
         else:
             raise ValueError("archType must be 'I3D' or 'CLSTM'")
-        return cam.cpu().numpy(), out
+        # pinned destination from torch's caching host allocator (a fresh block per call: the numpy array the caller
+        # keeps owns it), one asynchronous D2H, one stream synchronise - not a pageable bounce
+        host = torch.empty(cam.shape, dtype=cam.dtype, pin_memory=True)
+        host.copy_(cam, non_blocking=True)
+        torch.cuda.current_stream(cam.device).synchronize()
+        return host.numpy(), out
 
     def _i3d(self, x, indices):
         name = self.target_layer_names[-1]
@@ -62,19 +68,9 @@ class GradCamVideo:
             raise _lib.IvfError("native Grad-CAM targets 'Mixed_5c' (the layer the reference drivers use, "
                                 "pt/FindMasksComparison_I3D_smth.py:258); got %r" % name)
         eng.set_input(x)
-        probs = eng.forward_graphed() if os.environ.get("IVF_GRADCAM_GRAPH", "1") != "0" else eng.forward(None)
-        out = probs.clone()
-        if indices is None:
-            tg = torch.argmax(out, dim=1)  # pt/grad_cam_videos.py:70-71
-        else:
-            tg = torch.as_tensor(indices, device=out.device)
-        eng.set_targets(tg)  # one_hot * output, :73-79
-        grad = eng.head_grad_raw()
-        act = eng.acts[name]
-        step = x.shape[2] // act.d  # :112-113
-        w_out, h_out = self.input_spatial_size  # cv2 dsize = (width, height), :119-120
-        cam = torch.empty((x.shape[0], act.d * step, h_out, w_out), dtype=torch.float32, device=x.device)
-        ops.gradcam(act, grad, step, h_out, w_out, self.normalizePerFrame, cam)
+        w_out, h_out = self.input_spatial_size  # cv2 dsize = (width, height), pt/grad_cam_videos.py:119-120
+        cam, _, out = eng.gradcam(indices, (h_out, w_out), self.normalizePerFrame,
+                                  graphed=os.environ.get("IVF_GRADCAM_GRAPH", "1") != "0")
         return cam, out
 
     def _clstm(self, x, indices):

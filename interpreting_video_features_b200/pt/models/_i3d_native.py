@@ -173,10 +173,7 @@ class Unit3D(nn.Module):
         hit = self._pack_cache.get(key)
         if hit is None or hit[0] != ver:
             sd = {"u." + k: v for k, v in self.state_dict().items()}
-            unit = Unit(sd, "u", tuple(self._stride), mode, device)
-            bias = sd.get("u.conv3d.bias")
-            unit.shift_with_bias = unit.shift if bias is None else (
-                unit.shift + unit.scale * bias.detach().to(device=device, dtype=torch.float32)).contiguous()
+            unit = Unit(sd, "u", tuple(self._stride), mode, device)  # shift_with_bias folds a conv bias
             hit = (ver, unit)
             self._pack_cache[key] = hit
         return hit[1]

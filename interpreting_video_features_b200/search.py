@@ -41,12 +41,12 @@ class MaskSearch:
             self.slices.append(slice(off, off + e.B))
             off += e.B
         B, T, dev = self.B, self.T, self.device
-        self.m = torch.zeros((B, T), dtype=torch.float32, device=dev)        # raw mask (Adam parameter)
-        self.sig = torch.zeros((B, T), dtype=torch.float32, device=dev)      # sigmoid(m)
-        self.exp_avg = torch.zeros_like(self.m)
-        self.exp_avg_sq = torch.zeros_like(self.m)
-        self.step = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.losses = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+        self.m = ops.zeros((B, T), torch.float32, dev)        # raw mask (Adam parameter)
+        self.sig = ops.zeros((B, T), torch.float32, dev)      # sigmoid(m)
+        self.exp_avg = ops.zeros((B, T), torch.float32, dev)
+        self.exp_avg_sq = ops.zeros((B, T), torch.float32, dev)
+        self.step = ops.zeros((B,), torch.int32, dev)
+        self.losses = ops.zeros((B, 3), torch.float32, dev)
         self.graph = None
         self.launches_per_iter = None
         self._gstreams = None
@@ -74,6 +74,17 @@ class MaskSearch:
 
     def dm(self):
         return torch.cat([e.dm for e in self.engs]) if len(self.engs) > 1 else self.eng.dm
+
+    @_lib.on_device
+    def gradcam_lowres(self, targets):
+        """Un-normalised low-resolution Grad-CAM maps [B, T', h, w] of the clips in the static input buffers for
+        the given classes (forward replayed from the engines' graphs, head backward, fused kernel)."""
+        if getattr(self, "_cam_low", None) is None:
+            a = self.eng.acts["Mixed_5c"]
+            self._cam_low = torch.empty((self.B, a.d, a.h, a.w), dtype=torch.float32, device=self.device)
+        for e, sl in zip(self.engs, self.slices):
+            e.gradcam(targets[sl], None, True, cam=None, lowres=self._cam_low[sl])
+        return self._cam_low
 
     def _group_iteration(self, e, sl):
         e.forward(self.sig[sl], self.perturb)
@@ -115,10 +126,12 @@ class MaskSearch:
 
     @_lib.on_device
     def init_masks(self, targets, mode="central", generator=None):
-        """Batched pt/mask.py:103-169; returns raw masks [B,T] on the device and the unperturbed probs."""
+        """Batched pt/mask.py:103-169; returns raw masks [B,T] on the device and the unperturbed probs.
+        'central': every candidate window is one batched forward whose class scores stay on the device
+        (ivf_select_scores); ivf_init_mask_select then applies the reference's stopping rule per clip.  Nothing is
+        read back, so the host queues the whole search behind the initialisation without waiting for it."""
         B, T, dev = self.B, self.T, self.device
-        idx = torch.arange(B, device=dev)
-        tg = targets.to(dev).long()
+        self.set_targets(targets)
         probs_orig = self.forward(None, "freeze")
         if mode == "random":
             m = (torch.rand((B, T), generator=generator) > 0.7).float()
@@ -127,28 +140,31 @@ class MaskSearch:
                 if abs(float(m[b].sum())) == 2.5 * T:
                     m[b, 8] += 0.1
             return m.to(dev), probs_orig
-        cand = [torch.ones(T)]  # fully frozen
-        for i in range(1, T // 2):
-            c = torch.ones(T)
-            c[:i] = 0
-            c[-i:] = 0
-            cand.append(c)
-        scores = [probs_orig[idx, tg]]
-        for c in cand:
-            scores.append(self.forward(c.to(dev), self.perturb if c is not cand[0] else "freeze")[idx, tg])
-        sc = torch.stack(scores).cpu().numpy()  # [2 + ncand, B]; the one host read-back of init
-        orig, frozen, cen = sc[0], sc[1], sc[2:]
-        raw = np.empty((B, T), dtype=np.float32)
-        for b in range(B):
-            chosen = None
-            for k in range(cen.shape[0]):
-                chosen = k
-                ratio = np.float32(orig[b] - cen[k, b]) / np.float32(orig[b] - frozen[b])
-                if ratio < self.threshold:
-                    break
-            row = np.ones(T, dtype=np.float32) if chosen is None else cand[chosen + 1].numpy()
-            raw[b] = np.where(row == 0, -5.0, 5.0)
-        return torch.from_numpy(raw).to(dev), probs_orig
+        if mode != "central":
+            raise ValueError("mode must be 'central' or 'random'")
+        ncand = max(T // 2, 1)  # fully frozen + the centred windows i = 1 .. T/2-1
+        scores = torch.empty((1 + ncand, B), dtype=torch.float32, device=dev)
+        if getattr(self, "_cand", None) is None:  # candidate masks, uploaded once per searcher
+            cand = torch.ones((ncand, T))
+            for i in range(1, T // 2):
+                cand[i, :i] = 0
+                cand[i, T - i:] = 0
+            self._cand = cand.to(dev)
+
+        def score_row(j):
+            for e, sl in zip(self.engs, self.slices):
+                ops.select_scores(e.probs, e._targets, scores[j, sl])
+
+        score_row(0)
+        for j in range(ncand):
+            for e in self.engs:
+                e.forward(self._cand[j], "freeze" if j == 0 else self.perturb)
+            score_row(1 + j)
+        raw = torch.empty((B, T), dtype=torch.float32, device=dev)
+        self.init_choice = torch.empty(B, dtype=torch.int32, device=dev)
+        ops.init_mask_select(scores, T, self.threshold, raw, self.init_choice)
+        self.init_scores = scores
+        return raw, probs_orig
 
     @_lib.on_device
     def run(self, x, targets, init="central", raw_masks=None, n_iter=None, record=None):
@@ -164,9 +180,9 @@ class MaskSearch:
         else:
             probs_orig = self.forward(None, "freeze")
         self.m.copy_(raw_masks)
-        self.exp_avg.zero_()
-        self.exp_avg_sq.zero_()
-        self.step.zero_()
+        ops.fill_zero(self.exp_avg)
+        ops.fill_zero(self.exp_avg_sq)
+        ops.fill_zero(self.step)
         ops.sigmoid(self.m, self.sig)
         if self.use_graph and self.graph is None and n_iter > 0:
             saved = [t.clone() for t in (self.m, self.sig, self.exp_avg, self.exp_avg_sq, self.step)]
@@ -237,23 +253,76 @@ def make_engines(model, x, micro_batch, groups):
     return [model._engine(x, batch=per, tag=g) for g in range(groups)]
 
 
+class _Stager:
+    """Micro-batches of host clips -> the engine's static input buffer without a pageable bounce: two pinned
+    staging buffers filled by a host gather (clips[sel] of arbitrary indices), copied H2D on the search's
+    stream; an event per buffer keeps the host from refilling it before its copy has run.  Pinned clips whose
+    selection is one contiguous range skip the staging copy."""
+
+    def __init__(self, clips, micro_batch):
+        self.clips = clips
+        self.on_host = not clips.is_cuda
+        self.bufs, self.events, self.k = [None, None], [None, None], 0
+        self.shape = (micro_batch,) + tuple(clips.shape[1:])
+
+    def get(self, sel):
+        if not self.on_host:
+            return self.clips[sel]
+        lo, n = sel[0], len(sel)
+        if self.clips.is_pinned() and sel == list(range(lo, lo + n)):
+            return self.clips[lo:lo + n]
+        k = self.k = self.k ^ 1
+        if self.bufs[k] is None:
+            self.bufs[k] = torch.empty(self.shape, dtype=self.clips.dtype, pin_memory=True)
+        elif self.events[k] is not None:
+            self.events[k].synchronize()
+        torch.index_select(self.clips, 0, torch.as_tensor(sel), out=self.bufs[k])
+        return self.bufs[k]
+
+    def used(self, device):
+        if self.on_host and self.bufs[self.k] is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self.events[self.k] = ev
+
+
 def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, perturb="freeze",
                        init="central", threshold=0.9, micro_batch=8, lr=0.2, use_graph=True, rank=0, world=1,
-                       device=None, groups=None):
-    """Mask search over `clips` [N,3,T,H,W] (host or device) for this rank's shard; returns a dict of
-    [N, ...] tensors (gathered over ranks when torch.distributed is initialised and world > 1).
-    `model` is a drop-in models.I3D_doubled[_kth].Model in eval mode."""
+                       device=None, groups=None, gradcam=False, n_total=None, stats=None):
+    """Mask search (and, with gradcam=True, the Grad-CAM the drivers run per clip,
+    pt/FindMasksComparison_I3D_smth.py:257-269) over this rank's shard of the clips; returns a dict of [N, ...]
+    device tensors, gathered over ranks when torch.distributed is initialised and world > 1.
+
+    clips: [N,3,T,H,W] host or device, fp32 0..255 or uint8 - every rank holds all N and works on r::W; or, with
+    n_total given, only this rank's clips in the order of shard_indices(n_total, rank, world) (a loader that
+    decodes just its shard).  targets follow clips.  `model` is a drop-in models.I3D_doubled[_kth].Model in eval
+    mode.  gradcam=True adds cam_lowres [N, T', h, w]: the target class's un-normalised low-resolution map at
+    Mixed_5c (upsampling and normalisation are one kernel per clip wherever the maps are consumed).
+    Nothing in the loop reads back from the device: the host runs ahead of the GPU by whole micro-batches.
+    stats (dict, optional) receives 'gather_seconds' (device-timed) and 'micro_batches'."""
+    import torch.distributed as dist
     device = torch.device(device if device is not None else "cuda")
-    N, C, T, H, W = clips.shape
-    mine = shard_indices(N, rank, world)
+    N_in, C, T, H, W = clips.shape
+    if n_total is None:
+        N = N_in
+        mine = shard_indices(N, rank, world)
+        local_of = {g: g for g in mine}  # global index -> row of `clips`
+    else:
+        N = int(n_total)
+        mine = shard_indices(N, rank, world)
+        assert N_in == len(mine), "n_total: clips must hold exactly this rank's shard (%d != %d)" % (N_in, len(mine))
+        local_of = {g: i for i, g in enumerate(mine)}
+    stager = _Stager(clips, micro_batch)
+    targets = torch.as_tensor(targets)
     searcher = None
     rows = []
+    n_mb = 0
     for s in range(0, len(mine), micro_batch):
-        sel = mine[s:s + micro_batch]
+        sel = [local_of[g] for g in mine[s:s + micro_batch]]
         n_valid = len(sel)
         if n_valid < micro_batch:  # ragged tail: repeat the last clip, drop the duplicates afterwards
             sel = sel + [sel[-1]] * (micro_batch - n_valid)
-        x = clips[sel].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        x = stager.get(sel)
         tg = targets[sel]
         if searcher is None:
             engs = make_engines(model, x, micro_batch, default_groups(micro_batch) if groups is None else groups)
@@ -268,17 +337,37 @@ def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, 
                 searcher = cache[key] = MaskSearch(engs, lam1, lam2, lr, n_iter, perturb, threshold, use_graph)
             searcher.n_iter = int(n_iter)  # the captured graph is one iteration: the count is free
         res = searcher.run(x, tg, init=init)
-        row = torch.cat([res["time_mask"], res["freeze_score"][:, None], res["reverse_score"][:, None],
-                         res["probs_orig"]], dim=1)[:n_valid]
-        rows.append(row)
+        stager.used(device)
+        cols = [res["time_mask"], res["freeze_score"][:, None], res["reverse_score"][:, None], res["probs_orig"]]
+        if gradcam:  # the clips are still in the engines' static buffers
+            cols.append(searcher.gradcam_lowres(tg).flatten(1))
+        rows.append(torch.cat(cols, dim=1)[:n_valid])
+        n_mb += 1
     ncls = model._num_classes
-    local = torch.cat(rows) if rows else torch.zeros((0, T + 2 + ncls), device=device)
-    import torch.distributed as dist
+    if rows:
+        local = torch.cat(rows)
+    else:  # a rank without clips still takes part in the gather: it needs the row width
+        cam_elems = 1
+        for k in model.avg_pool.kernel_size:  # the Mixed_5c map is exactly the average pool's window (engine check)
+            cam_elems *= int(k)
+        local = torch.zeros((0, T + 2 + ncls + (cam_elems if gradcam else 0)), device=device)
     indices = mine
+    gather_s = 0.0
     if world > 1 and dist.is_available() and dist.is_initialized():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(device))
         full = gather_rows(local, mine, N, world)
+        e1.record(torch.cuda.current_stream(device))
+        if stats is not None:
+            e1.synchronize()
+            gather_s = e0.elapsed_time(e1) * 1e-3
         indices = list(range(N))
     else:  # single rank, or a shard computed without a process group (rows follow `indices`)
         full = local
-    return dict(time_mask=full[:, :T], freeze_score=full[:, T], reverse_score=full[:, T + 1],
-                probs_orig=full[:, T + 2:], indices=indices)
+    if stats is not None:
+        stats.update(gather_seconds=gather_s, micro_batches=n_mb, gathered_bytes=int(full.numel() * 4))
+    out = dict(time_mask=full[:, :T], freeze_score=full[:, T], reverse_score=full[:, T + 1],
+               probs_orig=full[:, T + 2:T + 2 + ncls], indices=indices)
+    if gradcam:
+        out["cam_lowres"] = full[:, T + 2 + ncls:].reshape(-1, *[int(k) for k in model.avg_pool.kernel_size])
+    return out

@@ -26,11 +26,16 @@ def _cell(sd, p, x, h, c, k, stride, quant=False):
 
 
 def forward(sd, x, num_layers, hidden, kernel=5, conv_stride=2, step=None, effective_step=(7, 15, 23, 31),
-            batch_norm=True, softmax=False, use_entire_seq=False, return_outputs=False, quant=False):
+            batch_norm=True, softmax=False, use_entire_seq=False, return_outputs=False, quant=False,
+            force_argmax=None):
     """x [B,C,T,H,W] -> logits/probs [B,classes] (pt/models/CLSTM_4.py:69-85).
     quant=True: the same network with the bf16 rounding points of the tensor-core path (bf16 conv
     weights, bf16-stored clip / hidden states / pooled maps and their stored gradients; fp32 cell
-    state, gate math and accumulation) — see oracle/i3d_oracle.py."""
+    state, gate math and accumulation) — see oracle/i3d_oracle.py.
+    force_argmax: optional per-layer list of IMPOSED 2x2 max-pool routings, int tensors [T,B,hid,h/2,w/2] holding
+    the window element (row*2 + col) each pooled value is taken from (instead of its own arg-maximum): the
+    max-pools are the only non-smooth operations of this network, so two evaluations that agree on the routing
+    agree on the gradient up to rounding."""
     B = x.shape[0]
     if quant:
         x = quant_input(x)
@@ -53,7 +58,12 @@ def forward(sd, x, num_layers, hidden, kernel=5, conv_stride=2, step=None, effec
             if batch_norm:
                 cur = F.batch_norm(cur, sd["clstm.bn.running_mean"], sd["clstm.bn.running_var"],
                                    sd["clstm.bn.weight"], sd["clstm.bn.bias"], training=False, eps=1e-5)
-            cur = F.max_pool2d(cur, 2)
+            if force_argmax is not None:
+                bb, cc, hh2, ww2 = cur.shape
+                win = cur.view(bb, cc, hh2 // 2, 2, ww2 // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(bb, cc, hh2 // 2, ww2 // 2, 4)
+                cur = win.gather(-1, force_argmax[i][t].long().unsqueeze(-1)).squeeze(-1)
+            else:
+                cur = F.max_pool2d(cur, 2)
             if quant:
                 cur = _q(_RoundGrad.apply(cur))
         if t in effective_step:

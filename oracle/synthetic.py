@@ -24,3 +24,9 @@ def moving_square_clip(index, c=3, t=16, h=224, w=224):
 def clips(n, kind="uniform", **kw):
     f = uniform_clip if kind == "uniform" else moving_square_clip
     return torch.stack([f(i, **kw) for i in range(n)])
+
+
+def uniform_clip_u8(index, c=3, t=16, h=224, w=224):
+    """The same clip as decoded frames: uint8 0..255 (pt/data_loader_jpg.py:27-30 reads uint8 frames and calls
+    .float() on them); .float() of this is what the reference path sees."""
+    return uniform_clip(index, c, t, h, w).to(torch.uint8)

@@ -4,11 +4,13 @@ world-size-2 gather over gloo."""
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from interpreting_video_features_b200 import engine, ops, search
+import packing_ref
+from interpreting_video_features_b200 import ops, search
 
 
 def test_same_pad_rule():
@@ -35,7 +37,7 @@ def test_space_to_depth_stem_equals_strided_conv():
     w = torch.randn(5, 3, 7, 7, 7)
     x = torch.randn(2, 3, 8, 12, 10)
     ref = F.conv3d(F.pad(x, (2, 3, 2, 3, 2, 3)), w, stride=2)
-    w2 = engine.s2d_weight(w, 4)
+    w2 = packing_ref.s2d_weight(w, 4)
     got = F.conv3d(F.pad(_s2d(x), (1, 2, 1, 2, 1, 2)), w2, stride=1)
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
 
@@ -59,10 +61,52 @@ def test_space_to_depth_stem_data_gradient():
     y = F.conv3d(F.pad(x, (2, 3, 2, 3, 2, 3)), w, stride=2)
     gy = torch.randn_like(y)
     (gx,) = torch.autograd.grad(y, x, gy)
-    w2 = engine.s2d_weight(w, 4)
+    w2 = packing_ref.s2d_weight(w, 4)
     wd = w2.flip(2, 3, 4).permute(1, 0, 2, 3, 4)
     got = F.conv3d(F.pad(gy, (2, 1, 2, 1, 2, 1)), wd)  # pad_front' = k-1-pf = 2, back 1
     torch.testing.assert_close(got, _s2d(gx.detach()), rtol=1e-4, atol=1e-4)
+
+
+def test_pack_kernel_index_math_equals_torch_packers():
+    """csrc/pack.cu's mapping (restated in numpy, packing_ref.emulate_pack_kernel) against the torch packers that
+    the tests above prove equivalent to the reference convolutions: forward, data gradient, 3-D space-to-depth
+    (the stem), 2-D space-to-depth with padded gate stacking (ConvLSTM), two data-gradient sources, fp32 layouts."""
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn((5, 3, 3, 3, 3), generator=g)
+    for dgrad, ref in ((0, packing_ref.pack_fwd), (1, packing_ref.pack_dgrad)):
+        want = ref(w, "bf16", 16, 16).float().numpy()
+        got = packing_ref.emulate_pack_kernel(w, dgrad, 0, (1, 1, 1), 0, 16, 16, 0, 0, np.zeros((16, 27, 16), np.float32))
+        assert np.array_equal(torch.from_numpy(got).bfloat16().float().numpy(), want), dgrad
+    # fp32 tap-major: forward [taps*ci, co], transposed-gather data gradient [taps*co, ci] (taps NOT flipped)
+    got = packing_ref.emulate_pack_kernel(w, 0, 1, (1, 1, 1), 0, 5, 3, 0, 0, np.zeros((27, 3, 5), np.float32))
+    assert np.array_equal(got.reshape(-1, 5), packing_ref.pack_fwd(w, "fp32").numpy())
+    got = packing_ref.emulate_pack_kernel(w, 2, 1, (1, 1, 1), 0, 3, 5, 0, 0, np.zeros((27, 5, 3), np.float32))
+    assert np.array_equal(got.reshape(-1, 3), packing_ref.pack_dgrad(w, "fp32").numpy())
+    # the stem: 7x7x7 stride 2 -> 4x4x4 over 8*3 channels
+    ws = torch.randn((4, 3, 7, 7, 7), generator=g)
+    w2 = packing_ref.s2d_weight(ws, 4)
+    for dgrad, ref, shp in ((0, packing_ref.pack_fwd, (16, 64, 32)), (1, packing_ref.pack_dgrad, (32, 64, 16))):
+        want = ref(w2, "bf16", shp[0], shp[2]).float().numpy()
+        got = packing_ref.emulate_pack_kernel(ws, dgrad, 0, (2, 2, 2), 0, shp[0], shp[2], 0, 0, np.zeros(shp, np.float32))
+        assert np.array_equal(torch.from_numpy(got).bfloat16().float().numpy(), want), ("stem", dgrad)
+    # ConvLSTM layer 1 x-convolution: four gates of hid 4 padded to he 8, input 4 -> 8 channels, 5x5 stride 2
+    gates = [torch.randn((4, 4, 5, 5), generator=g) for _ in range(4)]
+    wx = packing_ref.pad_gates(gates, 8, 8)
+    w2 = packing_ref.s2d_weight_2d(wx[:, :, 0], 3).unsqueeze(2)  # [32, 32, 1, 3, 3]
+    for dgrad, ref in ((0, packing_ref.pack_fwd), (1, packing_ref.pack_dgrad)):
+        want = ref(w2, "bf16", 32, 32).float().numpy()
+        got = np.zeros((32, 9, 32), np.float32)
+        for gi, wg in enumerate(gates):
+            off = (0, gi * 8) if dgrad else (gi * 8, 0)
+            packing_ref.emulate_pack_kernel(wg.unsqueeze(2), dgrad, 0, (1, 2, 2), 8, 32, 32, off[0], off[1], got)
+        assert np.array_equal(torch.from_numpy(got).bfloat16().float().numpy(), want), ("gates", dgrad)
+    # two data-gradient sources (b0 | b1a,b2a): first K block padded to 64
+    w0, w12 = torch.randn((24, 16, 1, 1, 1), generator=g), torch.randn((40, 16, 1, 1, 1), generator=g)
+    want = packing_ref.pack_dgrad_two_sources(w0, w12, 16, 112).float().numpy()
+    got = np.zeros((16, 1, 112), np.float32)
+    packing_ref.emulate_pack_kernel(w0, 1, 0, (1, 1, 1), 0, 16, 112, 0, 0, got)
+    packing_ref.emulate_pack_kernel(w12, 1, 0, (1, 1, 1), 0, 16, 112, 0, 64, got)
+    assert np.array_equal(torch.from_numpy(got).bfloat16().float().numpy(), want)
 
 
 def test_shard_indices_cover_all_clips_once():

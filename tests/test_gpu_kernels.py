@@ -619,3 +619,82 @@ def test_gradcam_fused_kernel(dev, per_frame, geom):
         want, want_low = gradcam_oracle.cam_from_features(act[i].numpy(), grad[i:i + 1].numpy(), clip, size, per_frame)
         np.testing.assert_allclose(low[i].cpu().numpy(), want_low, rtol=1e-4, atol=1e-7)
         np.testing.assert_allclose(cam[i].cpu().numpy(), want, rtol=1e-3, atol=2e-5)
+
+
+# ----------------------------------------------------------------------------- model-load kernels (pack.cu)
+def test_pack_weights_kernel_equals_torch_packers(dev):
+    """ivf_pack_weights (engine.pack) against the torch packers of tests/packing_ref.py, bit for bit: forward and
+    data-gradient operands in both dtypes, the space-to-depth stem, the padded ConvLSTM gate stack, two sources."""
+    import packing_ref as pr
+    from interpreting_video_features_b200 import _lib, engine
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+
+    def pads(n, k):
+        return lib.ivf_conv_bf16_cout_pad(n), lib.ivf_conv_bf16_cin_pad(k)
+
+    for shape in [(64, 24, 3, 3, 3), (208, 96, 3, 3, 3), (16, 480, 1, 1, 1), (128, 32, 1, 5, 5)]:
+        w = torch.randn(shape, generator=g)
+        co, ci = shape[:2]
+        assert torch.equal(engine.pack_fwd(w.to(dev), "bf16").cpu(), pr.pack_fwd(w, "bf16", *pads(co, ci)))
+        assert torch.equal(engine.pack_dgrad(w.to(dev), "bf16").cpu(), pr.pack_dgrad(w, "bf16", *pads(ci, co)))
+        assert torch.equal(engine.pack_fwd(w.to(dev), "fp32").cpu(), pr.pack_fwd(w, "fp32"))
+        assert torch.equal(engine.pack_dgrad(w.to(dev), "fp32").cpu(), pr.pack_dgrad(w, "fp32"))
+    ws = torch.randn((64, 3, 7, 7, 7), generator=g)
+    w2 = pr.s2d_weight(ws, 4)
+    assert torch.equal(engine.pack([ws.to(dev)], "bf16", s2d=(2, 2, 2)).cpu(), pr.pack_fwd(w2, "bf16", *pads(64, 24)))
+    assert torch.equal(engine.pack([ws.to(dev)], "bf16", dgrad=True, s2d=(2, 2, 2)).cpu(),
+                       pr.pack_dgrad(w2, "bf16", *pads(24, 64)))
+    # ConvLSTM gates: hidden 4 padded to 8; layer 0 (3 channels, record of 16) and layer 1 (4 -> 8 channels)
+    for cin, cin_eff, total in ((3, 3, 16), (4, 8, None)):
+        gates = [torch.randn((4, cin, 5, 5), generator=g) for _ in range(4)]
+        wx = pr.s2d_weight_2d(pr.pad_gates(gates, 8, cin_eff)[:, :, 0], 3)
+        if total:
+            wx = torch.cat([wx, wx.new_zeros(32, total - wx.shape[1], 3, 3)], dim=1)
+        wx = wx.unsqueeze(2)
+        kw = dict(s2d=(1, 2, 2), ci_stride=cin_eff, ceff_total=total, co_offs=[0, 8, 16, 24], co_total=32)
+        gd = [x.to(dev) for x in gates]
+        assert torch.equal(engine.pack(gd, "bf16", **kw).cpu(), pr.pack_fwd(wx, "bf16", *pads(32, wx.shape[1])))
+        assert torch.equal(engine.pack(gd, "bf16", dgrad=True, **kw).cpu(),
+                           pr.pack_dgrad(wx, "bf16", *pads(wx.shape[1], 32)))
+        wf = pr.pad_gates(gates, 8, cin_eff)
+        kw = dict(ci_stride=cin_eff, co_offs=[0, 8, 16, 24], co_total=32)
+        assert torch.equal(engine.pack(gd, "fp32", **kw).cpu(), pr.pack_fwd(wf, "fp32"))
+        assert torch.equal(engine.pack(gd, "fp32", dgrad=True, **kw).cpu(), pr.pack_dgrad(wf, "fp32"))
+    w0, w12 = torch.randn((96, 192, 1, 1, 1), generator=g), torch.randn((112, 192, 1, 1, 1), generator=g)
+    assert torch.equal(engine.pack_dgrad_two_sources(w0.to(dev), w12.to(dev)).cpu(),
+                       pr.pack_dgrad_two_sources(w0, w12, *pads(192, 128 + 112)))
+
+
+def test_bn_fold_fill_one_hot_argmax(dev):
+    from interpreting_video_features_b200 import engine, ops
+    g = torch.Generator().manual_seed(4)
+    c = 70
+    sd = {"u.bn.weight": torch.rand(c, generator=g) + 0.5, "u.bn.bias": torch.randn(c, generator=g),
+          "u.bn.running_mean": torch.randn(c, generator=g), "u.bn.running_var": torch.rand(c, generator=g) + 0.1,
+          "u.conv3d.bias": torch.randn(c, generator=g)}
+    scale, shift = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    keep = engine.bn_fold(sd, "u", dev, 1e-3, scale, shift)
+    want_s = sd["u.bn.weight"] / torch.sqrt(sd["u.bn.running_var"] + 1e-3)
+    want_b = sd["u.bn.bias"] - sd["u.bn.running_mean"] * want_s
+    torch.testing.assert_close(scale.cpu(), want_s, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(shift.cpu(), want_b, rtol=1e-6, atol=1e-6)
+    keep = engine.bn_fold(sd, "u", dev, 1e-3, scale, shift, with_conv_bias=True)
+    torch.testing.assert_close(shift.cpu(), want_b + want_s * sd["u.conv3d.bias"], rtol=1e-6, atol=1e-6)
+    keep = engine.bn_fold({"u.conv3d.bias": sd["u.conv3d.bias"]}, "u", dev, 1e-3, scale, shift, with_conv_bias=True)
+    assert torch.equal(scale.cpu(), torch.ones(c)) and torch.equal(shift.cpu(), sd["u.conv3d.bias"])
+    del keep
+    z = ops.zeros((3, 5, 7), torch.float32, dev)
+    assert torch.equal(z.cpu(), torch.zeros(3, 5, 7))
+    zb = ops.zeros((1, 2, 3, 4, 8), torch.bfloat16, dev)
+    assert float(zb.float().abs().sum()) == 0.0
+    tg = torch.tensor([3, 0, 173])
+    oh = torch.empty((3, 174), device=dev)
+    ops.one_hot(ops.as_int32_targets(tg, dev), oh)
+    assert torch.equal(oh.cpu(), F.one_hot(tg, 174).float())
+    x = torch.randn((5, 174), generator=g)
+    x[1, 7] = x[1, 90] = 9.0            # tie: first maximum
+    x[2, 40] = float("nan")             # NaN wins, like np.argmax
+    am = torch.empty(5, dtype=torch.int32, device=dev)
+    ops.argmax_rows(x.to(dev), am)
+    assert am.cpu().tolist() == np.argmax(x.numpy(), axis=1).tolist()

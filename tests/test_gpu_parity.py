@@ -1,0 +1,473 @@
+"""GPU (-m gpu): the parity cases round 1 left open (VERDICT r01 "Next round" item 1).
+
+  (a) config C1 - I3D-KTH (6 classes, finalTimeLength 4) at its native 32x120x160 geometry with odd maps and
+      asymmetric 'same' pads at every strided pool: probabilities and Grad-CAM vs the reference's golden vectors
+      and the oracle, B = 1 and B = 8;
+  (b) bf16 end-to-end class gradient on structured (moving-square) clips where the class term matters, and a
+      50-iteration bf16 trajectory with final-mask IoU;
+  (c) ConvLSTM (hidden 32) on structured clips at 0..255 and 0..1;
+  (d) the C2 geometry at B = 8 with the shipped tile plans;
+  (e) non-empty stride_mod_layers;
+  plus the drop-in snap_values path and init_mask 'random'.
+
+How a bf16 gradient is judged.  The network is piecewise linear in its input: the ReLUs and max-pools make
+DECISIONS (which units are active, which window element is the maximum) and, given the decisions, the backward
+pass is a fixed linear map.  bf16 rounding of the stored activations (relative 2^-9) flips the decisions of units
+that sit within that distance of a tie; every flip re-routes gradient.  Measured with the CPU oracle alone (no
+kernel involved, tools-free: oracle quant=True vs fp64): on a default-initialised I3D the features agree to 0.7 %
+up to Mixed_5c while the input-gradient FIELD differs by 38 % in L2 norm and d p/d mask by 10-35 % (cosine
+0.94-0.999) - a property of bf16 storage on a deep ReLU/max-pool net, not of an implementation.  The tests
+therefore split the claim:
+  1. decisions imposed: the oracle re-evaluates the network in fp32 with the engine's OWN decisions (read back
+     from the engine's activations and arg-max buffers) and bf16 rounding points; the engine's end-to-end
+     gradient must match to 2e-2 in relative L2 norm and 0.9995 in cosine (measured values in the asserts);
+  2. free running: against the fp64 oracle the engine's error may not exceed 1.5x the matched-rounding
+     oracle's own error + 0.05 (self-calibrated, like the fp32 test of round 1), cosine within 0.05 of it;
+  3. what the search needs: 50 bf16 iterations from several initial masks end at the fp32 reference's final
+     mask (frame-wise IoU >= 0.95) on a model whose class gradient is 100x the regulariser's.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import GOLD, i3d_state_dict, quiet, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(clip=(16, 64, 64), avg_pool=(2, 2, 2))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from interpreting_video_features_b200 import _lib
+    _lib.handle()
+    return torch.device("cuda")
+
+
+def cosine(a, b):
+    return float(F.cosine_similarity(torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten(), dim=0))
+
+
+def iou(a, b):
+    a, b = a > 0.5, b > 0.5
+    union = float((a | b).sum())
+    return 1.0 if union == 0 else float((a & b).sum()) / union
+
+
+def make_engine(sd, batch, mode, dev, clip, avg_pool, softmax=True, stride_mods=None):
+    from interpreting_video_features_b200.engine import I3DEngine
+    return I3DEngine(sd, batch, clip, mode=mode, softmax=softmax, avg_pool=avg_pool, device=dev,
+                     stride_mods=stride_mods)
+
+
+def engine_decisions(eng, clip=None):
+    """The decisions the engine's forward made, in the oracle's `force` format: ReLU masks from the stored
+    activations (the engine's backward derives ReLU' from exactly these), pool routings from its arg-max buffers."""
+    force = {}
+    sel = (lambda t: t) if clip is None else (lambda t: t[clip:clip + 1])
+
+    def idx_of(am, out):
+        return sel(am.view(out.n, out.d, out.h, out.w, -1).permute(0, 4, 1, 2, 3).cpu().long())
+
+    for st in eng.stages:
+        name = st["name"]
+        if st["kind"] == "unit":
+            force[name] = sel(st["out"].ncdhw().cpu() > 0)
+        elif st["kind"] == "pool":
+            force[name] = idx_of(st["argmax"], st["out"])
+        else:
+            u = st["units"]
+            out = st["out"].ncdhw().cpu()
+            off = 0
+            for b in ("b0", "b1b", "b2b", "b3b"):
+                force["%s.%s" % (name, b)] = sel(out[:, off:off + u[b].cout] > 0)
+                off += u[b].cout
+            force[name + ".b1a"] = sel(st["t1"].ncdhw().cpu() > 0)
+            force[name + ".b2a"] = sel(st["t2"].ncdhw().cpu() > 0)
+            force[name + ".b3a"] = idx_of(st["argmax"], st["t3"])
+    return force
+
+
+def oracle_grad(sd, x1, mask, perturb, avg_pool, target, quant=False, double=False, force=None, stride_mods=None):
+    from oracle import i3d_oracle, mask_oracle
+    if double:
+        sd = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        x1, mask = x1.double(), mask.double()
+    mi = mask.clone().requires_grad_()
+    out = i3d_oracle.forward(sd, mask_oracle.perturb_sequence(x1, mi, perturb), avg_pool, quant=quant, force=force,
+                             stride_mods=stride_mods)
+    p = out[0, target]
+    (gm,) = torch.autograd.grad(p, mi)
+    return float(p.detach()), gm
+
+
+# ------------------------------------------------------------------------------------------------ (a) config C1
+@pytest.fixture(scope="module")
+def kth_setup():
+    from oracle import synthetic
+    sd, _ = quiet(i3d_state_dict, 6, kth=True)
+    return sd, synthetic.clips(8, t=32, h=120, w=160)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("batch", [1, 8])
+def test_c1_kth_probs_and_gradcam(dev, kth_setup, mode, batch):
+    """pt/models/I3D_doubled_kth.py:302-307 (avg_pool [ftl,4,5], maps 16x60x80 -> 30x40 -> 15x20 -> 8x10 -> 4x5)
+    and pt/grad_cam_videos.py:112-140 at input_spatial_size (160,120): fp32 1e-4 / bf16 1e-2 on the probabilities
+    and on the un-normalised class-activation map; the per-slice normalised map within 1e-3 / 5e-2 absolute (the
+    normalisation divides by the slice's range and amplifies the error of nearly flat slices)."""
+    from interpreting_video_features_b200 import ops
+    from interpreting_video_features_b200.pt.grad_cam_videos import GradCamVideo
+    from interpreting_video_features_b200.pt.models import I3D_doubled_kth
+    from oracle import gradcam_oracle, i3d_oracle
+    g = np.load(os.path.join(GOLD, "i3d_kth.npz"))
+    sd, x8 = kth_setup
+    x = x8[:batch]
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    eng = make_engine(sd, batch, mode, dev, clip=(32, 120, 160), avg_pool=(4, 4, 5))
+    assert [(eng.acts[n].d, eng.acts[n].h, eng.acts[n].w) for n in ("Conv3d_1a_7x7", "MaxPool3d_3a_3x3",
+            "MaxPool3d_4a_3x3", "Mixed_5c")] == [(16, 60, 80), (16, 15, 20), (8, 8, 10), (4, 4, 5)]
+    eng.set_input(x.to(dev))
+    probs = eng.forward(None).clone().cpu()
+    assert rel_err(probs[0], g["probs"][0]) < tol, ("golden", rel_err(probs[0], g["probs"][0]))
+    with torch.no_grad():
+        feat, outs = i3d_oracle.features(sd, x)
+        want_p = i3d_oracle.head(sd, feat, (4, 4, 5), True)
+    for name in ("Conv3d_1a_7x7", "MaxPool3d_2a_3x3", "Conv3d_2c_3x3", "MaxPool3d_3a_3x3", "Mixed_3c",
+                 "MaxPool3d_4a_3x3", "Mixed_4f", "MaxPool3d_5a_2x2", "Mixed_5c"):
+        e = rel_err(eng.acts[name].ncdhw().cpu(), outs[name])
+        assert e < tol, (name, e)
+    assert rel_err(probs, want_p) < tol, rel_err(probs, want_p)
+    # Grad-CAM through the drop-in class (argmax class, as the golden run) and the raw low-resolution map
+    model = quiet(I3D_doubled_kth.Model, 6, last_stride=1, stride_mod_layers="", softMax=1, finalTimeLength=4)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval().set_mode(mode)
+    gc = GradCamVideo(model=model, target_layer_names=['Mixed_5c'], class_dict=None, use_cuda=True,
+                      input_spatial_size=(160, 120), normalizePerFrame=True, archType="I3D")
+    cams, out = gc.batched(x.to(dev), None)
+    assert cams.shape == (batch, 32, 120, 160) and cams.dtype == np.float32
+    assert rel_err(out.cpu(), want_p) < tol
+    for i in range(batch):
+        want, _, low = gradcam_oracle.gradcam_i3d(sd, x[i:i + 1], None, (160, 120), True, avg_pool=(4, 4, 5))
+        ok = ~np.isnan(want)
+        assert np.array_equal(np.isnan(cams[i]), np.isnan(want)), i
+        assert np.abs(cams[i][ok] - want[ok]).max() < (1e-3 if mode == "fp32" else 5e-2), i
+        if i == 0:
+            assert rel_err(low, g["cam_lowres"]) < 1e-4  # the oracle reproduces the golden low-res map
+            samp = cams[0][::8, ::12, ::16]
+            gk = ~np.isnan(g["cam_sample"])
+            assert np.abs(samp[gk] - g["cam_sample"][gk]).max() < (1e-3 if mode == "fp32" else 5e-2)
+    # the un-normalised map of clip 0 from the same fused kernel (cam_lowres output)
+    eng2 = model._engine(x.to(dev))
+    eng2.set_input(x.to(dev))
+    p2 = eng2.forward(None)
+    eng2.set_targets(torch.argmax(p2, dim=1))
+    grad = eng2.head_grad_raw()
+    act = eng2.acts["Mixed_5c"]
+    cam = torch.empty((batch, 32, 120, 160), dtype=torch.float32, device=dev)
+    low_dev = torch.empty((batch, act.d, act.h, act.w), dtype=torch.float32, device=dev)
+    ops.gradcam(act, grad, 32 // act.d, 120, 160, True, cam, cam_lowres=low_dev)
+    assert rel_err(low_dev[0].cpu(), g["cam_lowres"]) < tol, rel_err(low_dev[0].cpu(), g["cam_lowres"])
+
+
+# ------------------------------------------------------------------------------------------------ (b) bf16 end to end
+@pytest.fixture(scope="module")
+def structured_setup():
+    """Moving-square clips; two models where the class term matters: the BN-calibrated 'sharpened' net of
+    round 1 (chaotic: every perturbation is amplified) and the default-initialised trunk with a sharpened head
+    (well conditioned: bf16 features within 1e-2 of fp32)."""
+    from oracle import i3d_oracle, mask_oracle, synthetic
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = synthetic.clips(3, kind="square", t=16, h=64, w=64)
+    raw0 = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4)
+    xp = torch.cat([mask_oracle.perturb_sequence(x[i:i + 1], torch.sigmoid(raw0), "freeze") for i in range(3)])
+    sd_head = i3d_oracle.sharpen_head_only(sd, torch.cat([x, xp]), SMALL["avg_pool"])
+    sd_cal = i3d_oracle.calibrate_and_sharpen(sd, torch.cat([x, xp]), SMALL["avg_pool"])
+    return x, sd_head, sd_cal
+
+
+@pytest.mark.parametrize("which", ["head_sharpened", "bn_calibrated"])
+@pytest.mark.parametrize("perturb", ["freeze", "reverse"])
+def test_bf16_class_gradient_end_to_end(dev, structured_setup, which, perturb):
+    from oracle import i3d_oracle, mask_oracle
+    x, sd_head, sd_cal = structured_setup
+    sds = sd_head if which == "head_sharpened" else sd_cal
+    g = torch.Generator().manual_seed(21)
+    masks = torch.rand((3, 16), generator=g) * 0.8 + 0.1
+    with torch.no_grad():
+        targets = torch.stack([i3d_oracle.forward(sds, mask_oracle.perturb_sequence(x[i:i + 1], masks[i], perturb),
+                                                  SMALL["avg_pool"]).argmax(dim=1)[0] for i in range(3)])
+    eng = make_engine(sds, 3, "bf16", dev, **SMALL)
+    eng.set_input(x.to(dev))
+    eng.set_targets(targets)
+    probs = eng.forward(masks.to(dev), perturb).clone().cpu()
+    dm = eng.backward().clone().cpu()
+    report = []
+    for i in range(3):
+        tgt = int(targets[i])
+        # 1. decisions imposed (the engine's own ReLU / arg-max pattern), matched bf16 rounding points, fp32
+        force = engine_decisions(eng, clip=i)
+        p_f, g_f = oracle_grad(sds, x[i:i + 1], masks[i], perturb, SMALL["avg_pool"], tgt, quant=True, force=force)
+        # 2. free running: fp64 truth, and the matched-rounding oracle's own distance from it
+        p64, g64 = oracle_grad(sds, x[i:i + 1], masks[i], perturb, SMALL["avg_pool"], tgt, double=True)
+        p_q, g_q = oracle_grad(sds, x[i:i + 1], masks[i], perturb, SMALL["avg_pool"], tgt, quant=True)
+        assert float(g64.abs().max()) > 1e-3, "degenerate class gradient"
+        e_forced, c_forced = rel_err(dm[i], g_f), cosine(dm[i], g_f)
+        e_free, c_free = rel_err(dm[i], g64), cosine(dm[i], g64)
+        e_q, c_q = rel_err(g_q, g64), cosine(g_q, g64)
+        report.append((i, e_forced, c_forced, e_free, c_free, e_q, c_q, float(probs[i, tgt]), p_f, p64, p_q))
+    print("\n[%s/%s] clip: forced rel/cos | free-running vs fp64 rel/cos | matched oracle vs fp64 rel/cos | p ours/forced/fp64/q"
+          % (which, perturb))
+    for r in report:
+        print("  %d: %.3e %.6f | %.3e %.5f | %.3e %.5f | %.4f %.4f %.4f %.4f" % r)
+    for i, e_forced, c_forced, e_free, c_free, e_q, c_q, p_ours, p_f, p64, p_q in report:
+        assert e_forced < 2e-2 and c_forced > 0.9995, ("decisions imposed", which, perturb, i, e_forced, c_forced)
+        assert abs(p_ours - p_f) <= 1e-2 * abs(p_f) + 1e-4, ("probability, decisions imposed", i, p_ours, p_f)
+        assert e_free <= 1.5 * e_q + 0.05, ("free running", which, perturb, i, e_free, e_q)
+        assert c_free >= c_q - 0.05, ("free running cosine", which, perturb, i, c_free, c_q)
+
+
+def test_bf16_trajectory_50_iterations_iou(dev, structured_setup):
+    """North star: 'mask-gradient trajectories ... for the first 50 iterations, final temporal mask matching by
+    frame-wise IoU >= 0.95' - bf16 path vs the fp32 reference loop (pt/FindMasksComparison_I3D_smth.py:193-216) on
+    the head-sharpened model, where |d p/d mask| ~ 1-7 is two orders above the regulariser's gradient (0.01-0.02)
+    so the conv backward decides where the mask goes; three different initial masks (the reference's central
+    window, on for the first 13 frames, and a +-2.5 random pattern as init_mask 'random' produces).  The class-gradient trajectory is
+    checked at the reference's own masks of iterations 0/1/2/5/10/20/35/49 with the decisions-imposed bound."""
+    from interpreting_video_features_b200.search import MaskSearch
+    from oracle import i3d_oracle, mask_oracle
+    x, sd_head, _ = structured_setup
+    inits = torch.stack([torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4), torch.tensor([5.] * 13 + [-5.] * 3),
+                         torch.tensor([2.5, -2.5, -2.5, 2.5, 2.5, -2.5, 2.5, -2.5, -2.5, -2.5, 2.5, 2.5, -2.5, 2.5, -2.5,
+                                       -2.5])])
+    with torch.no_grad():
+        targets = i3d_oracle.forward(sd_head, x, SMALL["avg_pool"]).argmax(dim=1)
+    eng = make_engine(sd_head, 3, "bf16", dev, **SMALL)
+    rec = {}
+    res = MaskSearch(eng, lam1=0.01, lam2=0.02, n_iter=50, perturb="freeze", use_graph=True).run(
+        x.to(dev), targets, raw_masks=inits.to(dev), record=rec)
+    model = i3d_oracle.Model(sd_head, SMALL["avg_pool"], True)
+    moved = 0
+    recs = []
+    for i in range(3):
+        tm = inits[i].clone().requires_grad_()
+        r = {}
+        final, _ = mask_oracle.mask_search(x[i:i + 1], model, 0, [int(targets[i])], tm, 0.01, 0.02, 50, record=r)
+        recs.append(r)
+        got = res["time_mask"][i].cpu()
+        print("clip %d: ours %s  reference %s" % (i, (got > 0.5).int().tolist(), (final > 0.5).int().tolist()))
+        assert iou(got, final) >= 0.95, (i, got, final)
+        moved += int(((final > 0.5) != (torch.sigmoid(inits[i]) > 0.5)).any())
+        # the class term drives the search: its gradient dwarfs the regulariser's at the start
+        assert float(rec["dm_class"][0][i].abs().max()) > 0.1
+    assert moved >= 1, "no trajectory left its initial mask: the test would not notice a wrong class gradient"
+    for it in (0, 1, 2, 5, 10, 20, 35, 49):
+        raw_it = torch.stack([(recs[i]["mask"][it - 1] if it > 0 else inits[i]) for i in range(3)])
+        sig = torch.sigmoid(raw_it)
+        eng.set_targets(targets)
+        eng.forward(sig.to(dev), "freeze")
+        dm = eng.backward().clone().cpu()
+        for i in range(3):
+            force = engine_decisions(eng, clip=i)
+            _, g_f = oracle_grad(sd_head, x[i:i + 1], sig[i], "freeze", SMALL["avg_pool"], int(targets[i]), quant=True,
+                                 force=force)
+            if float(g_f.abs().max()) < 1e-6:
+                continue
+            assert rel_err(dm[i], g_f) < 2e-2 and cosine(dm[i], g_f) > 0.9995, (it, i, rel_err(dm[i], g_f))
+
+
+# ------------------------------------------------------------------------------------------------ (c) ConvLSTM
+KW = dict(num_layers=2, kernel=5, conv_stride=2, effective_step=(7, 15, 23, 31))
+
+
+def clstm_decisions(eng, hidden, clip):
+    """Per layer [T,1,hid,h/2,w/2] window indices of the engine's BN+max-pool launches for one clip."""
+    out = []
+    for rec in eng.layers:
+        am = rec["argmax"].view(eng.T, eng.B, rec["ho"] // 2, rec["wo"] // 2, eng.he)[:, clip:clip + 1, :, :, :hidden]
+        out.append(am.permute(0, 1, 4, 2, 3).cpu().long())
+    return out
+
+
+@pytest.mark.parametrize("scale", [1.0, 1.0 / 255.0])
+def test_clstm_hid32_bf16_structured(dev, scale):
+    """Config C3's model (hidden 32) on moving-square clips, both input ranges (the loaders deliver 0..255,
+    pt/data_loader_kth.py:28; round 1 fed 0..1): logits 1e-2; d logit/d mask with the 2x2 max-pool routing
+    imposed (the only non-smooth operation of a ConvLSTM) 2e-2 / cosine 0.9995 against the matched-rounding
+    oracle, and free running within 1.5x the matched oracle's own distance from fp64 + 0.05."""
+    from test_gpu_clstm import build, engine
+    from oracle import clstm_oracle, mask_oracle, synthetic
+    _, sd = build(32)
+    x = synthetic.clips(2, kind="square", t=32, h=120, w=160) * scale
+    masks = torch.rand((2, 32), generator=torch.Generator().manual_seed(9))
+    eng = engine(sd, 32, 2, "bf16", dev)
+    eng.set_input(x.to(dev))
+    tg = (2, 4)
+    eng.set_targets(torch.tensor(tg))
+    logits = eng.forward(masks.to(dev), "reverse").clone().cpu()
+    dm = eng.backward().clone().cpu()
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    print("\n[clstm hid32 scale %.4f] clip: forced rel/cos | free vs fp64 rel/cos | matched oracle vs fp64 rel/cos" % scale)
+    for i in range(2):
+        def run(sd_, xx, mm, quant, force):
+            mi = mm.clone().requires_grad_()
+            out = clstm_oracle.forward(sd_, mask_oracle.perturb_sequence(xx, mi, "reverse"), hidden=32, quant=quant,
+                                       force_argmax=force, **KW)
+            (gm,) = torch.autograd.grad(out[0, tg[i]], mi)
+            return out.detach()[0], gm
+        o_f, g_f = run(sd, x[i:i + 1], masks[i], True, clstm_decisions(eng, 32, i))
+        o_q, g_q = run(sd, x[i:i + 1], masks[i], True, None)
+        o64, g64 = run(sd64, x[i:i + 1].double(), masks[i].double(), False, None)
+        e_f, c_f = rel_err(dm[i], g_f), cosine(dm[i], g_f)
+        e_free, c_free, e_q, c_q = rel_err(dm[i], g64), cosine(dm[i], g64), rel_err(g_q, g64), cosine(g_q, g64)
+        print("  %d: %.3e %.6f | %.3e %.5f | %.3e %.5f" % (i, e_f, c_f, e_free, c_free, e_q, c_q))
+        assert rel_err(logits[i], o64.float()) < 1e-2, (i, rel_err(logits[i], o64.float()))
+        assert rel_err(logits[i], o_f) < 1e-2
+        assert e_f < 2e-2 and c_f > 0.9995, ("routing imposed", i, e_f, c_f)
+        assert e_free <= 1.5 * e_q + 0.05 and c_free >= c_q - 0.05, ("free running", i, e_free, e_q, c_free, c_q)
+
+
+# ------------------------------------------------------------------------------------------------ (d) C2 at B = 8
+def test_c2_geometry_batch8_shipped_plans(dev):
+    """The benched configuration itself: 8 clips of 16x224x224 through the bf16 path with the tile plans of
+    plans_sm100.json (keyed on n = 8, never exercised under an assertion in round 1).  Probabilities of all 8
+    clips vs the fp32 oracle (rows 0-1 are the reference's golden vectors) at 1e-2; the end-to-end class gradient
+    of two clips with the engine's decisions imposed at 2e-2."""
+    from interpreting_video_features_b200 import tune
+    from oracle import i3d_oracle, mask_oracle, synthetic
+    g = np.load(os.path.join(GOLD, "i3d_smth.npz"))
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = synthetic.clips(8)
+    eng = make_engine(sd, 8, "bf16", dev, clip=(16, 224, 224), avg_pool=(2, 7, 7))
+    planned = [it[1] for it in eng.fwd_ops + eng.bwd_ops if isinstance(it[0], int) and getattr(it[1], "plan", None)]
+    if tune.enabled():
+        assert len(planned) >= 4, "the shipped plan table was not applied to the B = 8 launches"
+    eng.set_input(x.to(dev))
+    probs = eng.forward(None).clone().cpu()
+    assert rel_err(probs[:2], g["probs_default"]) < 1e-2
+    with torch.no_grad():
+        want = torch.cat([i3d_oracle.forward(sd, x[i:i + 1]) for i in range(8)])
+    assert rel_err(probs, want) < 1e-2, rel_err(probs, want)
+    for i in range(8):
+        assert rel_err(probs[i], want[i]) < 1e-2, (i, rel_err(probs[i], want[i]))
+    raw = torch.tensor([-5.] * 4 + [5.] * 8 + [-5.] * 4)
+    sig = torch.sigmoid(raw).repeat(8, 1)
+    sig[5] = torch.rand(16, generator=torch.Generator().manual_seed(2))
+    targets = torch.tensor([3, 40, 100, 7, 150, 99, 0, 173])
+    eng.set_targets(targets)
+    p = eng.forward(sig.to(dev), "freeze").clone().cpu()
+    dm = eng.backward().clone().cpu()
+    for i in (0, 5):
+        force = engine_decisions(eng, clip=i)
+        p_f, g_f = oracle_grad(sd, x[i:i + 1], sig[i], "freeze", (2, 7, 7), int(targets[i]), quant=True, force=force)
+        assert abs(float(p[i, targets[i]]) - p_f) <= 1e-2 * abs(p_f)
+        e, c = rel_err(dm[i], g_f), cosine(dm[i], g_f)
+        print("C2 B=8 clip %d: decisions imposed rel %.3e cos %.6f" % (i, e, c))
+        assert e < 2e-2 and c > 0.9995, (i, e, c)
+
+
+# ------------------------------------------------------------------------------------------------ (e) stride mods
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mods", ["MaxPool3d_4a_3x3", "MaxPool3d_4a_3x3,MaxPool3d_5a_2x2", "Conv3d_1a_7x7"])
+def test_stride_mod_layers(dev, mode, mods):
+    """The 'doubled' temporal-resolution models the files are named after (pt/models/I3D_doubled.py:222-226,
+    260-264,292-296,313-319): listed layers take temporal stride last_stride (= 1) and the average pool grows by
+    2/last_stride per layer.  Through the drop-in constructor, vs the oracle with the same stride table; a modified
+    stem stride has no bf16 kernel (the stem is presented space-to-depth by 2 in t) and must be refused."""
+    from interpreting_video_features_b200 import _lib
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    from oracle import i3d_oracle, mask_oracle, synthetic
+    torch.manual_seed(0)
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers=mods, softMax=1).eval()
+    n_mod = len(mods.split(","))
+    assert list(model.avg_pool.kernel_size) == [2 * 2 ** n_mod, 7, 7]
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    smods = {m: (1, 2, 2) for m in mods.split(",")}
+    assert model._stride_mods == smods
+    t, h, w = 16, 64, 64
+    tt = t // 2 if "Conv3d_1a_7x7" not in smods else t
+    for m in ("MaxPool3d_4a_3x3", "MaxPool3d_5a_2x2"):
+        tt = tt if m in smods else (tt + 1) // 2
+    ap = (tt, 2, 2)
+    x = synthetic.clips(2, kind="square", t=t, h=h, w=w)
+    model.avg_pool.kernel_size = list(ap)  # 64x64 clips: the reference's [.,7,7] pool is sized for 224x224
+    model = model.to(dev).set_mode(mode)
+    if mode == "bf16" and "Conv3d_1a_7x7" in smods:
+        with pytest.raises(_lib.IvfError):
+            model(x.to(dev))
+        return
+    sds = i3d_oracle.sharpen_head_only(sd, x, ap, stride_mods=smods) if "Conv3d_1a_7x7" not in smods else sd
+    model.load_state_dict(sds)
+    eng = model._engine(x.to(dev))
+    assert (eng.acts["Mixed_5c"].d, eng.acts["Mixed_5c"].h, eng.acts["Mixed_5c"].w) == ap
+    with torch.no_grad():
+        got = model(x.to(dev)).cpu()
+        want = i3d_oracle.forward(sds, x, ap, stride_mods=smods)
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    assert rel_err(got, want) < tol, rel_err(got, want)
+    masks = torch.rand((2, t), generator=torch.Generator().manual_seed(4))
+    targets = want.argmax(dim=1)
+    eng.set_input(x.to(dev))
+    eng.set_targets(targets)
+    eng.forward(masks.to(dev), "freeze")
+    dm = eng.backward().clone().cpu()
+    for i in range(2):
+        if mode == "fp32":
+            _, g64 = oracle_grad(sds, x[i:i + 1], masks[i], "freeze", ap, int(targets[i]), double=True, stride_mods=smods)
+            _, g32 = oracle_grad(sds, x[i:i + 1], masks[i], "freeze", ap, int(targets[i]), stride_mods=smods)
+            assert rel_err(dm[i], g64) <= 3 * rel_err(g32, g64) + 1e-3, (i, rel_err(dm[i], g64), rel_err(g32, g64))
+        else:
+            force = engine_decisions(eng, clip=i)
+            _, g_f = oracle_grad(sds, x[i:i + 1], masks[i], "freeze", ap, int(targets[i]), quant=True, force=force,
+                                 stride_mods=smods)
+            assert rel_err(dm[i], g_f) < 2e-2 and cosine(dm[i], g_f) > 0.9995, (i, rel_err(dm[i], g_f))
+
+
+# ------------------------------------------------------------------------------------------------ a3 / a6
+def test_snap_values_dropin_on_gpu(dev):
+    """perturb_sequence(snap_values=True) through the drop-in module (pt/mask.py:5-10): the caller's mask is
+    binarised in place at 0.5 and the perturbation uses the snapped values - vs the reference's golden output."""
+    from interpreting_video_features_b200.pt import mask
+    g = np.load(os.path.join(GOLD, "mask_kats.npz"))
+    xr = torch.tensor([0., 10, 20, 30, 40, 50]).reshape(1, 1, 6, 1, 1).to(dev)
+    ms = torch.tensor([0, .5, 1, .2, .05, .8], device=dev)
+    out = mask.perturb_sequence(xr, ms, 'freeze', snap_values=True)
+    assert ms.cpu().tolist() == [0.0, 0.0, 1.0, 0.0, 0.0, 1.0]
+    assert np.array_equal(out.cpu().numpy(), g["snap_out"])
+    for mode in ("freeze", "reverse"):
+        x = torch.from_numpy(g["rand_x"]).to(dev)
+        m = torch.from_numpy(g["rand_%s_mask" % mode]).to(dev)
+        snapped = (m > 0.5).float()
+        want = mask.perturb_sequence(x, snapped.clone(), mode)
+        got = mask.perturb_sequence(x, m, mode, snap_values=True)
+        assert torch.equal(got, want) and torch.equal(m, snapped)
+
+
+def test_init_mask_random_mode(dev):
+    """pt/mask.py:155-165: U > 0.7 -> +2.5 else -2.5, and the all-equal guard mask[8] += 0.1.  The batched
+    searcher draws from a seeded host generator (same formula as the oracle); the drop-in draws on the device."""
+    from interpreting_video_features_b200.pt import mask
+    from interpreting_video_features_b200.search import MaskSearch
+    from oracle import mask_oracle
+    sd, _ = quiet(i3d_state_dict, 174)
+    eng = make_engine(sd, 2, "bf16", dev, **SMALL)
+    x = torch.rand((2, 3, 16, 64, 64), generator=torch.Generator().manual_seed(0)) * 255
+    eng.set_input(x.to(dev))
+    gen = torch.Generator().manual_seed(123)
+    raw, _ = MaskSearch(eng).init_masks(torch.tensor([3, 4]), mode="random", generator=gen)
+    gen2 = torch.Generator().manual_seed(123)
+    u = torch.rand((2, 16), generator=gen2)
+    want = ((u > 0.7).float() - 0.5) * 5
+    assert torch.equal(raw.cpu(), want)
+    one = mask_oracle.init_mask(x[:1], None, 0, [3], mode="random", generator=torch.Generator().manual_seed(5))
+    assert set(one.detach().abs().tolist()) <= {2.5, 2.6}
+    tm = mask.init_mask(x[:1].to(dev), None, 0, [3], mode='random')
+    assert tm.requires_grad and tm.is_cuda and tm.shape == (16,)
+    vals = set(round(v, 4) for v in tm.detach().cpu().tolist())
+    assert vals <= {2.5, -2.5, 2.6, -2.4}
+    res = MaskSearch(eng, n_iter=3, use_graph=False).run(x.to(dev), torch.tensor([3, 4]), init="random")
+    assert torch.isfinite(res["time_mask"]).all()
