@@ -43,7 +43,7 @@ enum {
   IVF_EWORKSPACE = 5    /* caller-owned workspace missing or too small       */
 };
 
-enum { IVF_F32 = 0, IVF_BF16 = 1 };
+enum { IVF_F32 = 0, IVF_BF16 = 1, IVF_U8 = 2 /* uint8 frames: clip ingest / visualisation only */ };
 
 /* epilogue flags shared by conv / pool-backward / head-backward */
 enum {
@@ -325,6 +325,15 @@ int ivf_bn_pool2d_fwd(ivf_handle* h, int dtype, const void* x, int n, int hh, in
 int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* argmax, int n, int hh,
                       int ww, int c, const float* scale, const float* acc_in, float* dx, int s2d,
                       void* stream);
+
+/* ---- visualisation (pt/visualisation.py:96-130 create_image_arrays, :35-93 mask dots) ---------------------
+ * One clip: clip [3][t][hh][ww] RGB 0..255 (fp32 or uint8), cam fp32 [t][hh][ww] in [0,1] (NaN allowed: an
+ * all-zero Grad-CAM slice), pert fp32 [3][t][hh][ww] (the clip under the snapped mask).  out: uint8
+ * [t][hh][3*ww][3] BGR - per frame [ frame | uint8(255*(JET(uint8(255*cam)) + frame)/max) | perturbed frame ],
+ * bit-exact with the host pipeline of the reference.  draw_dots != 0 also draws the temporal-mask dots under
+ * the third panel (mask fp32 [t], rounded at 0.5 as roundUpMask=True does).  Encoding stays on the host. */
+int ivf_viz_triptych(ivf_handle* h, int clip_dtype, const void* clip, const float* cam, const float* pert,
+                     const float* mask, int t, int hh, int ww, int draw_dots, uint8_t* out, void* stream);
 
 /* ---- bring-up probes (tests only) ---------------------------------------------------
  * Loads one 128-pixel x kchunk im2col TMA tile exactly as the conv kernel does and

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libivf.so")
 
-IVF_F32, IVF_BF16 = 0, 1
+IVF_F32, IVF_BF16, IVF_U8 = 0, 1, 2
 EP_AFFINE, EP_RELU, EP_ACCUM, EP_MASK, EP_OUT_F32 = 1, 2, 4, 8, 16
 PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, PFMT_TBHWC_F32, PFMT_S2D2_BF16 = 0, 1, 2, 3, 4
 PACK_KMAJOR, PACK_TAPMAJOR = 0, 1
@@ -90,6 +90,7 @@ SIGNATURES = {
     "ivf_clstm_gates_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ivf_bn_pool2d_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "ivf_bn_pool2d_bwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "ivf_viz_triptych": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ivf_probe_im2col": (_I, [_P, C.POINTER(ConvDesc), _P, _I, _I, _I, _P, _P]),
 }
 

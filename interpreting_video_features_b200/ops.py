@@ -326,6 +326,18 @@ def gradcam(act, grad, step, hout, wout, per_frame, cam, cam_lowres=None):
     return cam
 
 
+def viz_triptych(clip, cam, pert, mask, out, draw_dots=True):
+    """clip [3,T,H,W] fp32/uint8, cam fp32 [T,H,W], pert fp32 [3,T,H,W], mask fp32 [T] -> out uint8 [T,H,3W,3] (BGR)."""
+    c, t, hh, ww = clip.shape
+    assert c == 3 and tuple(cam.shape) == (t, hh, ww) and tuple(pert.shape) == (3, t, hh, ww)
+    assert tuple(out.shape) == (t, hh, 3 * ww, 3) and out.dtype == torch.uint8
+    code = _lib.IVF_U8 if clip.dtype == torch.uint8 else IVF_F32
+    check(_lib.load().ivf_viz_triptych(_lib.handle(out.device), code, ptr(clip), ptr(cam), ptr(pert), ptr(mask), t, hh,
+                                       ww, int(bool(draw_dots)), ptr(out), _lib.stream_ptr(out.device)),
+          "ivf_viz_triptych")
+    return out
+
+
 def clstm_gates_fwd(pre, c_prev, c_next, h_next, gate_act):
     m, four_hid = pre.shape
     check(_lib.load().ivf_clstm_gates_fwd(_lib.handle(pre.device), _lib.dtype_code(h_next), ptr(pre),

@@ -247,7 +247,7 @@ def default_groups(micro_batch):
 
 def make_engines(model, x, micro_batch, groups):
     """`groups` runners of micro_batch/groups clips each (one runner when groups == 1)."""
-    if groups <= 1:
+    if groups <= 1 or not hasattr(model, "MAX_ENGINE_GEOMETRIES"):  # the ConvLSTM model keeps one engine
         return [model._engine(x, batch=micro_batch)]
     per = micro_batch // groups
     return [model._engine(x, batch=per, tag=g) for g in range(groups)]
@@ -343,7 +343,7 @@ def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, 
             cols.append(searcher.gradcam_lowres(tg).flatten(1))
         rows.append(torch.cat(cols, dim=1)[:n_valid])
         n_mb += 1
-    ncls = model._num_classes
+    ncls = getattr(model, "_num_classes", None) or model.num_classes  # I3D / CLSTM_4 attribute names
     if rows:
         local = torch.cat(rows)
     else:  # a rank without clips still takes part in the gather: it needs the row width

@@ -60,7 +60,8 @@ def forward(sd, x, num_layers, hidden, kernel=5, conv_stride=2, step=None, effec
                                    sd["clstm.bn.weight"], sd["clstm.bn.bias"], training=False, eps=1e-5)
             if force_argmax is not None:
                 bb, cc, hh2, ww2 = cur.shape
-                win = cur.view(bb, cc, hh2 // 2, 2, ww2 // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(bb, cc, hh2 // 2, ww2 // 2, 4)
+                ev = cur[:, :, :hh2 // 2 * 2, :ww2 // 2 * 2]  # MaxPool2d(2) floors odd maps (15x20 -> 7x10)
+                win = ev.reshape(bb, cc, hh2 // 2, 2, ww2 // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(bb, cc, hh2 // 2, ww2 // 2, 4)
                 cur = win.gather(-1, force_argmax[i][t].long().unsqueeze(-1)).squeeze(-1)
             else:
                 cur = F.max_pool2d(cur, 2)
