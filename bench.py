@@ -208,49 +208,102 @@ def conv_time_one_engine(eng):
     return sum(a.elapsed_time(b) for a, b in events) * 1e-3, len(events)
 
 
-def gradcam_throughput(dev, rank, world, mode, clips_n=8, reps=5):
-    """Second half of the headline metric (config C1): Grad-CAM clips/s on I3D-KTH (6 classes), native
-    32x120x160 clips, through the drop-in GradCamVideo — `value`: clips resident in HBM, CAMs left on the
-    device; `e2e`: pinned host clips in, numpy CAMs out (H2D + forward + head' + fused CAM kernel + D2H)."""
+def gradcam_throughput(dev, rank, world, mode, batch=32, n_clips=256, reps=5, with_cpu=False):
+    """Second half of the headline metric (config C1): Grad-CAM clips/s on I3D-KTH (6 classes), native 32x120x160
+    clips, through the drop-in GradCamVideo.
+      value : clips resident in HBM as fp32, CAMs left on the device (forward graph + head' + fused CAM kernel);
+      e2e   : GradCamVideo.stream - uint8 frames in pinned host memory in, float32 [T,H,W] maps in pinned host
+              memory out, H2D / compute / D2H on three streams;
+      roofline (tensor): one I3D forward = 43.05 GFLOP per clip (SURVEY 8d) x clips/s against the bf16 peaks;
+      cpu_baseline: the oracle port of pt/grad_cam_videos.py:64-142 on the host cores (rank 0, N = 1 only);
+      geometry_224: the same weights on 32x224x224 clips with the head's pool widened to [4,7,7] - throughput only
+              (the KTH head is ill-formed at 224x224)."""
     import torch.distributed as dist
     from interpreting_video_features_b200.pt.grad_cam_videos import GradCamVideo
     from interpreting_video_features_b200.pt.models import I3D_doubled_kth
-    from oracle import synthetic
+    from oracle import gradcam_oracle, i3d_oracle, synthetic
     torch.manual_seed(0)
     m = quiet(I3D_doubled_kth.Model, 6, last_stride=1, stride_mod_layers="", softMax=1, finalTimeLength=4)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.to(dev).eval().set_mode(mode)
     gc = GradCamVideo(model=m, target_layer_names=['Mixed_5c'], class_dict=None, use_cuda=True,
                       input_spatial_size=(160, 120), normalizePerFrame=True, archType="I3D")
-    host = torch.stack([synthetic.uniform_clip_u8(1000 + rank * clips_n + i, t=32, h=120, w=160)
-                        for i in range(clips_n)]).pin_memory()  # decoded uint8 frames, as the loaders produce them
-    xd = host.to(dev).float()
-    idx = [i % 6 for i in range(clips_n)]
-    for _ in range(2):
-        gc._i3d(xd, idx)
+    uniq = torch.stack([synthetic.uniform_clip_u8(1000 + rank * batch + i, t=32, h=120, w=160) for i in range(batch)])
+    host = uniq.repeat(n_clips // batch, 1, 1, 1, 1).pin_memory()  # decoded uint8 frames, as the loaders produce them
+    xd = uniq.to(dev).float()
+    eng = m._engine(xd, batch=batch)
+    eng.set_input(xd)
+    cam_dev = torch.empty((batch, 32, 120, 160), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        eng.gradcam(None, (120, 160), True, cam=cam_dev)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        gc._i3d(xd, idx)
+        eng.gradcam(None, (120, 160), True, cam=cam_dev)
     e1.record()
     torch.cuda.synchronize()
     dev_s = e0.elapsed_time(e1) * 1e-3 / reps
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        cams, _ = gc.batched(host, idx)
+    gc.stream(host, None, batch=batch)  # untimed: stream objects, staging buffers, the pinned output block (629 MB of
+    # cudaHostAlloc on first use; torch's caching host allocator hands the same block back to the timed call)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / reps
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    cams, outs = gc.stream(host, None, batch=batch)
+    e2e_s = time.perf_counter() - t0
+    assert cams.shape == (n_clips, 32, 120, 160) and bool(np_isfinite_or_nan(cams))
     if world > 1:
         t = torch.tensor([dev_s, e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = float(t[0]), float(t[1])
-    return {"metric": "gradcam_clips_per_sec", "unit": "clips/s", "value": world * clips_n / dev_s,
-            "e2e": world * clips_n / e2e_s, "clips_per_gpu": clips_n,
-            "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(cams.size * 4),
-            "workload": "C1: I3D KTH (6 classes) Grad-CAM at Mixed_5c, 32x120x160 synthetic clips (the model's "
-                        "native geometry, SURVEY fact 10), %d clips per call, not CUDA-graphed" % clips_n}
+    pk, pk_src = peaks()
+    gf_clip = i3d_oracle.conv_flops_per_clip(sd, (32, 120, 160)) / 1e9
+    val = world * batch / dev_s
+    out = {"metric": "gradcam_clips_per_sec", "unit": "clips/s", "value": val, "e2e": world * n_clips / e2e_s,
+           "clips_per_gpu": n_clips, "batch": batch, "ms_per_batch_device": dev_s * 1e3,
+           "h2d_bytes_per_clip": int(host[0].numel()), "d2h_bytes_per_clip": int(cams[0].size * 4),
+           "roofline": {"bound": "tensor", "achieved": val / world * gf_clip / 1e3, "unit": "TFLOP/s",
+                        "peak": pk["bf16_tflops"], "frac": val / world * gf_clip / 1e3 / pk["bf16_tflops"],
+                        "algorithmic_gflop_per_clip": gf_clip, "peak_source": pk_src},
+           "workload": "C1: I3D KTH (6 classes) Grad-CAM at Mixed_5c, 32x120x160 synthetic clips (the model's native "
+                       "geometry, SURVEY fact 10), %d clips per launch sequence; e2e: %d uint8 clips from pinned host "
+                       "memory through GradCamVideo.stream" % (batch, n_clips)}
+    if with_cpu and rank == 0:
+        x1 = uniq[:1].float()
+        gradcam_oracle.gradcam_i3d(sd, x1, None, (160, 120), True, avg_pool=(4, 4, 5))
+        t0 = time.perf_counter()
+        for i in range(2):
+            gradcam_oracle.gradcam_i3d(sd, uniq[i:i + 1].float(), None, (160, 120), True, avg_pool=(4, 4, 5))
+        dt = (time.perf_counter() - t0) / 2
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "2 timed clips (32x120x160) of the oracle port of GradCamVideo after 1 warm-up"}
+    # throughput-only 32x224x224 variant
+    m.avg_pool.kernel_size = [4, 7, 7]
+    b224 = 8
+    x224 = torch.stack([synthetic.uniform_clip_u8(3000 + i, t=32, h=224, w=224) for i in range(b224)]).to(dev).float()
+    eng2 = m._engine(x224, batch=b224)
+    eng2.set_input(x224)
+    cam2 = torch.empty((b224, 32, 224, 224), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        eng2.gradcam(None, (224, 224), True, cam=cam2)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        eng2.gradcam(None, (224, 224), True, cam=cam2)
+    e1.record()
+    torch.cuda.synchronize()
+    out["geometry_224"] = {"value": world * b224 / (e0.elapsed_time(e1) * 1e-3 / reps), "unit": "clips/s",
+                           "clips_per_launch_sequence": b224,
+                           "note": "32x224x224 clips, device resident, throughput only (no parity claim)"}
+    return out
+
+
+def np_isfinite_or_nan(a):
+    import numpy as np
+    return np.all(np.isfinite(a) | np.isnan(a))
 
 
 def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10):
@@ -436,7 +489,8 @@ def run_ours(args, rank, world, local_rank):
                    "iteration of one 8-clip micro-batch; one 2-iteration call runs untimed first (lazy kernel "
                    "loading, graph capture)" % per_gpu}
 
-    gradcam = gradcam_throughput(dev, rank, world, args.mode) if not args.no_gradcam else None
+    gradcam = gradcam_throughput(dev, rank, world, args.mode, with_cpu=(world == 1 and not args.no_cpu)) \
+        if not args.no_gradcam else None
     clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
 
     if rank != 0:
@@ -465,7 +519,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--clips-per-gpu", type=int, default=128, help="clips per GPU of the end-to-end (C4) leg")
-    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "8")),
+    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "32")),
                     help="clips per launch sequence in the end-to-end leg (the headline `value` stays at BASELINE's 8)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")

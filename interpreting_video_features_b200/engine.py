@@ -345,28 +345,10 @@ class I3DEngine:
         self.g_feat_raw = feat.like(torch.float32)
 
         # ---- backward program
-        last = stages[-1]
-        self.bwd_ops.append((0, lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
-                                                     self.dprobs, mask=last["out"], mask_scale=last["scale"])))
+        self._add_unit_bwd = add_unit_bwd
+        self._emit_head_bwd()
         for i in range(len(stages) - 1, -1, -1):
-            st = stages[i]
-            prv = stages[i - 1] if i > 0 else None
-            if prv is None:
-                g_in, mask, mscale = self.g_xin, None, None
-            else:
-                g_in = prv["gout"]
-                mask = prv["out"] if prv["scale"] is not None else None
-                mscale = prv["scale"]
-            if st["kind"] == "unit":
-                add_unit_bwd(st["unit"], st["gout"], st["x"], g_in, mask=mask, mask_scale=mscale,
-                             xin_is_s2d=(st["first"] and mode == "bf16"))
-            elif st["kind"] == "pool":
-                self.bwd_ops.append((0, lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
-                                     ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
-                                                       mask=mask, mask_scale=mscale,
-                                                       relu_bits=st["bits"] if mask is not None else None)))
-            else:
-                self._build_inception_bwd(st, g_in, mask, mscale, add_unit_bwd)
+            self._emit_stage_bwd(i)
 
         # ---- mask-search state; x is a static buffer so a captured graph stays valid across batches
         self.x = ops.zeros((B, in_channels, self.T, self.H, self.W), torch.float32, dev)
@@ -380,6 +362,63 @@ class I3DEngine:
                 torch.cuda.synchronize(dev)
 
     # -------------------------------------------------------------------------------------
+    def _emit_head_bwd(self):
+        last = self.stages[-1]
+        self.bwd_ops.append((0, lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
+                                                     self.dprobs, mask=last["out"], mask_scale=last["scale"])))
+
+    def _emit_stage_bwd(self, i, raw_out=None):
+        """Append the data-gradient launches of stage i to self.bwd_ops.  Normally its input gradient goes to the
+        previous stage's `gout` with that stage's ReLU'/BN' applied; raw_out (an fp32 Act shaped like the previous
+        stage's output) receives the UNMASKED gradient w.r.t. that output instead - Grad-CAM's `grads_val`."""
+        stages, mode = self.stages, self.mode
+        st = stages[i]
+        prv = stages[i - 1] if i > 0 else None
+        if raw_out is not None:
+            g_in, mask, mscale = raw_out, None, None
+        elif prv is None:
+            g_in, mask, mscale = self.g_xin, None, None
+        else:
+            g_in = prv["gout"]
+            mask = prv["out"] if prv["scale"] is not None else None
+            mscale = prv["scale"]
+        if st["kind"] == "unit":
+            self._add_unit_bwd(st["unit"], st["gout"], st["x"], g_in, mask=mask, mask_scale=mscale,
+                               xin_is_s2d=(st["first"] and mode == "bf16"))
+        elif st["kind"] == "pool":
+            self.bwd_ops.append((0, lambda st=st, g_in=g_in, mask=mask, mscale=mscale:
+                                 ops.maxpool3d_bwd(st["gout"], st["argmax"], g_in, st["k"], st["s"], st["pads"],
+                                                   mask=mask, mask_scale=mscale,
+                                                   relu_bits=st["bits"] if mask is not None else None)))
+        else:
+            self._build_inception_bwd(st, g_in, mask, mscale, self._add_unit_bwd)
+
+    def raw_gradient_program(self, layer):
+        """(program, fp32 Act): the backward launches from the head down to the consumer of endpoint `layer`, the
+        last of them writing the unmasked gradient of sum(dprobs * probs) w.r.t. that endpoint's output - what the
+        reference's hook on the layer's output records (pt/pytorch-grad-cam/grad-cam.py:23-54).  Built on first use
+        per layer; the activations and the masked `gout` buffers of the later stages are the engine's own."""
+        cache = self.__dict__.setdefault("_raw_progs", {})
+        if layer in cache:
+            return cache[layer]
+        names = [st["name"] for st in self.stages]
+        if layer not in names:
+            raise _lib.IvfError("unknown endpoint %r (have %s)" % (layer, names))
+        idx = names.index(layer)
+        if idx == len(names) - 1:
+            raise _lib.IvfError("the last endpoint's raw gradient comes from head_grad_raw()")
+        raw = self.stages[idx]["out"].like(torch.float32)
+        saved, self.bwd_ops, self._lane = self.bwd_ops, [], 0
+        try:
+            self._emit_head_bwd()
+            for i in range(len(self.stages) - 1, idx, -1):
+                self._emit_stage_bwd(i, raw_out=raw if i == idx + 1 else None)
+            prog = self.bwd_ops
+        finally:
+            self.bwd_ops = saved
+        cache[layer] = (prog, raw)
+        return cache[layer]
+
     def _build_inception(self, sd, name, x, new_act, add_unit_fwd):
         mode, dev = self.mode, self.device
         u = {b: Unit(sd, "%s.%s" % (name, b), (1, 1, 1), mode, dev) for b in ("b0", "b1a", "b1b", "b2a", "b2b", "b3b")}
@@ -565,9 +604,8 @@ class I3DEngine:
         out_hw=(H, W) writes the upsampled, normalised map into `cam` [B, T, H, W] (allocated when None);
         `lowres` [B, T', h, w] receives the map before upsampling (what a multi-GPU job gathers).  Returns
         (cam or None, lowres or None, probs copy)."""
-        if layer != "Mixed_5c":
-            raise _lib.IvfError("the fused Grad-CAM path targets 'Mixed_5c'; other layers go through "
-                                "GradCamVideo's generic route")
+        if layer not in self.acts:
+            raise _lib.IvfError("unknown Grad-CAM target layer %r (endpoints: %s)" % (layer, list(self.acts)))
         probs = self.forward_graphed() if graphed else self.forward(None)
         out = probs.clone()
         if indices is None:
@@ -579,7 +617,11 @@ class I3DEngine:
             ops.one_hot(self._targets, self.dprobs)
         else:
             self.set_targets(indices)
-        grad = self.head_grad_raw()
+        if layer == self.stages[-1]["name"]:
+            grad = self.head_grad_raw()  # the head's backward alone reaches the last endpoint
+        else:  # any earlier endpoint: the data-gradient pass down to that layer's consumer, unmasked at the end
+            prog, grad = self.raw_gradient_program(layer)
+            self._run(prog)
         act = self.acts[layer]
         step = self.T // act.d  # pt/grad_cam_videos.py:112-113
         if out_hw is not None and cam is None:

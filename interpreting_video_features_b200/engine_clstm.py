@@ -135,15 +135,19 @@ class CLSTMEngine:
 
         # ---- classifier: Linear over the NCHW-flattened last effective step (CLSTM_4.py:78-80), columns
         # permuted once to our channels-last flattening
-        wfc = strip_module_prefix(state_dict)["endFC.weight"].detach().float().cpu()  # permuted on the host
-        ncls = wfc.shape[0]
-        if wfc.shape[1] != hidden * hin * win:
-            raise _lib.IvfError("endFC expects %d features, the stack produces %d (use_entire_seq is not supported)"
-                                % (wfc.shape[1], hidden * hin * win))
-        wp = torch.zeros((ncls, hin * win, he))
-        wp[:, :, :hidden] = wfc.view(ncls, hidden, hin * win).permute(0, 2, 1)
-        self.w_fc = wp.reshape(ncls, -1).contiguous().to(dev)
-        self.b_fc = sd["endFC.bias"].contiguous()
+        full_sd = strip_module_prefix(state_dict)
+        if "endFC.weight" in full_sd:
+            wfc = full_sd["endFC.weight"].detach().float().cpu()  # permuted on the host
+            ncls = wfc.shape[0]
+            if wfc.shape[1] != hidden * hin * win:
+                raise _lib.IvfError("endFC expects %d features, the stack produces %d (use_entire_seq is not supported)"
+                                    % (wfc.shape[1], hidden * hin * win))
+            wp = torch.zeros((ncls, hin * win, he))
+            wp[:, :, :hidden] = wfc.view(ncls, hidden, hin * win).permute(0, 2, 1)
+            self.w_fc = wp.reshape(ncls, -1).contiguous().to(dev)
+            self.b_fc = sd["endFC.bias"].contiguous()
+        else:  # the recurrent stack on its own (models.convolution_lstm.ConvLSTM.forward): no classifier
+            ncls, self.w_fc, self.b_fc = 1, None, None
         self.num_classes = ncls
         self.logits = ops.zeros((B, ncls), torch.float32, dev)
         self.probs = ops.zeros((B, ncls), torch.float32, dev)
@@ -223,10 +227,24 @@ class CLSTMEngine:
                                     rec["c"][t * B:(t + 1) * B], self._step(rec["h"], t).buf, rec["gact"][t * B:(t + 1) * B].view(m, 4 * he))
             ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
                               rec["pooled"].buf, rec["argmax"], s2d=rec["s2d_out"])
+        if self.w_fc is None:
+            return None
         te = self.eff[-1]
         ops.head_fwd(self._feat(self.layers[-1]["pooled"], te), self.w_fc, self.b_fc, self.softmax, self.probs,
                      self.logits, workspace=self.head_ws)
         return self.probs
+
+    def step_outputs(self):
+        """What ConvLSTM.forward returns (pt/models/convolution_lstm.py:96-132): the last layer's BN+pooled output at
+        every effective step as fp32 NCHW tensors, and (x, new_c) = that output and the last layer's cell state at
+        the final step."""
+        top = self.layers[-1]
+        B, T, hid = self.B, self.T, self.hid
+        pooled = top["pooled"].buf.view(T, B, self.fh, self.fw, self.he)[..., :hid]
+        outs = [pooled[t].permute(0, 3, 1, 2).float().contiguous() for t in self.eff]
+        last = pooled[T - 1].permute(0, 3, 1, 2).float().contiguous()
+        c = top["c"].view(T, B, top["ho"], top["wo"], self.he)[T - 1, ..., :hid].permute(0, 3, 1, 2).contiguous()
+        return outs, (last, c)
 
     # ------------------------------------------------------------------ backward (BPTT data gradient)
     @_lib.on_device

@@ -61,14 +61,16 @@ def cam_from_features(target, grads_val, clip_size, input_spatial_size, normaliz
 
 
 def gradcam_i3d(sd, x, index=None, input_spatial_size=(224, 224), normalize_per_frame=True,
-                avg_pool=(2, 7, 7), softmax=True, quant=False):
-    """pt/grad_cam_videos.py:27-43,64-98 for archType 'I3D', target layer Mixed_5c.
-    x [1,3,T,H,W]; returns (cam [T,H,W] float32, output [1,classes], lowres cam)."""
+                avg_pool=(2, 7, 7), softmax=True, quant=False, layer="Mixed_5c"):
+    """pt/grad_cam_videos.py:27-43,64-98 for archType 'I3D'; the target layer is any endpoint the reference's
+    FeatureExtractor can hook (pt/pytorch-grad-cam/grad-cam.py:23-31: children of the model by name), the drivers
+    use Mixed_5c.  x [1,3,T,H,W]; returns (cam [T,H,W] float32, output [1,classes], lowres cam)."""
     from . import i3d_oracle
 
-    feat, _ = i3d_oracle.features(sd, x, quant=quant)
+    feat, _ = i3d_oracle.features(sd, x, upto=layer, quant=quant)
     feat = feat.detach().requires_grad_(True)
-    output = i3d_oracle.head(sd, feat, avg_pool, softmax)
+    top = feat if layer == "Mixed_5c" else i3d_oracle.features(sd, feat, quant=quant, start_after=layer)[0]
+    output = i3d_oracle.head(sd, top, avg_pool, softmax)
     if index is None:
         index = int(np.argmax(output.detach().cpu().numpy()))
     score = output[0, int(index)]  # sum(one_hot * output)

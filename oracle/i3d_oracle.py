@@ -100,7 +100,7 @@ def inception(sd, name, x, quant=False, force=None):
     return torch.cat([b0, b1, b2, b3], dim=1)
 
 
-def features(sd, x, upto="Mixed_5c", stride_mods=None, quant=False, force=None):
+def features(sd, x, upto="Mixed_5c", stride_mods=None, quant=False, force=None, start_after=None):
     """force: optional dict of IMPOSED decisions - {unit prefix: bool ReLU mask [N,C,D,H,W]} and
     {pool name (Inception branch pools: '<module>.b3a'): window index [N,C,od,oh,ow]}.  With every decision
     imposed the network is a fixed linear map of its input, so two evaluations that agree on the decisions
@@ -108,9 +108,13 @@ def features(sd, x, upto="Mixed_5c", stride_mods=None, quant=False, force=None):
     from the re-routing that flipped ReLU / arg-max decisions cause."""
     stride_mods = stride_mods or {}
     outs = {}
-    if quant:
+    if quant and start_after is None:
         x = quant_input(x)
+    skipping = start_after is not None  # x is the output of endpoint `start_after`: run the rest of the network
     for name in ENDPOINTS:
+        if skipping:
+            skipping = name != start_after
+            continue
         if name == "Conv3d_1a_7x7":
             x = unit3d(sd, name, x, stride_mods.get(name, (2, 2, 2)), quant=quant, force=force)
         elif name.startswith("Conv3d"):

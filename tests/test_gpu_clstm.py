@@ -171,3 +171,44 @@ def test_clstm_mask_search_reverse(dev):
         assert union == 0 or float((a & b).sum()) / union >= 0.95
         assert float((res["time_mask"][i].cpu() - final).abs().max()) < 2e-2
         assert abs(float(res["freeze_score"][i]) - cls) < 1e-2 * abs(cls) + 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_convlstm_module_forward(dev, mode):
+    """models.convolution_lstm.ConvLSTM.forward on its own (pt/models/convolution_lstm.py:96-132): the outputs at the
+    effective steps and (x, new_c), as the reference's FeatureExtractor consumes them
+    (pt/pytorch-grad-cam/grad-cam.py:33-49), against the oracle."""
+    import torch.nn.functional as F
+    from oracle import clstm_oracle, synthetic
+    model, sd = build(4)
+    model = model.to(dev).eval()
+    model.clstm.ivf_mode = mode
+    x = synthetic.clips(2, kind="square", t=32, h=120, w=160) / 255.0
+    with torch.no_grad():
+        outs, (last, new_c) = model.clstm(x.to(dev))
+        _, want = clstm_oracle.forward(sd, x, hidden=4, return_outputs=True, **KW)
+    tol = 1e-4 if mode == "fp32" else 1e-2
+    assert len(outs) == 4 and tuple(outs[0].shape) == (2, 4, 7, 10)
+    for a, b in zip(outs, want):
+        assert rel_err(a.cpu(), b) < tol, rel_err(a.cpu(), b)
+    assert torch.equal(last, outs[-1]) and tuple(new_c.shape) == (2, 4, 15, 20)
+    with pytest.raises(Exception):
+        model.clstm(x.to(dev).requires_grad_())
+
+
+def test_convlstm_cell_forward_and_init_hidden(dev):
+    """ConvLSTMCell.forward / init_hidden on their own (pt/models/convolution_lstm.py:38-60)."""
+    from oracle import clstm_oracle
+    model, sd = build(4)
+    model = model.to(dev).eval()
+    cell = model.clstm.cell0
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand((2, 3, 24, 32), generator=g)
+    h0, c0 = cell.init_hidden(batch_size=2, hidden=4, shape=(24, 32))
+    assert tuple(h0.shape) == (2, 4, 12, 16) and float(h0.abs().sum()) == 0 and h0.is_cuda
+    h = torch.randn((2, 4, 12, 16), generator=g) * 0.5
+    c = torch.randn((2, 4, 12, 16), generator=g) * 0.5
+    with torch.no_grad():
+        h1, c1 = cell(x.to(dev), h.to(dev), c.to(dev))
+        wh, wc = clstm_oracle._cell(sd, "clstm.cell0", x, h, c, 5, 2)
+    assert rel_err(h1.cpu(), wh) < 1e-4 and rel_err(c1.cpu(), wc) < 1e-4

@@ -105,7 +105,8 @@ def test_smth_driver_native_two_clips(dev, tmp_path):
         want, _, _ = gradcam_oracle.gradcam_i3d(sds, x[b:b + 1], pred, (64, 64), True, avg_pool=(2, 2, 2))
         ok = ~np.isnan(want)
         assert g["GCHeatMap"].shape == (16, 64, 64) and np.array_equal(np.isnan(g["GCHeatMap"]), np.isnan(want))
-        assert np.abs(g["GCHeatMap"][ok] - want[ok]).max() < 2e-3
+        if ok.any():  # an all-zero class-activation map normalises to NaN everywhere, here and in the reference
+            assert np.abs(g["GCHeatMap"][ok] - want[ok]).max() < 2e-3
         folder = tmp_path / "cam_saved_images" / "t" / str(r["true_class"]) / (
             r["video_id"] + "g_%d_gs%5.4f_cs%5.4f" % (pred, r["original_score_guess"], r["original_score_true"])) / "combined"
         assert float((folder / ("ClassScoreFreezecase%s.txt" % r["video_id"])).read_text()) == r["freeze_score"]
