@@ -533,7 +533,9 @@ class I3DEngine:
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            # IVF_LANE_PRIO="p1,p2,p3": CUDA stream priorities of the three side lanes (lower = more urgent)
+            prio = [int(v) for v in os.environ.get("IVF_LANE_PRIO", "0,0,0").split(",")]
+            self._side = [torch.cuda.Stream(device=self.device, priority=prio[i]) for i in range(3)]
         for item in prog:
             if item[0] == "fork":  # ("fork",) all side lanes, ("fork", (lanes...)) only those
                 ev = torch.cuda.Event()
