@@ -51,7 +51,8 @@ enum {
   IVF_EP_RELU = 2,    /* v = max(v,0)                (pt/models/I3D_doubled.py:113)                      */
   IVF_EP_ACCUM = 4,   /* v += acc_in[...]  (fp32)    (sum over the consumers of a tensor in backward)    */
   IVF_EP_MASK = 8,    /* v = mask_y[...]>0 ? v*mask_scale[c] : 0  (ReLU'+BN' of the producing Unit3D)     */
-  IVF_EP_OUT_F32 = 16 /* store fp32 instead of the activation dtype                                       */
+  IVF_EP_OUT_F32 = 16,/* store fp32 instead of the activation dtype                                       */
+  IVF_EP_LSTM = 32    /* ConvLSTM gates in the epilogue (ivf_conv3d_lstm only)                             */
 };
 
 /* ---- lifetime ------------------------------------------------------------ */
@@ -156,6 +157,8 @@ typedef struct ivf_pack_desc {
   int32_t dtype;
   int32_t n_pad, k_pad, n_off, k_off;
   int32_t zero_first;
+  int32_t n_stride, k_stride; /* this source's rows / reduction entries land every n_stride / k_stride-th index
+                               * (0 = 1): the unit-major gate interleave of the fused ConvLSTM epilogue */
 } ivf_pack_desc;
 int ivf_pack_weights(ivf_handle* h, const ivf_pack_desc* d, const float* src, void* dst, void* stream);
 /* scale = gamma/sqrt(var+eps), shift = beta - mean*scale (+ scale*conv_bias): eval BatchNorm folded into the
@@ -308,13 +311,26 @@ int ivf_gradcam(ivf_handle* h, int act_dtype, int grad_dtype, const void* act, c
  *   i=s(.) f=s(.) c'=f*c+i*tanh(.) o=s(.) h'=o*tanh(c')      (zero peepholes, :52-54)
  * c_prev may be NULL (step 0, zero state).  gate_act (fp32 [m][4*hid]) keeps the activated
  * gates for the backward pass.                                                          */
+/* unit_major != 0: pre / gate_act / dgates rows are [i0 f0 c0 o0 i1 f1 c1 o1 ...] instead of [i.. | f.. | c.. | o..]
+ * (bf16 path, hid % 4 == 0): the channel order of the fused recurrent convolution below. */
 int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, const float* c_prev, int m,
-                        int hid, float* c_next, void* h_next, float* gate_act, void* stream);
+                        int hid, float* c_next, void* h_next, float* gate_act, int unit_major, void* stream);
 /* BPTT step: dh = dL/dh' (fp32 [m][hid]); dc_io holds dL/dc' carried from step t+1 on entry
  * and dL/dc for step t-1 on exit; dgates ([m][4*hid], activation dtype) = dL/dpre.      */
 int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_act, const float* c_prev,
                         const float* c_next, const float* dh, float* dc_io, int m, int hid,
-                        void* dgates, void* stream);
+                        void* dgates, int unit_major, void* stream);
+/* The recurrent step as ONE kernel (pt/models/convolution_lstm.py:38-48): the h-convolution (bf16 tcgen05
+ * implicit GEMM, stride 1, 'same') with the gates applied in its epilogue straight from the TMEM accumulator:
+ *   pre = pre_x[pix] + conv(h_prev, Wh)      (pre_x: the x-convolution of this step incl. bias, fp32 [pix][4*hid])
+ *   i,f,o = sigmoid, g = tanh;  c' = f*c_prev + i*g;  h' = o*tanh(c')
+ * Output channels are UNIT-MAJOR (4*k + gate, weights packed with n_stride = 4): a 16-column accumulator chunk
+ * holds four whole hidden units.  d describes the convolution (cout = 4*hid, out_ld = 4*hid, out_coff = 0);
+ * gate_act (fp32 [pix][4*hid], unit-major) keeps the activated gates for the backward pass; c_prev / c_next fp32
+ * [pix][hid]; h_next bf16 [pix][hid].  Replaces a convolution launch + a gate launch and the fp32 round trip of the
+ * pre-activations between them. */
+int ivf_conv3d_lstm(ivf_handle* h, const ivf_conv_desc* d, const void* h_prev, const void* w, const float* pre_x,
+                    const float* c_prev, float* c_next, void* h_next, float* gate_act, void* stream);
 /* eval BatchNorm2d affine + MaxPool2d(2) (pt/models/convolution_lstm.py:120-124);
  * x [n][hh][ww][c] -> y [n][hh/2][ww/2][c]; backward returns fp32 dx (+ acc_in if given).
  * s2d != 0: y (and dy) use the 2-D space-to-depth layout [n][hh/4][ww/4][4c] that the next layer's

@@ -149,6 +149,44 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
   return r;
 }
 
+// four gate vectors of units k..k+3: gate-major rows [i | f | c | o] (UM = false) or unit-major rows
+// [i0 f0 c0 o0 i1 f1 ...] (UM = true: the layout in which a 16-column chunk of the recurrent convolution's
+// accumulator holds whole hidden units, so the gates can be applied in that convolution's epilogue)
+template <bool UM>
+__device__ __forceinline__ void load_gates4(const float* __restrict__ row, int hid, int k, float4& a, float4& b, float4& c,
+                                            float4& d) {
+  if (UM) {
+    const float4* q = reinterpret_cast<const float4*>(row + 4 * k);
+    const float4 u0 = q[0], u1 = q[1], u2 = q[2], u3 = q[3];
+    a = make_float4(u0.x, u1.x, u2.x, u3.x);
+    b = make_float4(u0.y, u1.y, u2.y, u3.y);
+    c = make_float4(u0.z, u1.z, u2.z, u3.z);
+    d = make_float4(u0.w, u1.w, u2.w, u3.w);
+  } else {
+    a = *reinterpret_cast<const float4*>(row + k);
+    b = *reinterpret_cast<const float4*>(row + hid + k);
+    c = *reinterpret_cast<const float4*>(row + 2 * hid + k);
+    d = *reinterpret_cast<const float4*>(row + 3 * hid + k);
+  }
+}
+template <bool UM>
+__device__ __forceinline__ void store_gates4(float* __restrict__ row, int hid, int k, const float4& a, const float4& b,
+                                             const float4& c, const float4& d) {
+  if (UM) {
+    float4* q = reinterpret_cast<float4*>(row + 4 * k);
+    q[0] = make_float4(a.x, b.x, c.x, d.x);
+    q[1] = make_float4(a.y, b.y, c.y, d.y);
+    q[2] = make_float4(a.z, b.z, c.z, d.z);
+    q[3] = make_float4(a.w, b.w, c.w, d.w);
+  } else {
+    *reinterpret_cast<float4*>(row + k) = a;
+    *reinterpret_cast<float4*>(row + hid + k) = b;
+    *reinterpret_cast<float4*>(row + 2 * hid + k) = c;
+    *reinterpret_cast<float4*>(row + 3 * hid + k) = d;
+  }
+}
+
+template <bool UM>
 __global__ void __launch_bounds__(256)
 gates_fwd_bf16x4_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, int m, int hid,
                         float* __restrict__ c_next, __nv_bfloat16* __restrict__ h_next, float* __restrict__ gate_act) {
@@ -156,9 +194,8 @@ gates_fwd_bf16x4_kernel(const float* __restrict__ pre, const float* __restrict__
   const int total = m * hv;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / hv, k = (idx - r * hv) << 2;
-    const float* p = pre + (size_t)r * 4 * hid + k;
-    const float4 pi = *reinterpret_cast<const float4*>(p), pf = *reinterpret_cast<const float4*>(p + hid);
-    const float4 pg = *reinterpret_cast<const float4*>(p + 2 * hid), po = *reinterpret_cast<const float4*>(p + 3 * hid);
+    float4 pi, pf, pg, po;
+    load_gates4<UM>(pre + (size_t)r * 4 * hid, hid, k, pi, pf, pg, po);
     const size_t e = (size_t)r * hid + k;
     const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 gi, gf, gg, go, cn, hn;
@@ -173,16 +210,11 @@ gates_fwd_bf16x4_kernel(const float* __restrict__ pre, const float* __restrict__
 #undef IVF_GATE
     *reinterpret_cast<float4*>(c_next + e) = cn;
     *reinterpret_cast<uint2*>(h_next + e) = pack_bf16x4(hn.x, hn.y, hn.z, hn.w);
-    if (gate_act) {
-      float* a = gate_act + (size_t)r * 4 * hid + k;
-      *reinterpret_cast<float4*>(a) = gi;
-      *reinterpret_cast<float4*>(a + hid) = gf;
-      *reinterpret_cast<float4*>(a + 2 * hid) = gg;
-      *reinterpret_cast<float4*>(a + 3 * hid) = go;
-    }
+    if (gate_act) store_gates4<UM>(gate_act + (size_t)r * 4 * hid, hid, k, gi, gf, gg, go);
   }
 }
 
+template <bool UM>
 __global__ void __launch_bounds__(256)
 gates_bwd_bf16x4_kernel(const float* __restrict__ gate_act, const float* __restrict__ c_prev,
                         const float* __restrict__ c_next, const float* __restrict__ dh, float* __restrict__ dc_io,
@@ -191,9 +223,8 @@ gates_bwd_bf16x4_kernel(const float* __restrict__ gate_act, const float* __restr
   const int total = m * hv;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / hv, k = (idx - r * hv) << 2;
-    const float* a = gate_act + (size_t)r * 4 * hid + k;
-    const float4 gi = *reinterpret_cast<const float4*>(a), gf = *reinterpret_cast<const float4*>(a + hid);
-    const float4 gg = *reinterpret_cast<const float4*>(a + 2 * hid), go = *reinterpret_cast<const float4*>(a + 3 * hid);
+    float4 gi, gf, gg, go;
+    load_gates4<UM>(gate_act + (size_t)r * 4 * hid, hid, k, gi, gf, gg, go);
     const size_t e = (size_t)r * hid + k;
     const float4 cp = c_prev ? *reinterpret_cast<const float4*>(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 cn = *reinterpret_cast<const float4*>(c_next + e);
@@ -213,11 +244,19 @@ gates_bwd_bf16x4_kernel(const float* __restrict__ gate_act, const float* __restr
     IVF_GATE(x) IVF_GATE(y) IVF_GATE(z) IVF_GATE(w)
 #undef IVF_GATE
     *reinterpret_cast<float4*>(dc_io + e) = dco;
-    __nv_bfloat16* d = dgates + (size_t)r * 4 * hid + k;
-    *reinterpret_cast<uint2*>(d) = pack_bf16x4(d_i.x, d_i.y, d_i.z, d_i.w);
-    *reinterpret_cast<uint2*>(d + hid) = pack_bf16x4(d_f.x, d_f.y, d_f.z, d_f.w);
-    *reinterpret_cast<uint2*>(d + 2 * hid) = pack_bf16x4(d_g.x, d_g.y, d_g.z, d_g.w);
-    *reinterpret_cast<uint2*>(d + 3 * hid) = pack_bf16x4(d_o.x, d_o.y, d_o.z, d_o.w);
+    __nv_bfloat16* d = dgates + (size_t)r * 4 * hid;
+    if (UM) {
+      uint2* q = reinterpret_cast<uint2*>(d + 4 * k);
+      q[0] = pack_bf16x4(d_i.x, d_f.x, d_g.x, d_o.x);
+      q[1] = pack_bf16x4(d_i.y, d_f.y, d_g.y, d_o.y);
+      q[2] = pack_bf16x4(d_i.z, d_f.z, d_g.z, d_o.z);
+      q[3] = pack_bf16x4(d_i.w, d_f.w, d_g.w, d_o.w);
+    } else {
+      *reinterpret_cast<uint2*>(d + k) = pack_bf16x4(d_i.x, d_i.y, d_i.z, d_i.w);
+      *reinterpret_cast<uint2*>(d + hid + k) = pack_bf16x4(d_f.x, d_f.y, d_f.z, d_f.w);
+      *reinterpret_cast<uint2*>(d + 2 * hid + k) = pack_bf16x4(d_g.x, d_g.y, d_g.z, d_g.w);
+      *reinterpret_cast<uint2*>(d + 3 * hid + k) = pack_bf16x4(d_o.x, d_o.y, d_o.z, d_o.w);
+    }
   }
 }
 
@@ -318,19 +357,28 @@ int grid_for(ivf_handle* h, long long total) {
 
 extern "C" int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, const float* c_prev,
                                    int m, int hid, float* c_next, void* h_next, float* gate_act,
-                                   void* stream) {
+                                   int unit_major, void* stream) {
   IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && pre && c_next && h_next, "ivf_clstm_gates_fwd: null argument");
   IVF_REQUIRE(m > 0 && hid > 0, "ivf_clstm_gates_fwd: bad extent");
   long long total = (long long)m * hid;
   cudaStream_t st = (cudaStream_t)stream;
+  if (unit_major) {
+    IVF_REQUIRE(dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(pre) && aligned16(c_prev) &&
+                    aligned16(c_next) && aligned8(h_next) && aligned16(gate_act),
+                "ivf_clstm_gates_fwd: the unit-major layout is served by the bf16 vector kernel only");
+    gates_fwd_bf16x4_kernel<true><<<grid_for(h, total / 4), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
+                                                                          (__nv_bfloat16*)h_next, gate_act);
+    IVF_LAUNCHED(h);
+    return IVF_OK;
+  }
   if (dtype == IVF_F32)
     gates_fwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
                                                                 (float*)h_next, gate_act);
   else if (dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(pre) && aligned16(c_prev) &&
            aligned16(c_next) && aligned8(h_next) && aligned16(gate_act))
-    gates_fwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
-                                                                    (__nv_bfloat16*)h_next, gate_act);
+    gates_fwd_bf16x4_kernel<false><<<grid_for(h, total / 4), 256, 0, st>>>(pre, c_prev, m, hid, c_next,
+                                                                           (__nv_bfloat16*)h_next, gate_act);
   else if (dtype == IVF_BF16)
     gates_fwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         pre, c_prev, m, hid, c_next, (__nv_bfloat16*)h_next, gate_act);
@@ -342,19 +390,28 @@ extern "C" int ivf_clstm_gates_fwd(ivf_handle* h, int dtype, const float* pre, c
 
 extern "C" int ivf_clstm_gates_bwd(ivf_handle* h, int dtype, const float* gate_act,
                                    const float* c_prev, const float* c_next, const float* dh,
-                                   float* dc_io, int m, int hid, void* dgates, void* stream) {
+                                   float* dc_io, int m, int hid, void* dgates, int unit_major, void* stream) {
   IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && gate_act && c_next && dh && dc_io && dgates, "ivf_clstm_gates_bwd: null argument");
   IVF_REQUIRE(m > 0 && hid > 0, "ivf_clstm_gates_bwd: bad extent");
   long long total = (long long)m * hid;
   cudaStream_t st = (cudaStream_t)stream;
+  if (unit_major) {
+    IVF_REQUIRE(dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(gate_act) && aligned16(c_prev) &&
+                    aligned16(c_next) && aligned16(dh) && aligned16(dc_io) && aligned8(dgates),
+                "ivf_clstm_gates_bwd: the unit-major layout is served by the bf16 vector kernel only");
+    gates_bwd_bf16x4_kernel<true><<<grid_for(h, total / 4), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m, hid,
+                                                                          (__nv_bfloat16*)dgates);
+    IVF_LAUNCHED(h);
+    return IVF_OK;
+  }
   if (dtype == IVF_F32)
     gates_bwd_kernel<float><<<grid_for(h, total), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m,
                                                                 hid, (float*)dgates);
   else if (dtype == IVF_BF16 && hid % 4 == 0 && total < (1ll << 31) && aligned16(gate_act) && aligned16(c_prev) &&
            aligned16(c_next) && aligned16(dh) && aligned16(dc_io) && aligned8(dgates))
-    gates_bwd_bf16x4_kernel<<<grid_for(h, total / 4), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m, hid,
-                                                                    (__nv_bfloat16*)dgates);
+    gates_bwd_bf16x4_kernel<false><<<grid_for(h, total / 4), 256, 0, st>>>(gate_act, c_prev, c_next, dh, dc_io, m, hid,
+                                                                           (__nv_bfloat16*)dgates);
   else if (dtype == IVF_BF16)
     gates_bwd_kernel<__nv_bfloat16><<<grid_for(h, total), 256, 0, st>>>(
         gate_act, c_prev, c_next, dh, dc_io, m, hid, (__nv_bfloat16*)dgates);

@@ -17,7 +17,7 @@ struct PackParams {
   int wd, wh, ww;           // taps of the (space-to-depth) operand
   int ceff;                 // fd*fh*fw*ci
   int swap, flip, layout;
-  int n_pad, k_pad, n_off, k_off;
+  int n_pad, k_pad, n_off, k_off, n_stride, k_stride;
   int taps;                 // wd*wh*ww
 };
 
@@ -48,7 +48,7 @@ __global__ void pack_weights_kernel(PackParams p, const float* __restrict__ src,
     float v = 0.f;
     if (ch < p.ci && kt < p.kd && khh < p.kh && kww < p.kw)
       v = src[((((long long)co * p.ci + ch) * p.kd + kt) * p.kh + khh) * p.kw + kww];
-    const long long nn = p.n_off + n, kk = p.k_off + k;
+    const long long nn = p.n_off + (long long)n * p.n_stride, kk = p.k_off + (long long)k * p.k_stride;
     long long o;
     if (p.layout == IVF_PACK_KMAJOR) o = (nn * p.taps + tap) * p.k_pad + kk;
     else o = ((long long)tap * p.k_pad + kk) * p.n_pad + nn;
@@ -149,9 +149,11 @@ extern "C" int ivf_pack_weights(ivf_handle* h, const ivf_pack_desc* d, const flo
   IVF_REQUIRE(d->dgrad >= 0 && d->dgrad <= 2, "ivf_pack_weights: dgrad must be 0, 1 or 2");
   p.swap = d->dgrad != 0; p.flip = d->dgrad == 1; p.layout = d->layout;
   p.n_pad = d->n_pad; p.k_pad = d->k_pad; p.n_off = d->n_off; p.k_off = d->k_off;
+  p.n_stride = d->n_stride > 0 ? d->n_stride : 1; p.k_stride = d->k_stride > 0 ? d->k_stride : 1;
   p.taps = p.wd * p.wh * p.ww;
   const int nsrc = p.swap ? p.ceff : p.co, ksrc = p.swap ? p.co : p.ceff;
-  IVF_REQUIRE(d->n_off >= 0 && d->k_off >= 0 && d->n_off + nsrc <= d->n_pad && d->k_off + ksrc <= d->k_pad,
+  IVF_REQUIRE(d->n_off >= 0 && d->k_off >= 0 && d->n_off + (nsrc - 1) * p.n_stride < d->n_pad &&
+                  d->k_off + (ksrc - 1) * p.k_stride < d->k_pad,
               "ivf_pack_weights: block %dx%d at (%d,%d) exceeds the packed matrix %dx%d", nsrc, ksrc, d->n_off,
               d->k_off, d->n_pad, d->k_pad);
   cudaStream_t st = (cudaStream_t)stream;
