@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libivf.so")
 
 IVF_F32, IVF_BF16, IVF_U8 = 0, 1, 2
-EP_AFFINE, EP_RELU, EP_ACCUM, EP_MASK, EP_OUT_F32 = 1, 2, 4, 8, 16
+EP_AFFINE, EP_RELU, EP_ACCUM, EP_MASK, EP_OUT_F32, EP_LSTM = 1, 2, 4, 8, 16, 32
 PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, PFMT_TBHWC_F32, PFMT_S2D2_BF16 = 0, 1, 2, 3, 4
 PACK_KMAJOR, PACK_TAPMAJOR = 0, 1
 
@@ -36,7 +36,7 @@ class ConvSplit(C.Structure):
 class PackDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "co", "ci", "kd", "kh", "kw", "ci_stride", "s2d_d", "s2d_h", "s2d_w", "dgrad", "layout", "dtype", "n_pad",
-        "k_pad", "n_off", "k_off", "zero_first")]
+        "k_pad", "n_off", "k_off", "zero_first", "n_stride", "k_stride")]
 
 
 class PoolDesc(C.Structure):
@@ -86,8 +86,9 @@ SIGNATURES = {
     "ivf_init_mask_select": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
     "ivf_tv_norm": (_I, [_P, _P, _I, _F, _F, _P, _P, _P]),
     "ivf_gradcam": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "ivf_clstm_gates_fwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
-    "ivf_clstm_gates_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "ivf_clstm_gates_fwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _I, _P]),
+    "ivf_clstm_gates_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "ivf_conv3d_lstm": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ivf_bn_pool2d_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "ivf_bn_pool2d_bwd": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "ivf_viz_triptych": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),

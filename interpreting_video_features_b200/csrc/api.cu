@@ -120,6 +120,26 @@ extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf
                               in2, out2);
 }
 
+extern "C" int ivf_conv3d_lstm(ivf_handle* h, const ivf_conv_desc* d0, const void* h_prev, const void* w,
+                               const float* pre_x, const float* c_prev, float* c_next, void* h_next, float* gate_act,
+                               void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && d0 && h_prev && w && pre_x && c_next && h_next && gate_act, "ivf_conv3d_lstm: null argument");
+  ivf_conv_desc d = *d0;
+  IVF_REQUIRE(d.dtype == IVF_BF16, "ivf_conv3d_lstm: bf16 only");
+  IVF_REQUIRE(d.cout % 16 == 0 && d.out_ld == d.cout && d.out_coff == 0,
+              "ivf_conv3d_lstm: cout = 4*hid must be a multiple of 16 and fill the gate rows (out_ld = cout, out_coff = 0)");
+  IVF_REQUIRE(((uintptr_t)pre_x | (uintptr_t)c_prev | (uintptr_t)c_next | (uintptr_t)gate_act) % 16 == 0 &&
+                  (uintptr_t)h_next % 8 == 0,
+              "ivf_conv3d_lstm: state buffers must be 16-byte (h_next: 8-byte) aligned");
+  d.flags = IVF_EP_ACCUM | IVF_EP_OUT_F32 | IVF_EP_LSTM;
+  IVF_REQUIRE(ivf_conv3d_slab_eligible(h, &d),
+              "ivf_conv3d_lstm: the recurrent convolution must be a stride-1 'same' convolution on a map >= 7 wide "
+              "(the halo-slab kernel); use ivf_conv3d + ivf_clstm_gates_fwd otherwise");
+  return ivf_conv3d_slab_launch(h, &d, h_prev, w, nullptr, nullptr, pre_x, nullptr, nullptr, gate_act,
+                                (cudaStream_t)stream, c_prev, c_next, h_next);
+}
+
 // Diagnostic: copy the first `bytes` of the handle's scratch buffer to the host (kernel traces written under
 // IVF_TC_TRACE=1).  Synchronises the device.
 extern "C" int ivf_debug_read_scratch(ivf_handle* h, void* dst, size_t bytes) {

@@ -23,7 +23,7 @@ struct ivf_handle {
   // cache of encoded TMA tensor maps keyed by a byte string of everything that shapes them
   std::map<std::string, CUtensorMap> tmaps;
   bool tc_attr_set[4] = {false, false, false, false};
-  bool slab_attr_set[4] = {false, false, false, false};
+  bool slab_attr_set[8] = {false, false, false, false, false, false, false, false};
   // small per-handle scratch (partial logits of the head kernels); allocated once in ivf_create so
   // that no call allocates (CUDA-graph capture safe), freed in ivf_destroy
   float* scratch = nullptr;
@@ -121,4 +121,6 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
 bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d);
 int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                            const float* scale, const float* shift, const float* acc_in,
-                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st);
+                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st,
+                           const float* lstm_c_prev = nullptr, float* lstm_c_next = nullptr,
+                           void* lstm_h_next = nullptr);

@@ -260,7 +260,15 @@ struct EpilogueArgs {
   // go there and the warp sends the box with one TMA store (rows and channels past the tensor are clipped by
   // the tensor map, so no validity tests apply)
   uint32_t stage_smem = 0;
+  // IVF_EP_LSTM (ivf_conv3d_lstm): cell state in / out (fp32 [pix][hid]) and hidden state out (bf16 [pix][hid]);
+  // `out` then is the fp32 gate-activation buffer and acc_in the x-convolution's pre-activations, both
+  // [pix][4*hid] with UNIT-MAJOR channels (4*k + gate), so out_row / 4 is the pixel's offset in the hid-wide rows
+  const float* lstm_c_prev = nullptr;
+  float* lstm_c_next = nullptr;
+  __nv_bfloat16* lstm_h_next = nullptr;
 };
+
+__device__ __forceinline__ float ivf_sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
 
 // TMA store of a staged box: [tensor map, {channel, row}] <- shared memory; bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
@@ -300,6 +308,7 @@ __device__ __forceinline__ void epilogue_prefetch(const EpilogueArgs& e, int nb,
   }
 }
 
+template <bool LSTM = false>
 __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const uint32_t (&r)[16], int nb,
                                                  const float* sc, const float* sh, const float* ms,
                                                  size_t out_row, size_t mask_row, const EpiPre& pre) {
@@ -320,6 +329,38 @@ __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const ui
       for (int j = 0; j < 16; ++j)
         if (nb + j < e.cout) v[j] += e.acc_in[out_row + nb + j];
     }
+  }
+  if constexpr (LSTM) {  // a separate kernel instantiation: the gate math costs the other epilogues no registers
+    // ConvLSTM gates on four whole hidden units (pt/models/convolution_lstm.py:38-48, zero peepholes :50-54):
+    // v = x-conv pre-activation (acc_in) + h-conv accumulator, channels [i f c o] per unit.  Accurate expf/tanhf:
+    // tanh.approx perturbs the hidden state enough to flip 2x2 max-pool decisions downstream (clstm.cu).
+    const size_t hrow = out_row / 4 + (size_t)(nb >> 2);
+    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.lstm_c_prev) cp = *reinterpret_cast<const float4*>(e.lstm_c_prev + hrow);
+    const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+    float cn[4], hn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gi = ivf_sigmoid_f(v[4 * u]), gf = ivf_sigmoid_f(v[4 * u + 1]);
+      const float gg = tanhf(v[4 * u + 2]), go = ivf_sigmoid_f(v[4 * u + 3]);
+      cn[u] = fmaf(gf, cpv[u], gi * gg);
+      hn[u] = go * tanhf(cn[u]);
+      v[4 * u] = gi;
+      v[4 * u + 1] = gf;
+      v[4 * u + 2] = gg;
+      v[4 * u + 3] = go;
+    }
+    *reinterpret_cast<float4*>(e.lstm_c_next + hrow) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
+    uint2 hp;
+    hp.x = *reinterpret_cast<uint32_t*>(&h01);
+    hp.y = *reinterpret_cast<uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(e.lstm_h_next + hrow) = hp;
+    float* o = reinterpret_cast<float*>(e.out) + out_row + nb;  // activated gates for the backward pass
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    return;
   }
   if (e.flags & IVF_EP_AFFINE) {
 #pragma unroll

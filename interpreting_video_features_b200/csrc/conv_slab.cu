@@ -82,6 +82,10 @@ struct SlabParams {
   int diag;  // IVF_SLAB_DIAG (timing experiments, results are garbage): bit 0 / 1 = after the ring has filled
              // once, the slab / weight producer signals "full" without loading
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
+  // IVF_EP_LSTM: the recurrent step's state buffers (see EpilogueArgs)
+  const float* lstm_c_prev;
+  float* lstm_c_next;
+  __nv_bfloat16* lstm_h_next;
 };
 
 struct TileCoord {
@@ -103,7 +107,7 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile, 
 
 // KCH = channels per slab row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B, for
 // operands of <= 32 channels: the space-to-depth stem's 24-of-32 and the 16/32-channel bottlenecks)
-template <int KCH, int NCTA>
+template <int KCH, int NCTA, bool LSTM = false>
 __global__ void __launch_bounds__(SLAB_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const SlabParams p, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -382,6 +386,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.acc_in = acc_in;
     ea.mask_y = mask_y;
     ea.out = out;
+    ea.lstm_c_prev = p.lstm_c_prev;
+    ea.lstm_c_next = p.lstm_c_next;
+    ea.lstm_h_next = p.lstm_h_next;
     int it = 0;
     for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
       const TileCoord t = decode_tile(p, tile, NCTA, rank);
@@ -441,7 +448,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t rr[16];
             tmem_ld16(taddr + c0, rr);
             if (ok && nb < p.cout)
-              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+              epilogue_chunk16<LSTM>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
           }
         } else {
           const int kwm = p.kwm, bn = p.bn;
@@ -471,7 +478,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t rr[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
-              epilogue_chunk16(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+              epilogue_chunk16<LSTM>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
             }
           }
         }
@@ -742,13 +749,13 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   return found;
 }
 
-template <int KCH, int NCTA>
+template <int KCH, int NCTA, bool LSTM>
 int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, const CUtensorMap& mb,
                   const float* scale, const float* shift, const float* acc_in, const void* mask_y,
                   const float* mask_scale, void* out, cudaStream_t st) {
-  const int slot = (KCH == 64 ? 0 : 1) + 2 * (NCTA - 1);
+  const int slot = (KCH == 64 ? 0 : 1) + 2 * (NCTA - 1) + (LSTM ? 4 : 0);
   if (!h->slab_attr_set[slot]) {
-    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA, LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(SLAB_SMEM_BUDGET + 1024)));
     h->slab_attr_set[slot] = true;
   }
@@ -756,8 +763,8 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
   const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
   if (NCTA == 1) {
-    conv_slab_kernel<KCH, 1><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
-                                                               (const __nv_bfloat16*)mask_y, mask_scale, out);
+    conv_slab_kernel<KCH, 1, LSTM><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
+                                                                     (const __nv_bfloat16*)mask_y, mask_scale, out);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -771,7 +778,7 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    IVF_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<KCH, 2>, ma, mb, p, scale, shift, acc_in,
+    IVF_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<KCH, 2, LSTM>, ma, mb, p, scale, shift, acc_in,
                                 (const __nv_bfloat16*)mask_y, mask_scale, out));
   }
   IVF_LAUNCHED(h);
@@ -822,13 +829,17 @@ bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d0) {
 
 int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* in, const void* w,
                            const float* scale, const float* shift, const float* acc_in,
-                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st) {
+                           const void* mask_y, const float* mask_scale, void* out, cudaStream_t st,
+                           const float* lstm_c_prev, float* lstm_c_next, void* lstm_h_next) {
   const ivf_conv_desc dv = slab_view(d0);
   const ivf_conv_desc* d = &dv;
   int rc = ivf_load_driver_entry_points();
   if (rc) return rc;
   SlabParams p;
   if (!slab_config(d, h->sm_count, &p)) IVF_FAIL(IVF_EUNSUPPORTED, "conv(slab): no tile configuration fits");
+  p.lstm_c_prev = lstm_c_prev;
+  p.lstm_c_next = lstm_c_next;
+  p.lstm_h_next = (__nv_bfloat16*)lstm_h_next;
   p.n = d->n; p.dd = d->id; p.hh = d->ih; p.ww = d->iw;
   p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
@@ -855,14 +866,17 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* i
   const int box_rows = (p.ncta == 2 && p.kwm == 1) ? p.bn / 2 : p.bn;
   rc = slab_map_b(h, w, ntaps * p.cin_pad, ivf_conv_bf16_cout_pad(d->cout), box_rows, p.kch, &mb);
   if (rc) return rc;
+#define IVF_SLAB_GO(K, C, L) return slab_launch_t<K, C, L>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st)
+  const bool lstm = (p.flags & IVF_EP_LSTM) != 0;
   if (p.ncta == 2) {
-    if (p.kch == 64)
-      return slab_launch_t<64, 2>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
-    return slab_launch_t<32, 2>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+    if (p.kch == 64) { if (lstm) IVF_SLAB_GO(64, 2, true); IVF_SLAB_GO(64, 2, false); }
+    if (lstm) IVF_SLAB_GO(32, 2, true);
+    IVF_SLAB_GO(32, 2, false);
   }
-  if (p.kch == 64)
-    return slab_launch_t<64, 1>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
-  return slab_launch_t<32, 1>(h, p, ma, mb, scale, shift, acc_in, mask_y, mask_scale, out, st);
+  if (p.kch == 64) { if (lstm) IVF_SLAB_GO(64, 1, true); IVF_SLAB_GO(64, 1, false); }
+  if (lstm) IVF_SLAB_GO(32, 1, true);
+  IVF_SLAB_GO(32, 1, false);
+#undef IVF_SLAB_GO
 }
 
 // diagnostic (no GPU needed): the tile plan the slab kernel would use for a layer, or 0 when the layer

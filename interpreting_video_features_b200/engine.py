@@ -47,7 +47,8 @@ def _dev32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
-def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, co_total=None, ceff_total=None):
+def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, co_total=None, ceff_total=None,
+         co_stride=1):
     """Operand matrix of a convolution kernel from one or more fp32 OIDHW (OIHW: kd = 1) device weights that
     share their input channels and kernel (ivf_pack_weights; nothing is computed by torch).
 
@@ -55,6 +56,8 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
     data-gradient operand (dgrad): rows = operand channels, K = output channels (sources side by side at co_offs).
     s2d: per-axis space-to-depth factor of a stride-2 layer; ci_stride pads each parity block of operand
     channels; ceff_total pads the operand channels as a whole (the 12 -> 16 channel ConvLSTM input record).
+    co_stride: output channel j of a source lands at co_off + j * co_stride (4 with co_offs 0..3 interleaves the four
+    ConvLSTM gates unit-major for the fused recurrent step).
     bf16: K-major [n_pad][taps][k_pad]; fp32: tap-major [taps][k][n] (flat [taps*k, n] like the old packers)."""
     lib = _lib.load()
     ws = [w if w.dim() == 5 else w.unsqueeze(2) for w in sources]
@@ -73,7 +76,7 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
             co_offs.append(acc)
             acc += w.shape[0]
         co_total = acc if co_total is None else co_total
-    assert co_total >= max(o + w.shape[0] for o, w in zip(co_offs, ws))
+    assert co_total >= max(o + (w.shape[0] - 1) * co_stride + 1 for o, w in zip(co_offs, ws))
     n_total, k_total = (ceff_total, co_total) if dgrad else (co_total, ceff_total)
     bf = mode == "bf16"
     if bf:
@@ -93,6 +96,7 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
         d.dtype = _lib.IVF_BF16 if bf else _lib.IVF_F32
         d.n_pad, d.k_pad = n_pad, k_pad
         d.n_off, d.k_off = (0, off) if dgrad else (off, 0)
+        d.n_stride, d.k_stride = (1, co_stride) if dgrad else (co_stride, 1)
         d.zero_first = int(i == 0)
         _lib.check(lib.ivf_pack_weights(h, d, _lib.ptr(w), _lib.ptr(dst), _lib.stream_ptr(dev)), "ivf_pack_weights")
     return dst

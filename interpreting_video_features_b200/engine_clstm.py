@@ -48,6 +48,13 @@ class CLSTMEngine:
         self.generation = 0
         bf = mode == "bf16"
         he = max(8, (hidden + 7) // 8 * 8) if bf else hidden  # padded hidden size
+        # IVF_CLSTM_FUSED=1 (bf16): the recurrent step as ONE kernel (ivf_conv3d_lstm: h-convolution with the gates, the
+        # c/h update and the gate activations in its epilogue, unit-major channels).  Built, parity-tested and
+        # measured on a B200 (C3, 8 clips): 206 launches and 3.77 ms per step against 268 launches and 3.70 ms for the
+        # convolution + gate-kernel pair - the gate math (4 expf + 2 tanhf per hidden unit) lengthens the epilogue of
+        # a one-to-two-wave convolution by more than the separate bandwidth-bound gate kernel costs - so it is opt-in.
+        import os
+        self.unit_major = bf and os.environ.get("IVF_CLSTM_FUSED", "0") != "0"
         self.he = he
         B, T = batch, clip[0]
         N = T * B
@@ -87,10 +94,18 @@ class CLSTMEngine:
             # the four gates side by side (i, f, c, o), each padded from `hidden` to `he` channels
             wxs = [sd[p + "Wx%s.weight" % g].contiguous() for g in GATES]
             whs = [sd[p + "Wh%s.weight" % g].contiguous() for g in GATES]
-            gate_offs = [gi * he for gi in range(4)]
-            bias = ops.zeros((4 * he,), torch.float32, dev)
+            # gate-major [i.. | f.. | c.. | o..], or unit-major [i0 f0 c0 o0 i1 ...] when the gates run in the recurrent
+            # convolution's epilogue (a 16-column accumulator chunk then holds four whole hidden units)
+            um = self.unit_major
+            gate_offs = list(range(4)) if um else [gi * he for gi in range(4)]
+            bias_host = torch.zeros(4 * he)
             for gi, g in enumerate(GATES):
-                bias[gi * he:gi * he + hidden].copy_(sd[p + "Wx%s.bias" % g])
+                b_g = sd[p + "Wx%s.bias" % g].detach().float().cpu()
+                if um:
+                    bias_host[gi:4 * hidden:4] = b_g
+                else:
+                    bias_host[gi * he:gi * he + hidden] = b_g
+            bias = bias_host.to(dev)
             ho, wo = hin // 2, win // 2
             if (hin + 4 - 5) // 2 + 1 != ho or (win + 4 - 5) // 2 + 1 != wo:
                 raise _lib.IvfError("ConvLSTM layer %d: odd input %dx%d (the reference asserts here too)" % (l, hin, win))
@@ -102,7 +117,7 @@ class CLSTMEngine:
             _lib.check(lib.ivf_fill_u32(_lib.handle(dev), _lib.ptr(ones), 16 * he, 0x3F800000, _lib.stream_ptr(dev)),
                        "ivf_fill_u32")  # 1.0f
             rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias, ones=ones)
-            gk = dict(co_offs=gate_offs, co_total=4 * he)
+            gk = dict(co_offs=gate_offs, co_total=4 * he, co_stride=4 if um else 1)
             if bf:  # stride-2 5x5 as a stride-1 3x3 over the 2-D space-to-depth record (12 -> 16 channels at l = 0)
                 xk = dict(s2d=(1, 2, 2), ci_stride=cin_eff, ceff_total=16 if l == 0 else None, **gk)
                 rec.update(wx_f=pack(wxs, mode, **xk), wx_d=pack(wxs, mode, dgrad=True, **xk), xk=(1, 3, 3),
@@ -220,11 +235,17 @@ class CLSTMEngine:
             m = B * rec["ho"] * rec["wo"]
             for t in range(T):
                 gx_t = self._step(rec["gx"], t)
+                c_prev = rec["c"][(t - 1) * B:t * B] if t > 0 else None
+                c_next, gact_t = rec["c"][t * B:(t + 1) * B], rec["gact"][t * B:(t + 1) * B].view(m, 4 * he)
+                if t > 0 and self.unit_major:  # convolution + gates + state update in one launch
+                    ops.conv_lstm_step(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, c_prev, c_next,
+                                       self._step(rec["h"], t), gact_t, (1, 5, 5), (0, 2, 2), plan=rec.get("plan_hf"))
+                    continue
                 if t > 0:
                     ops.conv3d(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx_t,
                                plan=rec.get("plan_hf"))
-                ops.clstm_gates_fwd(gx_t.buf.view(m, 4 * he), rec["c"][(t - 1) * B:t * B] if t > 0 else None,
-                                    rec["c"][t * B:(t + 1) * B], self._step(rec["h"], t).buf, rec["gact"][t * B:(t + 1) * B].view(m, 4 * he))
+                ops.clstm_gates_fwd(gx_t.buf.view(m, 4 * he), c_prev, c_next, self._step(rec["h"], t).buf, gact_t,
+                                    unit_major=self.unit_major)
             ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
                               rec["pooled"].buf, rec["argmax"], s2d=rec["s2d_out"])
         if self.w_fc is None:
@@ -262,7 +283,8 @@ class CLSTMEngine:
             for t in range(T - 1, -1, -1):
                 ops.clstm_gates_bwd(rec["gact"][t * B:(t + 1) * B].view(m, 4 * he),
                                     rec["c"][(t - 1) * B:t * B] if t > 0 else None, rec["c"][t * B:(t + 1) * B],
-                                    self._step(dH, t).buf, rec["dc"], self._step(rec["dpre"], t).buf)
+                                    self._step(dH, t).buf, rec["dc"], self._step(rec["dpre"], t).buf,
+                                    unit_major=self.unit_major)
                 if t > 0:
                     dprev = self._step(dH, t - 1)
                     if self.mode == "fp32":

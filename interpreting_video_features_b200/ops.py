@@ -338,18 +338,31 @@ def viz_triptych(clip, cam, pert, mask, out, draw_dots=True):
     return out
 
 
-def clstm_gates_fwd(pre, c_prev, c_next, h_next, gate_act):
+def clstm_gates_fwd(pre, c_prev, c_next, h_next, gate_act, unit_major=False):
     m, four_hid = pre.shape
     check(_lib.load().ivf_clstm_gates_fwd(_lib.handle(pre.device), _lib.dtype_code(h_next), ptr(pre),
                                           ptr(c_prev), m, four_hid // 4, ptr(c_next), ptr(h_next),
-                                          ptr(gate_act), _lib.stream_ptr(pre.device)), "ivf_clstm_gates_fwd")
+                                          ptr(gate_act), int(bool(unit_major)), _lib.stream_ptr(pre.device)),
+          "ivf_clstm_gates_fwd")
 
 
-def clstm_gates_bwd(gate_act, c_prev, c_next, dh, dc_io, dgates):
+def clstm_gates_bwd(gate_act, c_prev, c_next, dh, dc_io, dgates, unit_major=False):
     m, four_hid = gate_act.shape
     check(_lib.load().ivf_clstm_gates_bwd(_lib.handle(dh.device), _lib.dtype_code(dgates), ptr(gate_act),
                                           ptr(c_prev), ptr(c_next), ptr(dh), ptr(dc_io), m, four_hid // 4,
-                                          ptr(dgates), _lib.stream_ptr(dh.device)), "ivf_clstm_gates_bwd")
+                                          ptr(dgates), int(bool(unit_major)), _lib.stream_ptr(dh.device)),
+          "ivf_clstm_gates_bwd")
+
+
+def conv_lstm_step(h_prev, w, pre_x, c_prev, c_next, h_next, gate_act, kernel, pad_front, plan=None):
+    """The recurrent ConvLSTM step as one kernel (ivf_conv3d_lstm): h_prev Act [b,1,h,w,hid] bf16, w the packed
+    UNIT-MAJOR h-convolution weights, pre_x Act [b,1,h,w,4hid] fp32 (x-convolution + bias of this step); writes
+    c_next (fp32 [m,hid]), h_next (bf16 Act) and gate_act (fp32 [m,4hid])."""
+    d = conv_desc(h_prev, pre_x, kernel, (1, 1, 1), pad_front, 0, None, None, None, 0, plan=plan)
+    d.flags = 0
+    check(_lib.load().ivf_conv3d_lstm(_lib.handle(h_prev.buf.device), C.byref(d), ptr(h_prev.buf), ptr(w),
+                                      ptr(pre_x.buf), ptr(c_prev), ptr(c_next), ptr(h_next.buf), ptr(gate_act),
+                                      _lib.stream_ptr(h_prev.buf.device)), "ivf_conv3d_lstm")
 
 
 def bn_pool2d_fwd(x, scale, shift, y, argmax, s2d=False):

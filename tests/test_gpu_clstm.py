@@ -212,3 +212,31 @@ def test_convlstm_cell_forward_and_init_hidden(dev):
         h1, c1 = cell(x.to(dev), h.to(dev), c.to(dev))
         wh, wc = clstm_oracle._cell(sd, "clstm.cell0", x, h, c, 5, 2)
     assert rel_err(h1.cpu(), wh) < 1e-4 and rel_err(c1.cpu(), wc) < 1e-4
+
+
+def test_fused_recurrent_step_equals_unfused(dev, monkeypatch):
+    """ivf_conv3d_lstm (h-convolution with the gates, c/h update and the gate activations for the backward pass in
+    its epilogue, unit-major channels) against the convolution + gate-kernel pair of round 1 (gate-major): same
+    arithmetic on the same fp32 accumulators, so logits and mask gradients agree to rounding; and the unit-major
+    weight packing is the gate-major one permuted."""
+    from interpreting_video_features_b200 import engine as eng_mod
+    from oracle import synthetic
+    _, sd = build(32)
+    x = synthetic.clips(2, kind="square", t=32, h=120, w=160)
+    masks = torch.rand((2, 32), generator=torch.Generator().manual_seed(3))
+    res = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("IVF_CLSTM_FUSED", fused)
+        e = engine(sd, 32, 2, "bf16", dev)
+        assert e.unit_major == (fused == "1")
+        e.set_input(x.to(dev))
+        e.set_targets(torch.tensor([2, 4]))
+        logits = e.forward(masks.to(dev), "reverse").clone()
+        dm = e.backward().clone()
+        res.append((logits, dm, e.layers[0]["wh_f"].clone(), e.layers[0]["c"].clone()))
+    # the data-gradient GEMMs reduce over the gate channels in a different order (unit-major K): measured 5e-4
+    assert rel_err(res[0][0].cpu(), res[1][0].cpu()) < 1e-5 and rel_err(res[0][1].cpu(), res[1][1].cpu()) < 2e-3
+    assert rel_err(res[0][3].cpu(), res[1][3].cpu()) < 1e-6
+    um, gm = res[0][2], res[1][2]                      # [4*he, taps, k]
+    he = um.shape[0] // 4
+    assert torch.equal(um.view(he, 4, *um.shape[1:]).permute(1, 0, 2, 3).reshape(gm.shape), gm)
