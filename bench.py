@@ -413,10 +413,10 @@ def run_ours(args, rank, world, local_rank):
     peak = pk["bf16_tflops"] if args.mode == "bf16" else None
     peak_sus = pk.get("bf16_tflops_sustained") if args.mode == "bf16" else None
     traffic, traffic_src = None, None
-    tp = os.path.join(REPO, "profiles", "r01_step_metrics.json")
+    tp = os.path.join(REPO, "profiles", "r02_step_metrics.json")
     if os.path.exists(tp) and args.mode == "bf16":  # DRAM bytes of the conv launches of one step (ncu, committed)
         traffic = json.load(open(tp))["families"]["conv"]["dram_bytes"]
-        traffic_src = "profiles/r01_step_metrics.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the " \
+        traffic_src = "profiles/r02_step_metrics.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the " \
                       "conv launches of one step (8 clips), one ncu capture"
     roofline = {"bound": "tensor", "kernel": "conv_slab_kernel + conv_tc_kernel (tcgen05 implicit GEMMs, all conv launches of a step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
