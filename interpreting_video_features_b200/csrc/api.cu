@@ -11,6 +11,15 @@ void ivf_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* ivf_last_error(void) { return g_err; }
+
+bool ivf_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IVF_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 extern "C" const char* ivf_version(void) { return "ivf-b200 0.1 (sm_100a)"; }
 
 extern "C" int ivf_create(int device, ivf_handle** out) {

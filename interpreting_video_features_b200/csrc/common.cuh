@@ -79,6 +79,45 @@ struct ivf_device_guard {
 
 static inline int ivf_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A kernel that calls ivf_pdl_wait() before its first access to memory written by earlier kernels may be
+// launched with the programmatic-stream-serialisation attribute: its CTAs become resident and run their set-up
+// (barrier init, TMEM allocation, tensor-map prefetch, constant per-channel vectors) while the previous kernel of
+// the stream drains, and block at the wait until that kernel has completed and flushed.  ivf_pdl_trigger() at the
+// top of a kernel lets ITS dependents start the same way.  Both are no-ops for a normal launch.  Under stream
+// capture the attribute becomes a programmatic edge of the CUDA graph.  IVF_PDL=0 launches everything normally.
+__device__ __forceinline__ void ivf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ivf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool ivf_pdl_enabled();
+
+// launch `kernel` (which must contain ivf_pdl_wait) with or without the PDL attribute, optionally as CTA pairs
+template <typename... P, typename... A>
+inline cudaError_t ivf_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (ivf_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // ---- dtype helpers (device) -------------------------------------------------------
 __device__ __forceinline__ float ivf_to_float(float v) { return v; }
 __device__ __forceinline__ float ivf_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -135,6 +135,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
+  ivf_pdl_trigger();  // the next kernel of the stream may begin its own set-up
   if (threadIdx.x == 0) {
     tma_prefetch_map(&tmA);  // descriptor fetch overlaps the set-up
     tma_prefetch_map(&tmB);
@@ -184,6 +185,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (NCTA == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = tmem_base_slot;
+  ivf_pdl_wait();  // everything above touched constants only; activations / gradients of earlier kernels from here
 
   if (warp == 0) {
     // ===================== slab (A) TMA producer =====================
@@ -762,25 +764,8 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
   const size_t smem = (size_t)p.xch_off + (size_t)2 * 4 * p.mt * p.xch_seg * 4 + 1024;
   const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
-  if (NCTA == 1) {
-    conv_slab_kernel<KCH, 1, LSTM><<<grid, SLAB_THREADS, smem, st>>>(ma, mb, p, scale, shift, acc_in,
-                                                                     (const __nv_bfloat16*)mask_y, mask_scale, out);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(SLAB_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    IVF_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<KCH, 2, LSTM>, ma, mb, p, scale, shift, acc_in,
-                                (const __nv_bfloat16*)mask_y, mask_scale, out));
-  }
+  IVF_CUDA(ivf_launch(conv_slab_kernel<KCH, NCTA, LSTM>, dim3(grid), dim3(SLAB_THREADS), smem, st, NCTA, ma, mb, p, scale,
+                      shift, acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out));
   IVF_LAUNCHED(h);
   return IVF_OK;
 }

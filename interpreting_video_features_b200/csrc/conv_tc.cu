@@ -110,6 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int kiters = p.ntaps * p.cchunks;
 
+  ivf_pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_map(&tmA);  // descriptor fetch overlaps the set-up (first operands used to land ~2 us in)
     tma_prefetch_map(&tmB);
@@ -150,6 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = tmem_base_slot;
+  ivf_pdl_wait();  // set-up above touched constants only
   if (warp == 1) TC_TRACE(2);  // set-up done
 
   if (warp == 0) {
@@ -585,8 +587,8 @@ int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CU
   }
   size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024;
   dim3 grid(p.grid_x, ntiles);
-  conv_tc_kernel<KCH><<<grid, NUM_THREADS, smem, st>>>(ma, mb, ma2, mo, mo2, p, scale, shift, acc_in,
-                                                       (const __nv_bfloat16*)mask_y, mask_scale, out, out2);
+  IVF_CUDA(ivf_launch(conv_tc_kernel<KCH>, grid, dim3(NUM_THREADS), smem, st, 1, ma, mb, ma2, mo, mo2, p, scale, shift,
+                      acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out, out2));
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
