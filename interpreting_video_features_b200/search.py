@@ -286,6 +286,35 @@ class _Stager:
             self.events[self.k] = ev
 
 
+def assemble_results(local, mine, n_total, world, t, ncls, cam_shape=None, stats=None, device=None):
+    """Per-rank result rows [n_local, t + 2 + ncls (+ cam elements)] -> the result dict; with torch.distributed
+    initialised and world > 1 the rows of all ranks are all_gather-ed into clip order first (NCCL on the GPUs, gloo
+    in the CPU tests).  stats receives 'gather_seconds' (device-timed on CUDA) and 'gathered_bytes'."""
+    import torch.distributed as dist
+    indices = list(mine)
+    gather_s = 0.0
+    if world > 1 and dist.is_available() and dist.is_initialized():
+        timed = stats is not None and local.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(local.device))
+        full = gather_rows(local, mine, n_total, world)
+        if timed:
+            e1.record(torch.cuda.current_stream(local.device))
+            e1.synchronize()
+            gather_s = e0.elapsed_time(e1) * 1e-3
+        indices = list(range(n_total))
+    else:  # single rank, or a shard computed without a process group (rows follow `indices`)
+        full = local
+    if stats is not None:
+        stats.update(gather_seconds=gather_s, gathered_bytes=int(full.numel() * 4))
+    out = dict(time_mask=full[:, :t], freeze_score=full[:, t], reverse_score=full[:, t + 1],
+               probs_orig=full[:, t + 2:t + 2 + ncls], indices=indices)
+    if cam_shape is not None:
+        out["cam_lowres"] = full[:, t + 2 + ncls:].reshape(-1, *cam_shape)
+    return out
+
+
 def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, perturb="freeze",
                        init="central", threshold=0.9, micro_batch=8, lr=0.2, use_graph=True, rank=0, world=1,
                        device=None, groups=None, gradcam=False, n_total=None, stats=None):
@@ -351,23 +380,8 @@ def find_masks_batched(model, clips, targets, lam1=0.01, lam2=0.02, n_iter=300, 
         for k in model.avg_pool.kernel_size:  # the Mixed_5c map is exactly the average pool's window (engine check)
             cam_elems *= int(k)
         local = torch.zeros((0, T + 2 + ncls + (cam_elems if gradcam else 0)), device=device)
-    indices = mine
-    gather_s = 0.0
-    if world > 1 and dist.is_available() and dist.is_initialized():
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(torch.cuda.current_stream(device))
-        full = gather_rows(local, mine, N, world)
-        e1.record(torch.cuda.current_stream(device))
-        if stats is not None:
-            e1.synchronize()
-            gather_s = e0.elapsed_time(e1) * 1e-3
-        indices = list(range(N))
-    else:  # single rank, or a shard computed without a process group (rows follow `indices`)
-        full = local
+    out = assemble_results(local, mine, N, world, T, ncls, [int(k) for k in model.avg_pool.kernel_size] if gradcam else None,
+                           stats=stats, device=device)
     if stats is not None:
-        stats.update(gather_seconds=gather_s, micro_batches=n_mb, gathered_bytes=int(full.numel() * 4))
-    out = dict(time_mask=full[:, :T], freeze_score=full[:, T], reverse_score=full[:, T + 1],
-               probs_orig=full[:, T + 2:T + 2 + ncls], indices=indices)
-    if gradcam:
-        out["cam_lowres"] = full[:, T + 2 + ncls:].reshape(-1, *[int(k) for k in model.avg_pool.kernel_size])
+        stats["micro_batches"] = n_mb
     return out

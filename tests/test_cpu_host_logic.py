@@ -145,3 +145,44 @@ def test_gather_rows_world2_gloo(n):
     want = torch.tensor([[float(i), float(i) * 10] for i in range(n)])
     for _, full in outs:
         assert torch.equal(full, want)
+
+
+def _assemble_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, ncls, cam = 4, 3, [2, 1, 2]
+    idx = search.shard_indices(n, rank, world)
+    width = t + 2 + ncls + 4
+    local = torch.stack([torch.arange(width, dtype=torch.float32) + 100.0 * i for i in idx]) if idx else \
+        torch.zeros((0, width))
+    stats = {}
+    out = search.assemble_results(local, idx, n, world, t, ncls, cam, stats=stats)
+    q.put((rank, {k: (v if k == "indices" else v.clone()) for k, v in out.items()}, stats))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [5, 1])
+def test_sharded_result_rows_world2_gloo(n):
+    """The end of the sharded job (search.assemble_results): masks, scores, probabilities and low-resolution CAMs of
+    two ranks gathered into clip order - ragged shards (5 clips over 2 ranks) and a rank with no clip at all."""
+    import torch.multiprocessing as mp
+    s_ = socket.socket()
+    s_.bind(("127.0.0.1", 0))
+    port = s_.getsockname()[1]
+    s_.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_assemble_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    want = torch.stack([torch.arange(13, dtype=torch.float32) + 100.0 * i for i in range(n)])
+    for _, out, stats in outs:
+        assert out["indices"] == list(range(n))
+        assert torch.equal(out["time_mask"], want[:, :4]) and torch.equal(out["freeze_score"], want[:, 4])
+        assert torch.equal(out["reverse_score"], want[:, 5]) and torch.equal(out["probs_orig"], want[:, 6:9])
+        assert torch.equal(out["cam_lowres"], want[:, 9:].reshape(n, 2, 1, 2))
+        assert stats["gathered_bytes"] == n * 13 * 4
