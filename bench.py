@@ -306,7 +306,7 @@ def np_isfinite_or_nan(a):
     return np.all(np.isfinite(a) | np.isnan(a))
 
 
-def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10):
+def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10, with_cpu=False):
     """Config C3: ConvLSTM (KTH geometry, 2 layers, 5x5, conv stride 2, 32 hidden units as in the paper)
     temporal-mask search with the reverse perturbation on 32x120x160 clips: clip-iterations/s, iteration
     replayed from a CUDA graph, clips resident in HBM."""
@@ -318,8 +318,8 @@ def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10):
     m = quiet(CLSTM_4.Model, num_classes=6, nb_lstm_units=32, channels=3, conv_kernel_size=(5, 5), lstm_layers=2,
               step=32, conv_stride=2, image_size=(160, 120), effective_step=[7, 15, 23, 31],
               batch_normalization=True, dropout=0.5, add_softmax=True).to(dev).eval().set_mode(mode)
-    x = torch.stack([synthetic.uniform_clip(2000 + rank * clips_n + i, t=32, h=120, w=160)
-                     for i in range(clips_n)]).to(dev) / 255.0
+    x = torch.stack([synthetic.uniform_clip_u8(2000 + rank * clips_n + i, t=32, h=120, w=160)
+                     for i in range(clips_n)]).to(dev).float()  # 0..255, as pt/data_loader_kth.py:28 delivers
     eng = m._engine(x, batch=clips_n)
     ms = search.MaskSearch(eng, 0.02, 0.04, 0.2, 100, "reverse", 0.9, use_graph=True)
     ms.set_input(x)
@@ -343,10 +343,30 @@ def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10):
         t = torch.tensor([sec], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t[0])
+    pk, pk_src = peaks()
+    val = world * clips_n * steps / sec
+    cpu = None
+    if with_cpu and rank == 0:  # the oracle port of the reference loop (pt/FindMasksComparison_I3D_KTH.py:250-270), B = 1
+        from oracle import clstm_oracle, mask_oracle
+        sdc = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        om = clstm_oracle.Model(sdc, hidden=32, softmax=True, num_layers=2, kernel=5, conv_stride=2,
+                                effective_step=(7, 15, 23, 31))
+        x1 = x[:1].cpu()
+        tm = torch.tensor([-5.] * 8 + [5.] * 16 + [-5.] * 8, requires_grad=True)
+        t0 = time.perf_counter()
+        mask_oracle.mask_search(x1, om, 0, [0], tm, 0.02, 0.04, 2, mask_type="reverse")
+        dt = (time.perf_counter() - t0) / 2
+        cpu = {"value": 1.0 / dt, "unit": "clip-iterations/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "2 clip-iterations (B=1, 32x120x160, hidden 32) of the oracle port of the reference loop"}
     return {"metric": "clstm_mask_search_clip_iterations_per_sec", "unit": "clip-iterations/s",
-            "value": world * clips_n * steps / sec, "ms_per_step": sec / steps * 1e3, "clips_per_gpu": clips_n,
+            "value": val, "ms_per_step": sec / steps * 1e3, "clips_per_gpu": clips_n,
             "launches_per_step": int(ms.launches_per_iter),
             "algorithmic_gflop_per_clip_iteration": 76.7,
+            "roofline": {"bound": "tensor", "achieved": val / world * 76.7 / 1e3, "unit": "TFLOP/s",
+                         "peak": pk["bf16_tflops"], "frac": val / world * 76.7 / 1e3 / pk["bf16_tflops"],
+                         "peak_source": pk_src, "note": "whole step (62 sequential recurrent steps per layer and "
+                         "direction: launch and latency bound, not tensor bound)"},
+            "cpu_baseline": cpu,
             "workload": "C3: ConvLSTM (6 classes, hidden 32, 2 layers) temporal-mask search, reverse perturbation, "
                         "%d synthetic 32x120x160 clips per step" % clips_n}
 
@@ -501,7 +521,8 @@ def run_ours(args, rank, world, local_rank):
                     "engine the end-to-end job runs: %d clips per launch sequence" % mb}
     gradcam = gradcam_throughput(dev, rank, world, args.mode, with_cpu=(world == 1 and not args.no_cpu)) \
         if not args.no_gradcam else None
-    clstm = clstm_throughput(dev, rank, world, args.mode) if not args.no_clstm else None
+    clstm = clstm_throughput(dev, rank, world, args.mode, with_cpu=(world == 1 and not args.no_cpu)) \
+        if not args.no_clstm else None
 
     if rank != 0:
         return

@@ -545,3 +545,30 @@ def test_searcher_reuse_and_graphed_forward(dev, small_setup):
     for _ in range(2):
         graphed = eng.forward_graphed().clone()
         assert torch.equal(graphed, eager)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_dataparallel_two_devices_and_foreign_current_device(small_setup):
+    """nn.DataParallel over two devices, as the reference drivers wrap the model (pt/FindMasksComparison_I3D_smth.py:61):
+    every replica runs its own engine on its own device (handles are per device and thread, engines keyed by device);
+    and an engine built for cuda:1 works while cuda:0 is the current device (the C ABI switches to the handle's device
+    for the call: ADVICE r1)."""
+    import torch.nn as nn
+    from interpreting_video_features_b200.pt.models import I3D_doubled
+    sd, _, x, _ = small_setup
+    model = quiet(I3D_doubled.Model, 174, last_stride=1, stride_mod_layers="", softMax=1)
+    model.load_state_dict(sd)
+    model.avg_pool.kernel_size = [2, 2, 2]
+    single = model.to("cuda:0").eval()
+    x4 = torch.cat([x, x[:1]])
+    with torch.no_grad():
+        want = single(x4.to("cuda:0")).cpu()
+        dp = nn.DataParallel(single, device_ids=[0, 1])
+        got = dp(x4.to("cuda:0")).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-6)
+    torch.cuda.set_device(0)
+    eng = make_engine(sd, 3, "bf16", torch.device("cuda:1"), **SMALL)
+    eng.set_input(x.to("cuda:1"))
+    p1 = eng.forward(None).clone().cpu()
+    torch.testing.assert_close(p1, want[:3], rtol=1e-3, atol=1e-6)
+    assert torch.cuda.current_device() == 0
