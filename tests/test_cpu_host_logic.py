@@ -123,7 +123,7 @@ def _gather_worker(rank, world, port, n, q):
     idx = search.shard_indices(n, rank, world)
     local = torch.tensor([[float(i), float(i) * 10] for i in idx]).reshape(len(idx), 2)
     full = search.gather_rows(local, idx, n, world)
-    q.put((rank, full))
+    q.put((rank, full.numpy().copy()))  # by value: a shared-memory tensor's fd hand-over races with process exit
     dist.destroy_process_group()
 
 
@@ -144,7 +144,7 @@ def test_gather_rows_world2_gloo(n):
         p.join(timeout=60)
     want = torch.tensor([[float(i), float(i) * 10] for i in range(n)])
     for _, full in outs:
-        assert torch.equal(full, want)
+        assert torch.equal(torch.from_numpy(full), want)
 
 
 def _assemble_worker(rank, world, port, n, q):
@@ -158,7 +158,8 @@ def _assemble_worker(rank, world, port, n, q):
         torch.zeros((0, width))
     stats = {}
     out = search.assemble_results(local, idx, n, world, t, ncls, cam, stats=stats)
-    q.put((rank, {k: (v if k == "indices" else v.clone()) for k, v in out.items()}, stats))
+    # by value (numpy), not as shared-memory tensors: the fd hand-over of a tensor races with this process's exit
+    q.put((rank, {k: (v if k == "indices" else v.numpy().copy()) for k, v in out.items()}, stats))
     dist.destroy_process_group()
 
 
@@ -181,6 +182,7 @@ def test_sharded_result_rows_world2_gloo(n):
         p.join(timeout=60)
     want = torch.stack([torch.arange(13, dtype=torch.float32) + 100.0 * i for i in range(n)])
     for _, out, stats in outs:
+        out = {k: (v if k == "indices" else torch.from_numpy(v)) for k, v in out.items()}
         assert out["indices"] == list(range(n))
         assert torch.equal(out["time_mask"], want[:, :4]) and torch.equal(out["freeze_score"], want[:, 4])
         assert torch.equal(out["reverse_score"], want[:, 5]) and torch.equal(out["probs_orig"], want[:, 6:9])
