@@ -195,9 +195,13 @@ typedef struct ivf_pool_desc {
   int32_t in_ld, in_coff;
   int32_t out_ld, out_coff;
   int32_t mask_ld, mask_coff; /* backward epilogue: mask tensor indexed like the pool INPUT */
-  int32_t flags;              /* backward: IVF_EP_ACCUM | IVF_EP_MASK | IVF_EP_OUT_F32       */
+  int32_t flags;              /* backward: IVF_EP_ACCUM | IVF_EP_MASK | IVF_EP_OUT_F32; forward: IVF_POOL_NONNEG */
   int32_t dtype;
 } ivf_pool_desc;
+/* forward flag: the caller vouches that no input element is negative (the input is a ReLU output, as at every
+ * max-pool of pt/models/I3D_doubled.py:351-380): the packed bf16 kernels then compare bit patterns directly.
+ * With the flag set and a negative input the result is unspecified. */
+#define IVF_POOL_NONNEG 64
 
 int ivf_maxpool3d_fwd(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out,
                       uint8_t* argmax, void* stream);

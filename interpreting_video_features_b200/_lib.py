@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libivf.so")
 
 IVF_F32, IVF_BF16, IVF_U8 = 0, 1, 2
 EP_AFFINE, EP_RELU, EP_ACCUM, EP_MASK, EP_OUT_F32, EP_LSTM = 1, 2, 4, 8, 16, 32
+POOL_NONNEG = 64  # ivf_pool_desc.flags, forward: no negative input (IVF_POOL_NONNEG)
 PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D_BF16, PFMT_TBHWC_F32, PFMT_S2D2_BF16 = 0, 1, 2, 3, 4
 PACK_KMAJOR, PACK_TAPMAJOR = 0, 1
 

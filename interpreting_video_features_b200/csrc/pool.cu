@@ -7,7 +7,11 @@
 // Bandwidth-bound: one thread per (pixel, 16-byte channel vector), coalesced along C.
 #include "common.cuh"
 
+#include <climits>
+
 namespace {
+
+#define COMMA ,
 
 template <typename T, int VEC>
 __device__ __forceinline__ void load_vec(const T* p, float (&f)[VEC]) {
@@ -37,6 +41,7 @@ __device__ __forceinline__ void store_vec(T* p, const float (&f)[VEC]) {
 // compiler unroll them; GEN = true keeps the fully general runtime-geometry path.
 template <int KD, int KH, int KW, int SD, int SH, int SW>
 struct PoolGeo {
+  enum : int { KD_ = KD, KH_ = KH, KW_ = KW, SD_ = SD, SH_ = SH, SW_ = SW };
   __device__ static int kd(const ivf_pool_desc&) { return KD; }
   __device__ static int kh(const ivf_pool_desc&) { return KH; }
   __device__ static int kw(const ivf_pool_desc&) { return KW; }
@@ -62,6 +67,45 @@ __device__ __forceinline__ uint8_t relu_byte(const uint4& raw) {
                    ((m2 >> 11) & 32u) | ((m3 & 1u) << 6) | ((m3 >> 9) & 128u));
 }
 
+// --- integer keys.  "First maximum in scan order wins" is one integer max per element when the bf16 value and
+// the tap share a 32-bit key: [bf16 bits made monotone as a signed integer : 16][255 - tap : 16].  Positive floats
+// already order like their bit patterns; negative ones get their 15 magnitude bits flipped.  A later tap carries a
+// smaller low half, so it only takes over when its value is strictly greater.  A (positive) NaN has the largest
+// pattern and wins like in ATen (with several NaNs in one window the first is kept, ATen keeps the last); -0
+// orders below +0 (ATen: equal) - neither occurs in a ReLU network.  ~4 instructions per element and tap
+// (PRMT, SHF, LOP3, IMNMX) against ~6 of the compare-to-mask form, which also needed two 16-bit lanes per word.
+// NONNEG (IVF_POOL_NONNEG: the caller vouches that no input is negative - ReLU outputs) skips the flip: 2
+// instructions per element and tap.
+template <bool NONNEG>
+__device__ __forceinline__ int pool_key_flip(int k) {
+  return NONNEG ? k : (k ^ ((k >> 31) & 0x7fff0000));
+}
+// keys of the two bf16 of a word; tapc = 255 - tap
+template <bool NONNEG>
+__device__ __forceinline__ void pool_keys_max(const uint4& raw, uint32_t tapc, int (&best)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int lo = pool_key_flip<NONNEG>((int)__byte_perm(w[i], tapc, 0x1054));
+    const int hi = pool_key_flip<NONNEG>((int)__byte_perm(w[i], tapc, 0x3254));
+    best[2 * i] = max(best[2 * i], lo);
+    best[2 * i + 1] = max(best[2 * i + 1], hi);
+  }
+}
+// eight keys -> eight bf16 values and eight arg-max bytes
+template <bool NONNEG>
+__device__ __forceinline__ void pool_keys_unpack(const int (&k)[8], uint4& val, uint2& idx) {
+  uint32_t v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    v[i] = __byte_perm((uint32_t)pool_key_flip<NONNEG>(k[2 * i]), (uint32_t)pool_key_flip<NONNEG>(k[2 * i + 1]), 0x7632);
+  val = make_uint4(v[0], v[1], v[2], v[3]);
+  const uint32_t a = __byte_perm((uint32_t)k[0], (uint32_t)k[1], 0x0040), b = __byte_perm((uint32_t)k[2], (uint32_t)k[3], 0x0040);
+  const uint32_t c = __byte_perm((uint32_t)k[4], (uint32_t)k[5], 0x0040), e = __byte_perm((uint32_t)k[6], (uint32_t)k[7], 0x0040);
+  idx.x = ~__byte_perm(a, b, 0x5410);
+  idx.y = ~__byte_perm(c, e, 0x5410);
+}
+
 // bf16 x 8 channels, packed arithmetic, one block row per output row.  The generic kernels below spend
 // ~5 instructions per channel per tap (convert, compare, two selects) plus 64-bit index arithmetic per
 // tap and are INSTRUCTION bound, not memory bound (ncu: 134 us for the 48 MB Mixed_3c pool; an
@@ -72,7 +116,8 @@ __device__ __forceinline__ uint8_t relu_byte(const uint4& raw) {
 //     two LOP3 on the 2 x 16-bit running index — ATen's "first maximum wins, NaN wins" rule; values are
 //     never converted.
 // Host guarantees every element offset fits 31 bits.
-template <typename G>
+// MODE 0: any input; 1: any input + ReLU' bit mask of the input (relu_bits); 2: non-negative input.
+template <typename G, int MODE>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                           uint8_t* __restrict__ argmax, uint8_t* __restrict__ relu_bits, int rows) {
@@ -89,14 +134,9 @@ maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in,
   const int zd0 = od * SD - d.pd, zh0 = oh * SH - d.ph, zw0 = ow * SW - d.pw;
   const int pix0 = ((n * d.id + zd0) * d.ih + zh0) * d.iw + zw0;  // window origin (may lie in the padding)
   const __nv_bfloat16* p0 = in + (long long)pix0 * d.in_ld + d.in_coff + c;
-  __nv_bfloat162 best[4];
-  uint32_t bidx[4];
-  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+  int best[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    best[i] = ninf;
-    bidx[i] = 0u;
-  }
+  for (int i = 0; i < 8; ++i) best[i] = INT_MIN;  // below every key: the first tap is always taken
 #pragma unroll
   for (int a = 0; a < KD; ++a) {
     const bool dok = (unsigned)(zd0 + a) < (unsigned)d.id;
@@ -106,40 +146,87 @@ maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in,
       const int delta_row = ((a * d.ih + b) * d.iw) * d.in_ld;
 #pragma unroll
       for (int e = 0; e < KW; ++e) {
-        const uint32_t tap2 = (uint32_t)((a * KH + b) * KW + e) * 0x00010001u;
+        const uint32_t tapc = 255u - (uint32_t)((a * KH + b) * KW + e);
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
         if (hok && (unsigned)(zw0 + e) < (unsigned)d.iw) {
           raw = *reinterpret_cast<const uint4*>(p0 + delta_row + e * d.in_ld);
           // ReLU' bit mask of the INPUT for the backward pass (one bit per element instead of re-reading the
           // producer's bf16 output there): every input element belongs to exactly one window origin - the taps
           // below the stride - so that output's thread, which holds the element anyway, writes its byte
-          if (relu_bits && a < SD && b < SH && e < SW) {
+          if (MODE == 1 && a < SD && b < SH && e < SW) {
             const int ipix = pix0 + (a * d.ih + b) * d.iw + e;
             relu_bits[(long long)ipix * cv + (c >> 3)] = relu_byte(raw);
           }
         }
-        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t m = __hgt2_mask(v[i], best[i]) | __hneu2_mask(v[i], v[i]);
-          best[i] = __hmax2_nan(best[i], v[i]);
-          bidx[i] = (bidx[i] & ~m) | (tap2 & m);
-        }
+        pool_keys_max<MODE == 2>(raw, tapc, best);
       }
     }
   }
   const int opix = row * d.ow + ow;
   uint4 o;
-  o.x = *reinterpret_cast<uint32_t*>(&best[0]);
-  o.y = *reinterpret_cast<uint32_t*>(&best[1]);
-  o.z = *reinterpret_cast<uint32_t*>(&best[2]);
-  o.w = *reinterpret_cast<uint32_t*>(&best[3]);
+  uint2 pk;
+  pool_keys_unpack<MODE == 2>(best, o, pk);
   *reinterpret_cast<uint4*>(out + (long long)opix * d.out_ld + d.out_coff + c) = o;
-  if (argmax) {
-    uint2 pk;  // 2 x 16-bit indices per word -> bytes
-    pk.x = (bidx[0] & 0xffu) | ((bidx[0] >> 8) & 0xff00u) | ((bidx[1] & 0xffu) << 16) | ((bidx[1] & 0xff0000u) << 8);
-    pk.y = (bidx[2] & 0xffu) | ((bidx[2] >> 8) & 0xff00u) | ((bidx[3] & 0xffu) << 16) | ((bidx[3] & 0xff0000u) << 8);
-    *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
+  if (argmax) *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
+}
+
+// Forward of the stride-2 stage pools: like the kernel above, but a thread keeps its (column, 8 channels) for a
+// SEGMENT of consecutive output rows.  The one-row-per-block form executed ~450 instructions per output vector of
+// which ~250 were index arithmetic and bounds set-up (ncu: issue bound, 66 % issue slots), and its blocks re-read each
+// other's halo rows from the other die's L2 (dram__bytes_read = 2x the tensor); here the set-up is paid once per
+// segment and consecutive rows of a slice stay on one SM.
+template <typename G, bool NONNEG>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_rows_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                        uint8_t* __restrict__ argmax, int items, int rseg, int nseg) {
+  const int item = blockIdx.z * gridDim.y + blockIdx.y;  // (clip, output depth, row segment)
+  if (item >= items) return;
+  const int cv = d.c >> 3;
+  const int el = blockIdx.x * 256 + threadIdx.x;
+  if (el >= d.ow * cv) return;
+  constexpr int KD = G::KD_, KH = G::KH_, KW = G::KW_, SD = G::SD_, SH = G::SH_, SW = G::SW_;
+  const int ow = el / cv, c = (el - ow * cv) << 3;
+  const int seg = item % nseg;
+  const int t = item / nseg;
+  const int od = t % d.od, n = t / d.od;
+  const int oh0 = seg * rseg, oh1 = min(d.oh, oh0 + rseg);
+  const int zd0 = od * SD - d.pd, zw0 = ow * SW - d.pw;
+  bool wok[KW], dok[KD];
+#pragma unroll
+  for (int e = 0; e < KW; ++e) wok[e] = (unsigned)(zw0 + e) < (unsigned)d.iw;
+#pragma unroll
+  for (int a = 0; a < KD; ++a) dok[a] = (unsigned)(zd0 + a) < (unsigned)d.id;
+  const int row_elems = d.iw * d.in_ld;
+  const int plane_elems = d.ih * row_elems;
+  // column of this thread in plane zd0, row 0 (only dereferenced where the tap is inside the tensor)
+  const __nv_bfloat16* pcol = in + ((long long)(n * d.id + zd0) * d.ih * d.iw + zw0) * d.in_ld + d.in_coff + c;
+  const int out_row0 = ((n * d.od + od) * d.oh) * d.ow + ow;
+#pragma unroll 1
+  for (int oh = oh0; oh < oh1; ++oh) {
+    const int zh0 = oh * SH - d.ph;
+    int best[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] = INT_MIN;
+#pragma unroll
+    for (int a = 0; a < KD; ++a) {
+#pragma unroll
+      for (int b = 0; b < KH; ++b) {
+        const bool rok = dok[a] && (unsigned)(zh0 + b) < (unsigned)d.ih;
+        const __nv_bfloat16* prow = pcol + (long long)a * plane_elems + (long long)(zh0 + b) * row_elems;
+#pragma unroll
+        for (int e = 0; e < KW; ++e) {
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
+          if (rok && wok[e]) raw = *reinterpret_cast<const uint4*>(prow + e * d.in_ld);
+          pool_keys_max<NONNEG>(raw, 255u - (uint32_t)((a * KH + b) * KW + e), best);
+        }
+      }
+    }
+    const int opix = out_row0 + oh * d.ow;
+    uint4 o;
+    uint2 pk;
+    pool_keys_unpack<NONNEG>(best, o, pk);
+    *reinterpret_cast<uint4*>(out + (long long)opix * d.out_ld + d.out_coff + c) = o;
+    if (argmax) *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
   }
 }
 
@@ -150,20 +237,10 @@ maxpool_fwd_bf16x8_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in,
 // order is (depth, row, column), so "first maximum wins" composes: within a plane the first tap wins, across
 // planes a later plane must be strictly greater (or NaN) to take over - the same rule the flat scan applies.
 struct PlaneMax {
-  __nv_bfloat162 v[4];
-  uint32_t idx[4];  // 2 x 16-bit tap index within the plane
+  int k[8];  // integer keys (pool_keys), low half = 255 - tap within the plane
 };
 
-__device__ __forceinline__ void pool_take(__nv_bfloat162 (&best)[4], uint32_t (&bidx)[4], const __nv_bfloat162* v,
-                                          const uint32_t* vidx) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t m = __hgt2_mask(v[i], best[i]) | __hneu2_mask(v[i], v[i]);
-    best[i] = __hmax2_nan(best[i], v[i]);
-    bidx[i] = (bidx[i] & ~m) | (vidx[i] & m);
-  }
-}
-
+template <bool NONNEG>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_s1col_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                          uint8_t* __restrict__ argmax, int rows, int dseg) {
@@ -179,8 +256,6 @@ maxpool_fwd_s1col_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, 
   const int seg = t % nseg, n = t / nseg;
   const int od0 = seg * dseg, od1 = min(d.od, od0 + dseg);
   const int zh0 = oh - d.ph, zw0 = ow - d.pw;
-  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
-  const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
   // tap validity in the plane (block-uniform rows, per-thread columns)
   bool hok[3], wok[3];
 #pragma unroll
@@ -193,10 +268,7 @@ maxpool_fwd_s1col_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, 
   auto plane_max = [&](int zd, PlaneMax& pm) {
     if ((unsigned)zd >= (unsigned)d.id) {  // a plane of padding: all zeros, first tap wins
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pm.v[i] = zero2;
-        pm.idx[i] = 0u;
-      }
+      for (int i = 0; i < 8; ++i) pm.k[i] = 255;
       return;
     }
     const __nv_bfloat16* pz = p00 + (long long)zd * plane_stride;
@@ -209,45 +281,26 @@ maxpool_fwd_s1col_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, 
         if (hok[b] && wok[e]) raw[b * 3 + e] = *reinterpret_cast<const uint4*>(pz + (b * d.iw + e) * d.in_ld);
       }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      pm.v[i] = ninf;
-      pm.idx[i] = 0u;
-    }
+    for (int i = 0; i < 8; ++i) pm.k[i] = INT_MIN;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const uint32_t tap2[4] = {k * 0x00010001u, k * 0x00010001u, k * 0x00010001u, k * 0x00010001u};
-      pool_take(pm.v, pm.idx, reinterpret_cast<const __nv_bfloat162*>(&raw[k]), tap2);
-    }
+    for (int k = 0; k < 9; ++k) pool_keys_max<NONNEG>(raw[k], 255u - (uint32_t)k, pm.k);
   };
   PlaneMax pa, pb, pc;
   plane_max(od0 - d.pd, pa);
   plane_max(od0 - d.pd + 1, pb);
   for (int od = od0; od < od1; ++od) {
     plane_max(od - d.pd + 2, pc);
-    __nv_bfloat162 best[4];
-    uint32_t bidx[4], ib[4], ic[4];
+    int best[8];
+    // taps of the second / third plane are 9 / 18 later in scan order: their low halves drop by as much (no
+    // borrow: 255 - 8 - 18 > 0), so an earlier plane keeps a tie
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      best[i] = pa.v[i];
-      bidx[i] = pa.idx[i];
-      ib[i] = pb.idx[i] + 9u * 0x00010001u;
-      ic[i] = pc.idx[i] + 18u * 0x00010001u;
-    }
-    pool_take(best, bidx, pb.v, ib);
-    pool_take(best, bidx, pc.v, ic);
+    for (int i = 0; i < 8; ++i) best[i] = max(max(pa.k[i], pb.k[i] - 9), pc.k[i] - 18);
     const int opix = ((n * d.od + od) * d.oh + oh) * d.ow + ow;
     uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&best[0]);
-    o.y = *reinterpret_cast<uint32_t*>(&best[1]);
-    o.z = *reinterpret_cast<uint32_t*>(&best[2]);
-    o.w = *reinterpret_cast<uint32_t*>(&best[3]);
+    uint2 pk;
+    pool_keys_unpack<NONNEG>(best, o, pk);
     *reinterpret_cast<uint4*>(out + (long long)opix * d.out_ld + d.out_coff + c) = o;
-    if (argmax) {
-      uint2 pk;  // 2 x 16-bit indices per word -> bytes
-      pk.x = (bidx[0] & 0xffu) | ((bidx[0] >> 8) & 0xff00u) | ((bidx[1] & 0xffu) << 16) | ((bidx[1] & 0xff0000u) << 8);
-      pk.y = (bidx[2] & 0xffu) | ((bidx[2] >> 8) & 0xff00u) | ((bidx[3] & 0xffu) << 16) | ((bidx[3] & 0xff0000u) << 8);
-      *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
-    }
+    if (argmax) *reinterpret_cast<uint2*>(argmax + (long long)opix * d.c + c) = pk;
     pa = pb;
     pb = pc;
   }
@@ -854,6 +907,7 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
   if (vec_ok(d, V, in, out, argmax)) {
     long long total = opix * (d->c / V);
     if constexpr (sizeof(T) == 2) {
+      const bool nonneg = (d->flags & IVF_POOL_NONNEG) != 0;
       if (fits31(d)) {  // row-block packed kernel
         static const bool col_on = [] {
           const char* e = getenv("IVF_POOL_S1COL");
@@ -868,14 +922,59 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
           const int dseg = (d->od + segs - 1) / segs;
           const int nseg = (d->od + dseg - 1) / dseg;
           const int rows = d->n * nseg * d->oh;
-          maxpool_fwd_s1col_kernel<<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
-              *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows, dseg);
+          if (nonneg)
+            maxpool_fwd_s1col_kernel<true><<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
+                *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows, dseg);
+          else
+            maxpool_fwd_s1col_kernel<false><<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
+                *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, rows, dseg);
           IVF_LAUNCHED(h);
           return IVF_OK;
         }
+        static const bool rows_on = [] {
+          const char* e = getenv("IVF_POOL_ROWS");
+          return !e || atoi(e) != 0;
+        }();
+        if (rows_on && !relu_bits && d->sh == 2 && d->sw == 2 && d->oh >= 4) {
+          // row segments: enough threads for ~1.5 full-occupancy waves, at least two rows per thread
+          const long long per_seg = (long long)d->n * d->od * d->ow * (d->c / V);
+          long long want = ((long long)h->sm_count * 2048 * 3 / 2 + per_seg - 1) / per_seg;
+          int nseg = (int)std::max<long long>(1, std::min<long long>(want, d->oh / 2));
+          const int rseg = (d->oh + nseg - 1) / nseg;
+          nseg = (d->oh + rseg - 1) / rseg;
+          const int items = d->n * d->od * nseg;
+          const dim3 rgrid = row_grid(items, d->ow * (d->c / V));
+          bool done = true;
+#define IVF_FWD_ROWS(GEO)                                                                                          \
+  do {                                                                                                             \
+    if (nonneg)                                                                                                    \
+      maxpool_fwd_rows_kernel<GEO, true><<<rgrid, threads, 0, st>>>(*d, (const __nv_bfloat16*)in,                  \
+                                                                    (__nv_bfloat16*)out, argmax, items, rseg, nseg); \
+    else                                                                                                           \
+      maxpool_fwd_rows_kernel<GEO, false><<<rgrid, threads, 0, st>>>(*d, (const __nv_bfloat16*)in,                 \
+                                                                     (__nv_bfloat16*)out, argmax, items, rseg, nseg); \
+  } while (0)
+          if (d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1) IVF_FWD_ROWS(PoolGeo<1 COMMA 3 COMMA 3 COMMA 1 COMMA 2 COMMA 2>);
+          else if (d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 2) IVF_FWD_ROWS(PoolGeo<3 COMMA 3 COMMA 3 COMMA 2 COMMA 2 COMMA 2>);
+          else if (d->kd == 2 && d->kh == 2 && d->kw == 2 && d->sd == 2) IVF_FWD_ROWS(PoolGeo<2 COMMA 2 COMMA 2 COMMA 2 COMMA 2 COMMA 2>);
+          else done = false;
+#undef IVF_FWD_ROWS
+          if (done) {
+            IVF_LAUNCHED(h);
+            return IVF_OK;
+          }
+        }
         const int rows = d->n * d->od * d->oh;
-        IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G><<<row_grid(rows, d->ow * (d->c / V)), threads, 0, st>>>(
-            *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, relu_bits, rows)));
+        const dim3 fgrid = row_grid(rows, d->ow * (d->c / V));
+        if (relu_bits)
+          IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G, 1><<<fgrid, threads, 0, st>>>(
+              *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, relu_bits, rows)));
+        else if (nonneg)
+          IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G, 2><<<fgrid, threads, 0, st>>>(
+              *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, nullptr, rows)));
+        else
+          IVF_POOL_GEO_DISPATCH((maxpool_fwd_bf16x8_kernel<G, 0><<<fgrid, threads, 0, st>>>(
+              *d, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, argmax, nullptr, rows)));
         IVF_LAUNCHED(h);
         return IVF_OK;
       }

@@ -244,6 +244,7 @@ class I3DEngine:
         self.fwd_ops, self.bwd_ops = [], []
         self._lane = 0
         self.use_streams = os.environ.get("IVF_STREAMS", "1") != "0"
+        self.pool_premask = os.environ.get("IVF_POOL_PREMASK", "1") != "0"
         self._side = None
         self.acts = {}  # endpoint -> Act (forward output)
         # each stage: dict(out=Act, scale=tensor|None (None: pool-type output), gout=Act)
@@ -318,8 +319,9 @@ class I3DEngine:
                 if (mode == "bf16" and x.c % 8 == 0 and min(s[1:]) >= 2 and stages and stages[-1]["scale"] is not None
                         and os.environ.get("IVF_POOL_BITS", "0") != "0"):
                     bits = torch.empty((x.pixels, x.c // 8), dtype=torch.uint8, device=dev)
+                # every pool of the network reads ReLU outputs (units, Inception concats, pools of those)
                 self.fwd_ops.append((0, lambda x=x, out=out, am=am, k=k, s=s, pads=pads, bits=bits:
-                                     ops.maxpool3d_fwd(x, out, am, k, s, pads, relu_bits=bits)))
+                                     ops.maxpool3d_fwd(x, out, am, k, s, pads, relu_bits=bits, nonneg=True)))
                 stages.append(dict(kind="pool", name=name, x=x, out=out, scale=None, gout=out.like(), argmax=am,
                                    k=k, s=s, pads=pads, bits=bits))
             else:  # Inception module
@@ -371,17 +373,33 @@ class I3DEngine:
         self.bwd_ops.append((0, lambda: ops.head_bwd(last["gout"], self.w_logits, self.softmax, self.probs,
                                                      self.dprobs, mask=last["out"], mask_scale=last["scale"])))
 
-    def _emit_stage_bwd(self, i, raw_out=None):
+    def _emit_stage_bwd(self, i, raw_out=None, premask=True):
         """Append the data-gradient launches of stage i to self.bwd_ops.  Normally its input gradient goes to the
         previous stage's `gout` with that stage's ReLU'/BN' applied; raw_out (an fp32 Act shaped like the previous
-        stage's output) receives the UNMASKED gradient w.r.t. that output instead - Grad-CAM's `grads_val`."""
+        stage's output) receives the UNMASKED gradient w.r.t. that output instead - Grad-CAM's `grads_val`.
+
+        Max-pool after a ReLU unit (the four stage pools): the pool routes each window's gradient to its arg-max
+        element only, and that element is positive exactly when the POOLED value is (inputs are ReLU outputs, the
+        padding is zero).  So the producer's ReLU'/BN' is applied one stage earlier, by the pool's CONSUMER, with the
+        pooled output as the mask (an eighth / a quarter of the pool's input), and the pool's own backward is pure
+        routing: it no longer reads the producer's output.  premask=False keeps the unmasked `gout` (needed when the
+        pool's backward feeds a raw Grad-CAM gradient)."""
         stages, mode = self.stages, self.mode
         st = stages[i]
         prv = stages[i - 1] if i > 0 else None
+
+        def pre(j):  # stage j is a pool whose consumer applies the ReLU'/BN' of the pool's producer
+            return (self.pool_premask and j >= 1 and stages[j]["kind"] == "pool"
+                    and stages[j - 1]["scale"] is not None)
+
         if raw_out is not None:
             g_in, mask, mscale = raw_out, None, None
         elif prv is None:
             g_in, mask, mscale = self.g_xin, None, None
+        elif premask and pre(i - 1):
+            g_in, mask, mscale = prv["gout"], prv["out"], stages[i - 2]["scale"]
+        elif st["kind"] == "pool" and pre(i):
+            g_in, mask, mscale = prv["gout"], None, None  # already applied to this pool's gout by its consumer
         else:
             g_in = prv["gout"]
             mask = prv["out"] if prv["scale"] is not None else None
@@ -416,7 +434,8 @@ class I3DEngine:
         try:
             self._emit_head_bwd()
             for i in range(len(self.stages) - 1, idx, -1):
-                self._emit_stage_bwd(i, raw_out=raw if i == idx + 1 else None)
+                # the raw gradient behind a stage pool needs that pool's gout WITHOUT the producer's ReLU'/BN'
+                self._emit_stage_bwd(i, raw_out=raw if i == idx + 1 else None, premask=(i != idx + 2))
             prog = self.bwd_ops
         finally:
             self.bwd_ops = saved
@@ -452,7 +471,7 @@ class I3DEngine:
         pads = tuple(same_pad(sz, 3, 1)[0] for sz in (x.d, x.h, x.w))
         self.fwd_ops.append(("fork",))
         self._lane = 3
-        self.fwd_ops.append((3, lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads)))
+        self.fwd_ops.append((3, lambda: ops.maxpool3d_fwd(x, t3, am, k3, (1, 1, 1), pads, nonneg=True)))
         add_unit_fwd(u["b3b"], t3, out.slice(c0 + c2 + c4, c5))
         self._lane = 0
         if fuse_b0:

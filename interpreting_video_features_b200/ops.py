@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (EP_ACCUM, EP_AFFINE, EP_MASK, EP_OUT_F32, EP_RELU, IVF_BF16, IVF_F32,
+from ._lib import (EP_ACCUM, EP_AFFINE, EP_MASK, EP_OUT_F32, EP_RELU, IVF_BF16, IVF_F32, POOL_NONNEG,
                    PFMT_NCDHW_F32, PFMT_NDHWC_F32, PFMT_S2D2_BF16, PFMT_S2D_BF16, PFMT_TBHWC_F32, ConvDesc,
                    PoolDesc, check, ptr)
 
@@ -187,10 +187,11 @@ def _pool_desc(x, out, kernel, stride, pad_front, mask=None, flags=0):
     return d
 
 
-def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front, relu_bits=None):
+def maxpool3d_fwd(x, out, argmax, kernel, stride, pad_front, relu_bits=None, nonneg=False):
     """relu_bits: optional uint8 [x.pixels, c/8] that receives one bit per input element (element > 0) for the
-    backward pass (ivf_maxpool3d_fwd_bits)."""
-    d = _pool_desc(x, out, kernel, stride, pad_front)
+    backward pass (ivf_maxpool3d_fwd_bits).  nonneg: the caller vouches that x holds no negative value (a ReLU
+    output): IVF_POOL_NONNEG, the packed bf16 kernels then order bit patterns directly."""
+    d = _pool_desc(x, out, kernel, stride, pad_front, flags=POOL_NONNEG if nonneg else 0)
     d.dtype = _lib.dtype_code(x.buf)
     check(_lib.load().ivf_maxpool3d_fwd_bits(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(out.buf),
                                              ptr(argmax), ptr(relu_bits), _lib.stream_ptr(x.buf.device)), "ivf_maxpool3d_fwd")

@@ -256,7 +256,15 @@ def test_backward_link_by_link(dev, small_setup, mode, perturb):
             gx = conv_in_grad(n + ".b0", xv.shape, dz[:, :c0]) + conv_in_grad(n + ".b1a", xv.shape, e_t1) + \
                 conv_in_grad(n + ".b2a", xv.shape, e_t2) + pool_in_grad(xv, e_t3, (3, 3, 3), (1, 1, 1))
         if prv is not None:
-            if prv["scale"] is not None:
+            pre = lambda j: (eng.pool_premask and j >= 1 and stages[j]["kind"] == "pool"
+                             and stages[j - 1]["scale"] is not None)
+            if pre(i - 1):
+                # the consumer of a stage pool applies the ReLU'/BN' of the pool's PRODUCER, masked by the pooled
+                # value (the routed element is positive iff the pooled value is; engine._emit_stage_bwd)
+                gx = gx * (xv > 0) * stages[i - 2]["scale"].cpu().view(1, -1, 1, 1, 1)
+            elif st["kind"] == "pool" and pre(i):
+                pass  # pure routing: the mask is already in this pool's gout
+            elif prv["scale"] is not None:
                 gx = gx * (xv > 0) * prv["scale"].cpu().view(1, -1, 1, 1, 1)
             got = prv["gout"].ncdhw().cpu()
         elif mode == "bf16":  # space-to-depth record [b][t/2][h/2][w/2][32] -> NCDHW

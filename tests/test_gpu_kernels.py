@@ -325,7 +325,10 @@ def test_conv1x1_two_destinations_and_two_sources(dev, case):
 @pytest.mark.parametrize("case", [((1, 3, 3), (1, 2, 2), (4, 13, 12), 64), ((3, 3, 3), (2, 2, 2), (5, 9, 10), 40),
                                   ((2, 2, 2), (2, 2, 2), (4, 7, 6), 24), ((3, 3, 3), (1, 1, 1), (2, 7, 7), 48),
                                   ((3, 3, 3), (1, 1, 1), (3, 5, 4), 6)])
-def test_maxpool_same_zero_padding(dev, dt, case):
+@pytest.mark.parametrize("nonneg", [False, True])
+def test_maxpool_same_zero_padding(dev, dt, case, nonneg):
+    """nonneg: ReLU-output-like input with the IVF_POOL_NONNEG promise (what the engine passes) - many exact zeros
+    and repeated values, so that ties between real elements and with the zero padding decide the routing."""
     from interpreting_video_features_b200 import ops
     from interpreting_video_features_b200.ops import Act, same_pad
     from oracle import i3d_oracle
@@ -334,6 +337,8 @@ def test_maxpool_same_zero_padding(dev, dt, case):
     # mix of negatives and zeros so that padded zeros and ties take part (post-ReLU maps are like this)
     x = torch.randn((2, c) + dhw, generator=g)
     x = torch.where(torch.rand(x.shape, generator=g) < 0.4, torch.zeros_like(x), x)
+    if nonneg:
+        x = torch.round(torch.relu(x) * 4) / 4  # few distinct values: ties between real elements
     x = x.to(dt).float().requires_grad_()
     y = i3d_oracle.maxpool_same(x, k, s)
     gy = torch.randn(y.shape, generator=g).to(dt).float()
@@ -343,7 +348,7 @@ def test_maxpool_same_zero_padding(dev, dt, case):
     xa = to_act(x.detach().to(dev), dt)
     out = Act.empty(2, *od, c, dt, dev)
     am = torch.empty((out.pixels, c), dtype=torch.uint8, device=dev)
-    ops.maxpool3d_fwd(xa, out, am, k, s, pf)
+    ops.maxpool3d_fwd(xa, out, am, k, s, pf, nonneg=nonneg)
     assert torch.equal(out.ncdhw().cpu(), y.detach()), "max-pool forward must be exact"
     gxa = xa.like(zero=True)
     ops.maxpool3d_bwd(to_act(gy.to(dev), dt), am, gxa, k, s, pf)
