@@ -293,8 +293,15 @@ struct EpiPre {
   float4 ac[4];
   uint4 mk[2];
 };
-__device__ __forceinline__ void epilogue_prefetch(const EpilogueArgs& e, int nb, size_t out_row, size_t mask_row,
+// FLAGS >= 0: the launch's epilogue flags as a compile-time constant (the kernels dispatch once per launch on the
+// common combinations): the flag tests fold away and the chunk becomes straight-line code - with run-time flags a
+// chunk executed ~250 instructions for ~60 of arithmetic, and three epilogue warps per scheduler made that the
+// bound of the 1x1x1 GEMMs (trace: 0.42 us of "math" per 16-channel chunk).
+template <int FLAGS = -1>
+__device__ __forceinline__ void epilogue_prefetch(const EpilogueArgs& e_, int nb, size_t out_row, size_t mask_row,
                                                   bool active, EpiPre& pre) {
+  struct { int cout, flags; const float* acc_in; const __nv_bfloat16* mask_y; } e = {
+      e_.cout, FLAGS >= 0 ? FLAGS : e_.flags, e_.acc_in, e_.mask_y};
   if (!active || nb + 16 > e.cout) return;  // partial chunks take the scalar path at use
   if (e.flags & IVF_EP_ACCUM) {
     const float4* a4 = reinterpret_cast<const float4*>(e.acc_in + out_row + nb);
@@ -308,10 +315,25 @@ __device__ __forceinline__ void epilogue_prefetch(const EpilogueArgs& e, int nb,
   }
 }
 
-template <bool LSTM = false>
-__device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const uint32_t (&r)[16], int nb,
+// 16 consecutive floats of a 16-byte aligned shared-memory vector (four LDS.128 instead of sixteen LDS.32)
+__device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = reinterpret_cast<const float4*>(p)[j];
+    v[4 * j] = t.x;
+    v[4 * j + 1] = t.y;
+    v[4 * j + 2] = t.z;
+    v[4 * j + 3] = t.w;
+  }
+}
+
+// sc / sh / ms must be 16-byte aligned (the kernels' per-channel vectors are, and chunks start at multiples of 16)
+template <bool LSTM = false, int FLAGS = -1>
+__device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e_, const uint32_t (&r)[16], int nb,
                                                  const float* sc, const float* sh, const float* ms,
                                                  size_t out_row, size_t mask_row, const EpiPre& pre) {
+  EpilogueArgs e = e_;
+  if (FLAGS >= 0) e.flags = FLAGS;
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -363,8 +385,11 @@ __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const ui
     return;
   }
   if (e.flags & IVF_EP_AFFINE) {
+    float scv[16], shv[16];
+    lds16(sc, scv);
+    lds16(sh, shv);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], scv[j], shv[j]);
   }
   if (e.flags & IVF_EP_RELU) {
 #pragma unroll
@@ -372,13 +397,15 @@ __device__ __forceinline__ void epilogue_chunk16(const EpilogueArgs& e, const ui
   }
   if (e.flags & IVF_EP_MASK) {
     if (full) {
+      float msv[16];
+      lds16(ms, msv);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&pre.mk[hh]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           int jj = hh * 8 + j;
-          v[jj] = __bfloat162float(mb[j]) > 0.f ? v[jj] * ms[jj] : 0.f;
+          v[jj] = __bfloat162float(mb[j]) > 0.f ? v[jj] * msv[jj] : 0.f;
         }
       }
     } else {

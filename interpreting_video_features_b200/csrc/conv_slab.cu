@@ -33,6 +33,8 @@
 // tile i overlaps the MMAs of tile i+1.
 #include "conv_common.cuh"
 
+#include <type_traits>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -120,7 +122,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint32_t tmem_base_slot;
   // per-channel epilogue vectors: s_scale = BN scale (AFFINE) or the producer's BN' mask scale (MASK; the two
   // are never combined on this path, the host checks), s_shift = BN shift
-  __shared__ float s_scale[SLAB_MAX_COUT], s_shift[SLAB_MAX_COUT];
+  __shared__ __align__(16) float s_scale[SLAB_MAX_COUT], s_shift[SLAB_MAX_COUT];
 
   constexpr uint32_t ROWB = KCH * 2;             // bytes per slab pixel / weight row
   constexpr uint32_t ROW16 = ROWB / 16;          // the same in descriptor (16-byte) units
@@ -391,104 +393,119 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ea.lstm_c_prev = p.lstm_c_prev;
     ea.lstm_c_next = p.lstm_c_next;
     ea.lstm_h_next = p.lstm_h_next;
-    int it = 0;
-    for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
-      const TileCoord t = decode_tile(p, tile, NCTA, rank);
-      const int acc = p.acc_stages == 2 ? (it & 1) : 0;
-      mbar_wait(&t_full[acc], p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // this warp's chunks: [c_lo, c_hi)
-      const int nchunks = p.bn >> 4;
-      const int c_lo = 16 * (nchunks * cgrp / SLAB_EPI_GROUPS), c_hi = 16 * (nchunks * (cgrp + 1) / SLAB_EPI_GROUPS);
-      float* xbase = nullptr;
-      if (p.kwm > 1) {
-        // kw-merge, out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  The rows v+g
-        // that fall into the NEXT 32-row segment (next TMEM lane quarter, or quarter 0 of the next accumulator)
-        // come through shared memory.  Every warp first publishes the first kwm-1 rows of each of its segments
-        // for its columns, ONE barrier per tile makes them visible, then the tile is finished without further
-        // synchronisation (the exchange is double buffered by tile parity; the barrier of the next tile orders
-        // this tile's reads before the buffer is written again two tiles later).
-        const int kwm = p.kwm, bn = p.bn, seg = p.xch_seg;
-        xbase = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.xch_off) +
-                (size_t)(it & 1) * 4 * p.mt * seg;
+    // the tile loop, instantiated per epilogue-flag combination (FL >= 0: compile-time flags, see epilogue_chunk16)
+    auto run_epilogue = [&](auto fl_tag) {
+      constexpr int FL = decltype(fl_tag)::value;
+      int it = 0;
+      for (int tile = item0; tile < p.num_tiles; tile += item_step, ++it) {
+        const TileCoord t = decode_tile(p, tile, NCTA, rank);
+        const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+        mbar_wait(&t_full[acc], p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // this warp's chunks: [c_lo, c_hi)
+        const int nchunks = p.bn >> 4;
+        const int c_lo = 16 * (nchunks * cgrp / SLAB_EPI_GROUPS), c_hi = 16 * (nchunks * (cgrp + 1) / SLAB_EPI_GROUPS);
+        float* xbase = nullptr;
+        if (p.kwm > 1) {
+          // kw-merge, out[v] = sum_g P_g[v + g]: block g of the accumulator, g rows further down.  The rows v+g
+          // that fall into the NEXT 32-row segment (next TMEM lane quarter, or quarter 0 of the next accumulator)
+          // come through shared memory.  Every warp first publishes the first kwm-1 rows of each of its segments
+          // for its columns, ONE barrier per tile makes them visible, then the tile is finished without further
+          // synchronisation (the exchange is double buffered by tile parity; the barrier of the next tile orders
+          // this tile's reads before the buffer is written again two tiles later).
+          const int kwm = p.kwm, bn = p.bn, seg = p.xch_seg;
+          xbase = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.xch_off) +
+                  (size_t)(it & 1) * 4 * p.mt * seg;
+          for (int m = 0; m < p.mt; ++m) {
+            const int sidx = m * 4 + q;
+            if (sidx == 0) continue;  // nobody looks below the first segment
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.mt + m) * p.slot);
+            float* xw = xbase + (size_t)sidx * seg;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              for (int g = 1; g < kwm; ++g) {
+                uint32_t bt[16];
+                tmem_ld16(taddr + g * bn + c0, bt);
+                if (lane < kwm - 1) {
+                  float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
+  #pragma unroll
+                  for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[j]);
+                }
+              }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows of the tile visible
+        }
         for (int m = 0; m < p.mt; ++m) {
-          const int sidx = m * 4 + q;
-          if (sidx == 0) continue;  // nobody looks below the first segment
-          const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.mt + m) * p.slot);
-          float* xw = xbase + (size_t)sidx * seg;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            for (int g = 1; g < kwm; ++g) {
-              uint32_t bt[16];
-              tmem_ld16(taddr + g * bn + c0, bt);
-              if (lane < kwm - 1) {
-                float* dst = xw + ((g - 1) * (kwm - 1) + lane) * bn + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(bt[j]);
-              }
-            }
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows of the tile visible
-      }
-      for (int m = 0; m < p.mt; ++m) {
-        const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
-        const int r = v / p.wp;
-        const int c = v - r * p.wp;
-        const int hrow = t.h0 + r;
-        const bool ok = r < p.th && hrow < p.hh && c < p.ww;
-        const size_t pix = (((size_t)t.nn * p.dd + t.dz) * p.hh + hrow) * p.ww + c;
-        const size_t out_row = pix * p.out_ld + p.out_coff;
-        const size_t mask_row = pix * p.mask_ld + p.mask_coff;
-        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
-                               (uint32_t)((acc * p.mt + m) * p.slot);
-        EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
-                     // the scheduler cover the latency
-        if (p.kwm == 1) {
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            const int nb = t.nt * p.bn + c0;
-            epilogue_prefetch(ea, nb, out_row, mask_row, ok, cur);
-            uint32_t rr[16];
-            tmem_ld16(taddr + c0, rr);
-            if (ok && nb < p.cout)
-              epilogue_chunk16<LSTM>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
-          }
-        } else {
-          const int kwm = p.kwm, bn = p.bn;
-          // the segment after this one (rows past the last segment of the tile are padding nobody stores)
-          const int snext = min(m * 4 + q + 1, 4 * p.mt - 1);
-          const float* xr = xbase + (size_t)snext * p.xch_seg;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            epilogue_prefetch(ea, t.nt * bn + c0, out_row, mask_row, ok, cur);
-            uint32_t tg[16];
-            tmem_ld16(taddr + c0, tg);
-            float accv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[j]);
-            for (int g = 1; g < kwm; ++g) {
-              tmem_ld16(taddr + g * bn + c0, tg);
-              const int src = lane + g - 32;  // >= 0: the row lives in the next segment
-              const float* xs = xr + ((g - 1) * (kwm - 1) + (src >= 0 ? src : 0)) * bn + c0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[j]), g);
-                if (src >= 0) sv = xs[j];
-                accv[j] += sv;
-              }
-            }
-            const int nb = t.nt * bn + c0;
-            if (ok && nb < p.cout) {
+          const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
+          const int r = v / p.wp;
+          const int c = v - r * p.wp;
+          const int hrow = t.h0 + r;
+          const bool ok = r < p.th && hrow < p.hh && c < p.ww;
+          const size_t pix = (((size_t)t.nn * p.dd + t.dz) * p.hh + hrow) * p.ww + c;
+          const size_t out_row = pix * p.out_ld + p.out_coff;
+          const size_t mask_row = pix * p.mask_ld + p.mask_coff;
+          const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
+                                 (uint32_t)((acc * p.mt + m) * p.slot);
+          EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
+                       // the scheduler cover the latency
+          if (p.kwm == 1) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              const int nb = t.nt * p.bn + c0;
+              epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok, cur);
               uint32_t rr[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
-              epilogue_chunk16<LSTM>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+              tmem_ld16(taddr + c0, rr);
+              if (ok && nb < p.cout)
+                epilogue_chunk16<LSTM, FL>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+            }
+          } else {
+            const int kwm = p.kwm, bn = p.bn;
+            // the segment after this one (rows past the last segment of the tile are padding nobody stores)
+            const int snext = min(m * 4 + q + 1, 4 * p.mt - 1);
+            const float* xr = xbase + (size_t)snext * p.xch_seg;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              epilogue_prefetch<FL>(ea, t.nt * bn + c0, out_row, mask_row, ok, cur);
+              uint32_t tg[16];
+              tmem_ld16(taddr + c0, tg);
+              float accv[16];
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(tg[j]);
+              for (int g = 1; g < kwm; ++g) {
+                tmem_ld16(taddr + g * bn + c0, tg);
+                const int src = lane + g - 32;  // >= 0: the row lives in the next segment
+                const float* xs = xr + ((g - 1) * (kwm - 1) + (src >= 0 ? src : 0)) * bn + c0;
+  #pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(tg[j]), g);
+                  if (src >= 0) sv = xs[j];
+                  accv[j] += sv;
+                }
+              }
+              const int nb = t.nt * bn + c0;
+              if (ok && nb < p.cout) {
+                uint32_t rr[16];
+  #pragma unroll
+                for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(accv[j]);
+                epilogue_chunk16<LSTM, FL>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+              }
             }
           }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (NCTA == 2) mbar_arrive_leader(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
+        }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (NCTA == 2) mbar_arrive_leader(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
+    };
+    if (LSTM) {
+      run_epilogue(std::integral_constant<int, -1>{});
+    } else {
+      switch (p.flags) {
+        case IVF_EP_AFFINE | IVF_EP_RELU: run_epilogue(std::integral_constant<int, IVF_EP_AFFINE | IVF_EP_RELU>{}); break;
+        case IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_MASK>{}); break;
+        case IVF_EP_ACCUM | IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_MASK>{}); break;
+        case 0: run_epilogue(std::integral_constant<int, 0>{}); break;
+        default: run_epilogue(std::integral_constant<int, -1>{}); break;
       }
     }
   }

@@ -16,6 +16,7 @@
 #include "conv_common.cuh"
 
 #include <cstring>
+#include <type_traits>
 
 IvfEncodeIm2colFn ivf_encode_im2col = nullptr;
 IvfEncodeTiledFn ivf_encode_tiled = nullptr;
@@ -99,7 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_scale[256], s_shift[256], s_mscale[256];
+  __shared__ __align__(16) float s_scale[256], s_shift[256], s_mscale[256];
   // bf16 results leave through TMA stores: per epilogue warp two boxes of 32 rows x 16 channels
   __shared__ __align__(128) uint8_t stage_buf[EPI_WARPS][2][32 * 32];
 
@@ -267,67 +268,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.split_cout > 0)
       ea2.out = (p.flags & IVF_EP_OUT_F32) ? (void*)(reinterpret_cast<float*>(out2) - p.split_cout)
                                            : (void*)(reinterpret_cast<__nv_bfloat16*>(out2) - p.split_cout);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int tcount = 0;
-    int sbuf = 0;
-    for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
-      const int m = mt * TILE_M + row;
-      const bool row_ok = m < p.M;
-      const uint32_t taddr_row = tmem_acc + (uint32_t)(acc * p.acc_cols) + ((uint32_t)(q * 32) << 16);
-      const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
-      const size_t out_row2 = (size_t)m * p.out2_ld + p.out2_coff;
-      const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
-      // the first chunk's global operands are fetched while the MMAs still run
-      EpiPre cur;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 4);  // accumulator complete
-      for (int c0 = 16 * cgrp; c0 < p.bn; c0 += 16 * EPI_GROUPS) {
-        const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
-        // global operands of the chunk are requested before the TMEM load; the other warps of the scheduler
-        // cover the latency
-        epilogue_prefetch(ea, nb, out_row, mask_row, row_ok, cur);
-        uint32_t r[16];
-        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 0);
-        tmem_ld16(taddr_row + c0, r);
-        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 1);
-        if (p.tma_store) {
-          if (nb < p.cout) {  // warp-uniform
-            const uint32_t box = smem_u32(&stage_buf[warp - 2][sbuf][0]);
-            if (lane == 0) tma_store_wait_read<1>();  // the store that last read this box has finished reading
-            __syncwarp();
-            const bool second = p.split_cout > 0 && nb >= p.split_cout;
-            if (row_ok) {
-              ea.stage_smem = ea2.stage_smem = box + (uint32_t)lane * 32u;
-              epilogue_chunk16(second ? ea2 : ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+    // the tile loop, instantiated per epilogue-flag combination (FL >= 0: compile-time flags, see epilogue_chunk16)
+    auto run_epilogue = [&](auto fl_tag) {
+      constexpr int FL = decltype(fl_tag)::value;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tcount = 0;
+      int rot = 0;  // tile count modulo EPI_GROUPS
+      int sbuf = 0;
+      for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+        const int m = mt * TILE_M + row;
+        const bool row_ok = m < p.M;
+        const uint32_t taddr_row = tmem_acc + (uint32_t)(acc * p.acc_cols) + ((uint32_t)(q * 32) << 16);
+        const size_t out_row = (size_t)m * p.out_ld + p.out_coff;
+        const size_t out_row2 = (size_t)m * p.out2_ld + p.out2_coff;
+        const size_t mask_row = (size_t)m * p.mask_ld + p.mask_coff;
+        // the first chunk's global operands are fetched while the MMAs still run
+        EpiPre cur;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 4);  // accumulator complete
+        // chunk c of tile t goes to column group (c + t) % EPI_GROUPS: with a chunk count that is not a multiple
+        // of the group count (4 chunks of a 64-channel layer over 3 groups) the extra chunk rotates over the
+        // groups from tile to tile instead of making one group the bottleneck of every tile
+        for (int c0 = 16 * ((cgrp + EPI_GROUPS - rot) % EPI_GROUPS); c0 < p.bn; c0 += 16 * EPI_GROUPS) {
+          const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
+          // global operands of the chunk are requested before the TMEM load; the other warps of the scheduler
+          // cover the latency
+          epilogue_prefetch<FL>(ea, nb, out_row, mask_row, row_ok, cur);
+          uint32_t r[16];
+          if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 0);
+          tmem_ld16(taddr_row + c0, r);
+          if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 1);
+          if (p.tma_store) {
+            if (nb < p.cout) {  // warp-uniform
+              const uint32_t box = smem_u32(&stage_buf[warp - 2][sbuf][0]);
+              const bool tr = warp == 2 && tcount == 1 && c0 < 16 * EPI_GROUPS;  // this warp's first chunk of tile 1
+              if (tr) TC_TRACE(52);
+              if (lane == 0) tma_store_wait_read<1>();  // the store that last read this box has finished reading
+              __syncwarp();
+              if (tr) TC_TRACE(53);
+              const bool second = p.split_cout > 0 && nb >= p.split_cout;
+              if (row_ok) {
+                ea.stage_smem = ea2.stage_smem = box + (uint32_t)lane * 32u;
+                epilogue_chunk16<false, FL>(second ? ea2 : ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+              }
+              if (tr) TC_TRACE(54);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (tr) TC_TRACE(55);
+              if (lane == 0) {
+                tma_store_2d(second ? &tmO2 : &tmO, box, second ? nb - p.split_cout : nb, mt * TILE_M + q * 32);
+                tma_store_commit();
+              }
+              if (tr) TC_TRACE(56);
+              sbuf ^= 1;
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(second ? &tmO2 : &tmO, box, second ? nb - p.split_cout : nb, mt * TILE_M + q * 32);
-              tma_store_commit();
-            }
-            sbuf ^= 1;
+          } else if (row_ok && nb < p.cout) {
+            if (p.split_cout > 0 && nb >= p.split_cout)
+              epilogue_chunk16<false, FL>(ea2, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row2, mask_row, cur);
+            else
+              epilogue_chunk16<false, FL>(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
           }
-        } else if (row_ok && nb < p.cout) {
-          if (p.split_cout > 0 && nb >= p.split_cout)
-            epilogue_chunk16(ea2, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row2, mask_row, cur);
-          else
-            epilogue_chunk16(ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+          if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 2);
         }
-        if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 2);
+        // this warp's TMEM reads are complete (tmem_ld16 waits): hand the accumulator back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 5);  // epilogue of the tile done
+        ++tcount;
+        if (++rot == EPI_GROUPS) rot = 0;
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
-      // this warp's TMEM reads are complete (tmem_ld16 waits): hand the accumulator back
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (warp == 2 && tcount < 4) TC_TRACE(8 + tcount * 8 + 5);  // epilogue of the tile done
-      ++tcount;
-      if (++acc == p.acc_stages) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
+    };
+    switch (p.flags) {
+      case IVF_EP_AFFINE | IVF_EP_RELU: run_epilogue(std::integral_constant<int, IVF_EP_AFFINE | IVF_EP_RELU>{}); break;
+      case IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_MASK>{}); break;
+      case IVF_EP_ACCUM | IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_MASK>{}); break;
+      case 0: run_epilogue(std::integral_constant<int, 0>{}); break;
+      default: run_epilogue(std::integral_constant<int, -1>{}); break;
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();  // the boxes are read until the stores complete
   }

@@ -76,6 +76,12 @@ __device__ __forceinline__ uint8_t relu_byte(const uint4& raw) {
 // (PRMT, SHF, LOP3, IMNMX) against ~6 of the compare-to-mask form, which also needed two 16-bit lanes per word.
 // NONNEG (IVF_POOL_NONNEG: the caller vouches that no input is negative - ReLU outputs) skips the flip: 2
 // instructions per element and tap.
+// 16-byte read-only load the compiler may not move (asm volatile keeps program order among themselves)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 template <bool NONNEG>
 __device__ __forceinline__ int pool_key_flip(int k) {
   return NONNEG ? k : (k ^ ((k >> 31) & 0x7fff0000));
@@ -209,17 +215,21 @@ maxpool_fwd_rows_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ in, _
     for (int i = 0; i < 8; ++i) best[i] = INT_MIN;
 #pragma unroll
     for (int a = 0; a < KD; ++a) {
+      // all loads of a plane are issued before the first compare waits on one of them (the compiler otherwise
+      // interleaves load and use: seven exposed memory latencies per output)
+      uint4 raw[KH * KW];
 #pragma unroll
       for (int b = 0; b < KH; ++b) {
         const bool rok = dok[a] && (unsigned)(zh0 + b) < (unsigned)d.ih;
         const __nv_bfloat16* prow = pcol + (long long)a * plane_elems + (long long)(zh0 + b) * row_elems;
 #pragma unroll
         for (int e = 0; e < KW; ++e) {
-          uint4 raw = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
-          if (rok && wok[e]) raw = *reinterpret_cast<const uint4*>(prow + e * d.in_ld);
-          pool_keys_max<NONNEG>(raw, 255u - (uint32_t)((a * KH + b) * KW + e), best);
+          raw[b * KW + e] = make_uint4(0u, 0u, 0u, 0u);  // explicit zero padding
+          if (rok && wok[e]) raw[b * KW + e] = ld_nc_v4(prow + e * d.in_ld);
         }
       }
+#pragma unroll
+      for (int k = 0; k < KH * KW; ++k) pool_keys_max<NONNEG>(raw[k], 255u - (uint32_t)(a * KH * KW + k), best);
     }
     const int opix = out_row0 + oh * d.ow;
     uint4 o;
@@ -504,6 +514,127 @@ maxpool_bwd_s2patch_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy
         pkd.z = *reinterpret_cast<uint32_t*>(&h2);
         pkd.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dx) + o) = pkd;
+      }
+    }
+  }
+}
+
+// Pure-routing backward of the stride-2 stage pools (bf16 in and out, no epilogue: the engine applies the
+// producer's ReLU'/BN' one stage earlier, see engine._emit_stage_bwd).  Same patch ownership as the kernel above -
+// a thread owns the 2x2 input cells that share a window origin, for 8 channels - but it keeps its column for a
+// SEGMENT of patch rows: the windows of output row qh serve patch row qh (their rows 0/1) and patch row qh + 1
+// (their row 2), so each window's arg-max / gradient vectors are loaded once and carried in registers to the next
+// iteration, and the index arithmetic is paid once per segment (the one-row form executed ~660 instructions per
+// patch for 9 x 26 of routing work; ncu: issue bound).
+template <typename G>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_s2route_kernel(ivf_pool_desc d, const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                           __nv_bfloat16* __restrict__ dx, int items, int qseg, int nseg, int qhn, int qwn) {
+  const int item = blockIdx.z * gridDim.y + blockIdx.y;  // (clip, input depth, patch-row segment)
+  if (item >= items) return;
+  const int cv = d.c >> 3;
+  const int el = blockIdx.x * 256 + threadIdx.x;
+  if (el >= qwn * cv) return;
+  constexpr int KD = G::KD_, KH = G::KH_, KW = G::KW_, SD = G::SD_;
+  constexpr int JA = (KD + SD - 1) / SD, JH = (KH + 1) / 2, JW = (KW + 1) / 2;
+  const int qw = el / cv, c = (el - qw * cv) << 3;
+  const int seg = item % nseg;
+  const int t = item / nseg;
+  const int idd = t % d.id, n = t / d.id;
+  const int qh0 = seg * qseg, qh1 = min(qhn, qh0 + qseg);
+  const int pd0 = (idd + d.pd) % SD, qd = (idd + d.pd) / SD;
+  // per window column / depth candidate: validity, tap base, offset of (od, row 0, ow) in output pixels
+  bool wv[JA][JW];
+  int obase[JA][JW];
+  uint32_t tapa[JA];
+#pragma unroll
+  for (int ja = 0; ja < JA; ++ja) {
+    const int a = pd0 + ja * SD, od = qd - ja;
+    const bool dv = a < KD && od >= 0 && od < d.od;
+    tapa[ja] = (uint32_t)(a * KH * KW) * 0x01010101u;
+#pragma unroll
+    for (int jw = 0; jw < JW; ++jw) {
+      const int ow = qw - jw;
+      wv[ja][jw] = dv && ow >= 0 && ow < d.ow;
+      obase[ja][jw] = ((n * d.od + od) * d.oh) * d.ow + ow;
+    }
+  }
+  auto load_win = [&](int ja, int jw, int oh, uint2& pk, uint4& raw) {
+    pk = make_uint2(0xffffffffu, 0xffffffffu);  // tap 255: matches nothing
+    raw = make_uint4(0u, 0u, 0u, 0u);
+    if (wv[ja][jw] && oh >= 0 && oh < d.oh) {
+      const int opix = obase[ja][jw] + oh * d.ow;
+      pk = *reinterpret_cast<const uint2*>(argmax + (long long)opix * d.c + c);
+      raw = *reinterpret_cast<const uint4*>(dy + (long long)opix * d.out_ld + d.out_coff + c);
+    }
+  };
+  // routes the window's gradients whose arg-max is (depth tap of ja, row b, column rw + 2 jw) into g[rw]
+  auto route_row = [&](const uint2& pk, const uint4& raw, uint32_t tap_row, int jw, float (&g)[2][8]) {
+    const uint32_t f[8] = {raw.x << 16, raw.x & 0xffff0000u, raw.y << 16, raw.y & 0xffff0000u,
+                           raw.z << 16, raw.z & 0xffff0000u, raw.w << 16, raw.w & 0xffff0000u};
+#pragma unroll
+    for (int rw = 0; rw < 2; ++rw) {
+      const int e = rw + 2 * jw;
+      if (e >= KW) continue;
+      const uint32_t tap4 = tap_row + (uint32_t)e * 0x01010101u;
+      const uint32_t e0 = __vcmpeq4(pk.x, tap4), e1 = __vcmpeq4(pk.y, tap4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t m = __byte_perm(i < 4 ? e0 : e1, 0u, 0x1111u * (i & 3));
+        g[rw][i] += __uint_as_float(f[i] & m);
+      }
+    }
+  };
+  uint2 pkT[JA][JW];
+  uint4 rawT[JA][JW];
+  if (JH == 2) {
+#pragma unroll
+    for (int ja = 0; ja < JA; ++ja)
+#pragma unroll
+      for (int jw = 0; jw < JW; ++jw) load_win(ja, jw, qh0 - 1, pkT[ja][jw], rawT[ja][jw]);
+  }
+  const int iw0 = 2 * qw - d.pw;
+  const int in_plane = (n * d.id + idd) * d.ih;
+#pragma unroll 1
+  for (int qh = qh0; qh < qh1; ++qh) {
+    float g[2][2][8];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) (&g[0][0][0])[i] = 0.f;
+#pragma unroll
+    for (int ja = 0; ja < JA; ++ja) {
+#pragma unroll
+      for (int jw = 0; jw < JW; ++jw) {
+        uint2 pk;
+        uint4 raw;
+        load_win(ja, jw, qh, pk, raw);
+        if (JH == 2)  // the windows one output row up reach patch row qh with their last row
+          route_row(pkT[ja][jw], rawT[ja][jw], tapa[ja] + (uint32_t)(2 * KW) * 0x01010101u, jw, g[0]);
+        route_row(pk, raw, tapa[ja], jw, g[0]);
+        if (KH >= 2) route_row(pk, raw, tapa[ja] + (uint32_t)KW * 0x01010101u, jw, g[1]);
+        if (JH == 2) {
+          pkT[ja][jw] = pk;
+          rawT[ja][jw] = raw;
+        }
+      }
+    }
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int ih = 2 * qh + rh - d.ph;
+      if (ih < 0 || ih >= d.ih) continue;
+#pragma unroll
+      for (int rw = 0; rw < 2; ++rw) {
+        const int iw = iw0 + rw;
+        if (iw < 0 || iw >= d.iw) continue;
+        const float* gg = g[rh][rw];
+        const int ipix = (in_plane + ih) * d.iw + iw;
+        uint4 pkd;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(gg[0], gg[1]), h1 = __floats2bfloat162_rn(gg[2], gg[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(gg[4], gg[5]), h3 = __floats2bfloat162_rn(gg[6], gg[7]);
+        pkd.x = *reinterpret_cast<uint32_t*>(&h0);
+        pkd.y = *reinterpret_cast<uint32_t*>(&h1);
+        pkd.z = *reinterpret_cast<uint32_t*>(&h2);
+        pkd.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dx + (long long)ipix * d.in_ld + d.in_coff + c) = pkd;
       }
     }
   }
@@ -935,10 +1066,16 @@ int fwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* in, void* out, uint
           const char* e = getenv("IVF_POOL_ROWS");
           return !e || atoi(e) != 0;
         }();
-        if (rows_on && !relu_bits && d->sh == 2 && d->sw == 2 && d->oh >= 4) {
+        // measured (B200, tools/pool_bench.py): equal to the one-row kernel at 8 clips, 4 % faster at 32 for the
+        // 1x3x3 pools; slower for the 27- and 8-tap pools (4a, 5a), which keep the one-row kernel
+        if (rows_on && !relu_bits && d->kd == 1 && d->sh == 2 && d->sw == 2 && d->oh >= 4) {
           // row segments: enough threads for ~1.5 full-occupancy waves, at least two rows per thread
           const long long per_seg = (long long)d->n * d->od * d->ow * (d->c / V);
-          long long want = ((long long)h->sm_count * 2048 * 3 / 2 + per_seg - 1) / per_seg;
+          static const int waves = [] {
+            const char* e = getenv("IVF_POOL_ROWS_WAVES");  // full-occupancy waves to aim for
+            return e ? std::max(1, atoi(e)) : 4;
+          }();
+          long long want = ((long long)h->sm_count * 2048 * waves + per_seg - 1) / per_seg;
           int nseg = (int)std::max<long long>(1, std::min<long long>(want, d->oh / 2));
           const int rseg = (d->oh + nseg - 1) / nseg;
           nseg = (d->oh + rseg - 1) / rseg;
@@ -1091,6 +1228,38 @@ int bwd_t(ivf_handle* h, const ivf_pool_desc* d, const void* dy, const uint8_t* 
           using GeoStem = PoolGeo<1, 3, 3, 1, 2, 2>;
           using Geo3s2 = PoolGeo<3, 3, 3, 2, 2, 2>;
           using Geo2s2 = PoolGeo<2, 2, 2, 2, 2, 2>;
+          static const bool route_on = [] {
+            const char* e = getenv("IVF_POOL_S2ROUTE");
+            return !e || atoi(e) != 0;
+          }();
+          // pure routing: row-segment kernel.  Measured (tools/pool_bench.py, 8 / 32 clips): 2a 51 -> 41 / 182 -> 129 us,
+          // 3a 40 -> 33 / 137 -> 100 us; the two-depth-candidate 4a pool (100 registers) and 5a are not faster
+          if (route_on && d->flags == 0 && !relu_bits && d->kd == 1 && qhn >= 4) {
+            const long long per_seg = (long long)d->n * d->id * qwn * (d->c / V);
+            static const int waves = [] {
+              const char* e = getenv("IVF_POOL_ROUTE_WAVES");
+              return e ? std::max(1, atoi(e)) : 3;
+            }();
+            long long want = ((long long)h->sm_count * 2048 * waves + per_seg - 1) / per_seg;
+            int nseg = (int)std::max<long long>(1, std::min<long long>(want, qhn / 2));
+            const int qseg = (qhn + nseg - 1) / nseg;
+            nseg = (qhn + qseg - 1) / qseg;
+            const int items = d->n * d->id * nseg;
+            const dim3 rgrid = row_grid(items, qwn * (d->c / V));
+#define IVF_S2ROUTE(GEO)                                                                                  \
+  maxpool_bwd_s2route_kernel<GEO><<<rgrid, threads, 0, st>>>(*d, (const __nv_bfloat16*)dy, argmax,        \
+                                                             (__nv_bfloat16*)dx, items, qseg, nseg, qhn, qwn)
+            bool routed = true;
+            if (d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1) IVF_S2ROUTE(GeoStem);
+            else if (d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 2) IVF_S2ROUTE(Geo3s2);
+            else if (d->kd == 2 && d->kh == 2 && d->kw == 2 && d->sd == 2) IVF_S2ROUTE(Geo2s2);
+            else routed = false;
+#undef IVF_S2ROUTE
+            if (routed) {
+              IVF_LAUNCHED(h);
+              return IVF_OK;
+            }
+          }
           const dim3 pgrid = row_grid(prow, qwn * (d->c / V));
 #define IVF_S2PATCH(GEO)                                                                                   \
   maxpool_bwd_s2patch_kernel<GEO><<<pgrid, threads, 0, st>>>(*d, (const __nv_bfloat16*)dy, argmax, acc_in, \

@@ -34,6 +34,8 @@ def show(name, t):
 
 def show_chunks(t):
     t0 = t[0]
+    print("    tile 1 chunk 0 detail: before wait_read +%.3f | after +%.3f | after math/st.shared +%.3f | after fence "
+          "+%.3f | after store issue +%.3f" % tuple((t[52 + k] - t0) / 1e3 for k in range(5)))
     for c in range(4):
         b = 40 + c * 3
         print("    tile 1 chunk %d: before tmem ld +%.3f | after ld +%.3f | after math+stores +%.3f" %
@@ -75,3 +77,4 @@ run("3c fwd b0|b1a|b2a (256 -> 128+160), 8x8x28x28", 8, (8, 28, 28), 256, 128, 1
 run("3c dgrad (128|160 -> 256)", 8, (8, 28, 28), 256, 128, 160, True)
 run("2b-like fwd (64 -> 32+32), 8x8x56x56", 8, (8, 56, 56), 64, 32, 32, False)
 run("4e fwd (528 -> 112+176), 8x4x14x14", 8, (4, 14, 14), 528, 112, 176, False)
+run("4e dgrad (112|176 -> 528), 8x4x14x14", 8, (4, 14, 14), 528, 112, 176, True)
