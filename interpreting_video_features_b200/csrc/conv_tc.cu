@@ -34,6 +34,7 @@ constexpr int EPI_GROUPS = 3;
 constexpr int EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_STAGES = 12;
+constexpr int EPI_STAGING_BYTES = EPI_WARPS * 2 * 3072;  // per warp two buffers of [32 x 16 fp32 | 32 x 16 bf16]
 
 struct TcParams {
   int M;                 // n*od*oh*ow
@@ -59,6 +60,8 @@ struct TcParams {
   int mtiles, grid_x;        // 128-pixel tiles; a CTA walks blockIdx.x, blockIdx.x + gridDim.x, ...
   int acc_stages, acc_cols;  // TMEM accumulators (1|2) and the column pitch between them
   int tma_store;             // bf16 results staged in shared memory and written by TMA stores
+  int tma_epi;               // data-gradient epilogue operands (fp32 consumer sum, bf16 ReLU mask) loaded by TMA
+  uint32_t epi_off;          // their staging area, byte offset from the aligned dynamic shared-memory base
   long long* trace;          // IVF_TC_TRACE=1: globaltimer stamps of CTA (0, 0) (diagnostic), else null
 };
 
@@ -89,7 +92,8 @@ template <int KCH>
 __global__ void __launch_bounds__(NUM_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmO,
-               const __grid_constant__ CUtensorMap tmO2, const TcParams p, const float* __restrict__ scale,
+               const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmM, const TcParams p, const float* __restrict__ scale,
                const float* __restrict__ shift, const float* __restrict__ acc_in,
                const __nv_bfloat16* __restrict__ mask_y, const float* __restrict__ mask_scale,
                void* __restrict__ out, void* __restrict__ out2) {
@@ -100,6 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(8) uint64_t epi_bar[EPI_WARPS][2];  // epilogue-operand boxes of a warp have landed
   __shared__ __align__(16) float s_scale[256], s_shift[256], s_mscale[256];
   // bf16 results leave through TMA stores: per epilogue warp two boxes of 32 rows x 16 channels
   __shared__ __align__(128) uint8_t stage_buf[EPI_WARPS][2][32 * 32];
@@ -123,6 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrival per epilogue warp
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&epi_bar[w][a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,6 +143,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 64 && p.tma_store) {
     tma_prefetch_map(&tmO);
     if (p.split_cout > 0) tma_prefetch_map(&tmO2);
+    if (p.tma_epi) {
+      if (p.flags & IVF_EP_ACCUM) tma_prefetch_map(&tmC);
+      if (p.flags & IVF_EP_MASK) tma_prefetch_map(&tmM);
+    }
   }
   if (warp >= 2) {
     // per-channel epilogue vectors of this N tile
@@ -276,6 +286,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int tcount = 0;
       int rot = 0;  // tile count modulo EPI_GROUPS
       int sbuf = 0;
+      // Data-gradient operands by TMA (p.tma_epi).  A lane owns an output ROW, so its 64 bytes of consumer sum and
+      // 32 bytes of ReLU mask per chunk are a row-scattered access: 32 different lines per warp instruction, six
+      // instructions per chunk - the L1 tag stage, not the memory, bounded these epilogues (trace: ~2 us per chunk
+      // against 0.5 us of a forward chunk).  Instead each warp fetches the [32 rows x 16 channels] boxes of its NEXT
+      // chunk (also across tiles, before that tile's MMAs finish) into its own double-buffered staging area and
+      // reads its row from shared memory (64-/32-byte swizzle: conflict-free per quarter warp).
+      constexpr bool OPS = FL >= 0 && (FL & (IVF_EP_ACCUM | IVF_EP_MASK)) != 0;
+      const bool te = OPS && p.tma_epi;
+      const uint32_t epi_stage = smem_base + p.epi_off + (uint32_t)(warp - 2) * 6144u;  // [2][2048 acc | 1024 mask]
+      const uint8_t* epi_gen = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off + (size_t)(warp - 2) * 6144u;
+      int ebuf = 0;
+      uint32_t eph0 = 0, eph1 = 0;
+      auto chunk_start = [&](int r) { return 16 * ((cgrp + EPI_GROUPS - r) % EPI_GROUPS); };
+      // boxes of chunk (tile mt_, column c0_) -> staging buffer b (whole warp calls; one lane issues)
+      auto issue_ops = [&](int mt_, int c0_, int b) {
+        if (lane == 0) {
+          constexpr uint32_t bytes = ((FL & IVF_EP_ACCUM) ? 2048u : 0u) + ((FL & IVF_EP_MASK) ? 1024u : 0u);
+          mbar_expect_tx(&epi_bar[warp - 2][b], bytes);
+          const int nb_ = ntile * p.bn + c0_, r0_ = mt_ * TILE_M + q * 32;
+          if (FL & IVF_EP_ACCUM) tma_load_2d(epi_stage + b * 3072u, &tmC, &epi_bar[warp - 2][b], nb_, r0_);
+          if (FL & IVF_EP_MASK) tma_load_2d(epi_stage + b * 3072u + 2048u, &tmM, &epi_bar[warp - 2][b], nb_, r0_);
+        }
+      };
+      if (te) {  // first chunk of this warp
+        int mt_ = blockIdx.x, r_ = 0, c_ = chunk_start(0);
+        while (mt_ < p.mtiles && c_ >= p.bn) {
+          mt_ += gridDim.x;
+          r_ = r_ + 1 == EPI_GROUPS ? 0 : r_ + 1;
+          c_ = chunk_start(r_);
+        }
+        if (mt_ < p.mtiles) issue_ops(mt_, c_, 0);
+      }
+      EpilogueArgs eaT = ea;
+      eaT.cout = 1 << 30;  // TMA zero-fills past the tensor and the TMA store clips: every chunk is a full chunk
       for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
         const int m = mt * TILE_M + row;
         const bool row_ok = m < p.M;
@@ -295,7 +339,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nb = ntile * p.bn + c0;  // first produced channel of this chunk
           // global operands of the chunk are requested before the TMEM load; the other warps of the scheduler
           // cover the latency
-          epilogue_prefetch<FL>(ea, nb, out_row, mask_row, row_ok, cur);
+          if (te) {
+            // next chunk of this warp (possibly in a later tile) -> the other buffer, whose last reader was the
+            // previous iteration of this loop
+            int mt_ = mt, r_ = rot, c_ = c0 + 16 * EPI_GROUPS;
+            while (mt_ < p.mtiles && c_ >= p.bn) {
+              mt_ += gridDim.x;
+              r_ = r_ + 1 == EPI_GROUPS ? 0 : r_ + 1;
+              c_ = chunk_start(r_);
+            }
+            __syncwarp();
+            if (mt_ < p.mtiles) issue_ops(mt_, c_, ebuf ^ 1);
+            mbar_wait(&epi_bar[warp - 2][ebuf], ebuf ? eph1 : eph0);
+            if (ebuf) eph1 ^= 1u; else eph0 ^= 1u;
+            const uint8_t* st = epi_gen + ebuf * 3072;
+            if (FL & IVF_EP_ACCUM) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                cur.ac[j] = *reinterpret_cast<const float4*>(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+            }
+            if (FL & IVF_EP_MASK) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                cur.mk[j] = *reinterpret_cast<const uint4*>(st + 2048 + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4));
+            }
+            ebuf ^= 1;
+          } else {
+            epilogue_prefetch<FL>(ea, nb, out_row, mask_row, row_ok, cur);
+          }
           uint32_t r[16];
           if (warp == 2 && tcount == 1 && c0 < 64 * EPI_GROUPS) TC_TRACE(40 + (c0 / (16 * EPI_GROUPS)) * 3 + 0);
           tmem_ld16(taddr_row + c0, r);
@@ -310,8 +381,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (tr) TC_TRACE(53);
               const bool second = p.split_cout > 0 && nb >= p.split_cout;
               if (row_ok) {
-                ea.stage_smem = ea2.stage_smem = box + (uint32_t)lane * 32u;
-                epilogue_chunk16<false, FL>(second ? ea2 : ea, r, nb, s_scale + c0, s_shift + c0, s_mscale + c0, out_row, mask_row, cur);
+                ea.stage_smem = ea2.stage_smem = eaT.stage_smem = box + (uint32_t)lane * 32u;
+                epilogue_chunk16<false, FL>(te ? eaT : (second ? ea2 : ea), r, nb, s_scale + c0, s_shift + c0, s_mscale + c0,
+                                            out_row, mask_row, cur);
               }
               if (tr) TC_TRACE(54);
               fence_proxy_async_smem();
@@ -580,6 +652,47 @@ int get_map_out(ivf_handle* h, const void* base, int coff, int ld, int channels,
   return IVF_OK;
 }
 
+// [rows = pixels][channels] tensor read in boxes of 32 rows x 16 channels with the swizzle that matches the box row
+// (64 bytes of fp32, 32 bytes of bf16): the TMA-loaded epilogue operands.  Boxes past either extent are zero filled.
+int get_map_rows(ivf_handle* h, const void* base, int elem_bytes, long long coff, int ld, int channels, long long rows,
+                 CUtensorMap* out) {
+  struct {
+    const void* base;
+    int elem_bytes, ld, channels;
+    long long coff, rows;
+  } key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.elem_bytes = elem_bytes; key.coff = coff; key.ld = ld; key.channels = channels; key.rows = rows;
+  std::string kb = key_bytes('R', key);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    auto it = h->tmaps.find(kb);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return IVF_OK;
+    }
+  }
+  const char* p0 = reinterpret_cast<const char*>(base) + (size_t)coff * elem_bytes;
+  cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = ivf_encode_tiled(&m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                              2, (void*)p0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    IVF_FAIL(IVF_ECUDA, "cuTensorMapEncodeTiled(epilogue operand) failed (%d): channels %d ld %d rows %lld", (int)r,
+             channels, ld, rows);
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->tmaps[kb] = m;
+  }
+  *out = m;
+  return IVF_OK;
+}
+
 int check_bf16_desc(const ivf_conv_desc* d) {
   IVF_REQUIRE(!d->transposed,
               "conv(bf16): transposed gather is fp32-only; present strided layers space-to-depth");
@@ -598,7 +711,7 @@ int check_bf16_desc(const ivf_conv_desc* d) {
 template <int KCH>
 int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CUtensorMap& ma,
               const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mo, const CUtensorMap& mo2,
-              int ntiles, const float* scale, const float* shift,
+              const CUtensorMap& mc, const CUtensorMap& mm, int ntiles, const float* scale, const float* shift,
               const float* acc_in, const void* mask_y, const float* mask_scale, void* out, void* out2,
               cudaStream_t st) {
   const int max_smem = 196 * 1024;  // 227 KB minus the static part (barriers, epilogue vectors, TMA-store boxes)
@@ -609,8 +722,9 @@ int launch_tc(ivf_handle* h, const ivf_conv_desc* d, const TcParams& p, const CU
     h->tc_attr_set[slot] = true;
   }
   size_t smem = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 1024;
+  if (p.tma_epi) smem = (size_t)p.epi_off + EPI_STAGING_BYTES + 1024;
   dim3 grid(p.grid_x, ntiles);
-  IVF_CUDA(ivf_launch(conv_tc_kernel<KCH>, grid, dim3(NUM_THREADS), smem, st, 1, ma, mb, ma2, mo, mo2, p, scale, shift,
+  IVF_CUDA(ivf_launch(conv_tc_kernel<KCH>, grid, dim3(NUM_THREADS), smem, st, 1, ma, mb, ma2, mo, mo2, mc, mm, p, scale, shift,
                       acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out, out2));
   IVF_LAUNCHED(h);
   return IVF_OK;
@@ -725,15 +839,29 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   p.acc_stages = acc_stages;
   p.acc_cols = cols;
   p.tmem_cols = acc_stages * cols;
-  const uint32_t budget = (ctas_per_sm >= 2 && (long long)grid_x * ntiles > h->sm_count ? 100u : 190u) * 1024u;
+  // epilogue operands by TMA: bf16 results through the TMA store, operands 16-byte aligned with 16-byte row pitches
+  static const bool tma_store_env = [] { const char* e = getenv("IVF_TC_TMA_STORE"); return !e || atoi(e) != 0; }();
+  static const bool tma_epi_env = [] { const char* e = getenv("IVF_TC_TMA_EPI"); return !e || atoi(e) != 0; }();
+  const bool want_ops = (d->flags == IVF_EP_MASK || d->flags == (IVF_EP_MASK | IVF_EP_ACCUM));
+  bool te = tma_store_env && tma_epi_env && want_ops && ctas_per_sm == 1;
+  if (te && (d->flags & IVF_EP_ACCUM))
+    te = (reinterpret_cast<uintptr_t>(acc_in + d->out_coff) & 15) == 0 && d->out_ld % 4 == 0;
+  if (te && (d->flags & IVF_EP_MASK))
+    te = (reinterpret_cast<uintptr_t>(reinterpret_cast<const __nv_bfloat16*>(mask_y) + d->mask_coff) & 15) == 0 &&
+         d->mask_ld % 8 == 0;
+  const uint32_t pipe_kb = te ? 190u - EPI_STAGING_BYTES / 1024u : 190u;
+  const uint32_t budget = (ctas_per_sm >= 2 && (long long)grid_x * ntiles > h->sm_count ? 100u : pipe_kb) * 1024u;
   int stages = (int)(budget / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  while ((size_t)stages * stage_bytes > 190u * 1024u) --stages;
+  while ((size_t)stages * stage_bytes > pipe_kb * 1024u && stages > 1) --stages;
+  if ((size_t)stages * stage_bytes > pipe_kb * 1024u) te = false;  // a single stage does not leave the room
   if (stages > kiters * ivf_cdiv(mtiles, grid_x)) stages = kiters * ivf_cdiv(mtiles, grid_x);
   if (stages < 1) stages = 1;
   p.stages = stages;
   p.grid_x = grid_x;
+  p.tma_epi = te ? 1 : 0;
+  p.epi_off = (uint32_t)(((size_t)stages * stage_bytes + 1023) & ~(size_t)1023);
   static const bool trace_env = [] { const char* e = getenv("IVF_TC_TRACE"); return e && atoi(e) != 0; }();
   p.trace = trace_env ? reinterpret_cast<long long*>(h->scratch) : nullptr;
 
@@ -757,8 +885,7 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   if (rc) return rc;
   // bf16 results go out through TMA stores (a thread holds one output ROW, and row-scattered 16-byte stores
   // measured ~0.2 us per warp instruction - the epilogue, not the MMAs, bounded the 1x1x1 layers)
-  static const bool tma_store_env = [] { const char* e = getenv("IVF_TC_TMA_STORE"); return !e || atoi(e) != 0; }();
-  CUtensorMap mo = ma, mo2 = ma;
+  CUtensorMap mo = ma, mo2 = ma, mc = ma, mm = ma;
   p.tma_store = (tma_store_env && !(d->flags & IVF_EP_OUT_F32)) ? 1 : 0;
   if (p.tma_store) {
     rc = get_map_out(h, out, d->out_coff, d->out_ld, split_cout > 0 ? split_cout : d->cout, M, &mo);
@@ -769,11 +896,21 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
       if (rc) return rc;
     }
   }
+  if (p.tma_epi) {
+    if (d->flags & IVF_EP_ACCUM) {
+      rc = get_map_rows(h, acc_in, 4, d->out_coff, d->out_ld, d->cout, M, &mc);
+      if (rc) return rc;
+    }
+    if (d->flags & IVF_EP_MASK) {
+      rc = get_map_rows(h, mask_y, 2, d->mask_coff, d->mask_ld, d->cout, M, &mm);
+      if (rc) return rc;
+    }
+  }
   if (kch == 64)
-    return launch_tc<64>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+    return launch_tc<64>(h, d, p, ma, mb, ma2, mo, mo2, mc, mm, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
   if (kch == 32)
-    return launch_tc<32>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
-  return launch_tc<16>(h, d, p, ma, mb, ma2, mo, mo2, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+    return launch_tc<32>(h, d, p, ma, mb, ma2, mo, mo2, mc, mm, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
+  return launch_tc<16>(h, d, p, ma, mb, ma2, mo, mo2, mc, mm, ntiles, scale, shift, acc_in, mask_y, mask_scale, out, out2, st);
 }
 
 extern "C" int ivf_probe_im2col(ivf_handle* h, const ivf_conv_desc* d, const void* in, int m0,
