@@ -550,7 +550,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--clips-per-gpu", type=int, default=128, help="clips per GPU of the end-to-end (C4) leg")
-    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "32")),
+    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "64")),
                     help="clips per launch sequence in the end-to-end leg (the headline `value` stays at BASELINE's 8)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")

@@ -104,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(8) uint64_t epi_bar[EPI_WARPS][2];  // epilogue-operand boxes of a warp have landed
+  __shared__ __align__(8) uint64_t epi_bar[EPI_WARPS][4];  // epilogue-operand boxes of a warp have landed
   __shared__ __align__(16) float s_scale[256], s_shift[256], s_mscale[256];
   // bf16 results leave through TMA stores: per epilogue warp two boxes of 32 rows x 16 channels
   __shared__ __align__(128) uint8_t stage_buf[EPI_WARPS][2][32 * 32];
@@ -128,8 +128,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrival per epilogue warp
-      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&epi_bar[w][a], 1);
     }
+    for (int w = 0; w < EPI_WARPS; ++w)
+      for (int a = 0; a < 4; ++a) mbar_init(&epi_bar[w][a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -290,33 +291,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 32 bytes of ReLU mask per chunk are a row-scattered access: 32 different lines per warp instruction, six
       // instructions per chunk - the L1 tag stage, not the memory, bounded these epilogues (trace: ~2 us per chunk
       // against 0.5 us of a forward chunk).  Instead each warp fetches the [32 rows x 16 channels] boxes of its NEXT
-      // chunk (also across tiles, before that tile's MMAs finish) into its own double-buffered staging area and
-      // reads its row from shared memory (64-/32-byte swizzle: conflict-free per quarter warp).
+      // chunks (also across tiles, before that tile's MMAs finish) into its own ring of staging buffers and reads
+      // its row from shared memory (64-/32-byte swizzle: conflict-free per quarter warp).
       constexpr bool OPS = FL >= 0 && (FL & (IVF_EP_ACCUM | IVF_EP_MASK)) != 0;
       const bool te = OPS && p.tma_epi;
-      const uint32_t epi_stage = smem_base + p.epi_off + (uint32_t)(warp - 2) * 6144u;  // [2][2048 acc | 1024 mask]
+      // per warp 6 KB of staging: two buffers of [2 KB sum | 1 KB mask], or four 1 KB mask buffers when there is no
+      // sum - the boxes of the chunk NB - 1 ahead are requested while the current one is consumed
+      constexpr bool HAS_ACC = FL >= 0 && (FL & IVF_EP_ACCUM) != 0;
+      constexpr int NB = HAS_ACC ? 2 : 4;
+      constexpr uint32_t BUF_BYTES = HAS_ACC ? 3072u : 1024u, MASK_OFF = HAS_ACC ? 2048u : 0u;
+      const uint32_t epi_stage = smem_base + p.epi_off + (uint32_t)(warp - 2) * 6144u;
       const uint8_t* epi_gen = smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off + (size_t)(warp - 2) * 6144u;
-      int ebuf = 0;
-      uint32_t eph0 = 0, eph1 = 0;
       auto chunk_start = [&](int r) { return 16 * ((cgrp + EPI_GROUPS - r) % EPI_GROUPS); };
-      // boxes of chunk (tile mt_, column c0_) -> staging buffer b (whole warp calls; one lane issues)
-      auto issue_ops = [&](int mt_, int c0_, int b) {
-        if (lane == 0) {
-          constexpr uint32_t bytes = ((FL & IVF_EP_ACCUM) ? 2048u : 0u) + ((FL & IVF_EP_MASK) ? 1024u : 0u);
-          mbar_expect_tx(&epi_bar[warp - 2][b], bytes);
-          const int nb_ = ntile * p.bn + c0_, r0_ = mt_ * TILE_M + q * 32;
-          if (FL & IVF_EP_ACCUM) tma_load_2d(epi_stage + b * 3072u, &tmC, &epi_bar[warp - 2][b], nb_, r0_);
-          if (FL & IVF_EP_MASK) tma_load_2d(epi_stage + b * 3072u + 2048u, &tmM, &epi_bar[warp - 2][b], nb_, r0_);
+      // prefetch iterator over this warp's chunks in consumption order: (tile, rotation, column)
+      int pmt = blockIdx.x, prot = 0, pc0 = chunk_start(0);
+      auto pf_norm = [&]() {
+        while (pmt < p.mtiles && pc0 >= p.bn) {
+          pmt += gridDim.x;
+          prot = prot + 1 == EPI_GROUPS ? 0 : prot + 1;
+          pc0 = chunk_start(prot);
         }
       };
-      if (te) {  // first chunk of this warp
-        int mt_ = blockIdx.x, r_ = 0, c_ = chunk_start(0);
-        while (mt_ < p.mtiles && c_ >= p.bn) {
-          mt_ += gridDim.x;
-          r_ = r_ + 1 == EPI_GROUPS ? 0 : r_ + 1;
-          c_ = chunk_start(r_);
+      int issued = 0, cons = 0;
+      // boxes of the iterator's chunk -> staging buffer issued % NB (whole warp calls; one lane issues)
+      auto issue_next = [&]() {
+        if (pmt >= p.mtiles) return;
+        const int b = issued % NB;
+        if (lane == 0) {
+          constexpr uint32_t bytes = (HAS_ACC ? 2048u : 0u) + ((FL & IVF_EP_MASK) ? 1024u : 0u);
+          mbar_expect_tx(&epi_bar[warp - 2][b], bytes);
+          const int nb_ = ntile * p.bn + pc0, r0_ = pmt * TILE_M + q * 32;
+          if (HAS_ACC) tma_load_2d(epi_stage + b * BUF_BYTES, &tmC, &epi_bar[warp - 2][b], nb_, r0_);
+          if (FL & IVF_EP_MASK) tma_load_2d(epi_stage + b * BUF_BYTES + MASK_OFF, &tmM, &epi_bar[warp - 2][b], nb_, r0_);
         }
-        if (mt_ < p.mtiles) issue_ops(mt_, c_, 0);
+        ++issued;
+        pc0 += 16 * EPI_GROUPS;
+        pf_norm();
+      };
+      if (te) {
+        pf_norm();
+        for (int i = 0; i < NB - 1; ++i) issue_next();
       }
       EpilogueArgs eaT = ea;
       eaT.cout = 1 << 30;  // TMA zero-fills past the tensor and the TMA store clips: every chunk is a full chunk
@@ -340,20 +354,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // global operands of the chunk are requested before the TMEM load; the other warps of the scheduler
           // cover the latency
           if (te) {
-            // next chunk of this warp (possibly in a later tile) -> the other buffer, whose last reader was the
-            // previous iteration of this loop
-            int mt_ = mt, r_ = rot, c_ = c0 + 16 * EPI_GROUPS;
-            while (mt_ < p.mtiles && c_ >= p.bn) {
-              mt_ += gridDim.x;
-              r_ = r_ + 1 == EPI_GROUPS ? 0 : r_ + 1;
-              c_ = chunk_start(r_);
-            }
+            // the buffer the next request goes to was last read in the previous iteration of this loop
             __syncwarp();
-            if (mt_ < p.mtiles) issue_ops(mt_, c_, ebuf ^ 1);
-            mbar_wait(&epi_bar[warp - 2][ebuf], ebuf ? eph1 : eph0);
-            if (ebuf) eph1 ^= 1u; else eph0 ^= 1u;
-            const uint8_t* st = epi_gen + ebuf * 3072;
-            if (FL & IVF_EP_ACCUM) {
+            issue_next();
+            const int b = cons % NB;
+            mbar_wait(&epi_bar[warp - 2][b], (uint32_t)(cons / NB) & 1u);
+            ++cons;
+            const uint8_t* st = epi_gen + b * BUF_BYTES;
+            if (HAS_ACC) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 cur.ac[j] = *reinterpret_cast<const float4*>(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
@@ -361,9 +369,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (FL & IVF_EP_MASK) {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                cur.mk[j] = *reinterpret_cast<const uint4*>(st + 2048 + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4));
+                cur.mk[j] = *reinterpret_cast<const uint4*>(st + MASK_OFF + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4));
             }
-            ebuf ^= 1;
           } else {
             epilogue_prefetch<FL>(ea, nb, out_row, mask_row, row_ok, cur);
           }
@@ -778,8 +785,11 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
   // grid covers the SMs; the activation tile is re-read per N tile from L2, which is cheap there.
   // (Rows of the weight box beyond cout_pad are TMA zero fill; the epilogue stores only real channels.)
   const int mtiles = ivf_cdiv(M, TILE_M);
-  if (mtiles * ntiles < h->sm_count) {
-    int want = std::max(1, h->sm_count / mtiles);  // one CTA per SM: stay within one wave
+  // IVF_TC_SPREAD = the share of the SMs (per cent) one launch tries to cover this way (default 100)
+  static const int spread = [] { const char* e = getenv("IVF_TC_SPREAD"); return e ? atoi(e) : 100; }();
+  const int sm_target = std::max(1, h->sm_count * spread / 100);
+  if (mtiles * ntiles < sm_target) {
+    int want = std::max(1, sm_target / mtiles);  // one CTA per SM: stay within one wave
     int bn2 = (ivf_cdiv(d->cout, want) + 15) / 16 * 16;
     if (bn2 < 32) bn2 = 32;
     if (bn2 < bn) {
