@@ -96,6 +96,7 @@ typedef struct ivf_conv_desc {
    * satisfy falls back to the model.  The host side measures a few plans per layer shape once and passes
    * the fastest (interpreting_video_features_b200/tune.py). */
   int32_t plan_kwm, plan_mt, plan_acc, plan_ncta, plan_ntiles;
+  int32_t plan_ds;       /* output depths stacked along the MMA's N by the halo-slab kernel (0 = its choice, 1, 2) */
 } ivf_conv_desc;
 
 int ivf_conv_bf16_kchunk(int cin);   /* channels per K stage: 16, 32 or 64 */
@@ -107,6 +108,8 @@ int ivf_conv_bf16_cout_pad(int cout);
  * {channels per slab row, N tile, N tiles, accumulators per tile, rows per tile, TMEM stages, slab stages,
  *  weight stages, tiles, dynamic smem bytes, kw taps merged into N, CTAs per work item (2 = cta_group::2 pairs)} when the halo-slab kernel serves it, 0 for the im2col kernel. */
 int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* plan);
+/* depth stacking (plan_ds) of that plan: 1 or 2, 0 when the layer does not go to the halo-slab kernel */
+int ivf_conv_slab_plan_ds(const ivf_conv_desc* d, int sm_count);
 
 int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                const float* scale, const float* shift, const float* acc_in, const void* mask_y,

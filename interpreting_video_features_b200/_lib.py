@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n", "id", "ih", "iw", "od", "oh", "ow", "cin", "cout", "kd", "kh", "kw", "sd", "sh", "sw",
         "pd", "ph", "pw", "transposed", "in_ld", "in_coff", "out_ld", "out_coff", "mask_ld",
-        "mask_coff", "flags", "dtype", "plan_kwm", "plan_mt", "plan_acc", "plan_ncta", "plan_ntiles")]
+        "mask_coff", "flags", "dtype", "plan_kwm", "plan_mt", "plan_acc", "plan_ncta", "plan_ntiles", "plan_ds")]
 
 
 class ConvSplit(C.Structure):
@@ -62,6 +62,7 @@ SIGNATURES = {
     "ivf_conv_bf16_ntile": (_I, [_I]),
     "ivf_conv_bf16_cout_pad": (_I, [_I]),
     "ivf_conv_slab_plan": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_int)]),
+    "ivf_conv_slab_plan_ds": (_I, [C.POINTER(ConvDesc), _I]),
     "ivf_conv3d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ivf_conv3d_split": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvSplit), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _P]),

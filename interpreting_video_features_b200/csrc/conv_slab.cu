@@ -21,6 +21,15 @@
 // between column blocks, done with warp shuffles plus a shared-memory exchange of the first kwm-1 rows of
 // the next 32-row segment (published by every warp for its columns, one block barrier per tile).
 //
+// depth stacking (ds = 2): the other way to a wide N for the layers with few output channels, without the shift-
+// and-add epilogue of the kw-merge.  The slab of input depth z feeds output depth d through depth tap kd = z - d + pd,
+// so a tile that owns TWO consecutive output depths d0, d0+1 reads each of its kd+1 slabs once and multiplies it by
+// the weight rows [W[kd(d0)] ; W[kd(d0+1)]] stacked along N: one MMA of N = 2*bn writes both depths' accumulators,
+// which sit side by side in TMEM (the first / last slab reach only one of the two depths: N = bn into that half).
+// Same FLOPs, (kd+1)/(2 kd) of the MMA instructions and slab loads - and from N = 128 up an MMA runs at the math
+// rate instead of the issue rate (tools/mma_bench.cu).  The slab of offset 0 reaches both depths and is issued first
+// (it needs pd >= 1), so one accumulate flag serves the whole N.
+//
 // NCTA = 2 (cta_group::2): a CTA pair on one TPC works on two row-adjacent tiles in lockstep.  Each SM loads
 // its own slab and HALF of the weight rows; the leader CTA issues M = 256 MMAs that read both SMs' shared
 // memory and write each SM's TMEM.  Per SM an MMA then fetches 4 KB + 16N bytes instead of 4 KB + 32N (the
@@ -73,6 +82,8 @@ struct SlabParams {
   int cin, cchunks, cin_pad;
   int cout, bn, ntiles, slot;  // slot = TMEM columns of one 128-row accumulator (>= kwm*bn)
   int kwm;                     // kw taps merged into the MMA's N (1 = none)
+  int ds;                      // output DEPTHS per tile stacked along the MMA's N (1 = none, 2), see below
+  int dgroups;                 // dd / ds
   int num_tiles;
   int out_ld, out_coff, mask_ld, mask_coff, flags;
   int a_stages, b_stages, tmem_cols;
@@ -102,9 +113,17 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile, 
   const int hp = ncta == 2 ? (p.htiles + 1) / 2 : p.htiles;
   t.h0 = ((r % hp) * ncta + rank) * p.th;
   r /= hp;
-  t.dz = r % p.dd;
-  t.nn = r / p.dd;
+  t.dz = (r % p.dgroups) * p.ds;  // first output depth of the tile
+  t.nn = r / p.dgroups;
   return t;
+}
+
+// Slabs of a tile in issue order: offset of the idx-th slab's input depth from the tile's first output depth.
+// ds == 1: ascending depth taps (kd = idx).  ds == 2: offset 0 first (it reaches both depths), then the rest.
+__device__ __forceinline__ int slab_offset(const SlabParams& p, int idx) {
+  if (p.ds == 1) return idx - p.pd;
+  if (idx == 0) return 0;
+  return idx <= p.pd ? -idx : idx - p.pd;
 }
 
 // KCH = channels per slab row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B, for
@@ -198,8 +217,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = item0; tile < p.num_tiles; tile += item_step) {
         const TileCoord t = decode_tile(p, tile, NCTA, rank);
-        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
-          const int zd = t.dz + kd_i - p.pd;
+        for (int si = 0; si < p.kd + p.ds - 1; ++si) {
+          const int zd = t.dz + slab_offset(p, si);
           if (zd < 0 || zd >= p.dd) continue;  // an all-padding depth tap contributes nothing
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(&a_empty[stage], phase ^ 1u);
@@ -235,15 +254,47 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = item0; tile < p.num_tiles; tile += item_step) {
         const TileCoord t = decode_tile(p, tile, NCTA, rank);
-        for (int kd_i = 0; kd_i < p.kd; ++kd_i) {
-          const int zd = t.dz + kd_i - p.pd;
+        for (int si = 0; si < p.kd + p.ds - 1; ++si) {
+          const int off = slab_offset(p, si);
+          const int zd = t.dz + off;
           if (zd < 0 || zd >= p.dd) continue;
+          // output depths (of the tile's ds) this slab reaches: s_lo .. s_lo + ns - 1, through depth tap off - s + pd
+          const int s_lo = max(0, off + p.pd - (p.kd - 1)), ns = min(p.ds - 1, off + p.pd) - s_lo + 1;
+          const int kd_i = off - s_lo + p.pd;
           for (int cc = 0; cc < p.cchunks; ++cc) {
             for (int kh_i = 0; kh_i < p.kh; ++kh_i) {
               mbar_wait(&b_empty[stage], phase ^ 1u);
               const int tap0 = (kd_i * p.kh + kh_i) * p.kw;
               if ((p.diag & 2) && b_loads >= p.b_stages) {
                 if (leader && rank == 0) mbar_arrive(&b_full[stage]);
+              } else if (leader && p.ds == 2) {
+                // stacked weight rows: block b of the MMA's N = depth s_lo + b = depth tap kd_i - b
+                const uint32_t dst0 = b_base + stage * p.b_stage_bytes;
+                const uint32_t blk = (uint32_t)p.bn * ROWB;  // bytes of one depth's rows of a tap
+                if constexpr (NCTA == 2) {
+                  // the pair splits N in halves: with two depths CTA r holds depth s_lo + r whole (two boxes of
+                  // bn/2 rows), with one depth half of its rows as in the unstacked case
+                  const uint32_t per_cta = (uint32_t)p.kw * (ns == 2 ? blk : blk / 2);
+                  if (rank == 0) mbar_expect_tx(&b_full[stage], 2u * per_cta);
+                  for (int kw_i = 0; kw_i < p.kw; ++kw_i) {
+                    if (ns == 2) {
+                      const int tap = ((kd_i - rank) * p.kh + kh_i) * p.kw + kw_i;
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage], tap * p.cin_pad + cc * KCH,
+                                       t.nt * p.bn);
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes + blk / 2, &tmB, &b_full[stage],
+                                       tap * p.cin_pad + cc * KCH, t.nt * p.bn + p.bn / 2);
+                    } else {
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                                       (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn + rank * (p.bn / 2));
+                    }
+                  }
+                } else {
+                  mbar_expect_tx(&b_full[stage], (uint32_t)(p.kw * ns) * blk);
+                  for (int kw_i = 0; kw_i < p.kw; ++kw_i)
+                    for (int b = 0; b < ns; ++b)
+                      tma_load_2d(dst0 + kw_i * p.b_tap_bytes + b * blk, &tmB, &b_full[stage],
+                                  (((kd_i - b) * p.kh + kh_i) * p.kw + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
+                }
               } else if (leader) {
                 if constexpr (NCTA == 2) {
                   // The N rows of an MMA (kwm stacked taps of bn rows) are split in halves over the pair:
@@ -287,7 +338,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int mw = warp == 1 ? 0 : 1, mstep = p.mt >= 2 ? 2 : 1;
     if (rank == 0 && (mw == 0 || p.mt >= 2)) {  // of a pair only the leader CTA issues
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.bn * p.kwm);
+      const uint32_t idesc1 = make_idesc_bf16(128 * NCTA, p.bn * p.kwm);
+      const uint32_t idesc2 = make_idesc_bf16(128 * NCTA, p.bn * 2);  // two stacked depths (ds == 2: kwm == 1)
+      const int ds = p.ds;
       const uint32_t desc_hi = smem_desc_hi(8 * ROWB, LAYOUT);  // 8-row swizzle atoms back to back
       // everything the loop needs, in registers (not re-read from the parameter bank per MMA)
       const int kd_n = p.kd, kh_n = p.kh, kw_n = p.kw, pd = p.pd, dd = p.dd, cin = p.cin, cchunks = p.cchunks;
@@ -308,11 +361,16 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tphase = p.acc_stages == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
         mbar_wait(&t_empty[acc], tphase ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_acc + (uint32_t)acc * (uint32_t)mt * slot;
+        const uint32_t d_tmem = tmem_acc + (uint32_t)acc * (uint32_t)(mt * ds) * slot;
         uint32_t accum = 0;  // 0 for the first MMA group of the tile (overwrite), 1 afterwards
-        for (int kd_i = 0; kd_i < kd_n; ++kd_i) {
-          const int zd = t.dz + kd_i - pd;
+        for (int si = 0; si < kd_n + ds - 1; ++si) {
+          const int off = slab_offset(p, si);
+          const int zd = t.dz + off;
           if (zd < 0 || zd >= dd) continue;
+          // the tile's output depths this slab reaches (ds == 1: the one) and the MMA shape / TMEM columns for them
+          const int s_lo = max(0, off + pd - (kd_n - 1)), ns = min(ds - 1, off + pd) - s_lo + 1;
+          const uint32_t idesc = ns == 2 ? idesc2 : idesc1;
+          const uint32_t d_slab = d_tmem + (uint32_t)s_lo * slot;
           for (int cc = 0; cc < cchunks; ++cc) {
             const int crem = cin - cc * KCH;
             const int ksteps = crem >= KCH ? KSTEPS : (crem + 15) / 16;
@@ -326,8 +384,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               // kw taps in merged groups of kwm (one MMA of N = kwm*bn each): group g reads the slab g*kwm pixels
               // further and the next group of weight rows.  Unrolled over the (at most 5) groups so that every
               // operand address is base + constant * g: no loop-carried adds between the MMAs.
-              const uint32_t a_row = row_lo + (uint32_t)mw * 128u * ROW16, d0 = d_tmem + (uint32_t)mw * slot;
-              const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)mstep * slot;
+              const uint32_t a_row = row_lo + (uint32_t)mw * 128u * ROW16, d0 = d_slab + (uint32_t)(mw * ds) * slot;
+              const uint32_t a_inc = (uint32_t)mstep * 128u * ROW16, d_inc = (uint32_t)(mstep * ds) * slot;
               const uint32_t a_grp = kwm * ROW16;
               if (leader) {
 #pragma unroll
@@ -435,17 +493,18 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // boundary rows of the tile visible
         }
-        for (int m = 0; m < p.mt; ++m) {
+        for (int sm = 0; sm < p.ds * p.mt; ++sm) {
+          const int sdep = p.ds == 1 ? 0 : sm / p.mt, m = p.ds == 1 ? sm : sm - sdep * p.mt;  // stacked depth, accumulator
           const int v = m * 128 + q * 32 + lane;  // padded-width pixel number inside the tile
           const int r = v / p.wp;
           const int c = v - r * p.wp;
           const int hrow = t.h0 + r;
           const bool ok = r < p.th && hrow < p.hh && c < p.ww;
-          const size_t pix = (((size_t)t.nn * p.dd + t.dz) * p.hh + hrow) * p.ww + c;
+          const size_t pix = (((size_t)t.nn * p.dd + t.dz + sdep) * p.hh + hrow) * p.ww + c;
           const size_t out_row = pix * p.out_ld + p.out_coff;
           const size_t mask_row = pix * p.mask_ld + p.mask_coff;
           const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) +
-                                 (uint32_t)((acc * p.mt + m) * p.slot);
+                                 (uint32_t)(((acc * p.mt + m) * p.ds + sdep) * p.slot);
           EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
                        // the scheduler cover the latency
           if (p.kwm == 1) {
@@ -637,10 +696,20 @@ int env_int(const char* name, int dflt) {
 // the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
 bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best);
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
+  // depth stacking is a request (plan_ds from the host-side tuner, IVF_SLAB_DS for diagnostics): a layer that
+  // cannot stack (odd depth, no front padding, N too wide) silently runs unstacked
+  ivf_conv_desc dd_ = *d;
+  if (!dd_.plan_ds) dd_.plan_ds = env_int("IVF_SLAB_DS", 1);
+  if (dd_.plan_ds == 2) {
+    if (slab_config_impl(&dd_, sm_count, best)) return true;
+    dd_.plan_ds = 1;
+  }
+  d = &dd_;
   if (slab_config_impl(d, sm_count, best)) return true;
-  if (d->plan_kwm | d->plan_mt | d->plan_acc | d->plan_ncta | d->plan_ntiles) {  // unsatisfiable request
+  if (d->plan_kwm | d->plan_mt | d->plan_acc | d->plan_ncta | d->plan_ntiles | d->plan_ds) {  // unsatisfiable request
     ivf_conv_desc auto_d = *d;
     auto_d.plan_kwm = auto_d.plan_mt = auto_d.plan_acc = auto_d.plan_ncta = auto_d.plan_ntiles = 0;
+    auto_d.plan_ds = 1;
     return slab_config_impl(&auto_d, sm_count, best);
   }
   return false;
@@ -666,6 +735,9 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   const int forced_acc = d->plan_acc ? d->plan_acc : env_int("IVF_SLAB_ACC", 0);
   const int forced_kwm = d->plan_kwm ? d->plan_kwm : env_int("IVF_SLAB_KWM", 0);
   const int forced_ncta = d->plan_ncta;
+  // depth stacking: 1 or 2, resolved by slab_config
+  const int forced_ds = d->plan_ds ? d->plan_ds : 1;
+  const bool ds2_ok = d->id % 2 == 0 && d->pd >= 1 && d->kd >= 2 && !(d->flags & IVF_EP_LSTM);
   const bool allow_pair = env_int("IVF_SLAB_2CTA", 1) != 0 && sm_count % 2 == 0;
   double best_cost = 1e30;
   bool found = false;
@@ -681,12 +753,18 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
     if (d->kw % kwm || kwm * bn > 256) continue;
     if (ncta == 2 && kwm == 3) continue;  // the pair splits the stacked N rows in halves: whole taps or half a tap
     if (forced_kwm && kwm != forced_kwm && !(forced_kwm > 1 && (d->kw % forced_kwm || forced_kwm * bn > 256))) continue;
+    for (int ds = 1; ds <= 2; ++ds) {
+    if (forced_ds && ds != forced_ds) continue;
+    // two stacked depths: their accumulators are adjacent TMEM column blocks of exactly bn columns
+    if (ds == 2 && (!ds2_ok || kwm != 1 || bn % 32 || 2 * bn > 256)) continue;
     const int slot = (kwm * bn + 31) / 32 * 32;
     // one CTA's share of a tap's weight rows: all bn, or (pair) bn/2 when kwm == 1; with kwm 2/4 a pair CTA holds
     // kwm/2 whole taps per merged group.  Taps are dense (bn % 16 == 0 keeps them on swizzle-atom boundaries).
-    const uint32_t b_tap = (uint32_t)((ncta == 2 && kwm == 1) ? bn / 2 : bn) * rowb;
-    const uint32_t b_stage = (uint32_t)bn * rowb * (uint32_t)d->kw / ncta;
+    // Two stacked depths double the rows of a tap (a pair CTA then holds one depth's bn rows).
+    const uint32_t b_tap = (uint32_t)((ncta == 2 && kwm == 1) ? bn / 2 : bn) * rowb * ds;
+    const uint32_t b_stage = (uint32_t)bn * rowb * (uint32_t)d->kw / ncta * ds;
     if (b_tap % (8u * rowb)) continue;
+    if (ds == 2 && ncta == 2 && (bn / 2) % 8) continue;
     for (int acc_stages = 2; acc_stages >= 1; --acc_stages) {
       if (forced_acc && acc_stages != forced_acc) continue;
       for (int mt = 4; mt >= 1; --mt) {
@@ -697,7 +775,7 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         const int htiles = (d->ih + th - 1) / th;
         th = (d->ih + htiles - 1) / htiles;  // balance the rows over the tiles
         const int mt_eff = (th * wp + 127) / 128;
-        if (acc_stages * mt_eff * slot > 512) continue;
+        if (acc_stages * mt_eff * ds * slot > 512) continue;
         const int rows = th + d->kh - 1;
         if (rows > 256) continue;
         const uint32_t a_stage =
@@ -712,22 +790,24 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
         int b_stages = (int)((budget - (uint32_t)a_stages * a_stage) / b_stage);
         if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
         // ---- cost
-        const double tiles = (double)d->n * d->id * ((htiles + ncta - 1) / ncta) * ntiles;  // work items
+        const double tiles = (double)d->n * (d->id / ds) * ((htiles + ncta - 1) / ncta) * ntiles;  // work items
         const double waves = ceil(tiles / (sm_count / ncta));
-        const double n_mma = (double)taps / kwm * ksteps_total * mt_eff;
-        const int n_eff = kwm * bn;
+        // per tile: kd + ds - 1 slabs; with two depths the first and the last run at N = bn, the others at 2 bn -
+        // modelled as (kd + 1) slabs' MMAs at the wide N (slightly pessimistic)
+        const double n_mma = (double)(d->kd + ds - 1) * d->kh * d->kw / kwm * ksteps_total * mt_eff;
+        const int n_eff = kwm * bn * ds;
         const int cin_real_bytes = (cin < kch ? cin : kch) * 2;
-        const double slab_smem = (double)d->kd * cchunks * rows * wp * rowb;
-        const double slab_l2 = (double)d->kd * cchunks * rows * wp * (cin_real_bytes < 128 ? 128 : cin_real_bytes);
-        const double w_bytes = (double)taps * cchunks * bn * rowb / ncta;  // per SM
+        const double slab_smem = (double)(d->kd + ds - 1) * cchunks * rows * wp * rowb;
+        const double slab_l2 = (double)(d->kd + ds - 1) * cchunks * rows * wp * (cin_real_bytes < 128 ? 128 : cin_real_bytes);
+        const double w_bytes = (double)taps * ds * cchunks * bn * rowb / ncta;  // per SM
         // per SM: 4 KB of activations + its share of the weight rows at ~64 B/clk, never below the math
         double per_mma = 64.0 + n_eff / (2.0 * ncta);
         if (per_mma < n_eff / 2.0) per_mma = n_eff / 2.0;
         const double mma_clk = n_mma * per_mma + 0.5 * (slab_smem + w_bytes) / 128.0;
         const double l2_clk = (slab_l2 + w_bytes) / 40.0;
-        const double epi_clk = (double)mt_eff * (bn / 16) *
+        const double epi_clk = (double)mt_eff * ds * (bn / 16) *
                                (220.0 + 200.0 * (kwm - 1) + ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 150.0 : 0.0)) +
-                               ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 1200.0 * mt_eff : 0.0);
+                               ((d->flags & (IVF_EP_MASK | IVF_EP_ACCUM)) ? 1200.0 * mt_eff * ds : 0.0);
         double tile_clk = mma_clk > l2_clk ? mma_clk : l2_clk;
         if (acc_stages == 1) tile_clk += epi_clk;
         else if (epi_clk > tile_clk) tile_clk = epi_clk;
@@ -745,6 +825,8 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->ntiles = ntiles;
           p->slot = slot;
           p->kwm = kwm;
+          p->ds = ds;
+          p->dgroups = d->id / ds;
           p->ncta = ncta;
           p->acc_stages = acc_stages;
           p->a_stages = a_stages;
@@ -757,10 +839,11 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->a_tx = (uint32_t)rows * wp * rowb;
           p->b_tx = b_stage;
           int cols = 32;
-          while (cols < acc_stages * mt_eff * slot) cols <<= 1;
+          while (cols < acc_stages * mt_eff * ds * slot) cols <<= 1;
           p->tmem_cols = cols;
         }
       }
+    }
     }
     }
     }
@@ -852,13 +935,13 @@ int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* i
   p.out_ld = d->out_ld; p.out_coff = d->out_coff;
   p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
   p.flags = d->flags;
-  long long tiles = (long long)d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;  // work items
+  long long tiles = (long long)d->n * p.dgroups * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;  // work items
   IVF_REQUIRE(tiles < (1ll << 31), "conv(slab): too many tiles");
   p.num_tiles = (int)tiles;
   p.diag = env_int("IVF_SLAB_DIAG", 0);
   if (env_int("IVF_SLAB_VERBOSE", 0))
-    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) items %d ncta %d\n",
-            d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.kwm, p.mt, p.th,
+    fprintf(stderr, "slab: %dx%dx%d c%d->%d k%d%d%d | kch %d bn %d x%d kwm %d ds %d mt %d th %d acc %d a_st %d(%u) b_st %d(%u) items %d ncta %d\n",
+            d->id, d->ih, d->iw, d->cin, d->cout, d->kd, d->kh, d->kw, p.kch, p.bn, p.ntiles, p.kwm, p.ds, p.mt, p.th,
             p.acc_stages, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.num_tiles, p.ncta);
 
   CUtensorMap ma, mb;
@@ -894,9 +977,21 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   if (!slab_config(d, sm_count, &p)) return 0;
   plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
   plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
-  plan[8] = d->n * d->id * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
+  plan[8] = d->n * p.dgroups * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
   plan[9] = (int)(p.xch_off + 2u * 4u * (uint32_t)p.mt * (uint32_t)p.xch_seg * 4u);
   plan[10] = p.kwm;
   plan[11] = p.ncta;
   return 1;
+}
+
+// depth stacking of the plan ivf_conv_slab_plan reports (1 or 2; 0 when the layer is not served by this kernel)
+extern "C" int ivf_conv_slab_plan_ds(const ivf_conv_desc* d, int sm_count) {
+  if (!d) return 0;
+  ivf_handle fake;
+  fake.sm_count = sm_count;
+  if (!ivf_conv3d_slab_eligible(&fake, d)) return 0;
+  const ivf_conv_desc dv = slab_view(d);
+  SlabParams p;
+  if (!slab_config(&dv, sm_count, &p)) return 0;
+  return p.ds;
 }

@@ -135,8 +135,9 @@ def conv_desc(x, out, kernel, stride, pad_front, flags=0, scale=None, acc_in=Non
     if out.buf.dtype == torch.float32 and x.buf.dtype == torch.bfloat16:
         flags |= EP_OUT_F32
     d.flags = flags
-    if plan is not None:
-        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = plan
+    if plan is not None:  # (kwm, mt, acc, ncta, ntiles[, ds]); five-entry requests leave depth stacking to the library's default
+        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = plan[:5]
+        d.plan_ds = plan[5] if len(plan) > 5 else 0
     return d
 
 

@@ -65,22 +65,29 @@ def _plan_of(d, sm_count):
     return tuple(out)
 
 
+def _ds_of(d, sm_count):
+    return int(_lib.load().ivf_conv_slab_plan_ds(C.byref(d), sm_count))
+
+
 def candidates(make_desc, sm_count):
-    """Distinct plans the kernel accepts for this layer: list of request tuples (kwm, mt, acc, ncta, ntiles)."""
+    """Distinct plans the kernel accepts for this layer: list of request tuples (kwm, mt, acc, ncta, ntiles, ds);
+    ds = output depths stacked along the MMA's N (conv_slab.cu)."""
     seen, reqs = set(), []
     kw = make_desc(None).kw
-    for ncta, kwm, mt, acc, nt in itertools.product((1, 2), (1, 2, 3, 4), (1, 2, 3, 4), (1, 2), (0, 1, 2, 3, 4, 6, 8)):
-        if kw % kwm:
+    for ds, ncta, kwm, mt, acc, nt in itertools.product((1, 2), (1, 2), (1, 2, 3, 4), (1, 2, 3, 4), (1, 2),
+                                                        (0, 1, 2, 3, 4, 6, 8)):
+        if kw % kwm or (ds == 2 and kwm != 1):
             continue
-        req = (kwm, mt, acc, ncta, nt)
-        p = _plan_of(make_desc(req), sm_count)
+        req = (kwm, mt, acc, ncta, nt, ds)
+        d = make_desc(req)
+        p = _plan_of(d, sm_count)
         if p is None:
             continue
-        got = (p[10], p[3], p[5], p[11], p[2], p[1])  # kwm mt acc ncta ntiles bn
-        if (p[10], p[3], p[5], p[11]) != (kwm, mt, acc, ncta) or got in seen:
+        got = (p[10], p[3], p[5], p[11], p[2], p[1], _ds_of(d, sm_count))  # kwm mt acc ncta ntiles bn ds
+        if (p[10], p[3], p[5], p[11], got[6]) != (kwm, mt, acc, ncta, ds) or got in seen:
             continue
         seen.add(got)
-        reqs.append((kwm, mt, acc, ncta, p[2]))
+        reqs.append((kwm, mt, acc, ncta, p[2], ds))
     return reqs
 
 

@@ -127,9 +127,12 @@ def test_shipped_tile_plans_are_accepted_by_the_kernel():
         if req is None:
             continue
         n_req += 1
-        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = req
+        d.plan_kwm, d.plan_mt, d.plan_acc, d.plan_ncta, d.plan_ntiles = req[:5]
+        d.plan_ds = req[5] if len(req) > 5 else 0
         out = (C.c_int * 12)()
         assert lib.ivf_conv_slab_plan(C.byref(d), 148, out) == 1, key
         got = (out[10], out[3], out[5], out[11], out[2])  # kwm, mt, acc, ncta, ntiles
-        assert got == tuple(req), (key, req, got)
+        assert got == tuple(req[:5]), (key, req, got)
+        if len(req) > 5:  # depth stacking (conv_slab.cu) as requested
+            assert lib.ivf_conv_slab_plan_ds(C.byref(d), 148) == req[5], (key, req)
     assert n_req >= 1

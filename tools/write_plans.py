@@ -44,6 +44,6 @@ for k, vs in votes.items():
     print(k, vs, "->", best)
 os.makedirs("gpurun_out", exist_ok=True)
 out = {"device": torch.cuda.get_device_name(0), "fields": list(tune._FIELDS),
-       "request": ["kwm", "mt", "acc", "ncta", "ntiles"], "plans": plans}
+       "request": ["kwm", "mt", "acc", "ncta", "ntiles", "ds"], "plans": plans}
 json.dump(out, open("gpurun_out/plans_sm100.json", "w"), indent=1, sort_keys=True)
 print("wrote %d plans" % len(plans))
