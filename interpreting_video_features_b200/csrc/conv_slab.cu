@@ -564,6 +564,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         case IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_MASK>{}); break;
         case IVF_EP_ACCUM | IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_MASK>{}); break;
         case 0: run_epilogue(std::integral_constant<int, 0>{}); break;
+        // the ConvLSTM's recurrent convolutions (fp32 pre-activations: x-conv + bias, h-conv accumulated onto them)
+        case IVF_EP_ACCUM | IVF_EP_OUT_F32: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_OUT_F32>{}); break;
+        case IVF_EP_AFFINE | IVF_EP_OUT_F32: run_epilogue(std::integral_constant<int, IVF_EP_AFFINE | IVF_EP_OUT_F32>{}); break;
         default: run_epilogue(std::integral_constant<int, -1>{}); break;
       }
     }

@@ -429,6 +429,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       case IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_MASK>{}); break;
       case IVF_EP_ACCUM | IVF_EP_MASK: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_MASK>{}); break;
       case 0: run_epilogue(std::integral_constant<int, 0>{}); break;
+        // the ConvLSTM's recurrent convolutions (fp32 pre-activations: x-conv + bias, h-conv accumulated onto them)
+        case IVF_EP_ACCUM | IVF_EP_OUT_F32: run_epilogue(std::integral_constant<int, IVF_EP_ACCUM | IVF_EP_OUT_F32>{}); break;
+        case IVF_EP_AFFINE | IVF_EP_OUT_F32: run_epilogue(std::integral_constant<int, IVF_EP_AFFINE | IVF_EP_OUT_F32>{}); break;
       default: run_epilogue(std::integral_constant<int, -1>{}); break;
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();  // the boxes are read until the stores complete
