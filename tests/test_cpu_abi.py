@@ -103,6 +103,31 @@ def test_slab_plan_diagnostic_needs_no_gpu():
     assert plan((2, 4, 4), 64, 64, (3, 3, 3), (1, 1, 1))[0] == 0         # map narrower than 7 -> im2col kernel
 
 
+def test_depth_stacking_is_a_soft_plan_request():
+    """ivf_conv_desc.plan_ds = 2 (conv_slab.cu depth stacking): honoured where the layer can stack two output depths
+    (even depth, front padding >= 1, N of whole 32-column TMEM blocks, 2 N <= 256), otherwise the layer silently
+    runs unstacked - and the default is unstacked."""
+    import ctypes as C
+    from interpreting_video_features_b200 import _lib
+    lib = _lib.load()
+
+    def ds_of(dhw, cin, cout, k, pf, want):
+        d = _lib.ConvDesc()
+        d.n, (d.id, d.ih, d.iw), (d.od, d.oh, d.ow) = 8, dhw, dhw
+        d.cin, d.cout, (d.kd, d.kh, d.kw), (d.pd, d.ph, d.pw) = cin, cout, k, pf
+        d.sd = d.sh = d.sw = 1
+        d.in_ld, d.out_ld, d.dtype, d.flags, d.plan_ds = max(cin, 32), cout, _lib.IVF_BF16, 3, want
+        return lib.ivf_conv_slab_plan_ds(C.byref(d), 148)
+
+    stem = ((8, 112, 112), 24, 64, (4, 4, 4), (1, 1, 1))
+    assert ds_of(*stem, 2) == 2 and ds_of(*stem, 0) == 1 and ds_of(*stem, 1) == 1
+    assert ds_of((8, 56, 56), 192, 64, (3, 3, 3), (1, 1, 1), 2) == 2          # Conv3d_2c data gradient
+    assert ds_of((7, 56, 56), 192, 64, (3, 3, 3), (1, 1, 1), 2) == 1          # odd depth
+    assert ds_of((8, 56, 56), 64, 192, (3, 3, 3), (1, 1, 1), 2) in (1, 2)     # N = 192: only as two N tiles of 96
+    assert ds_of((8, 28, 28), 32, 16, (3, 3, 3), (1, 1, 1), 2) == 1           # bn = 16 is not a whole TMEM block
+    assert ds_of((8, 30, 40), 32, 128, (1, 5, 5), (0, 2, 2), 2) == 1          # 2-D kernel: no depth taps to share
+
+
 def test_shipped_tile_plans_are_accepted_by_the_kernel():
     """plans_sm100.json (measured on a B200, tools/write_plans.py): every shape key parses into the descriptor
     fields tune.py hashes, and every stored request is a plan ivf_conv_slab_plan still accepts for that shape -

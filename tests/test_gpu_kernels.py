@@ -181,14 +181,23 @@ def test_conv_data_gradient_with_fused_mask_and_accumulate(dev, mode, case):
     torch.cuda.synchronize()
     tol = 1e-2 if mode == "bf16" else 1e-4
     assert rel_err(gxa.ncdhw().cpu(), ref) < tol
+    if mode == "bf16" and case in SLAB_CASES:
+        # the same data gradient with two output depths stacked along the MMA's N where the layer allows it (a
+        # request the kernel may decline: odd depth, no front padding, N not in whole TMEM blocks)
+        gxa.buf.zero_()
+        ops.conv3d(dza, wd, gxa, k, (1, 1, 1), pfd, acc_in=acc_a, mask=ya, mask_scale=sc_prev.to(dev),
+                   plan=(0, 0, 0, 0, 0, 2))
+        assert rel_err(gxa.ncdhw().cpu(), ref) < tol
 
 
 @pytest.mark.parametrize("case", [(1, 64, 64, (3, 10, 56), (3, 3, 3)), (2, 32, 32, (2, 9, 28), (3, 3, 3)),
-                                  (1, 32, 64, (3, 6, 40), (4, 4, 4)), (1, 96, 16, (2, 14, 14), (3, 3, 3))])
+                                  (1, 32, 64, (3, 6, 40), (4, 4, 4)), (1, 96, 16, (2, 14, 14), (3, 3, 3)),
+                                  (1, 32, 64, (4, 6, 40), (4, 4, 4)), (2, 64, 96, (6, 7, 14), (3, 3, 3))])
 def test_conv_slab_every_tile_plan(dev, case):
     """Every tile plan the halo-slab kernel accepts for a layer (kw-merge 1..4, 1..4 accumulators per tile, single
-    and double buffered TMEM, single CTAs and cta_group::2 pairs, 1..N tiles) gives the same convolution: each
-    within 1e-2 of the fp32 reference (bf16 operands) and within 2e-3 of the cost model's own plan."""
+    and double buffered TMEM, single CTAs and cta_group::2 pairs, 1..N tiles, one or two stacked output depths)
+    gives the same convolution: each within 1e-2 of the fp32 reference (bf16 operands) and within 2e-3 of the cost
+    model's own plan."""
     from interpreting_video_features_b200 import _lib, engine, ops, tune
     from interpreting_video_features_b200.ops import Act, same_pad
     n, cin, cout, dhw, k = case
@@ -209,6 +218,9 @@ def test_conv_slab_every_tile_plan(dev, case):
     plans = tune.candidates(make_desc, sm)
     assert len(plans) >= 6, plans
     assert {p[3] for p in plans} == {1, 2} and len({p[0] for p in plans}) >= 2 and len({p[2] for p in plans}) == 2
+    if dhw[0] % 2 == 0 and cout % 32 == 0:  # depth stacking: even depth, TMEM blocks of whole 32 columns
+        assert {p[5] for p in plans} == {1, 2}, plans
+        assert {p[3] for p in plans if p[5] == 2} == {1, 2}, plans  # stacked, single CTAs and pairs
     ops.conv3d(xa, wp, out, k, (1, 1, 1), pf)
     base = out.ncdhw().cpu()
     assert rel_err(base, ref) < 1e-2
