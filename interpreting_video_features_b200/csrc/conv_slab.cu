@@ -93,7 +93,8 @@ struct SlabParams {
   uint32_t xch_off;  // kw-merge: byte offset (from the aligned dynamic shared memory base) of the boundary-row
   int xch_seg;       // exchange [2 tile parities][4*mt segments][xch_seg floats], xch_seg = (kwm-1)^2 * bn
   int diag;  // IVF_SLAB_DIAG (timing experiments, results are garbage): bit 0 / 1 = after the ring has filled
-             // once, the slab / weight producer signals "full" without loading
+             // once, the slab / weight producer signals "full" without loading; bit 2 = the epilogue reads TMEM but
+             // neither loads its global operands nor stores anything
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes, a_tx, b_tx;  // a B stage holds the kw taps of one row
   // IVF_EP_LSTM: the recurrent step's state buffers (see EpilogueArgs)
   const float* lstm_c_prev;
@@ -510,10 +511,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.kwm == 1) {
             for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
               const int nb = t.nt * p.bn + c0;
-              epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok, cur);
+              epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok && !(p.diag & 4), cur);
               uint32_t rr[16];
               tmem_ld16(taddr + c0, rr);
-              if (ok && nb < p.cout)
+              if (ok && nb < p.cout && !(p.diag & 4))
                 epilogue_chunk16<LSTM, FL>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
             }
           } else {

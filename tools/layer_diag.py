@@ -29,10 +29,12 @@ e1.record(); torch.cuda.synchronize()
 print("%.1f" % (e0.elapsed_time(e1) * 50))
 '''
 for name, dhw, cin, cout in (("3b.b1b", "8,28,28", 96, 128), ("3c.b1b", "8,28,28", 128, 192), ("4b.b1b", "4,14,14", 96, 208),
-                             ("4f.b1b", "4,14,14", 160, 320), ("5c.b1b", "2,7,7", 192, 384)):
+                             ("4f.b1b", "4,14,14", 160, 320), ("5c.b1b", "2,7,7", 192, 384),
+                             ("3b.b2b", "8,28,28", 16, 32), ("4c.b2b", "4,14,14", 24, 64), ("5b.b2b", "2,7,7", 32, 128)):
     row = []
-    for diag in (0, 3):
+    for diag in (0, 3, 4, 7):
         env = dict(os.environ, DHW=dhw, CIN=str(cin), COUT=str(cout), IVF_SLAB_DIAG=str(diag))
         r = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
         row.append(r.stdout.strip() or r.stderr.strip()[-120:])
-    print("%-8s %s %d->%d  us: loads on %s | no loads %s" % (name, dhw, cin, cout, row[0], row[1]))
+    print("%-8s %s %d->%d  us: all on %s | no operand loads %s | no epilogue traffic %s | neither %s" %
+          (name, dhw, cin, cout, row[0], row[1], row[2], row[3]))
