@@ -190,8 +190,19 @@ def conv_time_one_engine(eng):
         events.append((e0, e1))
         return r
 
+    orig_pair = ops.conv3d_pair
+
+    def timed_pair(*a, **k):  # one grouped launch (or two plain ones): the two 3x3x3 branches of a module
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_pair(*a, **k)
+        e1.record()
+        events.append((e0, e1))
+        return r
+
     ops.conv3d = timed
     ops.conv1x1_split = timed_split
+    ops.conv3d_pair = timed_pair
     streams, eng.use_streams = eng.use_streams, False  # serialised: one kernel at a time on one stream
     try:
         # hold the stream for ~60 ms so that every launch and event of the iteration is already queued when
@@ -204,6 +215,7 @@ def conv_time_one_engine(eng):
     finally:
         ops.conv3d = orig
         ops.conv1x1_split = orig_split
+        ops.conv3d_pair = orig_pair
         eng.use_streams = streams
     return sum(a.elapsed_time(b) for a, b in events) * 1e-3, len(events)
 

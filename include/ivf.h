@@ -115,6 +115,15 @@ int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void
                const float* scale, const float* shift, const float* acc_in, const void* mask_y,
                const float* mask_scale, void* out, void* stream);
 
+/* Two independent convolutions as one launch where the halo-slab kernel can group them (bf16, multi-tap, stride 1:
+ * the two 3x3x3 branches of an InceptionModule, pt/models/I3D_doubled.py:136-146, forward or data gradient), otherwise
+ * issued one after the other.  Same arguments as two ivf_conv3d calls. */
+int ivf_conv3d_pair(ivf_handle* h, const ivf_conv_desc* d0, const void* in0, const void* w0, const float* scale0,
+                    const float* shift0, const float* acc_in0, const void* mask_y0, const float* mask_scale0,
+                    void* out0, const ivf_conv_desc* d1, const void* in1, const void* w1, const float* scale1,
+                    const float* shift1, const float* acc_in1, const void* mask_y1, const float* mask_scale1,
+                    void* out1, void* stream);
+
 /* 1x1x1 stride-1 bf16 convolution with two destinations and/or two sources: the Inception bottleneck trio
  * b0 | b1a | b2a reads the same x (pt/models/I3D_doubled.py:136-146: three Unit3D calls on one input, b0's
  * result concatenated with the branch outputs), so ONE GEMM produces all three - channels [0, split_cout)

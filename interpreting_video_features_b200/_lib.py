@@ -64,6 +64,7 @@ SIGNATURES = {
     "ivf_conv_slab_plan": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(C.c_int)]),
     "ivf_conv_slab_plan_ds": (_I, [C.POINTER(ConvDesc), _I]),
     "ivf_conv3d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ivf_conv3d_pair": (_I, [_P, C.POINTER(ConvDesc)] + [_P] * 8 + [C.POINTER(ConvDesc)] + [_P] * 8 + [_P]),
     "ivf_conv3d_split": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvSplit), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _P]),
     "ivf_debug_read_scratch": (_I, [_P, _P, C.c_size_t]),

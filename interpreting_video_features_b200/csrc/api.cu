@@ -90,6 +90,39 @@ extern "C" int ivf_conv3d(ivf_handle* h, const ivf_conv_desc* d, const void* in,
   IVF_FAIL(IVF_EINVAL, "ivf_conv3d: unknown dtype %d", d->dtype);
 }
 
+// Two independent convolutions - the two 3x3x3 branches of an Inception module (pt/models/I3D_doubled.py:136-146:
+// b1b(b1a(x)) and b2b(b2a(x)) and their data gradients) - issued as ONE launch where the halo-slab kernel can group
+// them (bf16, multi-tap, stride 1), otherwise one after the other on the same stream.  Results are those of two
+// ivf_conv3d calls (up to the summation order of a different tile plan).
+extern "C" int ivf_conv3d_pair(ivf_handle* h, const ivf_conv_desc* d0, const void* in0, const void* w0,
+                               const float* scale0, const float* shift0, const float* acc_in0, const void* mask_y0,
+                               const float* mask_scale0, void* out0, const ivf_conv_desc* d1, const void* in1,
+                               const void* w1, const float* scale1, const float* shift1, const float* acc_in1,
+                               const void* mask_y1, const float* mask_scale1, void* out1, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && d0 && d1 && in0 && in1 && w0 && w1 && out0 && out1, "ivf_conv3d_pair: null argument");
+  if (d0->dtype == IVF_BF16 && d1->dtype == IVF_BF16 && !d0->transposed && !d1->transposed) {
+    const ivf_conv_desc* ds[2] = {d0, d1};
+    const ivf_conv_operands op[2] = {{in0, w0, scale0, shift0, acc_in0, mask_y0, mask_scale0, out0},
+                                     {in1, w1, scale1, shift1, acc_in1, mask_y1, mask_scale1, out1}};
+    bool ok = true;
+    for (int i = 0; i < 2 && ok; ++i) {
+      const ivf_conv_desc* d = ds[i];
+      ok = d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->cin > 0 && d->cout > 0 && d->kd > 0 && d->kh > 0 &&
+           d->kw > 0 && d->in_ld >= d->in_coff + d->cin && d->out_ld >= d->out_coff + d->cout &&
+           (!(d->flags & IVF_EP_AFFINE) || (op[i].scale && op[i].shift)) && (!(d->flags & IVF_EP_ACCUM) || op[i].acc_in) &&
+           (!(d->flags & IVF_EP_MASK) || (op[i].mask_y && op[i].mask_scale));
+    }
+    if (ok) {
+      const int rc = ivf_conv3d_slab_launch_pair(h, ds, op, (cudaStream_t)stream);
+      if (rc != IVF_EUNSUPPORTED) return rc;
+    }
+  }
+  int rc = ivf_conv3d(h, d0, in0, w0, scale0, shift0, acc_in0, mask_y0, mask_scale0, out0, stream);
+  if (rc) return rc;
+  return ivf_conv3d(h, d1, in1, w1, scale1, shift1, acc_in1, mask_y1, mask_scale1, out1, stream);
+}
+
 extern "C" int ivf_conv3d_split(ivf_handle* h, const ivf_conv_desc* d, const ivf_conv_split* sp, const void* in,
                                 const void* in2, const void* w, const float* scale, const float* shift,
                                 const float* acc_in, const void* mask_y, const float* mask_scale, void* out,

@@ -23,7 +23,7 @@ struct ivf_handle {
   // cache of encoded TMA tensor maps keyed by a byte string of everything that shapes them
   std::map<std::string, CUtensorMap> tmaps;
   bool tc_attr_set[4] = {false, false, false, false};
-  bool slab_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool slab_attr_set[16] = {};  // per kernel instantiation: dynamic shared memory opt-in done ([15]: grouped)
   // small per-handle scratch (partial logits of the head kernels); allocated once in ivf_create so
   // that no call allocates (CUDA-graph capture safe), freed in ivf_destroy
   float* scratch = nullptr;
@@ -158,6 +158,20 @@ int ivf_conv3d_tc_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, 
 // halo-slab tcgen05 kernel (conv_slab.cu) for the wide stride-1 'same' layers; the launcher of the im2col
 // kernel above serves everything else the bf16 path supports
 bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d);
+// two independent slab-kernel convolutions as ONE launch; IVF_EUNSUPPORTED (and nothing launched) when the pair
+// cannot be grouped - the caller then issues them one after the other
+struct ivf_conv_operands {
+  const void* in;
+  const void* w;
+  const float* scale;
+  const float* shift;
+  const float* acc_in;
+  const void* mask_y;
+  const float* mask_scale;
+  void* out;
+};
+int ivf_conv3d_slab_launch_pair(ivf_handle* h, const ivf_conv_desc* const d[2], const ivf_conv_operands op[2],
+                                cudaStream_t st);
 int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d, const void* in, const void* w,
                            const float* scale, const float* shift, const float* acc_in,
                            const void* mask_y, const float* mask_scale, void* out, cudaStream_t st,

@@ -129,13 +129,43 @@ __device__ __forceinline__ int slab_offset(const SlabParams& p, int idx) {
 
 // KCH = channels per slab row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B, for
 // operands of <= 32 channels: the space-to-depth stem's 24-of-32 and the 16/32-channel bottlenecks)
-template <int KCH, int NCTA, bool LSTM = false>
+// GROUPED: one launch serves TWO independent convolutions (the two 3x3x3 branches of an Inception module, forward
+// or data gradient): CTAs [0, split) work on the first, the rest on the second, each walking its own tiles.  At 8
+// clips those branch convolutions are 10-25 us launches that are set-up and pipeline latency end to end; as one launch
+// they share it and run side by side on disjoint SMs (measured upper bound with the thin branch removed: -5 % step).
+struct SlabOperands {
+  const float* scale;
+  const float* shift;
+  const float* acc_in;
+  const __nv_bfloat16* mask_y;
+  const float* mask_scale;
+  void* out;
+};
+
+template <int KCH, int NCTA, bool LSTM = false, bool GROUPED = false>
 __global__ void __launch_bounds__(SLAB_THREADS, 1)
-conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const SlabParams p, const float* __restrict__ scale, const float* __restrict__ shift,
-                 const float* __restrict__ acc_in, const __nv_bfloat16* __restrict__ mask_y,
-                 const float* __restrict__ mask_scale, void* __restrict__ out) {
+conv_slab_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ SlabParams p1, const SlabOperands o1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ SlabParams p2, const SlabOperands o2, const int split) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ SlabParams s_params;  // GROUPED: this CTA's problem
+  const bool second = GROUPED && blockIdx.x >= (unsigned)split;
+  if (GROUPED) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(second ? &p2 : &p1);
+    for (int i = threadIdx.x; i < (int)(sizeof(SlabParams) / 4); i += blockDim.x)
+      reinterpret_cast<uint32_t*>(&s_params)[i] = src[i];
+    __syncthreads();
+  }
+  const SlabParams& p = GROUPED ? s_params : p1;
+  const CUtensorMap* const tmA = second ? &tmA2 : &tmA1;
+  const CUtensorMap* const tmB = second ? &tmB2 : &tmB1;
+  const float* __restrict__ scale = second ? o2.scale : o1.scale;
+  const float* __restrict__ shift = second ? o2.shift : o1.shift;
+  const float* __restrict__ acc_in = second ? o2.acc_in : o1.acc_in;
+  const __nv_bfloat16* __restrict__ mask_y = second ? o2.mask_y : o1.mask_y;
+  const float* __restrict__ mask_scale = second ? o2.mask_scale : o1.mask_scale;
+  void* __restrict__ out = second ? o2.out : o1.out;
   __shared__ __align__(8) uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
@@ -151,16 +181,18 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;  // 0 = leader of the pair
-  const int item0 = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // GROUPED (single CTAs only): this problem's CTAs are [0, split) or [split, gridDim.x)
+  const int item0 = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x - (second ? split : 0);
+  const int item_step = NCTA == 2 ? (int)(gridDim.x >> 1)
+                                  : (GROUPED ? (second ? (int)gridDim.x - split : split) : (int)gridDim.x);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   ivf_pdl_trigger();  // the next kernel of the stream may begin its own set-up
   if (threadIdx.x == 0) {
-    tma_prefetch_map(&tmA);  // descriptor fetch overlaps the set-up
-    tma_prefetch_map(&tmB);
+    tma_prefetch_map(tmA);  // descriptor fetch overlaps the set-up
+    tma_prefetch_map(tmB);
     const uint32_t nissue = p.mt >= 2 ? 2u : 1u;  // MMA-issuing warps: each commits once per slot / tile
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(&a_full[s], 1);
@@ -228,11 +260,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else if (leader) {
               if constexpr (NCTA == 2) {
                 if (rank == 0) mbar_expect_tx(&a_full[stage], 2u * p.a_tx);  // both CTAs' slabs
-                tma_load_5d_pair(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
+                tma_load_5d_pair(a_base + stage * p.a_stage_bytes, tmA, &a_full[stage], cc * KCH, -p.pw,
                                  t.h0 - p.ph, zd, t.nn);
               } else {
                 mbar_expect_tx(&a_full[stage], p.a_tx);
-                tma_load_5d(a_base + stage * p.a_stage_bytes, &tmA, &a_full[stage], cc * KCH, -p.pw,
+                tma_load_5d(a_base + stage * p.a_stage_bytes, tmA, &a_full[stage], cc * KCH, -p.pw,
                             t.h0 - p.ph, zd, t.nn);
               }
             }
@@ -280,12 +312,12 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int kw_i = 0; kw_i < p.kw; ++kw_i) {
                     if (ns == 2) {
                       const int tap = ((kd_i - rank) * p.kh + kh_i) * p.kw + kw_i;
-                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage], tap * p.cin_pad + cc * KCH,
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, tmB, &b_full[stage], tap * p.cin_pad + cc * KCH,
                                        t.nt * p.bn);
-                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes + blk / 2, &tmB, &b_full[stage],
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes + blk / 2, tmB, &b_full[stage],
                                        tap * p.cin_pad + cc * KCH, t.nt * p.bn + p.bn / 2);
                     } else {
-                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, tmB, &b_full[stage],
                                        (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn + rank * (p.bn / 2));
                     }
                   }
@@ -293,7 +325,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   mbar_expect_tx(&b_full[stage], (uint32_t)(p.kw * ns) * blk);
                   for (int kw_i = 0; kw_i < p.kw; ++kw_i)
                     for (int b = 0; b < ns; ++b)
-                      tma_load_2d(dst0 + kw_i * p.b_tap_bytes + b * blk, &tmB, &b_full[stage],
+                      tma_load_2d(dst0 + kw_i * p.b_tap_bytes + b * blk, tmB, &b_full[stage],
                                   (((kd_i - b) * p.kh + kh_i) * p.kw + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
                 }
               } else if (leader) {
@@ -305,20 +337,20 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const uint32_t dst0 = b_base + stage * p.b_stage_bytes;
                   if (p.kwm == 1) {
                     for (int kw_i = 0; kw_i < p.kw; ++kw_i)
-                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                      tma_load_2d_pair(dst0 + kw_i * p.b_tap_bytes, tmB, &b_full[stage],
                                        (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn + rank * (p.bn / 2));
                   } else {
                     const int half = p.kwm / 2;
                     int slot_i = 0;
                     for (int g0 = 0; g0 < p.kw; g0 += p.kwm)
                       for (int j = 0; j < half; ++j, ++slot_i)
-                        tma_load_2d_pair(dst0 + slot_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                        tma_load_2d_pair(dst0 + slot_i * p.b_tap_bytes, tmB, &b_full[stage],
                                          (tap0 + g0 + rank * half + j) * p.cin_pad + cc * KCH, t.nt * p.bn);
                   }
                 } else {
                   mbar_expect_tx(&b_full[stage], p.b_tx);
                   for (int kw_i = 0; kw_i < p.kw; ++kw_i)
-                    tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, &tmB, &b_full[stage],
+                    tma_load_2d(b_base + stage * p.b_stage_bytes + kw_i * p.b_tap_bytes, tmB, &b_full[stage],
                                 (tap0 + kw_i) * p.cin_pad + cc * KCH, t.nt * p.bn);
                 }
               }
@@ -698,6 +730,7 @@ int env_int(const char* name, int dflt) {
 //   l2    = (slab bytes read + weight bytes) / 40      (B/clk/SM with all 148 SMs pulling = the LTS cap; a slab
 //           pixel costs at least 128 B: the 48-byte rows of the 24-channel stem operand move at that rate)
 // the epilogue is exposed only when TMEM is single buffered.  Returns false when nothing fits.
+thread_local int g_force_kch = 0;  // grouped launches: 128-byte slab rows whatever the channel count
 bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best);
 bool slab_config(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   // depth stacking is a request (plan_ds from the host-side tuner, IVF_SLAB_DS for diagnostics): a layer that
@@ -723,7 +756,7 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
   const int cout = d->cout, cin = d->cin;
   // 64-byte rows (SWIZZLE_64B) cost more per MMA than 128-byte rows (tools/mma_bench.cu); IVF_SLAB_KCH64=1 gives the
   // narrow layers 128-byte rows too (the upper half is TMA zero fill and is never multiplied)
-  const int kch = (cin <= 32 && !env_int("IVF_SLAB_KCH64", 0)) ? 32 : 64;
+  const int kch = (cin <= 32 && !env_int("IVF_SLAB_KCH64", 0) && g_force_kch != 64) ? 32 : 64;
   const int rowb = kch * 2;
   const int wp = d->iw + d->kw - 1;
   const int cchunks = (cin + kch - 1) / kch;
@@ -861,15 +894,33 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
                   const float* mask_scale, void* out, cudaStream_t st) {
   const int slot = (KCH == 64 ? 0 : 1) + 2 * (NCTA - 1) + (LSTM ? 4 : 0);
   if (!h->slab_attr_set[slot]) {
-    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA, LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<KCH, NCTA, LSTM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(SLAB_SMEM_BUDGET + 1024)));
     h->slab_attr_set[slot] = true;
   }
   const size_t smem = (size_t)p.xch_off + (size_t)2 * 4 * p.mt * p.xch_seg * 4 + 1024;
   const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
-  IVF_CUDA(ivf_launch(conv_slab_kernel<KCH, NCTA, LSTM>, dim3(grid), dim3(SLAB_THREADS), smem, st, NCTA, ma, mb, p, scale,
-                      shift, acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out));
+  const SlabOperands o = {scale, shift, acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out};
+  IVF_CUDA(ivf_launch(conv_slab_kernel<KCH, NCTA, LSTM, false>, dim3(grid), dim3(SLAB_THREADS), smem, st, NCTA, ma, mb, p, o,
+                      ma, mb, p, o, grid));
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+// two problems, one launch (GROUPED): single CTAs, 128-byte slab rows for both
+int slab_launch_group(ivf_handle* h, const SlabParams (&p)[2], const CUtensorMap (&ma)[2], const CUtensorMap (&mb)[2],
+                      const SlabOperands (&o)[2], int split, int grid, cudaStream_t st) {
+  if (!h->slab_attr_set[15]) {
+    IVF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<64, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SLAB_SMEM_BUDGET + 1024)));
+    h->slab_attr_set[15] = true;
+  }
+  size_t smem = 0;
+  for (int i = 0; i < 2; ++i)
+    smem = std::max(smem, (size_t)p[i].xch_off + (size_t)2 * 4 * p[i].mt * p[i].xch_seg * 4 + 1024);
+  IVF_CUDA(ivf_launch(conv_slab_kernel<64, 1, false, true>, dim3(grid), dim3(SLAB_THREADS), smem, st, 1, ma[0], mb[0], p[0],
+                      o[0], ma[1], mb[1], p[1], o[1], split));
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -914,6 +965,79 @@ bool ivf_conv3d_slab_eligible(const ivf_handle* h, const ivf_conv_desc* d0) {
   if ((d->flags & IVF_EP_AFFINE) && (d->flags & IVF_EP_MASK)) return false;  // one shared scale vector
   SlabParams p;
   return slab_config(d, h->sm_count, &p);
+}
+
+namespace {
+// the fields of SlabParams that come straight from the descriptor (after slab_config chose the plan)
+void slab_fill(const ivf_conv_desc* d, SlabParams& p) {
+  p.n = d->n; p.dd = d->id; p.hh = d->ih; p.ww = d->iw;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
+  p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.cin = d->cin;
+  p.cchunks = (d->cin + p.kch - 1) / p.kch;
+  p.cin_pad = ivf_conv_bf16_cin_pad(d->cin);
+  p.cout = d->cout;
+  p.out_ld = d->out_ld; p.out_coff = d->out_coff;
+  p.mask_ld = d->mask_ld; p.mask_coff = d->mask_coff;
+  p.flags = d->flags;
+  p.num_tiles = d->n * p.dgroups * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
+  p.diag = env_int("IVF_SLAB_DIAG", 0);
+}
+}  // namespace
+
+int ivf_conv3d_slab_launch_pair(ivf_handle* h, const ivf_conv_desc* const d[2], const ivf_conv_operands op[2],
+                                cudaStream_t st) {
+  if (env_int("IVF_SLAB_GROUP", 1) == 0) return IVF_EUNSUPPORTED;
+  int rc = ivf_load_driver_entry_points();
+  if (rc) return rc;
+  SlabParams p[2];
+  CUtensorMap ma[2], mb[2];
+  SlabOperands o[2];
+  double cost[2];
+  for (int i = 0; i < 2; ++i) {
+    if (d[i]->kd * d[i]->kh * d[i]->kw == 1 || (d[i]->flags & IVF_EP_LSTM)) return IVF_EUNSUPPORTED;
+    if (!ivf_conv3d_slab_eligible(h, d[i])) return IVF_EUNSUPPORTED;
+    ivf_conv_desc dd = *d[i];
+    dd.plan_ncta = 1;                   // single CTAs: the two problems share one grid
+    dd.plan_kwm = dd.plan_kwm ? dd.plan_kwm : 0;
+    g_force_kch = 64;                   // one kernel instantiation: 128-byte slab rows for both
+    const bool ok = slab_config(&dd, h->sm_count, &p[i]);
+    g_force_kch = 0;
+    if (!ok || p[i].ncta != 1 || p[i].kch != 64) return IVF_EUNSUPPORTED;
+    slab_fill(&dd, p[i]);
+    p[i].lstm_c_prev = nullptr; p[i].lstm_c_next = nullptr; p[i].lstm_h_next = nullptr;
+    if ((long long)dd.n * p[i].dgroups * p[i].htiles * p[i].ntiles >= (1ll << 31)) return IVF_EUNSUPPORTED;
+    // relative cost of a problem: its MMAs (the cost model's per-instruction estimate) - decides the SM split
+    int ksteps_total = 0;
+    for (int cc = 0; cc < p[i].cchunks; ++cc) {
+      const int crem = dd.cin - cc * 64;
+      ksteps_total += crem >= 64 ? 4 : (crem + 15) / 16;
+    }
+    const int n_eff = p[i].kwm * p[i].bn * p[i].ds;
+    cost[i] = (double)p[i].num_tiles * (dd.kd + p[i].ds - 1) * dd.kh * dd.kw / p[i].kwm * ksteps_total * p[i].mt *
+                  std::max(64.0 + n_eff / 2.0, (double)n_eff / 2.0) +
+              (double)p[i].num_tiles * 4000.0;  // per-tile fixed part (pipeline fill, epilogue)
+  }
+  // CTAs: as many as there are tiles, at most one per SM, split by cost with at least one CTA each
+  const int total = std::min(h->sm_count, p[0].num_tiles + p[1].num_tiles);
+  if (total < 2) return IVF_EUNSUPPORTED;
+  int g0 = (int)std::lround(total * cost[0] / (cost[0] + cost[1]));
+  g0 = std::max(1, std::min(g0, total - 1));
+  g0 = std::min(g0, p[0].num_tiles);
+  int g1 = std::min(total - g0, p[1].num_tiles);
+  if (g0 + g1 < total) g0 = std::min(p[0].num_tiles, total - g1);
+  for (int i = 0; i < 2; ++i) {
+    rc = slab_map_a(h, d[i], op[i].in, p[i].wp, p[i].th + d[i]->kh - 1, 64, &ma[i]);
+    if (rc) return rc;
+    rc = slab_map_b(h, op[i].w, d[i]->kd * d[i]->kh * d[i]->kw * p[i].cin_pad, ivf_conv_bf16_cout_pad(d[i]->cout), p[i].bn,
+                    64, &mb[i]);
+    if (rc) return rc;
+    o[i] = {op[i].scale, op[i].shift, op[i].acc_in, (const __nv_bfloat16*)op[i].mask_y, op[i].mask_scale, op[i].out};
+  }
+  if (env_int("IVF_SLAB_VERBOSE", 0))
+    fprintf(stderr, "slab group: %d + %d CTAs | c%d->%d mt %d th %d items %d | c%d->%d mt %d th %d items %d\n", g0, g1,
+            d[0]->cin, d[0]->cout, p[0].mt, p[0].th, p[0].num_tiles, d[1]->cin, d[1]->cout, p[1].mt, p[1].th, p[1].num_tiles);
+  return slab_launch_group(h, p, ma, mb, o, g0, g0 + g1, st);
 }
 
 int ivf_conv3d_slab_launch(ivf_handle* h, const ivf_conv_desc* d0, const void* in, const void* w,

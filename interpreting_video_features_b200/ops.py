@@ -152,6 +152,23 @@ def conv3d(x, w, out, kernel, stride, pad_front, flags=0, scale=None, shift=None
     return out
 
 
+def conv3d_pair(a, b):
+    """Two independent convolutions as one launch where the library can group them (ivf_conv3d_pair: the two 3x3x3
+    branches of an Inception module), else one after the other.  a, b: dicts of conv3d's arguments."""
+    def parts(k):
+        d = conv_desc(k["x"], k["out"], k["kernel"], k["stride"], k["pad_front"], k.get("flags", 0), k.get("scale"),
+                      k.get("acc_in"), k.get("mask"), k.get("transposed", 0), None, None, k.get("plan"))
+        acc, mask = k.get("acc_in"), k.get("mask")
+        return d, [ptr(k["x"].buf), ptr(k["w"]), ptr(k.get("scale")), ptr(k.get("shift")),
+                   ptr(acc.buf if isinstance(acc, Act) else acc), ptr(mask.buf if mask is not None else None),
+                   ptr(k.get("mask_scale")), ptr(k["out"].buf)]
+    da, pa = parts(a)
+    db, pb = parts(b)
+    dev = a["x"].buf.device
+    check(_lib.load().ivf_conv3d_pair(_lib.handle(dev), C.byref(da), *pa, C.byref(db), *pb, _lib.stream_ptr(dev)),
+          "ivf_conv3d_pair")
+
+
 def conv1x1_split(x, w, out, x2=None, out2=None, flags=0, scale=None, shift=None, acc_in=None, mask=None,
                   mask_scale=None):
     """1x1x1 bf16 convolution with two sources (channels of x then of x2) and/or two destinations (produced

@@ -232,6 +232,61 @@ def test_conv_slab_every_tile_plan(dev, case):
         assert rel_err(got, base) < 2e-3, (plan, rel_err(got, base))
 
 
+@pytest.mark.parametrize("case", [((4, 14, 14), 96, 208, 24, 64), ((8, 28, 28), 96, 128, 16, 32),
+                                  ((2, 7, 7), 160, 320, 32, 128)])
+def test_conv3d_pair_grouped_launch(dev, case):
+    """ivf_conv3d_pair: the two 3x3x3 branches of an Inception module as ONE grouped launch of the halo-slab kernel
+    (CTAs split between the two problems) give what two separate convolutions give - forward with BN+ReLU into
+    channel slices of one concat buffer, and the data gradients with the fused ReLU'/BN' mask."""
+    from interpreting_video_features_b200 import _lib, engine, ops
+    from interpreting_video_features_b200.ops import Act
+    dhw, ci1, co1, ci2, co2 = case
+    n, k, pf = 2, (3, 3, 3), (1, 1, 1)
+    g = torch.Generator().manual_seed(3)
+    before = _lib.launch_count(dev)
+
+    def mk(cin, cout):
+        x = torch.randn((n, cin) + dhw, generator=g).bfloat16().float()
+        w = (torch.randn((cout, cin) + k, generator=g) / (cin * 27) ** 0.5).bfloat16().float()
+        sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+        return x, w, sc, sh
+
+    xa, wa, sca, sha = mk(ci1, co1)
+    xb, wb, scb, shb = mk(ci2, co2)
+    concat = Act.empty(n, *dhw, co1 + co2 + 16, torch.bfloat16, dev, zero=True)
+    oa, ob = concat.slice(8, co1), concat.slice(8 + co1, co2)
+    argsf = [dict(x=to_act(x.to(dev), torch.bfloat16), w=engine.pack_fwd(w.to(dev), "bf16"), out=o, kernel=k,
+                  stride=(1, 1, 1), pad_front=pf, flags=_lib.EP_RELU, scale=sc.to(dev), shift=sh.to(dev))
+             for x, w, sc, sh, o in ((xa, wa, sca, sha, oa), (xb, wb, scb, shb, ob))]
+    n0 = _lib.launch_count(dev)
+    ops.conv3d_pair(*argsf)
+    assert _lib.launch_count(dev) - n0 == 1, "the pair must go out as one grouped launch"
+    for x, w, sc, sh, o in ((xa, wa, sca, sha, oa), (xb, wb, scb, shb, ob)):
+        ref = F.relu(ref_conv(x, w, (1, 1, 1), pf, dhw) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+        assert rel_err(o.ncdhw().cpu(), ref) < 1e-2
+    assert float(concat.tensor()[..., :8].float().abs().max()) == 0.0
+    assert float(concat.tensor()[..., 8 + co1 + co2:].float().abs().max()) == 0.0
+    # data gradients with the producers' ReLU'/BN' masks, side by side in one buffer (g_t12 of the engine)
+    gt = Act.empty(n, *dhw, ci1 + ci2, torch.bfloat16, dev, zero=True)
+    argsb, refs = [], []
+    for (x, w, cin, cout, off) in ((xa, wa, ci1, co1, 0), (xb, wb, ci2, co2, ci1)):
+        dz = torch.randn((n, cout) + dhw, generator=g).bfloat16().float()
+        xr = x.clone().requires_grad_()
+        (gx,) = torch.autograd.grad(ref_conv(xr, w, (1, 1, 1), pf, dhw), xr, dz)
+        msc = torch.rand(cin, generator=g) + 0.5
+        refs.append((gx * (x > 0).float() * msc.view(1, -1, 1, 1, 1), off, cin))
+        argsb.append(dict(x=to_act(dz.to(dev), torch.bfloat16), w=engine.pack_dgrad(w.to(dev), "bf16"),
+                          out=gt.slice(off, cin), kernel=k, stride=(1, 1, 1), pad_front=pf,
+                          mask=to_act(x.to(dev), torch.bfloat16), mask_scale=msc.to(dev)))
+    n0 = _lib.launch_count(dev)
+    ops.conv3d_pair(*argsb)
+    assert _lib.launch_count(dev) - n0 == 1
+    full = gt.ncdhw().cpu()
+    for ref, off, cin in refs:
+        assert rel_err(full[:, off:off + cin], ref) < 1e-2
+    assert before >= 0
+
+
 def test_conv_fp32_strided_stem_and_its_gradient(dev):
     """The 7x7x7 stride-2 stem in fp32 mode (true strided gather, transposed data-gradient)."""
     from interpreting_video_features_b200 import _lib, engine, ops

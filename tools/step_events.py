@@ -28,7 +28,7 @@ for _ in range(2):
     ms._iteration()
 torch.cuda.synchronize()
 
-NAMES = ["conv3d", "conv1x1_split", "maxpool3d_fwd", "maxpool3d_bwd", "perturb_fwd", "perturb_bwd", "head_fwd",
+NAMES = ["conv3d", "conv3d_pair", "conv1x1_split", "maxpool3d_fwd", "maxpool3d_bwd", "perturb_fwd", "perturb_bwd", "head_fwd",
          "head_bwd", "mask_loss_adam"]
 events = []
 orig = {}
@@ -61,6 +61,10 @@ def describe(name, a, k):
             fl = k.get("flags", 0)
             tag = "fwd" if fl else ("dgrad" + ("+acc" if k.get("acc_in") is not None else "") + ("+mask" if k.get("mask") is not None else ""))
             return "%s k%s %d->%d @%dx%dx%dx%d %s" % (name, "x".join(map(str, kern)), x.c, out.c, x.n, x.d, x.h, x.w, tag)
+        if name == "conv3d_pair":
+            return "conv3d_pair " + " + ".join("k%s %d->%d @%dx%dx%dx%d %s" % (
+                "x".join(map(str, q["kernel"])), q["x"].c, q["out"].c, q["x"].n, q["x"].d, q["x"].h, q["x"].w,
+                "fwd" if q.get("flags", 0) else "dgrad") for q in a[:2])
         if name == "maxpool3d_fwd":
             x = a[0]
             return "pool_fwd k%s s%s c%d @%dx%dx%dx%d" % ("x".join(map(str, a[3])), "x".join(map(str, a[4])), x.c, x.n, x.d, x.h, x.w)
