@@ -490,7 +490,7 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     stats = {}
     t0 = time.perf_counter()
-    mb = args.e2e_micro_batch
+    mb = max(CLIPS, min(args.e2e_micro_batch, per_gpu))
     if mb != CLIPS:  # untimed: engine of the other micro-batch size (tile plans, graph capture)
         search.find_masks_batched(model, host[:mb], tg_mine[:mb], n_iter=2, micro_batch=mb, device=dev, gradcam=True)
         torch.cuda.synchronize()
@@ -516,10 +516,10 @@ def run_ours(args, rank, world, local_rank):
            "clips_total": n_total, "clips_per_gpu": per_gpu, "micro_batch": mb, "gather_seconds": stats["gather_seconds"],
            "gathered_bytes": stats.get("gathered_bytes"), "gather_equals_single_rank": check,
            "note": "C4-shaped job: %d uint8 clips per GPU in pinned host memory, find_masks_batched(gradcam=True): per "
-                   "micro-batch of 8 H2D + init_mask (T/2+1 forwards) + 300 iterations + reverse score + Grad-CAM; then "
-                   "NCCL all_gather of masks+scores+low-res CAMs (N>1) and D2H of the gathered result; a step = one "
-                   "iteration of one 8-clip micro-batch; one 2-iteration call runs untimed first (lazy kernel "
-                   "loading, graph capture)" % per_gpu}
+                   "micro-batch of %d clips H2D + init_mask (T/2+1 forwards) + 300 iterations + reverse score + Grad-CAM; "
+                   "then NCCL all_gather of masks+scores+low-res CAMs (N>1) and D2H of the gathered result; "
+                   "h2d/d2h_bytes_per_step are per 8-clip iteration (the `value` leg's step); one 2-iteration call runs "
+                   "untimed first (lazy kernel loading, graph capture)" % (per_gpu, mb)}
 
     # ---- the same conv roofline at the end-to-end leg's micro-batch (the late stages fill the machine there)
     if mb != CLIPS and args.mode == "bf16":
@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--clips-per-gpu", type=int, default=128, help="clips per GPU of the end-to-end (C4) leg")
-    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "64")),
+    ap.add_argument("--e2e-micro-batch", type=int, default=int(os.environ.get("IVF_E2E_MICRO_BATCH", "128")),
                     help="clips per launch sequence in the end-to-end leg (the headline `value` stays at BASELINE's 8)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")

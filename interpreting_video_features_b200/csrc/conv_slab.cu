@@ -71,6 +71,7 @@ constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr uint32_t SLAB_SMEM_BUDGET = 216u * 1024u;  // + 1 KB alignment slack + ~9.5 KB static = 227 KB
 constexpr int SLAB_MAX_COUT = 1024;  // per-channel epilogue vectors live in shared memory
+constexpr uint32_t SLAB_EST_BYTES = (uint32_t)(EPI_THREADS / 32) * 32u * 16u * 4u;  // transposition staging, 2 KB per warp
 
 struct SlabParams {
   int n, dd, hh, ww;  // spatial extent (output == gathered tensor: stride 1, 'same')
@@ -92,6 +93,8 @@ struct SlabParams {
   int ncta;  // 1, or 2 = CTA pairs (cta_group::2)
   uint32_t xch_off;  // kw-merge: byte offset (from the aligned dynamic shared memory base) of the boundary-row
   int xch_seg;       // exchange [2 tile parities][4*mt segments][xch_seg floats], xch_seg = (kwm-1)^2 * bn
+  uint32_t est_off;  // != 0: byte offset of the epilogue's transposition staging (SLAB_EST_BYTES, one 32 x 16 fp32
+                     // block per epilogue warp): the warps then touch global memory row-contiguously, see the epilogue
   int diag;  // IVF_SLAB_DIAG (timing experiments, results are garbage): bit 0 / 1 = after the ring has filled
              // once, the slab / weight producer signals "full" without loading; bit 2 = the epilogue reads TMEM but
              // neither loads its global operands nor stores anything
@@ -540,7 +543,148 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                                  (uint32_t)(((acc * p.mt + m) * p.ds + sdep) * p.slot);
           EpiPre cur;  // global operands of a chunk are requested right before its TMEM loads; the other warps of
                        // the scheduler cover the latency
-          if (p.kwm == 1) {
+          if (FL >= 0 && !LSTM && p.kwm == 1 && p.est_off != 0) {
+            // Row-contiguous epilogue.  tcgen05.ld hands every lane ONE pixel's 16 channels, and pixels are out_ld
+            // elements apart: a 16-byte access per lane touches 32 different lines per instruction, which is what
+            // the L1 pipeline charges for (32 lines per request, ~8 K cycles per 128 x 128 fp32 tile - the ConvLSTM's
+            // recurrent convolutions were bound by exactly this, 31 us for 10 us of MMAs).  The chunk is therefore
+            // transposed through a 2 KB block of shared memory (XOR-swizzled float4 columns: conflict-free both
+            // ways), after which four lanes cover one pixel's 16 channels and an instruction touches 8 lines; every
+            // per-element operand (consumer sum, ReLU mask, BN vectors) is read in that mapping too, the global
+            // ones before the TMEM load so that their latency overlaps it.
+            constexpr int F = FL >= 0 ? FL : 0;
+            float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.est_off) +
+                         (size_t)(warp - SLAB_ROLE_WARPS) * 512;
+            const int pixi = (ok && !(p.diag & 4)) ? (int)pix : -1;
+            int prow[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) prow[it] = __shfl_sync(0xffffffffu, pixi, it * 8 + (lane >> 2));
+            const int j4 = lane & 3, swz = (lane >> 1) & 3;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              const int nb = t.nt * p.bn + c0;
+              if (nb + 16 > p.cout) {  // partial chunk: the per-lane form (scalar tail)
+                epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok && !(p.diag & 4), cur);
+                uint32_t rr[16];
+                tmem_ld16(taddr + c0, rr);
+                if (ok && nb < p.cout && !(p.diag & 4))
+                  epilogue_chunk16<LSTM, FL>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+                continue;
+              }
+              const int cb = nb + 4 * j4;
+              float4 ac[4];
+              uint2 mk[4];
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                if (prow[it] < 0) continue;
+                if (F & IVF_EP_ACCUM)
+                  ac[it] = *reinterpret_cast<const float4*>(acc_in + (size_t)prow[it] * p.out_ld + p.out_coff + cb);
+                if (F & IVF_EP_MASK)
+                  mk[it] = *reinterpret_cast<const uint2*>(mask_y + (size_t)prow[it] * p.mask_ld + p.mask_coff + cb);
+              }
+              uint32_t rr[16];
+              tmem_ld16(taddr + c0, rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ swz) << 2)) =
+                    make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
+                                __uint_as_float(rr[4 * j + 3]));
+              __syncwarp();
+              float4 scv = make_float4(1.f, 1.f, 1.f, 1.f), shv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (F & (IVF_EP_AFFINE | IVF_EP_MASK)) scv = *reinterpret_cast<const float4*>(s_scale + cb);
+              if (F & IVF_EP_AFFINE) shv = *reinterpret_cast<const float4*>(s_shift + cb);
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + (lane >> 2);
+                float4 x = *reinterpret_cast<const float4*>(stg + row * 16 + ((j4 ^ ((row >> 1) & 3)) << 2));
+                if (prow[it] < 0) continue;
+                if (F & IVF_EP_ACCUM) {
+                  x.x += ac[it].x; x.y += ac[it].y; x.z += ac[it].z; x.w += ac[it].w;
+                }
+                if (F & IVF_EP_AFFINE) {
+                  x.x = fmaf(x.x, scv.x, shv.x); x.y = fmaf(x.y, scv.y, shv.y);
+                  x.z = fmaf(x.z, scv.z, shv.z); x.w = fmaf(x.w, scv.w, shv.w);
+                }
+                if (F & IVF_EP_RELU) {
+                  x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                }
+                if (F & IVF_EP_MASK) {  // ReLU'(y) * BN scale of the producer: y > 0 as the sign test of its bf16 bits
+                  x.x = __uint_as_float(mk[it].x << 16) > 0.f ? x.x * scv.x : 0.f;
+                  x.y = __uint_as_float(mk[it].x & 0xffff0000u) > 0.f ? x.y * scv.y : 0.f;
+                  x.z = __uint_as_float(mk[it].y << 16) > 0.f ? x.z * scv.z : 0.f;
+                  x.w = __uint_as_float(mk[it].y & 0xffff0000u) > 0.f ? x.w * scv.w : 0.f;
+                }
+                const size_t o = (size_t)prow[it] * p.out_ld + p.out_coff + cb;
+                if (F & IVF_EP_OUT_F32) {
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = x;
+                } else {
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pk;
+                }
+              }
+              __syncwarp();  // the block is rewritten by the next chunk
+            }
+          } else if (LSTM && p.kwm == 1 && p.est_off != 0) {
+            // The fused recurrent step, row-contiguous like the branch above: with unit-major channels the four
+            // lanes of a pixel each hold ONE hidden unit's [i f c o] pre-activations, so the gate math
+            // (pt/models/convolution_lstm.py:38-48, zero peepholes :50-54; the same expressions as epilogue_chunk16's
+            // LSTM branch) runs one unit per lane and pass, and every state access is 16 bytes per pixel (c, h: 4 / 2
+            // bytes per lane) next to its neighbours' instead of one pixel per lane.
+            float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.est_off) +
+                         (size_t)(warp - SLAB_ROLE_WARPS) * 512;
+            const int pixi = (ok && !(p.diag & 4)) ? (int)pix : -1;
+            int prow[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) prow[it] = __shfl_sync(0xffffffffu, pixi, it * 8 + (lane >> 2));
+            const int j4 = lane & 3, swz = (lane >> 1) & 3;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              const int nb = t.nt * p.bn + c0;
+              if (nb + 16 > p.cout) {  // partial chunk (hidden sizes that are no multiple of 4 units): per-lane form
+                epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok && !(p.diag & 4), cur);
+                uint32_t rr[16];
+                tmem_ld16(taddr + c0, rr);
+                if (ok && nb < p.cout && !(p.diag & 4))
+                  epilogue_chunk16<LSTM, FL>(ea, rr, nb, s_scale + nb, s_shift + nb, s_scale + nb, out_row, mask_row, cur);
+                continue;
+              }
+              const int cb = nb + 4 * j4;
+              float4 ac[4];
+              float cpv[4];
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                cpv[it] = 0.f;
+                if (prow[it] < 0) continue;
+                const size_t o = (size_t)prow[it] * p.out_ld + p.out_coff + cb;
+                ac[it] = *reinterpret_cast<const float4*>(acc_in + o);
+                if (p.lstm_c_prev) cpv[it] = p.lstm_c_prev[o >> 2];
+              }
+              uint32_t rr[16];
+              tmem_ld16(taddr + c0, rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ swz) << 2)) =
+                    make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
+                                __uint_as_float(rr[4 * j + 3]));
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + (lane >> 2);
+                const float4 x = *reinterpret_cast<const float4*>(stg + row * 16 + ((j4 ^ ((row >> 1) & 3)) << 2));
+                if (prow[it] < 0) continue;
+                const size_t o = (size_t)prow[it] * p.out_ld + p.out_coff + cb;
+                const float gi = ivf_sigmoid_f(x.x + ac[it].x), gf = ivf_sigmoid_f(x.y + ac[it].y);
+                const float gg = tanhf(x.z + ac[it].z), go = ivf_sigmoid_f(x.w + ac[it].w);
+                const float cn = fmaf(gf, cpv[it], gi * gg);
+                const float hn = go * tanhf(cn);
+                p.lstm_c_next[o >> 2] = cn;
+                p.lstm_h_next[o >> 2] = __float2bfloat16_rn(hn);
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(gi, gf, gg, go);
+              }
+              __syncwarp();
+            }
+          } else if (p.kwm == 1) {
             for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
               const int nb = t.nt * p.bn + c0;
               epilogue_prefetch<FL>(ea, nb, out_row, mask_row, ok && !(p.diag & 4), cur);
@@ -869,6 +1013,25 @@ bool slab_config_impl(const ivf_conv_desc* d, int sm_count, SlabParams* best) {
           p->a_stages = a_stages;
           p->b_stages = b_stages;
           p->xch_seg = xch_seg;
+          // transposition staging of the epilogue (kwm == 1 only).  fp32 outputs get it (a weight stage is given up
+          // if need be, never below two): ConvLSTM step 3.90 -> 3.49 ms at 8 clips, 10.15 -> 8.54 ms at 32.  bf16
+          // outputs do not by default - their 32-byte row pieces are a quarter of the lines per element, the
+          // epilogue hides behind the MMAs and the I3D step measured 0.5 % slower with it.  IVF_SLAB_XPOSE: 0 = never,
+          // 1 = fp32 outputs (default), 2 = bf16 too where the plan leaves the room, 3 = bf16 too, shrinking
+          p->est_off = 0;
+          const int xmode = env_int("IVF_SLAB_XPOSE", 1);
+          if (kwm == 1 && xmode && ((d->flags & IVF_EP_OUT_F32) || xmode >= 2) &&
+              (long long)d->n * d->id * d->ih * d->iw < (1ll << 31) && d->out_ld % 4 == 0 && d->out_coff % 4 == 0) {
+            const bool may_shrink = (d->flags & IVF_EP_OUT_F32) || xmode == 3;
+            auto used = [&](int bst) { return (uint32_t)a_stages * a_stage + (((uint32_t)bst * b_stage + 1023u) & ~1023u); };
+            int bst = b_stages;
+            while (used(bst) + SLAB_EST_BYTES > SLAB_SMEM_BUDGET && may_shrink && bst > 2) --bst;
+            if (used(bst) + SLAB_EST_BYTES <= SLAB_SMEM_BUDGET) {
+              b_stages = bst;
+              p->est_off = used(bst);
+            }
+          }
+          p->b_stages = b_stages;
           p->xch_off = (uint32_t)a_stages * a_stage + (((uint32_t)b_stages * b_stage + 1023u) & ~1023u);
           p->a_stage_bytes = a_stage;
           p->b_stage_bytes = b_stage;
@@ -898,7 +1061,7 @@ int slab_launch_t(ivf_handle* h, const SlabParams& p, const CUtensorMap& ma, con
                                   (int)(SLAB_SMEM_BUDGET + 1024)));
     h->slab_attr_set[slot] = true;
   }
-  const size_t smem = (size_t)p.xch_off + (size_t)2 * 4 * p.mt * p.xch_seg * 4 + 1024;
+  const size_t smem = (size_t)p.xch_off + (size_t)2 * 4 * p.mt * p.xch_seg * 4 + (p.est_off ? SLAB_EST_BYTES : 0u) + 1024;
   const int units = h->sm_count / NCTA;  // CTAs, or CTA pairs
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
   const SlabOperands o = {scale, shift, acc_in, (const __nv_bfloat16*)mask_y, mask_scale, out};
@@ -918,7 +1081,8 @@ int slab_launch_group(ivf_handle* h, const SlabParams (&p)[2], const CUtensorMap
   }
   size_t smem = 0;
   for (int i = 0; i < 2; ++i)
-    smem = std::max(smem, (size_t)p[i].xch_off + (size_t)2 * 4 * p[i].mt * p[i].xch_seg * 4 + 1024);
+    smem = std::max(smem, (size_t)p[i].xch_off + (size_t)2 * 4 * p[i].mt * p[i].xch_seg * 4 +
+                              (p[i].est_off ? SLAB_EST_BYTES : 0u) + 1024);
   IVF_CUDA(ivf_launch(conv_slab_kernel<64, 1, false, true>, dim3(grid), dim3(SLAB_THREADS), smem, st, 1, ma[0], mb[0], p[0],
                       o[0], ma[1], mb[1], p[1], o[1], split));
   IVF_LAUNCHED(h);
@@ -1106,7 +1270,7 @@ extern "C" int ivf_conv_slab_plan(const ivf_conv_desc* d, int sm_count, int* pla
   plan[0] = p.kch; plan[1] = p.bn; plan[2] = p.ntiles; plan[3] = p.mt; plan[4] = p.th;
   plan[5] = p.acc_stages; plan[6] = p.a_stages; plan[7] = p.b_stages;
   plan[8] = d->n * p.dgroups * ((p.htiles + p.ncta - 1) / p.ncta) * p.ntiles;
-  plan[9] = (int)(p.xch_off + 2u * 4u * (uint32_t)p.mt * (uint32_t)p.xch_seg * 4u);
+  plan[9] = (int)(p.xch_off + 2u * 4u * (uint32_t)p.mt * (uint32_t)p.xch_seg * 4u + (p.est_off ? SLAB_EST_BYTES : 0u));
   plan[10] = p.kwm;
   plan[11] = p.ncta;
   return 1;

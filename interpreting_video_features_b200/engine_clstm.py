@@ -54,7 +54,8 @@ class CLSTMEngine:
         # convolution + gate-kernel pair - the gate math (4 expf + 2 tanhf per hidden unit) lengthens the epilogue of
         # a one-to-two-wave convolution by more than the separate bandwidth-bound gate kernel costs - so it is opt-in.
         import os
-        self.unit_major = bf and os.environ.get("IVF_CLSTM_FUSED", "0") != "0"
+        self.fused_mode = os.environ.get("IVF_CLSTM_FUSED", "0") if bf else "0"  # "2": small maps only (per layer)
+        self.unit_major = self.fused_mode == "1"
         self.he = he
         B, T = batch, clip[0]
         N = T * B
@@ -96,7 +97,9 @@ class CLSTMEngine:
             whs = [sd[p + "Wh%s.weight" % g].contiguous() for g in GATES]
             # gate-major [i.. | f.. | c.. | o..], or unit-major [i0 f0 c0 o0 i1 ...] when the gates run in the recurrent
             # convolution's epilogue (a 16-column accumulator chunk then holds four whole hidden units)
-            um = self.unit_major
+            # "2": fuse the layers whose recurrent convolution is less than one wave of tiles (a launch of pure
+            # latency either way: the fused form saves the gate kernel's launch)
+            um = self.unit_major or (self.fused_mode == "2" and B * (hin // 2) * (win // 2) <= 128 * 148)
             gate_offs = list(range(4)) if um else [gi * he for gi in range(4)]
             bias_host = torch.zeros(4 * he)
             for gi, g in enumerate(GATES):
@@ -116,7 +119,7 @@ class CLSTMEngine:
             ones = torch.empty(4 * he, dtype=torch.float32, device=dev)
             _lib.check(lib.ivf_fill_u32(_lib.handle(dev), _lib.ptr(ones), 16 * he, 0x3F800000, _lib.stream_ptr(dev)),
                        "ivf_fill_u32")  # 1.0f
-            rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias, ones=ones)
+            rec = dict(l=l, ho=ho, wo=wo, hin=hin, win=win, bias=bias, ones=ones, um=um)
             gk = dict(co_offs=gate_offs, co_total=4 * he, co_stride=4 if um else 1)
             if bf:  # stride-2 5x5 as a stride-1 3x3 over the 2-D space-to-depth record (12 -> 16 channels at l = 0)
                 xk = dict(s2d=(1, 2, 2), ci_stride=cin_eff, ceff_total=16 if l == 0 else None, **gk)
@@ -237,7 +240,7 @@ class CLSTMEngine:
                 gx_t = self._step(rec["gx"], t)
                 c_prev = rec["c"][(t - 1) * B:t * B] if t > 0 else None
                 c_next, gact_t = rec["c"][t * B:(t + 1) * B], rec["gact"][t * B:(t + 1) * B].view(m, 4 * he)
-                if t > 0 and self.unit_major:  # convolution + gates + state update in one launch
+                if t > 0 and rec["um"]:  # convolution + gates + state update in one launch
                     ops.conv_lstm_step(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, c_prev, c_next,
                                        self._step(rec["h"], t), gact_t, (1, 5, 5), (0, 2, 2), plan=rec.get("plan_hf"))
                     continue
@@ -245,7 +248,7 @@ class CLSTMEngine:
                     ops.conv3d(self._step(rec["h"], t - 1), rec["wh_f"], gx_t, (1, 5, 5), (1, 1, 1), (0, 2, 2), acc_in=gx_t,
                                plan=rec.get("plan_hf"))
                 ops.clstm_gates_fwd(gx_t.buf.view(m, 4 * he), c_prev, c_next, self._step(rec["h"], t).buf, gact_t,
-                                    unit_major=self.unit_major)
+                                    unit_major=rec["um"])
             ops.bn_pool2d_fwd(rec["h"].buf.view(T * B, rec["ho"], rec["wo"], he), self.bn_scale, self.bn_shift,
                               rec["pooled"].buf, rec["argmax"], s2d=rec["s2d_out"])
         if self.w_fc is None:
@@ -284,7 +287,7 @@ class CLSTMEngine:
                 ops.clstm_gates_bwd(rec["gact"][t * B:(t + 1) * B].view(m, 4 * he),
                                     rec["c"][(t - 1) * B:t * B] if t > 0 else None, rec["c"][t * B:(t + 1) * B],
                                     self._step(dH, t).buf, rec["dc"], self._step(rec["dpre"], t).buf,
-                                    unit_major=self.unit_major)
+                                    unit_major=rec["um"])
                 if t > 0:
                     dprev = self._step(dH, t - 1)
                     if self.mode == "fp32":
