@@ -367,6 +367,50 @@ int ivf_bn_pool2d_bwd(ivf_handle* h, int dtype, const void* dy, const uint8_t* a
 int ivf_viz_triptych(ivf_handle* h, int clip_dtype, const void* clip, const float* cam, const float* pert,
                      const float* mask, int t, int hh, int ww, int draw_dots, uint8_t* out, void* stream);
 
+/* ---- training step (pt/train_i3d_smth.py:192-250: model.train(), forward, CrossEntropyLoss, backward, step) -----
+ * What the training path adds to the interpretation path: BatchNorm3d with batch statistics
+ * (pt/models/I3D_doubled.py:75: eps 1e-3, momentum 0.01) forward and backward, the convolution weight gradient,
+ * the classifier head with dropout + cross-entropy, and the optimizer update.  Tensors are channels-last
+ * [rows][ld] with a channel offset (dtype IVF_F32 | IVF_BF16); statistics and parameter gradients are fp32.
+ *
+ * ivf_bn_train_fwd: y = relu?(gamma * (z - mean_batch) * rstd_batch + beta) over m rows of c channels; writes
+ *   save_mean / save_rstd (fp32 [c]) for the backward pass and, when running_mean is given, updates the running
+ *   statistics in place as nn.BatchNorm3d does (running_var with the unbiased batch variance).  ws: 2*c doubles.
+ * ivf_bn_train_bwd: g = dy * [y > 0] (y NULL: no ReLU); dgamma = sum g*xhat, dbeta = sum g,
+ *   dz = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat)).  dz may alias dy.  ws: 2*c doubles.            */
+int ivf_bn_train_fwd(ivf_handle* h, int dtype, const void* z, int z_ld, int z_coff, long long m, int c,
+                     const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, float* save_mean, float* save_rstd, double* ws, void* y, int y_ld,
+                     int y_coff, int relu, void* stream);
+int ivf_bn_train_bwd(ivf_handle* h, int dtype, const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld,
+                     int y_coff, const void* z, int z_ld, int z_coff, long long m, int c, const float* gamma,
+                     const float* save_mean, const float* save_rstd, double* ws, void* dz, int dz_ld, int dz_coff,
+                     float* dgamma, float* dbeta, void* stream);
+/* Weight gradient of the convolution d describes (autograd's convolution_backward, weight part, of
+ * pt/models/I3D_doubled.py:109-113): x = the convolution's input (d->in_ld / in_coff), dz = the gradient w.r.t. its
+ * output (d->out_ld / out_coff), dw = fp32 [cout][cin][kd][kh][kw] (the nn.Conv3d parameter's layout), overwritten.
+ * d->pd/ph/pw are the front pads of the 'same' padding, as for ivf_conv3d; d->transposed must be 0.          */
+int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, void* stream);
+/* Classifier head in training mode (pt/models/I3D_doubled.py:360-371 + nn.CrossEntropyLoss,
+ * pt/train_i3d_smth.py:124-127): pooled = mean over the pix positions of a clip's feature map (the average
+ * pool's window must cover the map) * drop (fp32 [batch][c] dropout mask already scaled by 1/keep, NULL: none);
+ * logits = pooled . w^T + bias (w fp32 [classes][c]); loss = mean over the batch of -log softmax(logits)[target];
+ * dlogits = dloss/dlogits.  The backward call returns dw, db and writes d feat (the same value at every position). */
+int ivf_head_train_fwd(ivf_handle* h, int dtype, const void* feat, int ld, int coff, int batch, int pix, int c,
+                       const float* drop, const float* w, const float* bias, const int* target, int classes,
+                       float* pooled, float* logits, float* dlogits, float* loss, void* stream);
+int ivf_head_train_bwd(ivf_handle* h, int dtype, const float* dlogits, const float* pooled, const float* drop,
+                       const float* w, int batch, int pix, int c, int classes, float* dw, float* db, void* dfeat,
+                       int ld, int coff, void* stream);
+/* out[n] = 0 with probability p, else 1/(1-p): the scaled mask of nn.Dropout(p) (pt/models/I3D_doubled.py:319) from a
+ * counter-based generator (seed + element index); the `drop` operand of the head calls above.               */
+int ivf_dropout_mask(ivf_handle* h, float* out, long long n, float p, unsigned long long seed, void* stream);
+/* In-place parameter update, kind 0 = torch.optim.SGD(momentum = beta1, weight_decay; s1 = momentum buffer, may be
+ * NULL when beta1 == 0), kind 1 = torch.optim.Adam(betas, eps, weight_decay as L2; s1 / s2 = first / second moment);
+ * step counts from 1 (pt/train_i3d_smth.py:131-138).                                                          */
+int ivf_optim_step(ivf_handle* h, int kind, float* p, const float* g, float* s1, float* s2, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ---- bring-up probes (tests only) ---------------------------------------------------
  * Loads one 128-pixel x kchunk im2col TMA tile exactly as the conv kernel does and
  * copies the shared-memory image (de-swizzled, [128][kchunk] bf16) to `tile_out`.      */

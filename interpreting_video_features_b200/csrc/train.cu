@@ -1,0 +1,519 @@
+// Training step of the I3D classifier (pt/train_i3d_smth.py:192-250: model.train(), forward,
+// CrossEntropyLoss, loss.backward(), optimizer.step()): what the interpretation path does not need and the
+// training path adds - BatchNorm3d with batch statistics (pt/models/I3D_doubled.py:75, eps 1e-3, momentum 0.01)
+// forward and backward, the convolution WEIGHT gradient, the classifier head with dropout and the loss, and the
+// SGD / Adam update.  Forward convolutions, data gradients and max-pools are the kernels of the interpretation
+// path (ivf_conv3d, ivf_maxpool3d_*).  All tensors are channels-last [pixels][ld] with a channel offset, like every
+// activation of the engine; element type fp32 or bf16, statistics and gradients of parameters fp32.
+//
+// These are first-correct CUDA-core kernels (the weight gradient is a tiled fp32 outer-product GEMM with atomics
+// across pixel splits, not a tcgen05 kernel): parity against torch autograd first, see DESIGN.md "Training step".
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, long long i) { return ivf_to_float(p[i]); }
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchNorm (training): blocks of 32 channels x 8 row lanes; grid.x = channel groups, grid.y = row splits
+constexpr int BN_ROWS = 8;
+
+// Per-channel sums are accumulated in DOUBLE from the first addend on, like ATen's CPU BatchNorm (acc_type<float> =
+// double): the backward sums cancel almost completely on this network (a BatchNorm bias that feeds another
+// convolution + BatchNorm: sum g is ~1e-4 of sum |g|), and fp32 partial sums per thread left dbeta of such a tensor
+// 2 % off.  The kernels are bound by the memory traffic, not by the fp64 adds.
+__device__ __forceinline__ void bn_block_reduce2(double a, double b, double* dst_a, double* dst_b, int c, bool cok) {
+  __shared__ double sa[BN_ROWS][33], sb[BN_ROWS][33];
+  sa[threadIdx.y][threadIdx.x] = a;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && cok) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int r = 0; r < BN_ROWS; ++r) {
+      ta += sa[r][threadIdx.x];
+      tb += sb[r][threadIdx.x];
+    }
+    atomicAdd(dst_a + c, ta);
+    if (dst_b) atomicAdd(dst_b + c, tb);
+  }
+}
+
+// pass 1: ws[c] += sum z ; pass 2 (mean known): ws[C + c] += sum (z - mean)^2
+template <typename T, int PASS>
+__global__ void __launch_bounds__(32 * BN_ROWS)
+bn_stats_kernel(const T* __restrict__ z, int ld, int coff, long long m, int C, double* __restrict__ ws) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cok = c < C;
+  double mean = 0.0;
+  if (PASS == 2 && cok) mean = ws[c] / (double)m;
+  double acc = 0.0;
+  if (cok) {
+    for (long long r = (long long)blockIdx.y * BN_ROWS + threadIdx.y; r < m; r += (long long)gridDim.y * BN_ROWS) {
+      const double v = (double)ldf(z, r * ld + coff + c);
+      if (PASS == 1) acc += v;
+      else acc += (v - mean) * (v - mean);
+    }
+  }
+  bn_block_reduce2(acc, 0.0, PASS == 1 ? ws : ws + C, nullptr, c, cok);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * BN_ROWS)
+bn_apply_kernel(const T* __restrict__ z, int z_ld, int z_coff, long long m, int C, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                float* __restrict__ running_var, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                const double* __restrict__ ws, T* __restrict__ y, int y_ld, int y_coff, int relu) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= C) return;
+  const float mean = (float)(ws[c] / (double)m);
+  const float var = (float)(ws[C + c] / (double)m);  // biased: what normalises the batch
+  const float rstd = rsqrtf(var + eps);
+  const float g = gamma[c] * rstd, b = beta[c] - mean * g;
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    save_mean[c] = mean;
+    save_rstd[c] = rstd;
+    if (running_mean) {  // nn.BatchNorm3d: running_var takes the UNBIASED batch variance
+      const float unb = m > 1 ? (float)(ws[C + c] / (double)(m - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+  }
+  for (long long r = (long long)blockIdx.y * BN_ROWS + threadIdx.y; r < m; r += (long long)gridDim.y * BN_ROWS) {
+    float v = fmaf(ldf(z, r * z_ld + z_coff + c), g, b);
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * y_ld + y_coff + c] = ivf_from_float<T>(v);
+  }
+}
+
+// backward pass 1: ws[c] += sum g, ws[C + c] += sum g * xhat, g = dy * [y > 0]
+template <typename T>
+__global__ void __launch_bounds__(32 * BN_ROWS)
+bn_bwd_stats_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
+                    const T* __restrict__ z, int z_ld, int z_coff, long long m, int C,
+                    const float* __restrict__ save_mean, const float* __restrict__ save_rstd, double* __restrict__ ws) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool cok = c < C;
+  double sg = 0.0, sgx = 0.0;
+  if (cok) {
+    const float mean = save_mean[c], rstd = save_rstd[c];
+    for (long long r = (long long)blockIdx.y * BN_ROWS + threadIdx.y; r < m; r += (long long)gridDim.y * BN_ROWS) {
+      float g = ldf(dy, r * dy_ld + dy_coff + c);
+      if (y && !(ldf(y, r * y_ld + y_coff + c) > 0.f)) g = 0.f;
+      sg += (double)g;
+      sgx += (double)g * (double)((ldf(z, r * z_ld + z_coff + c) - mean) * rstd);
+    }
+  }
+  bn_block_reduce2(sg, sgx, ws, ws + C, c, cok);
+}
+
+// backward pass 2: dz = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat))
+template <typename T>
+__global__ void __launch_bounds__(32 * BN_ROWS)
+bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
+                    const T* __restrict__ z, int z_ld, int z_coff, long long m, int C, const float* __restrict__ gamma,
+                    const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                    const double* __restrict__ ws, T* __restrict__ dz, int dz_ld, int dz_coff,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= C) return;
+  const float mean = save_mean[c], rstd = save_rstd[c];
+  const float sg = (float)ws[c], sgx = (float)ws[C + c];
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    dbeta[c] = sg;
+    dgamma[c] = sgx;
+  }
+  const float k = gamma[c] * rstd, mg = sg / (float)m, mgx = sgx / (float)m;
+  for (long long r = (long long)blockIdx.y * BN_ROWS + threadIdx.y; r < m; r += (long long)gridDim.y * BN_ROWS) {
+    float g = ldf(dy, r * dy_ld + dy_coff + c);
+    if (y && !(ldf(y, r * y_ld + y_coff + c) > 0.f)) g = 0.f;
+    const float xh = (ldf(z, r * z_ld + z_coff + c) - mean) * rstd;
+    dz[r * dz_ld + dz_coff + c] = ivf_from_float<T>(k * (g - mg - xh * mgx));
+  }
+}
+
+dim3 bn_grid(const ivf_handle* h, long long m, int C) {
+  const int gx = (C + 31) / 32;
+  long long gy = (m + BN_ROWS - 1) / BN_ROWS;
+  const long long want = (long long)(h->sm_count * 8 + gx - 1) / gx;  // ~8 blocks per SM over all channel groups
+  if (gy > want) gy = want;
+  if (gy < 1) gy = 1;
+  return dim3(gx, (unsigned)gy);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Convolution weight gradient: dw[co][ci][tap] += sum_p dz[p][co] * x[p @ tap][ci] (fp32 OIDHW, atomics over the
+// pixel splits).  Block = 256 threads = 16 x 16, each RCO x RCI outputs: tile 64 co x (16*RCI) ci for ONE tap.
+constexpr int WG_PT = 16;  // pixels per shared-memory stage
+
+template <typename T, int RCI>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(ivf_conv_desc d, const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw,
+             int co_tiles, int ci_tiles, long long pix_per_block) {
+  constexpr int TCO = 64, TCI = 16 * RCI;
+  __shared__ float sdz[WG_PT][TCO + 4];
+  __shared__ float sx[WG_PT][TCI + 4];
+  __shared__ long long xoff[WG_PT];  // element offset of the tap's input pixel, -1 = padding / past the end
+  __shared__ long long zoff[WG_PT];
+  const int taps = d.kd * d.kh * d.kw;
+  int b = blockIdx.x;
+  const int cit = b % ci_tiles;
+  b /= ci_tiles;
+  const int cot = b % co_tiles;
+  const int tap = b / co_tiles;
+  const int kw_i = tap % d.kw, kh_i = (tap / d.kw) % d.kh, kd_i = tap / (d.kw * d.kh);
+  const int co0 = cot * TCO, ci0 = cit * TCI;
+  const long long P = (long long)d.n * d.od * d.oh * d.ow;
+  const long long p_lo = (long long)blockIdx.y * pix_per_block;
+  const long long p_hi = p_lo + pix_per_block < P ? p_lo + pix_per_block : P;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][RCI];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RCI; ++j) acc[i][j] = 0.f;
+  for (long long p0 = p_lo; p0 < p_hi; p0 += WG_PT) {
+    if (threadIdx.x < WG_PT) {
+      const long long p = p0 + threadIdx.x;
+      long long xo = -1, zo = -1;
+      if (p < p_hi) {
+        zo = p * d.out_ld + d.out_coff;
+        const int ow = (int)(p % d.ow);
+        long long t = p / d.ow;
+        const int oh = (int)(t % d.oh);
+        t /= d.oh;
+        const int od = (int)(t % d.od);
+        const int n = (int)(t / d.od);
+        const int iz = od * d.sd - d.pd + kd_i, iy = oh * d.sh - d.ph + kh_i, ix = ow * d.sw - d.pw + kw_i;
+        if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+          xo = ((((long long)n * d.id + iz) * d.ih + iy) * d.iw + ix) * d.in_ld + d.in_coff;
+      }
+      xoff[threadIdx.x] = xo;
+      zoff[threadIdx.x] = zo;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < WG_PT * TCO; i += 256) {
+      const int pp = i / TCO, cc = i - pp * TCO;
+      const long long zo = zoff[pp];
+      sdz[pp][cc] = (zo >= 0 && co0 + cc < d.cout) ? ldf(dz, zo + co0 + cc) : 0.f;
+    }
+    for (int i = threadIdx.x; i < WG_PT * TCI; i += 256) {
+      const int pp = i / TCI, cc = i - pp * TCI;
+      const long long xo = xoff[pp];
+      sx[pp][cc] = (xo >= 0 && ci0 + cc < d.cin) ? ldf(x, xo + ci0 + cc) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < WG_PT; ++pp) {
+      float a[4], bb[RCI];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sdz[pp][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < RCI; ++j) bb[j] = sx[pp][tx * RCI + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < RCI; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= d.cout) continue;
+#pragma unroll
+    for (int j = 0; j < RCI; ++j) {
+      const int ci = ci0 + tx * RCI + j;
+      if (ci < d.cin && acc[i][j] != 0.f) atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, cudaStream_t st) {
+  const int taps = d->kd * d->kh * d->kw;
+  const long long P = (long long)d->n * d->od * d->oh * d->ow;
+  IVF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->cout * d->cin * taps, st));
+  const bool narrow = d->cin <= 16;
+  const int tci = narrow ? 16 : 64;
+  const int co_tiles = (d->cout + 63) / 64, ci_tiles = (d->cin + tci - 1) / tci;
+  const long long bx = (long long)taps * co_tiles * ci_tiles;
+  IVF_REQUIRE(bx < (1ll << 31), "ivf_conv3d_wgrad: too many tiles");
+  long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;  // ~8 blocks per SM in total
+  const long long max_splits = (P + 255) / 256;                   // at least 256 pixels per block
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  long long ppb = (P + splits - 1) / splits;
+  ppb = (ppb + WG_PT - 1) / WG_PT * WG_PT;
+  splits = (P + ppb - 1) / ppb;
+  const dim3 grid((unsigned)bx, (unsigned)splits);
+  if (narrow)
+    wgrad_kernel<T, 1><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, co_tiles, ci_tiles, ppb);
+  else
+    wgrad_kernel<T, 4><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, co_tiles, ci_tiles, ppb);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Classifier head in training mode (pt/models/I3D_doubled.py:360-371 with the dropout active;
+// pt/train_i3d_smth.py:124-127 CrossEntropyLoss, mean over the batch).  The feature map must be exactly the
+// average pool's window (one pooled position per clip), as in the engine.
+template <typename T>
+__global__ void head_pool_kernel(const T* __restrict__ feat, int ld, int coff, int pix, int C,
+                                 const float* __restrict__ drop, float* __restrict__ pooled) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < pix; ++p) s += ldf(feat, ((long long)b * pix + p) * ld + coff + c);
+  s /= (float)pix;
+  if (drop) s *= drop[(long long)b * C + c];
+  pooled[(long long)b * C + c] = s;
+}
+
+// one block per clip: logits = pooled . W^T + bias, then softmax, loss_b = -log p[target], dlogits
+__global__ void __launch_bounds__(256)
+head_logits_ce_kernel(const float* __restrict__ pooled, const float* __restrict__ w, const float* __restrict__ bias,
+                      const int* __restrict__ target, int B, int C, int K, float* __restrict__ logits,
+                      float* __restrict__ dlogits, float* __restrict__ loss) {
+  extern __shared__ float sl[];  // K logits
+  __shared__ float red[8];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < K; k += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(pooled[(long long)b * C + c], w[(long long)k * C + c], s);
+    s = ivf_warp_sum(s);
+    if (lane == 0) sl[k] = s + bias[k];
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += 256) mx = fmaxf(mx, sl[k]);
+  mx = ivf_warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float se = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) se += expf(sl[k] - mx);
+  se = ivf_warp_sum(se);
+  if (lane == 0) red[warp] = se;
+  __syncthreads();
+  se = 0.f;
+  for (int i = 0; i < 8; ++i) se += red[i];
+  const int t = target[b];
+  const float lse = mx + logf(se);
+  for (int k = threadIdx.x; k < K; k += 256) {
+    logits[(long long)b * K + k] = sl[k];
+    dlogits[(long long)b * K + k] = (expf(sl[k] - lse) - (k == t ? 1.f : 0.f)) / (float)B;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, (lse - sl[t]) / (float)B);
+}
+
+// dW[k][c] = sum_b dlogits[b][k] pooled[b][c] ; db[k] = sum_b dlogits[b][k]
+__global__ void head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled, int B, int C, int K,
+                                  float* __restrict__ dw, float* __restrict__ db) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)K * C) {
+    const int k = (int)(i / C), c = (int)(i - (long long)k * C);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dlogits[(long long)b * K + k], pooled[(long long)b * C + c], s);
+    dw[i] = s;
+  }
+  if (i < K) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dlogits[(long long)b * K + i];
+    db[i] = s;
+  }
+}
+
+// d feat[b][p][c] = (sum_k dlogits[b][k] W[k][c]) * drop[b][c] / pix, the same for every pooled pixel
+template <typename T>
+__global__ void head_dfeat_kernel(const float* __restrict__ dlogits, const float* __restrict__ w,
+                                  const float* __restrict__ drop, int pix, int C, int K, T* __restrict__ dfeat, int ld,
+                                  int coff) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(dlogits[(long long)b * K + k], w[(long long)k * C + c], s);
+  if (drop) s *= drop[(long long)b * C + c];
+  s /= (float)pix;
+  for (int p = 0; p < pix; ++p) dfeat[((long long)b * pix + p) * ld + coff + c] = ivf_from_float<T>(s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// torch.optim.SGD (momentum, weight decay, no dampening / Nesterov) and torch.optim.Adam (L2 weight decay)
+__global__ void optim_kernel(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1,
+                             float* __restrict__ s2, long long n, float lr, float b1, float b2, float eps, float wd,
+                             int step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] + wd * p[i];
+  if (kind == 0) {
+    if (b1 != 0.f) {
+      const float buf = step == 1 ? gi : b1 * s1[i] + gi;  // first step: the buffer IS the gradient
+      s1[i] = buf;
+      gi = buf;
+    }
+    p[i] -= lr * gi;
+  } else {
+    const float m = b1 * s1[i] + (1.f - b1) * gi;
+    const float v = b2 * s2[i] + (1.f - b2) * gi * gi;
+    s1[i] = m;
+    s2[i] = v;
+    const float c1 = 1.f - powf(b1, (float)step), c2 = 1.f - powf(b2, (float)step);
+    p[i] -= lr / c1 * m / (sqrtf(v) / sqrtf(c2) + eps);
+  }
+}
+
+// dropout mask, already scaled: 0 with probability p, else 1/(1-p); one counter-based hash per element
+// (the reference draws from torch's generator, pt/models/I3D_doubled.py:319 - no stream can match it bit for bit)
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);  // splitmix64
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  const float u = (float)(x >> 40) * (1.0f / 16777216.0f);
+  out[i] = u < p ? 0.f : 1.f / (1.f - p);
+}
+
+}  // namespace
+
+extern "C" int ivf_dropout_mask(ivf_handle* h, float* out, long long n, float p, unsigned long long seed,
+                                void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && out && n > 0 && p >= 0.f && p < 1.f, "ivf_dropout_mask: null argument or p outside [0, 1)");
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ivf_bn_train_fwd(ivf_handle* h, int dtype, const void* z, int z_ld, int z_coff, long long m, int c,
+                                const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                float* running_var, float* save_mean, float* save_rstd, double* ws, void* y, int y_ld,
+                                int y_coff, int relu, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && z && gamma && beta && save_mean && save_rstd && ws && y && m > 0 && c > 0,
+              "ivf_bn_train_fwd: null argument or empty tensor");
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_bn_train_fwd: unknown dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  IVF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st));
+  const dim3 grid = bn_grid(h, m, c), block(32, BN_ROWS);
+#define IVF_BN_FWD(T)                                                                                              \
+  do {                                                                                                             \
+    bn_stats_kernel<T, 1><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, ws);                            \
+    IVF_LAUNCHED(h);                                                                                               \
+    bn_stats_kernel<T, 2><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, ws);                            \
+    IVF_LAUNCHED(h);                                                                                               \
+    bn_apply_kernel<T><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, gamma, beta, eps, momentum,       \
+                                               running_mean, running_var, save_mean, save_rstd, ws, (T*)y, y_ld,  \
+                                               y_coff, relu);                                                      \
+    IVF_LAUNCHED(h);                                                                                               \
+  } while (0)
+  if (dtype == IVF_F32) IVF_BN_FWD(float);
+  else IVF_BN_FWD(__nv_bfloat16);
+#undef IVF_BN_FWD
+  return IVF_OK;
+}
+
+extern "C" int ivf_bn_train_bwd(ivf_handle* h, int dtype, const void* dy, int dy_ld, int dy_coff, const void* y,
+                                int y_ld, int y_coff, const void* z, int z_ld, int z_coff, long long m, int c,
+                                const float* gamma, const float* save_mean, const float* save_rstd, double* ws,
+                                void* dz, int dz_ld, int dz_coff, float* dgamma, float* dbeta, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && dy && z && gamma && save_mean && save_rstd && ws && dz && dgamma && dbeta && m > 0 && c > 0,
+              "ivf_bn_train_bwd: null argument or empty tensor");
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_bn_train_bwd: unknown dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  IVF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st));
+  const dim3 grid = bn_grid(h, m, c), block(32, BN_ROWS);
+#define IVF_BN_BWD(T)                                                                                              \
+  do {                                                                                                             \
+    bn_bwd_stats_kernel<T><<<grid, block, 0, st>>>((const T*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,       \
+                                                   (const T*)z, z_ld, z_coff, m, c, save_mean, save_rstd, ws);     \
+    IVF_LAUNCHED(h);                                                                                               \
+    bn_bwd_apply_kernel<T><<<grid, block, 0, st>>>((const T*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,       \
+                                                   (const T*)z, z_ld, z_coff, m, c, gamma, save_mean, save_rstd,   \
+                                                   ws, (T*)dz, dz_ld, dz_coff, dgamma, dbeta);                     \
+    IVF_LAUNCHED(h);                                                                                               \
+  } while (0)
+  if (dtype == IVF_F32) IVF_BN_BWD(float);
+  else IVF_BN_BWD(__nv_bfloat16);
+#undef IVF_BN_BWD
+  return IVF_OK;
+}
+
+extern "C" int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw,
+                                void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && d && x && dz && dw, "ivf_conv3d_wgrad: null argument");
+  IVF_REQUIRE(d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->od > 0 && d->oh > 0 && d->ow > 0 && d->cin > 0 &&
+                  d->cout > 0 && d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0 &&
+                  !d->transposed && d->in_ld >= d->in_coff + d->cin && d->out_ld >= d->out_coff + d->cout,
+              "ivf_conv3d_wgrad: bad descriptor");
+  if (d->dtype == IVF_F32) return wgrad_launch<float>(h, d, x, dz, dw, (cudaStream_t)stream);
+  if (d->dtype == IVF_BF16) return wgrad_launch<__nv_bfloat16>(h, d, x, dz, dw, (cudaStream_t)stream);
+  IVF_FAIL(IVF_EINVAL, "ivf_conv3d_wgrad: unknown dtype %d", d->dtype);
+}
+
+extern "C" int ivf_head_train_fwd(ivf_handle* h, int dtype, const void* feat, int ld, int coff, int batch, int pix,
+                                  int c, const float* drop, const float* w, const float* bias, const int* target,
+                                  int classes, float* pooled, float* logits, float* dlogits, float* loss,
+                                  void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && feat && w && bias && target && pooled && logits && dlogits && loss && batch > 0 && pix > 0 &&
+                  c > 0 && classes > 0 && classes <= 8192,
+              "ivf_head_train_fwd: null argument or bad size");
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_head_train_fwd: unknown dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  IVF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  const dim3 grid((c + 127) / 128, batch);
+  if (dtype == IVF_F32)
+    head_pool_kernel<float><<<grid, 128, 0, st>>>((const float*)feat, ld, coff, pix, c, drop, pooled);
+  else
+    head_pool_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, ld, coff, pix, c, drop, pooled);
+  IVF_LAUNCHED(h);
+  head_logits_ce_kernel<<<batch, 256, sizeof(float) * classes, st>>>(pooled, w, bias, target, batch, c, classes, logits,
+                                                                    dlogits, loss);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+extern "C" int ivf_head_train_bwd(ivf_handle* h, int dtype, const float* dlogits, const float* pooled,
+                                  const float* drop, const float* w, int batch, int pix, int c, int classes, float* dw,
+                                  float* db, void* dfeat, int ld, int coff, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && dlogits && pooled && w && dw && db && dfeat && batch > 0 && pix > 0 && c > 0 && classes > 0,
+              "ivf_head_train_bwd: null argument or bad size");
+  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_head_train_bwd: unknown dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)classes * c;
+  head_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dlogits, pooled, batch, c, classes, dw, db);
+  IVF_LAUNCHED(h);
+  const dim3 grid((c + 127) / 128, batch);
+  if (dtype == IVF_F32)
+    head_dfeat_kernel<float><<<grid, 128, 0, st>>>(dlogits, w, drop, pix, c, classes, (float*)dfeat, ld, coff);
+  else
+    head_dfeat_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(dlogits, w, drop, pix, c, classes, (__nv_bfloat16*)dfeat, ld,
+                                                           coff);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+extern "C" int ivf_optim_step(ivf_handle* h, int kind, float* p, const float* g, float* s1, float* s2, long long n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && p && g && n > 0 && step >= 1, "ivf_optim_step: null argument, empty tensor or step < 1");
+  IVF_REQUIRE(kind == 0 || kind == 1, "ivf_optim_step: kind must be 0 (SGD) or 1 (Adam)");
+  IVF_REQUIRE(kind == 0 ? (beta1 == 0.f || s1) : (s1 && s2), "ivf_optim_step: optimizer state buffers missing");
+  optim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, p, g, s1, s2, n, lr, beta1, beta2,
+                                                                             eps, weight_decay, step);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}

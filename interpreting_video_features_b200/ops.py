@@ -415,3 +415,71 @@ def probe_im2col(x, kernel, stride, pad_front, out_dhw, m0, tap, c0):
     check(_lib.load().ivf_probe_im2col(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), m0, tap, c0,
                                        ptr(tile), _lib.stream_ptr(x.buf.device)), "ivf_probe_im2col")
     return tile
+
+
+# ---------------------------------------------------------------------------------------- training step (train.cu)
+def bn_train_fwd(z, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, ws, y, relu=True):
+    """y = relu(BatchNorm(z)) with BATCH statistics over all pixels of the Act z (ivf_bn_train_fwd); the running
+    statistics (fp32 [c], may be None) are updated in place; ws: float64 [2c] scratch."""
+    assert z.pixels == y.pixels and z.c == y.c and ws.dtype == torch.float64 and ws.numel() >= 2 * z.c
+    check(_lib.load().ivf_bn_train_fwd(_lib.handle(z.buf.device), _lib.dtype_code(z.buf), ptr(z.buf), z.ld, z.coff,
+                                       z.pixels, z.c, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+                                       ptr(running_var), ptr(save_mean), ptr(save_rstd), ptr(ws), ptr(y.buf), y.ld,
+                                       y.coff, int(bool(relu)), _lib.stream_ptr(z.buf.device)), "ivf_bn_train_fwd")
+    return y
+
+
+def bn_train_bwd(dy, y, z, gamma, save_mean, save_rstd, ws, dz, dgamma, dbeta):
+    """dz, dgamma, dbeta of relu(BatchNorm_train(z)) given dy (Act) and the forward's y (Act, None: no ReLU)."""
+    check(_lib.load().ivf_bn_train_bwd(_lib.handle(z.buf.device), _lib.dtype_code(z.buf), ptr(dy.buf), dy.ld, dy.coff,
+                                       ptr(y.buf if y is not None else None), y.ld if y is not None else 0,
+                                       y.coff if y is not None else 0, ptr(z.buf), z.ld, z.coff, z.pixels, z.c,
+                                       ptr(gamma), ptr(save_mean), ptr(save_rstd), ptr(ws), ptr(dz.buf), dz.ld, dz.coff,
+                                       ptr(dgamma), ptr(dbeta), _lib.stream_ptr(z.buf.device)), "ivf_bn_train_bwd")
+    return dz
+
+
+def conv3d_wgrad(x, dz, dw, kernel, stride, pad_front):
+    """dw (fp32, the nn.Conv3d parameter's [cout, cin, kd, kh, kw] layout) = weight gradient of the convolution that
+    maps the Act x to an Act shaped like dz (ivf_conv3d_wgrad)."""
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == dz.c * x.c * kernel[0] * kernel[1] * kernel[2]
+    d = conv_desc(x, dz, kernel, stride, pad_front)
+    d.flags = 0
+    check(_lib.load().ivf_conv3d_wgrad(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(dz.buf), ptr(dw),
+                                       _lib.stream_ptr(x.buf.device)), "ivf_conv3d_wgrad")
+    return dw
+
+
+def head_train_fwd(feat, drop, w, bias, target, pooled, logits, dlogits, loss):
+    """Training-mode classifier head + cross-entropy (ivf_head_train_fwd); feat: Act whose whole map is pooled."""
+    p = feat.d * feat.h * feat.w
+    check(_lib.load().ivf_head_train_fwd(_lib.handle(feat.buf.device), _lib.dtype_code(feat.buf), ptr(feat.buf), feat.ld,
+                                         feat.coff, feat.n, p, feat.c, ptr(drop), ptr(w), ptr(bias), ptr(target),
+                                         w.shape[0], ptr(pooled), ptr(logits), ptr(dlogits), ptr(loss),
+                                         _lib.stream_ptr(feat.buf.device)), "ivf_head_train_fwd")
+    return loss
+
+
+def head_train_bwd(dlogits, pooled, drop, w, dw, db, dfeat):
+    p = dfeat.d * dfeat.h * dfeat.w
+    check(_lib.load().ivf_head_train_bwd(_lib.handle(dfeat.buf.device), _lib.dtype_code(dfeat.buf), ptr(dlogits),
+                                         ptr(pooled), ptr(drop), ptr(w), dfeat.n, p, dfeat.c, w.shape[0], ptr(dw),
+                                         ptr(db), ptr(dfeat.buf), dfeat.ld, dfeat.coff,
+                                         _lib.stream_ptr(dfeat.buf.device)), "ivf_head_train_bwd")
+    return dfeat
+
+
+def optim_step(kind, p, g, s1, s2, lr, beta1, beta2, eps, weight_decay, step):
+    """In-place torch.optim.SGD (kind 'sgd': beta1 = momentum) / Adam ('adam') update of the fp32 tensor p."""
+    assert p.dtype == torch.float32 and g.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+    check(_lib.load().ivf_optim_step(_lib.handle(p.device), {"sgd": 0, "adam": 1}[kind], ptr(p), ptr(g), ptr(s1), ptr(s2),
+                                     p.numel(), lr, beta1, beta2, eps, weight_decay, step, _lib.stream_ptr(p.device)),
+          "ivf_optim_step")
+    return p
+
+
+def dropout_mask(out, p, seed):
+    """out (fp32, device) = the scaled mask of nn.Dropout(p): 0 with probability p, else 1/(1-p)."""
+    check(_lib.load().ivf_dropout_mask(_lib.handle(out.device), ptr(out), out.numel(), p, seed,
+                                       _lib.stream_ptr(out.device)), "ivf_dropout_mask")
+    return out

@@ -131,3 +131,27 @@ def test_dropin_constructor_matches_reference_weights():
     assert list(r._modules.keys()) == list(m._modules.keys())
     for k in sd:
         assert torch.equal(rsd[k], sd[k]), k
+
+
+def test_train_step_oracle_against_reference_golden():
+    """oracle/train_oracle.py (one training step: BatchNorm with batch statistics, CrossEntropyLoss, every parameter
+    gradient, SGD update) reproduces what the UNMODIFIED reference produced for the first step of
+    tests/golden/i3d_train.npz (pt/train_i3d_smth.py:208-226; written by oracle/pin_train_step.py)."""
+    from oracle import train_oracle
+    gold = np.load(os.path.join(GOLD, "i3d_train.npz"))
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = synthetic.clips(2)
+    target = torch.as_tensor(gold["target"])
+    loss, logits, grads, buf = train_oracle.loss_and_grads(sd, x, target)
+    assert abs(loss - float(gold["loss_1"])) < 1e-5 * abs(float(gold["loss_1"]))
+    np.testing.assert_allclose(logits.numpy(), gold["logits_1"], rtol=1e-4, atol=1e-5)
+    new, _ = train_oracle.sgd_step(sd, grads, float(gold["lr"]), float(gold["momentum"]), float(gold["weight_decay"]))
+    for k, g in grads.items():
+        idx = train_oracle.sample_index(k, g.numel())
+        # same torch operators in the same order as the reference: equal up to the thread count's summation order
+        ref = gold["gsamp_1/" + k]
+        assert np.linalg.norm(g.flatten()[idx].numpy() - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-9, k
+        np.testing.assert_allclose(new[k].flatten()[idx].numpy(), gold["psamp_1/" + k], rtol=1e-4, atol=1e-6)
+    for k, v in buf.items():
+        idx = train_oracle.sample_index(k, v.numel())
+        np.testing.assert_allclose(v.flatten()[idx].numpy(), gold["psamp_1/" + k], rtol=1e-4, atol=1e-6)
