@@ -383,6 +383,68 @@ def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10, with_cpu=False
                         "%d synthetic 32x120x160 clips per step" % clips_n}
 
 
+def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
+    """one TRAINING step of the I3D classifier (pt/train_i3d_smth.py:192-250: forward in training
+    mode, CrossEntropyLoss, backward to every parameter, SGD update) on synthetic 16x224x224 clips, fp32, through
+    I3DTrainer - forward convolutions and data gradients on the fp32 implicit-GEMM kernel, weight gradients on the
+    CUDA-core kernel of csrc/train.cu.  clips/s = clips per step / step time; algorithmic work per clip = forward +
+    data gradient (all but the stem's) + weight gradient convolutions."""
+    import torch.distributed as dist
+    from interpreting_video_features_b200.train import I3DTrainer
+    from oracle import i3d_oracle, synthetic
+    model = state_dict()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.stack([synthetic.uniform_clip(5000 + rank * clips_n + i) for i in range(clips_n)]).to(dev)
+    target = (torch.arange(clips_n) * 7 % NCLS).to(dev)
+    tr = I3DTrainer(sd, clips_n, (T, H, W), device=dev, optimizer="sgd", lr=1e-3, momentum=0.9, weight_decay=1e-5,
+                    dropout_p=0.5)
+    n0 = _launches(dev)
+    tr.step(x, target)  # warm-up (lazy kernel loading) and the launch count of one step
+    launches = _launches(dev) - n0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step(x, target)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    if world > 1:
+        t = torch.tensor([sec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t[0])
+    fwd = i3d_oracle.conv_flops_per_clip(sd, (T, H, W))
+    stem = 2.0 * 343 * 3 * 64 * (T // 2) * (H // 2) * (W // 2)
+    gf_clip = (3.0 * fwd - stem) / 1e9
+    val = world * clips_n / sec
+    out = {"metric": "i3d_training_clips_per_sec", "unit": "clips/s", "value": val, "ms_per_step": sec * 1e3,
+           "clips_per_step_per_gpu": clips_n, "launches_per_step": int(launches), "dtype": "f32",
+           "loss_after_%d_steps" % (steps + 1): float(loss),
+           "algorithmic_gflop_per_clip_step": gf_clip, "achieved_tflops": val / world * gf_clip / 1e3,
+           "note": "first-correct path: fp32 CUDA-core convolutions and weight gradients (no tensor-core kernel yet), "
+                   "so the bf16 tensor peak is not the roofline that applies; B200 fp32 FMA peak ~75 TFLOP/s",
+           "workload": "f4: I3D smth (174 classes) training step, %d synthetic 16x224x224 clips, SGD(momentum 0.9, "
+                       "weight decay 1e-5), dropout 0.5, BatchNorm with batch statistics" % clips_n}
+    if with_cpu and rank == 0:
+        from oracle import train_oracle
+        xc, tc = x[:2].cpu(), target[:2].cpu()
+        t0 = time.perf_counter()
+        _, _, g, _ = train_oracle.loss_and_grads(sd, xc, tc)
+        train_oracle.sgd_step(sd, g, 1e-3, 0.9, 1e-5)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "1 training step of 2 clips (16x224x224) of the oracle port of the reference's "
+                                         "PyTorch-CPU step, no warm-up"}
+    return out
+
+
+def _launches(dev):
+    from interpreting_video_features_b200 import _lib
+    return _lib.launch_count(dev)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from interpreting_video_features_b200 import _lib, search
@@ -535,6 +597,7 @@ def run_ours(args, rank, world, local_rank):
         if not args.no_gradcam else None
     clstm = clstm_throughput(dev, rank, world, args.mode, with_cpu=(world == 1 and not args.no_cpu)) \
         if not args.no_clstm else None
+    train = train_throughput(dev, rank, world, with_cpu=(world == 1 and not args.no_cpu)) if not args.no_train else None
 
     if rank != 0:
         return
@@ -548,7 +611,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32",
             "data": "synthetic", "config": CONFIG, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gradcam": gradcam, "clstm": clstm,
+            "gradcam": gradcam, "clstm": clstm, "train": train,
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "clocks": sampler.summary()}
     print(json.dumps(line), flush=True)
@@ -567,6 +630,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gradcam", action="store_true", help="skip the Grad-CAM clips/s leg")
     ap.add_argument("--no-clstm", action="store_true", help="skip the ConvLSTM (config C3) leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (f4) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -8,6 +8,8 @@
 //
 // These are first-correct CUDA-core kernels (the weight gradient is a tiled fp32 outer-product GEMM with atomics
 // across pixel splits, not a tcgen05 kernel): parity against torch autograd first, see DESIGN.md "Training step".
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace {
@@ -143,54 +145,74 @@ dim3 bn_grid(const ivf_handle* h, long long m, int C) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Convolution weight gradient: dw[co][ci][tap] += sum_p dz[p][co] * x[p @ tap][ci] (fp32 OIDHW, atomics over the
-// pixel splits).  Block = 256 threads = 16 x 16, each RCO x RCI outputs: tile 64 co x (16*RCI) ci for ONE tap.
+// Convolution weight gradient as a GEMM over the pixels: dw[co][j] = sum_p dz[p][co] * col[p][j], where the columns
+// j = tap * cin + ci run over the flattened (tap, input channel) axis - the im2col row of output pixel p, gathered
+// on the fly (zero outside the tensor: the 'same' padding).  A block owns a 64 x 64 tile of (co, j) for a range of
+// pixels and adds it to dw (fp32 OIDHW) with atomics; 256 threads = 16 x 16, each 4 x 4 outputs.  Tiling the
+// flattened axis keeps the tiles full whatever cin is: the stem (cin 3, 343 taps) is 17 column tiles of 64 instead
+// of 343 tiles holding three channels each, and a tile that spans taps still reads runs of (kw, ci) that are
+// contiguous in the channels-last input.
 constexpr int WG_PT = 16;  // pixels per shared-memory stage
 
-template <typename T, int RCI>
+template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(ivf_conv_desc d, const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw,
-             int co_tiles, int ci_tiles, long long pix_per_block) {
-  constexpr int TCO = 64, TCI = 16 * RCI;
+             int col_tiles, long long pix_per_block) {
+  constexpr int TCO = 64, TCJ = 64;
   __shared__ float sdz[WG_PT][TCO + 4];
-  __shared__ float sx[WG_PT][TCI + 4];
-  __shared__ long long xoff[WG_PT];  // element offset of the tap's input pixel, -1 = padding / past the end
+  __shared__ float sx[WG_PT][TCJ + 4];
+  __shared__ int col_off[TCJ];              // element offset of the column's (tap, ci) from the pixel's window origin
+  __shared__ int col_zyx[TCJ];              // kd | kh << 8 | kw << 16, -1: past the last column
+  __shared__ long long pix_base[WG_PT];     // element offset of the window origin (may lie in the padding)
+  __shared__ int pix_zyx[WG_PT][3];         // window origin coordinates; z = INT_MIN/2: no pixel
   __shared__ long long zoff[WG_PT];
-  const int taps = d.kd * d.kh * d.kw;
-  int b = blockIdx.x;
-  const int cit = b % ci_tiles;
-  b /= ci_tiles;
-  const int cot = b % co_tiles;
-  const int tap = b / co_tiles;
-  const int kw_i = tap % d.kw, kh_i = (tap / d.kw) % d.kh, kd_i = tap / (d.kw * d.kh);
-  const int co0 = cot * TCO, ci0 = cit * TCI;
+  const int taps = d.kd * d.kh * d.kw, ncols = taps * d.cin;
+  const int cot = blockIdx.x / col_tiles, colt = blockIdx.x - cot * col_tiles;
+  const int co0 = cot * TCO, j0 = colt * TCJ;
   const long long P = (long long)d.n * d.od * d.oh * d.ow;
   const long long p_lo = (long long)blockIdx.y * pix_per_block;
   const long long p_hi = p_lo + pix_per_block < P ? p_lo + pix_per_block : P;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][RCI];
+  if (threadIdx.x < TCJ) {
+    const int j = j0 + threadIdx.x;
+    if (j < ncols) {
+      const int tap = j / d.cin, ci = j - tap * d.cin;
+      const int kw_i = tap % d.kw, kh_i = (tap / d.kw) % d.kh, kd_i = tap / (d.kw * d.kh);
+      col_off[threadIdx.x] = ((kd_i * d.ih + kh_i) * d.iw + kw_i) * d.in_ld + ci;
+      col_zyx[threadIdx.x] = kd_i | (kh_i << 8) | (kw_i << 16);
+    } else {
+      col_off[threadIdx.x] = 0;
+      col_zyx[threadIdx.x] = -1;
+    }
+  }
+  float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < RCI; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long long p0 = p_lo; p0 < p_hi; p0 += WG_PT) {
+    __syncthreads();  // the previous stage has been consumed (and the column table is complete)
     if (threadIdx.x < WG_PT) {
       const long long p = p0 + threadIdx.x;
-      long long xo = -1, zo = -1;
       if (p < p_hi) {
-        zo = p * d.out_ld + d.out_coff;
+        zoff[threadIdx.x] = p * d.out_ld + d.out_coff;
         const int ow = (int)(p % d.ow);
         long long t = p / d.ow;
         const int oh = (int)(t % d.oh);
         t /= d.oh;
         const int od = (int)(t % d.od);
         const int n = (int)(t / d.od);
-        const int iz = od * d.sd - d.pd + kd_i, iy = oh * d.sh - d.ph + kh_i, ix = ow * d.sw - d.pw + kw_i;
-        if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
-          xo = ((((long long)n * d.id + iz) * d.ih + iy) * d.iw + ix) * d.in_ld + d.in_coff;
+        const int iz = od * d.sd - d.pd, iy = oh * d.sh - d.ph, ix = ow * d.sw - d.pw;
+        pix_zyx[threadIdx.x][0] = iz;
+        pix_zyx[threadIdx.x][1] = iy;
+        pix_zyx[threadIdx.x][2] = ix;
+        pix_base[threadIdx.x] = ((((long long)n * d.id + iz) * d.ih + iy) * d.iw + ix) * d.in_ld + d.in_coff;
+      } else {
+        zoff[threadIdx.x] = -1;
+        pix_zyx[threadIdx.x][0] = INT_MIN / 2;
+        pix_zyx[threadIdx.x][1] = pix_zyx[threadIdx.x][2] = 0;
+        pix_base[threadIdx.x] = 0;
       }
-      xoff[threadIdx.x] = xo;
-      zoff[threadIdx.x] = zo;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < WG_PT * TCO; i += 256) {
@@ -198,34 +220,39 @@ wgrad_kernel(ivf_conv_desc d, const T* __restrict__ x, const T* __restrict__ dz,
       const long long zo = zoff[pp];
       sdz[pp][cc] = (zo >= 0 && co0 + cc < d.cout) ? ldf(dz, zo + co0 + cc) : 0.f;
     }
-    for (int i = threadIdx.x; i < WG_PT * TCI; i += 256) {
-      const int pp = i / TCI, cc = i - pp * TCI;
-      const long long xo = xoff[pp];
-      sx[pp][cc] = (xo >= 0 && ci0 + cc < d.cin) ? ldf(x, xo + ci0 + cc) : 0.f;
+    for (int i = threadIdx.x; i < WG_PT * TCJ; i += 256) {
+      const int pp = i / TCJ, cc = i - pp * TCJ;
+      const int k = col_zyx[cc];
+      float v = 0.f;
+      if (k >= 0) {
+        const int iz = pix_zyx[pp][0] + (k & 255), iy = pix_zyx[pp][1] + ((k >> 8) & 255), ix = pix_zyx[pp][2] + (k >> 16);
+        if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+          v = ldf(x, pix_base[pp] + col_off[cc]);
+      }
+      sx[pp][cc] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int pp = 0; pp < WG_PT; ++pp) {
-      float a[4], bb[RCI];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sdz[pp][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < RCI; ++j) bb[j] = sx[pp][tx * RCI + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&sdz[pp][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sx[pp][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < RCI; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int co = co0 + ty * 4 + i;
     if (co >= d.cout) continue;
 #pragma unroll
-    for (int j = 0; j < RCI; ++j) {
-      const int ci = ci0 + tx * RCI + j;
-      if (ci < d.cin && acc[i][j] != 0.f) atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, acc[i][j]);
+    for (int j = 0; j < 4; ++j) {
+      const int col = j0 + tx * 4 + j;
+      if (col >= ncols || acc[i][j] == 0.f) continue;
+      const int tap = col / d.cin, ci = col - tap * d.cin;
+      atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, acc[i][j]);
     }
   }
 }
@@ -234,11 +261,12 @@ template <typename T>
 int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, cudaStream_t st) {
   const int taps = d->kd * d->kh * d->kw;
   const long long P = (long long)d->n * d->od * d->oh * d->ow;
+  IVF_REQUIRE(d->kd < 256 && d->kh < 256 && d->kw < 256, "ivf_conv3d_wgrad: kernel extent above 255");
+  IVF_REQUIRE((long long)d->n * d->id * d->ih * d->iw * d->in_ld < (1ll << 62), "ivf_conv3d_wgrad: tensor too large");
+  IVF_REQUIRE((long long)d->kd * d->ih * d->iw * d->in_ld < (1ll << 31), "ivf_conv3d_wgrad: window span above 2^31");
   IVF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->cout * d->cin * taps, st));
-  const bool narrow = d->cin <= 16;
-  const int tci = narrow ? 16 : 64;
-  const int co_tiles = (d->cout + 63) / 64, ci_tiles = (d->cin + tci - 1) / tci;
-  const long long bx = (long long)taps * co_tiles * ci_tiles;
+  const int co_tiles = (d->cout + 63) / 64, col_tiles = (taps * d->cin + 63) / 64;
+  const long long bx = (long long)co_tiles * col_tiles;
   IVF_REQUIRE(bx < (1ll << 31), "ivf_conv3d_wgrad: too many tiles");
   long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;  // ~8 blocks per SM in total
   const long long max_splits = (P + 255) / 256;                   // at least 256 pixels per block
@@ -249,10 +277,7 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   ppb = (ppb + WG_PT - 1) / WG_PT * WG_PT;
   splits = (P + ppb - 1) / ppb;
   const dim3 grid((unsigned)bx, (unsigned)splits);
-  if (narrow)
-    wgrad_kernel<T, 1><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, co_tiles, ci_tiles, ppb);
-  else
-    wgrad_kernel<T, 4><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, co_tiles, ci_tiles, ppb);
+  wgrad_kernel<T><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, col_tiles, ppb);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
