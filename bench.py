@@ -385,9 +385,8 @@ def clstm_throughput(dev, rank, world, mode, clips_n=8, steps=10, with_cpu=False
 
 def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
     """one TRAINING step of the I3D classifier (pt/train_i3d_smth.py:192-250: forward in training
-    mode, CrossEntropyLoss, backward to every parameter, SGD update) on synthetic 16x224x224 clips, fp32, through
-    I3DTrainer - forward convolutions and data gradients on the fp32 implicit-GEMM kernel, weight gradients on the
-    CUDA-core kernel of csrc/train.cu.  clips/s = clips per step / step time; algorithmic work per clip = forward +
+    mode, CrossEntropyLoss, backward to every parameter, SGD update) on synthetic 16x224x224 clips through I3DTrainer,
+    mixed precision (tcgen05 forward convolutions and data gradients, CUDA-core weight gradients) and fp32.  clips/s = clips per step / step time; algorithmic work per clip = forward +
     data gradient (all but the stem's) + weight gradient convolutions."""
     import torch.distributed as dist
     from interpreting_video_features_b200.train import I3DTrainer
@@ -396,35 +395,44 @@ def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     x = torch.stack([synthetic.uniform_clip(5000 + rank * clips_n + i) for i in range(clips_n)]).to(dev)
     target = (torch.arange(clips_n) * 7 % NCLS).to(dev)
-    tr = I3DTrainer(sd, clips_n, (T, H, W), device=dev, optimizer="sgd", lr=1e-3, momentum=0.9, weight_decay=1e-5,
-                    dropout_p=0.5)
-    n0 = _launches(dev)
-    tr.step(x, target)  # warm-up (lazy kernel loading) and the launch count of one step
-    launches = _launches(dev) - n0
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = tr.step(x, target)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / steps
-    if world > 1:
-        t = torch.tensor([sec], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t[0])
+    def timed(mode):
+        tr = I3DTrainer(sd, clips_n, (T, H, W), device=dev, optimizer="sgd", lr=1e-3, momentum=0.9, weight_decay=1e-5,
+                        dropout_p=0.5, mode=mode)
+        n0 = _launches(dev)
+        tr.step(x, target)  # warm-up (lazy kernel loading) and the launch count of one step
+        n_launch = _launches(dev) - n0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = tr.step(x, target)
+        e1.record()
+        torch.cuda.synchronize()
+        s = e0.elapsed_time(e1) * 1e-3 / steps
+        if world > 1:
+            t = torch.tensor([s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s = float(t[0])
+        return s, n_launch, float(last)
+
+    sec32, _, loss32 = timed("fp32")
+    sec, launches, loss = timed("bf16")
     fwd = i3d_oracle.conv_flops_per_clip(sd, (T, H, W))
     stem = 2.0 * 343 * 3 * 64 * (T // 2) * (H // 2) * (W // 2)
     gf_clip = (3.0 * fwd - stem) / 1e9
     val = world * clips_n / sec
     out = {"metric": "i3d_training_clips_per_sec", "unit": "clips/s", "value": val, "ms_per_step": sec * 1e3,
-           "clips_per_step_per_gpu": clips_n, "launches_per_step": int(launches), "dtype": "f32",
+           "clips_per_step_per_gpu": clips_n, "launches_per_step": int(launches), "dtype": "bf16",
            "loss_after_%d_steps" % (steps + 1): float(loss),
            "algorithmic_gflop_per_clip_step": gf_clip, "achieved_tflops": val / world * gf_clip / 1e3,
-           "note": "first-correct path: fp32 CUDA-core convolutions and weight gradients (no tensor-core kernel yet), "
-                   "so the bf16 tensor peak is not the roofline that applies; B200 fp32 FMA peak ~75 TFLOP/s",
+           "fp32_mode": {"value": world * clips_n / sec32, "ms_per_step": sec32 * 1e3,
+                         "loss_after_%d_steps" % (steps + 1): loss32,
+                         "achieved_tflops": clips_n / sec32 * gf_clip / 1e3},
+           "note": "mixed precision: forward convolutions and data gradients are the tcgen05 implicit GEMMs of the "
+                   "interpretation path, the weight gradient is still a CUDA-core fp32-accumulate kernel and is most "
+                   "of the step (tools/train_events.py); fp32_mode runs every convolution on CUDA cores",
            "workload": "f4: I3D smth (174 classes) training step, %d synthetic 16x224x224 clips, SGD(momentum 0.9, "
                        "weight decay 1e-5), dropout 0.5, BatchNorm with batch statistics" % clips_n}
     if with_cpu and rank == 0:

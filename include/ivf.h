@@ -377,20 +377,25 @@ int ivf_viz_triptych(ivf_handle* h, int clip_dtype, const void* clip, const floa
  *   save_mean / save_rstd (fp32 [c]) for the backward pass and, when running_mean is given, updates the running
  *   statistics in place as nn.BatchNorm3d does (running_var with the unbiased batch variance).  ws: 2*c doubles.
  * ivf_bn_train_bwd: g = dy * [y > 0] (y NULL: no ReLU); dgamma = sum g*xhat, dbeta = sum g,
- *   dz = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat)).  dz may alias dy.  ws: 2*c doubles.            */
+ *   dz = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat)).  dz may alias dy or z.  ws: 2*c doubles.  dy_dtype: the
+ *   element type of dy - IVF_F32 (gradients summed over the consumers of a tensor are kept in fp32 by the
+ *   mixed-precision step) or the activation type.                                                            */
 int ivf_bn_train_fwd(ivf_handle* h, int dtype, const void* z, int z_ld, int z_coff, long long m, int c,
                      const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                      float* running_var, float* save_mean, float* save_rstd, double* ws, void* y, int y_ld,
                      int y_coff, int relu, void* stream);
-int ivf_bn_train_bwd(ivf_handle* h, int dtype, const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld,
-                     int y_coff, const void* z, int z_ld, int z_coff, long long m, int c, const float* gamma,
+int ivf_bn_train_bwd(ivf_handle* h, int dtype, int dy_dtype, const void* dy, int dy_ld, int dy_coff, const void* y,
+                     int y_ld, int y_coff, const void* z, int z_ld, int z_coff, long long m, int c, const float* gamma,
                      const float* save_mean, const float* save_rstd, double* ws, void* dz, int dz_ld, int dz_coff,
                      float* dgamma, float* dbeta, void* stream);
 /* Weight gradient of the convolution d describes (autograd's convolution_backward, weight part, of
  * pt/models/I3D_doubled.py:109-113): x = the convolution's input (d->in_ld / in_coff), dz = the gradient w.r.t. its
  * output (d->out_ld / out_coff), dw = fp32 [cout][cin][kd][kh][kw] (the nn.Conv3d parameter's layout), overwritten.
- * d->pd/ph/pw are the front pads of the 'same' padding, as for ivf_conv3d; d->transposed must be 0.          */
-int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, void* stream);
+ * d->pd/ph/pw are the front pads of the 'same' padding, as for ivf_conv3d; d->transposed must be 0.  d->dtype is
+ * the element type of dz, x_dtype that of x (equal, or fp32 x with bf16 dz: the stem, whose tensor-core forward
+ * reads a space-to-depth copy while the weight gradient reads the clip itself).                              */
+int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, int x_dtype, const void* x, const void* dz, float* dw,
+                     void* stream);
 /* Classifier head in training mode (pt/models/I3D_doubled.py:360-371 + nn.CrossEntropyLoss,
  * pt/train_i3d_smth.py:124-127): pooled = mean over the pix positions of a clip's feature map (the average
  * pool's window must cover the map) * drop (fp32 [batch][c] dropout mask already scaled by 1/keep, NULL: none);

@@ -90,9 +90,9 @@ bn_apply_kernel(const T* __restrict__ z, int z_ld, int z_coff, long long m, int 
 }
 
 // backward pass 1: ws[c] += sum g, ws[C + c] += sum g * xhat, g = dy * [y > 0]
-template <typename T>
+template <typename T, typename TG>
 __global__ void __launch_bounds__(32 * BN_ROWS)
-bn_bwd_stats_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
+bn_bwd_stats_kernel(const TG* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
                     const T* __restrict__ z, int z_ld, int z_coff, long long m, int C,
                     const float* __restrict__ save_mean, const float* __restrict__ save_rstd, double* __restrict__ ws) {
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -111,9 +111,9 @@ bn_bwd_stats_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* _
 }
 
 // backward pass 2: dz = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat))
-template <typename T>
+template <typename T, typename TG>
 __global__ void __launch_bounds__(32 * BN_ROWS)
-bn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
+bn_bwd_apply_kernel(const TG* __restrict__ dy, int dy_ld, int dy_coff, const T* __restrict__ y, int y_ld, int y_coff,
                     const T* __restrict__ z, int z_ld, int z_coff, long long m, int C, const float* __restrict__ gamma,
                     const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                     const double* __restrict__ ws, T* __restrict__ dz, int dz_ld, int dz_coff,
@@ -154,9 +154,9 @@ dim3 bn_grid(const ivf_handle* h, long long m, int C) {
 // contiguous in the channels-last input.
 constexpr int WG_PT = 16;  // pixels per shared-memory stage
 
-template <typename T>
+template <typename TX, typename T>
 __global__ void __launch_bounds__(256)
-wgrad_kernel(ivf_conv_desc d, const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw,
+wgrad_kernel(ivf_conv_desc d, const TX* __restrict__ x, const T* __restrict__ dz, float* __restrict__ dw,
              int col_tiles, long long pix_per_block) {
   constexpr int TCO = 64, TCJ = 64;
   __shared__ float sdz[WG_PT][TCO + 4];
@@ -257,7 +257,7 @@ wgrad_kernel(ivf_conv_desc d, const T* __restrict__ x, const T* __restrict__ dz,
   }
 }
 
-template <typename T>
+template <typename TX, typename T>
 int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, cudaStream_t st) {
   const int taps = d->kd * d->kh * d->kw;
   const long long P = (long long)d->n * d->od * d->oh * d->ow;
@@ -277,7 +277,7 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   ppb = (ppb + WG_PT - 1) / WG_PT * WG_PT;
   splits = (P + ppb - 1) / ppb;
   const dim3 grid((unsigned)bx, (unsigned)splits);
-  wgrad_kernel<T><<<grid, 256, 0, st>>>(*d, (const T*)x, (const T*)dz, dw, col_tiles, ppb);
+  wgrad_kernel<TX, T><<<grid, 256, 0, st>>>(*d, (const TX*)x, (const T*)dz, dw, col_tiles, ppb);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }
@@ -446,44 +446,49 @@ extern "C" int ivf_bn_train_fwd(ivf_handle* h, int dtype, const void* z, int z_l
   return IVF_OK;
 }
 
-extern "C" int ivf_bn_train_bwd(ivf_handle* h, int dtype, const void* dy, int dy_ld, int dy_coff, const void* y,
-                                int y_ld, int y_coff, const void* z, int z_ld, int z_coff, long long m, int c,
-                                const float* gamma, const float* save_mean, const float* save_rstd, double* ws,
+extern "C" int ivf_bn_train_bwd(ivf_handle* h, int dtype, int dy_dtype, const void* dy, int dy_ld, int dy_coff,
+                                const void* y, int y_ld, int y_coff, const void* z, int z_ld, int z_coff, long long m,
+                                int c, const float* gamma, const float* save_mean, const float* save_rstd, double* ws,
                                 void* dz, int dz_ld, int dz_coff, float* dgamma, float* dbeta, void* stream) {
   IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && dy && z && gamma && save_mean && save_rstd && ws && dz && dgamma && dbeta && m > 0 && c > 0,
               "ivf_bn_train_bwd: null argument or empty tensor");
-  IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_bn_train_bwd: unknown dtype %d", dtype);
+  IVF_REQUIRE((dtype == IVF_F32 || dtype == IVF_BF16) && (dy_dtype == IVF_F32 || dy_dtype == dtype),
+              "ivf_bn_train_bwd: dtype %d / dy_dtype %d (dy is fp32 or of the activation type)", dtype, dy_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   IVF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)c, st));
   const dim3 grid = bn_grid(h, m, c), block(32, BN_ROWS);
-#define IVF_BN_BWD(T)                                                                                              \
+#define IVF_BN_BWD(T, TG)                                                                                          \
   do {                                                                                                             \
-    bn_bwd_stats_kernel<T><<<grid, block, 0, st>>>((const T*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,       \
-                                                   (const T*)z, z_ld, z_coff, m, c, save_mean, save_rstd, ws);     \
+    bn_bwd_stats_kernel<T, TG><<<grid, block, 0, st>>>((const TG*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,  \
+                                                       (const T*)z, z_ld, z_coff, m, c, save_mean, save_rstd, ws); \
     IVF_LAUNCHED(h);                                                                                               \
-    bn_bwd_apply_kernel<T><<<grid, block, 0, st>>>((const T*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,       \
-                                                   (const T*)z, z_ld, z_coff, m, c, gamma, save_mean, save_rstd,   \
-                                                   ws, (T*)dz, dz_ld, dz_coff, dgamma, dbeta);                     \
+    bn_bwd_apply_kernel<T, TG><<<grid, block, 0, st>>>((const TG*)dy, dy_ld, dy_coff, (const T*)y, y_ld, y_coff,  \
+                                                       (const T*)z, z_ld, z_coff, m, c, gamma, save_mean,          \
+                                                       save_rstd, ws, (T*)dz, dz_ld, dz_coff, dgamma, dbeta);      \
     IVF_LAUNCHED(h);                                                                                               \
   } while (0)
-  if (dtype == IVF_F32) IVF_BN_BWD(float);
-  else IVF_BN_BWD(__nv_bfloat16);
+  if (dtype == IVF_F32) IVF_BN_BWD(float, float);
+  else if (dy_dtype == IVF_F32) IVF_BN_BWD(__nv_bfloat16, float);
+  else IVF_BN_BWD(__nv_bfloat16, __nv_bfloat16);
 #undef IVF_BN_BWD
   return IVF_OK;
 }
 
-extern "C" int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw,
-                                void* stream) {
+extern "C" int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, int x_dtype, const void* x, const void* dz,
+                                float* dw, void* stream) {
   IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && d && x && dz && dw, "ivf_conv3d_wgrad: null argument");
   IVF_REQUIRE(d->n > 0 && d->id > 0 && d->ih > 0 && d->iw > 0 && d->od > 0 && d->oh > 0 && d->ow > 0 && d->cin > 0 &&
                   d->cout > 0 && d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0 &&
                   !d->transposed && d->in_ld >= d->in_coff + d->cin && d->out_ld >= d->out_coff + d->cout,
               "ivf_conv3d_wgrad: bad descriptor");
-  if (d->dtype == IVF_F32) return wgrad_launch<float>(h, d, x, dz, dw, (cudaStream_t)stream);
-  if (d->dtype == IVF_BF16) return wgrad_launch<__nv_bfloat16>(h, d, x, dz, dw, (cudaStream_t)stream);
-  IVF_FAIL(IVF_EINVAL, "ivf_conv3d_wgrad: unknown dtype %d", d->dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == IVF_F32 && x_dtype == IVF_F32) return wgrad_launch<float, float>(h, d, x, dz, dw, st);
+  if (d->dtype == IVF_BF16 && x_dtype == IVF_BF16) return wgrad_launch<__nv_bfloat16, __nv_bfloat16>(h, d, x, dz, dw, st);
+  if (d->dtype == IVF_BF16 && x_dtype == IVF_F32) return wgrad_launch<float, __nv_bfloat16>(h, d, x, dz, dw, st);
+  IVF_FAIL(IVF_EINVAL, "ivf_conv3d_wgrad: dtype %d (dz) / %d (x): fp32/fp32, bf16/bf16 or bf16 dz with fp32 x", d->dtype,
+           x_dtype);
 }
 
 extern "C" int ivf_head_train_fwd(ivf_handle* h, int dtype, const void* feat, int ld, int coff, int batch, int pix,

@@ -431,7 +431,8 @@ def bn_train_fwd(z, gamma, beta, eps, momentum, running_mean, running_var, save_
 
 def bn_train_bwd(dy, y, z, gamma, save_mean, save_rstd, ws, dz, dgamma, dbeta):
     """dz, dgamma, dbeta of relu(BatchNorm_train(z)) given dy (Act) and the forward's y (Act, None: no ReLU)."""
-    check(_lib.load().ivf_bn_train_bwd(_lib.handle(z.buf.device), _lib.dtype_code(z.buf), ptr(dy.buf), dy.ld, dy.coff,
+    check(_lib.load().ivf_bn_train_bwd(_lib.handle(z.buf.device), _lib.dtype_code(z.buf), _lib.dtype_code(dy.buf),
+                                       ptr(dy.buf), dy.ld, dy.coff,
                                        ptr(y.buf if y is not None else None), y.ld if y is not None else 0,
                                        y.coff if y is not None else 0, ptr(z.buf), z.ld, z.coff, z.pixels, z.c,
                                        ptr(gamma), ptr(save_mean), ptr(save_rstd), ptr(ws), ptr(dz.buf), dz.ld, dz.coff,
@@ -445,7 +446,9 @@ def conv3d_wgrad(x, dz, dw, kernel, stride, pad_front):
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == dz.c * x.c * kernel[0] * kernel[1] * kernel[2]
     d = conv_desc(x, dz, kernel, stride, pad_front)
     d.flags = 0
-    check(_lib.load().ivf_conv3d_wgrad(_lib.handle(x.buf.device), C.byref(d), ptr(x.buf), ptr(dz.buf), ptr(dw),
+    d.dtype = _lib.dtype_code(dz.buf)
+    check(_lib.load().ivf_conv3d_wgrad(_lib.handle(x.buf.device), C.byref(d), _lib.dtype_code(x.buf), ptr(x.buf),
+                                       ptr(dz.buf), ptr(dw),
                                        _lib.stream_ptr(x.buf.device)), "ivf_conv3d_wgrad")
     return dw
 

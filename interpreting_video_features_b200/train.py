@@ -9,15 +9,18 @@ optimizer.step() - as a fixed program of libivf launches over channels-last buff
             ivf_conv3d_wgrad (dW) -> ivf_conv3d data gradient, accumulated over the consumers of a tensor;
   update    ivf_optim_step per parameter (torch.optim.SGD / Adam semantics), weights re-packed for the next step.
 
-fp32 throughout (the reference trains in fp32): convolutions and data gradients on the fp32 implicit-GEMM kernel, the
-weight gradient on a CUDA-core kernel.  Parameters are fp32 device tensors updated IN PLACE: built from a drop-in
-model (`I3DTrainer.from_model`) they are the model's own parameter storage, so the model sees every step.
-torch is used for allocation only.
+Two modes.  "fp32" (the reference trains in fp32): every tensor fp32, convolutions and data gradients on the fp32
+implicit-GEMM kernel.  "bf16" (mixed precision): activations and convolution operands bf16 - forward convolutions and
+data gradients are the tcgen05 implicit GEMMs of the interpretation path (the stem reads its space-to-depth copy of
+the clips) - while parameters, BatchNorm statistics, every gradient that is summed over several consumers, the weight
+gradients and the optimizer state stay fp32.  The weight gradient is a CUDA-core kernel in both modes.
+Parameters are fp32 device tensors updated IN PLACE: built from a drop-in model (`I3DTrainer.from_model`) they are the
+model's own parameter storage, so the model sees every step.  torch is used for allocation only.
 """
 import torch
 
 from . import _lib, ops
-from ._lib import PFMT_NDHWC_F32
+from ._lib import PFMT_NDHWC_F32, PFMT_S2D_BF16
 from .engine import ENDPOINTS, POOLS, pack, strip_module_prefix
 from .ops import Act, same_pad
 
@@ -29,11 +32,13 @@ def _is_param(key):
 
 
 class _TrainUnit:
-    """One Unit3D in training mode: parameters (views of the trainer's fp32 tensors), packed operands, buffers."""
+    """One Unit3D in training mode: parameters (views of the trainer's fp32 tensors), packed operands, buffers.
+    x_conv: what the forward convolution reads (bf16 stem: the space-to-depth copy), x: the unit's input as the
+    weight gradient reads it."""
 
-    def __init__(self, tr, prefix, stride, x, y):
+    def __init__(self, tr, prefix, stride, x, y, x_conv=None):
         P, dev = tr.params, tr.device
-        self.prefix, self.stride, self.x, self.y = prefix, tuple(stride), x, y
+        self.mode, self.prefix, self.stride, self.x, self.y = tr.mode, prefix, tuple(stride), x, y
         self.w = P[prefix + ".conv3d.weight"]
         self.gamma, self.beta = P[prefix + ".bn.weight"], P[prefix + ".bn.bias"]
         self.rmean, self.rvar = tr.buffers[prefix + ".bn.running_mean"], tr.buffers[prefix + ".bn.running_var"]
@@ -41,27 +46,48 @@ class _TrainUnit:
         self.kernel = tuple(self.w.shape[2:])
         self.pf = tuple(same_pad(sz, k, s)[0] for sz, k, s in zip((x.d, x.h, x.w), self.kernel, self.stride))
         assert y.c == self.cout and x.c == self.cin
-        self.z = Act.empty(y.n, y.d, y.h, y.w, self.cout, torch.float32, dev)  # raw convolution output, then dz
+        self.s2d = x_conv is not None  # bf16 stem (pt/models/I3D_doubled.py:233-235): stride 2 as a stride-1 4x4x4
+        if self.s2d:                   # convolution over the 2x2x2 space-to-depth record, as in engine.Unit
+            assert self.stride == (2, 2, 2) and tr.mode == "bf16"
+            win = (self.kernel[0] + 1) // 2
+            self.conv_x = Act(x_conv.buf, x_conv.n, x_conv.d, x_conv.h, x_conv.w, x_conv.ld, 0, 8 * self.cin)
+            self.conv_kernel, self.conv_stride, self.conv_pf, self.f = (win,) * 3, (1, 1, 1), (1, 1, 1), (2, 2, 2)
+        else:
+            self.conv_x, self.conv_kernel, self.conv_stride, self.conv_pf, self.f = x, self.kernel, self.stride, self.pf, (1, 1, 1)
+        # data gradient: fp32 = transposed gather with the forward pads; bf16 = stride-1 convolution with flipped taps
+        self.dgrad_pf = self.pf if tr.mode == "fp32" else tuple(k - 1 - p for k, p in zip(self.kernel, self.pf))
+        self.z = Act.empty(y.n, y.d, y.h, y.w, self.cout, tr.adt, dev)  # raw convolution output, then dz
         self.save_mean = torch.empty(self.cout, dtype=torch.float32, device=dev)
         self.save_rstd = torch.empty(self.cout, dtype=torch.float32, device=dev)
         self.ws = torch.empty(2 * self.cout, dtype=torch.float64, device=dev)
         self.repack()
 
     def repack(self):
-        self.w_fwd = pack([self.w], "fp32")
-        self.w_dgrad = pack([self.w], "fp32", dgrad=True)
+        self.w_fwd = pack([self.w], self.mode, s2d=self.f)
+        self.w_dgrad = None if self.s2d else pack([self.w], self.mode, dgrad=True)
+
+    def dgrad(self, dz, gx, acc):
+        if self.mode == "fp32":
+            ops.conv3d(dz, self.w_dgrad, gx, self.kernel, self.stride, self.dgrad_pf, acc_in=gx if acc else None,
+                       transposed=1)
+        else:
+            assert self.stride == (1, 1, 1)
+            ops.conv3d(dz, self.w_dgrad, gx, self.kernel, (1, 1, 1), self.dgrad_pf, acc_in=gx if acc else None)
 
 
 class I3DTrainer:
     def __init__(self, state_dict, batch, clip, avg_pool=(2, 7, 7), device=None, optimizer="sgd", lr=0.01,
                  momentum=0.9, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, dropout_p=0.0, seed=0, in_channels=3,
-                 share_storage=False):
+                 share_storage=False, mode="fp32"):
         """state_dict: the reference-keyed parameters and BatchNorm buffers (pt/models/I3D_doubled.py).  dropout_p is
         what the reference hands to nn.Dropout (its `dropout_keep_prob` argument, pt/models/I3D_doubled.py:319).
         share_storage: fp32 contiguous tensors of state_dict that already live on the device are updated in place
         instead of copied (from_model)."""
         if optimizer not in ("sgd", "adam"):
             raise _lib.IvfError("optimizer must be 'sgd' or 'adam' (pt/train_i3d_smth.py:131-138)")
+        if mode not in ("fp32", "bf16"):
+            raise _lib.IvfError("mode must be 'fp32' or 'bf16'")
+        self.mode, self.adt = mode, (torch.float32 if mode == "fp32" else torch.bfloat16)
         self.device = dev = torch.device(device if device is not None else "cuda")
         _lib.handle(dev)  # fails loudly without the extension / a GPU
         sd = strip_module_prefix(state_dict)
@@ -88,19 +114,24 @@ class I3DTrainer:
         self.x = ops.zeros((B, in_channels, self.T, self.H, self.W), torch.float32, dev)
         self.zero_mask = ops.zeros((B, self.T), torch.float32, dev)
         self.xin = Act.empty(B, self.T, self.H, self.W, in_channels, torch.float32, dev)
+        self.xin_s2d = None
+        if mode == "bf16":  # the stem's tensor-core operand (the weight gradient reads xin itself)
+            if self.T % 2 or self.H % 2 or self.W % 2 or in_channels > 4:
+                raise _lib.IvfError("bf16 mode needs even T/H/W and at most 4 input channels; use mode='fp32'")
+            self.xin_s2d = Act.empty(B, self.T // 2, self.H // 2, self.W // 2, 32, torch.bfloat16, dev, zero=True)
         self.fwd, tape = [], []  # launches of the forward pass; records the backward pass is derived from
         self.units = []
 
         def new_act(n, d, h, w, c):
-            return Act.empty(n, d, h, w, c, torch.float32, dev)
+            return Act.empty(n, d, h, w, c, self.adt, dev)
 
         def out_dims(x, k, s):
             return tuple(same_pad(sz, kk, ss)[2] for sz, kk, ss in zip((x.d, x.h, x.w), k, s))
 
-        def add_unit(prefix, x, y, stride=(1, 1, 1)):
-            u = _TrainUnit(self, prefix, stride, x, y)
+        def add_unit(prefix, x, y, stride=(1, 1, 1), x_conv=None):
+            u = _TrainUnit(self, prefix, stride, x, y, x_conv)
             self.units.append(u)
-            self.fwd.append(lambda u=u: ops.conv3d(u.x, u.w_fwd, u.z, u.kernel, u.stride, u.pf))
+            self.fwd.append(lambda u=u: ops.conv3d(u.conv_x, u.w_fwd, u.z, u.conv_kernel, u.conv_stride, u.conv_pf))
             self.fwd.append(lambda u=u: ops.bn_train_fwd(u.z, u.gamma, u.beta, BN_EPS, BN_MOMENTUM, u.rmean, u.rvar,
                                                          u.save_mean, u.save_rstd, u.ws, u.y, relu=True))
             tape.append(("unit", u))
@@ -118,7 +149,7 @@ class I3DTrainer:
                 w = self.params[name + ".conv3d.weight"]
                 od, oh, ow = out_dims(x, tuple(w.shape[2:]), stride)
                 y = new_act(B, od, oh, ow, w.shape[0])
-                add_unit(name, x, y, stride)
+                add_unit(name, x, y, stride, x_conv=self.xin_s2d if name == "Conv3d_1a_7x7" else None)
             elif name.startswith("MaxPool"):
                 k, s = POOLS[name]
                 y = new_act(B, *out_dims(x, k, s), x.c)
@@ -161,8 +192,8 @@ class I3DTrainer:
 
         def grad(a):  # gradient buffer of a whole forward buffer, and the slice matching `a`
             g = grad_of.get(id(a.buf))
-            if g is None:
-                g = grad_of[id(a.buf)] = torch.empty_like(a.buf)
+            if g is None:  # fp32 in both modes: gradients are summed over consumers and feed the BatchNorm sums
+                g = grad_of[id(a.buf)] = torch.empty(a.buf.shape, dtype=torch.float32, device=dev)
             return Act(g, a.n, a.d, a.h, a.w, a.ld, a.coff, a.c)
 
         def contribute(a):  # -> (gradient Act, accumulate?)
@@ -170,6 +201,8 @@ class I3DTrainer:
             written.add(id(a.buf))
             return grad(a), acc
 
+        self.grad_act = grad  # forward Act -> its fp32 gradient Act (the tests read the backward pass link by link)
+        self.tape = tape
         gfeat = grad(feat)
         written.add(id(feat.buf))
         self.bwd.append(lambda: ops.head_train_bwd(self.dlogits, self.pooled, self.drop, self.w_logits,
@@ -187,8 +220,7 @@ class I3DTrainer:
                                                                     u.kernel, u.stride, u.pf))
                 if u.x is not self.xin:  # the clip needs no gradient
                     gx, acc = contribute(u.x)
-                    self.bwd.append(lambda u=u, dz=dz, gx=gx, acc=acc: ops.conv3d(
-                        dz, u.w_dgrad, gx, u.kernel, u.stride, u.pf, acc_in=gx if acc else None, transposed=1))
+                    self.bwd.append(lambda u=u, dz=dz, gx=gx, acc=acc: u.dgrad(dz, gx, acc))
             else:
                 _, px, py, am, k, s, pads = rec
                 gy = grad(py)
@@ -215,16 +247,21 @@ class I3DTrainer:
         return out
 
     @_lib.on_device
-    def forward_backward(self, x, target, drop=None):
+    def forward_backward(self, x, target, drop=None, after_forward=None):
         """One forward and backward pass in training mode; returns the loss as a device tensor [1] (no sync).
         x: [B,3,T,H,W] fp32 (host or device), target: class indices [B]; drop: optional scaled dropout mask
-        [B, 1024] to use instead of drawing one."""
+        [B, 1024] to use instead of drawing one; after_forward: optional callable run between the passes (the tests
+        snapshot the raw convolution outputs there: the backward pass overwrites them with dz)."""
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (tuple(x.shape),)
         self.x.copy_(x, non_blocking=True)
         self.target.copy_(ops.as_int32_targets(target, self.device), non_blocking=True)
         ops.perturb_fwd(self.x, self.zero_mask, "freeze", PFMT_NDHWC_F32, self.xin.buf)  # layout change only (mask 0)
+        if self.xin_s2d is not None:
+            ops.perturb_fwd(self.x, self.zero_mask, "freeze", PFMT_S2D_BF16, self.xin_s2d.buf)
         for op in self.fwd:
             op()
+        if after_forward is not None:
+            after_forward()
         d = None
         if drop is not None:
             d = drop.to(device=self.device, dtype=torch.float32).contiguous()

@@ -9,7 +9,7 @@ Pinned against the unmodified reference by oracle/pin_train_step.py, which also 
 import torch
 import torch.nn.functional as F
 
-from .i3d_oracle import ENDPOINTS, POOLS, _same_pad
+from .i3d_oracle import ENDPOINTS, POOLS, _RoundGrad, _q, _same_pad
 
 BN_EPS, BN_MOMENTUM = 1e-3, 0.01
 
@@ -25,28 +25,34 @@ def is_param(key):
     return key.endswith((".conv3d.weight", ".conv3d.bias", ".bn.weight", ".bn.bias"))
 
 
-def _unit(p, buf, prefix, x, stride=(1, 1, 1), probe=None):
+def _unit(p, buf, prefix, x, stride=(1, 1, 1), probe=None, quant=False):
+    """quant: the rounding points of the mixed-precision step (train.py, mode 'bf16') - convolution weights, the
+    stored convolution output z and the stored BatchNorm/ReLU output y rounded to bf16, and in the backward pass the
+    stored dz (the gradient both the weight gradient and the data gradient read) rounded to bf16; BatchNorm
+    statistics are taken from the rounded z, gradients summed over consumers stay fp32."""
     w = p[prefix + ".conv3d.weight"]
-    x = F.conv3d(_same_pad(x, w.shape[2:], stride), w, None, stride=stride)
+    x = F.conv3d(_same_pad(x, w.shape[2:], stride), _q(w) if quant else w, None, stride=stride)
+    if quant:
+        x = _q(_RoundGrad.apply(x))
     if probe is not None:
         probe[prefix + ":z"] = x
     x = F.batch_norm(x, buf[prefix + ".bn.running_mean"], buf[prefix + ".bn.running_var"], p[prefix + ".bn.weight"],
                      p[prefix + ".bn.bias"], training=True, momentum=BN_MOMENTUM, eps=BN_EPS)
-    return F.relu(x)
+    return _q(F.relu(x)) if quant else F.relu(x)
 
 
-def _inception(p, buf, name, x, probe=None):
-    b0 = _unit(p, buf, name + ".b0", x, probe=probe)
-    b1 = _unit(p, buf, name + ".b1b", _unit(p, buf, name + ".b1a", x, probe=probe), probe=probe)
-    b2 = _unit(p, buf, name + ".b2b", _unit(p, buf, name + ".b2a", x, probe=probe), probe=probe)
+def _inception(p, buf, name, x, probe=None, quant=False):
+    b0 = _unit(p, buf, name + ".b0", x, probe=probe, quant=quant)
+    b1 = _unit(p, buf, name + ".b1b", _unit(p, buf, name + ".b1a", x, probe=probe, quant=quant), probe=probe, quant=quant)
+    b2 = _unit(p, buf, name + ".b2b", _unit(p, buf, name + ".b2a", x, probe=probe, quant=quant), probe=probe, quant=quant)
     t3 = F.max_pool3d(_same_pad(x, (3, 3, 3), (1, 1, 1)), (3, 3, 3), (1, 1, 1))
     if probe is not None:
         probe[name + ".b3a:y"] = t3
-    b3 = _unit(p, buf, name + ".b3b", t3, probe=probe)
+    b3 = _unit(p, buf, name + ".b3b", t3, probe=probe, quant=quant)
     return torch.cat([b0, b1, b2, b3], dim=1)
 
 
-def loss_and_grads(sd, x, target, avg_pool=(2, 7, 7), drop=None, dtype=torch.float32, probe=None):
+def loss_and_grads(sd, x, target, avg_pool=(2, 7, 7), drop=None, dtype=torch.float32, probe=None, quant=False):
     """One forward/backward in training mode.  drop: optional [B, 1024] dropout mask already scaled by 1/keep
     (the reference draws it from torch's RNG; parity tests pass it in or disable dropout).
     Returns loss (float), logits [B, classes], grads {parameter key: tensor}, buffers {running stat key: tensor}
@@ -56,16 +62,18 @@ def loss_and_grads(sd, x, target, avg_pool=(2, 7, 7), drop=None, dtype=torch.flo
     p = {k: v.detach().clone().to(dtype).requires_grad_() for k, v in sd.items() if is_param(k)}
     buf = {k: v.detach().clone().to(dtype) for k, v in sd.items() if ".bn.running_" in k}
     h = x.to(dtype)
+    if quant:
+        h = _q(h)  # the stem's tensor-core operand is the bf16 copy of the clip
     for name in ENDPOINTS:
         if name == "Conv3d_1a_7x7":
-            h = _unit(p, buf, name, h, (2, 2, 2), probe=probe)
+            h = _unit(p, buf, name, h, (2, 2, 2), probe=probe, quant=quant)
         elif name.startswith("Conv3d"):
-            h = _unit(p, buf, name, h, probe=probe)
+            h = _unit(p, buf, name, h, probe=probe, quant=quant)
         elif name.startswith("MaxPool"):
             k, s = POOLS[name]
             h = F.max_pool3d(_same_pad(h, k, s), k, s)
         else:
-            h = _inception(p, buf, name, h, probe=probe)
+            h = _inception(p, buf, name, h, probe=probe, quant=quant)
         if probe is not None:
             probe[name + ":y"] = h
     pooled = F.avg_pool3d(h, avg_pool, stride=(1, 1, 1))

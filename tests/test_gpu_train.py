@@ -312,3 +312,102 @@ def test_trainer_updates_the_dropin_model_in_place(dev):
         p_model = model.eval()(x.to(dev))
         p_or = i3d_oracle.forward(new_sd, x, SMALL["avg_pool"])
     assert rel_err(p_model.cpu(), p_or) < 1e-3
+
+
+def _ncdhw(act):
+    return act.tensor().permute(0, 4, 1, 2, 3).float().cpu()
+
+
+def _conv_same(x, w, stride):
+    from oracle.i3d_oracle import _same_pad
+    return F.conv3d(_same_pad(x, w.shape[2:], stride), w, stride=stride)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_train_step_link_by_link(dev, mode):
+    """Every launch of one training step against torch evaluated on the step's OWN stored operands (teacher
+    forcing).  With bf16 rounding points the step is chaotic end to end - the oracle's matched-rounding restatement
+    evaluated in fp32 and in fp64 gives gradients that differ by 0.76 (median, relative) on this geometry, a flipped
+    rounding doubles per layer - so the mixed-precision mode cannot be held to any end-to-end gradient; what CAN be
+    held exactly is each link: convolution, BatchNorm forward and backward, weight gradient, data gradient (one and
+    several consumers, incl. the branch pool's routing).  Tolerances: bf16 storage rounds at 2^-9 = 2e-3."""
+    from interpreting_video_features_b200.train import I3DTrainer
+    from oracle import synthetic
+    from oracle.i3d_oracle import _same_pad
+    bf = mode == "bf16"
+    tol_store = 6e-3 if bf else 2e-5   # a stored tensor against its fp32 recomputation
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = synthetic.clips(2, t=SMALL['clip'][0], h=SMALL['clip'][1], w=SMALL['clip'][2])
+    target = torch.tensor([5, 77])
+    tr = I3DTrainer(sd, 2, SMALL["clip"], avg_pool=SMALL["avg_pool"], device=dev, optimizer="sgd", mode=mode)
+    zs = {}
+    tr.forward_backward(x, target, after_forward=lambda: zs.update({u.prefix: _ncdhw(u.z) for u in tr.units}))
+    torch.cuda.synchronize()
+    q = (lambda t: t.bfloat16().float()) if bf else (lambda t: t)
+    units = {u.prefix: u for u in tr.units}
+    checked = 0
+    for name, u in units.items():
+        w = q(sd[name + ".conv3d.weight"].float())
+        xin = q(x) if name == "Conv3d_1a_7x7" else _ncdhw(u.x)
+        # forward convolution and BatchNorm(batch statistics) + ReLU
+        z_ref = _conv_same(xin, w, u.stride)
+        assert rel_err(zs[name], z_ref) < tol_store, (name, "conv", rel_err(zs[name], z_ref))
+        zz = zs[name].clone().requires_grad_()
+        g, b = sd[name + ".bn.weight"].float().clone().requires_grad_(), sd[name + ".bn.bias"].float().clone().requires_grad_()
+        y_ref = F.relu(F.batch_norm(zz, None, None, g, b, training=True, eps=1e-3))
+        y = _ncdhw(u.y)
+        assert rel_err(y, y_ref.detach()) < tol_store, (name, "bn", rel_err(y, y_ref.detach()))
+        # BatchNorm backward from the step's own gradient of y; the ReLU mask is the stored y's
+        gy = _ncdhw(tr.grad_act(u.y))
+        y_m = F.batch_norm(zz, None, None, g, b, training=True, eps=1e-3) * (y > 0).float()
+        dz_ref, dg_ref, db_ref = torch.autograd.grad(y_m, [zz, g, b], gy)
+        dz = _ncdhw(u.z)
+        assert rel_err(dz, dz_ref) < tol_store, (name, "bn'", rel_err(dz, dz_ref))
+        assert rel_err(tr.grads[name + ".bn.weight"].cpu(), dg_ref) < 1e-3, (name, "dgamma")
+        assert rel_err(tr.grads[name + ".bn.bias"].cpu(), db_ref) < 1e-3, (name, "dbeta")
+        # weight gradient from the stored dz and the unit's input (the stem reads the fp32 clip)
+        xw = x.float() if name == "Conv3d_1a_7x7" else xin
+        ww = w.clone().requires_grad_()
+        (dw_ref,) = torch.autograd.grad(_conv_same(xw, ww, u.stride), ww, dz)
+        assert rel_err(tr.grads[name + ".conv3d.weight"].cpu(), dw_ref) < 1e-4, (name, "wgrad")
+        checked += 1
+    assert checked == 57
+    # data gradients.  One consumer: t1 = b1a's output feeds b1b only.
+    for mod in ("Mixed_3b", "Mixed_4d", "Mixed_5c"):
+        for a, b_ in (("b1a", "b1b"), ("b2a", "b2b")):
+            ub = units["%s.%s" % (mod, b_)]
+            w = q(sd["%s.%s.conv3d.weight" % (mod, b_)].float())
+            t = _ncdhw(ub.x).requires_grad_()
+            (g_ref,) = torch.autograd.grad(_conv_same(t, w, (1, 1, 1)), t, _ncdhw(ub.z))
+            got = _ncdhw(tr.grad_act(units["%s.%s" % (mod, a)].y))
+            assert rel_err(got, g_ref) < 1e-4, (mod, b_, "dgrad", rel_err(got, g_ref))
+        # Four consumers: the module's input gets b0' + b1a' + b2a' + pool'(b3b'), the pool routed by ITS arg-max
+        xm = _ncdhw(units[mod + ".b0"].x).requires_grad_()
+        total = 0
+        for br in ("b0", "b1a", "b2a"):
+            w = q(sd["%s.%s.conv3d.weight" % (mod, br)].float())
+            total = total + (_conv_same(xm, w, (1, 1, 1)) * _ncdhw(units["%s.%s" % (mod, br)].z)).sum()
+        w3 = q(sd[mod + ".b3b.conv3d.weight"].float())
+        t3 = F.max_pool3d(_same_pad(xm, (3, 3, 3), (1, 1, 1)), (3, 3, 3), (1, 1, 1))
+        total = total + (_conv_same(t3, w3, (1, 1, 1)) * _ncdhw(units[mod + ".b3b"].z)).sum()
+        (gx_ref,) = torch.autograd.grad(total, xm)
+        got = _ncdhw(tr.grad_act(units[mod + ".b0"].x))
+        assert rel_err(got, gx_ref) < 1e-4, (mod, "input gradient", rel_err(got, gx_ref))
+
+
+def test_mixed_precision_training_tracks_fp32(dev):
+    """Five SGD steps on eight 16x224x224 clips: the mixed-precision step (tcgen05 forward convolutions and data
+    gradients) lowers the loss like the fp32 step does - measured 5.36 -> 5.07 against 5.34 -> 5.09."""
+    from interpreting_video_features_b200.train import I3DTrainer
+    from oracle import synthetic
+    sd, _ = quiet(i3d_state_dict, 174)
+    x = torch.stack([synthetic.uniform_clip(5000 + i) for i in range(8)]).to(dev)
+    target = torch.arange(8) % 174
+    hist = {}
+    for mode in ("fp32", "bf16"):
+        tr = I3DTrainer(sd, 8, (16, 224, 224), device=dev, optimizer="sgd", lr=1e-3, momentum=0.9, mode=mode)
+        hist[mode] = [float(tr.step(x, target)) for _ in range(5)]
+        del tr
+    assert hist["fp32"][-1] < hist["fp32"][0] - 0.15 and hist["bf16"][-1] < hist["bf16"][0] - 0.15, hist
+    assert abs(hist["bf16"][0] - hist["fp32"][0]) < 0.05 * hist["fp32"][0], hist
+    assert abs(hist["bf16"][-1] - hist["fp32"][-1]) < 0.05 * hist["fp32"][-1], hist

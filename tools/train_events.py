@@ -8,9 +8,10 @@ from interpreting_video_features_b200.train import I3DTrainer
 from oracle import synthetic
 dev = torch.device("cuda:0"); torch.cuda.set_device(dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 sd = {k: v.detach().clone() for k, v in bench.state_dict().state_dict().items()}
 x = torch.stack([synthetic.uniform_clip(5000 + i) for i in range(n)]).to(dev)
-tr = I3DTrainer(sd, n, (16, 224, 224), device=dev, optimizer="sgd", lr=1e-3, dropout_p=0.5)
+tr = I3DTrainer(sd, n, (16, 224, 224), device=dev, optimizer="sgd", lr=1e-3, dropout_p=0.5, mode=mode)
 tr.step(x, torch.arange(n) % 174)
 torch.cuda.synchronize()
 events = []
@@ -24,7 +25,7 @@ for nm in names:
         e0.record(); r = _f(*a, **k); e1.record()
         tag = _n
         if _n == "conv3d":
-            tag = "conv3d dgrad" if k.get("transposed") else "conv3d fwd"
+            tag = "conv3d dgrad" if (k.get("transposed") or a[2].buf.dtype == torch.float32 and mode == "bf16") else "conv3d fwd"
         events.append((tag, e0, e1))
         return r
     setattr(ops, nm, wrap)
@@ -36,6 +37,6 @@ agg = collections.OrderedDict()
 for tag, e0, e1 in events:
     a = agg.setdefault(tag, [0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1)
 tot = sum(v[1] for v in agg.values())
-print("one training step, %d clips: %.1f ms in %d timed launches (weight re-packing not timed)" % (n, tot, len(events)))
+print("one training step (%s), %d clips: %.1f ms in %d timed launches (weight re-packing not timed)" % (mode, n, tot, len(events)))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("  %-16s %4d launches %8.2f ms %5.1f%%" % (k, v[0], v[1], 100 * v[1] / tot))
