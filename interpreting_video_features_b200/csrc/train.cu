@@ -9,6 +9,9 @@
 // These are first-correct CUDA-core kernels (the weight gradient is a tiled fp32 outer-product GEMM with atomics
 // across pixel splits, not a tcgen05 kernel): parity against torch autograd first, see DESIGN.md "Training step".
 #include <limits.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -257,6 +260,164 @@ wgrad_kernel(ivf_conv_desc d, const TX* __restrict__ x, const T* __restrict__ dz
   }
 }
 
+// The same GEMM on the tensor cores for bf16 gradients (mixed-precision step): operands staged as bf16 in shared
+// memory ([pixel][co] and [pixel][column], the layouts they have in global memory), fragments fetched with
+// ldmatrix.trans (both operands are "K-rows" here: the reduction index, the pixel, is the slow one), fp32
+// accumulators in registers (mma.sync.m16n8k16; a tcgen05 kernel needs both operands MN-major and is the next step).
+// Block = 8 warps on a 64 x 64 tile: warp (wm, wn) owns rows 16*wm.. and columns 32*wn..; 32 pixels per stage.
+// Rows are padded to 72 elements (144 bytes) so that the eight 16-byte rows of an ldmatrix tile fall into
+// different bank groups.
+constexpr int WM_PT = 32, WM_LD = 72;
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ld8_bf16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ uint4 ld8_bf16(const float* p) {  // fp32 source (the stem's clip): rounded while staging
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x, a.y), q1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x, b.y), q3 = __floats2bfloat162_rn(b.z, b.w);
+  return make_uint4(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1),
+                    *reinterpret_cast<uint32_t*>(&q2), *reinterpret_cast<uint32_t*>(&q3));
+}
+
+// VEC: cin % 8 == 0 and every channel offset % 8 == 0 - eight consecutive columns are eight consecutive channels of
+// one tap, fetched as one 16-byte vector; otherwise element by element (the stem: cin 3).
+template <typename TX, bool VEC>
+__global__ void __launch_bounds__(256)
+wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                 float* __restrict__ dw, int col_tiles, long long pix_per_block) {
+  __shared__ __align__(16) __nv_bfloat16 sdz[WM_PT][WM_LD];
+  __shared__ __align__(16) __nv_bfloat16 sx[WM_PT][WM_LD];
+  __shared__ int col_off[64];
+  __shared__ int col_zyx[64];
+  __shared__ long long pix_base[WM_PT];
+  __shared__ int pix_zyx[WM_PT][3];
+  __shared__ long long zoff[WM_PT];
+  const int taps = d.kd * d.kh * d.kw, ncols = taps * d.cin;
+  const int cot = blockIdx.x / col_tiles, colt = blockIdx.x - cot * col_tiles;
+  const int co0 = cot * 64, j0 = colt * 64;
+  const long long P = (long long)d.n * d.od * d.oh * d.ow;
+  const long long p_lo = (long long)blockIdx.y * pix_per_block;
+  const long long p_hi = p_lo + pix_per_block < P ? p_lo + pix_per_block : P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 1, wn = warp & 1;
+  if (threadIdx.x < 64) {
+    const int j = j0 + threadIdx.x;
+    if (j < ncols) {
+      const int tap = j / d.cin, ci = j - tap * d.cin;
+      const int kw_i = tap % d.kw, kh_i = (tap / d.kw) % d.kh, kd_i = tap / (d.kw * d.kh);
+      col_off[threadIdx.x] = ((kd_i * d.ih + kh_i) * d.iw + kw_i) * d.in_ld + ci;
+      col_zyx[threadIdx.x] = kd_i | (kh_i << 8) | (kw_i << 16);
+    } else {
+      col_off[threadIdx.x] = 0;
+      col_zyx[threadIdx.x] = -1;
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // ldmatrix row addresses of this lane.  A (dz^T): matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7),
+  // (k 8-15, m 8-15) -> a0..a3.  B: two n8 tiles per x4: (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15).
+  const int lr = lane & 7, lm = lane >> 3;
+  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(&sdz[(lm >> 1) * 8 + lr][wm * 16 + (lm & 1) * 8]);
+  const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(&sx[(lm & 1) * 8 + lr][wn * 32 + (lm >> 1) * 8]);
+  for (long long p0 = p_lo; p0 < p_hi; p0 += WM_PT) {
+    __syncthreads();  // the previous stage has been consumed (and the column table is complete)
+    if (threadIdx.x < WM_PT) {
+      const long long p = p0 + threadIdx.x;
+      if (p < p_hi) {
+        zoff[threadIdx.x] = p * d.out_ld + d.out_coff;
+        const int ow = (int)(p % d.ow);
+        long long t = p / d.ow;
+        const int oh = (int)(t % d.oh);
+        t /= d.oh;
+        const int od = (int)(t % d.od);
+        const int n = (int)(t / d.od);
+        const int iz = od * d.sd - d.pd, iy = oh * d.sh - d.ph, ix = ow * d.sw - d.pw;
+        pix_zyx[threadIdx.x][0] = iz;
+        pix_zyx[threadIdx.x][1] = iy;
+        pix_zyx[threadIdx.x][2] = ix;
+        pix_base[threadIdx.x] = ((((long long)n * d.id + iz) * d.ih + iy) * d.iw + ix) * d.in_ld + d.in_coff;
+      } else {
+        zoff[threadIdx.x] = -1;
+        pix_zyx[threadIdx.x][0] = INT_MIN / 2;
+        pix_zyx[threadIdx.x][1] = pix_zyx[threadIdx.x][2] = 0;
+        pix_base[threadIdx.x] = 0;
+      }
+    }
+    __syncthreads();
+    {  // one 8-element group of each operand tile per thread: 32 pixels x 8 groups
+      const int pp = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
+      uint4 vz = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
+      const long long zo = zoff[pp];
+      if (VEC) {
+        if (zo >= 0 && co0 + c8 < d.cout) vz = ld8_bf16(dz + zo + co0 + c8);  // cout % 8 == 0: whole groups
+        const int k = col_zyx[c8];
+        if (k >= 0) {
+          const int iz = pix_zyx[pp][0] + (k & 255), iy = pix_zyx[pp][1] + ((k >> 8) & 255), ix = pix_zyx[pp][2] + (k >> 16);
+          if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+            vx = ld8_bf16(x + pix_base[pp] + col_off[c8]);
+        }
+      } else {
+        __nv_bfloat16 ez[8], ex[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          ez[e] = (zo >= 0 && co0 + c8 + e < d.cout) ? dz[zo + co0 + c8 + e] : __float2bfloat16_rn(0.f);
+          float v = 0.f;
+          const int k = col_zyx[c8 + e];
+          if (k >= 0) {
+            const int iz = pix_zyx[pp][0] + (k & 255), iy = pix_zyx[pp][1] + ((k >> 8) & 255), ix = pix_zyx[pp][2] + (k >> 16);
+            if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+              v = ldf(x, pix_base[pp] + col_off[c8 + e]);
+          }
+          ex[e] = __float2bfloat16_rn(v);
+        }
+        vz = *reinterpret_cast<uint4*>(ez);
+        vx = *reinterpret_cast<uint4*>(ex);
+      }
+      *reinterpret_cast<uint4*>(&sdz[pp][c8]) = vz;
+      *reinterpret_cast<uint4*>(&sx[pp][c8]) = vx;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < WM_PT / 16; ++ks) {
+      uint32_t a[4], b01[4], b23[4];
+      const uint32_t koff = (uint32_t)(ks * 16 * WM_LD * 2);
+      ldsm_x4_t(a_addr + koff, a);
+      ldsm_x4_t(b_addr + koff, b01);        // n tiles 0, 1 of this warp's 32 columns
+      ldsm_x4_t(b_addr + koff + 32u, b23);  // n tiles 2, 3 (16 columns = 32 bytes further)
+      mma_bf16_16816(acc[0], a, b01[0], b01[1]);
+      mma_bf16_16816(acc[1], a, b01[2], b01[3]);
+      mma_bf16_16816(acc[2], a, b23[0], b23[1]);
+      mma_bf16_16816(acc[3], a, b23[2], b23[3]);
+    }
+  }
+  // accumulator fragment: c0, c1 = (row g, columns 2t, 2t+1), c2, c3 = (row g + 8, same columns)
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int co = co0 + wm * 16 + g + (e >> 1) * 8;
+      const int col = j0 + wn * 32 + nt * 8 + t2 + (e & 1);
+      const float v = acc[nt][e];
+      if (co >= d.cout || col >= ncols || v == 0.f) continue;
+      const int tap = col / d.cin, ci = col - tap * d.cin;
+      atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, v);
+    }
+}
+
 template <typename TX, typename T>
 int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, cudaStream_t st) {
   const int taps = d->kd * d->kh * d->kw;
@@ -277,6 +438,19 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   ppb = (ppb + WG_PT - 1) / WG_PT * WG_PT;
   splits = (P + ppb - 1) / ppb;
   const dim3 grid((unsigned)bx, (unsigned)splits);
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    static const bool use_mma = !(getenv("IVF_WGRAD_MMA") && atoi(getenv("IVF_WGRAD_MMA")) == 0);
+    if (use_mma) {
+      const bool vec = d->cin % 8 == 0 && d->in_ld % 8 == 0 && d->in_coff % 8 == 0 && d->cout % 8 == 0 &&
+                       d->out_ld % 8 == 0 && d->out_coff % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dz % 16) == 0;
+      ppb = (ppb + WM_PT - 1) / WM_PT * WM_PT;
+      const dim3 grid2((unsigned)bx, (unsigned)((P + ppb - 1) / ppb));
+      if (vec) wgrad_mma_kernel<TX, true><<<grid2, 256, 0, st>>>(*d, (const TX*)x, (const __nv_bfloat16*)dz, dw, col_tiles, ppb);
+      else wgrad_mma_kernel<TX, false><<<grid2, 256, 0, st>>>(*d, (const TX*)x, (const __nv_bfloat16*)dz, dw, col_tiles, ppb);
+      IVF_LAUNCHED(h);
+      return IVF_OK;
+    }
+  }
   wgrad_kernel<TX, T><<<grid, 256, 0, st>>>(*d, (const TX*)x, (const T*)dz, dw, col_tiles, ppb);
   IVF_LAUNCHED(h);
   return IVF_OK;
