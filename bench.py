@@ -397,7 +397,7 @@ def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
     target = (torch.arange(clips_n) * 7 % NCLS).to(dev)
     def timed(mode):
         tr = I3DTrainer(sd, clips_n, (T, H, W), device=dev, optimizer="sgd", lr=1e-3, momentum=0.9, weight_decay=1e-5,
-                        dropout_p=0.5, mode=mode)
+                        dropout_p=0.5, mode=mode, world=world)
         n0 = _launches(dev)
         tr.step(x, target)  # warm-up (lazy kernel loading) and the launch count of one step
         n_launch = _launches(dev) - n0
@@ -415,6 +415,12 @@ def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
             t = torch.tensor([s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             s = float(t[0])
+            # data parallel: every rank trained on its own clips and holds the same parameters afterwards
+            chk = torch.stack([p.double().abs().sum() for p in tr.params.values()]).sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert float(hi - lo) <= 1e-9 * float(hi), "ranks hold different parameters after data-parallel steps"
         return s, n_launch, float(last)
 
     sec32, _, loss32 = timed("fp32")
@@ -433,8 +439,12 @@ def train_throughput(dev, rank, world, clips_n=8, steps=3, with_cpu=False):
            "note": "mixed precision: forward convolutions and data gradients are the tcgen05 implicit GEMMs of the "
                    "interpretation path, the weight gradient is still a CUDA-core fp32-accumulate kernel and is most "
                    "of the step (tools/train_events.py); fp32_mode runs every convolution on CUDA cores",
-           "workload": "f4: I3D smth (174 classes) training step, %d synthetic 16x224x224 clips, SGD(momentum 0.9, "
-                       "weight decay 1e-5), dropout 0.5, BatchNorm with batch statistics" % clips_n}
+           "data_parallel": ("%d ranks, one NCCL all-reduce of the flat gradient buffer (%.1f MB) per step, parameters "
+                             "verified identical across ranks" % (world, 4e-6 * sum(v.numel() for v in sd.values()
+                                                                                    if v.dtype == torch.float32))
+                             if world > 1 else None),
+           "workload": "f4: I3D smth (174 classes) training step, %d synthetic 16x224x224 clips per GPU, SGD(momentum "
+                       "0.9, weight decay 1e-5), dropout 0.5, BatchNorm with batch statistics" % clips_n}
     if with_cpu and rank == 0:
         from oracle import train_oracle
         xc, tc = x[:2].cpu(), target[:2].cpu()

@@ -416,6 +416,13 @@ int ivf_dropout_mask(ivf_handle* h, float* out, long long n, float p, unsigned l
 int ivf_optim_step(ivf_handle* h, int kind, float* p, const float* g, float* s1, float* s2, long long n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* The same update for many tensors in ONE launch.  table (device): rows of five 64-bit words {p, g, s1, s2, n} -
+ * device pointers of a parameter chunk, its gradient and its two state buffers (unused ones may be 0) and the
+ * chunk's element count; one thread block per row, so long tensors are cut into chunks of a few thousand elements
+ * by the caller.  grad_scale multiplies the gradient before weight decay (1 / world size after an all-reduce). */
+int ivf_optim_step_multi(ivf_handle* h, int kind, const void* table, int rows, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* ---- bring-up probes (tests only) ---------------------------------------------------
  * Loads one 128-pixel x kchunk im2col TMA tile exactly as the conv kernel does and
  * copies the shared-memory image (de-swizzled, [128][kchunk] bf16) to `tile_out`.      */

@@ -103,6 +103,7 @@ SIGNATURES = {
     "ivf_head_train_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ivf_dropout_mask": (_I, [_P, _P, C.c_longlong, _F, C.c_ulonglong, _P]),
     "ivf_optim_step": (_I, [_P, _I, _P, _P, _P, _P, C.c_longlong, _F, _F, _F, _F, _F, _I, _P]),
+    "ivf_optim_step_multi": (_I, [_P, _I, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P]),
     "ivf_viz_triptych": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ivf_probe_im2col": (_I, [_P, C.POINTER(ConvDesc), _P, _I, _I, _I, _P, _P]),
 }

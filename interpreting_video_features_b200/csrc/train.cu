@@ -567,6 +567,38 @@ __global__ void optim_kernel(int kind, float* __restrict__ p, const float* __res
   }
 }
 
+// the same update for MANY tensors in one launch: table rows {p, g, s1, s2, n} (five 64-bit words), one block per
+// row, rows of at most a few thousand elements (the host cuts long tensors into chunks); grad_scale multiplies the
+// gradient first (1 / world size after the all-reduce of a data-parallel step)
+__global__ void __launch_bounds__(256)
+optim_multi_kernel(const long long* __restrict__ table, int kind, float lr, float b1, float b2, float eps, float wd,
+                   int step, float grad_scale) {
+  const long long* row = table + 5ll * blockIdx.x;
+  float* __restrict__ p = reinterpret_cast<float*>(row[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(row[1]);
+  float* __restrict__ s1 = reinterpret_cast<float*>(row[2]);
+  float* __restrict__ s2 = reinterpret_cast<float*>(row[3]);
+  const int n = (int)row[4];
+  const float c1 = 1.f - powf(b1, (float)step), c2 = 1.f - powf(b2, (float)step);
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float gi = g[i] * grad_scale + wd * p[i];
+    if (kind == 0) {
+      if (b1 != 0.f) {
+        const float buf = step == 1 ? gi : b1 * s1[i] + gi;
+        s1[i] = buf;
+        gi = buf;
+      }
+      p[i] -= lr * gi;
+    } else {
+      const float m = b1 * s1[i] + (1.f - b1) * gi;
+      const float v = b2 * s2[i] + (1.f - b2) * gi * gi;
+      s1[i] = m;
+      s2[i] = v;
+      p[i] -= lr / c1 * m / (sqrtf(v) / sqrtf(c2) + eps);
+    }
+  }
+}
+
 // dropout mask, already scaled: 0 with probability p, else 1/(1-p); one counter-based hash per element
 // (the reference draws from torch's generator, pt/models/I3D_doubled.py:319 - no stream can match it bit for bit)
 __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
@@ -718,6 +750,18 @@ extern "C" int ivf_optim_step(ivf_handle* h, int kind, float* p, const float* g,
   IVF_REQUIRE(kind == 0 ? (beta1 == 0.f || s1) : (s1 && s2), "ivf_optim_step: optimizer state buffers missing");
   optim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, p, g, s1, s2, n, lr, beta1, beta2,
                                                                              eps, weight_decay, step);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+extern "C" int ivf_optim_step_multi(ivf_handle* h, int kind, const void* table, int rows, float lr, float beta1,
+                                    float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                    void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && table && rows > 0 && step >= 1, "ivf_optim_step_multi: null argument, empty table or step < 1");
+  IVF_REQUIRE(kind == 0 || kind == 1, "ivf_optim_step_multi: kind must be 0 (SGD) or 1 (Adam)");
+  optim_multi_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const long long*)table, kind, lr, beta1, beta2, eps,
+                                                             weight_decay, step, grad_scale);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }

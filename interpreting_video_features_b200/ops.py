@@ -486,3 +486,25 @@ def dropout_mask(out, p, seed):
     check(_lib.load().ivf_dropout_mask(_lib.handle(out.device), ptr(out), out.numel(), p, seed,
                                        _lib.stream_ptr(out.device)), "ivf_dropout_mask")
     return out
+
+
+OPTIM_CHUNK = 4096
+
+
+def optim_table(params, grads, state1, state2, device):
+    """Device table for optim_step_multi: one row {p, g, s1, s2, n} per chunk of at most OPTIM_CHUNK elements of
+    every tensor (lists of equally shaped fp32 tensors; state lists may hold None)."""
+    rows = []
+    for p, g, a, b in zip(params, grads, state1, state2):
+        assert p.dtype == torch.float32 and g.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+        for off in range(0, p.numel(), OPTIM_CHUNK):
+            n = min(OPTIM_CHUNK, p.numel() - off)
+            rows.append([p.data_ptr() + 4 * off, g.data_ptr() + 4 * off, (a.data_ptr() + 4 * off) if a is not None else 0,
+                         (b.data_ptr() + 4 * off) if b is not None else 0, n])
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def optim_step_multi(kind, table, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_lib.load().ivf_optim_step_multi(_lib.handle(table.device), {"sgd": 0, "adam": 1}[kind], ptr(table),
+                                           table.shape[0], lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                                           _lib.stream_ptr(table.device)), "ivf_optim_step_multi")

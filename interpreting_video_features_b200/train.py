@@ -78,11 +78,14 @@ class _TrainUnit:
 class I3DTrainer:
     def __init__(self, state_dict, batch, clip, avg_pool=(2, 7, 7), device=None, optimizer="sgd", lr=0.01,
                  momentum=0.9, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, dropout_p=0.0, seed=0, in_channels=3,
-                 share_storage=False, mode="fp32"):
+                 share_storage=False, mode="fp32", world=1):
         """state_dict: the reference-keyed parameters and BatchNorm buffers (pt/models/I3D_doubled.py).  dropout_p is
         what the reference hands to nn.Dropout (its `dropout_keep_prob` argument, pt/models/I3D_doubled.py:319).
         share_storage: fp32 contiguous tensors of state_dict that already live on the device are updated in place
-        instead of copied (from_model)."""
+        instead of copied (from_model).  world > 1: data parallel over the ranks of torch.distributed's default group
+        (one process per GPU, each with its own clips): the parameter gradients - one flat fp32 buffer - are summed with
+        ONE all-reduce per step and averaged inside the update kernel; BatchNorm statistics stay per rank, as under
+        the reference's nn.DataParallel replicas (pt/train_i3d_smth.py:58)."""
         if optimizer not in ("sgd", "adam"):
             raise _lib.IvfError("optimizer must be 'sgd' or 'adam' (pt/train_i3d_smth.py:131-138)")
         if mode not in ("fp32", "bf16"):
@@ -105,10 +108,21 @@ class I3DTrainer:
         self._shared = [v for k, v in sd.items() if (_is_param(k) or ".bn.running_" in k) and own(v).data_ptr() == v.data_ptr()]
         self.params = {k: own(v) for k, v in sd.items() if _is_param(k)}
         self.buffers = {k: own(v) for k, v in sd.items() if ".bn.running_" in k}
-        self.grads = {k: torch.empty_like(v) for k, v in self.params.items()}
+        # all parameter gradients are views of ONE flat buffer (16-byte aligned pieces): one all-reduce for data
+        # parallelism, one table-driven launch for the update
+        offs, total = {}, 0
+        for k, v in self.params.items():
+            offs[k] = total
+            total += (v.numel() + 3) // 4 * 4
+        self.flat_grads = ops.zeros((total,), torch.float32, dev)
+        self.grads = {k: self.flat_grads[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in self.params.items()}
         self.state1 = {k: ops.zeros(v.shape, torch.float32, dev) for k, v in self.params.items()}
         self.state2 = {k: ops.zeros(v.shape, torch.float32, dev) for k, v in self.params.items()} \
             if optimizer == "adam" else {}
+        keys = list(self.params)
+        self.world = int(world)
+        self._table = ops.optim_table([self.params[k] for k in keys], [self.grads[k] for k in keys],
+                                      [self.state1[k] for k in keys], [self.state2.get(k) for k in keys], dev)
 
         B = batch
         self.x = ops.zeros((B, in_channels, self.T, self.H, self.W), torch.float32, dev)
@@ -285,9 +299,11 @@ class I3DTrainer:
         kind = self.opt
         b1 = self.momentum if kind == "sgd" else self.betas[0]
         b2 = 0.0 if kind == "sgd" else self.betas[1]
-        for k, p in self.params.items():
-            ops.optim_step(kind, p, self.grads[k], self.state1[k], self.state2.get(k), self.lr, b1, b2, self.eps, self.wd,
-                           self.step_count)
+        if self.world > 1:  # the one exchange of a data-parallel step: NCCL sum of every rank's gradients
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grads)
+        ops.optim_step_multi(kind, self._table, self.lr, b1, b2, self.eps, self.wd, self.step_count,
+                             grad_scale=1.0 / self.world)
         for u in self.units:
             u.repack()
         for t in self._shared:

@@ -326,8 +326,11 @@ def _conv_same(x, w, stride):
     return F.conv3d(_same_pad(x, w.shape[2:], stride), w, stride=stride)
 
 
+# the second geometry has the odd maps of the KTH configuration (60x80 -> 30x40 -> 15x20 -> 8x10 -> 4x5 -> 2x3):
+# asymmetric 'same' pads at every strided pool (pt/models/I3D_doubled.py:9-38)
+@pytest.mark.parametrize("geom", [SMALL, dict(clip=(16, 60, 80), avg_pool=(2, 2, 3))], ids=["96x96", "60x80"])
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
-def test_train_step_link_by_link(dev, mode):
+def test_train_step_link_by_link(dev, mode, geom):
     """Every launch of one training step against torch evaluated on the step's OWN stored operands (teacher
     forcing).  With bf16 rounding points the step is chaotic end to end - the oracle's matched-rounding restatement
     evaluated in fp32 and in fp64 gives gradients that differ by 0.76 (median, relative) on this geometry, a flipped
@@ -340,9 +343,9 @@ def test_train_step_link_by_link(dev, mode):
     bf = mode == "bf16"
     tol_store = 6e-3 if bf else 2e-5   # a stored tensor against its fp32 recomputation
     sd, _ = quiet(i3d_state_dict, 174)
-    x = synthetic.clips(2, t=SMALL['clip'][0], h=SMALL['clip'][1], w=SMALL['clip'][2])
+    x = synthetic.clips(2, t=geom['clip'][0], h=geom['clip'][1], w=geom['clip'][2])
     target = torch.tensor([5, 77])
-    tr = I3DTrainer(sd, 2, SMALL["clip"], avg_pool=SMALL["avg_pool"], device=dev, optimizer="sgd", mode=mode)
+    tr = I3DTrainer(sd, 2, geom["clip"], avg_pool=geom["avg_pool"], device=dev, optimizer="sgd", mode=mode)
     zs = {}
     tr.forward_backward(x, target, after_forward=lambda: zs.update({u.prefix: _ncdhw(u.z) for u in tr.units}))
     torch.cuda.synchronize()
@@ -414,3 +417,25 @@ def test_mixed_precision_training_tracks_fp32(dev):
     assert hist["fp32"][-1] < hist["fp32"][0] - 0.15 and hist["bf16"][-1] < hist["bf16"][0] - 0.15, hist
     assert abs(hist["bf16"][0] - hist["fp32"][0]) < 0.05 * hist["fp32"][0], hist
     assert abs(hist["bf16"][-1] - hist["fp32"][-1]) < 0.05 * hist["fp32"][-1], hist
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam"])
+def test_optimizer_one_launch_equals_per_tensor(dev, kind):
+    """ivf_optim_step_multi (every parameter chunk in one launch, gradient scaled by 1 / world first) gives what
+    ivf_optim_step gives tensor by tensor."""
+    from interpreting_video_features_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    sizes = [10, 5000, 4096, 12289]
+    ps = [torch.randn(n, generator=g).to(dev) for n in sizes]
+    gs = [torch.randn(n, generator=g).to(dev) for n in sizes]
+    a1, a2 = [torch.zeros(n, device=dev) for n in sizes], [torch.zeros(n, device=dev) for n in sizes]
+    qs, b1, b2 = [p.clone() for p in ps], [t.clone() for t in a1], [t.clone() for t in a2]
+    table = ops.optim_table(ps, gs, a1, a2 if kind == "adam" else [None] * 4, dev)
+    assert table.shape == (1 + 2 + 1 + 4, 5)
+    for step in (1, 2, 3):
+        ops.optim_step_multi(kind, table, 0.01, 0.9, 0.999, 1e-8, 1e-4, step, grad_scale=0.5)
+        for q, gr, s1, s2 in zip(qs, gs, b1, b2):
+            ops.optim_step(kind, q, gr * 0.5, s1, s2 if kind == "adam" else None, 0.01, 0.9, 0.999 if kind == "adam" else 0.0,
+                           1e-8, 1e-4, step)
+        for p, q in zip(ps, qs):
+            assert rel_err(p.cpu(), q.cpu()) < 1e-6
