@@ -430,7 +430,9 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   const long long bx = (long long)co_tiles * col_tiles;
   IVF_REQUIRE(bx < (1ll << 31), "ivf_conv3d_wgrad: too many tiles");
   long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;  // ~8 blocks per SM in total
-  const long long max_splits = (P + 255) / 256;                   // at least 256 pixels per block
+  // at least 256 pixels per block on the CUDA-core kernel; one 32-pixel stage on the tensor-core kernel (the 7x7 and
+  // 14x14 layers have 784 / 6 272 pixels: with few tiles they were 16 us of serial stages on a quarter of the SMs)
+  const long long max_splits = std::is_same<T, __nv_bfloat16>::value ? (P + WM_PT - 1) / WM_PT : (P + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
