@@ -396,6 +396,12 @@ int ivf_bn_train_bwd(ivf_handle* h, int dtype, int dy_dtype, const void* dy, int
  * reads a space-to-depth copy while the weight gradient reads the clip itself).                              */
 int ivf_conv3d_wgrad(ivf_handle* h, const ivf_conv_desc* d, int x_dtype, const void* x, const void* dz, float* dw,
                      void* stream);
+/* The same for a stride-2 layer whose tensor-core form is a stride-1 convolution over the 2x2x2 space-to-depth
+ * record of its input (the stem, pt/models/I3D_doubled.py:233-235; the operand ivf_perturb_fwd writes as
+ * IVF_PFMT_S2D_BF16 and ivf_pack_weights packs for with s2d = 2): d describes THAT convolution (bf16, cin = 8 * ci,
+ * kernel = ceil(k / 2), stride 1), dw is written in the original [cout][ci][kd][kh][kw] layout.               */
+int ivf_conv3d_wgrad_s2d(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw, int ci,
+                         int kd, int kh, int kw, void* stream);
 /* Classifier head in training mode (pt/models/I3D_doubled.py:360-371 + nn.CrossEntropyLoss,
  * pt/train_i3d_smth.py:124-127): pooled = mean over the pix positions of a clip's feature map (the average
  * pool's window must cover the map) * drop (fp32 [batch][c] dropout mask already scaled by 1/keep, NULL: none);

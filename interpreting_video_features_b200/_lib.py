@@ -99,6 +99,7 @@ SIGNATURES = {
     "ivf_bn_train_bwd": (_I, [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, C.c_longlong, _I, _P, _P, _P, _P, _P, _I,
                                 _I, _P, _P, _P]),
     "ivf_conv3d_wgrad": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P]),
+    "ivf_conv3d_wgrad_s2d": (_I, [_P, C.POINTER(ConvDesc), _P, _P, _P, _I, _I, _I, _I, _P]),
     "ivf_head_train_fwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "ivf_head_train_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ivf_dropout_mask": (_I, [_P, _P, C.c_longlong, _F, C.c_ulonglong, _P]),

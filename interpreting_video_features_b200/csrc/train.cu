@@ -291,17 +291,18 @@ __device__ __forceinline__ uint4 ld8_bf16(const float* p) {  // fp32 source (the
 
 // VEC: cin % 8 == 0 and every channel offset % 8 == 0 - eight consecutive columns are eight consecutive channels of
 // one tap, fetched as one 16-byte vector; otherwise element by element (the stem: cin 3).
-template <typename TX, bool VEC>
+// S2D: d describes the stride-1 convolution over the 2x2x2 space-to-depth record of a stride-2 layer (the stem's
+// tensor-core form: operand channel = ((a*2 + b)*2 + c)*ci + ch, operand tap t per axis, source tap = 2*t + parity,
+// as ivf_pack_weights lays the weights out); the result is written in the ORIGINAL [cout][ci][kd][kh][kw] layout,
+// taps past the kernel (the eighth of a 7-tap axis) dropped.  og = {ci, kd, kh, kw} of the original layer.
+template <typename TX, bool VEC, bool S2D = false>
 __global__ void __launch_bounds__(256)
 wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
-                 float* __restrict__ dw, int col_tiles, long long pix_per_block) {
+                 float* __restrict__ dw, int col_tiles, long long pix_per_block, int4 og = make_int4(0, 0, 0, 0)) {
   __shared__ __align__(16) __nv_bfloat16 sdz[WM_PT][WM_LD];
   __shared__ __align__(16) __nv_bfloat16 sx[WM_PT][WM_LD];
   __shared__ int col_off[64];
   __shared__ int col_zyx[64];
-  __shared__ long long pix_base[WM_PT];
-  __shared__ int pix_zyx[WM_PT][3];
-  __shared__ long long zoff[WM_PT];
   const int taps = d.kd * d.kh * d.kw, ncols = taps * d.cin;
   const int cot = blockIdx.x / col_tiles, colt = blockIdx.x - cot * col_tiles;
   const int co0 = cot * 64, j0 = colt * 64;
@@ -332,64 +333,70 @@ wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16*
   const int lr = lane & 7, lm = lane >> 3;
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(&sdz[(lm >> 1) * 8 + lr][wm * 16 + (lm & 1) * 8]);
   const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(&sx[(lm & 1) * 8 + lr][wn * 32 + (lm >> 1) * 8]);
-  for (long long p0 = p_lo; p0 < p_hi; p0 += WM_PT) {
-    __syncthreads();  // the previous stage has been consumed (and the column table is complete)
-    if (threadIdx.x < WM_PT) {
-      const long long p = p0 + threadIdx.x;
-      if (p < p_hi) {
-        zoff[threadIdx.x] = p * d.out_ld + d.out_coff;
-        const int ow = (int)(p % d.ow);
-        long long t = p / d.ow;
-        const int oh = (int)(t % d.oh);
-        t /= d.oh;
-        const int od = (int)(t % d.od);
-        const int n = (int)(t / d.od);
-        const int iz = od * d.sd - d.pd, iy = oh * d.sh - d.ph, ix = ow * d.sw - d.pw;
-        pix_zyx[threadIdx.x][0] = iz;
-        pix_zyx[threadIdx.x][1] = iy;
-        pix_zyx[threadIdx.x][2] = ix;
-        pix_base[threadIdx.x] = ((((long long)n * d.id + iz) * d.ih + iy) * d.iw + ix) * d.in_ld + d.in_coff;
-      } else {
-        zoff[threadIdx.x] = -1;
-        pix_zyx[threadIdx.x][0] = INT_MIN / 2;
-        pix_zyx[threadIdx.x][1] = pix_zyx[threadIdx.x][2] = 0;
-        pix_base[threadIdx.x] = 0;
-      }
-    }
-    __syncthreads();
-    {  // one 8-element group of each operand tile per thread: 32 pixels x 8 groups
-      const int pp = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
-      uint4 vz = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
-      const long long zo = zoff[pp];
-      if (VEC) {
-        if (zo >= 0 && co0 + c8 < d.cout) vz = ld8_bf16(dz + zo + co0 + c8);  // cout % 8 == 0: whole groups
-        const int k = col_zyx[c8];
-        if (k >= 0) {
-          const int iz = pix_zyx[pp][0] + (k & 255), iy = pix_zyx[pp][1] + ((k >> 8) & 255), ix = pix_zyx[pp][2] + (k >> 16);
-          if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
-            vx = ld8_bf16(x + pix_base[pp] + col_off[c8]);
-        }
-      } else {
-        __nv_bfloat16 ez[8], ex[8];
+  __syncthreads();  // the column table is complete
+  // This thread's piece of a stage: pixel pp, the 8-element group c8 of both operand tiles.  The pixel is decoded by
+  // the thread itself (eight threads share one) so that the loads of stage i + 1 can be issued BEFORE the MMAs of
+  // stage i: one barrier pair per stage, global latency behind the tensor work.
+  const int pp = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
+  int ck[8], co_[8];
+  if (VEC) {
+    ck[0] = col_zyx[c8];
+    co_[0] = col_off[c8];
+  } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          ez[e] = (zo >= 0 && co0 + c8 + e < d.cout) ? dz[zo + co0 + c8 + e] : __float2bfloat16_rn(0.f);
-          float v = 0.f;
-          const int k = col_zyx[c8 + e];
-          if (k >= 0) {
-            const int iz = pix_zyx[pp][0] + (k & 255), iy = pix_zyx[pp][1] + ((k >> 8) & 255), ix = pix_zyx[pp][2] + (k >> 16);
-            if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
-              v = ldf(x, pix_base[pp] + col_off[c8 + e]);
-          }
-          ex[e] = __float2bfloat16_rn(v);
-        }
-        vz = *reinterpret_cast<uint4*>(ez);
-        vx = *reinterpret_cast<uint4*>(ex);
-      }
-      *reinterpret_cast<uint4*>(&sdz[pp][c8]) = vz;
-      *reinterpret_cast<uint4*>(&sx[pp][c8]) = vx;
+    for (int e = 0; e < 8; ++e) {
+      ck[e] = col_zyx[c8 + e];
+      co_[e] = col_off[c8 + e];
     }
+  }
+  auto fetch = [&](long long p0, uint4& vz, uint4& vx) {
+    vz = make_uint4(0u, 0u, 0u, 0u);
+    vx = make_uint4(0u, 0u, 0u, 0u);
+    const long long p = p0 + pp;
+    if (p >= p_hi) return;
+    const long long zo = p * d.out_ld + d.out_coff;
+    const int ow = (int)(p % d.ow);
+    long long t = p / d.ow;
+    const int oh = (int)(t % d.oh);
+    t /= d.oh;
+    const int od = (int)(t % d.od);
+    const int n = (int)(t / d.od);
+    const int z0 = od * d.sd - d.pd, y0 = oh * d.sh - d.ph, x0 = ow * d.sw - d.pw;
+    const long long base = ((((long long)n * d.id + z0) * d.ih + y0) * d.iw + x0) * d.in_ld + d.in_coff;
+    if (VEC) {
+      if (co0 + c8 < d.cout) vz = ld8_bf16(dz + zo + co0 + c8);  // cout % 8 == 0: whole groups
+      const int k = ck[0];
+      if (k >= 0) {
+        const int iz = z0 + (k & 255), iy = y0 + ((k >> 8) & 255), ix = x0 + (k >> 16);
+        if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+          vx = ld8_bf16(x + base + co_[0]);
+      }
+    } else {
+      __nv_bfloat16 ez[8], ex[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ez[e] = co0 + c8 + e < d.cout ? dz[zo + co0 + c8 + e] : __float2bfloat16_rn(0.f);
+        float v = 0.f;
+        const int k = ck[e];
+        if (k >= 0) {
+          const int iz = z0 + (k & 255), iy = y0 + ((k >> 8) & 255), ix = x0 + (k >> 16);
+          if ((unsigned)iz < (unsigned)d.id && (unsigned)iy < (unsigned)d.ih && (unsigned)ix < (unsigned)d.iw)
+            v = ldf(x, base + co_[e]);
+        }
+        ex[e] = __float2bfloat16_rn(v);
+      }
+      vz = *reinterpret_cast<uint4*>(ez);
+      vx = *reinterpret_cast<uint4*>(ex);
+    }
+  };
+  uint4 vz, vx;
+  fetch(p_lo, vz, vx);
+  for (long long p0 = p_lo; p0 < p_hi; p0 += WM_PT) {
+    __syncthreads();  // the previous stage has been consumed
+    *reinterpret_cast<uint4*>(&sdz[pp][c8]) = vz;
+    *reinterpret_cast<uint4*>(&sx[pp][c8]) = vx;
     __syncthreads();
+    if (p0 + WM_PT < p_hi) fetch(p0 + WM_PT, vz, vx);  // in flight while this stage multiplies
 #pragma unroll
     for (int ks = 0; ks < WM_PT / 16; ++ks) {
       uint32_t a[4], b01[4], b23[4];
@@ -414,7 +421,15 @@ wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16*
       const float v = acc[nt][e];
       if (co >= d.cout || col >= ncols || v == 0.f) continue;
       const int tap = col / d.cin, ci = col - tap * d.cin;
-      atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, v);
+      if (S2D) {
+        const int ch = ci % og.x, par = ci / og.x;
+        const int kt = 2 * (tap / (d.kw * d.kh)) + (par >> 2), kh_ = 2 * ((tap / d.kw) % d.kh) + ((par >> 1) & 1);
+        const int kw_ = 2 * (tap % d.kw) + (par & 1);
+        if (kt >= og.y || kh_ >= og.z || kw_ >= og.w) continue;
+        atomicAdd(dw + ((((long long)co * og.x + ch) * og.y + kt) * og.z + kh_) * og.w + kw_, v);
+      } else {
+        atomicAdd(dw + ((long long)co * d.cin + ci) * taps + tap, v);
+      }
     }
 }
 
@@ -764,6 +779,39 @@ extern "C" int ivf_optim_step_multi(ivf_handle* h, int kind, const void* table, 
   IVF_REQUIRE(kind == 0 || kind == 1, "ivf_optim_step_multi: kind must be 0 (SGD) or 1 (Adam)");
   optim_multi_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const long long*)table, kind, lr, beta1, beta2, eps,
                                                              weight_decay, step, grad_scale);
+  IVF_LAUNCHED(h);
+  return IVF_OK;
+}
+
+extern "C" int ivf_conv3d_wgrad_s2d(ivf_handle* h, const ivf_conv_desc* d, const void* x, const void* dz, float* dw,
+                                    int ci, int kd, int kh, int kw, void* stream) {
+  IVF_ON_DEVICE(h);
+  IVF_REQUIRE(h && d && x && dz && dw, "ivf_conv3d_wgrad_s2d: null argument");
+  IVF_REQUIRE(d->dtype == IVF_BF16 && !d->transposed && d->sd == 1 && d->sh == 1 && d->sw == 1 && ci > 0 &&
+                  d->cin == 8 * ci && d->kd == (kd + 1) / 2 && d->kh == (kh + 1) / 2 && d->kw == (kw + 1) / 2 &&
+                  d->in_ld >= d->in_coff + d->cin && d->out_ld >= d->out_coff + d->cout,
+              "ivf_conv3d_wgrad_s2d: d must describe the stride-1 bf16 convolution over the 2x2x2 space-to-depth record "
+              "(cin = 8 * ci, kernel = ceil(k / 2))");
+  IVF_REQUIRE(d->cin % 8 == 0 && d->in_ld % 8 == 0 && d->in_coff % 8 == 0 && d->cout % 8 == 0 && d->out_ld % 8 == 0 &&
+                  d->out_coff % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dz % 16) == 0,
+              "ivf_conv3d_wgrad_s2d: channel counts / offsets must be multiples of 8 and the buffers 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long P = (long long)d->n * d->od * d->oh * d->ow;
+  IVF_REQUIRE((long long)d->kd * d->ih * d->iw * d->in_ld < (1ll << 31), "ivf_conv3d_wgrad_s2d: window span above 2^31");
+  IVF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->cout * ci * kd * kh * kw, st));
+  const int taps = d->kd * d->kh * d->kw;
+  const int co_tiles = (d->cout + 63) / 64, col_tiles = (taps * d->cin + 63) / 64;
+  const long long bx = (long long)co_tiles * col_tiles;
+  long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;
+  const long long max_splits = (P + WM_PT - 1) / WM_PT;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  long long ppb = (P + splits - 1) / splits;
+  ppb = (ppb + WM_PT - 1) / WM_PT * WM_PT;
+  const dim3 grid((unsigned)bx, (unsigned)((P + ppb - 1) / ppb));
+  wgrad_mma_kernel<__nv_bfloat16, true, true><<<grid, 256, 0, st>>>(
+      *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, col_tiles, ppb, make_int4(ci, kd, kh, kw));
   IVF_LAUNCHED(h);
   return IVF_OK;
 }

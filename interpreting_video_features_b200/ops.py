@@ -453,6 +453,19 @@ def conv3d_wgrad(x, dz, dw, kernel, stride, pad_front):
     return dw
 
 
+def conv3d_wgrad_s2d(x_s2d, dz, dw, kernel_eff, pad_front_eff):
+    """Weight gradient of a stride-2 layer from the 2x2x2 space-to-depth record of its input (Act of 8 * ci channels,
+    bf16): dw in the original [cout, ci, kd, kh, kw] layout (ivf_conv3d_wgrad_s2d)."""
+    co, ci, kd, kh, kw = dw.shape
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and x_s2d.c == 8 * ci and dz.c == co
+    d = conv_desc(x_s2d, dz, kernel_eff, (1, 1, 1), pad_front_eff)
+    d.flags = 0
+    d.dtype = _lib.dtype_code(dz.buf)
+    check(_lib.load().ivf_conv3d_wgrad_s2d(_lib.handle(dz.buf.device), C.byref(d), ptr(x_s2d.buf), ptr(dz.buf), ptr(dw),
+                                           ci, kd, kh, kw, _lib.stream_ptr(dz.buf.device)), "ivf_conv3d_wgrad_s2d")
+    return dw
+
+
 def head_train_fwd(feat, drop, w, bias, target, pooled, logits, dlogits, loss):
     """Training-mode classifier head + cross-entropy (ivf_head_train_fwd); feat: Act whose whole map is pooled."""
     p = feat.d * feat.h * feat.w

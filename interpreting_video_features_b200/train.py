@@ -230,8 +230,12 @@ class I3DTrainer:
                 self.bwd.append(lambda u=u, gy=gy, dz=dz: ops.bn_train_bwd(
                     gy, u.y, u.z, u.gamma, u.save_mean, u.save_rstd, u.ws, dz, self.grads[u.prefix + ".bn.weight"],
                     self.grads[u.prefix + ".bn.bias"]))
-                self.bwd.append(lambda u=u, dz=dz: ops.conv3d_wgrad(u.x, dz, self.grads[u.prefix + ".conv3d.weight"],
-                                                                    u.kernel, u.stride, u.pf))
+                if u.s2d:  # the stem in mixed precision: from the space-to-depth record its forward read
+                    self.bwd.append(lambda u=u, dz=dz: ops.conv3d_wgrad_s2d(
+                        u.conv_x, dz, self.grads[u.prefix + ".conv3d.weight"], u.conv_kernel, u.conv_pf))
+                else:
+                    self.bwd.append(lambda u=u, dz=dz: ops.conv3d_wgrad(
+                        u.x, dz, self.grads[u.prefix + ".conv3d.weight"], u.kernel, u.stride, u.pf))
                 if u.x is not self.xin:  # the clip needs no gradient
                     gx, acc = contribute(u.x)
                     self.bwd.append(lambda u=u, dz=dz, gx=gx, acc=acc: u.dgrad(dz, gx, acc))
@@ -269,8 +273,9 @@ class I3DTrainer:
         assert tuple(x.shape) == (self.B, self.C, self.T, self.H, self.W), (tuple(x.shape),)
         self.x.copy_(x, non_blocking=True)
         self.target.copy_(ops.as_int32_targets(target, self.device), non_blocking=True)
-        ops.perturb_fwd(self.x, self.zero_mask, "freeze", PFMT_NDHWC_F32, self.xin.buf)  # layout change only (mask 0)
-        if self.xin_s2d is not None:
+        if self.xin_s2d is None:  # layout change only (mask 0): channels-last fp32, or the stem's bf16 space-to-depth record
+            ops.perturb_fwd(self.x, self.zero_mask, "freeze", PFMT_NDHWC_F32, self.xin.buf)
+        else:
             ops.perturb_fwd(self.x, self.zero_mask, "freeze", PFMT_S2D_BF16, self.xin_s2d.buf)
         for op in self.fwd:
             op()

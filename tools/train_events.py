@@ -15,7 +15,7 @@ tr = I3DTrainer(sd, n, (16, 224, 224), device=dev, optimizer="sgd", lr=1e-3, dro
 tr.step(x, torch.arange(n) % 174)
 torch.cuda.synchronize()
 events = []
-names = ["conv3d", "bn_train_fwd", "bn_train_bwd", "conv3d_wgrad", "maxpool3d_fwd", "maxpool3d_bwd", "head_train_fwd",
+names = ["conv3d", "bn_train_fwd", "bn_train_bwd", "conv3d_wgrad", "conv3d_wgrad_s2d", "optim_step_multi", "maxpool3d_fwd", "maxpool3d_bwd", "head_train_fwd",
          "head_train_bwd", "optim_step", "perturb_fwd", "dropout_mask"]
 orig = {}
 for nm in names:
