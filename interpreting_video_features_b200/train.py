@@ -98,14 +98,17 @@ class I3DTrainer:
         self.opt, self.lr, self.momentum, self.betas, self.eps, self.wd = optimizer, lr, momentum, betas, eps, weight_decay
         self.dropout_p, self.seed, self.step_count = float(dropout_p), int(seed), 0
 
+        def shared(t):
+            return share_storage and t.is_cuda and t.device == dev and t.dtype == torch.float32 and t.is_contiguous()
+
         def own(t):
-            if share_storage and t.is_cuda and t.device == dev and t.dtype == torch.float32 and t.is_contiguous():
+            if shared(t):
                 return t.detach()
             return t.detach().to(device=dev, dtype=torch.float32).contiguous().clone()
 
         # tensors of the caller that this trainer writes in place: their autograd version counters are bumped after
         # every update so that whoever caches by version (the drop-in model's engines) sees the change
-        self._shared = [v for k, v in sd.items() if (_is_param(k) or ".bn.running_" in k) and own(v).data_ptr() == v.data_ptr()]
+        self._shared = [v for k, v in sd.items() if (_is_param(k) or ".bn.running_" in k) and shared(v)]
         self.params = {k: own(v) for k, v in sd.items() if _is_param(k)}
         self.buffers = {k: own(v) for k, v in sd.items() if ".bn.running_" in k}
         # all parameter gradients are views of ONE flat buffer (16-byte aligned pieces): one all-reduce for data
