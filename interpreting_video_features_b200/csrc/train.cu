@@ -445,9 +445,10 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   const long long bx = (long long)co_tiles * col_tiles;
   IVF_REQUIRE(bx < (1ll << 31), "ivf_conv3d_wgrad: too many tiles");
   long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;  // ~8 blocks per SM in total
-  // at least 256 pixels per block on the CUDA-core kernel; one 32-pixel stage on the tensor-core kernel (the 7x7 and
-  // 14x14 layers have 784 / 6 272 pixels: with few tiles they were 16 us of serial stages on a quarter of the SMs)
-  const long long max_splits = std::is_same<T, __nv_bfloat16>::value ? (P + WM_PT - 1) / WM_PT : (P + 255) / 256;
+  // at least 256 pixels per block on the CUDA-core kernel, four 32-pixel stages on the tensor-core kernel (the 7x7 and
+  // 14x14 layers have 784 / 6 272 pixels; one stage per block made the fp32 atomics of the epilogue the bound: ncu,
+  // 60 % issue slots, 27 us for a 42-tile layer)
+  const long long max_splits = std::is_same<T, __nv_bfloat16>::value ? (P + 4 * WM_PT - 1) / (4 * WM_PT) : (P + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
@@ -489,21 +490,27 @@ __global__ void head_pool_kernel(const T* __restrict__ feat, int ld, int coff, i
   pooled[(long long)b * C + c] = s;
 }
 
-// one block per clip: logits = pooled . W^T + bias, then softmax, loss_b = -log p[target], dlogits
+// logits = pooled . W^T + bias: one warp per (clip, class), eight classes per block (one block per clip took 250 us
+// for 8 x 174 x 1024: a serial loop over the classes)
 __global__ void __launch_bounds__(256)
-head_logits_ce_kernel(const float* __restrict__ pooled, const float* __restrict__ w, const float* __restrict__ bias,
-                      const int* __restrict__ target, int B, int C, int K, float* __restrict__ logits,
-                      float* __restrict__ dlogits, float* __restrict__ loss) {
-  extern __shared__ float sl[];  // K logits
+head_logits_kernel(const float* __restrict__ pooled, const float* __restrict__ w, const float* __restrict__ bias, int C,
+                   int K, float* __restrict__ logits) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(pooled[(long long)b * C + c], w[(long long)k * C + c], s);
+  s = ivf_warp_sum(s);
+  if (lane == 0) logits[(long long)b * K + k] = s + bias[k];
+}
+
+// one block per clip: softmax of its logits, loss_b = -log p[target], dlogits
+__global__ void __launch_bounds__(256)
+head_ce_kernel(const float* __restrict__ logits, const int* __restrict__ target, int B, int K,
+               float* __restrict__ dlogits, float* __restrict__ loss) {
   __shared__ float red[8];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < K; k += 8) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(pooled[(long long)b * C + c], w[(long long)k * C + c], s);
-    s = ivf_warp_sum(s);
-    if (lane == 0) sl[k] = s + bias[k];
-  }
-  __syncthreads();
+  const float* sl = logits + (long long)b * K;
   float mx = -INFINITY;
   for (int k = threadIdx.x; k < K; k += 256) mx = fmaxf(mx, sl[k]);
   mx = ivf_warp_max(mx);
@@ -521,10 +528,8 @@ head_logits_ce_kernel(const float* __restrict__ pooled, const float* __restrict_
   for (int i = 0; i < 8; ++i) se += red[i];
   const int t = target[b];
   const float lse = mx + logf(se);
-  for (int k = threadIdx.x; k < K; k += 256) {
-    logits[(long long)b * K + k] = sl[k];
+  for (int k = threadIdx.x; k < K; k += 256)
     dlogits[(long long)b * K + k] = (expf(sl[k] - lse) - (k == t ? 1.f : 0.f)) / (float)B;
-  }
   if (threadIdx.x == 0) atomicAdd(loss, (lse - sl[t]) / (float)B);
 }
 
@@ -720,7 +725,7 @@ extern "C" int ivf_head_train_fwd(ivf_handle* h, int dtype, const void* feat, in
                                   void* stream) {
   IVF_ON_DEVICE(h);
   IVF_REQUIRE(h && feat && w && bias && target && pooled && logits && dlogits && loss && batch > 0 && pix > 0 &&
-                  c > 0 && classes > 0 && classes <= 8192,
+                  c > 0 && classes > 0,
               "ivf_head_train_fwd: null argument or bad size");
   IVF_REQUIRE(dtype == IVF_F32 || dtype == IVF_BF16, "ivf_head_train_fwd: unknown dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
@@ -731,8 +736,9 @@ extern "C" int ivf_head_train_fwd(ivf_handle* h, int dtype, const void* feat, in
   else
     head_pool_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, ld, coff, pix, c, drop, pooled);
   IVF_LAUNCHED(h);
-  head_logits_ce_kernel<<<batch, 256, sizeof(float) * classes, st>>>(pooled, w, bias, target, batch, c, classes, logits,
-                                                                    dlogits, loss);
+  head_logits_kernel<<<dim3((classes + 7) / 8, batch), 256, 0, st>>>(pooled, w, bias, c, classes, logits);
+  IVF_LAUNCHED(h);
+  head_ce_kernel<<<batch, 256, 0, st>>>(logits, target, batch, classes, dlogits, loss);
   IVF_LAUNCHED(h);
   return IVF_OK;
 }

@@ -188,3 +188,30 @@ def test_sharded_result_rows_world2_gloo(n):
         assert torch.equal(out["reverse_score"], want[:, 5]) and torch.equal(out["probs_orig"], want[:, 6:9])
         assert torch.equal(out["cam_lowres"], want[:, 9:].reshape(n, 2, 1, 2))
         assert stats["gathered_bytes"] == n * 13 * 4
+
+
+def test_optimizer_chunk_table_covers_every_element_once():
+    """ops.optim_table (the row table of ivf_optim_step_multi: one thread block per row): every element of every
+    tensor in exactly one row of at most OPTIM_CHUNK elements, pointers advanced by whole elements, absent state
+    buffers as NULL."""
+    import torch
+    from interpreting_video_features_b200 import ops
+    sizes = [1, 4095, 4096, 4097, 3 * 4096 + 5]
+    ps = [torch.zeros(n) for n in sizes]
+    gs = [torch.zeros(n) for n in sizes]
+    s1 = [torch.zeros(n) for n in sizes]
+    table = ops.optim_table(ps, gs, s1, [None] * len(sizes), "cpu")
+    assert table.dtype == torch.int64 and table.shape[1] == 5
+    rows = table.tolist()
+    assert len(rows) == sum((n + ops.OPTIM_CHUNK - 1) // ops.OPTIM_CHUNK for n in sizes)
+    i = 0
+    for p, g, a in zip(ps, gs, s1):
+        covered = 0
+        while covered < p.numel():
+            pp, gp, ap, bp, n = rows[i]
+            assert 0 < n <= ops.OPTIM_CHUNK and bp == 0
+            assert pp == p.data_ptr() + 4 * covered and gp == g.data_ptr() + 4 * covered and ap == a.data_ptr() + 4 * covered
+            covered += n
+            i += 1
+        assert covered == p.numel()
+    assert i == len(rows)
