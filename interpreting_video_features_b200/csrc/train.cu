@@ -45,23 +45,24 @@ __device__ __forceinline__ void bn_block_reduce2(double a, double b, double* dst
   }
 }
 
-// pass 1: ws[c] += sum z ; pass 2 (mean known): ws[C + c] += sum (z - mean)^2
-template <typename T, int PASS>
+// ONE pass over z: ws[c] += sum (z - z0), ws[C + c] += sum (z - z0)^2 with z0 = the channel's first element as the
+// shift.  In double both sums are exact to ~1e-16 of their size, so the centred variance E[(z-z0)^2] - E[z-z0]^2
+// keeps ~12 digits even where |mean| >> sigma (the two-pass form read z a second time for the same digits).
+template <typename T>
 __global__ void __launch_bounds__(32 * BN_ROWS)
 bn_stats_kernel(const T* __restrict__ z, int ld, int coff, long long m, int C, double* __restrict__ ws) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool cok = c < C;
-  double mean = 0.0;
-  if (PASS == 2 && cok) mean = ws[c] / (double)m;
-  double acc = 0.0;
+  double s1 = 0.0, s2 = 0.0;
   if (cok) {
+    const double z0 = (double)ldf(z, (long long)coff + c);
     for (long long r = (long long)blockIdx.y * BN_ROWS + threadIdx.y; r < m; r += (long long)gridDim.y * BN_ROWS) {
-      const double v = (double)ldf(z, r * ld + coff + c);
-      if (PASS == 1) acc += v;
-      else acc += (v - mean) * (v - mean);
+      const double v = (double)ldf(z, r * ld + coff + c) - z0;
+      s1 += v;
+      s2 += v * v;
     }
   }
-  bn_block_reduce2(acc, 0.0, PASS == 1 ? ws : ws + C, nullptr, c, cok);
+  bn_block_reduce2(s1, s2, ws, ws + C, c, cok);
 }
 
 template <typename T>
@@ -72,15 +73,17 @@ bn_apply_kernel(const T* __restrict__ z, int z_ld, int z_coff, long long m, int 
                 const double* __restrict__ ws, T* __restrict__ y, int y_ld, int y_coff, int relu) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   if (c >= C) return;
-  const float mean = (float)(ws[c] / (double)m);
-  const float var = (float)(ws[C + c] / (double)m);  // biased: what normalises the batch
+  const double d1 = ws[c] / (double)m;
+  const double var_d = fmax(ws[C + c] / (double)m - d1 * d1, 0.0);  // biased: what normalises the batch
+  const float mean = (float)((double)ldf(z, (long long)z_coff + c) + d1);
+  const float var = (float)var_d;
   const float rstd = rsqrtf(var + eps);
   const float g = gamma[c] * rstd, b = beta[c] - mean * g;
   if (blockIdx.y == 0 && threadIdx.y == 0) {
     save_mean[c] = mean;
     save_rstd[c] = rstd;
     if (running_mean) {  // nn.BatchNorm3d: running_var takes the UNBIASED batch variance
-      const float unb = m > 1 ? (float)(ws[C + c] / (double)(m - 1)) : var;
+      const float unb = m > 1 ? (float)(var_d * (double)m / (double)(m - 1)) : var;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
     }
@@ -659,9 +662,7 @@ extern "C" int ivf_bn_train_fwd(ivf_handle* h, int dtype, const void* z, int z_l
   const dim3 grid = bn_grid(h, m, c), block(32, BN_ROWS);
 #define IVF_BN_FWD(T)                                                                                              \
   do {                                                                                                             \
-    bn_stats_kernel<T, 1><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, ws);                            \
-    IVF_LAUNCHED(h);                                                                                               \
-    bn_stats_kernel<T, 2><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, ws);                            \
+    bn_stats_kernel<T><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, ws);                               \
     IVF_LAUNCHED(h);                                                                                               \
     bn_apply_kernel<T><<<grid, block, 0, st>>>((const T*)z, z_ld, z_coff, m, c, gamma, beta, eps, momentum,       \
                                                running_mean, running_var, save_mean, save_rstd, ws, (T*)y, y_ld,  \

@@ -48,7 +48,7 @@ def _dev32(t, device):
 
 
 def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, co_total=None, ceff_total=None,
-         co_stride=1):
+         co_stride=1, out=None):
     """Operand matrix of a convolution kernel from one or more fp32 OIDHW (OIHW: kd = 1) device weights that
     share their input channels and kernel (ivf_pack_weights; nothing is computed by torch).
 
@@ -58,7 +58,9 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
     channels; ceff_total pads the operand channels as a whole (the 12 -> 16 channel ConvLSTM input record).
     co_stride: output channel j of a source lands at co_off + j * co_stride (4 with co_offs 0..3 interleaves the four
     ConvLSTM gates unit-major for the fused recurrent step).
-    bf16: K-major [n_pad][taps][k_pad]; fp32: tap-major [taps][k][n] (flat [taps*k, n] like the old packers)."""
+    bf16: K-major [n_pad][taps][k_pad]; fp32: tap-major [taps][k][n] (flat [taps*k, n] like the old packers).
+    out: an operand matrix a previous call with the same arguments returned - refilled in place (its padding is
+    already zero: no clearing pass, no allocation; the training step re-packs every weight after every update)."""
     lib = _lib.load()
     ws = [w if w.dim() == 5 else w.unsqueeze(2) for w in sources]
     dev = ws[0].device
@@ -81,10 +83,15 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
     bf = mode == "bf16"
     if bf:
         n_pad, k_pad = lib.ivf_conv_bf16_cout_pad(n_total), lib.ivf_conv_bf16_cin_pad(k_total)
-        dst = torch.empty((n_pad, taps, k_pad), dtype=torch.bfloat16, device=dev)
+        shape, dt = (n_pad, taps, k_pad), torch.bfloat16
     else:
         n_pad, k_pad = n_total, k_total
-        dst = torch.empty((taps * k_pad, n_pad), dtype=torch.float32, device=dev)
+        shape, dt = (taps * k_pad, n_pad), torch.float32
+    if out is not None:
+        assert tuple(out.shape) == shape and out.dtype == dt and out.device == dev
+        dst = out
+    else:
+        dst = torch.empty(shape, dtype=dt, device=dev)
     h = _lib.handle(dev)
     for i, (w, off) in enumerate(zip(ws, co_offs)):
         d = _lib.PackDesc()
@@ -97,7 +104,7 @@ def pack(sources, mode, dgrad=False, s2d=(1, 1, 1), ci_stride=0, co_offs=None, c
         d.n_pad, d.k_pad = n_pad, k_pad
         d.n_off, d.k_off = (0, off) if dgrad else (off, 0)
         d.n_stride, d.k_stride = (1, co_stride) if dgrad else (co_stride, 1)
-        d.zero_first = int(i == 0)
+        d.zero_first = int(i == 0 and out is None)
         _lib.check(lib.ivf_pack_weights(h, d, _lib.ptr(w), _lib.ptr(dst), _lib.stream_ptr(dev)), "ivf_pack_weights")
     return dst
 

@@ -62,9 +62,11 @@ class _TrainUnit:
         self.ws = torch.empty(2 * self.cout, dtype=torch.float64, device=dev)
         self.repack()
 
+    w_fwd = w_dgrad = None
+
     def repack(self):
-        self.w_fwd = pack([self.w], self.mode, s2d=self.f)
-        self.w_dgrad = None if self.s2d else pack([self.w], self.mode, dgrad=True)
+        self.w_fwd = pack([self.w], self.mode, s2d=self.f, out=self.w_fwd)
+        self.w_dgrad = None if self.s2d else pack([self.w], self.mode, dgrad=True, out=self.w_dgrad)
 
     def dgrad(self, dz, gx, acc):
         if self.mode == "fp32":
