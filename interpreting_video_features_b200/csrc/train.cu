@@ -270,7 +270,7 @@ wgrad_kernel(ivf_conv_desc d, const TX* __restrict__ x, const T* __restrict__ dz
 // Block = 8 warps on a 64 x 64 tile: warp (wm, wn) owns rows 16*wm.. and columns 32*wn..; 32 pixels per stage.
 // Rows are padded to 72 elements (144 bytes) so that the eight 16-byte rows of an ldmatrix tile fall into
 // different bank groups.
-constexpr int WM_PT = 32, WM_LD = 72;
+constexpr int WM_PT = 64, WM_LD = 72;  // pixels per stage (two 32-pixel halves per thread), padded row length
 
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -352,10 +352,10 @@ wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16*
       co_[e] = col_off[c8 + e];
     }
   }
-  auto fetch = [&](long long p0, uint4& vz, uint4& vx) {
+  auto fetch = [&](long long p0, int half, uint4& vz, uint4& vx) {
     vz = make_uint4(0u, 0u, 0u, 0u);
     vx = make_uint4(0u, 0u, 0u, 0u);
-    const long long p = p0 + pp;
+    const long long p = p0 + pp + 32 * half;
     if (p >= p_hi) return;
     const long long zo = p * d.out_ld + d.out_coff;
     const int ow = (int)(p % d.ow);
@@ -392,14 +392,21 @@ wgrad_mma_kernel(ivf_conv_desc d, const TX* __restrict__ x, const __nv_bfloat16*
       vx = *reinterpret_cast<uint4*>(ex);
     }
   };
-  uint4 vz, vx;
-  fetch(p_lo, vz, vx);
+  uint4 vz[2], vx[2];
+  fetch(p_lo, 0, vz[0], vx[0]);
+  fetch(p_lo, 1, vz[1], vx[1]);
   for (long long p0 = p_lo; p0 < p_hi; p0 += WM_PT) {
     __syncthreads();  // the previous stage has been consumed
-    *reinterpret_cast<uint4*>(&sdz[pp][c8]) = vz;
-    *reinterpret_cast<uint4*>(&sx[pp][c8]) = vx;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      *reinterpret_cast<uint4*>(&sdz[pp + 32 * hf][c8]) = vz[hf];
+      *reinterpret_cast<uint4*>(&sx[pp + 32 * hf][c8]) = vx[hf];
+    }
     __syncthreads();
-    if (p0 + WM_PT < p_hi) fetch(p0 + WM_PT, vz, vx);  // in flight while this stage multiplies
+    if (p0 + WM_PT < p_hi) {  // in flight while this stage multiplies
+      fetch(p0 + WM_PT, 0, vz[0], vx[0]);
+      fetch(p0 + WM_PT, 1, vz[1], vx[1]);
+    }
 #pragma unroll
     for (int ks = 0; ks < WM_PT / 16; ++ks) {
       uint32_t a[4], b01[4], b23[4];
@@ -448,10 +455,10 @@ int wgrad_launch(ivf_handle* h, const ivf_conv_desc* d, const void* x, const voi
   const long long bx = (long long)co_tiles * col_tiles;
   IVF_REQUIRE(bx < (1ll << 31), "ivf_conv3d_wgrad: too many tiles");
   long long splits = ((long long)h->sm_count * 8 + bx - 1) / bx;  // ~8 blocks per SM in total
-  // at least 256 pixels per block on the CUDA-core kernel, four 32-pixel stages on the tensor-core kernel (the 7x7 and
+  // at least 256 pixels per block on the CUDA-core kernel, 128 pixels (two stages) on the tensor-core kernel (the 7x7 and
   // 14x14 layers have 784 / 6 272 pixels; one stage per block made the fp32 atomics of the epilogue the bound: ncu,
   // 60 % issue slots, 27 us for a 42-tile layer)
-  const long long max_splits = std::is_same<T, __nv_bfloat16>::value ? (P + 4 * WM_PT - 1) / (4 * WM_PT) : (P + 255) / 256;
+  const long long max_splits = std::is_same<T, __nv_bfloat16>::value ? (P + 2 * WM_PT - 1) / (2 * WM_PT) : (P + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
