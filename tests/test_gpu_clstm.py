@@ -240,3 +240,28 @@ def test_fused_recurrent_step_equals_unfused(dev, monkeypatch):
     um, gm = res[0][2], res[1][2]                      # [4*he, taps, k]
     he = um.shape[0] // 4
     assert torch.equal(um.view(he, 4, *um.shape[1:]).permute(1, 0, 2, 3).reshape(gm.shape), gm)
+
+
+def test_wavefront_schedule_equals_layer_by_layer(dev, monkeypatch):
+    """IVF_CLSTM_WAVE=1 (layers as a wavefront on one stream each, per-step x-convolution / BN+pool / their
+    gradients, cross-stream events) computes what the layer-by-layer schedule computes: the same launches on the
+    same operands in a different order - logits and mask gradients agree to the accumulation order of the
+    recurrent data gradients."""
+    from oracle import synthetic
+    _, sd = build(32)
+    x = synthetic.clips(2, kind="square", t=32, h=120, w=160)
+    masks = torch.rand((2, 32), generator=torch.Generator().manual_seed(4))
+    res = []
+    for wave in ("1", "0"):
+        monkeypatch.setenv("IVF_CLSTM_WAVE", wave)
+        e = engine(sd, 32, 2, "bf16", dev)
+        assert e.wave == (wave == "1")
+        e.set_input(x.to(dev))
+        e.set_targets(torch.tensor([1, 5]))
+        for _ in range(2):  # twice: the events and lanes are reused
+            logits = e.forward(masks.to(dev), "reverse").clone()
+            dm = e.backward().clone()
+        torch.cuda.synchronize()
+        res.append((logits.cpu(), dm.cpu(), e.layers[0]["c"].clone().cpu(), e.layers[1]["dH"].clone().cpu()))
+    assert rel_err(res[0][0], res[1][0]) < 1e-6 and rel_err(res[0][2], res[1][2]) < 1e-6
+    assert rel_err(res[0][3], res[1][3]) < 1e-5 and rel_err(res[0][1], res[1][1]) < 1e-5
