@@ -54,15 +54,15 @@ class CLSTMEngine:
         # convolution + gate-kernel pair - the gate math (4 expf + 2 tanhf per hidden unit) lengthens the epilogue of
         # a one-to-two-wave convolution by more than the separate bandwidth-bound gate kernel costs - so it is opt-in.
         import os
-        # IVF_CLSTM_WAVE=1 (bf16, opt-in): the layers run as a wavefront on one stream each - layer l's step t starts
+        # IVF_CLSTM_WAVE (bf16, default on): the layers run as a wavefront on one stream each - layer l's step t starts
         # as soon as layer l-1 has produced its step t (forward) / layer l+1 its step t (backward) - instead of one
-        # whole recurrence after the other, so that the upper layers' small, latency-bound launches (15x20 maps) could
-        # hide behind the first layer's.  Built, parity-tested (the whole ConvLSTM suite passes with it) and measured
-        # on a B200: 3.45 ms per step either way at 8 clips (423 launches against 268), 5.27 against 5.39 ms at 16,
-        # 8.98 against 8.71 ms at 32 - a convolution CTA owns its SM (200 KB of shared memory) and the second layer's
-        # 64-CTA launches do not fit beside the first layer's 120, so little overlaps and the per-step x-convolution /
-        # pooling launches cost what it gains.
-        self.wave = bf and layers > 1 and os.environ.get("IVF_CLSTM_WAVE", "0") != "0"
+        # whole recurrence after the other, so that the upper layers' small, latency-bound launches (15x20 maps) hide
+        # behind the first layer's.  A convolution CTA owns its SM (200 KB of shared memory), so this only works when
+        # an upper layer's launch fits on the SMs the first layer leaves (120 CTAs of 148 at 8 clips): the upper
+        # layers get the plan with the fewest CTAs (_small_plan: 24).  Measured on a B200 (C3): 3.45 -> 3.08 ms per
+        # step at 8 clips, 5.39 -> 4.82 ms at 16, 8.71 -> 8.51 ms at 32; without the small plans nothing was gained
+        # (the second layer's 64-CTA launches waited for the first layer's to drain).
+        self.wave = bf and layers > 1 and os.environ.get("IVF_CLSTM_WAVE", "1") != "0"
         self._lanes, self._ev_f, self._ev_b = None, None, None
         self.fused_mode = os.environ.get("IVF_CLSTM_FUSED", "0") if bf else "0"  # "2": small maps only (per layer)
         self.unit_major = self.fused_mode == "1"
@@ -237,7 +237,14 @@ class CLSTMEngine:
 
     # ------------------------------------------------------------------ forward
     # ------------------------------------------------------------------ wavefront schedule (bf16)
+    # upper layers in the wavefront: single CTAs, one accumulator per tile, all of N in one tile - the FEWEST CTAs a
+    # launch can have (24 on the 15x20 map at 8 clips), so that it fits on the SMs the first layer's launch leaves
+    _small_plan = (1, 1, 2, 1, 1, 1)
+
     def _wave_setup(self):
+        if self._lanes is None:
+            for rec in self.layers[1:]:
+                rec["plan_hf"] = rec["plan_hd"] = self._small_plan
         if self._lanes is None:
             L, T = len(self.layers), self.T
             self._lanes = [None] + [torch.cuda.Stream(self.device) for _ in range(L - 1)]
@@ -285,7 +292,7 @@ class CLSTMEngine:
                     if l > 0:
                         st.wait_event(self._ev_f[l - 1][t])
                         ops.conv3d(self._step(rec["x"], t), rec["wx_f"], self._step(rec["gx"], t), rec["xk"], rec["xs"],
-                                   rec["xpf"], scale=rec["ones"], shift=rec["bias"])
+                                   rec["xpf"], scale=rec["ones"], shift=rec["bias"], plan=self._small_plan)
                     self._cell_step(rec, t)
                     self._pool_step_fwd(rec, t)
                     if l < L - 1:
@@ -329,7 +336,7 @@ class CLSTMEngine:
                     if l > 0:  # this step's gradient for the layer below: x-convolution', BN'/pool' of its step t
                         low = self.layers[l - 1]
                         ops.conv3d(self._step(rec["dpre"], t), rec["wx_d"], self._step(rec["g_x"], t), rec["xk"],
-                                   (1, 1, 1), rec["xdpf"])
+                                   (1, 1, 1), rec["xdpf"], plan=self._small_plan)
                         dh_low = low["dH"][t * B:(t + 1) * B]
                         ops.bn_pool2d_bwd(self._step(low["g_pooled"], t).buf, low["argmax"][t * B:(t + 1) * B],
                                           self.bn_scale, dh_low, s2d=low["s2d_out"])
