@@ -245,6 +245,15 @@ class CLSTMEngine:
         if self._lanes is None:
             for rec in self.layers[1:]:
                 rec["plan_hf"] = rec["plan_hd"] = self._small_plan
+            # first layer's recurrent data gradient: where the plan table has no entry the cost model picks CTA pairs
+            # (128 CTAs at 8 clips), which leave the upper layer's launches no room; single CTAs with two
+            # double-buffered accumulators measured 3.07 -> 2.94 ms per step at 8 clips
+            import os
+            env = os.environ.get("IVF_CLSTM_L0_DGRAD_PLAN")  # diagnostics: "kwm,mt,acc,ncta,ntiles,ds" or "auto"
+            if env and env != "auto":
+                self.layers[0]["plan_hd"] = tuple(int(v) for v in env.split(","))
+            elif not env and self.layers[0].get("plan_hd") is None:
+                self.layers[0]["plan_hd"] = (1, 2, 2, 1, 1, 1)
         if self._lanes is None:
             L, T = len(self.layers), self.T
             self._lanes = [None] + [torch.cuda.Stream(self.device) for _ in range(L - 1)]
