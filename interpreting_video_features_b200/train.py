@@ -261,7 +261,8 @@ class I3DTrainer:
         return cls(sd, batch, clip, device=dev, share_storage=True, **kw)
 
     def state_dict(self):
-        """Parameters and running statistics as the reference keys them (num_batches_tracked counts the steps)."""
+        """Parameters and running statistics as the reference keys them (num_batches_tracked counts the steps).  The
+        tensors are the trainer's own (live, updated in place by every step): clone them to keep a snapshot."""
         out = dict(self.params)
         out.update(self.buffers)
         for k in list(self.buffers):
